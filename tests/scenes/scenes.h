@@ -1,0 +1,284 @@
+// Synthetic scene builders shared by BOTH arms of every parity test.
+//
+// This header is written only against the reference's public object-model API
+// (Scene::AddLight/AddPlane/AddSphere/AddCube/AddBallPlane/AddModel/MovePos/ChgMtl,
+// Scene::{EnvLight,Lights,Objects,MtlLiby,cam}; /root/reference/Scene.h:24-45), so the same
+// source compiles against
+//   * the reference's own headers  -> oracle/_ref/ref_render   (oracle/build_ref.sh), and
+//   * raytrace_b200/host/ headers  -> raytrace_b200/bin/rt_render (the B200 product).
+// That both compile from one file is the drop-in check for SURVEY.md section 8 (b) B1.
+//
+// Scene ids follow SURVEY.md section 8 (d): c1..c5 plus small "t_*" cases for tests.
+#pragma once
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+namespace rtscenes
+{
+
+struct SceneArgs
+{
+	std::string name = "c1";
+	int n = 0;            // primary size knob (spheres per side, mesh cells per side); 0 = scene default
+	int parts = 0;        // mesh parts per side; 0 = scene default
+	std::string tmpdir = "/tmp";
+};
+
+inline std::wstring widen(const std::string &s) { return std::wstring(s.begin(), s.end()); }
+
+// main.cpp:165-168 of the reference: the two default lights.
+template<class SceneT> inline void default_lights(SceneT &scene)
+{
+	scene.EnvLight = Vertex(0.05f, 0.05f, 0.05f, 1.0f);
+	auto l = scene.AddLight(MY_LIGHT_PARALLEL, Vertex(0.1f, 0.45f, 0.45f));
+	scene.MovePos(MY_MODEL_LIGHT, l, Vertex(-45, 45, 0));
+	scene.AddLight(MY_LIGHT_POINT, Vertex(0.15f, 0.55f, 0.3f), Vertex(0.0f, 0.0f, 1.0f, 256));
+}
+
+// Height field y = 1.5 + 0.6 sin3x cos2.5z + 0.25 sin(9x+1) sin7z on [-4,4]^2, `cells` x `cells`
+// quads split in two, `pside` x `pside` usemtl parts, analytic normals, written as OBJ + MTL.
+inline void write_heightfield(const std::string &obj, const std::string &mtl, int cells, int pside)
+{
+	FILE *fm = fopen(mtl.c_str(), "w");
+	if (!fm) { fprintf(stderr, "cannot write %s\n", mtl.c_str()); exit(2); }
+	fprintf(fm, "newmtl hfa\nKa 0.100000 0.100000 0.100000\nKd 0.100000 0.500000 0.800000\nKs 1.000000 1.000000 1.000000\nNs 100.000000\n");
+	fprintf(fm, "newmtl hfb\nKa 0.200000 0.100000 0.100000\nKd 0.800000 0.400000 0.100000\nKs 0.500000 0.500000 0.500000\nNs 20.000000\n");
+	fclose(fm);
+	FILE *fo = fopen(obj.c_str(), "w");
+	if (!fo) { fprintf(stderr, "cannot write %s\n", obj.c_str()); exit(2); }
+	const int nv = cells + 1;
+	for (int j = 0; j < nv; ++j)
+		for (int i = 0; i < nv; ++i)
+		{
+			const double x = -4.0 + 8.0 * i / cells, z = -4.0 + 8.0 * j / cells;
+			const double y = 1.5 + 0.6 * sin(3 * x) * cos(2.5 * z) + 0.25 * sin(9 * x + 1) * sin(7 * z);
+			fprintf(fo, "v %.6f %.6f %.6f\n", x, y, z);
+		}
+	for (int j = 0; j < nv; ++j)
+		for (int i = 0; i < nv; ++i)
+		{
+			const double x = -4.0 + 8.0 * i / cells, z = -4.0 + 8.0 * j / cells;
+			const double dx = 1.8 * cos(3 * x) * cos(2.5 * z) + 2.25 * cos(9 * x + 1) * sin(7 * z);
+			const double dz = -1.5 * sin(3 * x) * sin(2.5 * z) + 1.75 * sin(9 * x + 1) * cos(7 * z);
+			const double inv = 1.0 / sqrt(dx * dx + 1.0 + dz * dz);
+			fprintf(fo, "vn %.6f %.6f %.6f\n", -dx * inv, inv, -dz * inv);
+		}
+	for (int j = 0; j < nv; ++j)
+		for (int i = 0; i < nv; ++i)
+			fprintf(fo, "vt %.6f %.6f\n", (double)i / cells, (double)j / cells);
+	const int pc = cells / pside;   // cells per part side
+	for (int pj = 0; pj < pside; ++pj)
+		for (int pi = 0; pi < pside; ++pi)
+		{
+			fprintf(fo, "usemtl %s\n", ((pi + pj) & 1) ? "hfb" : "hfa");
+			for (int j = pj * pc; j < (pj + 1) * pc; ++j)
+				for (int i = pi * pc; i < (pi + 1) * pc; ++i)
+				{
+					const int a = j * nv + i + 1, b = a + 1, c = a + nv, d = c + 1;
+					fprintf(fo, "f %d/%d/%d %d/%d/%d %d/%d/%d\n", a, a, a, c, c, c, b, b, b);
+					fprintf(fo, "f %d/%d/%d %d/%d/%d %d/%d/%d\n", b, b, b, c, c, c, d, d, d);
+				}
+		}
+	fclose(fo);
+}
+
+// A closed, coarse icosphere-like blob written with quads and "v//vn" faces, to exercise the
+// loader's quad split (Model.cpp:88-117) and the no-tcoord parse path (Model.cpp:903-906).
+inline void write_quadblob(const std::string &obj, int rings, int sectors)
+{
+	FILE *fo = fopen(obj.c_str(), "w");
+	if (!fo) { fprintf(stderr, "cannot write %s\n", obj.c_str()); exit(2); }
+	for (int r = 0; r <= rings; ++r)
+		for (int s = 0; s < sectors; ++s)
+		{
+			const double th = 3.14159265358979323846 * (0.08 + 0.84 * r / rings), ph = 2 * 3.14159265358979323846 * s / sectors;
+			const double rad = 1.0 + 0.25 * sin(3 * ph) * sin(2 * th);
+			fprintf(fo, "v %.6f %.6f %.6f\n", rad * sin(th) * cos(ph), rad * cos(th), rad * sin(th) * sin(ph));
+		}
+	for (int r = 0; r <= rings; ++r)
+		for (int s = 0; s < sectors; ++s)
+		{
+			const double th = 3.14159265358979323846 * (0.08 + 0.84 * r / rings), ph = 2 * 3.14159265358979323846 * s / sectors;
+			fprintf(fo, "vn %.6f %.6f %.6f\n", sin(th) * cos(ph), cos(th), sin(th) * sin(ph));
+		}
+	for (int r = 0; r < rings; ++r)
+	{
+		if (r == rings / 2) fprintf(fo, "usemtl lower\n");
+		for (int s = 0; s < sectors; ++s)
+		{
+			const int a = r * sectors + s + 1, b = r * sectors + (s + 1) % sectors + 1, c = b + sectors, d = a + sectors;
+			fprintf(fo, "f %d//%d %d//%d %d//%d %d//%d\n", a, a, b, b, c, c, d, d);
+		}
+	}
+	fclose(fo);
+}
+
+template<class SceneT> inline int add_heightfield(SceneT &scene, const SceneArgs &a, int cells, int pside)
+{
+	char tag[64];
+	snprintf(tag, sizeof tag, "/rt_hf_%d_%d", cells, pside);
+	const std::string obj = a.tmpdir + tag + ".obj", mtl = a.tmpdir + tag + ".mtl";
+	write_heightfield(obj, mtl, cells, pside);
+	return scene.AddModel(widen(obj), widen(mtl));
+}
+
+// ---- C1: exactly main.cpp:165-174 ------------------------------------------------------
+template<class SceneT> inline void build_c1(SceneT &scene, const SceneArgs &)
+{
+	default_lights(scene);
+	scene.AddPlane();
+	scene.AddSphere(1.0);
+}
+
+// ---- C2: plane + n x n spheres r=0.4, 4 point lights -----------------------
+template<class SceneT> inline void build_c2(SceneT &scene, const SceneArgs &a)
+{
+	const int n = a.n > 0 ? a.n : 32;
+	scene.EnvLight = Vertex(0.05f, 0.05f, 0.05f, 1.0f);
+	const float lx[4] = { 12, -12, 12, -12 }, lz[4] = { 6, 6, -26, -26 };
+	for (int k = 0; k < 4; ++k)
+	{
+		scene.AddLight(MY_LIGHT_POINT, Vertex(0.15f, 0.55f, 0.3f), Vertex(0.0f, 0.0f, 1.0f, 256));
+		scene.Lights[k].position = Vertex(lx[k], 10, lz[k], 1.0f);
+	}
+	scene.AddPlane();
+	for (int j = 0; j < n; ++j)
+		for (int i = 0; i < n; ++i)
+		{
+			scene.AddSphere(0.4f);
+			scene.Objects.back()->position = Vertex(-(n - 1) * 0.5f + i, 0.4f, 4.0f - j);
+		}
+}
+
+// ---- C3: plane + height-field Model (n x n cells, parts x parts usemtl groups) ---------
+template<class SceneT> inline void build_c3(SceneT &scene, const SceneArgs &a)
+{
+	const int cells = a.n > 0 ? a.n : 720, pside = a.parts > 0 ? a.parts : cells / 16;
+	default_lights(scene);
+	scene.Lights[1].position = Vertex(3, 9, 12, 1.0f);   // lifted off the ground plane
+	scene.AddPlane();
+	const int m = add_heightfield(scene, a, cells, pside);
+	scene.ChgMtl(m, scene.MtlLiby[1]);
+	scene.MovePos(MY_MODEL_OBJECT, m, Vertex(0, 0, 5));
+}
+
+// ---- C4/C5: mesh + 8x8 glass spheres + mirror spheres (refraction) ---------------------
+template<class SceneT> inline void build_c4(SceneT &scene, const SceneArgs &a)
+{
+	const int cells = a.n > 0 ? a.n : 1440, pside = a.parts > 0 ? a.parts : cells / 16;
+	default_lights(scene);
+	scene.Lights[1].position = Vertex(3, 9, 12, 1.0f);
+	scene.AddPlane();
+	const int m = add_heightfield(scene, a, cells, pside);
+	scene.ChgMtl(m, scene.MtlLiby[1]);
+	scene.MovePos(MY_MODEL_OBJECT, m, Vertex(0, 0, 3));
+	for (int j = 0; j < 8; ++j)
+		for (int i = 0; i < 8; ++i)
+		{
+			const int s = scene.AddSphere(0.35f);
+			scene.Objects.back()->position = Vertex(-3.5f + i, 2.9f + 0.25f * ((i + j) & 1), 7.5f - 0.9f * j);
+			scene.ChgMtl(s, scene.MtlLiby[4]);   // "grass" = glass: reflect .15, refract .75, rfr 1.5
+		}
+	for (int i = 0; i < 6; ++i)
+	{
+		const int s = scene.AddSphere(0.8f);
+		scene.Objects.back()->position = Vertex(-7.5f + 3.0f * i, 0.8f, 9.5f + ((i & 1) ? 1.0f : 0.0f));
+		scene.ChgMtl(s, scene.MtlLiby[2]);       // mirror
+	}
+}
+
+// ---- small test scenes -----------------------------------------------------------------
+// every analytic primitive kind + glass + mirror + box, two default lights
+template<class SceneT> inline void build_t_mixed(SceneT &scene, const SceneArgs &)
+{
+	default_lights(scene);
+	scene.Lights[1].position = Vertex(-2, 7, 9, 1.0f);
+	scene.AddPlane();
+	int s = scene.AddSphere(1.0f);                       // default blue sphere
+	scene.MovePos(MY_MODEL_OBJECT, s, Vertex(-2.5f, 0, 1));
+	s = scene.AddSphere(1.2f);                           // glass
+	scene.ChgMtl(s, scene.MtlLiby[4]);
+	scene.MovePos(MY_MODEL_OBJECT, s, Vertex(0.5f, 0.2f, 4));
+	s = scene.AddSphere(0.9f);                           // mirror
+	scene.ChgMtl(s, scene.MtlLiby[2]);
+	scene.MovePos(MY_MODEL_OBJECT, s, Vertex(3.2f, 0, 0.5f));
+	int b = scene.AddCube(1.6f);                         // brass box
+	scene.MovePos(MY_MODEL_OBJECT, b, Vertex(-0.5f, 0, -2.5f));
+	b = scene.AddCube(1.0f);
+	scene.ChgMtl(b, scene.MtlLiby[5]);                   // wall box
+	scene.MovePos(MY_MODEL_OBJECT, b, Vertex(2.2f, 0.0f, 5.5f));
+	s = scene.AddSphere(0.5f);                           // green reflective
+	scene.ChgMtl(s, scene.MtlLiby[3]);
+	scene.MovePos(MY_MODEL_OBJECT, s, Vertex(-1.2f, 0, 6.5f));
+}
+
+// BallPlane lattice + plane + glass sphere
+template<class SceneT> inline void build_t_ballplane(SceneT &scene, const SceneArgs &)
+{
+	default_lights(scene);
+	scene.Lights[1].position = Vertex(2, 8, 10, 1.0f);
+	scene.AddPlane();
+	const int bp = scene.AddBallPlane(0.3f);
+	scene.Objects[bp]->position = Vertex(0, 1.2f, 3);
+	const int s = scene.AddSphere(0.8f);
+	scene.ChgMtl(s, scene.MtlLiby[4]);
+	scene.MovePos(MY_MODEL_OBJECT, s, Vertex(2.5f, 0, 6));
+}
+
+// small mesh + spheres + plane (c3/c4 shape at test size); n = cells, parts = parts per side
+template<class SceneT> inline void build_t_mesh(SceneT &scene, const SceneArgs &a)
+{
+	SceneArgs b = a;
+	if (b.n <= 0) b.n = 48;
+	if (b.parts <= 0) b.parts = 3;
+	default_lights(scene);
+	scene.Lights[1].position = Vertex(3, 9, 12, 1.0f);
+	scene.AddPlane();
+	int s = scene.AddSphere(0.7f);
+	scene.ChgMtl(s, scene.MtlLiby[4]);
+	scene.MovePos(MY_MODEL_OBJECT, s, Vertex(-2.0f, 2.6f, 7));
+	const int m = add_heightfield(scene, b, b.n, b.parts);
+	scene.MovePos(MY_MODEL_OBJECT, m, Vertex(0, 0, 5));
+	s = scene.AddSphere(0.9f);
+	scene.ChgMtl(s, scene.MtlLiby[2]);
+	scene.MovePos(MY_MODEL_OBJECT, s, Vertex(3.0f, 1.9f, 6));
+}
+
+// two meshes (one reflective, one with MTL materials and quads), box between them
+template<class SceneT> inline void build_t_twomesh(SceneT &scene, const SceneArgs &a)
+{
+	SceneArgs b = a;
+	if (b.n <= 0) b.n = 32;
+	if (b.parts <= 0) b.parts = 2;
+	default_lights(scene);
+	scene.Lights[1].position = Vertex(-3, 9, 12, 1.0f);
+	scene.AddPlane();
+	const int m = add_heightfield(scene, b, b.n, b.parts);
+	scene.ChgMtl(m, scene.MtlLiby[3]);
+	scene.MovePos(MY_MODEL_OBJECT, m, Vertex(-1, -0.4f, 2));
+	const int c = scene.AddCube(1.2f);
+	scene.MovePos(MY_MODEL_OBJECT, c, Vertex(3.5f, 0, 7));
+	const std::string blob = b.tmpdir + "/rt_blob.obj";
+	write_quadblob(blob, 10, 16);
+	const int q = scene.AddModel(widen(blob), widen(b.tmpdir + "/rt_blob_missing.mtl"));
+	scene.MovePos(MY_MODEL_OBJECT, q, Vertex(-6.0f, 4.5f, -4.0f));
+}
+
+template<class SceneT> inline bool build(SceneT &scene, const SceneArgs &a)
+{
+	if (a.name == "c1") build_c1(scene, a);
+	else if (a.name == "c2") build_c2(scene, a);
+	else if (a.name == "c3") build_c3(scene, a);
+	else if (a.name == "c4" || a.name == "c5") build_c4(scene, a);
+	else if (a.name == "t_mixed") build_t_mixed(scene, a);
+	else if (a.name == "t_ballplane") build_t_ballplane(scene, a);
+	else if (a.name == "t_mesh") build_t_mesh(scene, a);
+	else if (a.name == "t_twomesh") build_t_twomesh(scene, a);
+	else return false;
+	return true;
+}
+
+}  // namespace rtscenes
