@@ -1,0 +1,228 @@
+/*
+ * rt_b200.h -- C ABI of the B200-native trace-and-shade path (librt_b200.so).
+ *
+ * The reference (XZiar/RayTrace) has no FFI; its render path is entered through two C++ class
+ * surfaces:
+ *   B1  RayTracer::start/stop + isFinish/useTime/output   /root/reference/RayTracer.h:16-56
+ *   B2  DrawObject::intersect (per-primitive operator)     /root/reference/3DElement.h:185-202
+ * This header is the boundary a maintainer binds instead of RayTracer.cpp's CPU workers: every
+ * entry point below names the reference code it replaces.  Plain C types only; caller-owned host
+ * buffers; library-owned device memory; every call returns 0 or a negative RT_E_* code and
+ * leaves a message in rt_last_error().  There is NO CPU fallback: without a CUDA device (or
+ * without the sm_100a kernels) rt_create() fails.
+ */
+#ifndef RT_B200_H
+#define RT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_ABI_VERSION 1
+
+/* error codes */
+#define RT_OK            0
+#define RT_E_INVALID    -1   /* bad argument / inconsistent scene description */
+#define RT_E_CUDA       -2   /* CUDA runtime error (text in rt_last_error) */
+#define RT_E_NODEVICE   -3   /* no usable sm_100 device: the product path refuses to run */
+#define RT_E_STATE      -4   /* call order violated (e.g. render before upload) */
+#define RT_E_LIMIT      -5   /* a structural limit was exceeded (stack depth, counts) */
+
+/* object kinds == MY_OBJECT_* (3DElement.h:4-8) */
+#define RT_OBJ_SPHERE    1
+#define RT_OBJ_CUBE      2
+#define RT_OBJ_MODEL     3
+#define RT_OBJ_PLANE     4
+#define RT_OBJ_BALLPLANE 5
+/* light kinds == MY_LIGHT_* (3DElement.h:13-15) */
+#define RT_LIGHT_PARALLEL 1
+#define RT_LIGHT_POINT    2
+#define RT_LIGHT_SPOT     3
+/* render types == MY_MODEL_* (RayTracer.h:5-13), the `type` argument of RayTracer::start */
+#define RT_TYPE_CHECK     0x01
+#define RT_TYPE_DEPTH     0x02
+#define RT_TYPE_NORMAL    0x03
+#define RT_TYPE_TEXTURE   0x04
+#define RT_TYPE_MATERIAL  0x05
+#define RT_TYPE_SHADOW    0x06
+#define RT_TYPE_REFLECT   0x07
+#define RT_TYPE_REFRACT   0x08
+#define RT_TYPE_RAYTRACE  0x80
+
+typedef struct rt_ctx rt_ctx;
+
+typedef struct { float x, y, z, w; } rt_vec4;
+
+/* Material, 3DElement.h:106-120 */
+typedef struct
+{
+	rt_vec4 ambient, diffuse, specular, emission;
+	float shiness, reflect, refract, rfr;
+} rt_material;
+
+/* Light, 3DElement.h:204-223: the fields RTfrac reads (RayTracer.cpp:474-503) */
+typedef struct
+{
+	rt_vec4 position, ambient, diffuse, specular, attenuation;
+	uint32_t type;      /* RT_LIGHT_* */
+	uint32_t enabled;   /* Light::bLight */
+	uint32_t pad0, pad1;
+} rt_light;
+
+/* Camera, 3DElement.h:225-237 */
+typedef struct
+{
+	rt_vec4 u, v, n, position;
+	int32_t width, height;
+	float fovy, zNear, zFar;
+	uint32_t pad0, pad1, pad2;
+} rt_camera;
+
+/* Texture, 3DElement.h:92-104: BGR8 rows, `offset` bytes into rt_scene_desc::texels */
+typedef struct
+{
+	int32_t w, h;
+	uint32_t offset;
+	uint32_t pad0;
+} rt_texture;
+
+/*
+ * One analytic primitive.  Sphere (Basic3DObject.h:5-16): position=centre, radius.
+ * Cube (:18-33): position, a=min, b=max (object-local).  Plane (:35-50): position, a=normal,
+ * b=axisx, c=axisy.  A BallPlane (:52-68) is passed as its 16 lattice spheres, sub = 1..16 in
+ * the reference's loop order (Basic3DObject.cpp:492-497), position = the lattice centre.
+ * Records must be sorted by (object, sub); object order is the closest-hit tie-break order
+ * (RayTracer.cpp:458-465).
+ */
+typedef struct
+{
+	uint32_t kind;       /* RT_OBJ_SPHERE / RT_OBJ_CUBE / RT_OBJ_PLANE */
+	uint32_t object;     /* index in Scene::Objects */
+	uint32_t sub;
+	uint32_t material;   /* index into rt_scene_desc::materials */
+	int32_t texture;     /* index into textures, -1 = none */
+	float radius, radius_sqr;
+	uint32_t pad0;
+	rt_vec4 position;
+	rt_vec4 a, b, c;
+} rt_prim;
+
+/* One Model (Model.h:6-52): placement + bounds; its parts are parts[part_begin .. +part_count) */
+typedef struct
+{
+	uint32_t object;             /* index in Scene::Objects */
+	uint32_t part_begin, part_count;
+	uint32_t pad0;
+	rt_vec4 position;            /* DrawObject::position */
+	rt_vec4 ver_min, ver_max;    /* Model::VerMin/VerMax, untranslated (Model.cpp:404) */
+} rt_model;
+
+/* One `usemtl` part (Model::parts[p], borders[2p], borders[2p+1], part_mtl, mtl_tex) */
+typedef struct
+{
+	rt_vec4 border_min, border_max;  /* untranslated */
+	uint32_t tri_begin, tri_count;   /* range in the triangle arrays; count <= 32767 */
+	uint32_t material;
+	int32_t texture;
+} rt_part;
+
+/*
+ * Flattened Scene (Scene.h:24-29 + everything hanging off Objects).  Hidden objects (bShow ==
+ * false) are simply not listed.  Triangle arrays are SoA copies of `Triangle` (3DElement.h:
+ * 128-139): 3 points, 3 normals, 3 texture coordinates per triangle, parts in model order.
+ * `geometry_epoch` lets the caller skip the heavy arrays: if it equals the epoch of the previous
+ * upload on this context the tri_* pointers may be NULL and the resident triangles are reused.
+ */
+typedef struct
+{
+	rt_camera camera;
+	rt_vec4 env_light;
+	uint32_t n_lights;     const rt_light *lights;
+	uint32_t n_materials;  const rt_material *materials;
+	uint32_t n_textures;   const rt_texture *textures;
+	size_t texel_bytes;    const uint8_t *texels;
+	uint32_t n_prims;      const rt_prim *prims;
+	uint32_t n_models;     const rt_model *models;
+	uint32_t n_parts;      const rt_part *parts;
+	uint32_t n_tris;
+	const rt_vec4 *tri_points;    /* 3 * n_tris */
+	const rt_vec4 *tri_norms;     /* 3 * n_tris */
+	const float *tri_tcoords;     /* 6 * n_tris */
+	uint64_t geometry_epoch;      /* 0 = always upload */
+} rt_scene_desc;
+
+/* Per-render parameters: the arguments and latched state of RayTracer::start (RayTracer.cpp:614-626) */
+typedef struct
+{
+	uint32_t type;        /* RT_TYPE_* */
+	uint32_t max_level;   /* RayTracer::maxLevel; levels 0..max_level are traced (RayTracer.cpp:453) */
+	uint32_t rank, world; /* image-space shard: 64-row tile t is rendered iff t % world == rank; world=0 or 1 = whole frame */
+	uint32_t flags;       /* RT_FLAG_* */
+	uint32_t pad0;
+} rt_render_params;
+
+#define RT_FLAG_HIT_IDS   0x1   /* keep primary closest-hit identities for rt_read_hit_ids */
+#define RT_FLAG_STATS     0x2   /* count BVH node visits / primitive tests (slower kernels) */
+#define RT_FLAG_BRUTE     0x4   /* diagnostic: ignore the BVHs, test every primitive (small scenes) */
+
+/* primary closest-hit identity, the GPU-side meaning of HitRes::obj (3DElement.h:174) */
+typedef struct
+{
+	int32_t object;   /* index in Scene::Objects, -1 = miss */
+	int32_t sub;      /* BallPlane slot (1..16) / Model part (clTri::numa) / 0 */
+	int32_t index;    /* triangle index in its part (clTri::numb), else -1 */
+	int32_t octant;   /* which octant copy of the triangle won (Model.cpp:765-785), else -1 */
+	float distance;   /* HitRes::distance, 1e20 = miss */
+} rt_hit_id;
+
+typedef struct
+{
+	uint64_t primary, shadow, reflect, refract;      /* rays = closest-hit or any-hit queries */
+	uint64_t nodes_visited, tri_tests, prim_tests;   /* filled only with RT_FLAG_STATS */
+	double render_ms;      /* device time of the last frame (CUDA events) */
+	double trace_ms, shadow_ms, shade_ms, other_ms;   /* per-stage split (RT_FLAG_STATS) */
+	double upload_ms, build_ms;                      /* last scene upload / LBVH build */
+	uint32_t launches;                               /* kernels launched for the last frame */
+	uint32_t bvh_nodes, bvh_depth;
+	uint32_t pad0;
+} rt_counters;
+
+const char *rt_last_error(void);
+int rt_abi_version(void);
+
+/* replaces RayTracer::RayTracer (RayTracer.cpp:600-607): one context per GPU */
+int rt_create(int device, rt_ctx **out);
+void rt_destroy(rt_ctx *ctx);
+/* optional: run on a caller-provided cudaStream_t (e.g. torch's current stream) */
+int rt_set_stream(rt_ctx *ctx, void *cuda_stream);
+
+/* replaces the per-start scene walk + Model::RTPrepare (RayTracer.cpp:621-625, Model.cpp:402-480):
+ * copies the description to SoA device buffers and (re)builds the LBVHs when geometry changed */
+int rt_upload_scene(rt_ctx *ctx, const rt_scene_desc *scene);
+
+/* replaces RayTracer::start's thread fan-out (RayTracer.cpp:626-695): enqueues one frame, returns at once */
+int rt_render_async(rt_ctx *ctx, const rt_render_params *params);
+/* replaces the isFinish / useTime polling protocol (RayTracer.h:47-48) */
+int rt_poll(rt_ctx *ctx, int *done, double *seconds);
+int rt_wait(rt_ctx *ctx, double *seconds);
+/* replaces RayTracer::stop (RayTracer.cpp:698-701) */
+int rt_stop(rt_ctx *ctx);
+
+/* RayTracer::output (RayTracer.h:46): RGB8, row 0 = bottom, `stride` bytes per row (>= 3*width).
+ * Only floor(W/64)*64 x floor(H/64)*64 pixels are rendered, the rest is 127 (RayTracer.cpp:13,620).
+ * With world > 1 only this rank's rows are valid. */
+int rt_read_output(rt_ctx *ctx, uint8_t *rgb, size_t stride);
+/* device-resident framebuffer of the last frame (for NCCL gathers / zero-copy consumers) */
+int rt_output_device(rt_ctx *ctx, void **device_ptr, size_t *bytes);
+
+/* diagnostics / parity taps */
+int rt_read_hit_ids(rt_ctx *ctx, rt_hit_id *ids /* width*height */);
+int rt_read_counters(rt_ctx *ctx, rt_counters *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_B200_H */

@@ -98,13 +98,17 @@ inline void primary_ids(Scene &scene, RayTracer &rt, int width, int height, HitI
 					Ray baseray(cam.position, dir, MY_RAY_BASERAY);
 					HitRes basehr;
 					HitRes hr = basehr;
+					intptr_t newobj = basehr.obj;
 					for (auto dobj : scene.Objects)
 						if (dobj->bShow)
 						{
 							hr.obj = basehr.obj;
 							hr = dobj->intersect(baseray, hr);
+							if (hr.obj != basehr.obj)
+								newobj = hr.obj;
 						}
 					HitId id = { -1, -1, -1, -1, hr.distance };
+					hr.obj = newobj;
 					if (hr.obj != basehr.obj)
 					{
 						for (size_t o = 0; o < scene.Objects.size() && id.obj < 0; ++o)

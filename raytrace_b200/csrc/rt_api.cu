@@ -1,0 +1,658 @@
+// C ABI of librt_b200.so (include/rt_b200.h): context, scene upload (SoA flattening on the device
+// side + LBVH builds) and the per-frame wavefront schedule.  Host-side glue only; every per-ray
+// operation runs in the kernels of rt_kernels.cu.  There is deliberately no CPU path here.
+#include "rt_kernels.h"
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...)
+{
+	char buf[1024];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof buf, fmt, ap);
+	va_end(ap);
+	g_err = buf;
+	return code;
+}
+
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(RT_E_CUDA, "%s: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+template<class T> struct DevBuf
+{
+	T *p = nullptr;
+	size_t cap = 0;
+	cudaError_t reserve(size_t n)
+	{
+		if (n <= cap) return cudaSuccess;
+		if (p) cudaFree(p);
+		p = nullptr, cap = 0;
+		const size_t want = n + n / 16 + 16;
+		cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+		if (e == cudaSuccess) cap = want;
+		return e;
+	}
+	cudaError_t upload(const T *src, size_t n, cudaStream_t st)
+	{
+		cudaError_t e = reserve(n);
+		if (e != cudaSuccess || n == 0) return e;
+		return cudaMemcpyAsync(p, src, n * sizeof(T), cudaMemcpyHostToDevice, st);
+	}
+	void release() { if (p) cudaFree(p); p = nullptr, cap = 0; }
+};
+
+struct LevelStore
+{
+	DevBuf<float4> ray_o, ray_d, hit_p, color;
+	DevBuf<uint2> ray_meta;
+	DevBuf<uint32_t> hit_id;
+	DevBuf<int4> aux;
+	DevBuf<uint8_t> shadow;
+	uint32_t capacity = 0, lights = 0;
+	void release() { ray_o.release(), ray_d.release(), hit_p.release(), color.release(), ray_meta.release(), hit_id.release(), aux.release(), shadow.release(); capacity = 0; }
+};
+
+struct rt_ctx
+{
+	int device = 0, sms = 148;
+	cudaStream_t stream = nullptr;
+	bool ownStream = false;
+	cudaEvent_t evStart = nullptr, evStop = nullptr, evA = nullptr, evB = nullptr;
+
+	// resident scene
+	bool hasScene = false;
+	uint64_t geometryEpoch = 0;
+	std::vector<rt_prim> prims;
+	std::vector<rt_model> models;
+	std::vector<rt_part> parts;
+	std::vector<rt_light> lights;
+	rt_camera camera;
+	rt_vec4 envLight;
+	bool anyRefract = false;
+	uint32_t nTris = 0;
+	DevBuf<float4> primGeom, materials, triPoints, triNorms, triGeomOrig, triGeom, boxLo, boxHi, partMid, partPos;
+	DevBuf<int4> primMeta, textures;
+	DevBuf<uint8_t> texels;
+	DevBuf<float2> triTcoords;
+	DevBuf<uint32_t> bvhPrims, triSlot, triPart, leafOrder;
+	DevBuf<DevModel> dModels;
+	DevBuf<DevPart> dParts;
+	DevBuf<BvhNode> nodes;
+	DevBuf<SceneItem> items;
+	SceneDev S;
+	BuildScratch *scratch = nullptr;
+	uint32_t bvhNodes = 0, bvhDepth = 0, leafSize = 4;
+
+	// per frame
+	FrameParams *hFrame = nullptr, *dFrame = nullptr;
+	WaveState *hWave = nullptr, *dWave = nullptr;
+	LevelStore levels[RT_MAX_LEVELS + 2];
+	DevBuf<uint8_t> out;
+	int outW = 0, outH = 0;
+	rt_render_params lastParams;
+	uint32_t lastPixels = 0, lastLaunches = 0, lastMaxLevel = 0;
+	bool frameInFlight = false, frameValid = false;
+	double uploadMs = 0, buildMs = 0, renderMs = 0;
+	float levelFactor = 2.0f;
+};
+
+extern "C" const char *rt_last_error(void) { return g_err.c_str(); }
+extern "C" int rt_abi_version(void) { return RT_ABI_VERSION; }
+
+extern "C" int rt_create(int device, rt_ctx **out)
+{
+	if (!out) return fail(RT_E_INVALID, "rt_create: out is NULL");
+	*out = nullptr;
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0)
+		return fail(RT_E_NODEVICE, "rt_create: no CUDA device (%s); this library has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+	if (device < 0 || device >= n) return fail(RT_E_INVALID, "rt_create: device %d out of range (%d devices)", device, n);
+	cudaDeviceProp prop;
+	CU(cudaGetDeviceProperties(&prop, device));
+	if (prop.major < 10)
+		return fail(RT_E_NODEVICE, "rt_create: device %d is sm_%d%d; the kernels are built for sm_100a only", device, prop.major, prop.minor);
+	CU(cudaSetDevice(device));
+	rt_ctx *c = new rt_ctx();
+	c->device = device, c->sms = prop.multiProcessorCount;
+	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	c->ownStream = true;
+	CU(cudaEventCreate(&c->evStart)); CU(cudaEventCreate(&c->evStop)); CU(cudaEventCreate(&c->evA)); CU(cudaEventCreate(&c->evB));
+	CU(cudaMallocHost(&c->hFrame, sizeof(FrameParams)));
+	CU(cudaMalloc(&c->dFrame, sizeof(FrameParams)));
+	CU(cudaMallocHost(&c->hWave, sizeof(WaveState)));
+	CU(cudaMalloc(&c->dWave, sizeof(WaveState)));
+	memset(&c->S, 0, sizeof c->S);
+	if (const char *v = getenv("RT_B200_LEAF_SIZE")) c->leafSize = (uint32_t)atoi(v);
+	if (const char *v = getenv("RT_B200_LEVEL_FACTOR")) c->levelFactor = (float)atof(v);
+	*out = c;
+	return RT_OK;
+}
+
+extern "C" void rt_destroy(rt_ctx *c)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	for (auto &l : c->levels) l.release();
+	c->primGeom.release(), c->materials.release(), c->triPoints.release(), c->triNorms.release(), c->triGeomOrig.release(), c->triGeom.release();
+	c->boxLo.release(), c->boxHi.release(), c->partMid.release(), c->partPos.release(), c->primMeta.release(), c->textures.release(), c->texels.release();
+	c->triTcoords.release(), c->bvhPrims.release(), c->triSlot.release(), c->triPart.release(), c->leafOrder.release();
+	c->dModels.release(), c->dParts.release(), c->nodes.release(), c->items.release(), c->out.release();
+	rtb_free_scratch(c->scratch);
+	cudaFreeHost(c->hFrame), cudaFree(c->dFrame), cudaFreeHost(c->hWave), cudaFree(c->dWave);
+	cudaEventDestroy(c->evStart), cudaEventDestroy(c->evStop), cudaEventDestroy(c->evA), cudaEventDestroy(c->evB);
+	if (c->ownStream) cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+extern "C" int rt_set_stream(rt_ctx *c, void *s)
+{
+	if (!c) return fail(RT_E_INVALID, "rt_set_stream: ctx is NULL");
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	if (c->ownStream) cudaStreamDestroy(c->stream);
+	c->stream = (cudaStream_t)s, c->ownStream = false;
+	return RT_OK;
+}
+
+static inline float4 f4(const rt_vec4 &v) { return make_float4(v.x, v.y, v.z, v.w); }
+static inline rt_vec4 addv(const rt_vec4 &a, const rt_vec4 &b) { return rt_vec4{ a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w }; }
+
+template<class T> static bool same(const std::vector<T> &a, const T *b, size_t n)
+{
+	return a.size() == n && (n == 0 || memcmp(a.data(), b, n * sizeof(T)) == 0);
+}
+
+extern "C" int rt_upload_scene(rt_ctx *c, const rt_scene_desc *s)
+{
+	if (!c || !s) return fail(RT_E_INVALID, "rt_upload_scene: NULL argument");
+	CU(cudaSetDevice(c->device));
+	if (c->frameInFlight) { CU(cudaEventSynchronize(c->evStop)); c->frameInFlight = false; }
+	if (s->n_lights > RT_MAX_LIGHTS) return fail(RT_E_LIMIT, "rt_upload_scene: %u lights (max %d, Scene.cpp:85)", s->n_lights, RT_MAX_LIGHTS);
+	if (s->n_tris >= 0x0FFFFFFFu) return fail(RT_E_LIMIT, "rt_upload_scene: too many triangles");
+	for (uint32_t i = 1; i < s->n_prims; ++i)
+		if (s->prims[i].object < s->prims[i - 1].object || (s->prims[i].object == s->prims[i - 1].object && s->prims[i].sub <= s->prims[i - 1].sub))
+			return fail(RT_E_INVALID, "rt_upload_scene: prims must be sorted by (object, sub)");
+	for (uint32_t i = 0; i < s->n_prims; ++i)
+	{
+		const rt_prim &p = s->prims[i];
+		if (p.kind != RT_OBJ_SPHERE && p.kind != RT_OBJ_CUBE && p.kind != RT_OBJ_PLANE) return fail(RT_E_INVALID, "rt_upload_scene: prim %u has kind %u", i, p.kind);
+		if (p.material >= s->n_materials || p.texture >= (int32_t)s->n_textures) return fail(RT_E_INVALID, "rt_upload_scene: prim %u material/texture out of range", i);
+	}
+	uint32_t triCheck = 0;
+	for (uint32_t m = 0; m < s->n_models; ++m)
+	{
+		const rt_model &M = s->models[m];
+		if (M.part_begin + M.part_count > s->n_parts) return fail(RT_E_INVALID, "rt_upload_scene: model %u part range", m);
+		if (m && M.object <= s->models[m - 1].object) return fail(RT_E_INVALID, "rt_upload_scene: models must be sorted by object");
+		for (uint32_t p = 0; p < M.part_count; ++p)
+		{
+			const rt_part &P = s->parts[M.part_begin + p];
+			if (P.tri_begin != triCheck) return fail(RT_E_INVALID, "rt_upload_scene: part triangle ranges must be contiguous in part order");
+			if (P.tri_count > 32767) return fail(RT_E_LIMIT, "rt_upload_scene: part with %u triangles (clTri::numb is int16)", P.tri_count);
+			if (P.material >= s->n_materials || P.texture >= (int32_t)s->n_textures) return fail(RT_E_INVALID, "rt_upload_scene: part material/texture out of range");
+			triCheck += P.tri_count;
+		}
+	}
+	if (triCheck != s->n_tris) return fail(RT_E_INVALID, "rt_upload_scene: parts cover %u triangles, n_tris = %u", triCheck, s->n_tris);
+
+	cudaStream_t st = c->stream;
+	CU(cudaEventRecord(c->evA, st));
+
+	// ---- cheap tables: always refreshed -------------------------------------------------------
+	c->camera = s->camera, c->envLight = s->env_light;
+	c->lights.assign(s->lights, s->lights + s->n_lights);
+	{
+		std::vector<float4> m(4 * (size_t)s->n_materials);
+		c->anyRefract = false;
+		for (uint32_t i = 0; i < s->n_materials; ++i)
+		{
+			const rt_material &r = s->materials[i];
+			m[4 * i] = f4(r.ambient), m[4 * i + 1] = f4(r.diffuse), m[4 * i + 2] = f4(r.specular);
+			m[4 * i + 3] = make_float4(r.shiness, r.reflect, r.refract, r.rfr);
+			if (r.refract > 0.01f) c->anyRefract = true;
+		}
+		CU(c->materials.upload(m.data(), m.size(), st));
+		std::vector<int4> t(s->n_textures);
+		for (uint32_t i = 0; i < s->n_textures; ++i) t[i] = make_int4(s->textures[i].w, s->textures[i].h, (int)s->textures[i].offset, 0);
+		CU(c->textures.upload(t.data(), t.size(), st));
+		CU(c->texels.upload(s->texels, s->texel_bytes, st));
+		CU(cudaStreamSynchronize(st));   // staging vectors go out of scope
+	}
+
+	// ---- what changed? ------------------------------------------------------------------------
+	const bool trisChanged = !c->hasScene || s->geometry_epoch == 0 || s->geometry_epoch != c->geometryEpoch || s->n_tris != c->nTris;
+	const bool modelsChanged = trisChanged || !same(c->models, s->models, s->n_models) || !same(c->parts, s->parts, s->n_parts);
+	const bool primsChanged = !c->hasScene || !same(c->prims, s->prims, s->n_prims);
+	if (trisChanged && s->n_tris && (!s->tri_points || !s->tri_norms || !s->tri_tcoords))
+		return fail(RT_E_INVALID, "rt_upload_scene: geometry changed but triangle arrays are NULL");
+	c->prims.assign(s->prims, s->prims + s->n_prims);
+	c->models.assign(s->models, s->models + s->n_models);
+	c->parts.assign(s->parts, s->parts + s->n_parts);
+	c->nTris = s->n_tris;
+	c->geometryEpoch = s->geometry_epoch;
+
+	if (trisChanged && s->n_tris)
+	{
+		CU(c->triPoints.upload((const float4 *)s->tri_points, 3 * (size_t)s->n_tris, st));
+		CU(c->triNorms.upload((const float4 *)s->tri_norms, 3 * (size_t)s->n_tris, st));
+		CU(c->triTcoords.upload((const float2 *)s->tri_tcoords, 3 * (size_t)s->n_tris, st));
+		std::vector<uint32_t> tp(s->n_tris);
+		for (uint32_t p = 0; p < s->n_parts; ++p)
+			for (uint32_t k = 0; k < s->parts[p].tri_count; ++k) tp[s->parts[p].tri_begin + k] = p;
+		CU(c->triPart.upload(tp.data(), tp.size(), st));
+		CU(cudaStreamSynchronize(st));
+	}
+
+	if (primsChanged || modelsChanged)
+	{
+		// ---- analytic primitives ------------------------------------------------------------------
+		std::vector<float4> pg(4 * (size_t)s->n_prims);
+		std::vector<int4> pm(s->n_prims);
+		for (uint32_t i = 0; i < s->n_prims; ++i)
+		{
+			const rt_prim &p = s->prims[i];
+			pg[4 * i] = make_float4(p.position.x, p.position.y, p.position.z, p.radius);
+			if (p.kind == RT_OBJ_SPHERE)
+				pg[4 * i + 1] = make_float4(p.radius_sqr, 0, 0, 0), pg[4 * i + 2] = pg[4 * i + 3] = make_float4(0, 0, 0, 0);
+			else if (p.kind == RT_OBJ_CUBE)
+			{
+				// Box::intersect tests (min + position, max + position), Basic3DObject.cpp:280
+				pg[4 * i + 1] = f4(addv(p.a, p.position)), pg[4 * i + 2] = f4(addv(p.b, p.position)), pg[4 * i + 3] = f4(p.b);
+			}
+			else
+				pg[4 * i + 1] = f4(p.a), pg[4 * i + 2] = f4(p.b), pg[4 * i + 3] = f4(p.c);
+			pm[i] = make_int4((int)p.kind, (int)p.material, p.texture, (int)((p.object << 8) | (p.sub & 0xFF)));
+		}
+		CU(c->primGeom.upload(pg.data(), pg.size(), st));
+		CU(c->primMeta.upload(pm.data(), pm.size(), st));
+
+		// ---- models / parts -----------------------------------------------------------------------
+		std::vector<DevModel> dm(s->n_models);
+		std::vector<DevPart> dp(s->n_parts);
+		std::vector<float4> mid(s->n_parts), pos(s->n_parts);
+		for (uint32_t m = 0; m < s->n_models; ++m)
+		{
+			const rt_model &M = s->models[m];
+			memset(&dm[m], 0, sizeof(DevModel));
+			dm[m].border_min = f4(addv(M.ver_min, M.position)), dm[m].border_max = f4(addv(M.ver_max, M.position));
+			dm[m].part_begin = M.part_begin, dm[m].part_count = M.part_count, dm[m].object = M.object;
+			uint32_t tb = 0xFFFFFFFFu, tc = 0;
+			for (uint32_t p = 0; p < M.part_count; ++p)
+			{
+				const rt_part &P = s->parts[M.part_begin + p];
+				if (tb == 0xFFFFFFFFu) tb = P.tri_begin;
+				tc += P.tri_count;
+				DevPart &D = dp[M.part_begin + p];
+				D.box_min = f4(addv(P.border_min, M.position)), D.box_max = f4(addv(P.border_max, M.position));
+				D.tri_begin = P.tri_begin, D.tri_count = P.tri_count, D.material = P.material, D.texture = P.texture;
+				// va = (va + vb) * 0.5, Model.cpp:421 (untranslated)
+				const rt_vec4 sum = addv(P.border_min, P.border_max);
+				mid[M.part_begin + p] = make_float4(sum.x * 0.5f, sum.y * 0.5f, sum.z * 0.5f, 0);
+				pos[M.part_begin + p] = f4(M.position);
+			}
+			dm[m].tri_begin = tb == 0xFFFFFFFFu ? 0 : tb, dm[m].tri_count = tc;
+		}
+		CU(c->dModels.upload(dm.data(), dm.size(), st));
+		CU(c->dParts.upload(dp.data(), dp.size(), st));
+		CU(c->partMid.upload(mid.data(), mid.size(), st));
+		CU(c->partPos.upload(pos.data(), pos.size(), st));
+		CU(cudaStreamSynchronize(st));
+
+		// ---- scene-order item list + BVH budget ---------------------------------------------------
+		const uint32_t runMin = 8;   // runs of >= runMin bounded primitives get their own BVH
+		std::vector<SceneItem> items;
+		uint32_t pi = 0, mi = 0, nodeBudget = 0, primLeafSlots = 0;
+		while (pi < s->n_prims || mi < s->n_models)
+		{
+			const bool takePrim = mi >= s->n_models || (pi < s->n_prims && s->prims[pi].object < s->models[mi].object);
+			if (!takePrim)
+			{
+				items.push_back(SceneItem{ RT_ITEM_MODEL, mi, 0, 0 });
+				nodeBudget += dm[mi].tri_count;
+				++mi;
+				continue;
+			}
+			if (s->prims[pi].kind == RT_OBJ_PLANE) { items.push_back(SceneItem{ RT_ITEM_PRIM, pi, 1, 0 }); ++pi; continue; }
+			uint32_t end = pi;
+			const uint32_t limitObj = mi < s->n_models ? s->models[mi].object : 0xFFFFFFFFu;
+			while (end < s->n_prims && s->prims[end].kind != RT_OBJ_PLANE && s->prims[end].object < limitObj) ++end;
+			if (end - pi >= runMin)
+			{
+				items.push_back(SceneItem{ RT_ITEM_PRIMBVH, pi, end - pi, 0 });
+				nodeBudget += end - pi, primLeafSlots += end - pi;
+			}
+			else
+				for (uint32_t k = pi; k < end; ++k) items.push_back(SceneItem{ RT_ITEM_PRIM, k, 1, 0 });
+			pi = end;
+		}
+		CU(c->nodes.reserve(nodeBudget + 1));
+		CU(c->bvhPrims.reserve(primLeafSlots + 1));
+		CU(c->triGeomOrig.reserve(3 * (size_t)s->n_tris + 1));
+		CU(c->triGeom.reserve(3 * (size_t)s->n_tris + 1));
+		CU(c->triSlot.reserve(s->n_tris + 1));
+		uint32_t maxBoxes = 1;
+		for (const SceneItem &it : items)
+			maxBoxes = std::max(maxBoxes, it.kind == RT_ITEM_MODEL ? dm[it.first].tri_count : it.count);
+		CU(c->boxLo.reserve(maxBoxes)); CU(c->boxHi.reserve(maxBoxes)); CU(c->leafOrder.reserve(maxBoxes));
+
+		// ---- builds ---------------------------------------------------------------------------------
+		cudaEvent_t b0 = c->evB;
+		CU(cudaEventRecord(b0, st));
+		uint32_t nodeCursor = 0, primLeafCursor = 0;
+		c->bvhDepth = 0;
+		for (SceneItem &it : items)
+		{
+			BvhBuildResult res;
+			if (it.kind == RT_ITEM_PRIMBVH)
+			{
+				PrimBoxArgs a{ c->primGeom.p, c->primMeta.p, c->boxLo.p, c->boxHi.p, it.first, it.count };
+				rtb_prim_boxes(st, a);
+				int rc = rtb_build(st, &c->scratch, c->boxLo.p, c->boxHi.p, it.count, 2, c->nodes.p, nodeCursor, primLeafCursor, c->bvhPrims.p + primLeafCursor, &res);
+				if (rc) return fail(RT_E_CUDA, "LBVH build (primitives) failed: %s", cudaGetErrorString((cudaError_t)rc));
+				rtb_offset_order(st, c->bvhPrims.p + primLeafCursor, it.count, it.first);
+				it.root = res.root;
+				nodeCursor += res.nodesUsed, primLeafCursor += it.count;
+				c->bvhDepth = std::max(c->bvhDepth, res.depth);
+			}
+			else if (it.kind == RT_ITEM_MODEL)
+			{
+				const DevModel &M = dm[it.first];
+				if (M.tri_count == 0) { it.root = (int)0x80000000u; it.count = 0; continue; }
+				TriPrepArgs a;
+				a.points = c->triPoints.p + 3 * (size_t)M.tri_begin, a.models = c->dModels.p, a.parts = c->dParts.p;
+				a.tri_part = c->triPart.p + M.tri_begin, a.part_mid_pos = c->partMid.p, a.part_position = c->partPos.p;
+				a.tri_geom_orig = c->triGeomOrig.p + 3 * (size_t)M.tri_begin, a.box_lo = c->boxLo.p, a.box_hi = c->boxHi.p, a.n = M.tri_count;
+				a.id_base = M.tri_begin;
+				rtb_prepare_tris(st, a);
+				int rc = rtb_build(st, &c->scratch, c->boxLo.p, c->boxHi.p, M.tri_count, c->leafSize, c->nodes.p, nodeCursor, M.tri_begin, c->leafOrder.p, &res);
+				if (rc) return fail(RT_E_CUDA, "LBVH build (model %u) failed: %s", it.first, cudaGetErrorString((cudaError_t)rc));
+				rtb_scatter_tris(st, c->triGeomOrig.p, c->leafOrder.p, M.tri_begin, M.tri_begin, M.tri_count, c->triGeom.p, c->triSlot.p);
+				it.root = res.root, it.count = M.tri_count;
+				nodeCursor += res.nodesUsed;
+				c->bvhDepth = std::max(c->bvhDepth, res.depth);
+			}
+		}
+		c->bvhNodes = nodeCursor;
+		if (c->bvhDepth + 1 > RT_STACK)
+			return fail(RT_E_LIMIT, "LBVH depth %u exceeds the traversal stack (%d)", c->bvhDepth, RT_STACK);
+		CU(c->items.upload(items.data(), items.size(), st));
+		CU(cudaEventRecord(c->evStop, st));
+		CU(cudaStreamSynchronize(st));
+		float ms = 0;
+		cudaEventElapsedTime(&ms, b0, c->evStop);
+		c->buildMs = ms;
+
+		SceneDev &S = c->S;
+		S.prim_geom = c->primGeom.p, S.prim_meta = c->primMeta.p, S.bvh_prims = c->bvhPrims.p;
+		S.models = c->dModels.p, S.parts = c->dParts.p;
+		S.tri_geom = c->triGeom.p, S.tri_norms = c->triNorms.p, S.tri_tcoords = c->triTcoords.p;
+		S.tri_slot = c->triSlot.p, S.tri_part = c->triPart.p, S.nodes = c->nodes.p, S.items = c->items.p;
+		S.n_items = (uint32_t)items.size(), S.n_prims = s->n_prims, S.n_tris = s->n_tris, S.n_parts = s->n_parts;
+	}
+	c->S.materials = c->materials.p, c->S.textures = c->textures.p, c->S.texels = c->texels.p;
+	CU(cudaEventRecord(c->evStop, st));
+	CU(cudaStreamSynchronize(st));
+	float ms = 0;
+	cudaEventElapsedTime(&ms, c->evA, c->evStop);
+	c->uploadMs = ms;
+	c->hasScene = true;
+	c->frameValid = false;
+	return RT_OK;
+}
+
+static int ensure_level(rt_ctx *c, uint32_t l, uint32_t cap, uint32_t lights)
+{
+	LevelStore &L = c->levels[l];
+	if (cap <= L.capacity && lights <= L.lights) return RT_OK;
+	L.capacity = 0;
+	CU(L.ray_o.reserve(cap)); CU(L.ray_d.reserve(cap)); CU(L.ray_meta.reserve(cap)); CU(L.hit_p.reserve(cap));
+	CU(L.hit_id.reserve(cap)); CU(L.color.reserve(cap)); CU(L.aux.reserve(cap)); CU(L.shadow.reserve((size_t)cap * (lights ? lights : 1)));
+	L.capacity = cap, L.lights = lights;
+	return RT_OK;
+}
+
+static LevelBuf level_buf(const LevelStore &L)
+{
+	LevelBuf b;
+	b.ray_o = L.ray_o.p, b.ray_d = L.ray_d.p, b.ray_meta = L.ray_meta.p, b.hit_p = L.hit_p.p, b.hit_id = L.hit_id.p;
+	b.color = L.color.p, b.aux = L.aux.p, b.shadow = L.shadow.p, b.capacity = L.capacity;
+	return b;
+}
+
+extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
+{
+	if (!c || !p) return fail(RT_E_INVALID, "rt_render_async: NULL argument");
+	if (!c->hasScene) return fail(RT_E_STATE, "rt_render_async: no scene uploaded");
+	if (p->type != RT_TYPE_RAYTRACE && p->type != RT_TYPE_REFRACT && p->type != RT_TYPE_REFLECT)
+		return fail(RT_E_INVALID, "rt_render_async: render type 0x%x is not implemented on the device path yet", p->type);
+	if (p->max_level >= RT_MAX_LEVELS) return fail(RT_E_LIMIT, "rt_render_async: max_level %u (limit %d)", p->max_level, RT_MAX_LEVELS - 1);
+	CU(cudaSetDevice(c->device));
+	if (c->frameInFlight) { CU(cudaEventSynchronize(c->evStop)); c->frameInFlight = false; }
+	cudaStream_t st = c->stream;
+	const rt_camera &cam = c->camera;
+	const int W = cam.width, H = cam.height;
+	if (W <= 0 || H <= 0) return fail(RT_E_INVALID, "rt_render_async: camera is %dx%d", W, H);
+	const uint32_t world = p->world > 1 ? p->world : 1, rank = p->world > 1 ? p->rank : 0;
+	if (rank >= world) return fail(RT_E_INVALID, "rt_render_async: rank %u of world %u", rank, world);
+
+	// frame constants (RayTracer.cpp:13-15)
+	FrameParams &F = *c->hFrame;
+	memset(&F, 0, sizeof F);
+	F.cam_u = f4(cam.u), F.cam_v = f4(cam.v), F.cam_n = f4(cam.n), F.cam_pos = f4(cam.position);
+	F.dp = tan(cam.fovy * 3.1415926535897932384 / 360) / (H / 2);
+	F.zNear = cam.zNear, F.zFar = (float)(sqrt(2) * cam.zFar);
+	F.width = W, F.height = H, F.blk_w = W / 64, F.blk_h = H / 64, F.half_w = W / 2, F.half_h = H / 2;
+	F.max_level = p->max_level, F.type = p->type, F.rank = rank, F.world = world;
+	uint32_t bands = 0;
+	for (uint32_t t = 0; t < (uint32_t)F.blk_h; ++t) if (t % world == rank) ++bands;
+	F.n_rows = bands * 64;
+	F.n_lights = (uint32_t)c->lights.size();
+	F.env_light = f4(c->envLight);
+	uint32_t enabledLights = 0;
+	for (uint32_t k = 0; k < F.n_lights; ++k)
+	{
+		const rt_light &l = c->lights[k];
+		DevLight &d = F.lights[k];
+		d.position = f4(l.position), d.ambient = f4(l.ambient), d.diffuse = f4(l.diffuse), d.specular = f4(l.specular), d.attenuation = f4(l.attenuation);
+		d.type = l.type, d.enabled = l.enabled;
+		if (l.enabled) ++enabledLights;
+	}
+	const uint32_t nPix = (uint32_t)F.blk_w * 64u * F.n_rows;
+
+	// framebuffer: margins stay 127 (RayTracer.cpp:620)
+	if (c->outW != W || c->outH != H || !c->out.p)
+	{
+		CU(c->out.reserve((size_t)W * H * 3));
+		c->outW = W, c->outH = H;
+	}
+	CU(cudaMemsetAsync(c->out.p, 127, (size_t)W * H * 3, st));
+
+	const bool refr = c->anyRefract && p->type != RT_TYPE_REFLECT;
+	for (uint32_t l = 0; l <= p->max_level; ++l)
+	{
+		const uint32_t cap = l == 0 || !refr ? nPix : (uint32_t)std::min<double>((double)nPix * c->levelFactor, 4.0e9);
+		int rc = ensure_level(c, l, cap ? cap : 1, F.n_lights);
+		if (rc != RT_OK) return rc;
+	}
+	{ int rc = ensure_level(c, p->max_level + 1, 1, 1); if (rc != RT_OK) return rc; }
+
+	WaveState &Wv = *c->hWave;
+	memset(&Wv, 0, sizeof Wv);
+	Wv.count[0] = nPix;
+	CU(cudaMemcpyAsync(c->dFrame, c->hFrame, sizeof(FrameParams), cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(c->dWave, c->hWave, sizeof(WaveState), cudaMemcpyHostToDevice, st));
+	CU(cudaEventRecord(c->evStart, st));
+
+	const bool stats = (p->flags & RT_FLAG_STATS) != 0;
+	uint32_t launches = 0;
+	if (nPix)
+	{
+		rtk_raygen(st, c->dFrame, level_buf(c->levels[0]), nPix, c->sms); ++launches;
+		for (uint32_t l = 0; l <= p->max_level; ++l)
+		{
+			const LevelBuf L = level_buf(c->levels[l]), N = level_buf(c->levels[l + 1]);
+			const float zNear = l == 0 ? F.zNear : 0.0f;
+			const uint32_t maxRays = c->levels[l].capacity;
+			rtk_trace(st, c->S, L, &c->dWave->count[l], c->dWave, maxRays, c->sms, stats); ++launches;
+			if (enabledLights) { rtk_shadow(st, c->S, c->dFrame, L, &c->dWave->count[l], c->dWave, zNear, F.n_lights, maxRays, c->sms, stats); ++launches; }
+			rtk_shade(st, c->S, c->dFrame, L, N, c->dWave, l, zNear, maxRays, c->sms); ++launches;
+		}
+		for (int l = (int)p->max_level; l >= 0; --l)
+		{
+			rtk_combine(st, c->S, c->dFrame, level_buf(c->levels[l]), level_buf(c->levels[l + 1]), c->dWave, (uint32_t)l, c->out.p, c->levels[l].capacity, c->sms);
+			++launches;
+		}
+	}
+	CU(cudaGetLastError());
+	CU(cudaEventRecord(c->evStop, st));
+	CU(cudaMemcpyAsync(c->hWave, c->dWave, sizeof(WaveState), cudaMemcpyDeviceToHost, st));
+	CU(cudaEventRecord(c->evB, st));
+	c->lastParams = *p, c->lastPixels = nPix, c->lastLaunches = launches, c->lastMaxLevel = p->max_level;
+	c->frameInFlight = true, c->frameValid = false;
+	return RT_OK;
+}
+
+static int finish_frame(rt_ctx *c)
+{
+	CU(cudaSetDevice(c->device));
+	CU(cudaEventSynchronize(c->evB));
+	float ms = 0;
+	CU(cudaEventElapsedTime(&ms, c->evStart, c->evStop));
+	c->renderMs = ms;
+	c->frameInFlight = false;
+	if (c->hWave->overflow)
+		return fail(RT_E_LIMIT, "a ray level overflowed its queue (capacity factor %.2f); raise RT_B200_LEVEL_FACTOR", c->levelFactor);
+	c->frameValid = true;
+	return RT_OK;
+}
+
+extern "C" int rt_poll(rt_ctx *c, int *done, double *seconds)
+{
+	if (!c || !done) return fail(RT_E_INVALID, "rt_poll: NULL argument");
+	if (!c->frameInFlight) { *done = 1; if (seconds) *seconds = c->renderMs * 1e-3; return RT_OK; }
+	cudaSetDevice(c->device);
+	cudaError_t e = cudaEventQuery(c->evB);
+	if (e == cudaErrorNotReady) { *done = 0; return RT_OK; }
+	if (e != cudaSuccess) return fail(RT_E_CUDA, "rt_poll: %s", cudaGetErrorString(e));
+	int rc = finish_frame(c);
+	*done = 1;
+	if (seconds) *seconds = c->renderMs * 1e-3;
+	return rc;
+}
+
+extern "C" int rt_wait(rt_ctx *c, double *seconds)
+{
+	if (!c) return fail(RT_E_INVALID, "rt_wait: ctx is NULL");
+	int rc = RT_OK;
+	if (c->frameInFlight) rc = finish_frame(c);
+	if (seconds) *seconds = c->renderMs * 1e-3;
+	return rc;
+}
+
+// A frame is a few milliseconds of queued kernels; stop() lets it drain (RayTracer::stop only
+// asks the workers to return early, RayTracer.cpp:698-701).
+extern "C" int rt_stop(rt_ctx *c)
+{
+	if (!c) return fail(RT_E_INVALID, "rt_stop: ctx is NULL");
+	return RT_OK;
+}
+
+extern "C" int rt_read_output(rt_ctx *c, uint8_t *rgb, size_t stride)
+{
+	if (!c || !rgb) return fail(RT_E_INVALID, "rt_read_output: NULL argument");
+	if (c->frameInFlight) { int rc = finish_frame(c); if (rc != RT_OK) return rc; }
+	if (!c->out.p) return fail(RT_E_STATE, "rt_read_output: nothing rendered yet");
+	CU(cudaSetDevice(c->device));
+	const size_t row = (size_t)c->outW * 3;
+	if (stride < row) return fail(RT_E_INVALID, "rt_read_output: stride %zu < %zu", stride, row);
+	CU(cudaMemcpy2DAsync(rgb, stride, c->out.p, row, row, (size_t)c->outH, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	return RT_OK;
+}
+
+extern "C" int rt_output_device(rt_ctx *c, void **ptr, size_t *bytes)
+{
+	if (!c || !ptr) return fail(RT_E_INVALID, "rt_output_device: NULL argument");
+	if (!c->out.p) return fail(RT_E_STATE, "rt_output_device: nothing rendered yet");
+	*ptr = c->out.p;
+	if (bytes) *bytes = (size_t)c->outW * c->outH * 3;
+	return RT_OK;
+}
+
+extern "C" int rt_read_hit_ids(rt_ctx *c, rt_hit_id *ids)
+{
+	if (!c || !ids) return fail(RT_E_INVALID, "rt_read_hit_ids: NULL argument");
+	if (c->frameInFlight) { int rc = finish_frame(c); if (rc != RT_OK) return rc; }
+	if (!c->frameValid) return fail(RT_E_STATE, "rt_read_hit_ids: no finished frame");
+	CU(cudaSetDevice(c->device));
+	const uint32_t n = c->lastPixels;
+	std::vector<uint32_t> hid(n);
+	std::vector<float4> hp(n);
+	CU(cudaMemcpy(hid.data(), c->levels[0].hit_id.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	CU(cudaMemcpy(hp.data(), c->levels[0].hit_p.p, n * sizeof(float4), cudaMemcpyDeviceToHost));
+	const int W = c->outW, H = c->outH;
+	for (size_t i = 0; i < (size_t)W * H; ++i) ids[i] = rt_hit_id{ -1, -1, -1, -1, 1e20f };
+	const uint32_t world = c->lastParams.world > 1 ? c->lastParams.world : 1, rank = c->lastParams.world > 1 ? c->lastParams.rank : 0;
+	const uint32_t w64 = (uint32_t)(W / 64) * 64u, tilesX = w64 >> 3;
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		const uint32_t tile = i >> 6, in = i & 63u, tx = tile % tilesX, ty = tile / tilesX;
+		const uint32_t x = tx * 8u + (in & 7u), row = ty * 8u + (in >> 3), band = row >> 6;
+		const uint32_t y = ((band * world + rank) << 6) + (row & 63u);
+		rt_hit_id id = { -1, -1, -1, -1, hp[i].w };
+		const uint32_t h = hid[i];
+		if (h != RT_ID_NONE)
+		{
+			if (h & RT_ID_TRI)
+			{
+				const uint32_t t = h & 0x0FFFFFFFu;
+				for (const rt_model &M : c->models)
+				{
+					bool found = false;
+					for (uint32_t q = 0; q < M.part_count && !found; ++q)
+					{
+						const rt_part &P = c->parts[M.part_begin + q];
+						if (t >= P.tri_begin && t < P.tri_begin + P.tri_count)
+						{
+							id.object = (int32_t)M.object, id.sub = (int32_t)q, id.index = (int32_t)(t - P.tri_begin), id.octant = (int32_t)((h >> 28) & 7u);
+							found = true;
+						}
+					}
+					if (found) break;
+				}
+			}
+			else if (h < c->prims.size())
+				id.object = (int32_t)c->prims[h].object, id.sub = (int32_t)c->prims[h].sub;
+		}
+		ids[(size_t)y * W + x] = id;
+	}
+	return RT_OK;
+}
+
+extern "C" int rt_read_counters(rt_ctx *c, rt_counters *out)
+{
+	if (!c || !out) return fail(RT_E_INVALID, "rt_read_counters: NULL argument");
+	if (c->frameInFlight) { int rc = finish_frame(c); if (rc != RT_OK) return rc; }
+	memset(out, 0, sizeof *out);
+	out->upload_ms = c->uploadMs, out->build_ms = c->buildMs, out->bvh_nodes = c->bvhNodes, out->bvh_depth = c->bvhDepth;
+	if (!c->frameValid) return RT_OK;
+	const WaveState &W = *c->hWave;
+	uint32_t enabled = 0;
+	for (const rt_light &l : c->lights) if (l.enabled) ++enabled;
+	out->primary = W.count[0];
+	out->reflect = W.n_reflect, out->refract = W.n_refract;
+	out->shadow = W.n_hits * enabled;
+	out->nodes_visited = W.nodes_visited, out->tri_tests = W.tri_tests, out->prim_tests = W.prim_tests;
+	out->render_ms = c->renderMs;
+	out->launches = c->lastLaunches;
+	return RT_OK;
+}

@@ -1,0 +1,380 @@
+// GPU LBVH build: Morton codes -> radix sort -> Karras (2012) hierarchy -> bottom-up refit that
+// emits 64-byte two-child nodes.  Replaces the reference's per-frame, single-threaded octant
+// binning (Model::RTPrepare, /root/reference/Model.cpp:402-480); the octant membership itself is
+// still computed (bit-exactly) per triangle in k_prepare_tris because the traversal replays the
+// reference's culling predicate with it.
+#include "rt_kernels.h"
+#include "rt_intersect.cuh"
+#include <cub/device/device_radix_sort.cuh>
+#include <cstdio>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
+
+struct BuildScratch
+{
+	uint32_t cap = 0;
+	unsigned long long *keysIn = nullptr, *keysOut = nullptr;
+	uint32_t *valsIn = nullptr, *valsOut = nullptr;
+	void *cubTemp = nullptr;
+	size_t cubBytes = 0;
+	int *bounds = nullptr;          // 6 ordered-int floats: min xyz, max xyz
+	int *parentOfInternal = nullptr, *parentOfLeaf = nullptr;
+	int2 *children = nullptr;       // per internal: left, right (>=0 internal, <0: ~leaf)
+	int2 *range = nullptr;          // per internal: first, last leaf (inclusive)
+	uint32_t *flags = nullptr;
+	float4 *ilo = nullptr, *ihi = nullptr;   // internal node boxes
+	uint32_t *height = nullptr;
+};
+
+void rtb_free_scratch(BuildScratch *s)
+{
+	if (!s) return;
+	cudaFree(s->keysIn), cudaFree(s->keysOut), cudaFree(s->valsIn), cudaFree(s->valsOut), cudaFree(s->cubTemp);
+	cudaFree(s->bounds), cudaFree(s->parentOfInternal), cudaFree(s->parentOfLeaf), cudaFree(s->children), cudaFree(s->range);
+	cudaFree(s->flags), cudaFree(s->ilo), cudaFree(s->ihi), cudaFree(s->height);
+	delete s;
+}
+
+static int ensure_scratch(BuildScratch **ps, uint32_t n)
+{
+	if (!*ps) *ps = new BuildScratch();
+	BuildScratch *s = *ps;
+	if (n <= s->cap) return 0;
+	BuildScratch fresh;
+	cudaFree(s->keysIn), cudaFree(s->keysOut), cudaFree(s->valsIn), cudaFree(s->valsOut), cudaFree(s->cubTemp);
+	cudaFree(s->bounds), cudaFree(s->parentOfInternal), cudaFree(s->parentOfLeaf), cudaFree(s->children), cudaFree(s->range);
+	cudaFree(s->flags), cudaFree(s->ilo), cudaFree(s->ihi), cudaFree(s->height);
+	*s = fresh;
+	const uint32_t cap = n + n / 8 + 1024;
+	CK(cudaMalloc(&s->keysIn, sizeof(unsigned long long) * cap));
+	CK(cudaMalloc(&s->keysOut, sizeof(unsigned long long) * cap));
+	CK(cudaMalloc(&s->valsIn, sizeof(uint32_t) * cap));
+	CK(cudaMalloc(&s->valsOut, sizeof(uint32_t) * cap));
+	s->cubBytes = 0;
+	cub::DeviceRadixSort::SortPairs(nullptr, s->cubBytes, s->keysIn, s->keysOut, s->valsIn, s->valsOut, (int)cap);
+	CK(cudaMalloc(&s->cubTemp, s->cubBytes));
+	CK(cudaMalloc(&s->bounds, sizeof(int) * 8));
+	CK(cudaMalloc(&s->parentOfInternal, sizeof(int) * cap));
+	CK(cudaMalloc(&s->parentOfLeaf, sizeof(int) * cap));
+	CK(cudaMalloc(&s->children, sizeof(int2) * cap));
+	CK(cudaMalloc(&s->range, sizeof(int2) * cap));
+	CK(cudaMalloc(&s->flags, sizeof(uint32_t) * cap));
+	CK(cudaMalloc(&s->ilo, sizeof(float4) * cap));
+	CK(cudaMalloc(&s->ihi, sizeof(float4) * cap));
+	CK(cudaMalloc(&s->height, sizeof(uint32_t) * cap));
+	s->cap = cap;
+	return 0;
+}
+
+// order-preserving float <-> int so atomicMin/atomicMax work on floats
+__device__ __forceinline__ int f2ord(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7FFFFFFF; }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
+
+// ---- triangle preparation (Model::RTPrepare on the GPU) ------------------------------------------
+
+__global__ void k_prepare_tris(TriPrepArgs a)
+{
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= a.n) return;
+	const uint32_t part = a.tri_part[t];
+	const F3 pos = f3(a.part_position[part]);
+	const F3 p0 = f3(a.points[3 * t]), p1 = f3(a.points[3 * t + 1]), p2 = f3(a.points[3 * t + 2]);
+	// clTri(t.points[1]-t.points[0], t.points[2]-t.points[0], t.points[0]+position), Model.cpp:426
+	const F3 e1 = p1 - p0, e2 = p2 - p0, p0w = p0 + pos;
+	// octant membership against the part's box centre, untranslated coordinates, Model.cpp:421,430-465
+	const F3 va = f3(a.part_mid_pos[part]);
+	const float tminx = sse_min(p0.x, sse_min(p1.x, p2.x)), tminy = sse_min(p0.y, sse_min(p1.y, p2.y)), tminz = sse_min(p0.z, sse_min(p1.z, p2.z));
+	const float tmaxx = sse_max(p0.x, sse_max(p1.x, p2.x)), tmaxy = sse_max(p0.y, sse_max(p1.y, p2.y)), tmaxz = sse_max(p0.z, sse_max(p1.z, p2.z));
+	uint32_t octs = 0;
+	const bool ylo = tminy <= va.y, yhi = tmaxy >= va.y;
+	if (tminx <= va.x)
+	{
+		if (tminz <= va.z) octs |= (ylo ? 1u : 0u) | (yhi ? 2u : 0u);
+		if (tmaxz >= va.z) octs |= (ylo ? 4u : 0u) | (yhi ? 8u : 0u);
+	}
+	if (tmaxx >= va.x)
+	{
+		if (tminz <= va.z) octs |= (ylo ? 16u : 0u) | (yhi ? 32u : 0u);
+		if (tmaxz >= va.z) octs |= (ylo ? 64u : 0u) | (yhi ? 128u : 0u);
+	}
+	a.tri_geom_orig[3 * t] = make_float4(e1.x, e1.y, e1.z, __uint_as_float(t + a.id_base));
+	a.tri_geom_orig[3 * t + 1] = make_float4(e2.x, e2.y, e2.z, __uint_as_float((part << 8) | octs));
+	a.tri_geom_orig[3 * t + 2] = make_float4(p0w.x, p0w.y, p0w.z, 0.0f);
+	// conservative world box of the triangle the hit test actually sees: p0w, p0w+e1, p0w+e2
+	const F3 q1 = p0w + e1, q2 = p0w + e2;
+	F3 lo = f3(fminf(p0w.x, fminf(q1.x, q2.x)), fminf(p0w.y, fminf(q1.y, q2.y)), fminf(p0w.z, fminf(q1.z, q2.z)));
+	F3 hi = f3(fmaxf(p0w.x, fmaxf(q1.x, q2.x)), fmaxf(p0w.y, fmaxf(q1.y, q2.y)), fmaxf(p0w.z, fmaxf(q1.z, q2.z)));
+	const float mag = fmaxf(fmaxf(fmaxf(fabsf(lo.x), fabsf(hi.x)), fmaxf(fabsf(lo.y), fabsf(hi.y))), fmaxf(fabsf(lo.z), fabsf(hi.z)));
+	const float pad = mag * 4e-6f + 1e-7f;
+	a.box_lo[t] = make_float4(lo.x - pad, lo.y - pad, lo.z - pad, 0);
+	a.box_hi[t] = make_float4(hi.x + pad, hi.y + pad, hi.z + pad, 0);
+}
+
+void rtb_prepare_tris(cudaStream_t st, const TriPrepArgs &a)
+{
+	if (a.n) k_prepare_tris<<<(a.n + 255) / 256, 256, 0, st>>>(a);
+}
+
+__global__ void k_prim_boxes(PrimBoxArgs a)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= a.n) return;
+	const uint32_t p = a.first + i;
+	const int kind = a.prim_meta[p].x;
+	F3 lo, hi;
+	if (kind == RT_OBJ_SPHERE)
+	{
+		const float4 g = a.prim_geom[4 * p];
+		lo = f3(g.x - g.w, g.y - g.w, g.z - g.w), hi = f3(g.x + g.w, g.y + g.w, g.z + g.w);
+	}
+	else
+		lo = f3(a.prim_geom[4 * p + 1]), hi = f3(a.prim_geom[4 * p + 2]);
+	const float mag = fmaxf(fmaxf(fmaxf(fabsf(lo.x), fabsf(hi.x)), fmaxf(fabsf(lo.y), fabsf(hi.y))), fmaxf(fabsf(lo.z), fabsf(hi.z)));
+	const float pad = mag * 8e-6f + 1e-6f;
+	a.box_lo[i] = make_float4(lo.x - pad, lo.y - pad, lo.z - pad, 0);
+	a.box_hi[i] = make_float4(hi.x + pad, hi.y + pad, hi.z + pad, 0);
+}
+
+void rtb_prim_boxes(cudaStream_t st, const PrimBoxArgs &a)
+{
+	if (a.n) k_prim_boxes<<<(a.n + 255) / 256, 256, 0, st>>>(a);
+}
+
+// ---- Morton codes --------------------------------------------------------------------------------
+
+__global__ void k_init_bounds(int *b)
+{
+	if (threadIdx.x < 3) b[threadIdx.x] = 0x7F7FFFFF;              // +FLT_MAX ordered
+	else if (threadIdx.x < 6) b[threadIdx.x] = f2ord(-3.4e38f);
+}
+
+__global__ void k_bounds(const float4 *lo, const float4 *hi, uint32_t n, int *b)
+{
+	float mn[3] = { 3.4e38f, 3.4e38f, 3.4e38f }, mx[3] = { -3.4e38f, -3.4e38f, -3.4e38f };
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+	{
+		const float4 l = lo[i], h = hi[i];
+		const float cx = 0.5f * (l.x + h.x), cy = 0.5f * (l.y + h.y), cz = 0.5f * (l.z + h.z);
+		mn[0] = fminf(mn[0], cx), mn[1] = fminf(mn[1], cy), mn[2] = fminf(mn[2], cz);
+		mx[0] = fmaxf(mx[0], cx), mx[1] = fmaxf(mx[1], cy), mx[2] = fmaxf(mx[2], cz);
+	}
+	for (int k = 0; k < 3; ++k)
+	{
+		for (int o = 16; o > 0; o >>= 1)
+		{
+			mn[k] = fminf(mn[k], __shfl_down_sync(0xffffffffu, mn[k], o));
+			mx[k] = fmaxf(mx[k], __shfl_down_sync(0xffffffffu, mx[k], o));
+		}
+		if ((threadIdx.x & 31) == 0)
+		{
+			atomicMin(&b[k], f2ord(mn[k]));
+			atomicMax(&b[3 + k], f2ord(mx[k]));
+		}
+	}
+}
+
+__device__ __forceinline__ unsigned long long spread21(unsigned long long v)
+{
+	v &= 0x1FFFFFull;
+	v = (v | v << 32) & 0x1F00000000FFFFull;
+	v = (v | v << 16) & 0x1F0000FF0000FFull;
+	v = (v | v << 8) & 0x100F00F00F00F00Full;
+	v = (v | v << 4) & 0x10C30C30C30C30C3ull;
+	v = (v | v << 2) & 0x1249249249249249ull;
+	return v;
+}
+
+__global__ void k_morton(const float4 *lo, const float4 *hi, uint32_t n, const int *b, unsigned long long *keys, uint32_t *vals)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const float bx = ord2f(b[0]), by = ord2f(b[1]), bz = ord2f(b[2]);
+	const float ex = fmaxf(ord2f(b[3]) - bx, 1e-30f), ey = fmaxf(ord2f(b[4]) - by, 1e-30f), ez = fmaxf(ord2f(b[5]) - bz, 1e-30f);
+	const float4 l = lo[i], h = hi[i];
+	const float scale = 2097151.0f;   // 2^21 - 1
+	const float fx = (0.5f * (l.x + h.x) - bx) / ex, fy = (0.5f * (l.y + h.y) - by) / ey, fz = (0.5f * (l.z + h.z) - bz) / ez;
+	const unsigned long long qx = (unsigned long long)fminf(fmaxf(fx * scale, 0.0f), scale);
+	const unsigned long long qy = (unsigned long long)fminf(fmaxf(fy * scale, 0.0f), scale);
+	const unsigned long long qz = (unsigned long long)fminf(fmaxf(fz * scale, 0.0f), scale);
+	keys[i] = spread21(qx) << 2 | spread21(qy) << 1 | spread21(qz);
+	vals[i] = i;
+}
+
+// ---- Karras hierarchy ----------------------------------------------------------------------------
+
+__device__ __forceinline__ int delta(const unsigned long long *keys, int n, int i, int j)
+{
+	if (j < 0 || j >= n) return -1;
+	const unsigned long long a = keys[i], b = keys[j];
+	if (a == b) return 64 + __clz(i ^ j);
+	return __clzll((long long)(a ^ b));
+}
+
+__global__ void k_karras(const unsigned long long *keys, int n, int2 *children, int2 *range, int *parentOfInternal, int *parentOfLeaf)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n - 1) return;
+	const int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+	const int dmin = delta(keys, n, i, i - d);
+	int lmax = 2;
+	while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+	int l = 0;
+	for (int t = lmax >> 1; t >= 1; t >>= 1)
+		if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+	const int j = i + l * d;
+	const int dnode = delta(keys, n, i, j);
+	int s = 0, t = l;
+	do
+	{
+		t = (t + 1) >> 1;
+		if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+	} while (t > 1);
+	const int gamma = i + s * d + min(d, 0);
+	const int lo = min(i, j), hi = max(i, j);
+	const int left = (lo == gamma) ? ~gamma : gamma;
+	const int right = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+	children[i] = make_int2(left, right);
+	range[i] = make_int2(lo, hi);
+	if (left >= 0) parentOfInternal[left] = i; else parentOfLeaf[~left] = i;
+	if (right >= 0) parentOfInternal[right] = i; else parentOfLeaf[~right] = i;
+	if (i == 0) parentOfInternal[0] = -1;
+}
+
+// ---- bottom-up refit + node emission -------------------------------------------------------------
+
+struct RefitArgs
+{
+	const float4 *box_lo, *box_hi;   // input boxes (unsorted)
+	const uint32_t *sorted;          // leaf slot -> input index
+	const int2 *children, *range;
+	const int *parentOfInternal, *parentOfLeaf;
+	uint32_t *flags;
+	float4 *ilo, *ihi;
+	uint32_t *height;
+	BvhNode *nodes;
+	uint32_t nodeBase, leafBase, leafSize;
+	int n;
+};
+
+__device__ __forceinline__ int child_link(const RefitArgs &a, int child)
+{
+	if (child < 0)
+		return (int)(0x80000000u | ((a.leafBase + (uint32_t)(~child)) << 3));
+	const int2 r = a.range[child];
+	const uint32_t cnt = (uint32_t)(r.y - r.x + 1);
+	if (cnt <= a.leafSize)
+		return (int)(0x80000000u | ((a.leafBase + (uint32_t)r.x) << 3) | (cnt - 1u));
+	return (int)(a.nodeBase + (uint32_t)child);
+}
+
+__global__ void k_refit(RefitArgs a)
+{
+	const int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+	if (leaf >= a.n) return;
+	int node = a.parentOfLeaf[leaf];
+	while (node >= 0)
+	{
+		// the second thread to arrive owns the node; its sibling subtree is complete and visible
+		if (atomicAdd(&a.flags[node], 1u) == 0u)
+			return;
+		__threadfence();
+		const int2 ch = a.children[node];
+		float4 l0, h0, l1, h1;
+		uint32_t hgt0 = 0, hgt1 = 0;
+		if (ch.x < 0) { const uint32_t s = a.sorted[~ch.x]; l0 = a.box_lo[s], h0 = a.box_hi[s]; }
+		else { l0 = __ldcg(&a.ilo[ch.x]), h0 = __ldcg(&a.ihi[ch.x]), hgt0 = __ldcg(&a.height[ch.x]); }   // L2 reads: written by another SM
+		if (ch.y < 0) { const uint32_t s = a.sorted[~ch.y]; l1 = a.box_lo[s], h1 = a.box_hi[s]; }
+		else { l1 = __ldcg(&a.ilo[ch.y]), h1 = __ldcg(&a.ihi[ch.y]), hgt1 = __ldcg(&a.height[ch.y]); }
+		const int link0 = child_link(a, ch.x), link1 = child_link(a, ch.y);
+		if (link0 < 0) hgt0 = 0;
+		if (link1 < 0) hgt1 = 0;
+		BvhNode out;
+		out.a = make_float4(l0.x, l0.y, l0.z, h0.x);
+		out.b = make_float4(h0.y, h0.z, l1.x, l1.y);
+		out.c = make_float4(l1.z, h1.x, h1.y, h1.z);
+		out.link = make_int4(link0, link1, 0, 0);
+		a.nodes[a.nodeBase + node] = out;
+		a.ilo[node] = make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), 0);
+		a.ihi[node] = make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0);
+		a.height[node] = 1u + max(hgt0, hgt1);
+		__threadfence();
+		node = a.parentOfInternal[node];
+	}
+}
+
+__global__ void k_copy_order(const uint32_t *sorted, uint32_t n, uint32_t *out)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = sorted[i];
+}
+
+int rtb_build(cudaStream_t st, BuildScratch **scratch, const float4 *box_lo, const float4 *box_hi, uint32_t n,
+	uint32_t leafSize, BvhNode *nodes, uint32_t nodeBase, uint32_t leafBase, uint32_t *leafOrder, BvhBuildResult *res)
+{
+	if (n == 0) { res->root = 0, res->nodesUsed = 0, res->depth = 0; return 0; }
+	if (leafSize < 1) leafSize = 1;
+	if (leafSize > 8) leafSize = 8;
+	int rc = ensure_scratch(scratch, n);
+	if (rc) return rc;
+	BuildScratch *s = *scratch;
+	const unsigned blocks = (n + 255) / 256;
+	k_init_bounds<<<1, 32, 0, st>>>(s->bounds);
+	k_bounds<<<blocks < 1024 ? blocks : 1024, 256, 0, st>>>(box_lo, box_hi, n, s->bounds);
+	k_morton<<<blocks, 256, 0, st>>>(box_lo, box_hi, n, s->bounds, s->keysIn, s->valsIn);
+	size_t bytes = s->cubBytes;
+	CK(cub::DeviceRadixSort::SortPairs(s->cubTemp, bytes, s->keysIn, s->keysOut, s->valsIn, s->valsOut, (int)n, 0, 63, st));
+	k_copy_order<<<blocks, 256, 0, st>>>(s->valsOut, n, leafOrder);
+	if (n <= leafSize)
+	{
+		res->root = (int)(0x80000000u | (leafBase << 3) | (n - 1u));
+		res->nodesUsed = 0, res->depth = 0;
+		return (int)cudaGetLastError();
+	}
+	k_karras<<<blocks, 256, 0, st>>>(s->keysOut, (int)n, s->children, s->range, s->parentOfInternal, s->parentOfLeaf);
+	CK(cudaMemsetAsync(s->flags, 0, sizeof(uint32_t) * n, st));
+	RefitArgs a;
+	a.box_lo = box_lo, a.box_hi = box_hi, a.sorted = s->valsOut, a.children = s->children, a.range = s->range;
+	a.parentOfInternal = s->parentOfInternal, a.parentOfLeaf = s->parentOfLeaf, a.flags = s->flags;
+	a.ilo = s->ilo, a.ihi = s->ihi, a.height = s->height, a.nodes = nodes;
+	a.nodeBase = nodeBase, a.leafBase = leafBase, a.leafSize = leafSize, a.n = (int)n;
+	k_refit<<<blocks, 256, 0, st>>>(a);
+	uint32_t depth = 0;
+	CK(cudaMemcpyAsync(&depth, s->height, sizeof depth, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	res->root = (int)nodeBase;
+	res->nodesUsed = n - 1;
+	res->depth = depth;
+	return (int)cudaGetLastError();
+}
+
+// ---- leaf-order scatter --------------------------------------------------------------------------
+
+__global__ void k_scatter_tris(const float4 *geomOrig, const uint32_t *leafOrder, uint32_t leafBase, uint32_t origBase, uint32_t n,
+	float4 *geomLeaf, uint32_t *triSlot)
+{
+	const uint32_t sIdx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (sIdx >= n) return;
+	const uint32_t orig = origBase + leafOrder[sIdx];   // leafOrder holds indices local to this model
+	const uint32_t slot = leafBase + sIdx;
+	geomLeaf[3 * slot] = geomOrig[3 * orig];
+	geomLeaf[3 * slot + 1] = geomOrig[3 * orig + 1];
+	geomLeaf[3 * slot + 2] = geomOrig[3 * orig + 2];
+	triSlot[orig] = slot;
+}
+
+void rtb_scatter_tris(cudaStream_t st, const float4 *geomOrig, const uint32_t *leafOrder, uint32_t leafBase, uint32_t origBase, uint32_t n,
+	float4 *geomLeaf, uint32_t *triSlot)
+{
+	if (n) k_scatter_tris<<<(n + 255) / 256, 256, 0, st>>>(geomOrig, leafOrder, leafBase, origBase, n, geomLeaf, triSlot);
+}
+
+__global__ void k_offset_order(uint32_t *order, uint32_t n, uint32_t add)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) order[i] += add;
+}
+
+void rtb_offset_order(cudaStream_t st, uint32_t *order, uint32_t n, uint32_t add)
+{
+	if (n) k_offset_order<<<(n + 255) / 256, 256, 0, st>>>(order, n, add);
+}

@@ -1,0 +1,134 @@
+// Device-side scene layout and the bit-exact FP32 element math.
+//
+// Everything in the "parity" section reproduces the reference's operation order, one IEEE
+// rounding per source-level operation (this translation unit is compiled with -fmad=false, so
+// nvcc never contracts a*b+c; the conservative BVH slab code asks for FMA explicitly):
+//   dot   = (x0*y0 + x1*y1) + x2*y2          dpps 0x71, /root/reference/3DElement.cpp:206-214
+//           (the reference adds +0.0f to the z product; that only changes the sign of an
+//            exact zero and is dropped on the device)
+//   cross = (a.y*b.z - a.z*b.y, ...)          3DElement.cpp:190-197
+//   normalise = v / sqrt(dot)  IEEE div/sqrt  3DElement.cpp:218-238
+//   v / s  = v * (1/s)                        3DElement.cpp:137-147
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/rt_b200.h"
+
+#define RT_ID_NONE 0xFFFFFFFFu
+#define RT_ID_TRI  0x80000000u
+#define RT_MAX_LIGHTS 8
+#define RT_MAX_LEVELS 16
+#define RT_STACK 64
+
+struct F3 { float x, y, z; };
+
+__device__ __forceinline__ F3 f3(float x, float y, float z) { return F3{ x, y, z }; }
+__device__ __forceinline__ F3 f3(const float4 &v) { return F3{ v.x, v.y, v.z }; }
+__device__ __forceinline__ F3 operator+(const F3 &a, const F3 &b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ F3 operator-(const F3 &a, const F3 &b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ F3 operator*(const F3 &a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ F3 mixmul(const F3 &a, const F3 &b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ float dot(const F3 &a, const F3 &b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__device__ __forceinline__ F3 cross(const F3 &a, const F3 &b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ F3 normalize(const F3 &v)
+{
+	const float len = sqrtf(dot(v, v));
+	return f3(v.x / len, v.y / len, v.z / len);
+}
+// SSE min/max (second operand on NaN/equal) and std::min/std::max as the reference calls them
+__device__ __forceinline__ float sse_min(float a, float b) { return a < b ? a : b; }
+__device__ __forceinline__ float sse_max(float a, float b) { return a > b ? a : b; }
+__device__ __forceinline__ float std_min(float a, float b) { return b < a ? b : a; }
+__device__ __forceinline__ float std_max(float a, float b) { return a < b ? b : a; }
+
+// float images of the reference's double-literal comparisons (t > 1e-6, |a| < 1e-6):
+// 0x358637BD = 9.99999997e-7f is the largest float below 1e-6, so for float x
+//   x > 1e-6  <=>  x > 9.99999997e-7f      and      x < 1e-6  <=>  x <= 9.99999997e-7f
+#define RT_EPS6_BELOW 9.99999997e-7f
+__device__ __forceinline__ bool gt_1em6(float x) { return x > RT_EPS6_BELOW; }
+__device__ __forceinline__ bool lt_1em6(float x) { return x <= RT_EPS6_BELOW; }
+
+// ---- flattened scene, device pointers --------------------------------------------------------
+
+struct DevLight
+{
+	float4 position, ambient, diffuse, specular, attenuation;
+	uint32_t type, enabled, pad0, pad1;
+};
+
+// per-frame constants (device memory, rewritten by every rt_render_async)
+struct FrameParams
+{
+	float4 cam_u, cam_v, cam_n, cam_pos;
+	double dp;                 // tan(fovy*pi/360)/(height/2), RayTracer.cpp:14
+	float zNear, zFar;         // zFar = float(sqrt(2)*cam.zFar), RayTracer.cpp:15
+	int width, height;         // latched frame size
+	int blk_w, blk_h;          // 64x64 tiles actually rendered
+	int half_w, half_h;        // width/2, height/2 (integer division)
+	uint32_t max_level, type;
+	uint32_t rank, world;
+	uint32_t n_rows;           // rows rendered by this shard
+	uint32_t n_lights;
+	float4 env_light;
+	DevLight lights[RT_MAX_LIGHTS];
+};
+
+struct SceneItem   // one entry of the scene-order walk (RayTracer.cpp:458)
+{
+	uint32_t kind;      // 0 = single analytic primitive, 1 = BVH over a run of primitives, 2 = Model
+	uint32_t first;     // prim flat index / first prim of the run / model index
+	uint32_t count;     // run length
+	int32_t root;       // BVH root node (kinds 1, 2)
+};
+#define RT_ITEM_PRIM 0u
+#define RT_ITEM_PRIMBVH 1u
+#define RT_ITEM_MODEL 2u
+
+struct DevModel
+{
+	float4 border_min, border_max;   // VerMin/VerMax + position (Model.cpp:404)
+	uint32_t part_begin, part_count, tri_begin, tri_count;
+	uint32_t object, pad0, pad1, pad2;
+};
+
+struct DevPart
+{
+	float4 box_min, box_max;         // borders + position (Model.cpp:418-419)
+	uint32_t tri_begin, tri_count, material;
+	int32_t texture;
+};
+
+struct BvhNode   // 64 bytes: both children's boxes + links, fetched as 4 x 128-bit loads
+{
+	float4 a;    // c0.lo.xyz, c0.hi.x
+	float4 b;    // c0.hi.yz, c1.lo.xy
+	float4 c;    // c1.lo.z, c1.hi.xyz
+	int4 link;   // child0, child1 (>=0 node, <0 leaf: 0x80000000 | first<<3 | (count-1)), unused
+};
+
+struct SceneDev
+{
+	// analytic primitives: 4 float4 + 1 int4 each
+	const float4 *prim_geom;     // [4*i+0] pos.xyz,radius  [1] sphere: r2 | box: wmin | plane: normal  [2] box: wmax | plane: axisx  [3] box: lmax | plane: axisy
+	const int4 *prim_meta;       // kind, material, texture, object<<8|sub
+	const uint32_t *bvh_prims;   // leaf order -> prim flat index (prim-run BVHs)
+	// materials: 4 float4 each (ambient, diffuse, specular, {shiness, reflect, refract, rfr})
+	const float4 *materials;
+	const int4 *textures;        // w, h, offset, -
+	const uint8_t *texels;
+	// models
+	const DevModel *models;
+	const DevPart *parts;
+	// triangles in BVH leaf order: e1|id, e2|part<<8|octmask, p0|-   (clTri, 3DElement.h:122-127)
+	const float4 *tri_geom;
+	// shading data in original (part, index) order
+	const float4 *tri_norms;     // 3 per triangle
+	const float2 *tri_tcoords;   // 3 per triangle
+	const uint32_t *tri_slot;    // original index -> leaf-order slot (to re-run the hit test when shading)
+	const uint32_t *tri_part;    // original index -> global part index
+	const BvhNode *nodes;
+	const SceneItem *items;
+	uint32_t n_items, n_prims, n_tris, n_parts;
+};
+
+__device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }

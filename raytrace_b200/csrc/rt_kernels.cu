@@ -1,0 +1,470 @@
+// Wavefront kernels of the trace-and-shade path (sm_100a, compiled with -fmad=false):
+//
+//   k_raygen        RayTracer::parallelRT pixel loop          /root/reference/RayTracer.cpp:20-27
+//   k_trace         closest-hit walk of one ray level         RayTracer.cpp:455-465 (+ all intersect operators)
+//   k_shadow        one any-hit query per (hit, light)        RayTracer.cpp:482-520
+//   k_shade         Blinn-Phong + spawn reflect/refract rays  RayTracer.cpp:467-592 (pre-order half)
+//   k_combine       post-order colour combine + Color::put    RayTracer.cpp:552-594, 3DElement.cpp:463-468
+//
+// The reference recursion (binary ray tree per pixel) is unrolled level by level: level l holds
+// every ray whose recursion depth is l; a ray's slot index is also its ray-tree node index, and
+// each node remembers the slots of its two children in level l+1.  Shading stores the node-local
+// colour; k_combine then walks the levels bottom-up and applies exactly the reference's
+// c = c*(1-kr) + c_refl*kr ; c = c*(1-kt) + (c_refr (*) beer)*kt sequence, so the colour
+// arithmetic is bit-identical to the recursive evaluation order.
+#include "rt_traverse.cuh"
+#include "rt_kernels.h"
+
+// ---- helpers -------------------------------------------------------------------------------------
+
+// level-0 slot -> pixel: slots are laid out in 8x8 pixel tiles so a warp covers an 8x4 block
+__device__ __forceinline__ void slot_to_pixel(const FrameParams &F, uint32_t i, int &x, int &y)
+{
+	const uint32_t w64 = (uint32_t)F.blk_w * 64u;
+	const uint32_t tile = i >> 6, in = i & 63u;
+	const uint32_t tiles_x = w64 >> 3;
+	const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
+	x = (int)(tx * 8u + (in & 7u));
+	const uint32_t row = ty * 8u + (in >> 3);            // row among this shard's rows
+	const uint32_t band = row >> 6;                       // 64-row tile among this shard's tiles
+	y = (int)(((band * F.world + F.rank) << 6) + (row & 63u));
+}
+
+__device__ __forceinline__ uint8_t put8(float c)
+{
+	// Color::put: clamp with strict compares, truncate; NaN -> 0 (x86 cvttss2si low byte)
+	if (c > 1.0f) return 255;
+	if (c < 0.0f) return 0;
+	const float v = c * 255;
+	if (!(v == v)) return 0;
+	return (uint8_t)v;
+}
+
+// Color(const Texture*, Coord2D), 3DElement.cpp:430-450
+__device__ __forceinline__ F3 texel(const SceneDev &S, int tex, float cu, float cv)
+{
+	if (tex < 0)
+		return f3(1.0f, 1.0f, 1.0f);
+	const int4 T = __ldg(&S.textures[tex]);
+	float whole;
+	float nu = modff(cu, &whole), nv = modff(cv, &whole);
+	if (nu < 0) nu += 1;
+	if (nv < 0) nv += 1;
+	const int x = (int)(short)(int)(nu * (float)T.x), y = (int)(short)(int)(nv * (float)T.y);
+	const uint8_t *px = S.texels + (uint32_t)T.z + (y * T.x + x) * 3;
+	return f3(px[2] / 255.0f, px[1] / 255.0f, px[0] / 255.0f);
+}
+
+// pow(float,float) / exp(float) of the host libm are within a fraction of an ulp of correctly
+// rounded; FP64 evaluation rounded once reproduces them (DESIGN.md "transcendentals").
+__device__ __forceinline__ float pow_ref(float a, float b) { return (float)pow((double)a, (double)b); }
+__device__ __forceinline__ float exp_ref(float a) { return (float)exp((double)a); }
+
+__device__ __forceinline__ RayD load_ray(const LevelBuf &L, uint32_t i)
+{
+	const float4 o = L.ray_o[i], d = L.ray_d[i];
+	const uint2 m = L.ray_meta[i];
+	RayD r;
+	r.o = f3(o), r.d = f3(d), r.mtlrfr = o.w;
+	r.skip = m.x, r.type = (uint8_t)(m.y & 0xFF), r.isInside = (uint8_t)((m.y >> 8) & 0xFF);
+	return r;
+}
+
+template<bool STATS>
+__device__ __forceinline__ void flush_stats(WaveState *ws, const TravStats &st)
+{
+	if (!STATS) return;
+	unsigned long long n = st.nodes, t = st.tris, p = st.prims;
+	for (int o = 16; o > 0; o >>= 1)
+	{
+		n += __shfl_down_sync(0xffffffffu, n, o);
+		t += __shfl_down_sync(0xffffffffu, t, o);
+		p += __shfl_down_sync(0xffffffffu, p, o);
+	}
+	if ((threadIdx.x & 31) == 0)
+	{
+		atomicAdd(&ws->nodes_visited, n);
+		atomicAdd(&ws->tri_tests, t);
+		atomicAdd(&ws->prim_tests, p);
+	}
+}
+
+// ---- ray generation ------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) k_raygen(const FrameParams *__restrict__ Fp, LevelBuf L, uint32_t n)
+{
+	const FrameParams &F = *Fp;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+	{
+		int x, y;
+		slot_to_pixel(F, i, x, y);
+		const int xcur = x - F.half_w, ycur = y - F.half_h;
+		const float sx = (float)(xcur * F.dp), sy = (float)(ycur * F.dp);
+		// dir = cam.n + cam.u*(xcur*dp) + cam.v*(ycur*dp), then Ray() normalises
+		const F3 dir = (f3(F.cam_n) + f3(F.cam_u) * sx) + f3(F.cam_v) * sy;
+		const F3 d = normalize(dir);
+		L.ray_o[i] = make_float4(F.cam_pos.x, F.cam_pos.y, F.cam_pos.z, 1.0f);
+		L.ray_d[i] = make_float4(d.x, d.y, d.z, 1.0f);
+		L.ray_meta[i] = make_uint2(RT_ID_NONE, (uint32_t)MY_RAY_BASERAY_);
+	}
+}
+
+// ---- closest hit ---------------------------------------------------------------------------------
+
+template<bool STATS>
+__global__ void __launch_bounds__(RT_BLOCK) k_trace(SceneDev S, LevelBuf L, const uint32_t *__restrict__ count, WaveState *ws)
+{
+	__shared__ int s_stack[RT_STACK * RT_BLOCK];
+	int *stack = s_stack + threadIdx.x;
+	const uint32_t n = *count < L.capacity ? *count : L.capacity;
+	TravStats st = { 0, 0, 0 };
+	for (uint32_t i = blockIdx.x * RT_BLOCK + threadIdx.x; i < n; i += gridDim.x * RT_BLOCK)
+	{
+		const RayD ray = load_ray(L, i);
+		Best best = { 1e20f, RT_ID_NONE };
+		bool done = false;
+		trace_scene<false, STATS>(S, ray, stack, best, done, st);
+		const F3 P = ray.o + ray.d * best.t;
+		L.hit_p[i] = make_float4(P.x, P.y, P.z, best.t);
+		L.hit_id[i] = best.id;
+	}
+	flush_stats<STATS>(ws, st);
+}
+
+// ---- shadow any-hit ------------------------------------------------------------------------------
+
+// light k as seen from P: direction p2l and occlusion range (RayTracer.cpp:482-503)
+__device__ __forceinline__ void light_dir(const DevLight &lit, const F3 &P, F3 &p2l, float &dis, float &lum)
+{
+	if (lit.type == RT_LIGHT_POINT)
+	{
+		const F3 v = f3(lit.position) - P;
+		dis = dot(v, v);
+		float step = lit.attenuation.x + lit.attenuation.z * dis;
+		dis = sqrtf(dis);
+		step += lit.attenuation.y * dis;
+		lum = 1 / step;
+		p2l = normalize(v);
+	}
+	else
+	{
+		dis = 1e10f;
+		lum = 1.0f;   // parallel and spot lights are used unattenuated
+		p2l = normalize(f3(lit.position));
+	}
+}
+
+template<bool STATS>
+__global__ void __launch_bounds__(RT_BLOCK) k_shadow(SceneDev S, const FrameParams *__restrict__ Fp, LevelBuf L,
+	const uint32_t *__restrict__ count, WaveState *ws, float zNear)
+{
+	__shared__ int s_stack[RT_STACK * RT_BLOCK];
+	int *stack = s_stack + threadIdx.x;
+	const FrameParams &F = *Fp;
+	const uint32_t k = blockIdx.y;
+	if (!F.lights[k].enabled)
+		return;
+	const uint32_t n = *count < L.capacity ? *count : L.capacity;
+	TravStats st = { 0, 0, 0 };
+	for (uint32_t i = blockIdx.x * RT_BLOCK + threadIdx.x; i < n; i += gridDim.x * RT_BLOCK)
+	{
+		const float4 hp = L.hit_p[i];
+		if (hp.w > F.zFar || hp.w < zNear)
+			continue;   // no surface: no light loop (RayTracer.cpp:467-468)
+		RayD ray;
+		float dis, lum;
+		light_dir(F.lights[k], f3(hp), ray.d, dis, lum);
+		ray.o = f3(hp);
+		ray.mtlrfr = 1.0f;
+		ray.skip = L.hit_id[i];
+		ray.type = F.type == RT_TYPE_REFLECT ? 0 : MY_RAY_SHADOWRAY_;
+		ray.isInside = 0;
+		Best best = { dis, RT_ID_NONE };
+		bool done = false;
+		trace_scene<true, STATS>(S, ray, stack, best, done, st);
+		L.shadow[(size_t)k * L.capacity + i] = done ? 1 : 0;
+	}
+	flush_stats<STATS>(ws, st);
+}
+
+// ---- shading + secondary-ray queue ---------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t warp_append(uint32_t *counter, bool want)
+{
+	// warp-aggregated queue append: one atomic per warp, slots in lane order (keeps rays coherent)
+	const uint32_t m = __ballot_sync(0xffffffffu, want);
+	if (m == 0) return 0xFFFFFFFFu;
+	const uint32_t lane = threadIdx.x & 31u, leader = __ffs((int)m) - 1;
+	uint32_t base = 0;
+	if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+	base = __shfl_sync(0xffffffffu, base, leader);
+	return want ? base + __popc(m & ((1u << lane) - 1u)) : 0xFFFFFFFFu;
+}
+
+__global__ void __launch_bounds__(128) k_shade(SceneDev S, const FrameParams *__restrict__ Fp, LevelBuf L, LevelBuf N,
+	WaveState *ws, uint32_t level, float zNear)
+{
+	const FrameParams &F = *Fp;
+	const uint32_t n = ws->count[level] < L.capacity ? ws->count[level] : L.capacity;
+	const uint32_t nIter = (n + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
+	const bool refraction = F.type != RT_TYPE_REFLECT;
+	unsigned long long myHits = 0;
+	for (uint32_t it = 0; it < nIter; ++it)
+	{
+		const uint32_t i = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+		bool wantFlec = false, wantFrac = false;
+		float4 co = make_float4(0, 0, 0, 0), cdFlec = co, cdFrac = co;
+		uint2 metaFlec = make_uint2(0, 0), metaFrac = metaFlec;
+		float fracRfr = 1.0f;
+		int4 aux = make_int4(-1, -1, -1, 0);
+		if (i < n)
+		{
+			const float4 hp = L.hit_p[i];
+			const uint32_t id = L.hit_id[i];
+			float4 color = make_float4(0.0f, 0.0f, 0.0f, 1e20f);   // Color(false)
+			if (!(hp.w > F.zFar || hp.w < zNear))
+			{
+				++myHits;
+				const RayD ray = load_ray(L, i);
+				const float bwc = L.ray_d[i].w;
+				const F3 P = f3(hp);
+				F3 Nn;
+				float tu = 0, tv = 0, rfr = 1.0f;
+				int mtlIndex, tex = -1;
+				uint8_t hitInside = 0;
+				if (is_tri(id))
+				{
+					// Model::intersect epilogue, Model.cpp:794-807
+					const uint32_t tri = id & 0x0FFFFFFFu, slot = __ldg(&S.tri_slot[tri]);
+					const float4 g0 = ldg4(&S.tri_geom[3 * slot]), g1 = ldg4(&S.tri_geom[3 * slot + 1]), g2 = ldg4(&S.tri_geom[3 * slot + 2]);
+					F3 bary = f3(0, 0, 0);
+					triangle_t(ray.o, ray.d, f3(g0), f3(g1), f3(g2), &bary);
+					const F3 n0 = f3(ldg4(&S.tri_norms[3 * tri])), n1 = f3(ldg4(&S.tri_norms[3 * tri + 1])), n2 = f3(ldg4(&S.tri_norms[3 * tri + 2]));
+					Nn = normalize((n0 * bary.x + n1 * bary.y) + n2 * bary.z);
+					const float2 c0 = __ldg(&S.tri_tcoords[3 * tri]), c1 = __ldg(&S.tri_tcoords[3 * tri + 1]), c2 = __ldg(&S.tri_tcoords[3 * tri + 2]);
+					tu = (c0.x * bary.x + c1.x * bary.y) + c2.x * bary.z;
+					tv = (c0.y * bary.x + c1.y * bary.y) + c2.y * bary.z;
+					const DevPart &part = S.parts[__ldg(&S.tri_part[tri])];
+					mtlIndex = (int)__ldg(&part.material);
+					tex = __ldg(&part.texture);
+					rfr = __ldg(&S.materials[4 * mtlIndex + 3]).w;
+				}
+				else
+				{
+					const int4 meta = __ldg(&S.prim_meta[id]);
+					const float4 g0 = ldg4(&S.prim_geom[4 * id]);
+					mtlIndex = meta.y;
+					if (meta.x == RT_OBJ_SPHERE)
+					{
+						const bool leaving = ray.skip == id;   // only reachable with ray.isInside
+						Nn = leaving ? normalize(f3(g0) - P) : normalize(P - f3(g0));
+						hitInside = (uint8_t)~ray.isInside;
+						rfr = (leaving && ray.type == MY_RAY_REFRACTRAY_) ? 1.0f : __ldg(&S.materials[4 * mtlIndex + 3]).w;
+					}
+					else if (meta.x == RT_OBJ_PLANE)
+					{
+						Nn = f3(ldg4(&S.prim_geom[4 * id + 1]));
+						const float2 tc = plane_tcoord(ray.o, ray.d, f3(g0), f3(ldg4(&S.prim_geom[4 * id + 2])), f3(ldg4(&S.prim_geom[4 * id + 3])));
+						tu = tc.x, tv = tc.y;
+						tex = meta.z;
+					}
+					else
+						Nn = box_normal(P, f3(g0), f3(ldg4(&S.prim_geom[4 * id + 3])));
+				}
+				const F3 mA = f3(ldg4(&S.materials[4 * mtlIndex])), mD = f3(ldg4(&S.materials[4 * mtlIndex + 1])), mS = f3(ldg4(&S.materials[4 * mtlIndex + 2]));
+				const float4 mP = ldg4(&S.materials[4 * mtlIndex + 3]);   // shiness, reflect, refract, rfr
+				const F3 vc = texel(S, tex, tu, tv);
+				F3 mix_vd = f3(0, 0, 0), mix_vsc = f3(0, 0, 0);
+				F3 mix_va = mixmul(mA, f3(F.env_light));
+				for (uint32_t k = 0; k < F.n_lights; ++k)
+				{
+					const DevLight &lit = F.lights[k];
+					if (!lit.enabled)
+						continue;
+					F3 p2l;
+					float dis, lum;
+					light_dir(lit, P, p2l, dis, lum);
+					F3 la = f3(lit.ambient), ld = f3(lit.diffuse), ls = f3(lit.specular);
+					if (lit.type == RT_LIGHT_POINT)
+						la = la * lum, ld = ld * lum, ls = ls * lum;
+					mix_va = mix_va + mixmul(mA, la);   // ambient is added before the shadow test
+					if (L.shadow[(size_t)k * L.capacity + i])
+						continue;
+					float n_n = dot(Nn, p2l);
+					if (n_n > 0)
+						mix_vd = mix_vd + mixmul(mD, ld) * n_n;
+					const F3 h = normalize(p2l - ray.d);
+					n_n = dot(Nn, h);
+					if (n_n > 0)
+						mix_vsc = mix_vsc + mixmul(mS, ls) * pow_ref(n_n, mP.x);
+				}
+				const F3 c_all = mixmul(vc, mix_vd + mix_va) + mix_vsc;
+				color = make_float4(c_all.x, c_all.y, c_all.z, hp.w);
+				aux.z = mtlIndex;
+				const bool deeper = level + 1 <= F.max_level;
+				if (mP.y > 0.01f)
+				{
+					aux.w |= 1;
+					const float bw = bwc * mP.y;
+					if (deeper && !(bw < 1e-5f))
+					{
+						const float n_n = 2 * dot(ray.d, Nn);
+						const F3 r = normalize(ray.d - Nn * n_n);
+						wantFlec = true;
+						cdFlec = make_float4(r.x, r.y, r.z, bw);
+						metaFlec = make_uint2(id, refraction ? (uint32_t)MY_RAY_REFLECTRAY_ : 0u);
+					}
+				}
+				if (refraction && mP.z > 0.01f)
+				{
+					aux.w |= 2;
+					if (hitInside) aux.w |= 4;
+					const float nn = ray.mtlrfr / rfr;
+					const float cosIn = -dot(ray.d, Nn);
+					const float cosOut2 = 1.0f - (nn * nn) * (1.0f - cosIn * cosIn);
+					const float bw = bwc * mP.z;
+					if (!(cosOut2 < 0.0f) && deeper && !(bw < 1e-5f))
+					{
+						const F3 l2 = ray.d * nn, l1 = Nn * (nn * cosIn - sqrtf(cosOut2));
+						const F3 r = normalize(l1 + l2);
+						wantFrac = true;
+						cdFrac = make_float4(r.x, r.y, r.z, bw);
+						metaFrac = make_uint2(id, (uint32_t)MY_RAY_REFRACTRAY_ | ((uint32_t)hitInside << 8));
+						fracRfr = rfr;
+					}
+				}
+				co = make_float4(P.x, P.y, P.z, 1.0f);
+			}
+			L.color[i] = color;
+		}
+		// append the children to level+1 (whole warp participates)
+		const uint32_t sFlec = warp_append(&ws->count[level + 1], wantFlec);
+		if (wantFlec)
+		{
+			if (sFlec < N.capacity)
+			{
+				N.ray_o[sFlec] = co, N.ray_d[sFlec] = cdFlec, N.ray_meta[sFlec] = metaFlec;
+				aux.x = (int)sFlec;
+			}
+			else
+				ws->overflow = 1;
+		}
+		const uint32_t sFrac = warp_append(&ws->count[level + 1], wantFrac);
+		if (wantFrac)
+		{
+			if (sFrac < N.capacity)
+			{
+				N.ray_o[sFrac] = make_float4(co.x, co.y, co.z, fracRfr), N.ray_d[sFrac] = cdFrac, N.ray_meta[sFrac] = metaFrac;
+				aux.y = (int)sFrac;
+			}
+			else
+				ws->overflow = 1;
+		}
+		if (i < n)
+			L.aux[i] = aux;
+		// ray statistics (one atomic per warp)
+		const uint32_t mf = __ballot_sync(0xffffffffu, wantFlec), mr = __ballot_sync(0xffffffffu, wantFrac);
+		if ((threadIdx.x & 31) == 0)
+		{
+			if (mf) atomicAdd(&ws->n_reflect, (unsigned long long)__popc(mf));
+			if (mr) atomicAdd(&ws->n_refract, (unsigned long long)__popc(mr));
+		}
+	}
+	for (int o = 16; o > 0; o >>= 1)
+		myHits += __shfl_down_sync(0xffffffffu, myHits, o);
+	if ((threadIdx.x & 31) == 0 && myHits)
+		atomicAdd(&ws->n_hits, myHits);
+}
+
+// ---- post-order combine --------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) k_combine(SceneDev S, const FrameParams *__restrict__ Fp, LevelBuf L, LevelBuf N,
+	const WaveState *__restrict__ ws, uint32_t level, uint8_t *__restrict__ out)
+{
+	const FrameParams &F = *Fp;
+	const uint32_t n = ws->count[level] < L.capacity ? ws->count[level] : L.capacity;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+	{
+		float4 color = L.color[i];
+		const int4 aux = L.aux[i];
+		if (aux.z >= 0 && (aux.w & 3))
+		{
+			F3 c = f3(color);
+			const float4 mP = ldg4(&S.materials[4 * aux.z + 3]);
+			if (aux.w & 1)
+			{
+				c = c * (1 - mP.y);
+				if (aux.x >= 0)
+					c = c + f3(N.color[aux.x]) * mP.y;
+			}
+			if (aux.w & 2)
+			{
+				c = c * (1 - mP.z);
+				if (aux.y >= 0)
+				{
+					const float4 cf = N.color[aux.y];
+					F3 vcf = f3(1, 1, 1);
+					if (aux.w & 4)
+					{
+						// Beer's law on the way out of the medium, RayTracer.cpp:585-590
+						const F3 e = (f3(ldg4(&S.materials[4 * aux.z + 1])) * 0.15f) * (-cf.w);
+						vcf = f3(exp_ref(e.x), exp_ref(e.y), exp_ref(e.z));
+					}
+					c = c + mixmul(f3(cf), vcf) * mP.z;
+				}
+			}
+			color = make_float4(c.x, c.y, c.z, color.w);
+			if (level > 0)
+				L.color[i] = color;
+		}
+		if (level == 0)
+		{
+			int x, y;
+			slot_to_pixel(F, i, x, y);
+			uint8_t *o = out + ((size_t)y * F.width + x) * 3;
+			o[0] = put8(color.x), o[1] = put8(color.y), o[2] = put8(color.z);
+		}
+	}
+}
+
+// ---- launchers -----------------------------------------------------------------------------------
+
+static inline unsigned grid_for(uint32_t n, unsigned block, unsigned maxBlocks)
+{
+	unsigned g = (n + block - 1) / block;
+	if (g < 1) g = 1;
+	return g < maxBlocks ? g : maxBlocks;
+}
+
+void rtk_raygen(cudaStream_t st, const FrameParams *F, const LevelBuf &L, uint32_t n, unsigned sms)
+{
+	k_raygen<<<grid_for(n, 256, sms * 16), 256, 0, st>>>(F, L, n);
+}
+
+void rtk_trace(cudaStream_t st, const SceneDev &S, const LevelBuf &L, const uint32_t *count, WaveState *ws, uint32_t maxRays, unsigned sms, bool stats)
+{
+	const unsigned g = grid_for(maxRays, RT_BLOCK, sms * 64);
+	if (stats) k_trace<true><<<g, RT_BLOCK, 0, st>>>(S, L, count, ws);
+	else k_trace<false><<<g, RT_BLOCK, 0, st>>>(S, L, count, ws);
+}
+
+void rtk_shadow(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const uint32_t *count, WaveState *ws,
+	float zNear, uint32_t nLights, uint32_t maxRays, unsigned sms, bool stats)
+{
+	if (nLights == 0) return;
+	const dim3 g(grid_for(maxRays, RT_BLOCK, sms * 64), nLights);
+	if (stats) k_shadow<true><<<g, RT_BLOCK, 0, st>>>(S, F, L, count, ws, zNear);
+	else k_shadow<false><<<g, RT_BLOCK, 0, st>>>(S, F, L, count, ws, zNear);
+}
+
+void rtk_shade(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const LevelBuf &N, WaveState *ws,
+	uint32_t level, float zNear, uint32_t maxRays, unsigned sms)
+{
+	k_shade<<<grid_for(maxRays, 128, sms * 64), 128, 0, st>>>(S, F, L, N, ws, level, zNear);
+}
+
+void rtk_combine(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const LevelBuf &N, const WaveState *ws,
+	uint32_t level, uint8_t *out, uint32_t maxRays, unsigned sms)
+{
+	k_combine<<<grid_for(maxRays, 256, sms * 32), 256, 0, st>>>(S, F, L, N, ws, level, out);
+}

@@ -1,0 +1,85 @@
+// Host-visible declarations of the wavefront buffers and kernel launchers (rt_kernels.cu) and
+// of the LBVH builder (rt_build.cu).
+#pragma once
+#include "rt_device.cuh"
+
+#define MY_RAY_BASERAY_    0x1
+#define MY_RAY_SHADOWRAY_  0x2
+#define MY_RAY_REFLECTRAY_ 0x3
+#define MY_RAY_REFRACTRAY_ 0x4
+
+// One recursion level of the ray tree: slot i is both ray i and ray-tree node i of that level.
+struct LevelBuf
+{
+	float4 *ray_o;       // origin.xyz, Ray::mtlrfr
+	float4 *ray_d;       // direction.xyz (unit), bwc ("benefit weight", RayTracer.cpp:451)
+	uint2 *ray_meta;     // x: HitRes::obj to skip, y: Ray::type | Ray::isInside << 8
+	float4 *hit_p;       // HitRes::position.xyz, HitRes::distance (1e20 = miss)
+	uint32_t *hit_id;    // closest primitive (newobj of RayTracer.cpp:456-465)
+	float4 *color;       // node-local colour, then combined colour; w = Color::alpha (distance)
+	int4 *aux;           // x: reflect child slot, y: refract child slot (-1 none), z: material (-1 = no surface), w: bit0 reflect, bit1 refract, bit2 Beer
+	uint8_t *shadow;     // [light][capacity]: 1 = occluded
+	uint32_t capacity;
+};
+
+struct WaveState
+{
+	uint32_t count[RT_MAX_LEVELS + 2];   // rays queued per level
+	uint32_t overflow;                   // a level ran out of slots
+	uint32_t pad;
+	unsigned long long n_reflect, n_refract, n_hits;
+	unsigned long long nodes_visited, tri_tests, prim_tests;
+};
+
+void rtk_raygen(cudaStream_t st, const FrameParams *F, const LevelBuf &L, uint32_t n, unsigned sms);
+void rtk_trace(cudaStream_t st, const SceneDev &S, const LevelBuf &L, const uint32_t *count, WaveState *ws, uint32_t maxRays, unsigned sms, bool stats);
+void rtk_shadow(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const uint32_t *count, WaveState *ws,
+	float zNear, uint32_t nLights, uint32_t maxRays, unsigned sms, bool stats);
+void rtk_shade(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const LevelBuf &N, WaveState *ws,
+	uint32_t level, float zNear, uint32_t maxRays, unsigned sms);
+void rtk_combine(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const LevelBuf &N, const WaveState *ws,
+	uint32_t level, uint8_t *out, uint32_t maxRays, unsigned sms);
+
+// ---- LBVH build (rt_build.cu) --------------------------------------------------------------------
+
+struct BuildScratch;   // opaque, owned by the context
+
+// Triangle preparation = the GPU restatement of Model::RTPrepare (Model.cpp:402-480): clTri edge
+// form, world-space p0, octant membership mask per triangle.
+struct TriPrepArgs
+{
+	const float4 *points;      // 3 per triangle, original order (untranslated)
+	const DevModel *models;
+	const DevPart *parts;
+	const uint32_t *tri_part;  // original index -> global part
+	const float4 *part_mid_pos;   // per part: (borders[2p]+borders[2p+1])*0.5 (untranslated), w unused
+	const float4 *part_position;  // per part: model position
+	float4 *tri_geom_orig;     // out: 3 float4 per triangle, original order: e1|id, e2|part<<8|octs, p0w|0
+	float4 *box_lo, *box_hi;   // out: padded world AABB per triangle
+	uint32_t n;
+	uint32_t id_base;          // global original index of local triangle 0
+};
+void rtb_prepare_tris(cudaStream_t st, const TriPrepArgs &a);
+
+struct PrimBoxArgs
+{
+	const float4 *prim_geom;
+	const int4 *prim_meta;
+	float4 *box_lo, *box_hi;
+	uint32_t first, n;
+};
+void rtb_prim_boxes(cudaStream_t st, const PrimBoxArgs &a);
+
+// Builds one LBVH over boxes [0,n): Morton codes of box centres -> radix sort -> Karras
+// hierarchy -> bottom-up refit, emitting 64-byte BvhNodes at nodes[nodeBase ...) and the leaf
+// order.  Returns the root link (node index, or a leaf code when n <= leafSize) and tree depth.
+struct BvhBuildResult { int root; uint32_t nodesUsed; uint32_t depth; };
+int rtb_build(cudaStream_t st, BuildScratch **scratch, const float4 *box_lo, const float4 *box_hi, uint32_t n,
+	uint32_t leafSize, BvhNode *nodes, uint32_t nodeBase, uint32_t leafBase, uint32_t *leafOrder /* out: leaf slot -> input index */,
+	BvhBuildResult *res);
+void rtb_free_scratch(BuildScratch *s);
+
+// tri_geom (leaf order) = tri_geom_orig[leafOrder]; tri_slot[orig] = leaf slot
+void rtb_scatter_tris(cudaStream_t st, const float4 *geomOrig, const uint32_t *leafOrder, uint32_t leafBase, uint32_t origBase, uint32_t n,
+	float4 *geomLeaf, uint32_t *triSlot);
+void rtb_offset_order(cudaStream_t st, uint32_t *order, uint32_t n, uint32_t add);

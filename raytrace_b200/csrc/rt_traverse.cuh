@@ -1,0 +1,240 @@
+// Software BVH traversal on the SM (B200 exposes no RT cores to CUDA) and the scene-order walk
+// that replaces the reference's per-ray virtual dispatch loop (RayTracer.cpp:455-465 closest hit,
+// :510-520 shadow any-hit) and Model::intersect's brute-force part/octant/triangle loops
+// (Model.cpp:748-811).
+//
+// Exactness contract:
+//  * every accepted hit distance comes from the bit-exact operators of rt_intersect.cuh;
+//  * BVH boxes are only a conservative cull (padded boxes, widened slab interval);
+//  * a triangle hit is accepted only if the reference would have tested that triangle for this
+//    ray: its Model passes BorderTest (< hr.distance), its part passes BorderTestEx
+//    (< hr.distance), and one of the octant lists that hold a copy of it is enabled in the ray's
+//    octant mask -- excluding the single copy the ray left from (the reference's self-skip
+//    compares clTri addresses, Model.cpp:775);
+//  * equal distances resolve to the first candidate in reference iteration order
+//    (object, part, first enabled octant, triangle index), independent of traversal order.
+#pragma once
+#include "rt_intersect.cuh"
+
+#define RT_BLOCK 128
+
+struct TravStats { uint32_t nodes, tris, prims; };
+
+__device__ __forceinline__ bool is_tri(uint32_t id) { return id != RT_ID_NONE && (id & RT_ID_TRI); }
+
+struct Best
+{
+	float t;        // HitRes::distance so far
+	uint32_t id;    // RT_ID_NONE | prim flat index | RT_ID_TRI | oct<<28 | tri original index
+};
+
+// Conservative ray/box interval test: (plane - o) * (1/d) has bounded relative error, the far
+// bound is widened by a few ulp (Ize 2013) and the boxes themselves are padded at build time.
+__device__ __forceinline__ bool slab_hit(float lx, float ly, float lz, float hx, float hy, float hz,
+	const F3 &o, const F3 &id, float tbest, float &tnear)
+{
+	const float ax = (lx - o.x) * id.x, bx = (hx - o.x) * id.x;
+	const float ay = (ly - o.y) * id.y, by = (hy - o.y) * id.y;
+	const float az = (lz - o.z) * id.z, bz = (hz - o.z) * id.z;
+	const float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+	const float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tbest));
+	tnear = t0;
+	return t0 <= t1 * 1.0000005f;
+}
+
+// Per-ray cache of the reference's part-level predicate (BorderTestEx), so the replay costs one
+// evaluation per (ray, part) that produces a candidate.
+struct PartCache
+{
+	uint32_t part;   // global part index, 0xFFFFFFFF = empty
+	uint32_t mask;   // enabled octants, 0 if the part fails `minist < hr.distance`
+};
+
+__device__ __forceinline__ uint32_t part_mask(const SceneDev &S, const RayD &ray, uint32_t part, float hr_distance, PartCache &pc)
+{
+	if (pc.part != part)
+	{
+		const DevPart &P = S.parts[part];
+		const float4 bmin = __ldg(&P.box_min), bmax = __ldg(&P.box_max);
+		uint32_t m;
+		const float minist = border_test_ex(ray.o, ray.d, f3(bmin), f3(bmax), &m);
+		pc.part = part;
+		pc.mask = (minist < hr_distance) ? m : 0u;
+	}
+	return pc.mask;
+}
+
+// `first octant list that would test this triangle`, or -1 if the reference never tests it
+__device__ __forceinline__ int tested_octant(uint32_t tri_octs, uint32_t mask, uint32_t tri, uint32_t skip)
+{
+	uint32_t s = tri_octs & mask;
+	if (is_tri(skip) && (skip & 0x0FFFFFFFu) == tri)
+		s &= ~(1u << ((skip >> 28) & 7u));
+	return s ? (__ffs((int)s) - 1) : -1;
+}
+
+// reference iteration rank of a triangle hit inside one Model: (part, octant, index in part)
+__device__ __forceinline__ bool tri_rank_less(const SceneDev &S, uint32_t partA, int octA, uint32_t triA, uint32_t idB)
+{
+	const uint32_t triB = idB & 0x0FFFFFFFu;
+	const uint32_t partB = __ldg(&S.tri_part[triB]);
+	const int octB = (int)((idB >> 28) & 7u);
+	if (partA != partB) return partA < partB;
+	if (octA != octB) return octA < octB;
+	return triA < triB;   // same part: original index order == index-in-part order
+}
+
+template<bool ANY, bool STATS>
+__device__ __forceinline__ void leaf_tris(const SceneDev &S, const RayD &ray, uint32_t first, uint32_t count,
+	float hr_distance, uint32_t model_tri_begin, uint32_t model_tri_end, PartCache &pc, Best &best, bool &done, TravStats &st)
+{
+	for (uint32_t k = 0; k < count; ++k)
+	{
+		const float4 g0 = ldg4(&S.tri_geom[3 * (first + k)]);
+		const float4 g1 = ldg4(&S.tri_geom[3 * (first + k) + 1]);
+		const float4 g2 = ldg4(&S.tri_geom[3 * (first + k) + 2]);
+		if (STATS) ++st.tris;
+		const float t = triangle_t(ray.o, ray.d, f3(g0), f3(g1), f3(g2), nullptr);
+		if (ANY ? !(t < best.t) : !(t <= best.t && t < 1e20f))
+			continue;
+		const uint32_t tri = __float_as_uint(g0.w);
+		const uint32_t pinfo = __float_as_uint(g1.w);
+		const uint32_t part = pinfo >> 8, octs = pinfo & 0xFFu;
+		const uint32_t mask = part_mask(S, ray, part, hr_distance, pc);
+		const int oct = tested_octant(octs, mask, tri, ray.skip);
+		if (oct < 0)
+			continue;
+		if (ANY)
+		{
+			best.t = t;
+			done = true;
+			return;
+		}
+		if (t == best.t)
+		{
+			// exact tie: an earlier object keeps the hit; inside this model the reference order decides
+			const bool bestHere = is_tri(best.id) && (best.id & 0x0FFFFFFFu) >= model_tri_begin && (best.id & 0x0FFFFFFFu) < model_tri_end;
+			if (!bestHere || !tri_rank_less(S, part, oct, tri, best.id))
+				continue;
+		}
+		best.t = t;
+		best.id = RT_ID_TRI | ((uint32_t)oct << 28) | tri;
+	}
+}
+
+// one analytic primitive against the running best (closest) or the light distance (any-hit)
+template<bool ANY>
+__device__ __forceinline__ void test_prim(const SceneDev &S, const RayD &ray, uint32_t p, bool tieLower, Best &best, bool &done)
+{
+	const int4 meta = __ldg(&S.prim_meta[p]);
+	const float4 g0 = ldg4(&S.prim_geom[4 * p]);
+	const bool self = ray.skip == p;
+	float t;
+	if (meta.x == RT_OBJ_SPHERE)
+	{
+		const float4 g1 = ldg4(&S.prim_geom[4 * p + 1]);
+		t = sphere_t(ray, f3(g0), g1.x, self);
+	}
+	else if (self)
+		return;   // Box / Plane: `if (hr.obj == this) return hr`
+	else if (meta.x == RT_OBJ_PLANE)
+	{
+		const float4 g1 = ldg4(&S.prim_geom[4 * p + 1]);
+		t = plane_t(ray, f3(g0), f3(g1));
+	}
+	else
+	{
+		const float4 g1 = ldg4(&S.prim_geom[4 * p + 1]), g2 = ldg4(&S.prim_geom[4 * p + 2]);
+		t = box_t(ray, f3(g1), f3(g2));
+	}
+	if (t < best.t || (!ANY && tieLower && t == best.t && t < 1e20f && p < best.id))
+	{
+		best.t = t;
+		best.id = p;
+		if (ANY) done = true;
+	}
+}
+
+// BVH walk shared by Models (triangle leaves) and runs of analytic primitives (prim leaves).
+template<bool ANY, bool TRIS, bool STATS>
+__device__ __forceinline__ void traverse(const SceneDev &S, const RayD &ray, const F3 &idir, int root,
+	float hr_distance, uint32_t rangeBegin, uint32_t rangeEnd, int *stack /* [RT_STACK][RT_BLOCK] slice */,
+	Best &best, bool &done, TravStats &st)
+{
+	PartCache pc;
+	pc.part = 0xFFFFFFFFu, pc.mask = 0;
+	int sp = 0;
+	int cur = root;
+	while (true)
+	{
+		if (cur >= 0)
+		{
+			const BvhNode *n = &S.nodes[cur];
+			const float4 a = ldg4(&n->a), b = ldg4(&n->b), c = ldg4(&n->c);
+			const int4 link = __ldg(&n->link);
+			if (STATS) ++st.nodes;
+			float t0, t1;
+			const bool h0 = slab_hit(a.x, a.y, a.z, a.w, b.x, b.y, ray.o, idir, best.t, t0);
+			const bool h1 = slab_hit(b.z, b.w, c.x, c.y, c.z, c.w, ray.o, idir, best.t, t1);
+			if (h0 && h1)
+			{
+				const bool swap = t1 < t0;
+				stack[sp * RT_BLOCK] = swap ? link.x : link.y;
+				++sp;
+				cur = swap ? link.y : link.x;
+				continue;
+			}
+			if (h0) { cur = link.x; continue; }
+			if (h1) { cur = link.y; continue; }
+		}
+		else
+		{
+			const uint32_t first = ((uint32_t)cur & 0x7FFFFFFFu) >> 3, count = ((uint32_t)cur & 7u) + 1u;
+			if (TRIS)
+				leaf_tris<ANY, STATS>(S, ray, first, count, hr_distance, rangeBegin, rangeEnd, pc, best, done, st);
+			else
+				for (uint32_t k = 0; k < count; ++k)
+				{
+					if (STATS) ++st.prims;
+					test_prim<ANY>(S, ray, __ldg(&S.bvh_prims[first + k]), !(best.id & RT_ID_TRI) && best.id >= rangeBegin, best, done);
+				}
+			if (ANY && done)
+				return;
+		}
+		if (sp == 0)
+			return;
+		--sp;
+		cur = stack[sp * RT_BLOCK];
+	}
+}
+
+// The scene walk in Objects order.  Closest hit: best starts at (1e20, NONE).  Any-hit: best.t
+// starts at the light distance and `done` reports occlusion.
+template<bool ANY, bool STATS>
+__device__ __forceinline__ void trace_scene(const SceneDev &S, const RayD &ray, int *stack, Best &best, bool &done, TravStats &st)
+{
+	const F3 idir = f3(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
+	for (uint32_t i = 0; i < S.n_items; ++i)
+	{
+		const SceneItem it = S.items[i];
+		if (it.kind == RT_ITEM_PRIM)
+		{
+			if (STATS) ++st.prims;
+			test_prim<ANY>(S, ray, it.first, false, best, done);
+		}
+		else if (it.kind == RT_ITEM_PRIMBVH)
+			traverse<ANY, false, STATS>(S, ray, idir, it.root, best.t, it.first, it.first + it.count, stack, best, done, st);
+		else
+		{
+			const DevModel &M = S.models[it.first];
+			const float4 mn = __ldg(&M.border_min), mx = __ldg(&M.border_max);
+			// Model.cpp:752: `if (BorderTest(ray, BorderMin, BorderMax) < hr.distance)`
+			if (!(border_test(ray.o, ray.d, f3(mn), f3(mx)) < best.t))
+				continue;
+			const uint32_t tb = __ldg(&M.tri_begin);
+			traverse<ANY, true, STATS>(S, ray, idir, it.root, best.t, tb, tb + __ldg(&M.tri_count), stack, best, done, st);
+		}
+		if (ANY && done)
+			return;
+	}
+}

@@ -1,0 +1,54 @@
+// Render driver of the object model -- the drop-in for the reference's RayTracer
+// (/root/reference/RayTracer.h:16-56).  Same public surface (start/stop, output, width, height,
+// maxLevel, isFinish, useTime); underneath, start() flattens the Scene, hands it to the CUDA
+// library through the C ABI of include/rt_b200.h and returns at once, exactly like the
+// reference returns after spawning its worker threads (RayTracer.cpp:664-695).
+#pragma once
+#include "Scene.h"
+#include "../../include/rt_b200.h"
+#include <thread>
+
+#define MY_MODEL_CHECK 0x1
+#define MY_MODEL_DEPTHTEST 0x2
+#define MY_MODEL_NORMALTEST 0x3
+#define MY_MODEL_TEXTURETEST 0x4
+#define MY_MODEL_MATERIALTEST 0x5
+#define MY_MODEL_SHADOWTEST 0x6
+#define MY_MODEL_REFLECTTEST 0x7
+#define MY_MODEL_REFRACTTEST 0x8
+#define MY_MODEL_RAYTRACE 0x80
+
+class SceneFlattener;
+
+class RayTracer
+{
+	Scene *scene;
+	rt_ctx *ctx = nullptr;
+	SceneFlattener *flattener = nullptr;
+	std::thread monitor;
+	size_t outputBytes;
+	void ensureContext();
+public:
+	GLuint texID = 0;
+	uint8_t *output;
+	volatile bool isFinish = true;
+	volatile double useTime = 0.0;
+	uint8_t maxLevel = 1;
+	int width = 0, height = 0;
+	RayTracer(Scene &scene);
+	~RayTracer();
+
+	// `tnum` was the CPU worker-thread count; the GPU path ignores it.
+	void start(const uint8_t type, const int8_t tnum = 1);
+	void stop();
+
+	// ---- additions of this build (not in the reference) ----
+	int device = 0;                 // CUDA device ordinal used when the context is created
+	uint32_t shardRank = 0, shardWorld = 1;   // image-space shard rendered by this tracer
+	uint32_t renderFlags = 0;       // RT_FLAG_* passed to the next start()
+	void reserveOutput(size_t bytes);          // frames beyond 2048x2048
+	void wait();                               // block until isFinish
+	bool readHitIds(rt_hit_id *ids);           // primary closest-hit identities of the last frame
+	bool readCounters(rt_counters *out);
+	rt_ctx *context() { ensureContext(); return ctx; }
+};

@@ -1,0 +1,135 @@
+// C shim over the C++ object model so that Python (ctypes) tests and bench.py can drive the
+// SAME classes a C++ user of the reference API would: Scene, the scene builders and RayTracer.
+// Prefix rth_ ("ray tracer host").  No per-ray work happens here.
+#include "RayTracer.h"
+#include "SceneUpload.h"
+#include "../scenes/scenes.h"
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+namespace
+{
+struct HostScene
+{
+	Scene scene;
+	SceneFlattener flattener;
+	rt_scene_desc desc;
+};
+thread_local std::string g_err;
+template<class F> int guarded(F &&f)
+{
+	try { f(); return 0; }
+	catch (const std::exception &e) { g_err = e.what(); return -1; }
+}
+}
+
+extern "C" {
+
+const char *rth_last_error(void) { return g_err.c_str(); }
+
+void *rth_scene_new(void) { return new HostScene(); }
+void rth_scene_free(void *h) { delete (HostScene *)h; }
+
+// named synthetic scenes of raytrace_b200/scenes/scenes.h ("c1".."c5", "t_*")
+int rth_scene_build(void *h, const char *name, int n, int parts, int width, int height, const char *tmpdir)
+{
+	return guarded([&]
+	{
+		HostScene *hs = (HostScene *)h;
+		rtscenes::SceneArgs a;
+		a.name = name, a.n = n, a.parts = parts;
+		if (tmpdir && *tmpdir) a.tmpdir = tmpdir;
+		hs->scene.cam.resize(width, height);
+		if (!rtscenes::build(hs->scene, a))
+			throw std::runtime_error(std::string("unknown scene ") + name);
+	});
+}
+
+int rth_scene_resize(void *h, int width, int height) { ((HostScene *)h)->scene.cam.resize(width, height); return 0; }
+int rth_scene_object_count(void *h) { return (int)((HostScene *)h)->scene.Objects.size(); }
+int rth_scene_light_count(void *h) { return (int)((HostScene *)h)->scene.Lights.size(); }
+
+// Scene::MovePos / Switch / ChgMtl(library material) / camera edits, for incremental-upload tests
+int rth_scene_move(void *h, int type, int num, float x, float y, float z)
+{
+	return ((HostScene *)h)->scene.MovePos((uint8_t)type, (uint8_t)num, Vertex(x, y, z)) ? 0 : -1;
+}
+int rth_scene_switch(void *h, int type, int num, int show)
+{
+	((HostScene *)h)->scene.Switch((uint8_t)type, (uint8_t)num, show != 0);
+	return 0;
+}
+int rth_scene_chgmtl(void *h, int num, int libIndex)
+{
+	Scene &s = ((HostScene *)h)->scene;
+	if (libIndex < 0 || libIndex >= (int)s.MtlLiby.size()) return -1;
+	return s.ChgMtl((uint8_t)num, s.MtlLiby[libIndex]) ? 0 : -1;
+}
+int rth_scene_set_object_position(void *h, int num, float x, float y, float z)
+{
+	Scene &s = ((HostScene *)h)->scene;
+	if (num < 0 || num >= (int)s.Objects.size()) return -1;
+	s.Objects[num]->position = Vertex(x, y, z);
+	return 0;
+}
+int rth_scene_set_light_position(void *h, int num, float x, float y, float z, float w)
+{
+	Scene &s = ((HostScene *)h)->scene;
+	if (num < 0 || num >= (int)s.Lights.size()) return -1;
+	s.Lights[num].position = Vertex(x, y, z, w);
+	return 0;
+}
+int rth_scene_camera_move(void *h, float x, float y, float z) { ((HostScene *)h)->scene.cam.move(x, y, z); return 0; }
+int rth_scene_camera_yaw(void *h, float a) { ((HostScene *)h)->scene.cam.yaw(a); return 0; }
+int rth_scene_camera_pitch(void *h, float a) { ((HostScene *)h)->scene.cam.pitch(a); return 0; }
+// sub-pixel jitter as the harness of SURVEY.md 8c does it: n' = n + u*(dx*dp) + v*(dy*dp)
+int rth_scene_camera_jitter(void *h, float dx, float dy)
+{
+	Camera &c = ((HostScene *)h)->scene.cam;
+	const double dp = tan(c.fovy * PI / 360) / (c.height / 2);
+	const Vertex n = c.n + c.u * (float)(dx * dp) + c.v * (float)(dy * dp);
+	c.n.x = n.x, c.n.y = n.y, c.n.z = n.z, c.n.w = n.w;   // deliberately NOT re-normalised
+	return 0;
+}
+
+// flatten to the C-ABI description; the pointer stays valid until the next flatten/free
+const rt_scene_desc *rth_scene_flatten(void *h)
+{
+	HostScene *hs = (HostScene *)h;
+	for (DrawObject *o : hs->scene.Objects)
+		if (o->bShow) o->RTPrepare();
+	if (guarded([&] { hs->flattener.flatten(hs->scene, hs->desc); }) != 0)
+		return nullptr;
+	return &hs->desc;
+}
+
+// RayTracer (the drop-in surface)
+void *rth_tracer_new(void *scene, int device)
+{
+	RayTracer *t = new RayTracer(((HostScene *)scene)->scene);
+	t->device = device;
+	return t;
+}
+void rth_tracer_free(void *t) { delete (RayTracer *)t; }
+int rth_tracer_start(void *t, int type, int tnum) { return guarded([&] { ((RayTracer *)t)->start((uint8_t)type, (int8_t)tnum); }); }
+void rth_tracer_stop(void *t) { ((RayTracer *)t)->stop(); }
+int rth_tracer_is_finished(void *t) { return ((RayTracer *)t)->isFinish ? 1 : 0; }
+void rth_tracer_wait(void *t) { ((RayTracer *)t)->wait(); }
+double rth_tracer_use_time(void *t) { return ((RayTracer *)t)->useTime; }
+const uint8_t *rth_tracer_output(void *t) { return ((RayTracer *)t)->output; }
+int rth_tracer_width(void *t) { return ((RayTracer *)t)->width; }
+int rth_tracer_height(void *t) { return ((RayTracer *)t)->height; }
+void rth_tracer_set_max_level(void *t, int level) { ((RayTracer *)t)->maxLevel = (uint8_t)level; }
+void rth_tracer_set_shard(void *t, int rank, int world) { ((RayTracer *)t)->shardRank = rank, ((RayTracer *)t)->shardWorld = world; }
+void rth_tracer_set_flags(void *t, unsigned flags) { ((RayTracer *)t)->renderFlags = flags; }
+int rth_tracer_read_hit_ids(void *t, rt_hit_id *ids) { return ((RayTracer *)t)->readHitIds(ids) ? 0 : -1; }
+int rth_tracer_read_counters(void *t, rt_counters *c) { return ((RayTracer *)t)->readCounters(c) ? 0 : -1; }
+void *rth_tracer_context(void *t)
+{
+	void *c = nullptr;
+	guarded([&] { c = ((RayTracer *)t)->context(); });
+	return c;
+}
+
+}  // extern "C"

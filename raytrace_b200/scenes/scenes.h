@@ -5,7 +5,7 @@
 // Scene::{EnvLight,Lights,Objects,MtlLiby,cam}; /root/reference/Scene.h:24-45), so the same
 // source compiles against
 //   * the reference's own headers  -> oracle/_ref/ref_render   (oracle/build_ref.sh), and
-//   * raytrace_b200/host/ headers  -> raytrace_b200/bin/rt_render (the B200 product).
+//   * raytrace_b200/host/ headers  -> raytrace_b200/bin/rt_render (the B200 product, also via host/capi.cpp).
 // That both compile from one file is the drop-in check for SURVEY.md section 8 (b) B1.
 //
 // Scene ids follow SURVEY.md section 8 (d): c1..c5 plus small "t_*" cases for tests.

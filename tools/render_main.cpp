@@ -16,7 +16,7 @@
 #include "Scene.h"
 #include "RayTracer.h"
 #include "render_taps.h"
-#include "../tests/scenes/scenes.h"
+#include "../raytrace_b200/scenes/scenes.h"
 
 #include <chrono>
 #include <cstdint>
