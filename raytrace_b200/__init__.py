@@ -32,14 +32,8 @@ def _check(rc, what):
 
 def fnv1a64(buf) -> str:
     """FNV-1a-64 of a byte buffer -- the golden-hash convention of BASELINE.md."""
-    a = np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else buf.reshape(-1).view(np.uint8)
-    h = 1469598103934665603
-    # process in python-int arithmetic per chunk via numpy is not associative; do it exactly but fast enough
-    mask = (1 << 64) - 1
-    prime = 1099511628211
-    for b in a.tobytes():
-        h = ((h ^ b) * prime) & mask
-    return f"{h:016x}"
+    a = np.ascontiguousarray(np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else buf).reshape(-1).view(np.uint8)
+    return f"{rth.rth_fnv1a64(a.ctypes.data, a.size):016x}"
 
 
 class Scene:

@@ -107,6 +107,7 @@ RT_SYMBOLS = {
 
 RTH_SYMBOLS = {
     "rth_last_error": (C.c_char_p, []),
+    "rth_fnv1a64": (C.c_ulonglong, [C.c_void_p, C.c_size_t]),
     "rth_scene_new": (C.c_void_p, []),
     "rth_scene_free": (None, [C.c_void_p]),
     "rth_scene_build": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p]),

@@ -51,8 +51,7 @@ template<class T> struct DevBuf
 struct LevelStore
 {
 	DevBuf<float4> ray_o, ray_d, hit_p, color;
-	DevBuf<uint2> ray_meta;
-	DevBuf<uint32_t> hit_id;
+	DevBuf<uint2> ray_meta, hit_id;
 	DevBuf<int4> aux;
 	DevBuf<uint8_t> shadow;
 	uint32_t capacity = 0, lights = 0;
@@ -595,9 +594,9 @@ extern "C" int rt_read_hit_ids(rt_ctx *c, rt_hit_id *ids)
 	if (!c->frameValid) return fail(RT_E_STATE, "rt_read_hit_ids: no finished frame");
 	CU(cudaSetDevice(c->device));
 	const uint32_t n = c->lastPixels;
-	std::vector<uint32_t> hid(n);
+	std::vector<uint2> hid(n);
 	std::vector<float4> hp(n);
-	CU(cudaMemcpy(hid.data(), c->levels[0].hit_id.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	CU(cudaMemcpy(hid.data(), c->levels[0].hit_id.p, n * sizeof(uint2), cudaMemcpyDeviceToHost));
 	CU(cudaMemcpy(hp.data(), c->levels[0].hit_p.p, n * sizeof(float4), cudaMemcpyDeviceToHost));
 	const int W = c->outW, H = c->outH;
 	for (size_t i = 0; i < (size_t)W * H; ++i) ids[i] = rt_hit_id{ -1, -1, -1, -1, 1e20f };
@@ -609,7 +608,7 @@ extern "C" int rt_read_hit_ids(rt_ctx *c, rt_hit_id *ids)
 		const uint32_t x = tx * 8u + (in & 7u), row = ty * 8u + (in >> 3), band = row >> 6;
 		const uint32_t y = ((band * world + rank) << 6) + (row & 63u);
 		rt_hit_id id = { -1, -1, -1, -1, hp[i].w };
-		const uint32_t h = hid[i];
+		const uint32_t h = hid[i].y;
 		if (h != RT_ID_NONE)
 		{
 			if (h & RT_ID_TRI)

@@ -121,12 +121,12 @@ __global__ void __launch_bounds__(RT_BLOCK) k_trace(SceneDev S, LevelBuf L, cons
 	for (uint32_t i = blockIdx.x * RT_BLOCK + threadIdx.x; i < n; i += gridDim.x * RT_BLOCK)
 	{
 		const RayD ray = load_ray(L, i);
-		Best best = { 1e20f, RT_ID_NONE };
+		Best best = { 1e20f, RT_ID_NONE, ray.skip };
 		bool done = false;
 		trace_scene<false, STATS>(S, ray, stack, best, done, st);
 		const F3 P = ray.o + ray.d * best.t;
 		L.hit_p[i] = make_float4(P.x, P.y, P.z, best.t);
-		L.hit_id[i] = best.id;
+		L.hit_id[i] = make_uint2(best.id, best.newobj);
 	}
 	flush_stats<STATS>(ws, st);
 }
@@ -176,10 +176,10 @@ __global__ void __launch_bounds__(RT_BLOCK) k_shadow(SceneDev S, const FramePara
 		light_dir(F.lights[k], f3(hp), ray.d, dis, lum);
 		ray.o = f3(hp);
 		ray.mtlrfr = 1.0f;
-		ray.skip = L.hit_id[i];
+		ray.skip = L.hit_id[i].y;
 		ray.type = F.type == RT_TYPE_REFLECT ? 0 : MY_RAY_SHADOWRAY_;
 		ray.isInside = 0;
-		Best best = { dis, RT_ID_NONE };
+		Best best = { dis, RT_ID_NONE, RT_ID_NONE };
 		bool done = false;
 		trace_scene<true, STATS>(S, ray, stack, best, done, st);
 		L.shadow[(size_t)k * L.capacity + i] = done ? 1 : 0;
@@ -220,7 +220,8 @@ __global__ void __launch_bounds__(128) k_shade(SceneDev S, const FrameParams *__
 		if (i < n)
 		{
 			const float4 hp = L.hit_p[i];
-			const uint32_t id = L.hit_id[i];
+			const uint2 hid = L.hit_id[i];
+			const uint32_t id = hid.x, newobj = hid.y;
 			float4 color = make_float4(0.0f, 0.0f, 0.0f, 1e20f);   // Color(false)
 			if (!(hp.w > F.zFar || hp.w < zNear))
 			{
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(128) k_shade(SceneDev S, const FrameParams *__
 						const F3 r = normalize(ray.d - Nn * n_n);
 						wantFlec = true;
 						cdFlec = make_float4(r.x, r.y, r.z, bw);
-						metaFlec = make_uint2(id, refraction ? (uint32_t)MY_RAY_REFLECTRAY_ : 0u);
+						metaFlec = make_uint2(newobj, refraction ? (uint32_t)MY_RAY_REFLECTRAY_ : 0u);
 					}
 				}
 				if (refraction && mP.z > 0.01f)
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(128) k_shade(SceneDev S, const FrameParams *__
 						const F3 r = normalize(l1 + l2);
 						wantFrac = true;
 						cdFrac = make_float4(r.x, r.y, r.z, bw);
-						metaFrac = make_uint2(id, (uint32_t)MY_RAY_REFRACTRAY_ | ((uint32_t)hitInside << 8));
+						metaFrac = make_uint2(newobj, (uint32_t)MY_RAY_REFRACTRAY_ | ((uint32_t)hitInside << 8));
 						fracRfr = rfr;
 					}
 				}

@@ -15,7 +15,7 @@ struct LevelBuf
 	float4 *ray_d;       // direction.xyz (unit), bwc ("benefit weight", RayTracer.cpp:451)
 	uint2 *ray_meta;     // x: HitRes::obj to skip, y: Ray::type | Ray::isInside << 8
 	float4 *hit_p;       // HitRes::position.xyz, HitRes::distance (1e20 = miss)
-	uint32_t *hit_id;    // closest primitive (newobj of RayTracer.cpp:456-465)
+	uint2 *hit_id;       // x: closest primitive, y: `newobj` (RayTracer.cpp:456-465) = identity for child rays
 	float4 *color;       // node-local colour, then combined colour; w = Color::alpha (distance)
 	int4 *aux;           // x: reflect child slot, y: refract child slot (-1 none), z: material (-1 = no surface), w: bit0 reflect, bit1 refract, bit2 Beer
 	uint8_t *shadow;     // [light][capacity]: 1 = occluded

@@ -26,6 +26,10 @@ struct Best
 {
 	float t;        // HitRes::distance so far
 	uint32_t id;    // RT_ID_NONE | prim flat index | RT_ID_TRI | oct<<28 | tri original index
+	// `newobj` of RayTracer.cpp:456-465: identity handed to shadow/secondary rays.  It follows the
+	// accepted hits EXCEPT a sphere's own inside-exit hit (Basic3DObject.cpp:153 returns obj == hr.obj,
+	// so `if (hr.obj != basehr.obj) newobj = hr.obj` leaves it at the previous winner).
+	uint32_t newobj;
 };
 
 // Conservative ray/box interval test: (plane - o) * (1/d) has bounded relative error, the far
@@ -118,7 +122,7 @@ __device__ __forceinline__ void leaf_tris(const SceneDev &S, const RayD &ray, ui
 				continue;
 		}
 		best.t = t;
-		best.id = RT_ID_TRI | ((uint32_t)oct << 28) | tri;
+		best.id = best.newobj = RT_ID_TRI | ((uint32_t)oct << 28) | tri;
 	}
 }
 
@@ -151,6 +155,7 @@ __device__ __forceinline__ void test_prim(const SceneDev &S, const RayD &ray, ui
 	{
 		best.t = t;
 		best.id = p;
+		if (!self) best.newobj = p;
 		if (ANY) done = true;
 	}
 }
@@ -159,7 +164,7 @@ __device__ __forceinline__ void test_prim(const SceneDev &S, const RayD &ray, ui
 template<bool ANY, bool TRIS, bool STATS>
 __device__ __forceinline__ void traverse(const SceneDev &S, const RayD &ray, const F3 &idir, int root,
 	float hr_distance, uint32_t rangeBegin, uint32_t rangeEnd, int *stack /* [RT_STACK][RT_BLOCK] slice */,
-	Best &best, bool &done, TravStats &st)
+	Best &best, bool &done, TravStats &st, uint32_t winLo = 0u, uint32_t winHi = 0xFFFFFFFFu)
 {
 	PartCache pc;
 	pc.part = 0xFFFFFFFFu, pc.mask = 0;
@@ -195,8 +200,11 @@ __device__ __forceinline__ void traverse(const SceneDev &S, const RayD &ray, con
 			else
 				for (uint32_t k = 0; k < count; ++k)
 				{
+					const uint32_t p = __ldg(&S.bvh_prims[first + k]);
+					if (p < winLo || p >= winHi)
+						continue;
 					if (STATS) ++st.prims;
-					test_prim<ANY>(S, ray, __ldg(&S.bvh_prims[first + k]), !(best.id & RT_ID_TRI) && best.id >= rangeBegin, best, done);
+					test_prim<ANY>(S, ray, p, !(best.id & RT_ID_TRI) && best.id >= rangeBegin, best, done);
 				}
 			if (ANY && done)
 				return;
@@ -223,7 +231,21 @@ __device__ __forceinline__ void trace_scene(const SceneDev &S, const RayD &ray, 
 			test_prim<ANY>(S, ray, it.first, false, best, done);
 		}
 		else if (it.kind == RT_ITEM_PRIMBVH)
-			traverse<ANY, false, STATS>(S, ray, idir, it.root, best.t, it.first, it.first + it.count, stack, best, done, st);
+		{
+			const uint32_t end = it.first + it.count;
+			if (!ANY && ray.isInside && !(ray.skip & RT_ID_TRI) && ray.skip >= it.first && ray.skip < end)
+			{
+				// the ray starts inside a sphere of this run: `newobj` depends on which hits were
+				// accepted before / after that sphere in object order, so walk the run in three
+				// order-respecting phases (primitives before it, the sphere itself, primitives after)
+				traverse<ANY, false, STATS>(S, ray, idir, it.root, best.t, it.first, end, stack, best, done, st, it.first, ray.skip);
+				if (STATS) ++st.prims;
+				test_prim<ANY>(S, ray, ray.skip, false, best, done);
+				traverse<ANY, false, STATS>(S, ray, idir, it.root, best.t, it.first, end, stack, best, done, st, ray.skip + 1u, end);
+			}
+			else
+				traverse<ANY, false, STATS>(S, ray, idir, it.root, best.t, it.first, end, stack, best, done, st);
+		}
 		else
 		{
 			const DevModel &M = S.models[it.first];

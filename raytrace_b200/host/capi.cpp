@@ -28,6 +28,14 @@ extern "C" {
 
 const char *rth_last_error(void) { return g_err.c_str(); }
 
+// FNV-1a-64, the golden-hash convention of BASELINE.md (offset 1469598103934665603, prime 1099511628211)
+unsigned long long rth_fnv1a64(const uint8_t *p, size_t n)
+{
+	unsigned long long h = 1469598103934665603ULL;
+	for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ULL; }
+	return h;
+}
+
 void *rth_scene_new(void) { return new HostScene(); }
 void rth_scene_free(void *h) { delete (HostScene *)h; }
 

@@ -1,0 +1,129 @@
+"""GPU parity tests (run on the B200 box with -m gpu).  Every case goes through the C++ RayTracer
+drop-in surface -> C ABI -> CUDA kernels and is compared with (a) the CPU oracle on the same
+flattened scene and (b) the golden vectors recorded from the unmodified reference.
+
+Tolerance: the path is integer/FP32 with one rounding per operation, so the bar is BIT-EXACT frames,
+hit identities and ray counts.  The only non-replayed arithmetic is powf/expf (FP64 evaluation
+rounded once on the device vs glibc on the host); a case may therefore differ by +-1 LSB on a
+handful of pixels, which is what `LSB_BUDGET` allows (0 observed so far)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import raytrace_b200 as R
+from parity_util import compare_ids, compare_images, oracle_render
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = json.load(open(os.path.join(HERE, "golden", "golden.json")))["cases"]
+LSB_BUDGET = 4   # pixels allowed to differ by exactly 1 LSB (powf/expf); anything else fails
+
+
+def case_id(c):
+    return f"{c['scene']}-{c['w']}x{c['h']}-l{c['level']}-n{c['n']}-t{c['type']}"
+
+
+def gpu_frame(sc, level, typ=R.MY_MODEL_RAYTRACE, want_ids=True, **kw):
+    rt = R.RayTracer(sc)
+    rt.maxLevel = level
+    img = rt.render(typ, flags=R.RT_FLAG_HIT_IDS if want_ids else 0, **kw)
+    ids = rt.hit_ids() if want_ids else None
+    return img, ids, rt.counters(), rt
+
+
+def assert_frames_match(img, ref):
+    if np.array_equal(img, ref):
+        return
+    r = compare_images(img, ref)
+    assert r["n_gt1"] == 0 and r["n_diff"] <= LSB_BUDGET, r
+
+
+@pytest.mark.parametrize("case", GOLDEN, ids=case_id)
+def test_gpu_matches_reference_golden_and_oracle(gpu_present, case):
+    sc = R.Scene(case["scene"], case["w"], case["h"], case["n"], case["parts"])
+    is_rt = case["type"] == 0x80
+    img, ids, c, _ = gpu_frame(sc, case["level"], case["type"], want_ids=is_rt)
+    oimg, oids, oc = oracle_render(sc, case["level"], case["type"], want_ids=is_rt)
+    assert_frames_match(img, oimg)
+    if np.array_equal(img, oimg):
+        assert R.fnv1a64(img) == case["hash"]            # == the unmodified reference's frame
+    rays = case["rays"]
+    assert c.primary == rays["primary"]
+    assert c.primary + c.shadow + c.reflect + c.refract == rays["total"]
+    if case["type"] != 7:
+        assert (c.shadow, c.reflect, c.refract) == (rays["shadow"], rays["reflect"], rays["refract"])
+    if is_rt:
+        assert compare_ids(ids, oids) == (0, 0)
+        assert R.fnv1a64(ids) == case["ids_hash"]
+
+
+def test_bvh_and_wavefront_are_deterministic(gpu_present):
+    sc = R.Scene("c4", 640, 384, 96, 6)
+    a, ia, ca, rt = gpu_frame(sc, 6)
+    b = rt.render(R.MY_MODEL_RAYTRACE)
+    assert np.array_equal(a, b)
+
+
+def test_row_shards_assemble_to_the_full_frame(gpu_present):
+    # interleaved 64-row tiles, tile % world == rank
+    sc = R.Scene("t_mesh", 640, 512)
+    full, _, cf, _ = gpu_frame(sc, 3, want_ids=False)
+    acc = np.full_like(full, 127)
+    total = 0
+    for r in range(3):
+        part, _, c, _ = gpu_frame(sc, 3, want_ids=False, rank=r, world=3)
+        rows = [y for y in range(512) if (y // 64) % 3 == r]
+        acc[rows] = part[rows]
+        total += c.primary + c.shadow + c.reflect + c.refract
+    assert np.array_equal(acc, full)
+    assert total == cf.primary + cf.shadow + cf.reflect + cf.refract
+
+
+def test_scene_edits_reupload_incrementally(gpu_present):
+    # MovePos / Switch / ChgMtl between frames (Scene.cpp:157-301): same tracer, new frame == oracle
+    sc = R.Scene("t_mesh", 384, 256)
+    rt = R.RayTracer(sc)
+    rt.maxLevel = 3
+    for edit in (lambda: None,
+                 lambda: sc.move(R.MY_MODEL_OBJECT, 2, 0.4, 0.0, -0.6),      # move the mesh: clTri + BVH rebuilt on device
+                 lambda: sc.set_light_position(1, -4, 7, 9),
+                 lambda: sc.chgmtl(2, 2),                                     # mesh becomes a mirror
+                 lambda: sc.switch(R.MY_MODEL_OBJECT, 1, False),              # hide the glass sphere
+                 lambda: sc.camera_move(0.5, -0.5, 2.0)):
+        edit()
+        img = rt.render(R.MY_MODEL_RAYTRACE)
+        oimg, _, _ = oracle_render(sc, 3, want_ids=False)
+        assert_frames_match(img, oimg)
+
+
+def test_full_size_c2_band_against_oracle(gpu_present):
+    # BASELINE config 2 at full size (1920x1080, 1024 spheres, 4 point lights, depth 5): one
+    # interleaved band set (1/8 of the frame) through the oracle, bit-exact; whole frame through
+    # size-independent properties (shards tile the frame, determinism, ray-count additivity).
+    sc = R.Scene("c2", 1920, 1080)
+    full, _, cf, rt = gpu_frame(sc, 5, want_ids=False)
+    assert (full[1024:] == 127).all()
+    part, _, cp, _ = gpu_frame(sc, 5, want_ids=False, rank=3, world=8)
+    opart, _, oc = oracle_render(sc, 5, want_ids=False, rank=3, world=8)
+    assert_frames_match(part, opart)
+    assert (cp.primary, cp.shadow, cp.reflect, cp.refract) == (oc.primary, oc.shadow, oc.reflect, oc.refract)
+    rows = [y for y in range(1024) if (y // 64) % 8 == 3]
+    assert np.array_equal(full[rows], part[rows])
+
+
+def test_full_size_c3_band_against_oracle(gpu_present):
+    # BASELINE config 3 at full size: 1 036 800-triangle Model, 2 025 parts, GPU-built LBVH, depth 5
+    sc = R.Scene("c3", 1920, 1080)
+    full, ids, cf, rt = gpu_frame(sc, 5)
+    c = rt.counters()
+    assert c.bvh_nodes >= 1036800 // 8 and c.bvh_depth < 64
+    part, pids, cp, _ = gpu_frame(sc, 5, rank=5, world=16)
+    opart, oids, oc = oracle_render(sc, 5, rank=5, world=16)
+    assert_frames_match(part, opart)
+    assert compare_ids(pids, oids) == (0, 0)
+    assert (cp.primary, cp.shadow, cp.reflect, cp.refract) == (oc.primary, oc.shadow, oc.reflect, oc.refract)
+    rows = [y for y in range(1024) if (y // 64) % 16 == 5]
+    assert np.array_equal(full[rows], part[rows])
