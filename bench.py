@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- Mrays/s and ms/frame of the trace-and-shade path on N B200s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c3] [--impl b200|reference]
+
+One "step" = one frame of the named configuration (default c3: 1920x1080, 1 036 800-triangle Model
++ ground plane, 2 lights, shadows + reflection depth 5 -- the configuration BASELINE.json's target
+is quoted on).  A ray = one closest-hit or one shadow any-hit query.
+
+  value    whole-job Mrays/s with the scene resident in HBM: K frames enqueued through the C ABI
+           (rt_render_async), timed with CUDA events on the launching stream, max over ranks.
+  e2e      same metric through the reference-facing call RayTracer::start() with HOST buffers:
+           every step re-flattens the Scene, uploads the per-frame tables (H2D) and reads the
+           RGB8 frame back into RayTracer::output (D2H) inside the timed region.
+  roofline FP32-issue roofline of the traversal kernels (k_trace + k_shadow): algorithmic FLOPs
+           from device counters (DESIGN.md "flop model") / their CUDA-event time, against
+           148 SMs x 128 lanes x sm_max_mhz of MEASURED_PEAKS.json (1 lane-instr = 1 flop because the
+           parity path is unfused); HBM figures are reported beside it as the secondary bound.
+  cpu_baseline  the reference's own CPU tracer (oracle/_ref/ref_render, else the oracle port) on
+           the box's host cores, on a bounded tile sample of the same workload.
+
+N > 1 (torchrun): the frame is split into interleaved 64-row tiles (tile % N == rank), the scene is
+replicated, and the RGB8 rows are gathered to rank 0 over NCCL each step ("strong" scaling).
+`--impl reference` times the reference CPU tracer itself (rank 0 only).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (scene, width, height, maxLevel, n, parts, description)
+    "c1": ("c1", 1088, 576, 1, 0, 0, "reference default scene (plane + sphere, 2 lights), 1088x576, depth 1"),
+    "c2": ("c2", 1920, 1080, 5, 0, 0, "1024 spheres + plane, 4 point lights, 1920x1080, depth 5"),
+    "c3": ("c3", 1920, 1080, 5, 0, 0, "1036800-triangle Model + plane, 2 lights, 1920x1080, depth 5, GPU LBVH"),
+    "c4": ("c4", 3840, 2160, 8, 0, 0, "4147200-triangle Model + 64 glass + 6 mirror spheres + plane, 3840x2160, depth 8"),
+}
+REF_TILES = {"c1": 153, "c2": 12, "c3": 6, "c4": 2}   # 64x64 tiles per reference step (bounded sample)
+
+
+def sm_peak_fp32_tflops():
+    """148 SMs x 128 FP32 lanes x max SM clock -> T lane-instr/s."""
+    mhz, src = 1965.0, "fallback 1965 MHz"
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        mhz, src = float(mp["sm_max_mhz"]), "MEASURED_PEAKS.json sm_max_mhz"
+        hbm = float(mp["hbm_gbs"])
+    except Exception:
+        hbm = 6650.0
+    return 148 * 128 * mhz * 1e6 / 1e12, src, hbm
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def run_reference(args, cfg):
+    """--impl reference: the reference's own CPU tracer on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    scene, w, h, level, n, parts, desc = cfg
+    cores = min(32, os.cpu_count() or 1)   # the reference hard-caps at 32 threads (RayTracer.h:22)
+    tiles = REF_TILES[args.config]
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_render")
+    if os.path.exists(ref):
+        kind = "reference"
+        out = subprocess.check_output([ref, "--scene", scene, "--width", str(w), "--height", str(h), "--level", str(level), "--n", str(n),
+                                       "--parts", str(parts), "--threads", str(cores), "--tiles", str(tiles), "--counts",
+                                       "--repeat", str(args.steps), "--warmup", str(args.warmup)]).decode()
+        j = json.loads(out.strip().splitlines()[-1])
+        secs, rays, px = j["step_s"], j["rays_per_step"], j["pixels"]
+    else:
+        kind = "port"
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import raytrace_b200 as R
+        from parity_util import oracle_render
+        sc = R.Scene(scene, w, h, n, parts)
+        world = max(1, (h // 64) * (w // 64) // tiles)
+        world = min(world, h // 64)
+        secs = []
+        for s in range(args.warmup + args.steps):
+            t0 = time.time()
+            _, _, c = oracle_render(sc, level, want_ids=False, threads=cores, rank=0, world=world)
+            if s >= args.warmup:
+                secs.append(time.time() - t0)
+        rays, px = c.primary + c.shadow + c.reflect + c.refract, c.primary
+    total = sum(secs)
+    mrays = rays * len(secs) / total / 1e6
+    sample = f"{tiles} seeded 64x64 tiles ({px} px, {rays} rays) of the {w}x{h} frame per step, {cores} threads"
+    line = {"impl": "reference", "metric": "Mrays/s", "value": mrays, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total / len(secs) * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.config}: {desc}", "sample": sample},
+            "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(args, cfg):
+    """Bounded reference sample timed beside the GPU numbers (rank 0, N=1 only)."""
+    scene, w, h, level, n, parts, desc = cfg
+    cores = min(32, os.cpu_count() or 1)
+    tiles = REF_TILES[args.config]
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_render")
+    try:
+        if os.path.exists(ref):
+            out = subprocess.check_output([ref, "--scene", scene, "--width", str(w), "--height", str(h), "--level", str(level), "--n", str(n),
+                                           "--parts", str(parts), "--threads", str(cores), "--tiles", str(tiles), "--counts",
+                                           "--repeat", "2", "--warmup", "1"], timeout=900).decode()
+            j = json.loads(out.strip().splitlines()[-1])
+            v = j["rays_per_step"] * len(j["step_s"]) / sum(j["step_s"]) / 1e6
+            return {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "reference",
+                    "sample": f"{tiles} seeded 64x64 tiles ({j['pixels']} px, {j['rays_per_step']} rays) of the {w}x{h} frame, 2 timed passes after 1 warm-up"}
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import raytrace_b200 as R
+        from parity_util import oracle_render
+        sc = R.Scene(scene, w, h, n, parts)
+        world = min(h // 64, max(1, (h // 64) * (w // 64) // tiles))
+        oracle_render(sc, level, want_ids=False, threads=cores, rank=0, world=world)
+        t0 = time.time()
+        _, _, c = oracle_render(sc, level, want_ids=False, threads=cores, rank=0, world=world)
+        dt = time.time() - t0
+        rays = c.primary + c.shadow + c.reflect + c.refract
+        return {"value": rays / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                "sample": f"row bands rank 0 of {world} ({c.primary} px, {rays} rays) of the {w}x{h} frame, 1 timed pass after 1 warm-up"}
+    except Exception as e:   # a baseline failure must not hide the GPU numbers
+        return {"value": None, "unit": "Mrays/s", "cores": cores, "kind": "unavailable", "sample": repr(e)[:200]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        return run_reference(args, cfg)
+
+    import numpy as np
+    import torch
+
+    import raytrace_b200 as R
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    scene, w, h, level, n, parts, desc = cfg
+
+    tmpdir = f"/tmp/rt_bench_{rank}"
+    os.makedirs(tmpdir, exist_ok=True)
+    sc = R.Scene(scene, w, h, n, parts, tmpdir=tmpdir)
+    rt = R.RayTracer(sc, device=local)           # the drop-in surface (used for e2e)
+    rt.maxLevel = level
+    h_ctx = C.c_void_p(rt.context())             # the tracer's C-ABI context, reused for the resident-scene loop
+
+    def ck(rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what}: {R.rt.rt_last_error().decode()}")
+
+    # everything (kernels, copies, NCCL) on torch's current stream so torch events see it
+    stream = torch.cuda.current_stream(dev)
+    ck(R.rt.rt_set_stream(h_ctx, C.c_void_p(stream.cuda_stream)), "rt_set_stream")
+    frame = torch.full((h, w, 3), 127, dtype=torch.uint8, device=dev)
+    ck(R.rt.rt_set_output(h_ctx, C.c_void_p(frame.data_ptr()), frame.numel()), "rt_set_output")
+    desc_ptr = sc.flatten()
+    ck(R.rt.rt_upload_scene(h_ctx, desc_ptr), "rt_upload_scene")
+    params = R.RenderParams(R.MY_MODEL_RAYTRACE, level, rank, world, 0, 0)
+
+    blk_h = h // 64
+    my_bands = [t for t in range(blk_h) if t % world == rank]
+    max_bands = (blk_h + world - 1) // world
+    band_bytes = 64 * w * 3
+    gathered = [torch.empty((max_bands, band_bytes), dtype=torch.uint8, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+    mine = torch.empty((max_bands, band_bytes), dtype=torch.uint8, device=dev) if world > 1 else None
+    full = torch.full((h, w, 3), 127, dtype=torch.uint8, device=dev) if (world > 1 and rank == 0) else None
+
+    def step():
+        ck(R.rt.rt_render_async(h_ctx, C.byref(params)), "rt_render_async")
+        if world > 1:
+            # NCCL framebuffer gather: this rank's 64-row bands -> rank 0, de-interleaved there
+            bands = frame.view(-1)[: blk_h * band_bytes].view(blk_h, band_bytes)
+            mine[: len(my_bands)].copy_(bands[rank::world])
+            dist.gather(mine, gathered, dst=0)
+            if rank == 0:
+                fb = full.view(-1)[: blk_h * band_bytes].view(blk_h, band_bytes)
+                for r in range(world):
+                    nb = len(range(r, blk_h, world))
+                    fb[r::world].copy_(gathered[r][:nb])
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    # ---- warm-up + one counted frame (ray totals are deterministic per configuration) ----------
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+    cnt = R.Counters()
+    ck(R.rt.rt_read_counters(h_ctx, C.byref(cnt)), "rt_read_counters")
+    rays_local = cnt.primary + cnt.shadow + cnt.reflect + cnt.refract
+    launches_per_step = cnt.launches + (0 if world == 1 else 0)
+    rays_t = torch.tensor([rays_local], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(rays_t)
+    rays_total = int(rays_t.item())
+
+    # ---- timed region: exactly K steps, CUDA events on the launching stream, max over ranks -----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage = {"trace": 0.0, "shadow": 0.0, "shade": 0.0, "other": 0.0, "render": 0.0}
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    sync_all()
+    # per-stage split from the library's own CUDA events (last timed frame, scaled to K steps)
+    ck(R.rt.rt_read_counters(h_ctx, C.byref(cnt)), "rt_read_counters")
+    stage = {"trace": cnt.trace_ms * args.steps, "shadow": cnt.shadow_ms * args.steps, "shade": cnt.shade_ms * args.steps,
+             "other": cnt.other_ms * args.steps, "render": cnt.render_ms * args.steps}
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    clocks = sampler.stop() if rank == 0 else None
+    value = rays_total * args.steps / (ms_total * 1e-3) / 1e6
+
+    # ---- traversal statistics for the roofline (one extra, untimed, counted frame) ---------------
+    pstats = R.RenderParams(R.MY_MODEL_RAYTRACE, level, rank, world, R.RT_FLAG_STATS, 0)
+    ck(R.rt.rt_render_async(h_ctx, C.byref(pstats)), "rt_render_async(stats)")
+    cs = R.Counters()
+    ck(R.rt.rt_read_counters(h_ctx, C.byref(cs)), "rt_read_counters")
+
+    # ---- e2e: RayTracer::start() with host buffers (flatten + H2D tables + render + D2H frame) ----
+    ck(R.rt.rt_set_output(h_ctx, None, 0), "rt_set_output")
+    for _ in range(2):
+        rt.start(R.MY_MODEL_RAYTRACE, rank=rank, world=world)
+        rt.wait()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rt.start(R.MY_MODEL_RAYTRACE, rank=rank, world=world)
+        rt.wait()
+    torch.cuda.synchronize(dev)
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = rays_total * args.steps / float(e2e_s.item()) / 1e6
+    ce = rt.counters()                           # bytes the library itself copied for the last start()
+    h2d, d2h = int(ce.h2d_bytes), int(ce.d2h_bytes)
+
+    if rank == 0:
+        peak, peak_src, hbm_peak = sm_peak_fp32_tflops()
+        # flop model: 22 per child box, 47 per triangle test, 23 per analytic primitive
+        flops = cs.nodes_visited * 2 * 22 + cs.tri_tests * 47 + cs.prim_tests * 23
+        trav_ms = (stage["trace"] + stage["shadow"]) / args.steps
+        trav_launches = (level + 1) * 2
+        achieved = flops / (trav_ms * 1e-3) / 1e12 if trav_ms > 0 else 0.0
+        queue_bytes = rays_local * 100   # ~100 B of ray/hit/node records written+read per ray
+        line = {
+            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.config}: {desc}", "rays_per_frame": rays_total, "pixels": w * (h // 64 * 64) if w % 64 == 0 else (w // 64 * 64) * (h // 64 * 64),
+                       "l2_policy": "per-frame working set (ray/hit/node queues + BVH + triangles, > 500 MB touched per frame) exceeds the 126 MB L2; no flush needed",
+                       "parallelism": f"image-space row tiles x{world}" if world > 1 else "single GPU",
+                       "ms_per_frame_kernels_only": stage["render"] / args.steps},
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": float(e2e_s.item()) / args.steps * 1e3,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": {"bound": "fp32_issue", "kernel": "k_trace + k_shadow (BVH traversal, all levels)", "achieved": achieved, "peak": peak,
+                         "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": f"148 SMs x 128 lanes x {peak_src} (of measured)",
+                         "traffic": None, "launches_per_step": trav_launches, "avg_launch_ms": trav_ms / trav_launches,
+                         "flops_per_step": flops, "nodes_per_ray": cs.nodes_visited / max(rays_local, 1), "tri_tests_per_ray": cs.tri_tests / max(rays_local, 1),
+                         "stage_ms": {k: v / args.steps for k, v in stage.items()},
+                         "hbm_secondary": {"queue_bytes_per_step": queue_bytes, "achieved_gbs": queue_bytes / (stage["render"] / args.steps * 1e-3) / 1e9,
+                                           "peak_gbs": hbm_peak}},
+            "clocks": clocks,
+            "build": {"upload_ms": cs.upload_ms, "lbvh_build_ms": cs.build_ms, "bvh_nodes": cs.bvh_nodes, "bvh_depth": cs.bvh_depth},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, cfg)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -188,6 +188,8 @@ typedef struct
 	uint32_t launches;                               /* kernels launched for the last frame */
 	uint32_t bvh_nodes, bvh_depth;
 	uint32_t pad0;
+	uint64_t h2d_bytes;    /* host->device bytes of the last rt_upload_scene + rt_render_async */
+	uint64_t d2h_bytes;    /* device->host bytes of the last frame (counters + rt_read_output) */
 } rt_counters;
 
 const char *rt_last_error(void);
@@ -217,6 +219,9 @@ int rt_stop(rt_ctx *ctx);
 int rt_read_output(rt_ctx *ctx, uint8_t *rgb, size_t stride);
 /* device-resident framebuffer of the last frame (for NCCL gathers / zero-copy consumers) */
 int rt_output_device(rt_ctx *ctx, void **device_ptr, size_t *bytes);
+/* render into a caller-owned device buffer of >= 3*width*height bytes (e.g. a torch tensor that is
+ * then gathered over NCCL); NULL switches back to the library-owned framebuffer */
+int rt_set_output(rt_ctx *ctx, void *device_ptr, size_t bytes);
 
 /* diagnostics / parity taps */
 int rt_read_hit_ids(rt_ctx *ctx, rt_hit_id *ids /* width*height */);

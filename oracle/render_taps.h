@@ -140,8 +140,14 @@ inline void primary_ids(Scene &scene, RayTracer &rt, int width, int height, HitI
 }
 
 // `tiles` seeded 64x64 tiles, traced pixel by pixel through RTfrac/RTflec on `threads` threads.
-inline long render_tiles(Scene &scene, RayTracer &rt, int width, int height, int tiles, int seed, int threads, int type)
+inline long render_tiles(Scene &scene, RayTracer &rt, int width, int height, int tiles, int seed, int threads, int type, Counts *counts)
 {
+	CountingProxy *proxy = nullptr;
+	if (counts)
+	{
+		proxy = new CountingProxy();
+		scene.Objects.insert(scene.Objects.begin(), proxy);
+	}
 	rt.width = width, rt.height = height;
 	for (auto dobj : scene.Objects)
 		if (dobj->bShow) dobj->RTPrepare();
@@ -180,6 +186,13 @@ inline long render_tiles(Scene &scene, RayTracer &rt, int width, int height, int
 			}
 		});
 	for (auto &t : pool) t.join();
+	if (proxy)
+	{
+		scene.Objects.erase(scene.Objects.begin());
+		counts->primary = proxy->n[MY_RAY_BASERAY], counts->shadow = proxy->n[MY_RAY_SHADOWRAY] + proxy->n[0];
+		counts->reflect = proxy->n[MY_RAY_REFLECTRAY], counts->refract = proxy->n[MY_RAY_REFRACTRAY];
+		delete proxy;
+	}
 	return (long)tiles * 64 * 64;
 }
 

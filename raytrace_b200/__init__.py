@@ -191,6 +191,9 @@ class Context:
         _check(rt.rt_output_device(self._h, C.byref(p), C.byref(n)), "rt_output_device")
         return p.value, n.value
 
+    def set_output(self, device_ptr: int, nbytes: int):
+        _check(rt.rt_set_output(self._h, C.c_void_p(device_ptr), nbytes), "rt_set_output")
+
     def hit_ids(self, width, height) -> np.ndarray:
         out = np.zeros(width * height, dtype=HIT_DTYPE)
         _check(rt.rt_read_hit_ids(self._h, out.ctypes.data_as(C.POINTER(HitId))), "rt_read_hit_ids")

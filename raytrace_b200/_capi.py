@@ -84,7 +84,8 @@ class Counters(C.Structure):
                 ("nodes_visited", C.c_uint64), ("tri_tests", C.c_uint64), ("prim_tests", C.c_uint64),
                 ("render_ms", C.c_double), ("trace_ms", C.c_double), ("shadow_ms", C.c_double),
                 ("shade_ms", C.c_double), ("other_ms", C.c_double), ("upload_ms", C.c_double), ("build_ms", C.c_double),
-                ("launches", C.c_uint32), ("bvh_nodes", C.c_uint32), ("bvh_depth", C.c_uint32), ("pad0", C.c_uint32)]
+                ("launches", C.c_uint32), ("bvh_nodes", C.c_uint32), ("bvh_depth", C.c_uint32), ("pad0", C.c_uint32),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
 # every symbol include/rt_b200.h declares: name -> (restype, argtypes)
@@ -101,6 +102,7 @@ RT_SYMBOLS = {
     "rt_stop": (C.c_int, [C.c_void_p]),
     "rt_read_output": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "rt_output_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "rt_set_output": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "rt_read_hit_ids": (C.c_int, [C.c_void_p, C.POINTER(HitId)]),
     "rt_read_counters": (C.c_int, [C.c_void_p, C.POINTER(Counters)]),
 }

@@ -39,8 +39,9 @@ template<class T> struct DevBuf
 		if (e == cudaSuccess) cap = want;
 		return e;
 	}
-	cudaError_t upload(const T *src, size_t n, cudaStream_t st)
+	cudaError_t upload(const T *src, size_t n, cudaStream_t st, uint64_t *bytes = nullptr)
 	{
+		if (bytes) *bytes += n * sizeof(T);
 		cudaError_t e = reserve(n);
 		if (e != cudaSuccess || n == 0) return e;
 		return cudaMemcpyAsync(p, src, n * sizeof(T), cudaMemcpyHostToDevice, st);
@@ -64,6 +65,11 @@ struct rt_ctx
 	cudaStream_t stream = nullptr;
 	bool ownStream = false;
 	cudaEvent_t evStart = nullptr, evStop = nullptr, evA = nullptr, evB = nullptr;
+	cudaEvent_t evStage[4 * (RT_MAX_LEVELS + 1) + 2];   // per level: before trace, after trace, after shadow, after shade; then combine begin/end
+	bool stageTiming = true;
+	double traceMs = 0, shadowMs = 0, shadeMs = 0, otherMs = 0;
+	uint8_t *extOut = nullptr;      // caller-provided device framebuffer (rt_set_output)
+	size_t extOutBytes = 0;
 
 	// resident scene
 	bool hasScene = false;
@@ -95,10 +101,12 @@ struct rt_ctx
 	LevelStore levels[RT_MAX_LEVELS + 2];
 	DevBuf<uint8_t> out;
 	int outW = 0, outH = 0;
+	uint8_t *fb = nullptr;          // framebuffer of the last frame (c->out or extOut)
 	rt_render_params lastParams;
 	uint32_t lastPixels = 0, lastLaunches = 0, lastMaxLevel = 0;
 	bool frameInFlight = false, frameValid = false;
 	double uploadMs = 0, buildMs = 0, renderMs = 0;
+	uint64_t uploadBytes = 0, frameH2D = 0, frameD2H = 0;
 	float levelFactor = 2.0f;
 };
 
@@ -124,6 +132,8 @@ extern "C" int rt_create(int device, rt_ctx **out)
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	c->ownStream = true;
 	CU(cudaEventCreate(&c->evStart)); CU(cudaEventCreate(&c->evStop)); CU(cudaEventCreate(&c->evA)); CU(cudaEventCreate(&c->evB));
+	for (auto &e : c->evStage) CU(cudaEventCreate(&e));
+	if (const char *v = getenv("RT_B200_STAGE_TIMING")) c->stageTiming = atoi(v) != 0;
 	CU(cudaMallocHost(&c->hFrame, sizeof(FrameParams)));
 	CU(cudaMalloc(&c->dFrame, sizeof(FrameParams)));
 	CU(cudaMallocHost(&c->hWave, sizeof(WaveState)));
@@ -148,6 +158,7 @@ extern "C" void rt_destroy(rt_ctx *c)
 	rtb_free_scratch(c->scratch);
 	cudaFreeHost(c->hFrame), cudaFree(c->dFrame), cudaFreeHost(c->hWave), cudaFree(c->dWave);
 	cudaEventDestroy(c->evStart), cudaEventDestroy(c->evStop), cudaEventDestroy(c->evA), cudaEventDestroy(c->evB);
+	for (auto &e : c->evStage) cudaEventDestroy(e);
 	if (c->ownStream) cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -205,6 +216,8 @@ extern "C" int rt_upload_scene(rt_ctx *c, const rt_scene_desc *s)
 
 	cudaStream_t st = c->stream;
 	CU(cudaEventRecord(c->evA, st));
+	c->uploadBytes = 0;
+	uint64_t *ub = &c->uploadBytes;
 
 	// ---- cheap tables: always refreshed -------------------------------------------------------
 	c->camera = s->camera, c->envLight = s->env_light;
@@ -219,11 +232,11 @@ extern "C" int rt_upload_scene(rt_ctx *c, const rt_scene_desc *s)
 			m[4 * i + 3] = make_float4(r.shiness, r.reflect, r.refract, r.rfr);
 			if (r.refract > 0.01f) c->anyRefract = true;
 		}
-		CU(c->materials.upload(m.data(), m.size(), st));
+		CU(c->materials.upload(m.data(), m.size(), st, ub));
 		std::vector<int4> t(s->n_textures);
 		for (uint32_t i = 0; i < s->n_textures; ++i) t[i] = make_int4(s->textures[i].w, s->textures[i].h, (int)s->textures[i].offset, 0);
-		CU(c->textures.upload(t.data(), t.size(), st));
-		CU(c->texels.upload(s->texels, s->texel_bytes, st));
+		CU(c->textures.upload(t.data(), t.size(), st, ub));
+		CU(c->texels.upload(s->texels, s->texel_bytes, st, ub));
 		CU(cudaStreamSynchronize(st));   // staging vectors go out of scope
 	}
 
@@ -241,13 +254,13 @@ extern "C" int rt_upload_scene(rt_ctx *c, const rt_scene_desc *s)
 
 	if (trisChanged && s->n_tris)
 	{
-		CU(c->triPoints.upload((const float4 *)s->tri_points, 3 * (size_t)s->n_tris, st));
-		CU(c->triNorms.upload((const float4 *)s->tri_norms, 3 * (size_t)s->n_tris, st));
-		CU(c->triTcoords.upload((const float2 *)s->tri_tcoords, 3 * (size_t)s->n_tris, st));
+		CU(c->triPoints.upload((const float4 *)s->tri_points, 3 * (size_t)s->n_tris, st, ub));
+		CU(c->triNorms.upload((const float4 *)s->tri_norms, 3 * (size_t)s->n_tris, st, ub));
+		CU(c->triTcoords.upload((const float2 *)s->tri_tcoords, 3 * (size_t)s->n_tris, st, ub));
 		std::vector<uint32_t> tp(s->n_tris);
 		for (uint32_t p = 0; p < s->n_parts; ++p)
 			for (uint32_t k = 0; k < s->parts[p].tri_count; ++k) tp[s->parts[p].tri_begin + k] = p;
-		CU(c->triPart.upload(tp.data(), tp.size(), st));
+		CU(c->triPart.upload(tp.data(), tp.size(), st, ub));
 		CU(cudaStreamSynchronize(st));
 	}
 
@@ -271,8 +284,8 @@ extern "C" int rt_upload_scene(rt_ctx *c, const rt_scene_desc *s)
 				pg[4 * i + 1] = f4(p.a), pg[4 * i + 2] = f4(p.b), pg[4 * i + 3] = f4(p.c);
 			pm[i] = make_int4((int)p.kind, (int)p.material, p.texture, (int)((p.object << 8) | (p.sub & 0xFF)));
 		}
-		CU(c->primGeom.upload(pg.data(), pg.size(), st));
-		CU(c->primMeta.upload(pm.data(), pm.size(), st));
+		CU(c->primGeom.upload(pg.data(), pg.size(), st, ub));
+		CU(c->primMeta.upload(pm.data(), pm.size(), st, ub));
 
 		// ---- models / parts -----------------------------------------------------------------------
 		std::vector<DevModel> dm(s->n_models);
@@ -300,10 +313,10 @@ extern "C" int rt_upload_scene(rt_ctx *c, const rt_scene_desc *s)
 			}
 			dm[m].tri_begin = tb == 0xFFFFFFFFu ? 0 : tb, dm[m].tri_count = tc;
 		}
-		CU(c->dModels.upload(dm.data(), dm.size(), st));
-		CU(c->dParts.upload(dp.data(), dp.size(), st));
-		CU(c->partMid.upload(mid.data(), mid.size(), st));
-		CU(c->partPos.upload(pos.data(), pos.size(), st));
+		CU(c->dModels.upload(dm.data(), dm.size(), st, ub));
+		CU(c->dParts.upload(dp.data(), dp.size(), st, ub));
+		CU(c->partMid.upload(mid.data(), mid.size(), st, ub));
+		CU(c->partPos.upload(pos.data(), pos.size(), st, ub));
 		CU(cudaStreamSynchronize(st));
 
 		// ---- scene-order item list + BVH budget ---------------------------------------------------
@@ -383,7 +396,7 @@ extern "C" int rt_upload_scene(rt_ctx *c, const rt_scene_desc *s)
 		c->bvhNodes = nodeCursor;
 		if (c->bvhDepth + 1 > RT_STACK)
 			return fail(RT_E_LIMIT, "LBVH depth %u exceeds the traversal stack (%d)", c->bvhDepth, RT_STACK);
-		CU(c->items.upload(items.data(), items.size(), st));
+		CU(c->items.upload(items.data(), items.size(), st, ub));
 		CU(cudaEventRecord(c->evStop, st));
 		CU(cudaStreamSynchronize(st));
 		float ms = 0;
@@ -468,12 +481,19 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 	const uint32_t nPix = (uint32_t)F.blk_w * 64u * F.n_rows;
 
 	// framebuffer: margins stay 127 (RayTracer.cpp:620)
-	if (c->outW != W || c->outH != H || !c->out.p)
+	uint8_t *fb;
+	if (c->extOut)
+	{
+		if (c->extOutBytes < (size_t)W * H * 3) return fail(RT_E_INVALID, "rt_render_async: external framebuffer holds %zu bytes, frame needs %zu", c->extOutBytes, (size_t)W * H * 3);
+		fb = c->extOut;
+	}
+	else
 	{
 		CU(c->out.reserve((size_t)W * H * 3));
-		c->outW = W, c->outH = H;
+		fb = c->out.p;
 	}
-	CU(cudaMemsetAsync(c->out.p, 127, (size_t)W * H * 3, st));
+	c->outW = W, c->outH = H, c->fb = fb;
+	CU(cudaMemsetAsync(fb, 127, (size_t)W * H * 3, st));
 
 	const bool refr = c->anyRefract && p->type != RT_TYPE_REFLECT;
 	for (uint32_t l = 0; l <= p->max_level; ++l)
@@ -489,6 +509,7 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 	Wv.count[0] = nPix;
 	CU(cudaMemcpyAsync(c->dFrame, c->hFrame, sizeof(FrameParams), cudaMemcpyHostToDevice, st));
 	CU(cudaMemcpyAsync(c->dWave, c->hWave, sizeof(WaveState), cudaMemcpyHostToDevice, st));
+	c->frameH2D = sizeof(FrameParams) + sizeof(WaveState), c->frameD2H = sizeof(WaveState);
 	CU(cudaEventRecord(c->evStart, st));
 
 	const bool stats = (p->flags & RT_FLAG_STATS) != 0;
@@ -501,13 +522,17 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 			const LevelBuf L = level_buf(c->levels[l]), N = level_buf(c->levels[l + 1]);
 			const float zNear = l == 0 ? F.zNear : 0.0f;
 			const uint32_t maxRays = c->levels[l].capacity;
+			if (c->stageTiming) CU(cudaEventRecord(c->evStage[4 * l], st));
 			rtk_trace(st, c->S, L, &c->dWave->count[l], c->dWave, maxRays, c->sms, stats); ++launches;
+			if (c->stageTiming) CU(cudaEventRecord(c->evStage[4 * l + 1], st));
 			if (enabledLights) { rtk_shadow(st, c->S, c->dFrame, L, &c->dWave->count[l], c->dWave, zNear, F.n_lights, maxRays, c->sms, stats); ++launches; }
+			if (c->stageTiming) CU(cudaEventRecord(c->evStage[4 * l + 2], st));
 			rtk_shade(st, c->S, c->dFrame, L, N, c->dWave, l, zNear, maxRays, c->sms); ++launches;
+			if (c->stageTiming) CU(cudaEventRecord(c->evStage[4 * l + 3], st));
 		}
 		for (int l = (int)p->max_level; l >= 0; --l)
 		{
-			rtk_combine(st, c->S, c->dFrame, level_buf(c->levels[l]), level_buf(c->levels[l + 1]), c->dWave, (uint32_t)l, c->out.p, c->levels[l].capacity, c->sms);
+			rtk_combine(st, c->S, c->dFrame, level_buf(c->levels[l]), level_buf(c->levels[l + 1]), c->dWave, (uint32_t)l, fb, c->levels[l].capacity, c->sms);
 			++launches;
 		}
 	}
@@ -528,6 +553,19 @@ static int finish_frame(rt_ctx *c)
 	CU(cudaEventElapsedTime(&ms, c->evStart, c->evStop));
 	c->renderMs = ms;
 	c->frameInFlight = false;
+	c->traceMs = c->shadowMs = c->shadeMs = c->otherMs = 0;
+	if (c->stageTiming && c->lastPixels)
+	{
+		for (uint32_t l = 0; l <= c->lastMaxLevel; ++l)
+		{
+			float a = 0, b = 0, d = 0;
+			cudaEventElapsedTime(&a, c->evStage[4 * l], c->evStage[4 * l + 1]);
+			cudaEventElapsedTime(&b, c->evStage[4 * l + 1], c->evStage[4 * l + 2]);
+			cudaEventElapsedTime(&d, c->evStage[4 * l + 2], c->evStage[4 * l + 3]);
+			c->traceMs += a, c->shadowMs += b, c->shadeMs += d;
+		}
+		c->otherMs = c->renderMs - c->traceMs - c->shadowMs - c->shadeMs;
+	}
 	if (c->hWave->overflow)
 		return fail(RT_E_LIMIT, "a ray level overflowed its queue (capacity factor %.2f); raise RT_B200_LEVEL_FACTOR", c->levelFactor);
 	c->frameValid = true;
@@ -569,11 +607,12 @@ extern "C" int rt_read_output(rt_ctx *c, uint8_t *rgb, size_t stride)
 {
 	if (!c || !rgb) return fail(RT_E_INVALID, "rt_read_output: NULL argument");
 	if (c->frameInFlight) { int rc = finish_frame(c); if (rc != RT_OK) return rc; }
-	if (!c->out.p) return fail(RT_E_STATE, "rt_read_output: nothing rendered yet");
+	if (!c->fb) return fail(RT_E_STATE, "rt_read_output: nothing rendered yet");
 	CU(cudaSetDevice(c->device));
 	const size_t row = (size_t)c->outW * 3;
 	if (stride < row) return fail(RT_E_INVALID, "rt_read_output: stride %zu < %zu", stride, row);
-	CU(cudaMemcpy2DAsync(rgb, stride, c->out.p, row, row, (size_t)c->outH, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaMemcpy2DAsync(rgb, stride, c->fb, row, row, (size_t)c->outH, cudaMemcpyDeviceToHost, c->stream));
+	c->frameD2H += row * (size_t)c->outH;
 	CU(cudaStreamSynchronize(c->stream));
 	return RT_OK;
 }
@@ -581,9 +620,17 @@ extern "C" int rt_read_output(rt_ctx *c, uint8_t *rgb, size_t stride)
 extern "C" int rt_output_device(rt_ctx *c, void **ptr, size_t *bytes)
 {
 	if (!c || !ptr) return fail(RT_E_INVALID, "rt_output_device: NULL argument");
-	if (!c->out.p) return fail(RT_E_STATE, "rt_output_device: nothing rendered yet");
-	*ptr = c->out.p;
+	if (!c->fb) return fail(RT_E_STATE, "rt_output_device: nothing rendered yet");
+	*ptr = c->fb;
 	if (bytes) *bytes = (size_t)c->outW * c->outH * 3;
+	return RT_OK;
+}
+
+extern "C" int rt_set_output(rt_ctx *c, void *device_ptr, size_t bytes)
+{
+	if (!c) return fail(RT_E_INVALID, "rt_set_output: ctx is NULL");
+	if (c->frameInFlight) { int rc = finish_frame(c); if (rc != RT_OK) return rc; }
+	c->extOut = (uint8_t *)device_ptr, c->extOutBytes = device_ptr ? bytes : 0;
 	return RT_OK;
 }
 
@@ -643,6 +690,7 @@ extern "C" int rt_read_counters(rt_ctx *c, rt_counters *out)
 	if (c->frameInFlight) { int rc = finish_frame(c); if (rc != RT_OK) return rc; }
 	memset(out, 0, sizeof *out);
 	out->upload_ms = c->uploadMs, out->build_ms = c->buildMs, out->bvh_nodes = c->bvhNodes, out->bvh_depth = c->bvhDepth;
+	out->h2d_bytes = c->uploadBytes + c->frameH2D, out->d2h_bytes = c->frameD2H;
 	if (!c->frameValid) return RT_OK;
 	const WaveState &W = *c->hWave;
 	uint32_t enabled = 0;
@@ -652,6 +700,7 @@ extern "C" int rt_read_counters(rt_ctx *c, rt_counters *out)
 	out->shadow = W.n_hits * enabled;
 	out->nodes_visited = W.nodes_visited, out->tri_tests = W.tri_tests, out->prim_tests = W.prim_tests;
 	out->render_ms = c->renderMs;
+	out->trace_ms = c->traceMs, out->shadow_ms = c->shadowMs, out->shade_ms = c->shadeMs, out->other_ms = c->otherMs;
 	out->launches = c->lastLaunches;
 	return RT_OK;
 }

@@ -45,7 +45,7 @@ int main(int argc, char **argv)
 {
 	rtscenes::SceneArgs sa;
 	int width = 1088, height = 576, level = 1, type = MY_MODEL_RAYTRACE, threads = 8, repeat = 1;
-	int tiles = 0, seed = 0;
+	int tiles = 0, seed = 0, warmup = 0;
 	bool counts = false;
 	std::string out, ids;
 	for (int i = 1; i < argc; ++i)
@@ -67,6 +67,7 @@ int main(int argc, char **argv)
 		else if (k == "--counts") counts = true;
 		else if (k == "--tiles") tiles = atoi(val());
 		else if (k == "--seed") seed = atoi(val());
+		else if (k == "--warmup") warmup = atoi(val());
 		else if (k == "--gpus") rt_taps::set_gpus(atoi(val()));
 		else { fprintf(stderr, "unknown option %s\n", k.c_str()); return 2; }
 	}
@@ -83,14 +84,26 @@ int main(int argc, char **argv)
 	rt_taps::Counts cnt;
 	if (tiles > 0)
 	{
-		// bounded CPU sample: `tiles` seeded 64x64 tiles through the per-pixel entry
-		double t0 = now_s();
-		long px = rt_taps::render_tiles(scene, rayt, width, height, tiles, seed, threads, type);
-		double t1 = now_s();
-		walls.push_back(t1 - t0); uses.push_back(t1 - t0);
-		printf("{\"scene\":\"%s\",\"arm\":\"%s\",\"w\":%d,\"h\":%d,\"level\":%d,\"threads\":%d,\"tiles\":%d,\"pixels\":%ld,\"wall_s\":%.6f,\"hash\":\"%016llx\"}\n",
-			sa.name.c_str(), rt_taps::arm(), width, height, level, threads, tiles, px, t1 - t0,
-			(unsigned long long)fnv1a64(rayt.output, need));
+		// bounded CPU sample: `tiles` seeded 64x64 tiles through the per-pixel entry, `warmup`
+		// untimed + `repeat` timed passes over the same tiles; rays counted in one extra pass
+		long px = 0;
+		for (int r = 0; r < warmup + repeat; ++r)
+		{
+			double t0 = now_s();
+			px = rt_taps::render_tiles(scene, rayt, width, height, tiles, seed, threads, type, nullptr);
+			double t1 = now_s();
+			if (r >= warmup) walls.push_back(t1 - t0);
+		}
+		unsigned long long rays = 0;
+		if (counts)
+		{
+			rt_taps::render_tiles(scene, rayt, width, height, tiles, seed, threads, type, &cnt);
+			rays = cnt.primary + cnt.shadow + cnt.reflect + cnt.refract;
+		}
+		printf("{\"scene\":\"%s\",\"arm\":\"%s\",\"w\":%d,\"h\":%d,\"level\":%d,\"threads\":%d,\"tiles\":%d,\"pixels\":%ld,\"rays_per_step\":%llu,\"hash\":\"%016llx\",\"step_s\":[",
+			sa.name.c_str(), rt_taps::arm(), width, height, level, threads, tiles, px, rays, (unsigned long long)fnv1a64(rayt.output, need));
+		for (size_t i = 0; i < walls.size(); ++i) printf("%s%.6f", i ? "," : "", walls[i]);
+		printf("]}\n");
 		return 0;
 	}
 	for (int r = 0; r < repeat; ++r)
