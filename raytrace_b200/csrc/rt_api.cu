@@ -55,8 +55,9 @@ struct LevelStore
 	DevBuf<uint2> ray_meta, hit_id;
 	DevBuf<int4> aux;
 	DevBuf<uint8_t> shadow;
+	DevBuf<uint32_t> hit_list;
 	uint32_t capacity = 0, lights = 0;
-	void release() { ray_o.release(), ray_d.release(), hit_p.release(), color.release(), ray_meta.release(), hit_id.release(), aux.release(), shadow.release(); capacity = 0; }
+	void release() { ray_o.release(), ray_d.release(), hit_p.release(), color.release(), ray_meta.release(), hit_id.release(), aux.release(), shadow.release(), hit_list.release(); capacity = 0; }
 };
 
 struct rt_ctx
@@ -427,7 +428,7 @@ static int ensure_level(rt_ctx *c, uint32_t l, uint32_t cap, uint32_t lights)
 	if (cap <= L.capacity && lights <= L.lights) return RT_OK;
 	L.capacity = 0;
 	CU(L.ray_o.reserve(cap)); CU(L.ray_d.reserve(cap)); CU(L.ray_meta.reserve(cap)); CU(L.hit_p.reserve(cap));
-	CU(L.hit_id.reserve(cap)); CU(L.color.reserve(cap)); CU(L.aux.reserve(cap)); CU(L.shadow.reserve((size_t)cap * (lights ? lights : 1)));
+	CU(L.hit_id.reserve(cap)); CU(L.color.reserve(cap)); CU(L.aux.reserve(cap)); CU(L.shadow.reserve((size_t)cap * (lights ? lights : 1))); CU(L.hit_list.reserve(cap));
 	L.capacity = cap, L.lights = lights;
 	return RT_OK;
 }
@@ -436,7 +437,7 @@ static LevelBuf level_buf(const LevelStore &L)
 {
 	LevelBuf b;
 	b.ray_o = L.ray_o.p, b.ray_d = L.ray_d.p, b.ray_meta = L.ray_meta.p, b.hit_p = L.hit_p.p, b.hit_id = L.hit_id.p;
-	b.color = L.color.p, b.aux = L.aux.p, b.shadow = L.shadow.p, b.capacity = L.capacity;
+	b.color = L.color.p, b.aux = L.aux.p, b.shadow = L.shadow.p, b.hit_list = L.hit_list.p, b.capacity = L.capacity;
 	return b;
 }
 
@@ -476,8 +477,9 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 		DevLight &d = F.lights[k];
 		d.position = f4(l.position), d.ambient = f4(l.ambient), d.diffuse = f4(l.diffuse), d.specular = f4(l.specular), d.attenuation = f4(l.attenuation);
 		d.type = l.type, d.enabled = l.enabled;
-		if (l.enabled) ++enabledLights;
+		if (l.enabled) F.enabled_index[enabledLights++] = k;
 	}
+	F.n_enabled = enabledLights;
 	const uint32_t nPix = (uint32_t)F.blk_w * 64u * F.n_rows;
 
 	// framebuffer: margins stay 127 (RayTracer.cpp:620)
@@ -523,9 +525,9 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 			const float zNear = l == 0 ? F.zNear : 0.0f;
 			const uint32_t maxRays = c->levels[l].capacity;
 			if (c->stageTiming) CU(cudaEventRecord(c->evStage[4 * l], st));
-			rtk_trace(st, c->S, L, &c->dWave->count[l], c->dWave, maxRays, c->sms, stats); ++launches;
+			rtk_trace(st, c->S, c->dFrame, L, c->dWave, l, zNear, maxRays, c->sms, stats); ++launches;
 			if (c->stageTiming) CU(cudaEventRecord(c->evStage[4 * l + 1], st));
-			if (enabledLights) { rtk_shadow(st, c->S, c->dFrame, L, &c->dWave->count[l], c->dWave, zNear, F.n_lights, maxRays, c->sms, stats); ++launches; }
+			if (enabledLights) { rtk_shadow(st, c->S, c->dFrame, L, c->dWave, l, enabledLights, maxRays, c->sms, stats); ++launches; }
 			if (c->stageTiming) CU(cudaEventRecord(c->evStage[4 * l + 2], st));
 			rtk_shade(st, c->S, c->dFrame, L, N, c->dWave, l, zNear, maxRays, c->sms); ++launches;
 			if (c->stageTiming) CU(cudaEventRecord(c->evStage[4 * l + 3], st));
@@ -697,7 +699,9 @@ extern "C" int rt_read_counters(rt_ctx *c, rt_counters *out)
 	for (const rt_light &l : c->lights) if (l.enabled) ++enabled;
 	out->primary = W.count[0];
 	out->reflect = W.n_reflect, out->refract = W.n_refract;
-	out->shadow = W.n_hits * enabled;
+	unsigned long long hits = 0;
+	for (uint32_t l = 0; l <= c->lastMaxLevel; ++l) hits += W.n_hit[l];
+	out->shadow = hits * enabled;
 	out->nodes_visited = W.nodes_visited, out->tri_tests = W.tri_tests, out->prim_tests = W.prim_tests;
 	out->render_ms = c->renderMs;
 	out->trace_ms = c->traceMs, out->shadow_ms = c->shadowMs, out->shade_ms = c->shadeMs, out->other_ms = c->otherMs;

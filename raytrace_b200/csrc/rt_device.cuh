@@ -69,6 +69,9 @@ struct FrameParams
 	uint32_t rank, world;
 	uint32_t n_rows;           // rows rendered by this shard
 	uint32_t n_lights;
+	uint32_t n_enabled;        // enabled lights, listed in light order
+	uint32_t enabled_index[RT_MAX_LIGHTS];
+	uint32_t pad_[3];
 	float4 env_light;
 	DevLight lights[RT_MAX_LIGHTS];
 };

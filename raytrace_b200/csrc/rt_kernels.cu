@@ -111,22 +111,61 @@ __global__ void __launch_bounds__(256) k_raygen(const FrameParams *__restrict__ 
 
 // ---- closest hit ---------------------------------------------------------------------------------
 
-template<bool STATS>
-__global__ void __launch_bounds__(RT_BLOCK) k_trace(SceneDev S, LevelBuf L, const uint32_t *__restrict__ count, WaveState *ws)
+// Persistent warps: each warp pulls 32 consecutive rays at a time from the level's queue (one
+// atomic per fetch), so SMs stay busy until the queue is dry and ray order (8x4 pixel tiles for
+// primary rays, parent order for secondary rays) keeps the lanes of a warp coherent.
+__device__ __forceinline__ uint32_t warp_fetch(uint32_t *head)
 {
-	__shared__ int s_stack[RT_STACK * RT_BLOCK];
-	int *stack = s_stack + threadIdx.x;
-	const uint32_t n = *count < L.capacity ? *count : L.capacity;
+	uint32_t base = 0;
+	if ((threadIdx.x & 31) == 0) base = atomicAdd(head, 32u);
+	return __shfl_sync(0xffffffffu, base, 0);
+}
+
+__device__ __forceinline__ uint32_t warp_append(uint32_t *counter, bool want)
+{
+	// warp-aggregated queue append: one atomic per warp, slots in lane order (keeps rays coherent)
+	const uint32_t m = __ballot_sync(0xffffffffu, want);
+	if (m == 0) return 0xFFFFFFFFu;
+	const uint32_t lane = threadIdx.x & 31u, leader = __ffs((int)m) - 1;
+	uint32_t base = 0;
+	if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+	base = __shfl_sync(0xffffffffu, base, leader);
+	return want ? base + __popc(m & ((1u << lane) - 1u)) : 0xFFFFFFFFu;
+}
+
+template<bool STATS>
+__global__ void __launch_bounds__(RT_BLOCK, 8) k_trace(SceneDev S, const FrameParams *__restrict__ Fp, LevelBuf L, WaveState *ws, uint32_t level, float zNear)
+{
+	const float zFar = Fp->zFar;
+	const uint32_t n = ws->count[level] < L.capacity ? ws->count[level] : L.capacity;
 	TravStats st = { 0, 0, 0 };
-	for (uint32_t i = blockIdx.x * RT_BLOCK + threadIdx.x; i < n; i += gridDim.x * RT_BLOCK)
+	while (true)
 	{
-		const RayD ray = load_ray(L, i);
-		Best best = { 1e20f, RT_ID_NONE, ray.skip };
-		bool done = false;
-		trace_scene<false, STATS>(S, ray, stack, best, done, st);
-		const F3 P = ray.o + ray.d * best.t;
-		L.hit_p[i] = make_float4(P.x, P.y, P.z, best.t);
-		L.hit_id[i] = make_uint2(best.id, best.newobj);
+		const uint32_t base = warp_fetch(&ws->head_trace[level]);
+		if (base >= n)
+			break;
+		const uint32_t i = base + (threadIdx.x & 31u);
+		bool surface = false;
+		if (i < n)
+		{
+			const RayD ray = load_ray(L, i);
+			Best best = { 1e20f, RT_ID_NONE, ray.skip };
+			bool done = false;
+			trace_scene<false, STATS>(S, ray, best, done, st);
+			const F3 P = ray.o + ray.d * best.t;
+			L.hit_p[i] = make_float4(P.x, P.y, P.z, best.t);
+			L.hit_id[i] = make_uint2(best.id, best.newobj);
+			// early cut of RayTracer.cpp:467-468: no surface -> Color(false), no children
+			surface = !(best.t > zFar || best.t < zNear);
+			if (!surface)
+			{
+				L.color[i] = make_float4(0.0f, 0.0f, 0.0f, 1e20f);
+				L.aux[i] = make_int4(-1, -1, -1, 0);
+			}
+		}
+		const uint32_t slot = warp_append(&ws->n_hit[level], surface);
+		if (surface)
+			L.hit_list[slot] = i;
 	}
 	flush_stats<STATS>(ws, st);
 }
@@ -154,78 +193,67 @@ __device__ __forceinline__ void light_dir(const DevLight &lit, const F3 &P, F3 &
 	}
 }
 
+// Work item w = (enabled light w / n_hit, surface w % n_hit): a warp's 32 rays go to the same
+// light from neighbouring surfaces.
 template<bool STATS>
-__global__ void __launch_bounds__(RT_BLOCK) k_shadow(SceneDev S, const FrameParams *__restrict__ Fp, LevelBuf L,
-	const uint32_t *__restrict__ count, WaveState *ws, float zNear)
+__global__ void __launch_bounds__(RT_BLOCK, 8) k_shadow(SceneDev S, const FrameParams *__restrict__ Fp, LevelBuf L, WaveState *ws, uint32_t level)
 {
-	__shared__ int s_stack[RT_STACK * RT_BLOCK];
-	int *stack = s_stack + threadIdx.x;
 	const FrameParams &F = *Fp;
-	const uint32_t k = blockIdx.y;
-	if (!F.lights[k].enabled)
-		return;
-	const uint32_t n = *count < L.capacity ? *count : L.capacity;
+	const uint32_t nHit = ws->n_hit[level];
+	const uint32_t n = nHit * F.n_enabled;
 	TravStats st = { 0, 0, 0 };
-	for (uint32_t i = blockIdx.x * RT_BLOCK + threadIdx.x; i < n; i += gridDim.x * RT_BLOCK)
+	while (true)
 	{
-		const float4 hp = L.hit_p[i];
-		if (hp.w > F.zFar || hp.w < zNear)
-			continue;   // no surface: no light loop (RayTracer.cpp:467-468)
-		RayD ray;
-		float dis, lum;
-		light_dir(F.lights[k], f3(hp), ray.d, dis, lum);
-		ray.o = f3(hp);
-		ray.mtlrfr = 1.0f;
-		ray.skip = L.hit_id[i].y;
-		ray.type = F.type == RT_TYPE_REFLECT ? 0 : MY_RAY_SHADOWRAY_;
-		ray.isInside = 0;
-		Best best = { dis, RT_ID_NONE, RT_ID_NONE };
-		bool done = false;
-		trace_scene<true, STATS>(S, ray, stack, best, done, st);
-		L.shadow[(size_t)k * L.capacity + i] = done ? 1 : 0;
+		const uint32_t base = warp_fetch(&ws->head_shadow[level]);
+		if (base >= n)
+			break;
+		const uint32_t w = base + (threadIdx.x & 31u);
+		if (w < n)
+		{
+			const uint32_t k = F.enabled_index[w / nHit], i = L.hit_list[w % nHit];
+			const float4 hp = L.hit_p[i];
+			RayD ray;
+			float dis, lum;
+			light_dir(F.lights[k], f3(hp), ray.d, dis, lum);
+			ray.o = f3(hp);
+			ray.mtlrfr = 1.0f;
+			ray.skip = L.hit_id[i].y;
+			ray.type = F.type == RT_TYPE_REFLECT ? 0 : MY_RAY_SHADOWRAY_;
+			ray.isInside = 0;
+			Best best = { dis, RT_ID_NONE, RT_ID_NONE };
+			bool done = false;
+			trace_scene<true, STATS>(S, ray, best, done, st);
+			L.shadow[(size_t)k * L.capacity + i] = done ? 1 : 0;
+		}
 	}
 	flush_stats<STATS>(ws, st);
 }
 
 // ---- shading + secondary-ray queue ---------------------------------------------------------------
 
-__device__ __forceinline__ uint32_t warp_append(uint32_t *counter, bool want)
-{
-	// warp-aggregated queue append: one atomic per warp, slots in lane order (keeps rays coherent)
-	const uint32_t m = __ballot_sync(0xffffffffu, want);
-	if (m == 0) return 0xFFFFFFFFu;
-	const uint32_t lane = threadIdx.x & 31u, leader = __ffs((int)m) - 1;
-	uint32_t base = 0;
-	if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
-	base = __shfl_sync(0xffffffffu, base, leader);
-	return want ? base + __popc(m & ((1u << lane) - 1u)) : 0xFFFFFFFFu;
-}
-
 __global__ void __launch_bounds__(128) k_shade(SceneDev S, const FrameParams *__restrict__ Fp, LevelBuf L, LevelBuf N,
-	WaveState *ws, uint32_t level, float zNear)
+	WaveState *ws, uint32_t level)
 {
 	const FrameParams &F = *Fp;
-	const uint32_t n = ws->count[level] < L.capacity ? ws->count[level] : L.capacity;
+	const uint32_t n = ws->n_hit[level];   // only rays that found a surface are shaded (k_trace wrote the others)
 	const uint32_t nIter = (n + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
 	const bool refraction = F.type != RT_TYPE_REFLECT;
-	unsigned long long myHits = 0;
 	for (uint32_t it = 0; it < nIter; ++it)
 	{
-		const uint32_t i = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+		const uint32_t h = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+		const uint32_t i = h < n ? L.hit_list[h] : 0xFFFFFFFFu;
 		bool wantFlec = false, wantFrac = false;
 		float4 co = make_float4(0, 0, 0, 0), cdFlec = co, cdFrac = co;
 		uint2 metaFlec = make_uint2(0, 0), metaFrac = metaFlec;
 		float fracRfr = 1.0f;
 		int4 aux = make_int4(-1, -1, -1, 0);
-		if (i < n)
+		if (h < n)
 		{
 			const float4 hp = L.hit_p[i];
 			const uint2 hid = L.hit_id[i];
 			const uint32_t id = hid.x, newobj = hid.y;
-			float4 color = make_float4(0.0f, 0.0f, 0.0f, 1e20f);   // Color(false)
-			if (!(hp.w > F.zFar || hp.w < zNear))
+			float4 color;
 			{
-				++myHits;
 				const RayD ray = load_ray(L, i);
 				const float bwc = L.ray_d[i].w;
 				const F3 P = f3(hp);
@@ -361,7 +389,7 @@ __global__ void __launch_bounds__(128) k_shade(SceneDev S, const FrameParams *__
 			else
 				ws->overflow = 1;
 		}
-		if (i < n)
+		if (h < n)
 			L.aux[i] = aux;
 		// ray statistics (one atomic per warp)
 		const uint32_t mf = __ballot_sync(0xffffffffu, wantFlec), mr = __ballot_sync(0xffffffffu, wantFrac);
@@ -371,10 +399,6 @@ __global__ void __launch_bounds__(128) k_shade(SceneDev S, const FrameParams *__
 			if (mr) atomicAdd(&ws->n_refract, (unsigned long long)__popc(mr));
 		}
 	}
-	for (int o = 16; o > 0; o >>= 1)
-		myHits += __shfl_down_sync(0xffffffffu, myHits, o);
-	if ((threadIdx.x & 31) == 0 && myHits)
-		atomicAdd(&ws->n_hits, myHits);
 }
 
 // ---- post-order combine --------------------------------------------------------------------------
@@ -442,26 +466,27 @@ void rtk_raygen(cudaStream_t st, const FrameParams *F, const LevelBuf &L, uint32
 	k_raygen<<<grid_for(n, 256, sms * 16), 256, 0, st>>>(F, L, n);
 }
 
-void rtk_trace(cudaStream_t st, const SceneDev &S, const LevelBuf &L, const uint32_t *count, WaveState *ws, uint32_t maxRays, unsigned sms, bool stats)
+void rtk_trace(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, WaveState *ws, uint32_t level, float zNear, uint32_t maxRays, unsigned sms, bool stats)
 {
-	const unsigned g = grid_for(maxRays, RT_BLOCK, sms * 64);
-	if (stats) k_trace<true><<<g, RT_BLOCK, 0, st>>>(S, L, count, ws);
-	else k_trace<false><<<g, RT_BLOCK, 0, st>>>(S, L, count, ws);
+	const unsigned g = grid_for(maxRays, RT_BLOCK, sms * 8);   // persistent: 8 CTAs per SM
+	if (stats) k_trace<true><<<g, RT_BLOCK, 0, st>>>(S, F, L, ws, level, zNear);
+	else k_trace<false><<<g, RT_BLOCK, 0, st>>>(S, F, L, ws, level, zNear);
 }
 
-void rtk_shadow(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const uint32_t *count, WaveState *ws,
-	float zNear, uint32_t nLights, uint32_t maxRays, unsigned sms, bool stats)
+void rtk_shadow(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, WaveState *ws,
+	uint32_t level, uint32_t nEnabled, uint32_t maxRays, unsigned sms, bool stats)
 {
-	if (nLights == 0) return;
-	const dim3 g(grid_for(maxRays, RT_BLOCK, sms * 64), nLights);
-	if (stats) k_shadow<true><<<g, RT_BLOCK, 0, st>>>(S, F, L, count, ws, zNear);
-	else k_shadow<false><<<g, RT_BLOCK, 0, st>>>(S, F, L, count, ws, zNear);
+	if (nEnabled == 0) return;
+	const unsigned g = grid_for(maxRays * nEnabled, RT_BLOCK, sms * 8);
+	if (stats) k_shadow<true><<<g, RT_BLOCK, 0, st>>>(S, F, L, ws, level);
+	else k_shadow<false><<<g, RT_BLOCK, 0, st>>>(S, F, L, ws, level);
 }
 
 void rtk_shade(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const LevelBuf &N, WaveState *ws,
 	uint32_t level, float zNear, uint32_t maxRays, unsigned sms)
 {
-	k_shade<<<grid_for(maxRays, 128, sms * 64), 128, 0, st>>>(S, F, L, N, ws, level, zNear);
+	(void)zNear;
+	k_shade<<<grid_for(maxRays, 128, sms * 16), 128, 0, st>>>(S, F, L, N, ws, level);
 }
 
 void rtk_combine(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const LevelBuf &N, const WaveState *ws,

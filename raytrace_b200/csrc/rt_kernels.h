@@ -19,22 +19,25 @@ struct LevelBuf
 	float4 *color;       // node-local colour, then combined colour; w = Color::alpha (distance)
 	int4 *aux;           // x: reflect child slot, y: refract child slot (-1 none), z: material (-1 = no surface), w: bit0 reflect, bit1 refract, bit2 Beer
 	uint8_t *shadow;     // [light][capacity]: 1 = occluded
+	uint32_t *hit_list;  // compacted slots of the rays that found a surface inside [zNear, zFar]
 	uint32_t capacity;
 };
 
 struct WaveState
 {
 	uint32_t count[RT_MAX_LEVELS + 2];   // rays queued per level
+	uint32_t n_hit[RT_MAX_LEVELS + 2];   // surfaces found per level (length of hit_list)
+	uint32_t head_trace[RT_MAX_LEVELS + 2], head_shadow[RT_MAX_LEVELS + 2];   // work-fetch cursors of the persistent warps
 	uint32_t overflow;                   // a level ran out of slots
 	uint32_t pad;
-	unsigned long long n_reflect, n_refract, n_hits;
+	unsigned long long n_reflect, n_refract;
 	unsigned long long nodes_visited, tri_tests, prim_tests;
 };
 
 void rtk_raygen(cudaStream_t st, const FrameParams *F, const LevelBuf &L, uint32_t n, unsigned sms);
-void rtk_trace(cudaStream_t st, const SceneDev &S, const LevelBuf &L, const uint32_t *count, WaveState *ws, uint32_t maxRays, unsigned sms, bool stats);
-void rtk_shadow(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const uint32_t *count, WaveState *ws,
-	float zNear, uint32_t nLights, uint32_t maxRays, unsigned sms, bool stats);
+void rtk_trace(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, WaveState *ws, uint32_t level, float zNear, uint32_t maxRays, unsigned sms, bool stats);
+void rtk_shadow(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, WaveState *ws,
+	uint32_t level, uint32_t nEnabled, uint32_t maxRays, unsigned sms, bool stats);
 void rtk_shade(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const LevelBuf &N, WaveState *ws,
 	uint32_t level, float zNear, uint32_t maxRays, unsigned sms);
 void rtk_combine(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const LevelBuf &N, const WaveState *ws,

@@ -161,22 +161,32 @@ __device__ __forceinline__ void test_prim(const SceneDev &S, const RayD &ray, ui
 }
 
 // BVH walk shared by Models (triangle leaves) and runs of analytic primitives (prim leaves).
+//
+// "while-while" shape (Aila & Laine 2009): every lane first descends through inner nodes until it
+// holds a leaf (or has finished); lanes that already hold a leaf wait at the end of the inner
+// loop, so the long, divergent leaf code runs once per warp iteration with as many lanes as
+// possible instead of interleaving with box tests.  The stack lives in local memory (L1-resident,
+// one 128-byte line per depth and warp) so no shared memory is reserved and occupancy is bound by
+// registers only.
+#define RT_TRAV_DONE (-1)   // never a valid leaf code: that would be first = 2^28-1, count = 8
+
 template<bool ANY, bool TRIS, bool STATS>
 __device__ __forceinline__ void traverse(const SceneDev &S, const RayD &ray, const F3 &idir, int root,
-	float hr_distance, uint32_t rangeBegin, uint32_t rangeEnd, int *stack /* [RT_STACK][RT_BLOCK] slice */,
-	Best &best, bool &done, TravStats &st, uint32_t winLo = 0u, uint32_t winHi = 0xFFFFFFFFu)
+	float hr_distance, uint32_t rangeBegin, uint32_t rangeEnd, Best &best, bool &done, TravStats &st,
+	uint32_t winLo = 0u, uint32_t winHi = 0xFFFFFFFFu)
 {
 	PartCache pc;
 	pc.part = 0xFFFFFFFFu, pc.mask = 0;
+	int stack[RT_STACK];
 	int sp = 0;
 	int cur = root;
 	while (true)
 	{
-		if (cur >= 0)
+		while (cur >= 0)
 		{
 			const BvhNode *n = &S.nodes[cur];
 			const float4 a = ldg4(&n->a), b = ldg4(&n->b), c = ldg4(&n->c);
-			const int4 link = __ldg(&n->link);
+			const int2 link = __ldg((const int2 *)&n->link);
 			if (STATS) ++st.nodes;
 			float t0, t1;
 			const bool h0 = slab_hit(a.x, a.y, a.z, a.w, b.x, b.y, ray.o, idir, best.t, t0);
@@ -184,42 +194,37 @@ __device__ __forceinline__ void traverse(const SceneDev &S, const RayD &ray, con
 			if (h0 && h1)
 			{
 				const bool swap = t1 < t0;
-				stack[sp * RT_BLOCK] = swap ? link.x : link.y;
-				++sp;
+				stack[sp++] = swap ? link.x : link.y;
 				cur = swap ? link.y : link.x;
-				continue;
 			}
-			if (h0) { cur = link.x; continue; }
-			if (h1) { cur = link.y; continue; }
+			else if (h0) cur = link.x;
+			else if (h1) cur = link.y;
+			else cur = sp ? stack[--sp] : RT_TRAV_DONE;
 		}
-		else
-		{
-			const uint32_t first = ((uint32_t)cur & 0x7FFFFFFFu) >> 3, count = ((uint32_t)cur & 7u) + 1u;
-			if (TRIS)
-				leaf_tris<ANY, STATS>(S, ray, first, count, hr_distance, rangeBegin, rangeEnd, pc, best, done, st);
-			else
-				for (uint32_t k = 0; k < count; ++k)
-				{
-					const uint32_t p = __ldg(&S.bvh_prims[first + k]);
-					if (p < winLo || p >= winHi)
-						continue;
-					if (STATS) ++st.prims;
-					test_prim<ANY>(S, ray, p, !(best.id & RT_ID_TRI) && best.id >= rangeBegin, best, done);
-				}
-			if (ANY && done)
-				return;
-		}
-		if (sp == 0)
+		if (cur == RT_TRAV_DONE)
 			return;
-		--sp;
-		cur = stack[sp * RT_BLOCK];
+		const uint32_t first = ((uint32_t)cur & 0x7FFFFFFFu) >> 3, count = ((uint32_t)cur & 7u) + 1u;
+		if (TRIS)
+			leaf_tris<ANY, STATS>(S, ray, first, count, hr_distance, rangeBegin, rangeEnd, pc, best, done, st);
+		else
+			for (uint32_t k = 0; k < count; ++k)
+			{
+				const uint32_t p = __ldg(&S.bvh_prims[first + k]);
+				if (p < winLo || p >= winHi)
+					continue;
+				if (STATS) ++st.prims;
+				test_prim<ANY>(S, ray, p, !(best.id & RT_ID_TRI) && best.id >= rangeBegin, best, done);
+			}
+		if (ANY && done)
+			return;
+		cur = sp ? stack[--sp] : RT_TRAV_DONE;
 	}
 }
 
 // The scene walk in Objects order.  Closest hit: best starts at (1e20, NONE).  Any-hit: best.t
 // starts at the light distance and `done` reports occlusion.
 template<bool ANY, bool STATS>
-__device__ __forceinline__ void trace_scene(const SceneDev &S, const RayD &ray, int *stack, Best &best, bool &done, TravStats &st)
+__device__ __forceinline__ void trace_scene(const SceneDev &S, const RayD &ray, Best &best, bool &done, TravStats &st)
 {
 	const F3 idir = f3(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
 	for (uint32_t i = 0; i < S.n_items; ++i)
@@ -238,13 +243,13 @@ __device__ __forceinline__ void trace_scene(const SceneDev &S, const RayD &ray, 
 				// the ray starts inside a sphere of this run: `newobj` depends on which hits were
 				// accepted before / after that sphere in object order, so walk the run in three
 				// order-respecting phases (primitives before it, the sphere itself, primitives after)
-				traverse<ANY, false, STATS>(S, ray, idir, it.root, best.t, it.first, end, stack, best, done, st, it.first, ray.skip);
+				traverse<ANY, false, STATS>(S, ray, idir, it.root, best.t, it.first, end, best, done, st, it.first, ray.skip);
 				if (STATS) ++st.prims;
 				test_prim<ANY>(S, ray, ray.skip, false, best, done);
-				traverse<ANY, false, STATS>(S, ray, idir, it.root, best.t, it.first, end, stack, best, done, st, ray.skip + 1u, end);
+				traverse<ANY, false, STATS>(S, ray, idir, it.root, best.t, it.first, end, best, done, st, ray.skip + 1u, end);
 			}
 			else
-				traverse<ANY, false, STATS>(S, ray, idir, it.root, best.t, it.first, end, stack, best, done, st);
+				traverse<ANY, false, STATS>(S, ray, idir, it.root, best.t, it.first, end, best, done, st);
 		}
 		else
 		{
@@ -254,7 +259,7 @@ __device__ __forceinline__ void trace_scene(const SceneDev &S, const RayD &ray, 
 			if (!(border_test(ray.o, ray.d, f3(mn), f3(mx)) < best.t))
 				continue;
 			const uint32_t tb = __ldg(&M.tri_begin);
-			traverse<ANY, true, STATS>(S, ray, idir, it.root, best.t, tb, tb + __ldg(&M.tri_count), stack, best, done, st);
+			traverse<ANY, true, STATS>(S, ray, idir, it.root, best.t, tb, tb + __ldg(&M.tri_count), best, done, st);
 		}
 		if (ANY && done)
 			return;
