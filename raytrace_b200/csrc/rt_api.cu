@@ -51,13 +51,13 @@ template<class T> struct DevBuf
 
 struct LevelStore
 {
-	DevBuf<float4> ray_o, ray_d, hit_p, color;
+	DevBuf<float4> ray_o, ray_d, hit_p, color, hit_n, hit_uv;
 	DevBuf<uint2> ray_meta, hit_id;
 	DevBuf<int4> aux;
 	DevBuf<uint8_t> shadow;
 	DevBuf<uint32_t> hit_list;
 	uint32_t capacity = 0, lights = 0;
-	void release() { ray_o.release(), ray_d.release(), hit_p.release(), color.release(), ray_meta.release(), hit_id.release(), aux.release(), shadow.release(), hit_list.release(); capacity = 0; }
+	void release() { ray_o.release(), ray_d.release(), hit_p.release(), color.release(), ray_meta.release(), hit_id.release(), aux.release(), shadow.release(), hit_list.release(), hit_n.release(), hit_uv.release(); capacity = 0; }
 };
 
 struct rt_ctx
@@ -140,8 +140,10 @@ extern "C" int rt_create(int device, rt_ctx **out)
 	CU(cudaMallocHost(&c->hWave, sizeof(WaveState)));
 	CU(cudaMalloc(&c->dWave, sizeof(WaveState)));
 	memset(&c->S, 0, sizeof c->S);
+	c->S.tune = 0;
 	if (const char *v = getenv("RT_B200_LEAF_SIZE")) c->leafSize = (uint32_t)atoi(v);
 	if (const char *v = getenv("RT_B200_LEVEL_FACTOR")) c->levelFactor = (float)atof(v);
+	if (const char *v = getenv("RT_B200_TUNE")) c->S.tune = (uint32_t)atoi(v);
 	*out = c;
 	return RT_OK;
 }
@@ -428,7 +430,7 @@ static int ensure_level(rt_ctx *c, uint32_t l, uint32_t cap, uint32_t lights)
 	if (cap <= L.capacity && lights <= L.lights) return RT_OK;
 	L.capacity = 0;
 	CU(L.ray_o.reserve(cap)); CU(L.ray_d.reserve(cap)); CU(L.ray_meta.reserve(cap)); CU(L.hit_p.reserve(cap));
-	CU(L.hit_id.reserve(cap)); CU(L.color.reserve(cap)); CU(L.aux.reserve(cap)); CU(L.shadow.reserve((size_t)cap * (lights ? lights : 1))); CU(L.hit_list.reserve(cap));
+	CU(L.hit_id.reserve(cap)); CU(L.color.reserve(cap)); CU(L.aux.reserve(cap)); CU(L.shadow.reserve((size_t)cap * (lights ? lights : 1))); CU(L.hit_list.reserve(cap)); CU(L.hit_n.reserve(cap)); CU(L.hit_uv.reserve(cap));
 	L.capacity = cap, L.lights = lights;
 	return RT_OK;
 }
@@ -437,7 +439,7 @@ static LevelBuf level_buf(const LevelStore &L)
 {
 	LevelBuf b;
 	b.ray_o = L.ray_o.p, b.ray_d = L.ray_d.p, b.ray_meta = L.ray_meta.p, b.hit_p = L.hit_p.p, b.hit_id = L.hit_id.p;
-	b.color = L.color.p, b.aux = L.aux.p, b.shadow = L.shadow.p, b.hit_list = L.hit_list.p, b.capacity = L.capacity;
+	b.color = L.color.p, b.aux = L.aux.p, b.shadow = L.shadow.p, b.hit_list = L.hit_list.p, b.hit_n = L.hit_n.p, b.hit_uv = L.hit_uv.p, b.capacity = L.capacity;
 	return b;
 }
 
@@ -519,19 +521,23 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 	if (nPix)
 	{
 		rtk_raygen(st, c->dFrame, level_buf(c->levels[0]), nPix, c->sms); ++launches;
-		for (uint32_t l = 0; l <= p->max_level; ++l)
+		// wave l = closest hit of level l (+ spawn of level l+1) fused with the shadow rays of level l-1
+		if (c->stageTiming) CU(cudaEventRecord(c->evStage[0], st));
+		LevelSet LS;
+		for (uint32_t l = 0; l <= p->max_level + 1; ++l) LS.l[l] = level_buf(c->levels[l]);
+		for (uint32_t l = 0; l <= p->max_level + 1; ++l)
 		{
-			const LevelBuf L = level_buf(c->levels[l]), N = level_buf(c->levels[l + 1]);
+			const bool traceOn = l <= p->max_level, shadowOn = l >= 1 && enabledLights > 0;
+			if (!traceOn && !shadowOn) continue;
 			const float zNear = l == 0 ? F.zNear : 0.0f;
-			const uint32_t maxRays = c->levels[l].capacity;
-			if (c->stageTiming) CU(cudaEventRecord(c->evStage[4 * l], st));
-			rtk_trace(st, c->S, c->dFrame, L, c->dWave, l, zNear, maxRays, c->sms, stats); ++launches;
-			if (c->stageTiming) CU(cudaEventRecord(c->evStage[4 * l + 1], st));
-			if (enabledLights) { rtk_shadow(st, c->S, c->dFrame, L, c->dWave, l, enabledLights, maxRays, c->sms, stats); ++launches; }
-			if (c->stageTiming) CU(cudaEventRecord(c->evStage[4 * l + 2], st));
-			rtk_shade(st, c->S, c->dFrame, L, N, c->dWave, l, zNear, maxRays, c->sms); ++launches;
-			if (c->stageTiming) CU(cudaEventRecord(c->evStage[4 * l + 3], st));
+			uint32_t items = traceOn ? c->levels[l].capacity : 0;
+			if (shadowOn) items = std::max(items, (uint32_t)std::min<uint64_t>((uint64_t)c->levels[l - 1].capacity * enabledLights, 0x7FFFFFFFu));
+			rtk_wave(st, c->S, c->dFrame, LS.l[l], LS.l[traceOn ? l + 1 : l], LS.l[l ? l - 1 : 0], c->dWave, l, traceOn, shadowOn, zNear, items, c->sms, stats);
+			++launches;
 		}
+		if (c->stageTiming) CU(cudaEventRecord(c->evStage[1], st));
+		rtk_shade(st, c->S, c->dFrame, LS, c->dWave, p->max_level + 1, c->levels[0].capacity, c->sms); ++launches;
+		if (c->stageTiming) CU(cudaEventRecord(c->evStage[2], st));
 		for (int l = (int)p->max_level; l >= 0; --l)
 		{
 			rtk_combine(st, c->S, c->dFrame, level_buf(c->levels[l]), level_buf(c->levels[l + 1]), c->dWave, (uint32_t)l, fb, c->levels[l].capacity, c->sms);
@@ -558,15 +564,12 @@ static int finish_frame(rt_ctx *c)
 	c->traceMs = c->shadowMs = c->shadeMs = c->otherMs = 0;
 	if (c->stageTiming && c->lastPixels)
 	{
-		for (uint32_t l = 0; l <= c->lastMaxLevel; ++l)
-		{
-			float a = 0, b = 0, d = 0;
-			cudaEventElapsedTime(&a, c->evStage[4 * l], c->evStage[4 * l + 1]);
-			cudaEventElapsedTime(&b, c->evStage[4 * l + 1], c->evStage[4 * l + 2]);
-			cudaEventElapsedTime(&d, c->evStage[4 * l + 2], c->evStage[4 * l + 3]);
-			c->traceMs += a, c->shadowMs += b, c->shadeMs += d;
-		}
-		c->otherMs = c->renderMs - c->traceMs - c->shadowMs - c->shadeMs;
+		// the closest-hit and shadow queries share the fused wave kernels: reported together as trace_ms
+		float a = 0, d = 0;
+		cudaEventElapsedTime(&a, c->evStage[0], c->evStage[1]);
+		cudaEventElapsedTime(&d, c->evStage[1], c->evStage[2]);
+		c->traceMs = a, c->shadeMs = d;
+		c->otherMs = c->renderMs - c->traceMs - c->shadeMs;
 	}
 	if (c->hWave->overflow)
 		return fail(RT_E_LIMIT, "a ray level overflowed its queue (capacity factor %.2f); raise RT_B200_LEVEL_FACTOR", c->levelFactor);

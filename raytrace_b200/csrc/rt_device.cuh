@@ -132,6 +132,7 @@ struct SceneDev
 	const BvhNode *nodes;
 	const SceneItem *items;
 	uint32_t n_items, n_prims, n_tris, n_parts;
+	uint32_t tune;               // bit0: prefetch child nodes (RT_B200_TUNE, development switch)
 };
 
 __device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }

@@ -38,9 +38,11 @@ __device__ __forceinline__ float sphere_t(const RayD &ray, const F3 &c, float r2
 }
 
 // ---- BorderTest, Basic3DObject.cpp:44-81 -------------------------------------------------------
-__device__ __forceinline__ float border_test(const F3 &o, const F3 &d, const F3 &Min, const F3 &Max)
+// `rrd` = 1.0f / direction, the reference's _mm_div_ps(1, direction); callers that already hold the
+// ray's reciprocal direction pass it in (same IEEE division, same bits).
+__device__ __forceinline__ float border_test(const F3 &o, const F3 &d, const F3 &rrd, const F3 &Min, const F3 &Max)
 {
-	const float rx = 1.0f / d.x, ry = 1.0f / d.y, rz = 1.0f / d.z;
+	const float rx = rrd.x, ry = rrd.y, rz = rrd.z;
 	const float ax = (Min.x - o.x) * rx, bx = (Max.x - o.x) * rx;
 	const float ay = (Min.y - o.y) * ry, by = (Max.y - o.y) * ry;
 	const float az = (Min.z - o.z) * rz, bz = (Max.z - o.z) * rz;
@@ -72,7 +74,7 @@ __device__ __forceinline__ float border_test(const F3 &o, const F3 &d, const F3 
 // ---- Box::intersect, Basic3DObject.cpp:274-300 -------------------------------------------------
 __device__ __forceinline__ float box_t(const RayD &ray, const F3 &wmin, const F3 &wmax)
 {
-	const float res = border_test(ray.o, ray.d, wmin, wmax);
+	const float res = border_test(ray.o, ray.d, f3(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z), wmin, wmax);
 	return gt_1em6(res) ? res : 1e20f;
 }
 __device__ __forceinline__ F3 box_normal(const F3 &P, const F3 &pos, const F3 &lmax)
@@ -135,10 +137,10 @@ __device__ __forceinline__ float triangle_t(const F3 &o, const F3 &d, const F3 &
 // ---- BorderTestEx, Model.cpp:482-664 -----------------------------------------------------------
 // The 8 octants of a part's box in one pass.  Returns the reference's `minist`; *mask gets bit a
 // set iff octant a (x half = a&4, y half = a&1, z half = a&2) passes ansmin <= ansmax.
-static __device__ __noinline__ float border_test_ex(const F3 &o, const F3 &d, const F3 &Min, const F3 &Max, uint32_t *mask)
+static __device__ __noinline__ float border_test_ex(const F3 &o, const F3 &d, const F3 &rrd, const F3 &Min, const F3 &Max, uint32_t *mask)
 {
 	const F3 Mid = (Min + Max) * 0.5f;
-	const float rx = 1.0f / d.x, ry = 1.0f / d.y, rz = 1.0f / d.z;
+	const float rx = rrd.x, ry = rrd.y, rz = rrd.z;
 	const float x0 = (Min.x - o.x) * rx, x1 = (Mid.x - o.x) * rx, x2 = (Max.x - o.x) * rx;
 	const float y0 = (Min.y - o.y) * ry, y1 = (Mid.y - o.y) * ry, y2 = (Max.y - o.y) * ry;
 	const float z0 = (Min.z - o.z) * rz, z1 = (Mid.z - o.z) * rz, z2 = (Max.z - o.z) * rz;

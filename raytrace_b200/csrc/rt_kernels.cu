@@ -1,10 +1,17 @@
 // Wavefront kernels of the trace-and-shade path (sm_100a, compiled with -fmad=false):
 //
 //   k_raygen        RayTracer::parallelRT pixel loop          /root/reference/RayTracer.cpp:20-27
-//   k_trace         closest-hit walk of one ray level         RayTracer.cpp:455-465 (+ all intersect operators)
-//   k_shadow        one any-hit query per (hit, light)        RayTracer.cpp:482-520
-//   k_shade         Blinn-Phong + spawn reflect/refract rays  RayTracer.cpp:467-592 (pre-order half)
+//   k_wave(l)       closest hit of ray level l  +  surface attributes  +  secondary-ray queue (level l+1)
+//                   fused with the shadow any-hit queries of level l-1
+//                                                             RayTracer.cpp:455-468, 548-581 and :482-520
+//   k_shade         Blinn-Phong of every surface of every level (one launch)   RayTracer.cpp:470-546
 //   k_combine       post-order colour combine + Color::put    RayTracer.cpp:552-594, 3DElement.cpp:463-468
+//
+// Why trace(l) and shadow(l-1) share a launch: a few rays skim the height field and visit
+// thousands of BVH nodes; with one kernel per stage every launch ended in a ~250 us tail of such
+// rays with the rest of the chip idle.  Spawning level l+1 inside the trace epilogue removes the
+// trace(l+1) -> shade(l) -> shadow(l) dependency, so the long rays of one stage overlap the bulk
+// of the next.
 //
 // The reference recursion (binary ray tree per pixel) is unrolled level by level: level l holds
 // every ray whose recursion depth is l; a ray's slot index is also its ray-tree node index, and
@@ -109,11 +116,11 @@ __global__ void __launch_bounds__(256) k_raygen(const FrameParams *__restrict__ 
 	}
 }
 
-// ---- closest hit ---------------------------------------------------------------------------------
+// ---- queue helpers ---------------------------------------------------------------------------------
 
-// Persistent warps: each warp pulls 32 consecutive rays at a time from the level's queue (one
-// atomic per fetch), so SMs stay busy until the queue is dry and ray order (8x4 pixel tiles for
-// primary rays, parent order for secondary rays) keeps the lanes of a warp coherent.
+// Persistent warps: each warp pulls 32 consecutive work items at a time (one atomic per fetch), so
+// SMs stay busy until the queue is dry and queue order (8x4 pixel tiles for primary rays, parent
+// order for secondary rays, same light for shadow rays) keeps the lanes of a warp coherent.
 __device__ __forceinline__ uint32_t warp_fetch(uint32_t *head)
 {
 	uint32_t base = 0;
@@ -132,45 +139,6 @@ __device__ __forceinline__ uint32_t warp_append(uint32_t *counter, bool want)
 	base = __shfl_sync(0xffffffffu, base, leader);
 	return want ? base + __popc(m & ((1u << lane) - 1u)) : 0xFFFFFFFFu;
 }
-
-template<bool STATS>
-__global__ void __launch_bounds__(RT_BLOCK, 8) k_trace(SceneDev S, const FrameParams *__restrict__ Fp, LevelBuf L, WaveState *ws, uint32_t level, float zNear)
-{
-	const float zFar = Fp->zFar;
-	const uint32_t n = ws->count[level] < L.capacity ? ws->count[level] : L.capacity;
-	TravStats st = { 0, 0, 0 };
-	while (true)
-	{
-		const uint32_t base = warp_fetch(&ws->head_trace[level]);
-		if (base >= n)
-			break;
-		const uint32_t i = base + (threadIdx.x & 31u);
-		bool surface = false;
-		if (i < n)
-		{
-			const RayD ray = load_ray(L, i);
-			Best best = { 1e20f, RT_ID_NONE, ray.skip };
-			bool done = false;
-			trace_scene<false, STATS>(S, ray, best, done, st);
-			const F3 P = ray.o + ray.d * best.t;
-			L.hit_p[i] = make_float4(P.x, P.y, P.z, best.t);
-			L.hit_id[i] = make_uint2(best.id, best.newobj);
-			// early cut of RayTracer.cpp:467-468: no surface -> Color(false), no children
-			surface = !(best.t > zFar || best.t < zNear);
-			if (!surface)
-			{
-				L.color[i] = make_float4(0.0f, 0.0f, 0.0f, 1e20f);
-				L.aux[i] = make_int4(-1, -1, -1, 0);
-			}
-		}
-		const uint32_t slot = warp_append(&ws->n_hit[level], surface);
-		if (surface)
-			L.hit_list[slot] = i;
-	}
-	flush_stats<STATS>(ws, st);
-}
-
-// ---- shadow any-hit ------------------------------------------------------------------------------
 
 // light k as seen from P: direction p2l and occlusion range (RayTracer.cpp:482-503)
 __device__ __forceinline__ void light_dir(const DevLight &lit, const F3 &P, F3 &p2l, float &dis, float &lum)
@@ -193,211 +161,259 @@ __device__ __forceinline__ void light_dir(const DevLight &lit, const F3 &P, F3 &
 	}
 }
 
-// Work item w = (enabled light w / n_hit, surface w % n_hit): a warp's 32 rays go to the same
-// light from neighbouring surfaces.
+// ---- surface attributes: what the intersect operators leave in HitRes ------------------------------
+
+struct Surface
+{
+	F3 N;
+	float tu, tv, rfr;
+	int mtl, tex;
+	uint8_t isInside;
+};
+
+__device__ __forceinline__ Surface surface_attributes(const SceneDev &S, const RayD &ray, const F3 &P, uint32_t id)
+{
+	Surface s;
+	s.tu = s.tv = 0.0f, s.rfr = 1.0f, s.tex = -1, s.isInside = 0;
+	if (is_tri(id))
+	{
+		// Model::intersect epilogue, Model.cpp:794-807
+		const uint32_t tri = id & 0x0FFFFFFFu, slot = __ldg(&S.tri_slot[tri]);
+		const float4 g0 = ldg4(&S.tri_geom[3 * slot]), g1 = ldg4(&S.tri_geom[3 * slot + 1]), g2 = ldg4(&S.tri_geom[3 * slot + 2]);
+		F3 bary = f3(0, 0, 0);
+		triangle_t(ray.o, ray.d, f3(g0), f3(g1), f3(g2), &bary);
+		const F3 n0 = f3(ldg4(&S.tri_norms[3 * tri])), n1 = f3(ldg4(&S.tri_norms[3 * tri + 1])), n2 = f3(ldg4(&S.tri_norms[3 * tri + 2]));
+		s.N = normalize((n0 * bary.x + n1 * bary.y) + n2 * bary.z);
+		const float2 c0 = __ldg(&S.tri_tcoords[3 * tri]), c1 = __ldg(&S.tri_tcoords[3 * tri + 1]), c2 = __ldg(&S.tri_tcoords[3 * tri + 2]);
+		s.tu = (c0.x * bary.x + c1.x * bary.y) + c2.x * bary.z;
+		s.tv = (c0.y * bary.x + c1.y * bary.y) + c2.y * bary.z;
+		const DevPart &part = S.parts[__ldg(&S.tri_part[tri])];
+		s.mtl = (int)__ldg(&part.material);
+		s.tex = __ldg(&part.texture);
+		s.rfr = __ldg(&S.materials[4 * s.mtl + 3]).w;
+		return s;
+	}
+	const int4 meta = __ldg(&S.prim_meta[id]);
+	const float4 g0 = ldg4(&S.prim_geom[4 * id]);
+	s.mtl = meta.y;
+	if (meta.x == RT_OBJ_SPHERE)
+	{
+		// Basic3DObject.cpp:146-160 (leaving through the far wall) and :179-187
+		const bool leaving = ray.skip == id;   // only reachable with ray.isInside
+		s.N = leaving ? normalize(f3(g0) - P) : normalize(P - f3(g0));
+		s.isInside = (uint8_t)~ray.isInside;
+		s.rfr = (leaving && ray.type == MY_RAY_REFRACTRAY_) ? 1.0f : __ldg(&S.materials[4 * s.mtl + 3]).w;
+	}
+	else if (meta.x == RT_OBJ_PLANE)
+	{
+		s.N = f3(ldg4(&S.prim_geom[4 * id + 1]));
+		const float2 tc = plane_tcoord(ray.o, ray.d, f3(g0), f3(ldg4(&S.prim_geom[4 * id + 2])), f3(ldg4(&S.prim_geom[4 * id + 3])));
+		s.tu = tc.x, s.tv = tc.y;
+		s.tex = meta.z;
+	}
+	else
+		s.N = box_normal(P, f3(g0), f3(ldg4(&S.prim_geom[4 * id + 3])));
+	return s;
+}
+
+// ---- fused wave kernel: closest hit of level `level` + shadow rays of level `level - 1` -------------
+
 template<bool STATS>
-__global__ void __launch_bounds__(RT_BLOCK, 8) k_shadow(SceneDev S, const FrameParams *__restrict__ Fp, LevelBuf L, WaveState *ws, uint32_t level)
+__global__ void __launch_bounds__(RT_BLOCK, 8) k_wave(SceneDev S, const FrameParams *__restrict__ Fp, LevelBuf L, LevelBuf N, LevelBuf Lprev,
+	WaveState *ws, uint32_t level, uint32_t traceOn, uint32_t shadowOn, float zNear)
 {
 	const FrameParams &F = *Fp;
-	const uint32_t nHit = ws->n_hit[level];
-	const uint32_t n = nHit * F.n_enabled;
 	TravStats st = { 0, 0, 0 };
-	while (true)
+
+	// ---- phase A: closest hit + surface attributes + children ------------------------------------
+	if (traceOn)
 	{
-		const uint32_t base = warp_fetch(&ws->head_shadow[level]);
-		if (base >= n)
-			break;
-		const uint32_t w = base + (threadIdx.x & 31u);
-		if (w < n)
+		const uint32_t n = ws->count[level] < L.capacity ? ws->count[level] : L.capacity;
+		const bool refraction = F.type != RT_TYPE_REFLECT;
+		const bool deeper = level + 1 <= F.max_level;
+		while (true)
 		{
-			const uint32_t k = F.enabled_index[w / nHit], i = L.hit_list[w % nHit];
-			const float4 hp = L.hit_p[i];
-			RayD ray;
-			float dis, lum;
-			light_dir(F.lights[k], f3(hp), ray.d, dis, lum);
-			ray.o = f3(hp);
-			ray.mtlrfr = 1.0f;
-			ray.skip = L.hit_id[i].y;
-			ray.type = F.type == RT_TYPE_REFLECT ? 0 : MY_RAY_SHADOWRAY_;
-			ray.isInside = 0;
-			Best best = { dis, RT_ID_NONE, RT_ID_NONE };
-			bool done = false;
-			trace_scene<true, STATS>(S, ray, best, done, st);
-			L.shadow[(size_t)k * L.capacity + i] = done ? 1 : 0;
+			const uint32_t base = warp_fetch(&ws->head_trace[level]);
+			if (base >= n)
+				break;
+			const uint32_t i = base + (threadIdx.x & 31u);
+			bool surface = false, wantFlec = false, wantFrac = false;
+			float4 co = make_float4(0, 0, 0, 0), cdFlec = co, cdFrac = co;
+			uint2 metaFlec = make_uint2(0, 0), metaFrac = metaFlec;
+			float fracRfr = 1.0f;
+			int4 aux = make_int4(-1, -1, -1, 0);
+			if (i < n)
+			{
+				const RayD ray = load_ray(L, i);
+				Best best = { 1e20f, RT_ID_NONE, ray.skip };
+				bool done = false;
+				trace_scene<false, STATS>(S, ray, best, done, st);
+				const F3 P = ray.o + ray.d * best.t;
+				L.hit_p[i] = make_float4(P.x, P.y, P.z, best.t);
+				L.hit_id[i] = make_uint2(best.id, best.newobj);
+				// early cut of RayTracer.cpp:467-468: no surface -> Color(false), no light loop, no children
+				surface = !(best.t > F.zFar || best.t < zNear);
+				if (!surface)
+					L.color[i] = make_float4(0.0f, 0.0f, 0.0f, 1e20f);
+				else
+				{
+					const Surface sf = surface_attributes(S, ray, P, best.id);
+					L.hit_n[i] = make_float4(sf.N.x, sf.N.y, sf.N.z, __int_as_float(sf.mtl));
+					L.hit_uv[i] = make_float4(sf.tu, sf.tv, __int_as_float(sf.tex), 0.0f);
+					const float4 mP = ldg4(&S.materials[4 * sf.mtl + 3]);   // shiness, reflect, refract, rfr
+					const float bwc = L.ray_d[i].w;
+					aux.z = sf.mtl;
+					co = make_float4(P.x, P.y, P.z, 1.0f);
+					if (mP.y > 0.01f)
+					{
+						// reflection, RayTracer.cpp:548-563
+						aux.w |= 1;
+						const float bw = bwc * mP.y;
+						if (deeper && !(bw < 1e-5f))
+						{
+							const float n_n = 2 * dot(ray.d, sf.N);
+							const F3 r = normalize(ray.d - sf.N * n_n);
+							wantFlec = true;
+							cdFlec = make_float4(r.x, r.y, r.z, bw);
+							metaFlec = make_uint2(best.newobj, refraction ? (uint32_t)MY_RAY_REFLECTRAY_ : 0u);
+						}
+					}
+					if (refraction && mP.z > 0.01f)
+					{
+						// refraction, RayTracer.cpp:565-583
+						aux.w |= 2;
+						if (sf.isInside) aux.w |= 4;
+						const float nn = ray.mtlrfr / sf.rfr;
+						const float cosIn = -dot(ray.d, sf.N);
+						const float cosOut2 = 1.0f - (nn * nn) * (1.0f - cosIn * cosIn);
+						const float bw = bwc * mP.z;
+						if (!(cosOut2 < 0.0f) && deeper && !(bw < 1e-5f))
+						{
+							const F3 l2 = ray.d * nn, l1 = sf.N * (nn * cosIn - sqrtf(cosOut2));
+							const F3 r = normalize(l1 + l2);
+							wantFrac = true;
+							cdFrac = make_float4(r.x, r.y, r.z, bw);
+							metaFrac = make_uint2(best.newobj, (uint32_t)MY_RAY_REFRACTRAY_ | ((uint32_t)sf.isInside << 8));
+							fracRfr = sf.rfr;
+						}
+					}
+				}
+			}
+			// queue appends: the whole warp takes part
+			const uint32_t hslot = warp_append(&ws->n_hit[level], surface);
+			if (surface)
+				L.hit_list[hslot] = i;
+			const uint32_t sFlec = warp_append(&ws->count[level + 1], wantFlec);
+			if (wantFlec)
+			{
+				if (sFlec < N.capacity)
+				{
+					N.ray_o[sFlec] = co, N.ray_d[sFlec] = cdFlec, N.ray_meta[sFlec] = metaFlec;
+					aux.x = (int)sFlec;
+				}
+				else
+					ws->overflow = 1;
+			}
+			const uint32_t sFrac = warp_append(&ws->count[level + 1], wantFrac);
+			if (wantFrac)
+			{
+				if (sFrac < N.capacity)
+				{
+					N.ray_o[sFrac] = make_float4(co.x, co.y, co.z, fracRfr), N.ray_d[sFrac] = cdFrac, N.ray_meta[sFrac] = metaFrac;
+					aux.y = (int)sFrac;
+				}
+				else
+					ws->overflow = 1;
+			}
+			if (i < n)
+				L.aux[i] = aux;
+			const uint32_t mf = __ballot_sync(0xffffffffu, wantFlec), mr = __ballot_sync(0xffffffffu, wantFrac);
+			if ((threadIdx.x & 31) == 0)
+			{
+				if (mf) atomicAdd(&ws->n_reflect, (unsigned long long)__popc(mf));
+				if (mr) atomicAdd(&ws->n_refract, (unsigned long long)__popc(mr));
+			}
+		}
+	}
+
+	// ---- phase B: shadow any-hit of the previous level's surfaces -----------------------------------
+	// work item w = (enabled light w / n_hit, surface w % n_hit): a warp's rays go to one light
+	if (shadowOn)
+	{
+		const uint32_t lp = level - 1u;
+		const uint32_t nHit = ws->n_hit[lp];
+		const uint32_t n = nHit * F.n_enabled;
+		while (true)
+		{
+			const uint32_t base = warp_fetch(&ws->head_shadow[lp]);
+			if (base >= n)
+				break;
+			const uint32_t w = base + (threadIdx.x & 31u);
+			if (w < n)
+			{
+				const uint32_t k = F.enabled_index[w / nHit], i = Lprev.hit_list[w % nHit];
+				const float4 hp = Lprev.hit_p[i];
+				RayD ray;
+				float dis, lum;
+				light_dir(F.lights[k], f3(hp), ray.d, dis, lum);
+				ray.o = f3(hp);
+				ray.mtlrfr = 1.0f;
+				ray.skip = Lprev.hit_id[i].y;
+				ray.type = F.type == RT_TYPE_REFLECT ? 0 : MY_RAY_SHADOWRAY_;
+				ray.isInside = 0;
+				Best best = { dis, RT_ID_NONE, RT_ID_NONE };
+				bool done = false;
+				trace_scene<true, STATS>(S, ray, best, done, st);
+				Lprev.shadow[(size_t)k * Lprev.capacity + i] = done ? 1 : 0;
+			}
 		}
 	}
 	flush_stats<STATS>(ws, st);
 }
 
-// ---- shading + secondary-ray queue ---------------------------------------------------------------
+// ---- shading: light loop of every surface of every level ------------------------------------------
 
-__global__ void __launch_bounds__(128) k_shade(SceneDev S, const FrameParams *__restrict__ Fp, LevelBuf L, LevelBuf N,
-	WaveState *ws, uint32_t level)
+__global__ void __launch_bounds__(128) k_shade(SceneDev S, const FrameParams *__restrict__ Fp, LevelSet LS, const WaveState *__restrict__ ws)
 {
 	const FrameParams &F = *Fp;
-	const uint32_t n = ws->n_hit[level];   // only rays that found a surface are shaded (k_trace wrote the others)
-	const uint32_t nIter = (n + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
-	const bool refraction = F.type != RT_TYPE_REFLECT;
-	for (uint32_t it = 0; it < nIter; ++it)
+	const uint32_t level = blockIdx.y;
+	const LevelBuf &L = LS.l[level];
+	const uint32_t n = ws->n_hit[level];
+	for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < n; h += gridDim.x * blockDim.x)
 	{
-		const uint32_t h = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
-		const uint32_t i = h < n ? L.hit_list[h] : 0xFFFFFFFFu;
-		bool wantFlec = false, wantFrac = false;
-		float4 co = make_float4(0, 0, 0, 0), cdFlec = co, cdFrac = co;
-		uint2 metaFlec = make_uint2(0, 0), metaFrac = metaFlec;
-		float fracRfr = 1.0f;
-		int4 aux = make_int4(-1, -1, -1, 0);
-		if (h < n)
+		const uint32_t i = L.hit_list[h];
+		const float4 hp = L.hit_p[i], hn = L.hit_n[i], huv = L.hit_uv[i];
+		const F3 P = f3(hp), Nn = f3(hn), rd = f3(L.ray_d[i]);
+		const int mtl = __float_as_int(hn.w), tex = __float_as_int(huv.z);
+		const F3 mA = f3(ldg4(&S.materials[4 * mtl])), mD = f3(ldg4(&S.materials[4 * mtl + 1])), mS = f3(ldg4(&S.materials[4 * mtl + 2]));
+		const float shiness = ldg4(&S.materials[4 * mtl + 3]).x;
+		const F3 vc = texel(S, tex, huv.x, huv.y);
+		F3 mix_vd = f3(0, 0, 0), mix_vsc = f3(0, 0, 0);
+		F3 mix_va = mixmul(mA, f3(F.env_light));
+		for (uint32_t k = 0; k < F.n_lights; ++k)
 		{
-			const float4 hp = L.hit_p[i];
-			const uint2 hid = L.hit_id[i];
-			const uint32_t id = hid.x, newobj = hid.y;
-			float4 color;
-			{
-				const RayD ray = load_ray(L, i);
-				const float bwc = L.ray_d[i].w;
-				const F3 P = f3(hp);
-				F3 Nn;
-				float tu = 0, tv = 0, rfr = 1.0f;
-				int mtlIndex, tex = -1;
-				uint8_t hitInside = 0;
-				if (is_tri(id))
-				{
-					// Model::intersect epilogue, Model.cpp:794-807
-					const uint32_t tri = id & 0x0FFFFFFFu, slot = __ldg(&S.tri_slot[tri]);
-					const float4 g0 = ldg4(&S.tri_geom[3 * slot]), g1 = ldg4(&S.tri_geom[3 * slot + 1]), g2 = ldg4(&S.tri_geom[3 * slot + 2]);
-					F3 bary = f3(0, 0, 0);
-					triangle_t(ray.o, ray.d, f3(g0), f3(g1), f3(g2), &bary);
-					const F3 n0 = f3(ldg4(&S.tri_norms[3 * tri])), n1 = f3(ldg4(&S.tri_norms[3 * tri + 1])), n2 = f3(ldg4(&S.tri_norms[3 * tri + 2]));
-					Nn = normalize((n0 * bary.x + n1 * bary.y) + n2 * bary.z);
-					const float2 c0 = __ldg(&S.tri_tcoords[3 * tri]), c1 = __ldg(&S.tri_tcoords[3 * tri + 1]), c2 = __ldg(&S.tri_tcoords[3 * tri + 2]);
-					tu = (c0.x * bary.x + c1.x * bary.y) + c2.x * bary.z;
-					tv = (c0.y * bary.x + c1.y * bary.y) + c2.y * bary.z;
-					const DevPart &part = S.parts[__ldg(&S.tri_part[tri])];
-					mtlIndex = (int)__ldg(&part.material);
-					tex = __ldg(&part.texture);
-					rfr = __ldg(&S.materials[4 * mtlIndex + 3]).w;
-				}
-				else
-				{
-					const int4 meta = __ldg(&S.prim_meta[id]);
-					const float4 g0 = ldg4(&S.prim_geom[4 * id]);
-					mtlIndex = meta.y;
-					if (meta.x == RT_OBJ_SPHERE)
-					{
-						const bool leaving = ray.skip == id;   // only reachable with ray.isInside
-						Nn = leaving ? normalize(f3(g0) - P) : normalize(P - f3(g0));
-						hitInside = (uint8_t)~ray.isInside;
-						rfr = (leaving && ray.type == MY_RAY_REFRACTRAY_) ? 1.0f : __ldg(&S.materials[4 * mtlIndex + 3]).w;
-					}
-					else if (meta.x == RT_OBJ_PLANE)
-					{
-						Nn = f3(ldg4(&S.prim_geom[4 * id + 1]));
-						const float2 tc = plane_tcoord(ray.o, ray.d, f3(g0), f3(ldg4(&S.prim_geom[4 * id + 2])), f3(ldg4(&S.prim_geom[4 * id + 3])));
-						tu = tc.x, tv = tc.y;
-						tex = meta.z;
-					}
-					else
-						Nn = box_normal(P, f3(g0), f3(ldg4(&S.prim_geom[4 * id + 3])));
-				}
-				const F3 mA = f3(ldg4(&S.materials[4 * mtlIndex])), mD = f3(ldg4(&S.materials[4 * mtlIndex + 1])), mS = f3(ldg4(&S.materials[4 * mtlIndex + 2]));
-				const float4 mP = ldg4(&S.materials[4 * mtlIndex + 3]);   // shiness, reflect, refract, rfr
-				const F3 vc = texel(S, tex, tu, tv);
-				F3 mix_vd = f3(0, 0, 0), mix_vsc = f3(0, 0, 0);
-				F3 mix_va = mixmul(mA, f3(F.env_light));
-				for (uint32_t k = 0; k < F.n_lights; ++k)
-				{
-					const DevLight &lit = F.lights[k];
-					if (!lit.enabled)
-						continue;
-					F3 p2l;
-					float dis, lum;
-					light_dir(lit, P, p2l, dis, lum);
-					F3 la = f3(lit.ambient), ld = f3(lit.diffuse), ls = f3(lit.specular);
-					if (lit.type == RT_LIGHT_POINT)
-						la = la * lum, ld = ld * lum, ls = ls * lum;
-					mix_va = mix_va + mixmul(mA, la);   // ambient is added before the shadow test
-					if (L.shadow[(size_t)k * L.capacity + i])
-						continue;
-					float n_n = dot(Nn, p2l);
-					if (n_n > 0)
-						mix_vd = mix_vd + mixmul(mD, ld) * n_n;
-					const F3 h = normalize(p2l - ray.d);
-					n_n = dot(Nn, h);
-					if (n_n > 0)
-						mix_vsc = mix_vsc + mixmul(mS, ls) * pow_ref(n_n, mP.x);
-				}
-				const F3 c_all = mixmul(vc, mix_vd + mix_va) + mix_vsc;
-				color = make_float4(c_all.x, c_all.y, c_all.z, hp.w);
-				aux.z = mtlIndex;
-				const bool deeper = level + 1 <= F.max_level;
-				if (mP.y > 0.01f)
-				{
-					aux.w |= 1;
-					const float bw = bwc * mP.y;
-					if (deeper && !(bw < 1e-5f))
-					{
-						const float n_n = 2 * dot(ray.d, Nn);
-						const F3 r = normalize(ray.d - Nn * n_n);
-						wantFlec = true;
-						cdFlec = make_float4(r.x, r.y, r.z, bw);
-						metaFlec = make_uint2(newobj, refraction ? (uint32_t)MY_RAY_REFLECTRAY_ : 0u);
-					}
-				}
-				if (refraction && mP.z > 0.01f)
-				{
-					aux.w |= 2;
-					if (hitInside) aux.w |= 4;
-					const float nn = ray.mtlrfr / rfr;
-					const float cosIn = -dot(ray.d, Nn);
-					const float cosOut2 = 1.0f - (nn * nn) * (1.0f - cosIn * cosIn);
-					const float bw = bwc * mP.z;
-					if (!(cosOut2 < 0.0f) && deeper && !(bw < 1e-5f))
-					{
-						const F3 l2 = ray.d * nn, l1 = Nn * (nn * cosIn - sqrtf(cosOut2));
-						const F3 r = normalize(l1 + l2);
-						wantFrac = true;
-						cdFrac = make_float4(r.x, r.y, r.z, bw);
-						metaFrac = make_uint2(newobj, (uint32_t)MY_RAY_REFRACTRAY_ | ((uint32_t)hitInside << 8));
-						fracRfr = rfr;
-					}
-				}
-				co = make_float4(P.x, P.y, P.z, 1.0f);
-			}
-			L.color[i] = color;
+			const DevLight &lit = F.lights[k];
+			if (!lit.enabled)
+				continue;
+			F3 p2l;
+			float dis, lum;
+			light_dir(lit, P, p2l, dis, lum);
+			F3 la = f3(lit.ambient), ld = f3(lit.diffuse), ls = f3(lit.specular);
+			if (lit.type == RT_LIGHT_POINT)
+				la = la * lum, ld = ld * lum, ls = ls * lum;
+			mix_va = mix_va + mixmul(mA, la);   // ambient is added before the shadow test
+			if (L.shadow[(size_t)k * L.capacity + i])
+				continue;
+			float n_n = dot(Nn, p2l);
+			if (n_n > 0)
+				mix_vd = mix_vd + mixmul(mD, ld) * n_n;
+			const F3 h2 = normalize(p2l - rd);
+			n_n = dot(Nn, h2);
+			if (n_n > 0)
+				mix_vsc = mix_vsc + mixmul(mS, ls) * pow_ref(n_n, shiness);
 		}
-		// append the children to level+1 (whole warp participates)
-		const uint32_t sFlec = warp_append(&ws->count[level + 1], wantFlec);
-		if (wantFlec)
-		{
-			if (sFlec < N.capacity)
-			{
-				N.ray_o[sFlec] = co, N.ray_d[sFlec] = cdFlec, N.ray_meta[sFlec] = metaFlec;
-				aux.x = (int)sFlec;
-			}
-			else
-				ws->overflow = 1;
-		}
-		const uint32_t sFrac = warp_append(&ws->count[level + 1], wantFrac);
-		if (wantFrac)
-		{
-			if (sFrac < N.capacity)
-			{
-				N.ray_o[sFrac] = make_float4(co.x, co.y, co.z, fracRfr), N.ray_d[sFrac] = cdFrac, N.ray_meta[sFrac] = metaFrac;
-				aux.y = (int)sFrac;
-			}
-			else
-				ws->overflow = 1;
-		}
-		if (h < n)
-			L.aux[i] = aux;
-		// ray statistics (one atomic per warp)
-		const uint32_t mf = __ballot_sync(0xffffffffu, wantFlec), mr = __ballot_sync(0xffffffffu, wantFrac);
-		if ((threadIdx.x & 31) == 0)
-		{
-			if (mf) atomicAdd(&ws->n_reflect, (unsigned long long)__popc(mf));
-			if (mr) atomicAdd(&ws->n_refract, (unsigned long long)__popc(mr));
-		}
+		const F3 c_all = mixmul(vc, mix_vd + mix_va) + mix_vsc;
+		L.color[i] = make_float4(c_all.x, c_all.y, c_all.z, hp.w);
 	}
 }
 
@@ -466,27 +482,18 @@ void rtk_raygen(cudaStream_t st, const FrameParams *F, const LevelBuf &L, uint32
 	k_raygen<<<grid_for(n, 256, sms * 16), 256, 0, st>>>(F, L, n);
 }
 
-void rtk_trace(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, WaveState *ws, uint32_t level, float zNear, uint32_t maxRays, unsigned sms, bool stats)
+void rtk_wave(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const LevelBuf &N, const LevelBuf &Lprev, WaveState *ws,
+	uint32_t level, bool traceOn, bool shadowOn, float zNear, uint32_t maxItems, unsigned sms, bool stats)
 {
-	const unsigned g = grid_for(maxRays, RT_BLOCK, sms * 8);   // persistent: 8 CTAs per SM
-	if (stats) k_trace<true><<<g, RT_BLOCK, 0, st>>>(S, F, L, ws, level, zNear);
-	else k_trace<false><<<g, RT_BLOCK, 0, st>>>(S, F, L, ws, level, zNear);
+	const unsigned g = grid_for(maxItems, RT_BLOCK, sms * 8);   // persistent: 8 CTAs per SM
+	if (stats) k_wave<true><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+	else k_wave<false><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
 }
 
-void rtk_shadow(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, WaveState *ws,
-	uint32_t level, uint32_t nEnabled, uint32_t maxRays, unsigned sms, bool stats)
+void rtk_shade(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelSet &LS, const WaveState *ws, uint32_t levels, uint32_t maxRays, unsigned sms)
 {
-	if (nEnabled == 0) return;
-	const unsigned g = grid_for(maxRays * nEnabled, RT_BLOCK, sms * 8);
-	if (stats) k_shadow<true><<<g, RT_BLOCK, 0, st>>>(S, F, L, ws, level);
-	else k_shadow<false><<<g, RT_BLOCK, 0, st>>>(S, F, L, ws, level);
-}
-
-void rtk_shade(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const LevelBuf &N, WaveState *ws,
-	uint32_t level, float zNear, uint32_t maxRays, unsigned sms)
-{
-	(void)zNear;
-	k_shade<<<grid_for(maxRays, 128, sms * 16), 128, 0, st>>>(S, F, L, N, ws, level);
+	const dim3 g(grid_for(maxRays, 128, sms * 8), levels);
+	k_shade<<<g, 128, 0, st>>>(S, F, LS, ws);
 }
 
 void rtk_combine(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const LevelBuf &N, const WaveState *ws,

@@ -19,9 +19,13 @@ struct LevelBuf
 	float4 *color;       // node-local colour, then combined colour; w = Color::alpha (distance)
 	int4 *aux;           // x: reflect child slot, y: refract child slot (-1 none), z: material (-1 = no surface), w: bit0 reflect, bit1 refract, bit2 Beer
 	uint8_t *shadow;     // [light][capacity]: 1 = occluded
+	float4 *hit_n;       // HitRes::normal.xyz, bits of the material index
+	float4 *hit_uv;      // HitRes::tcoord.u, .v, bits of the texture index (-1 none), unused
 	uint32_t *hit_list;  // compacted slots of the rays that found a surface inside [zNear, zFar]
 	uint32_t capacity;
 };
+
+struct LevelSet { LevelBuf l[RT_MAX_LEVELS + 2]; };
 
 struct WaveState
 {
@@ -35,11 +39,9 @@ struct WaveState
 };
 
 void rtk_raygen(cudaStream_t st, const FrameParams *F, const LevelBuf &L, uint32_t n, unsigned sms);
-void rtk_trace(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, WaveState *ws, uint32_t level, float zNear, uint32_t maxRays, unsigned sms, bool stats);
-void rtk_shadow(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, WaveState *ws,
-	uint32_t level, uint32_t nEnabled, uint32_t maxRays, unsigned sms, bool stats);
-void rtk_shade(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const LevelBuf &N, WaveState *ws,
-	uint32_t level, float zNear, uint32_t maxRays, unsigned sms);
+void rtk_wave(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const LevelBuf &N, const LevelBuf &Lprev, WaveState *ws,
+	uint32_t level, bool traceOn, bool shadowOn, float zNear, uint32_t maxItems, unsigned sms, bool stats);
+void rtk_shade(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelSet &LS, const WaveState *ws, uint32_t levels, uint32_t maxRays, unsigned sms);
 void rtk_combine(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const LevelBuf &N, const WaveState *ws,
 	uint32_t level, uint8_t *out, uint32_t maxRays, unsigned sms);
 

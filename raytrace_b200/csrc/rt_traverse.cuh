@@ -54,14 +54,14 @@ struct PartCache
 	uint32_t mask;   // enabled octants, 0 if the part fails `minist < hr.distance`
 };
 
-__device__ __forceinline__ uint32_t part_mask(const SceneDev &S, const RayD &ray, uint32_t part, float hr_distance, PartCache &pc)
+__device__ __forceinline__ uint32_t part_mask(const SceneDev &S, const RayD &ray, const F3 &idir, uint32_t part, float hr_distance, PartCache &pc)
 {
 	if (pc.part != part)
 	{
 		const DevPart &P = S.parts[part];
 		const float4 bmin = __ldg(&P.box_min), bmax = __ldg(&P.box_max);
 		uint32_t m;
-		const float minist = border_test_ex(ray.o, ray.d, f3(bmin), f3(bmax), &m);
+		const float minist = border_test_ex(ray.o, ray.d, idir, f3(bmin), f3(bmax), &m);
 		pc.part = part;
 		pc.mask = (minist < hr_distance) ? m : 0u;
 	}
@@ -88,9 +88,15 @@ __device__ __forceinline__ bool tri_rank_less(const SceneDev &S, uint32_t partA,
 	return triA < triB;   // same part: original index order == index-in-part order
 }
 
-template<bool ANY, bool STATS>
-__device__ __forceinline__ void leaf_tris(const SceneDev &S, const RayD &ray, uint32_t first, uint32_t count,
-	float hr_distance, uint32_t model_tri_begin, uint32_t model_tri_end, PartCache &pc, Best &best, bool &done, TravStats &st)
+// FAST (closest hit only): accept the nearest exact hit tentatively and postpone the replay of the
+// reference's culling predicate to ONE check per ray after the walk (verify_fast_hit); anything
+// the postponed check cannot decide -- an exact distance tie, a hit on the triangle the ray left
+// from -- raises `slow`, and the caller redoes this Model with the immediate per-candidate replay.
+// The result is identical either way: if the final nearest hit passes the replay, every candidate
+// that was tentatively accepted before it was farther and irrelevant; if it fails, we fall back.
+template<bool ANY, bool FAST, bool STATS>
+__device__ __forceinline__ void leaf_tris(const SceneDev &S, const RayD &ray, const F3 &idir, uint32_t first, uint32_t count,
+	float hr_distance, uint32_t model_tri_begin, uint32_t model_tri_end, PartCache &pc, Best &best, bool &done, bool &slow, TravStats &st)
 {
 	for (uint32_t k = 0; k < count; ++k)
 	{
@@ -103,8 +109,20 @@ __device__ __forceinline__ void leaf_tris(const SceneDev &S, const RayD &ray, ui
 			continue;
 		const uint32_t tri = __float_as_uint(g0.w);
 		const uint32_t pinfo = __float_as_uint(g1.w);
+		if (FAST)
+		{
+			if (t == best.t || (is_tri(ray.skip) && (ray.skip & 0x0FFFFFFFu) == tri))
+			{
+				slow = true;
+				continue;
+			}
+			best.t = t;
+			best.id = RT_ID_TRI | tri;   // octant filled in by verify_fast_hit
+			pc.part = pinfo;             // FAST reuses the cache slot to remember the winner's part | octants
+			continue;
+		}
 		const uint32_t part = pinfo >> 8, octs = pinfo & 0xFFu;
-		const uint32_t mask = part_mask(S, ray, part, hr_distance, pc);
+		const uint32_t mask = part_mask(S, ray, idir, part, hr_distance, pc);
 		const int oct = tested_octant(octs, mask, tri, ray.skip);
 		if (oct < 0)
 			continue;
@@ -170,13 +188,15 @@ __device__ __forceinline__ void test_prim(const SceneDev &S, const RayD &ray, ui
 // registers only.
 #define RT_TRAV_DONE (-1)   // never a valid leaf code: that would be first = 2^28-1, count = 8
 
-template<bool ANY, bool TRIS, bool STATS>
+template<bool ANY, bool TRIS, bool FAST, bool STATS>
 __device__ __forceinline__ void traverse(const SceneDev &S, const RayD &ray, const F3 &idir, int root,
 	float hr_distance, uint32_t rangeBegin, uint32_t rangeEnd, Best &best, bool &done, TravStats &st,
 	uint32_t winLo = 0u, uint32_t winHi = 0xFFFFFFFFu)
 {
 	PartCache pc;
 	pc.part = 0xFFFFFFFFu, pc.mask = 0;
+	bool slow = false;
+	const uint32_t idBefore = best.id;
 	int stack[RT_STACK];
 	int sp = 0;
 	int cur = root;
@@ -187,6 +207,12 @@ __device__ __forceinline__ void traverse(const SceneDev &S, const RayD &ray, con
 			const BvhNode *n = &S.nodes[cur];
 			const float4 a = ldg4(&n->a), b = ldg4(&n->b), c = ldg4(&n->c);
 			const int2 link = __ldg((const int2 *)&n->link);
+			if (S.tune & 1u)
+			{
+				// warm L1 with both children while the slab tests run (one of them is needed next)
+				if (link.x >= 0) asm volatile("prefetch.global.L1 [%0];" :: "l"(&S.nodes[link.x]));
+				if (link.y >= 0) asm volatile("prefetch.global.L1 [%0];" :: "l"(&S.nodes[link.y]));
+			}
 			if (STATS) ++st.nodes;
 			float t0, t1;
 			const bool h0 = slab_hit(a.x, a.y, a.z, a.w, b.x, b.y, ray.o, idir, best.t, t0);
@@ -202,10 +228,10 @@ __device__ __forceinline__ void traverse(const SceneDev &S, const RayD &ray, con
 			else cur = sp ? stack[--sp] : RT_TRAV_DONE;
 		}
 		if (cur == RT_TRAV_DONE)
-			return;
+			break;
 		const uint32_t first = ((uint32_t)cur & 0x7FFFFFFFu) >> 3, count = ((uint32_t)cur & 7u) + 1u;
 		if (TRIS)
-			leaf_tris<ANY, STATS>(S, ray, first, count, hr_distance, rangeBegin, rangeEnd, pc, best, done, st);
+			leaf_tris<ANY, FAST, STATS>(S, ray, idir, first, count, hr_distance, rangeBegin, rangeEnd, pc, best, done, slow, st);
 		else
 			for (uint32_t k = 0; k < count; ++k)
 			{
@@ -218,6 +244,21 @@ __device__ __forceinline__ void traverse(const SceneDev &S, const RayD &ray, con
 		if (ANY && done)
 			return;
 		cur = sp ? stack[--sp] : RT_TRAV_DONE;
+	}
+	if (FAST)
+	{
+		// one replay per ray, executed by the whole warp together
+		if (!slow && best.id != idBefore)
+		{
+			const uint32_t pinfo = pc.part, tri = best.id & 0x0FFFFFFFu;
+			PartCache one;
+			one.part = 0xFFFFFFFFu, one.mask = 0;
+			const uint32_t mask = part_mask(S, ray, idir, pinfo >> 8, hr_distance, one);
+			const int oct = tested_octant(pinfo & 0xFFu, mask, tri, ray.skip);
+			if (oct < 0) slow = true;
+			else best.id = best.newobj = RT_ID_TRI | ((uint32_t)oct << 28) | tri;
+		}
+		if (slow) best.t = -1.0f;   // tells the caller to redo the item with the immediate replay
 	}
 }
 
@@ -243,23 +284,34 @@ __device__ __forceinline__ void trace_scene(const SceneDev &S, const RayD &ray, 
 				// the ray starts inside a sphere of this run: `newobj` depends on which hits were
 				// accepted before / after that sphere in object order, so walk the run in three
 				// order-respecting phases (primitives before it, the sphere itself, primitives after)
-				traverse<ANY, false, STATS>(S, ray, idir, it.root, best.t, it.first, end, best, done, st, it.first, ray.skip);
+				traverse<ANY, false, false, STATS>(S, ray, idir, it.root, best.t, it.first, end, best, done, st, it.first, ray.skip);
 				if (STATS) ++st.prims;
 				test_prim<ANY>(S, ray, ray.skip, false, best, done);
-				traverse<ANY, false, STATS>(S, ray, idir, it.root, best.t, it.first, end, best, done, st, ray.skip + 1u, end);
+				traverse<ANY, false, false, STATS>(S, ray, idir, it.root, best.t, it.first, end, best, done, st, ray.skip + 1u, end);
 			}
 			else
-				traverse<ANY, false, STATS>(S, ray, idir, it.root, best.t, it.first, end, best, done, st);
+				traverse<ANY, false, false, STATS>(S, ray, idir, it.root, best.t, it.first, end, best, done, st);
 		}
 		else
 		{
 			const DevModel &M = S.models[it.first];
 			const float4 mn = __ldg(&M.border_min), mx = __ldg(&M.border_max);
 			// Model.cpp:752: `if (BorderTest(ray, BorderMin, BorderMax) < hr.distance)`
-			if (!(border_test(ray.o, ray.d, f3(mn), f3(mx)) < best.t))
+			if (!(border_test(ray.o, ray.d, idir, f3(mn), f3(mx)) < best.t))
 				continue;
 			const uint32_t tb = __ldg(&M.tri_begin);
-			traverse<ANY, true, STATS>(S, ray, idir, it.root, best.t, tb, tb + __ldg(&M.tri_count), best, done, st);
+			if (ANY)
+				traverse<true, true, false, STATS>(S, ray, idir, it.root, best.t, tb, tb + __ldg(&M.tri_count), best, done, st);
+			else
+			{
+				const Best before = best;
+				traverse<false, true, true, STATS>(S, ray, idir, it.root, before.t, tb, tb + __ldg(&M.tri_count), best, done, st);
+				if (best.t < 0.0f)
+				{
+					best = before;
+					traverse<false, true, false, STATS>(S, ray, idir, it.root, before.t, tb, tb + __ldg(&M.tri_count), best, done, st);
+				}
+			}
 		}
 		if (ANY && done)
 			return;

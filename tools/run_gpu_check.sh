@@ -1,4 +1,3 @@
 set -x
 timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -5
-python tools/perf_probe.py c2 c3 c4 2>&1 | tee gpurun_out/perf2.log
-for l in 1 2; do RT_B200_LEAF_SIZE=$l python tools/perf_probe.py c3 2>&1 | tee -a gpurun_out/perf2.log; done
+python tools/perf_probe.py c2 c3 c4 2>&1 | tee gpurun_out/perf5.log
