@@ -706,6 +706,14 @@ extern "C" int rt_read_counters(rt_ctx *c, rt_counters *out)
 	for (uint32_t l = 0; l <= c->lastMaxLevel; ++l) hits += W.n_hit[l];
 	out->shadow = hits * enabled;
 	out->nodes_visited = W.nodes_visited, out->tri_tests = W.tri_tests, out->prim_tests = W.prim_tests;
+	if (getenv("RT_B200_PRINT_HIST") && W.nodes_visited)
+	{
+		fprintf(stderr, "nodes-per-ray histogram (log2 buckets) closest:");
+		for (int b = 0; b < 12; ++b) fprintf(stderr, " %u", W.node_hist[b]);
+		fprintf(stderr, "\n                                          shadow:");
+		for (int b = 12; b < 24; ++b) fprintf(stderr, " %u", W.node_hist[b]);
+		fprintf(stderr, "\n");
+	}
 	out->render_ms = c->renderMs;
 	out->trace_ms = c->traceMs, out->shadow_ms = c->shadowMs, out->shade_ms = c->shadeMs, out->other_ms = c->otherMs;
 	out->launches = c->lastLaunches;

@@ -121,11 +121,22 @@ __global__ void __launch_bounds__(256) k_raygen(const FrameParams *__restrict__ 
 // Persistent warps: each warp pulls 32 consecutive work items at a time (one atomic per fetch), so
 // SMs stay busy until the queue is dry and queue order (8x4 pixel tiles for primary rays, parent
 // order for secondary rays, same light for shadow rays) keeps the lanes of a warp coherent.
-__device__ __forceinline__ uint32_t warp_fetch(uint32_t *head)
+__device__ __forceinline__ uint32_t warp_fetch(uint32_t *head, uint32_t batch)
 {
 	uint32_t base = 0;
-	if ((threadIdx.x & 31) == 0) base = atomicAdd(head, 32u);
+	if ((threadIdx.x & 31) == 0) base = atomicAdd(head, batch);
 	return __shfl_sync(0xffffffffu, base, 0);
+}
+
+// Rays per fetch.  A warp executes the union of its lanes' divergent paths, so when a queue holds
+// fewer rays than the resident warps could take 32 at a time (deep recursion levels), handing each
+// warp only a few rays spreads the same work over more schedulers and shortens the critical path.
+__device__ __forceinline__ uint32_t fetch_batch(uint32_t n)
+{
+	const uint32_t warps = gridDim.x * (RT_BLOCK / 32);
+	uint32_t b = (n + warps - 1) / warps;
+	b = b < 2u ? 2u : b;
+	return b > 32u ? 32u : b;
 }
 
 __device__ __forceinline__ uint32_t warp_append(uint32_t *counter, bool want)
@@ -231,12 +242,14 @@ __global__ void __launch_bounds__(RT_BLOCK, 8) k_wave(SceneDev S, const FramePar
 		const uint32_t n = ws->count[level] < L.capacity ? ws->count[level] : L.capacity;
 		const bool refraction = F.type != RT_TYPE_REFLECT;
 		const bool deeper = level + 1 <= F.max_level;
+		const uint32_t batch = fetch_batch(n);
 		while (true)
 		{
-			const uint32_t base = warp_fetch(&ws->head_trace[level]);
+			const uint32_t base = warp_fetch(&ws->head_trace[level], batch);
 			if (base >= n)
 				break;
-			const uint32_t i = base + (threadIdx.x & 31u);
+			const uint32_t lane = threadIdx.x & 31u;
+			const uint32_t i = lane < batch ? base + lane : 0xFFFFFFFFu;
 			bool surface = false, wantFlec = false, wantFrac = false;
 			float4 co = make_float4(0, 0, 0, 0), cdFlec = co, cdFrac = co;
 			uint2 metaFlec = make_uint2(0, 0), metaFrac = metaFlec;
@@ -247,7 +260,9 @@ __global__ void __launch_bounds__(RT_BLOCK, 8) k_wave(SceneDev S, const FramePar
 				const RayD ray = load_ray(L, i);
 				Best best = { 1e20f, RT_ID_NONE, ray.skip };
 				bool done = false;
+				const uint32_t nodes0 = st.nodes;
 				trace_scene<false, STATS>(S, ray, best, done, st);
+				if (STATS) atomicAdd(&ws->node_hist[min(11, 31 - __clz((int)(st.nodes - nodes0 + 1u)))], 1u);
 				const F3 P = ray.o + ray.d * best.t;
 				L.hit_p[i] = make_float4(P.x, P.y, P.z, best.t);
 				L.hit_id[i] = make_uint2(best.id, best.newobj);
@@ -343,12 +358,14 @@ __global__ void __launch_bounds__(RT_BLOCK, 8) k_wave(SceneDev S, const FramePar
 		const uint32_t lp = level - 1u;
 		const uint32_t nHit = ws->n_hit[lp];
 		const uint32_t n = nHit * F.n_enabled;
+		const uint32_t batch = fetch_batch(n);
 		while (true)
 		{
-			const uint32_t base = warp_fetch(&ws->head_shadow[lp]);
+			const uint32_t base = warp_fetch(&ws->head_shadow[lp], batch);
 			if (base >= n)
 				break;
-			const uint32_t w = base + (threadIdx.x & 31u);
+			const uint32_t lane = threadIdx.x & 31u;
+			const uint32_t w = lane < batch ? base + lane : 0xFFFFFFFFu;
 			if (w < n)
 			{
 				const uint32_t k = F.enabled_index[w / nHit], i = Lprev.hit_list[w % nHit];
@@ -363,7 +380,9 @@ __global__ void __launch_bounds__(RT_BLOCK, 8) k_wave(SceneDev S, const FramePar
 				ray.isInside = 0;
 				Best best = { dis, RT_ID_NONE, RT_ID_NONE };
 				bool done = false;
+				const uint32_t nodes0 = st.nodes;
 				trace_scene<true, STATS>(S, ray, best, done, st);
+				if (STATS) atomicAdd(&ws->node_hist[12 + min(11, 31 - __clz((int)(st.nodes - nodes0 + 1u)))], 1u);
 				Lprev.shadow[(size_t)k * Lprev.capacity + i] = done ? 1 : 0;
 			}
 		}

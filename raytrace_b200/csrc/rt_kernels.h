@@ -36,6 +36,7 @@ struct WaveState
 	uint32_t pad;
 	unsigned long long n_reflect, n_refract;
 	unsigned long long nodes_visited, tri_tests, prim_tests;
+	unsigned int node_hist[24];          // RT_FLAG_STATS: rays by floor(log2(nodes visited + 1)), closest-hit [0..11], shadow [12..23]
 };
 
 void rtk_raygen(cudaStream_t st, const FrameParams *F, const LevelBuf &L, uint32_t n, unsigned sms);

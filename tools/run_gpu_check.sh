@@ -1,3 +1,3 @@
-set -x
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -5
-python tools/perf_probe.py c2 c3 c4 2>&1 | tee gpurun_out/perf5.log
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+python tools/perf_probe.py c2 c3 c4 2>&1 | tee gpurun_out/perf7.log
+RT_B200_LEAF_SIZE=2 python tools/perf_probe.py c3 2>&1 | tee -a gpurun_out/perf7.log
