@@ -12,7 +12,7 @@ is quoted on).  A ray = one closest-hit or one shadow any-hit query (SURVEY.md 8
   e2e      same metric through the reference-facing call RayTracer::start() with HOST buffers:
            every step re-flattens the Scene, uploads the per-frame tables (H2D) and reads the
            RGB8 frame back into RayTracer::output (D2H) inside the timed region.
-  roofline FP32-issue roofline of the traversal kernels (k_trace + k_shadow): algorithmic FLOPs
+  roofline FP32-issue roofline of the traversal kernel (k_wave, all launches of a frame): algorithmic FLOPs
            from device counters (DESIGN.md "flop model") / their CUDA-event time, against
            148 SMs x 128 lanes x sm_max_mhz of MEASURED_PEAKS.json (1 lane-instr = 1 flop because the
            parity path is unfused); HBM figures are reported beside it as the secondary bound.
@@ -216,26 +216,13 @@ def main():
     ck(R.rt.rt_upload_scene(h_ctx, desc_ptr), "rt_upload_scene")
     params = R.RenderParams(R.MY_MODEL_RAYTRACE, level, rank, world, 0, 0)
 
-    blk_h = h // 64
-    my_bands = [t for t in range(blk_h) if t % world == rank]
-    max_bands = (blk_h + world - 1) // world
-    band_bytes = 64 * w * 3
-    gathered = [torch.empty((max_bands, band_bytes), dtype=torch.uint8, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
-    mine = torch.empty((max_bands, band_bytes), dtype=torch.uint8, device=dev) if world > 1 else None
-    full = torch.full((h, w, 3), 127, dtype=torch.uint8, device=dev) if (world > 1 and rank == 0) else None
+    from raytrace_b200.distributed import FrameGather
+    gather = FrameGather(w, h, rank, world, dev) if world > 1 else None
 
     def step():
         ck(R.rt.rt_render_async(h_ctx, C.byref(params)), "rt_render_async")
-        if world > 1:
-            # NCCL framebuffer gather: this rank's 64-row bands -> rank 0, de-interleaved there
-            bands = frame.view(-1)[: blk_h * band_bytes].view(blk_h, band_bytes)
-            mine[: len(my_bands)].copy_(bands[rank::world])
-            dist.gather(mine, gathered, dst=0)
-            if rank == 0:
-                fb = full.view(-1)[: blk_h * band_bytes].view(blk_h, band_bytes)
-                for r in range(world):
-                    nb = len(range(r, blk_h, world))
-                    fb[r::world].copy_(gathered[r][:nb])
+        if gather is not None:
+            gather.gather(frame)   # NCCL: this rank's 64-row bands -> rank 0, de-interleaved there
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -262,7 +249,6 @@ def main():
         sampler.start()
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage = {"trace": 0.0, "shadow": 0.0, "shade": 0.0, "other": 0.0, "render": 0.0}
     e0.record(stream)
     for _ in range(args.steps):
         step()
@@ -270,12 +256,21 @@ def main():
     sync_all()
     # per-stage split from the library's own CUDA events (last timed frame, scaled to K steps)
     ck(R.rt.rt_read_counters(h_ctx, C.byref(cnt)), "rt_read_counters")
-    stage = {"trace": cnt.trace_ms * args.steps, "shadow": cnt.shadow_ms * args.steps, "shade": cnt.shade_ms * args.steps,
+    # (closest-hit and shadow queries share the fused wave kernels: "traverse")
+    stage = {"traverse": cnt.trace_ms * args.steps, "shade": cnt.shade_ms * args.steps,
              "other": cnt.other_ms * args.steps, "render": cnt.render_ms * args.steps}
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
+    # per-rank view (load balance of the image-space shards)
+    mine_t = torch.tensor([e0.elapsed_time(e1) / args.steps, float(rays_local)], dtype=torch.float64, device=dev)
+    per_rank = [torch.zeros_like(mine_t) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(per_rank, mine_t)
+    else:
+        per_rank = [mine_t]
+    per_rank = [{"rank": r, "ms_per_step": float(t[0].item()), "rays_per_frame": int(t[1].item())} for r, t in enumerate(per_rank)]
     clocks = sampler.stop() if rank == 0 else None
     value = rays_total * args.steps / (ms_total * 1e-3) / 1e6
 
@@ -307,8 +302,8 @@ def main():
         peak, peak_src, hbm_peak = sm_peak_fp32_tflops()
         # flop model: 22 per child box, 47 per triangle test, 23 per analytic primitive
         flops = cs.nodes_visited * 2 * 22 + cs.tri_tests * 47 + cs.prim_tests * 23
-        trav_ms = (stage["trace"] + stage["shadow"]) / args.steps
-        trav_launches = (level + 1) * 2
+        trav_ms = stage["traverse"] / args.steps
+        trav_launches = level + 2
         achieved = flops / (trav_ms * 1e-3) / 1e12 if trav_ms > 0 else 0.0
         queue_bytes = rays_local * 100   # ~100 B of ray/hit/node records written+read per ray
         line = {
@@ -322,14 +317,14 @@ def main():
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": float(e2e_s.item()) / args.steps * 1e3,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": {"bound": "fp32_issue", "kernel": "k_trace + k_shadow (BVH traversal, all levels)", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "fp32_issue", "kernel": "k_wave (closest-hit level l fused with shadow any-hit level l-1; all launches of a frame)", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": f"148 SMs x 128 lanes x {peak_src} (of measured)",
                          "traffic": None, "launches_per_step": trav_launches, "avg_launch_ms": trav_ms / trav_launches,
                          "flops_per_step": flops, "nodes_per_ray": cs.nodes_visited / max(rays_local, 1), "tri_tests_per_ray": cs.tri_tests / max(rays_local, 1),
                          "stage_ms": {k: v / args.steps for k, v in stage.items()},
                          "hbm_secondary": {"queue_bytes_per_step": queue_bytes, "achieved_gbs": queue_bytes / (stage["render"] / args.steps * 1e-3) / 1e9,
                                            "peak_gbs": hbm_peak}},
-            "clocks": clocks,
+            "clocks": clocks, "per_rank": per_rank,
             "build": {"upload_ms": cs.upload_ms, "lbvh_build_ms": cs.build_ms, "bvh_nodes": cs.bvh_nodes, "bvh_depth": cs.bvh_depth},
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -98,7 +98,7 @@ struct rt_ctx
 
 	// per frame
 	FrameParams *hFrame = nullptr, *dFrame = nullptr;
-	WaveState *hWave = nullptr, *dWave = nullptr;
+	WaveState *hWave = nullptr, *hWaveInit = nullptr, *dWave = nullptr;   // hWave: D2H results, hWaveInit: H2D initial state
 	LevelStore levels[RT_MAX_LEVELS + 2];
 	DevBuf<uint8_t> out;
 	int outW = 0, outH = 0;
@@ -138,6 +138,7 @@ extern "C" int rt_create(int device, rt_ctx **out)
 	CU(cudaMallocHost(&c->hFrame, sizeof(FrameParams)));
 	CU(cudaMalloc(&c->dFrame, sizeof(FrameParams)));
 	CU(cudaMallocHost(&c->hWave, sizeof(WaveState)));
+	CU(cudaMallocHost(&c->hWaveInit, sizeof(WaveState)));
 	CU(cudaMalloc(&c->dWave, sizeof(WaveState)));
 	memset(&c->S, 0, sizeof c->S);
 	c->S.tune = 0;
@@ -159,7 +160,7 @@ extern "C" void rt_destroy(rt_ctx *c)
 	c->triTcoords.release(), c->bvhPrims.release(), c->triSlot.release(), c->triPart.release(), c->leafOrder.release();
 	c->dModels.release(), c->dParts.release(), c->nodes.release(), c->items.release(), c->out.release();
 	rtb_free_scratch(c->scratch);
-	cudaFreeHost(c->hFrame), cudaFree(c->dFrame), cudaFreeHost(c->hWave), cudaFree(c->dWave);
+	cudaFreeHost(c->hFrame), cudaFree(c->dFrame), cudaFreeHost(c->hWave), cudaFreeHost(c->hWaveInit), cudaFree(c->dWave);
 	cudaEventDestroy(c->evStart), cudaEventDestroy(c->evStop), cudaEventDestroy(c->evA), cudaEventDestroy(c->evB);
 	for (auto &e : c->evStage) cudaEventDestroy(e);
 	if (c->ownStream) cudaStreamDestroy(c->stream);
@@ -188,7 +189,7 @@ extern "C" int rt_upload_scene(rt_ctx *c, const rt_scene_desc *s)
 {
 	if (!c || !s) return fail(RT_E_INVALID, "rt_upload_scene: NULL argument");
 	CU(cudaSetDevice(c->device));
-	if (c->frameInFlight) { CU(cudaEventSynchronize(c->evStop)); c->frameInFlight = false; }
+	if (c->frameInFlight) { CU(cudaEventSynchronize(c->evB)); c->frameInFlight = false; }
 	if (s->n_lights > RT_MAX_LIGHTS) return fail(RT_E_LIMIT, "rt_upload_scene: %u lights (max %d, Scene.cpp:85)", s->n_lights, RT_MAX_LIGHTS);
 	if (s->n_tris >= 0x0FFFFFFFu) return fail(RT_E_LIMIT, "rt_upload_scene: too many triangles");
 	for (uint32_t i = 1; i < s->n_prims; ++i)
@@ -443,6 +444,8 @@ static LevelBuf level_buf(const LevelStore &L)
 	return b;
 }
 
+static int finish_frame(rt_ctx *c);
+
 extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 {
 	if (!c || !p) return fail(RT_E_INVALID, "rt_render_async: NULL argument");
@@ -451,7 +454,9 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 		return fail(RT_E_INVALID, "rt_render_async: render type 0x%x is not implemented on the device path yet", p->type);
 	if (p->max_level >= RT_MAX_LEVELS) return fail(RT_E_LIMIT, "rt_render_async: max_level %u (limit %d)", p->max_level, RT_MAX_LEVELS - 1);
 	CU(cudaSetDevice(c->device));
-	if (c->frameInFlight) { CU(cudaEventSynchronize(c->evStop)); c->frameInFlight = false; }
+	// the previous frame must have drained completely (including the read-back of its WaveState)
+	// before the pinned staging buffers are rewritten
+	if (c->frameInFlight) { int rc = finish_frame(c); if (rc != RT_OK) return rc; }
 	cudaStream_t st = c->stream;
 	const rt_camera &cam = c->camera;
 	const int W = cam.width, H = cam.height;
@@ -508,11 +513,11 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 	}
 	{ int rc = ensure_level(c, p->max_level + 1, 1, 1); if (rc != RT_OK) return rc; }
 
-	WaveState &Wv = *c->hWave;
+	WaveState &Wv = *c->hWaveInit;
 	memset(&Wv, 0, sizeof Wv);
 	Wv.count[0] = nPix;
 	CU(cudaMemcpyAsync(c->dFrame, c->hFrame, sizeof(FrameParams), cudaMemcpyHostToDevice, st));
-	CU(cudaMemcpyAsync(c->dWave, c->hWave, sizeof(WaveState), cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(c->dWave, c->hWaveInit, sizeof(WaveState), cudaMemcpyHostToDevice, st));
 	c->frameH2D = sizeof(FrameParams) + sizeof(WaveState), c->frameD2H = sizeof(WaveState);
 	CU(cudaEventRecord(c->evStart, st));
 

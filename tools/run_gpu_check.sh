@@ -1,3 +1,2 @@
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-python tools/perf_probe.py c2 c3 c4 2>&1 | tee gpurun_out/perf7.log
-RT_B200_LEAF_SIZE=2 python tools/perf_probe.py c3 2>&1 | tee -a gpurun_out/perf7.log
+python bench.py --steps 20 --warmup 3 2>gpurun_out/bench_err.log | tee gpurun_out/bench_c3_n1.json
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 2>gpurun_out/bench_err2.log | tee gpurun_out/bench_c3_n2.json
