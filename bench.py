@@ -300,8 +300,8 @@ def main():
 
     if rank == 0:
         peak, peak_src, hbm_peak = sm_peak_fp32_tflops()
-        # flop model: 22 per child box, 47 per triangle test, 23 per analytic primitive
-        flops = cs.nodes_visited * 2 * 22 + cs.tri_tests * 47 + cs.prim_tests * 23
+        # flop model: 22 per child box (4 per 4-wide node), 47 per triangle test, 23 per analytic primitive
+        flops = cs.nodes_visited * 4 * 22 + cs.tri_tests * 47 + cs.prim_tests * 23
         trav_ms = stage["traverse"] / args.steps
         trav_launches = level + 2
         achieved = flops / (trav_ms * 1e-3) / 1e12 if trav_ms > 0 else 0.0

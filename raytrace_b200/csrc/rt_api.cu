@@ -90,11 +90,12 @@ struct rt_ctx
 	DevBuf<uint32_t> bvhPrims, triSlot, triPart, leafOrder;
 	DevBuf<DevModel> dModels;
 	DevBuf<DevPart> dParts;
-	DevBuf<BvhNode> nodes;
+	DevBuf<BvhNode> nodes;      // binary LBVH (build-time only)
+	DevBuf<BvhNode4> nodes4;    // 4-wide collapse used by the traversal
 	DevBuf<SceneItem> items;
 	SceneDev S;
 	BuildScratch *scratch = nullptr;
-	uint32_t bvhNodes = 0, bvhDepth = 0, leafSize = 4;
+	uint32_t bvhNodes = 0, bvhDepth = 0, leafSize = 2;
 
 	// per frame
 	FrameParams *hFrame = nullptr, *dFrame = nullptr;
@@ -158,7 +159,7 @@ extern "C" void rt_destroy(rt_ctx *c)
 	c->primGeom.release(), c->materials.release(), c->triPoints.release(), c->triNorms.release(), c->triGeomOrig.release(), c->triGeom.release();
 	c->boxLo.release(), c->boxHi.release(), c->partMid.release(), c->partPos.release(), c->primMeta.release(), c->textures.release(), c->texels.release();
 	c->triTcoords.release(), c->bvhPrims.release(), c->triSlot.release(), c->triPart.release(), c->leafOrder.release();
-	c->dModels.release(), c->dParts.release(), c->nodes.release(), c->items.release(), c->out.release();
+	c->dModels.release(), c->dParts.release(), c->nodes.release(), c->nodes4.release(), c->items.release(), c->out.release();
 	rtb_free_scratch(c->scratch);
 	cudaFreeHost(c->hFrame), cudaFree(c->dFrame), cudaFreeHost(c->hWave), cudaFreeHost(c->hWaveInit), cudaFree(c->dWave);
 	cudaEventDestroy(c->evStart), cudaEventDestroy(c->evStop), cudaEventDestroy(c->evA), cudaEventDestroy(c->evB);
@@ -351,6 +352,7 @@ extern "C" int rt_upload_scene(rt_ctx *c, const rt_scene_desc *s)
 			pi = end;
 		}
 		CU(c->nodes.reserve(nodeBudget + 1));
+		CU(c->nodes4.reserve(nodeBudget + 1));
 		CU(c->bvhPrims.reserve(primLeafSlots + 1));
 		CU(c->triGeomOrig.reserve(3 * (size_t)s->n_tris + 1));
 		CU(c->triGeom.reserve(3 * (size_t)s->n_tris + 1));
@@ -372,7 +374,7 @@ extern "C" int rt_upload_scene(rt_ctx *c, const rt_scene_desc *s)
 			{
 				PrimBoxArgs a{ c->primGeom.p, c->primMeta.p, c->boxLo.p, c->boxHi.p, it.first, it.count };
 				rtb_prim_boxes(st, a);
-				int rc = rtb_build(st, &c->scratch, c->boxLo.p, c->boxHi.p, it.count, 2, c->nodes.p, nodeCursor, primLeafCursor, c->bvhPrims.p + primLeafCursor, &res);
+				int rc = rtb_build(st, &c->scratch, c->boxLo.p, c->boxHi.p, it.count, 2, c->nodes.p, c->nodes4.p, nodeCursor, primLeafCursor, c->bvhPrims.p + primLeafCursor, &res);
 				if (rc) return fail(RT_E_CUDA, "LBVH build (primitives) failed: %s", cudaGetErrorString((cudaError_t)rc));
 				rtb_offset_order(st, c->bvhPrims.p + primLeafCursor, it.count, it.first);
 				it.root = res.root;
@@ -389,7 +391,7 @@ extern "C" int rt_upload_scene(rt_ctx *c, const rt_scene_desc *s)
 				a.tri_geom_orig = c->triGeomOrig.p + 3 * (size_t)M.tri_begin, a.box_lo = c->boxLo.p, a.box_hi = c->boxHi.p, a.n = M.tri_count;
 				a.id_base = M.tri_begin;
 				rtb_prepare_tris(st, a);
-				int rc = rtb_build(st, &c->scratch, c->boxLo.p, c->boxHi.p, M.tri_count, c->leafSize, c->nodes.p, nodeCursor, M.tri_begin, c->leafOrder.p, &res);
+				int rc = rtb_build(st, &c->scratch, c->boxLo.p, c->boxHi.p, M.tri_count, c->leafSize, c->nodes.p, c->nodes4.p, nodeCursor, M.tri_begin, c->leafOrder.p, &res);
 				if (rc) return fail(RT_E_CUDA, "LBVH build (model %u) failed: %s", it.first, cudaGetErrorString((cudaError_t)rc));
 				rtb_scatter_tris(st, c->triGeomOrig.p, c->leafOrder.p, M.tri_begin, M.tri_begin, M.tri_count, c->triGeom.p, c->triSlot.p);
 				it.root = res.root, it.count = M.tri_count;
@@ -398,7 +400,8 @@ extern "C" int rt_upload_scene(rt_ctx *c, const rt_scene_desc *s)
 			}
 		}
 		c->bvhNodes = nodeCursor;
-		if (c->bvhDepth + 1 > RT_STACK)
+		// a 4-wide step pushes up to three siblings and descends two binary levels
+		if (3 * ((c->bvhDepth + 1) / 2) + 1 > RT_STACK)
 			return fail(RT_E_LIMIT, "LBVH depth %u exceeds the traversal stack (%d)", c->bvhDepth, RT_STACK);
 		CU(c->items.upload(items.data(), items.size(), st, ub));
 		CU(cudaEventRecord(c->evStop, st));
@@ -411,7 +414,7 @@ extern "C" int rt_upload_scene(rt_ctx *c, const rt_scene_desc *s)
 		S.prim_geom = c->primGeom.p, S.prim_meta = c->primMeta.p, S.bvh_prims = c->bvhPrims.p;
 		S.models = c->dModels.p, S.parts = c->dParts.p;
 		S.tri_geom = c->triGeom.p, S.tri_norms = c->triNorms.p, S.tri_tcoords = c->triTcoords.p;
-		S.tri_slot = c->triSlot.p, S.tri_part = c->triPart.p, S.nodes = c->nodes.p, S.items = c->items.p;
+		S.tri_slot = c->triSlot.p, S.tri_part = c->triPart.p, S.nodes4 = c->nodes4.p, S.items = c->items.p;
 		S.n_items = (uint32_t)items.size(), S.n_prims = s->n_prims, S.n_tris = s->n_tris, S.n_parts = s->n_parts;
 	}
 	c->S.materials = c->materials.p, c->S.textures = c->textures.p, c->S.texels = c->texels.p;

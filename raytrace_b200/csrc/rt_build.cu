@@ -302,6 +302,60 @@ __global__ void k_refit(RefitArgs a)
 	}
 }
 
+// ---- collapse to 4-wide nodes ----------------------------------------------------------------------
+// Every binary node at even depth becomes a 4-wide node whose children are its grandchildren
+// (a child that is already a leaf stays a single child).  Only even-depth nodes are reachable from
+// the root through 4-wide links, so odd-depth slots of nodes4 stay unused.
+__global__ void k_collapse4(const BvhNode *nodes, BvhNode4 *nodes4, const int *parentOfInternal, uint32_t nodeBase, int nInternal)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nInternal) return;
+	int depth = 0;
+	for (int p = parentOfInternal[i]; p >= 0; p = parentOfInternal[p]) ++depth;
+	if (depth & 1) return;
+	const BvhNode n = nodes[nodeBase + i];
+	// unused slot: a degenerate box far away -- the min/max slab test is order-agnostic, so an
+	// "inverted" box would be hit; a point at 3e38 gives |t| ~ 3e38/|d| on every axis and always misses
+	const float far = 3.0e38f;
+	float lo[4][3], hi[4][3];
+	int link[4];
+	for (int k = 0; k < 4; ++k)
+	{
+		lo[k][0] = lo[k][1] = lo[k][2] = far, hi[k][0] = hi[k][1] = hi[k][2] = far;
+		link[k] = 0x7FFFFFFF;
+	}
+	int m = 0;
+	for (int side = 0; side < 2; ++side)
+	{
+		const int l = side ? n.link.y : n.link.x;
+		if (l < 0)
+		{
+			// leaf child: keep it with the box this node stores for it
+			if (side == 0) lo[m][0] = n.a.x, lo[m][1] = n.a.y, lo[m][2] = n.a.z, hi[m][0] = n.a.w, hi[m][1] = n.b.x, hi[m][2] = n.b.y;
+			else lo[m][0] = n.b.z, lo[m][1] = n.b.w, lo[m][2] = n.c.x, hi[m][0] = n.c.y, hi[m][1] = n.c.z, hi[m][2] = n.c.w;
+			link[m++] = l;
+		}
+		else
+		{
+			const BvhNode c = nodes[l];
+			lo[m][0] = c.a.x, lo[m][1] = c.a.y, lo[m][2] = c.a.z, hi[m][0] = c.a.w, hi[m][1] = c.b.x, hi[m][2] = c.b.y;
+			link[m++] = c.link.x;
+			lo[m][0] = c.b.z, lo[m][1] = c.b.w, lo[m][2] = c.c.x, hi[m][0] = c.c.y, hi[m][1] = c.c.z, hi[m][2] = c.c.w;
+			link[m++] = c.link.y;
+		}
+	}
+	BvhNode4 o;
+	o.lox = make_float4(lo[0][0], lo[1][0], lo[2][0], lo[3][0]);
+	o.loy = make_float4(lo[0][1], lo[1][1], lo[2][1], lo[3][1]);
+	o.loz = make_float4(lo[0][2], lo[1][2], lo[2][2], lo[3][2]);
+	o.hix = make_float4(hi[0][0], hi[1][0], hi[2][0], hi[3][0]);
+	o.hiy = make_float4(hi[0][1], hi[1][1], hi[2][1], hi[3][1]);
+	o.hiz = make_float4(hi[0][2], hi[1][2], hi[2][2], hi[3][2]);
+	o.link = make_int4(link[0], link[1], link[2], link[3]);
+	o.pad = make_int4(0, 0, 0, 0);
+	nodes4[nodeBase + i] = o;
+}
+
 __global__ void k_copy_order(const uint32_t *sorted, uint32_t n, uint32_t *out)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -309,7 +363,7 @@ __global__ void k_copy_order(const uint32_t *sorted, uint32_t n, uint32_t *out)
 }
 
 int rtb_build(cudaStream_t st, BuildScratch **scratch, const float4 *box_lo, const float4 *box_hi, uint32_t n,
-	uint32_t leafSize, BvhNode *nodes, uint32_t nodeBase, uint32_t leafBase, uint32_t *leafOrder, BvhBuildResult *res)
+	uint32_t leafSize, BvhNode *nodes, BvhNode4 *nodes4, uint32_t nodeBase, uint32_t leafBase, uint32_t *leafOrder, BvhBuildResult *res)
 {
 	if (n == 0) { res->root = 0, res->nodesUsed = 0, res->depth = 0; return 0; }
 	if (leafSize < 1) leafSize = 1;
@@ -338,6 +392,7 @@ int rtb_build(cudaStream_t st, BuildScratch **scratch, const float4 *box_lo, con
 	a.ilo = s->ilo, a.ihi = s->ihi, a.height = s->height, a.nodes = nodes;
 	a.nodeBase = nodeBase, a.leafBase = leafBase, a.leafSize = leafSize, a.n = (int)n;
 	k_refit<<<blocks, 256, 0, st>>>(a);
+	k_collapse4<<<blocks, 256, 0, st>>>(nodes, nodes4, s->parentOfInternal, nodeBase, (int)n - 1);
 	uint32_t depth = 0;
 	CK(cudaMemcpyAsync(&depth, s->height, sizeof depth, cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));

@@ -109,6 +109,16 @@ struct BvhNode   // 64 bytes: both children's boxes + links, fetched as 4 x 128-
 	int4 link;   // child0, child1 (>=0 node, <0 leaf: 0x80000000 | first<<3 | (count-1)), unused
 };
 
+// 4-wide node used by the traversal kernels: the two children of each child of a binary LBVH node
+// (collapsed on the GPU, rt_build.cu k_collapse4).  SoA so that one float4 holds the same plane of
+// all four child boxes; 7 x 128-bit loads, 128-byte aligned.  Unused slots carry a degenerate far-away box that no ray hits.
+struct BvhNode4
+{
+	float4 lox, loy, loz, hix, hiy, hiz;
+	int4 link;     // per child: >=0 node index, <0 leaf code 0x80000000 | first<<3 | (count-1)
+	int4 pad;
+};
+
 struct SceneDev
 {
 	// analytic primitives: 4 float4 + 1 int4 each
@@ -129,7 +139,7 @@ struct SceneDev
 	const float2 *tri_tcoords;   // 3 per triangle
 	const uint32_t *tri_slot;    // original index -> leaf-order slot (to re-run the hit test when shading)
 	const uint32_t *tri_part;    // original index -> global part index
-	const BvhNode *nodes;
+	const BvhNode4 *nodes4;
 	const SceneItem *items;
 	uint32_t n_items, n_prims, n_tris, n_parts;
 	uint32_t tune;               // bit0: prefetch child nodes (RT_B200_TUNE, development switch)

@@ -81,7 +81,7 @@ void rtb_prim_boxes(cudaStream_t st, const PrimBoxArgs &a);
 // order.  Returns the root link (node index, or a leaf code when n <= leafSize) and tree depth.
 struct BvhBuildResult { int root; uint32_t nodesUsed; uint32_t depth; };
 int rtb_build(cudaStream_t st, BuildScratch **scratch, const float4 *box_lo, const float4 *box_hi, uint32_t n,
-	uint32_t leafSize, BvhNode *nodes, uint32_t nodeBase, uint32_t leafBase, uint32_t *leafOrder /* out: leaf slot -> input index */,
+	uint32_t leafSize, BvhNode *nodes, BvhNode4 *nodes4, uint32_t nodeBase, uint32_t leafBase, uint32_t *leafOrder /* out: leaf slot -> input index */,
 	BvhBuildResult *res);
 void rtb_free_scratch(BuildScratch *s);
 

@@ -198,34 +198,45 @@ __device__ __forceinline__ void traverse(const SceneDev &S, const RayD &ray, con
 	bool slow = false;
 	const uint32_t idBefore = best.id;
 	int stack[RT_STACK];
+	float stackT[RT_STACK];   // entry distance of each stacked subtree (closest hit: culled again on pop)
 	int sp = 0;
 	int cur = root;
 	while (true)
 	{
 		while (cur >= 0)
 		{
-			const BvhNode *n = &S.nodes[cur];
-			const float4 a = ldg4(&n->a), b = ldg4(&n->b), c = ldg4(&n->c);
-			const int2 link = __ldg((const int2 *)&n->link);
-			if (S.tune & 1u)
-			{
-				// warm L1 with both children while the slab tests run (one of them is needed next)
-				if (link.x >= 0) asm volatile("prefetch.global.L1 [%0];" :: "l"(&S.nodes[link.x]));
-				if (link.y >= 0) asm volatile("prefetch.global.L1 [%0];" :: "l"(&S.nodes[link.y]));
-			}
+			const BvhNode4 *n = &S.nodes4[cur];
+			const float4 lox = ldg4(&n->lox), loy = ldg4(&n->loy), loz = ldg4(&n->loz);
+			const float4 hix = ldg4(&n->hix), hiy = ldg4(&n->hiy), hiz = ldg4(&n->hiz);
+			const int4 link = __ldg(&n->link);
 			if (STATS) ++st.nodes;
-			float t0, t1;
-			const bool h0 = slab_hit(a.x, a.y, a.z, a.w, b.x, b.y, ray.o, idir, best.t, t0);
-			const bool h1 = slab_hit(b.z, b.w, c.x, c.y, c.z, c.w, ray.o, idir, best.t, t1);
-			if (h0 && h1)
+			float t0, t1, t2, t3;
+			const bool h0 = slab_hit(lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, ray.o, idir, best.t, t0);
+			const bool h1 = slab_hit(lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, ray.o, idir, best.t, t1);
+			const bool h2 = slab_hit(lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, ray.o, idir, best.t, t2);
+			const bool h3 = slab_hit(lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, ray.o, idir, best.t, t3);
+			// nearest hit child first, the other hit children go on the stack
+			const float inf = __int_as_float(0x7f800000);
+			float bt = h0 ? t0 : inf;
+			int bi = 0;
+			if (h1 && t1 < bt) bt = t1, bi = 1;
+			if (h2 && t2 < bt) bt = t2, bi = 2;
+			if (h3 && t3 < bt) bt = t3, bi = 3;
+			if (!(h0 | h1 | h2 | h3))
 			{
-				const bool swap = t1 < t0;
-				stack[sp++] = swap ? link.x : link.y;
-				cur = swap ? link.y : link.x;
+				cur = RT_TRAV_DONE;
+				while (sp)
+				{
+					--sp;
+					if (ANY || stackT[sp] <= best.t) { cur = stack[sp]; break; }
+				}
+				continue;
 			}
-			else if (h0) cur = link.x;
-			else if (h1) cur = link.y;
-			else cur = sp ? stack[--sp] : RT_TRAV_DONE;
+			if (h0 && bi != 0) { stack[sp] = link.x; if (!ANY) stackT[sp] = t0; ++sp; }
+			if (h1 && bi != 1) { stack[sp] = link.y; if (!ANY) stackT[sp] = t1; ++sp; }
+			if (h2 && bi != 2) { stack[sp] = link.z; if (!ANY) stackT[sp] = t2; ++sp; }
+			if (h3 && bi != 3) { stack[sp] = link.w; if (!ANY) stackT[sp] = t3; ++sp; }
+			cur = bi == 0 ? link.x : bi == 1 ? link.y : bi == 2 ? link.z : link.w;
 		}
 		if (cur == RT_TRAV_DONE)
 			break;
@@ -243,7 +254,12 @@ __device__ __forceinline__ void traverse(const SceneDev &S, const RayD &ray, con
 			}
 		if (ANY && done)
 			return;
-		cur = sp ? stack[--sp] : RT_TRAV_DONE;
+		cur = RT_TRAV_DONE;
+		while (sp)
+		{
+			--sp;
+			if (ANY || stackT[sp] <= best.t) { cur = stack[sp]; break; }
+		}
 	}
 	if (FAST)
 	{

@@ -35,8 +35,8 @@ for nm in names:
             best = (c, wall)
     c, wall = best
     total = c.primary + c.shadow + c.reflect + c.refract
-    flops = cs.nodes_visited * 2 * 22 + cs.tri_tests * 47 + cs.prim_tests * 23
-    print(json.dumps({"cfg": nm, "leaf": os.environ.get("RT_B200_LEAF_SIZE", "4"), "scene_s": round(t_build, 1), "rays": total,
+    flops = cs.nodes_visited * 4 * 22 + cs.tri_tests * 47 + cs.prim_tests * 23
+    print(json.dumps({"cfg": nm, "leaf": os.environ.get("RT_B200_LEAF_SIZE", "2"), "scene_s": round(t_build, 1), "rays": total,
                       "rays_per_px": round(total / max(c.primary, 1), 2),
                       "render_ms": round(c.render_ms, 3), "start_to_finish_ms": round(wall * 1e3, 3), "mrays_s": round(total / c.render_ms / 1e3, 1),
                       "trace_ms": round(c.trace_ms, 3), "shadow_ms": round(c.shadow_ms, 3), "shade_ms": round(c.shade_ms, 3), "other_ms": round(c.other_ms, 3),
