@@ -223,6 +223,10 @@ int rt_output_device(rt_ctx *ctx, void **device_ptr, size_t *bytes);
  * then gathered over NCCL); NULL switches back to the library-owned framebuffer */
 int rt_set_output(rt_ctx *ctx, void *device_ptr, size_t bytes);
 
+/* page-locked host memory for RayTracer::output: rt_read_output into it runs at full PCIe speed */
+int rt_host_alloc(void **ptr, size_t bytes);
+int rt_host_free(void *ptr);
+
 /* diagnostics / parity taps */
 int rt_read_hit_ids(rt_ctx *ctx, rt_hit_id *ids /* width*height */);
 int rt_read_counters(rt_ctx *ctx, rt_counters *out);

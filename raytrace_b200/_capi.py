@@ -103,6 +103,8 @@ RT_SYMBOLS = {
     "rt_read_output": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "rt_output_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "rt_set_output": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "rt_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "rt_host_free": (C.c_int, [C.c_void_p]),
     "rt_read_hit_ids": (C.c_int, [C.c_void_p, C.POINTER(HitId)]),
     "rt_read_counters": (C.c_int, [C.c_void_p, C.POINTER(Counters)]),
 }

@@ -79,6 +79,9 @@ struct rt_ctx
 	std::vector<rt_model> models;
 	std::vector<rt_part> parts;
 	std::vector<rt_light> lights;
+	std::vector<rt_material> matCache;      // last uploaded tables: unchanged tables are not re-sent
+	std::vector<rt_texture> texCache;
+	std::vector<uint8_t> texelCache;
 	rt_camera camera;
 	rt_vec4 envLight;
 	bool anyRefract = false;
@@ -227,6 +230,7 @@ extern "C" int rt_upload_scene(rt_ctx *c, const rt_scene_desc *s)
 	// ---- cheap tables: always refreshed -------------------------------------------------------
 	c->camera = s->camera, c->envLight = s->env_light;
 	c->lights.assign(s->lights, s->lights + s->n_lights);
+	if (!same(c->matCache, s->materials, s->n_materials))
 	{
 		std::vector<float4> m(4 * (size_t)s->n_materials);
 		c->anyRefract = false;
@@ -238,11 +242,18 @@ extern "C" int rt_upload_scene(rt_ctx *c, const rt_scene_desc *s)
 			if (r.refract > 0.01f) c->anyRefract = true;
 		}
 		CU(c->materials.upload(m.data(), m.size(), st, ub));
+		CU(cudaStreamSynchronize(st));   // staging vector goes out of scope
+		c->matCache.assign(s->materials, s->materials + s->n_materials);
+	}
+	if (!same(c->texCache, s->textures, s->n_textures) || !same(c->texelCache, s->texels, s->texel_bytes))
+	{
 		std::vector<int4> t(s->n_textures);
 		for (uint32_t i = 0; i < s->n_textures; ++i) t[i] = make_int4(s->textures[i].w, s->textures[i].h, (int)s->textures[i].offset, 0);
 		CU(c->textures.upload(t.data(), t.size(), st, ub));
 		CU(c->texels.upload(s->texels, s->texel_bytes, st, ub));
-		CU(cudaStreamSynchronize(st));   // staging vectors go out of scope
+		CU(cudaStreamSynchronize(st));
+		c->texCache.assign(s->textures, s->textures + s->n_textures);
+		c->texelCache.assign(s->texels, s->texels + s->texel_bytes);
 	}
 
 	// ---- what changed? ------------------------------------------------------------------------
@@ -418,11 +429,14 @@ extern "C" int rt_upload_scene(rt_ctx *c, const rt_scene_desc *s)
 		S.n_items = (uint32_t)items.size(), S.n_prims = s->n_prims, S.n_tris = s->n_tris, S.n_parts = s->n_parts;
 	}
 	c->S.materials = c->materials.p, c->S.textures = c->textures.p, c->S.texels = c->texels.p;
-	CU(cudaEventRecord(c->evStop, st));
-	CU(cudaStreamSynchronize(st));
-	float ms = 0;
-	cudaEventElapsedTime(&ms, c->evA, c->evStop);
-	c->uploadMs = ms;
+	if (c->uploadBytes)
+	{
+		CU(cudaEventRecord(c->evStop, st));
+		CU(cudaStreamSynchronize(st));
+		float ms = 0;
+		cudaEventElapsedTime(&ms, c->evA, c->evStop);
+		c->uploadMs = ms;
+	}
 	c->hasScene = true;
 	c->frameValid = false;
 	return RT_OK;
@@ -636,6 +650,19 @@ extern "C" int rt_output_device(rt_ctx *c, void **ptr, size_t *bytes)
 	if (!c->fb) return fail(RT_E_STATE, "rt_output_device: nothing rendered yet");
 	*ptr = c->fb;
 	if (bytes) *bytes = (size_t)c->outW * c->outH * 3;
+	return RT_OK;
+}
+
+extern "C" int rt_host_alloc(void **ptr, size_t bytes)
+{
+	if (!ptr) return fail(RT_E_INVALID, "rt_host_alloc: ptr is NULL");
+	CU(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+	return RT_OK;
+}
+
+extern "C" int rt_host_free(void *ptr)
+{
+	if (ptr) CU(cudaFreeHost(ptr));
 	return RT_OK;
 }
 

@@ -13,11 +13,28 @@ static void fail(const char *what, int code)
 	throw std::runtime_error(msg);
 }
 
+// `output` is page-locked when a CUDA device is present (the D2H copy of a frame then runs at PCIe
+// speed); on a box without a GPU it is plain memory and start() will fail loudly anyway.
+static uint8_t *alloc_output(size_t bytes, bool &pinned)
+{
+	void *p = nullptr;
+	pinned = rt_host_alloc(&p, bytes) == RT_OK && p != nullptr;
+	if (!pinned) p = new uint8_t[bytes];
+	memset(p, 127, bytes);
+	return (uint8_t *)p;
+}
+
+static void free_output(uint8_t *p, bool pinned)
+{
+	if (pinned) rt_host_free(p);
+	else delete[] p;
+}
+
 RayTracer::RayTracer(Scene &scene) : scene(&scene)
 {
 	outputBytes = (size_t)2048 * 2048 * 3;   // the reference's fixed framebuffer, RayTracer.cpp:603
-	output = new uint8_t[outputBytes];
-	memset(output, 127, outputBytes);
+	output = new uint8_t[outputBytes];       // plain memory here (no CUDA call during static init);
+	memset(output, 127, outputBytes);        // swapped for page-locked memory by the first start()
 }
 
 RayTracer::~RayTracer()
@@ -27,7 +44,7 @@ RayTracer::~RayTracer()
 	if (ctx)
 		rt_destroy(ctx);
 	delete flattener;
-	delete[] output;
+	if (output) free_output(output, outputPinned);
 }
 
 void RayTracer::ensureContext()
@@ -42,14 +59,13 @@ void RayTracer::ensureContext()
 
 void RayTracer::reserveOutput(size_t bytes)
 {
-	if (bytes <= outputBytes)
+	if (output && bytes <= outputBytes && (outputPinned || !ctx))
 		return;
 	if (monitor.joinable())
 		monitor.join();
-	delete[] output;
-	outputBytes = bytes;
-	output = new uint8_t[outputBytes];
-	memset(output, 127, outputBytes);
+	if (output) free_output(output, outputPinned);
+	if (bytes > outputBytes) outputBytes = bytes;
+	output = alloc_output(outputBytes, outputPinned);
 }
 
 void RayTracer::start(const uint8_t type, const int8_t)
@@ -59,8 +75,8 @@ void RayTracer::start(const uint8_t type, const int8_t)
 	isFinish = false;
 	width = scene->cam.width;
 	height = scene->cam.height;
-	reserveOutput((size_t)width * height * 3);
 	ensureContext();
+	reserveOutput((size_t)width * height * 3);
 	for (DrawObject *o : scene->Objects)
 		if (o->bShow)
 			o->RTPrepare();

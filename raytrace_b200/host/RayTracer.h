@@ -27,6 +27,7 @@ class RayTracer
 	SceneFlattener *flattener = nullptr;
 	std::thread monitor;
 	size_t outputBytes;
+	bool outputPinned = false;
 	void ensureContext();
 public:
 	GLuint texID = 0;
