@@ -41,7 +41,7 @@ extern "C" {
 #define RT_LIGHT_PARALLEL 1
 #define RT_LIGHT_POINT    2
 #define RT_LIGHT_SPOT     3
-/* render types == MY_MODEL_* (RayTracer.h:5-13), the `type` argument of RayTracer::start */
+/* render types == MY_MODEL_* (RayTracer.h:5-13), the `type` argument of RayTracer::start; all nine run on the device */
 #define RT_TYPE_CHECK     0x01
 #define RT_TYPE_DEPTH     0x02
 #define RT_TYPE_NORMAL    0x03

@@ -524,6 +524,90 @@ struct Tracer
 		return hr;
 	}
 
+	// The staged debug shaders RTdepth :81, RTnorm :94, RTtex :109, RTmtl :127, RTshd :222
+	// (RayTracer.cpp).  They run the object loop WITHOUT resetting hr.obj, which cannot change the
+	// result for a primary ray (every object is visited once), and shade one level only.
+	V4 debug(uint32_t type, float zNear, float zFar, const RayO &baseray)
+	{
+		int64_t newobj;
+		const Hit hr = closest(baseray, Hit(), newobj);
+		if (type == RT_TYPE_DEPTH)
+		{
+			// Color::set, 3DElement.cpp:451-462
+			if (hr.distance <= zNear) return mk(1.0f, 0.0f, 0.0f);
+			if (hr.distance >= zFar) return mk(0.0f, 0.0f, 0.0f);
+			const float after = std::log(hr.distance), mx = std::log(zFar);
+			const float g = (mx - after) / mx;
+			return mk(g, g, g);
+		}
+		if (hr.distance > zFar) return mk(0.0f, 0.0f, 0.0f);
+		if (hr.distance < zNear) return mk(1.0f, 1.0f, 1.0f);
+		if (type == RT_TYPE_NORMAL)   // Color(const Normal&), 3DElement.cpp:423-428
+			return mk((float)(0.5 * (hr.normal.x + 1)), (float)(0.5 * (hr.normal.y + 1)), (float)(0.5 * (hr.normal.z + 1)));
+		if (type == RT_TYPE_TEXTURE)
+			return hr.tex >= 0 ? texel(hr.tex, hr.tu, hr.tv) : mk(0.588f, 0.588f, 0.588f);
+		const rt_material &mtl = s.materials[hr.mtl];
+		const V4 vc = texel(hr.tex, hr.tu, hr.tv);
+		V4 mix_vd = mk(0, 0, 0), mix_va = mk(0, 0, 0), mix_vsc = mk(0, 0, 0);
+		for (uint32_t li = 0; li < s.n_lights; ++li)
+		{
+			const rt_light &lit = s.lights[li];
+			if (!lit.enabled)
+				continue;
+			float light_lum, dis = 1e10;
+			V4 p2l;
+			const bool point = type == RT_TYPE_MATERIAL ? lit.position.w > 1e-6 : lit.type == RT_LIGHT_POINT;
+			if (point)
+			{
+				const V4 p2l_v = sub(from(lit.position), hr.position);
+				dis = dot(p2l_v, p2l_v);
+				float step;
+				if (type == RT_TYPE_MATERIAL)   // RTmtl sums in a different order, RayTracer.cpp:153-155
+					step = lit.attenuation.x + lit.attenuation.y * std::sqrt(dis) + lit.attenuation.z * dis;
+				else
+				{
+					step = lit.attenuation.x + lit.attenuation.z * dis;
+					dis = std::sqrt(dis);
+					step += lit.attenuation.y * dis;
+				}
+				light_lum = 1 / step;
+				p2l = normalize(p2l_v);
+			}
+			else
+			{
+				light_lum = 1.0f;
+				p2l = normalize(from(lit.position));
+			}
+			const V4 light_a = mul(from(lit.ambient), light_lum), light_d = mul(from(lit.diffuse), light_lum), light_s = mul(from(lit.specular), light_lum);
+			mix_va = add(mix_va, mixmul(from(mtl.ambient), light_a));
+			if (type == RT_TYPE_SHADOW)
+			{
+				RayO shadowray;
+				shadowray.origin = hr.position, shadowray.direction = p2l, shadowray.type = 0;
+				count(shadowray);
+				Hit shr(dis);
+				shr.obj = newobj;
+				bool blocked = false;
+				for (const Item &it : P.items)
+				{
+					shr = intersect(it, shadowray, shr, dis);
+					if (shr.distance < dis) { blocked = true; break; }
+				}
+				if (blocked)
+					continue;
+			}
+			float n_n = dot(hr.normal, p2l);
+			if (n_n > 0)
+				mix_vd = add(mix_vd, mul(mixmul(from(mtl.diffuse), light_d), n_n));
+			const V4 h = normalize(sub(p2l, baseray.direction));
+			n_n = dot(hr.normal, h);
+			if (n_n > 0)
+				mix_vsc = add(mix_vsc, mul(mixmul(from(mtl.specular), light_s), std::pow(n_n, mtl.shiness)));
+		}
+		mix_va = add(mix_va, mixmul(from(mtl.ambient), from(s.env_light)));   // environment term LAST here
+		return add(mixmul(vc, add(mix_vd, mix_va)), mix_vsc);
+	}
+
 	// RTfrac (refraction = true) / RTflec (false); returns rgb + alpha = hit distance
 	V4 shade(float zNear, float zFar, const RayO &baseray, uint32_t level, float bwc, const Hit &basehr, bool refraction)
 	{
@@ -663,7 +747,7 @@ int rto_render(const rt_scene_desc *scene, const rt_render_params *params, uint8
 	if (!scene || !params || !rgb)
 		return RT_E_INVALID;
 	const uint32_t type = params->type;
-	if (type != RT_TYPE_RAYTRACE && type != RT_TYPE_REFRACT && type != RT_TYPE_REFLECT)
+	if (type != RT_TYPE_RAYTRACE && (type < RT_TYPE_CHECK || type > RT_TYPE_REFRACT))
 		return RT_E_INVALID;
 	Prepared P;
 	prepare(*scene, P);
@@ -694,10 +778,20 @@ int rto_render(const rt_scene_desc *scene, const rt_render_params *params, uint8
 					RayO baseray;
 					baseray.origin = cpos, baseray.direction = normalize(dir), baseray.type = 1;
 					Hit base;
-					const V4 c = tr.shade(zNear, zFar, baseray, 0, 1.0f, base, type != RT_TYPE_REFLECT);
+					V4 c;
+					if (type == RT_TYPE_CHECK)
+					{
+						// RTcheck, RayTracer.cpp:48-79: 64x64 checkerboard, no rays
+						const float v = ((y / 64) & 1) == ((x / 64) & 1) ? 1.0f : 0.0f;
+						c = mk(v, v, v);
+					}
+					else if (type < RT_TYPE_REFLECT)
+						c = tr.debug(type, zNear, zFar, baseray);
+					else
+						c = tr.shade(zNear, zFar, baseray, 0, 1.0f, base, type != RT_TYPE_REFLECT);
 					uint8_t *o = rgb + ((size_t)y * width + x) * 3;
 					o[0] = put1(c.x), o[1] = put1(c.y), o[2] = put1(c.z);
-					if (ids)
+					if (ids && type != RT_TYPE_CHECK)
 					{
 						// primary closest hit again, without counting it
 						Tracer probe(P, 0);

@@ -467,9 +467,11 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 {
 	if (!c || !p) return fail(RT_E_INVALID, "rt_render_async: NULL argument");
 	if (!c->hasScene) return fail(RT_E_STATE, "rt_render_async: no scene uploaded");
-	if (p->type != RT_TYPE_RAYTRACE && p->type != RT_TYPE_REFRACT && p->type != RT_TYPE_REFLECT)
-		return fail(RT_E_INVALID, "rt_render_async: render type 0x%x is not implemented on the device path yet", p->type);
-	if (p->max_level >= RT_MAX_LEVELS) return fail(RT_E_LIMIT, "rt_render_async: max_level %u (limit %d)", p->max_level, RT_MAX_LEVELS - 1);
+	if (p->type != RT_TYPE_RAYTRACE && (p->type < RT_TYPE_CHECK || p->type > RT_TYPE_REFRACT))
+		return fail(RT_E_INVALID, "rt_render_async: unknown render type 0x%x (RayTracer.h:5-13)", p->type);
+	const bool debugStage = p->type >= RT_TYPE_CHECK && p->type <= RT_TYPE_SHADOW;
+	const uint32_t maxLevel = debugStage ? 0u : p->max_level;   // the staged shaders shade one level only
+	if (maxLevel >= RT_MAX_LEVELS) return fail(RT_E_LIMIT, "rt_render_async: max_level %u (limit %d)", maxLevel, RT_MAX_LEVELS - 1);
 	CU(cudaSetDevice(c->device));
 	// the previous frame must have drained completely (including the read-back of its WaveState)
 	// before the pinned staging buffers are rewritten
@@ -488,7 +490,7 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 	F.dp = tan(cam.fovy * 3.1415926535897932384 / 360) / (H / 2);
 	F.zNear = cam.zNear, F.zFar = (float)(sqrt(2) * cam.zFar);
 	F.width = W, F.height = H, F.blk_w = W / 64, F.blk_h = H / 64, F.half_w = W / 2, F.half_h = H / 2;
-	F.max_level = p->max_level, F.type = p->type, F.rank = rank, F.world = world;
+	F.max_level = maxLevel, F.type = p->type, F.rank = rank, F.world = world;
 	uint32_t bands = 0;
 	for (uint32_t t = 0; t < (uint32_t)F.blk_h; ++t) if (t % world == rank) ++bands;
 	F.n_rows = bands * 64;
@@ -522,13 +524,13 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 	CU(cudaMemsetAsync(fb, 127, (size_t)W * H * 3, st));
 
 	const bool refr = c->anyRefract && p->type != RT_TYPE_REFLECT;
-	for (uint32_t l = 0; l <= p->max_level; ++l)
+	for (uint32_t l = 0; l <= maxLevel; ++l)
 	{
 		const uint32_t cap = l == 0 || !refr ? nPix : (uint32_t)std::min<double>((double)nPix * c->levelFactor, 4.0e9);
 		int rc = ensure_level(c, l, cap ? cap : 1, F.n_lights);
 		if (rc != RT_OK) return rc;
 	}
-	{ int rc = ensure_level(c, p->max_level + 1, 1, 1); if (rc != RT_OK) return rc; }
+	{ int rc = ensure_level(c, maxLevel + 1, 1, 1); if (rc != RT_OK) return rc; }
 
 	WaveState &Wv = *c->hWaveInit;
 	memset(&Wv, 0, sizeof Wv);
@@ -546,10 +548,11 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 		// wave l = closest hit of level l (+ spawn of level l+1) fused with the shadow rays of level l-1
 		if (c->stageTiming) CU(cudaEventRecord(c->evStage[0], st));
 		LevelSet LS;
-		for (uint32_t l = 0; l <= p->max_level + 1; ++l) LS.l[l] = level_buf(c->levels[l]);
-		for (uint32_t l = 0; l <= p->max_level + 1; ++l)
+		for (uint32_t l = 0; l <= maxLevel + 1; ++l) LS.l[l] = level_buf(c->levels[l]);
+		for (uint32_t l = 0; l <= maxLevel + 1 && p->type != RT_TYPE_CHECK; ++l)
 		{
-			const bool traceOn = l <= p->max_level, shadowOn = l >= 1 && enabledLights > 0;
+			// staged shaders: only RTshd (type 6) shoots shadow rays
+			const bool traceOn = l <= maxLevel, shadowOn = l >= 1 && enabledLights > 0 && (!debugStage || p->type == RT_TYPE_SHADOW);
 			if (!traceOn && !shadowOn) continue;
 			const float zNear = l == 0 ? F.zNear : 0.0f;
 			uint32_t items = traceOn ? c->levels[l].capacity : 0;
@@ -558,9 +561,16 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 			++launches;
 		}
 		if (c->stageTiming) CU(cudaEventRecord(c->evStage[1], st));
-		rtk_shade(st, c->S, c->dFrame, LS, c->dWave, p->max_level + 1, c->levels[0].capacity, c->sms); ++launches;
+		if (debugStage)
+		{
+			rtk_debug(st, c->S, c->dFrame, LS.l[0], nPix, fb, c->sms); ++launches;
+		}
+		else
+		{
+			rtk_shade(st, c->S, c->dFrame, LS, c->dWave, maxLevel + 1, c->levels[0].capacity, c->sms); ++launches;
+		}
 		if (c->stageTiming) CU(cudaEventRecord(c->evStage[2], st));
-		for (int l = (int)p->max_level; l >= 0; --l)
+		for (int l = (int)maxLevel; l >= 0 && !debugStage; --l)
 		{
 			rtk_combine(st, c->S, c->dFrame, level_buf(c->levels[l]), level_buf(c->levels[l + 1]), c->dWave, (uint32_t)l, fb, c->levels[l].capacity, c->sms);
 			++launches;
@@ -570,7 +580,7 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 	CU(cudaEventRecord(c->evStop, st));
 	CU(cudaMemcpyAsync(c->hWave, c->dWave, sizeof(WaveState), cudaMemcpyDeviceToHost, st));
 	CU(cudaEventRecord(c->evB, st));
-	c->lastParams = *p, c->lastPixels = nPix, c->lastLaunches = launches, c->lastMaxLevel = p->max_level;
+	c->lastParams = *p, c->lastPixels = nPix, c->lastLaunches = launches, c->lastMaxLevel = maxLevel;
 	c->frameInFlight = true, c->frameValid = false;
 	return RT_OK;
 }
@@ -735,11 +745,12 @@ extern "C" int rt_read_counters(rt_ctx *c, rt_counters *out)
 	const WaveState &W = *c->hWave;
 	uint32_t enabled = 0;
 	for (const rt_light &l : c->lights) if (l.enabled) ++enabled;
-	out->primary = W.count[0];
+	out->primary = c->lastParams.type == RT_TYPE_CHECK ? 0 : W.count[0];
 	out->reflect = W.n_reflect, out->refract = W.n_refract;
 	unsigned long long hits = 0;
 	for (uint32_t l = 0; l <= c->lastMaxLevel; ++l) hits += W.n_hit[l];
-	out->shadow = hits * enabled;
+	const uint32_t ty = c->lastParams.type;
+	out->shadow = (ty >= RT_TYPE_CHECK && ty <= RT_TYPE_MATERIAL) ? 0 : hits * enabled;
 	out->nodes_visited = W.nodes_visited, out->tri_tests = W.tri_tests, out->prim_tests = W.prim_tests;
 	if (getenv("RT_B200_PRINT_HIST") && W.nodes_visited)
 	{

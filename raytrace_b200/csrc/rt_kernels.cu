@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(RT_BLOCK, 8) k_wave(SceneDev S, const FramePar
 				ray.o = f3(hp);
 				ray.mtlrfr = 1.0f;
 				ray.skip = Lprev.hit_id[i].y;
-				ray.type = F.type == RT_TYPE_REFLECT ? 0 : MY_RAY_SHADOWRAY_;
+				ray.type = (F.type == RT_TYPE_REFLECT || F.type == RT_TYPE_SHADOW) ? 0 : MY_RAY_SHADOWRAY_;
 				ray.isInside = 0;
 				Best best = { dis, RT_ID_NONE, RT_ID_NONE };
 				bool done = false;
@@ -433,6 +433,107 @@ __global__ void __launch_bounds__(128) k_shade(SceneDev S, const FrameParams *__
 		}
 		const F3 c_all = mixmul(vc, mix_vd + mix_va) + mix_vsc;
 		L.color[i] = make_float4(c_all.x, c_all.y, c_all.z, hp.w);
+	}
+}
+
+// ---- staged debug shaders (RayTracer::start types 1..6) -------------------------------------------
+// RTcheck :48, RTdepth :81, RTnorm :94, RTtex :109, RTmtl :127, RTshd :222 of RayTracer.cpp: one
+// closest-hit wave (plus one shadow wave for RTshd), then this kernel colours every pixel.
+__device__ __forceinline__ float log_ref(float a) { return (float)log((double)a); }
+
+__global__ void __launch_bounds__(128) k_debug(SceneDev S, const FrameParams *__restrict__ Fp, LevelBuf L, uint32_t n, uint8_t *__restrict__ out)
+{
+	const FrameParams &F = *Fp;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+	{
+		int x, y;
+		slot_to_pixel(F, i, x, y);
+		F3 c = f3(0, 0, 0);
+		if (F.type == RT_TYPE_CHECK)
+		{
+			const float v = ((y >> 6) & 1) == ((x >> 6) & 1) ? 1.0f : 0.0f;
+			c = f3(v, v, v);
+		}
+		else
+		{
+			const float t = L.hit_p[i].w;
+			if (F.type == RT_TYPE_DEPTH)
+			{
+				// Color::set, 3DElement.cpp:451-462
+				if (t <= F.zNear) c = f3(1.0f, 0.0f, 0.0f);
+				else if (t >= F.zFar) c = f3(0.0f, 0.0f, 0.0f);
+				else
+				{
+					const float after = log_ref(t), mx = log_ref(F.zFar);
+					const float g = (mx - after) / mx;
+					c = f3(g, g, g);
+				}
+			}
+			else if (t > F.zFar) c = f3(0.0f, 0.0f, 0.0f);
+			else if (t < F.zNear) c = f3(1.0f, 1.0f, 1.0f);
+			else
+			{
+				const float4 hn = L.hit_n[i], huv = L.hit_uv[i];
+				const F3 Nn = f3(hn), P = f3(L.hit_p[i]), rd = f3(L.ray_d[i]);
+				const int mtl = __float_as_int(hn.w), tex = __float_as_int(huv.z);
+				if (F.type == RT_TYPE_NORMAL)   // Color(const Normal&): 0.5 * (n + 1) with a double multiply
+					c = f3((float)(0.5 * (double)(Nn.x + 1)), (float)(0.5 * (double)(Nn.y + 1)), (float)(0.5 * (double)(Nn.z + 1)));
+				else if (F.type == RT_TYPE_TEXTURE)
+					c = tex >= 0 ? texel(S, tex, huv.x, huv.y) : f3(0.588f, 0.588f, 0.588f);
+				else
+				{
+					const bool mtlStage = F.type == RT_TYPE_MATERIAL;
+					const F3 mA = f3(ldg4(&S.materials[4 * mtl])), mD = f3(ldg4(&S.materials[4 * mtl + 1])), mS = f3(ldg4(&S.materials[4 * mtl + 2]));
+					const float shiness = ldg4(&S.materials[4 * mtl + 3]).x;
+					const F3 vc = texel(S, tex, huv.x, huv.y);
+					F3 mix_vd = f3(0, 0, 0), mix_va = f3(0, 0, 0), mix_vsc = f3(0, 0, 0);
+					for (uint32_t k = 0; k < F.n_lights; ++k)
+					{
+						const DevLight &lit = F.lights[k];
+						if (!lit.enabled)
+							continue;
+						F3 p2l;
+						float lum;
+						// RTmtl tells point lights by position.alpha and sums the attenuation in another order
+						if (mtlStage ? lit.position.w > RT_EPS6_BELOW : lit.type == RT_LIGHT_POINT)
+						{
+							const F3 v = f3(lit.position) - P;
+							float dis = dot(v, v), step;
+							if (mtlStage)
+								step = (lit.attenuation.x + lit.attenuation.y * sqrtf(dis)) + lit.attenuation.z * dis;
+							else
+							{
+								step = lit.attenuation.x + lit.attenuation.z * dis;
+								dis = sqrtf(dis);
+								step += lit.attenuation.y * dis;
+							}
+							lum = 1 / step;
+							p2l = normalize(v);
+						}
+						else
+						{
+							lum = 1.0f;
+							p2l = normalize(f3(lit.position));
+						}
+						const F3 la = f3(lit.ambient) * lum, ld = f3(lit.diffuse) * lum, ls = f3(lit.specular) * lum;
+						mix_va = mix_va + mixmul(mA, la);
+						if (!mtlStage && L.shadow[(size_t)k * L.capacity + i])
+							continue;
+						float n_n = dot(Nn, p2l);
+						if (n_n > 0)
+							mix_vd = mix_vd + mixmul(mD, ld) * n_n;
+						const F3 h2 = normalize(p2l - rd);
+						n_n = dot(Nn, h2);
+						if (n_n > 0)
+							mix_vsc = mix_vsc + mixmul(mS, ls) * pow_ref(n_n, shiness);
+					}
+					mix_va = mix_va + mixmul(mA, f3(F.env_light));   // environment ambient last in these stages
+					c = mixmul(vc, mix_vd + mix_va) + mix_vsc;
+				}
+			}
+		}
+		uint8_t *o = out + ((size_t)y * F.width + x) * 3;
+		o[0] = put8(c.x), o[1] = put8(c.y), o[2] = put8(c.z);
 	}
 }
 
@@ -513,6 +614,11 @@ void rtk_shade(cudaStream_t st, const SceneDev &S, const FrameParams *F, const L
 {
 	const dim3 g(grid_for(maxRays, 128, sms * 8), levels);
 	k_shade<<<g, 128, 0, st>>>(S, F, LS, ws);
+}
+
+void rtk_debug(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, uint32_t n, uint8_t *out, unsigned sms)
+{
+	k_debug<<<grid_for(n, 128, sms * 16), 128, 0, st>>>(S, F, L, n, out);
 }
 
 void rtk_combine(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const LevelBuf &N, const WaveState *ws,

@@ -43,6 +43,7 @@ void rtk_raygen(cudaStream_t st, const FrameParams *F, const LevelBuf &L, uint32
 void rtk_wave(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const LevelBuf &N, const LevelBuf &Lprev, WaveState *ws,
 	uint32_t level, bool traceOn, bool shadowOn, float zNear, uint32_t maxItems, unsigned sms, bool stats);
 void rtk_shade(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelSet &LS, const WaveState *ws, uint32_t levels, uint32_t maxRays, unsigned sms);
+void rtk_debug(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, uint32_t n, uint8_t *out, unsigned sms);
 void rtk_combine(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const LevelBuf &N, const WaveState *ws,
 	uint32_t level, uint8_t *out, uint32_t maxRays, unsigned sms);
 

@@ -267,6 +267,70 @@ template<class SceneT> inline void build_t_twomesh(SceneT &scene, const SceneArg
 	scene.MovePos(MY_MODEL_OBJECT, q, Vertex(-6.0f, 4.5f, -4.0f));
 }
 
+// ---- edge cases ------------------------------------------------------------------------------------
+// nothing to hit: every ray misses (black frame, 1e20 distances)
+template<class SceneT> inline void build_t_empty(SceneT &scene, const SceneArgs &)
+{
+	default_lights(scene);
+}
+
+// no lights at all: only the environment ambient term survives (RayTracer.cpp:472)
+template<class SceneT> inline void build_t_nolight(SceneT &scene, const SceneArgs &)
+{
+	scene.EnvLight = Vertex(0.6f, 0.5f, 0.4f, 1.0f);
+	scene.AddPlane();
+	const int s = scene.AddSphere(1.3f);
+	scene.ChgMtl(s, scene.MtlLiby[0]);
+}
+
+// 8 lights (the maximum, Scene.cpp:85) of all three kinds, one switched off, a hidden object, a
+// spot light (shaded as a parallel light by the reference, RayTracer.cpp:496-503), overlapping and
+// ground-piercing spheres, the camera moved and turned
+template<class SceneT> inline void build_t_lights(SceneT &scene, const SceneArgs &)
+{
+	scene.EnvLight = Vertex(0.05f, 0.05f, 0.05f, 1.0f);
+	for (int k = 0; k < 8; ++k)
+	{
+		const uint8_t type = k % 3 == 0 ? MY_LIGHT_PARALLEL : (k % 3 == 1 ? MY_LIGHT_POINT : MY_LIGHT_SPOT);
+		scene.AddLight(type, Vertex(0.1f + 0.02f * k, 0.5f, 0.3f), type == MY_LIGHT_PARALLEL ? Vertex(1, 0, 0, 0.25f) : Vertex(0.2f, 0.05f, 0.6f, 40));
+		scene.MovePos(MY_MODEL_LIGHT, k, Vertex(-20.0f + 9.0f * k, 33.0f * k, -2.0f * k));
+	}
+	scene.AddLight(MY_LIGHT_POINT, Vertex(1, 1, 1));           // ninth light: rejected (returns 0xff)
+	scene.Switch(MY_MODEL_LIGHT, 3, false);
+	scene.AddPlane();
+	int s = scene.AddSphere(1.0f);
+	scene.MovePos(MY_MODEL_OBJECT, s, Vertex(-1.0f, -0.6f, 2));   // pierces the ground plane
+	s = scene.AddSphere(1.0f);
+	scene.ChgMtl(s, scene.MtlLiby[4]);
+	scene.MovePos(MY_MODEL_OBJECT, s, Vertex(0.2f, 0.1f, 2.5f));  // glass, overlaps the first sphere
+	s = scene.AddSphere(0.8f);
+	scene.MovePos(MY_MODEL_OBJECT, s, Vertex(2.5f, 0, 4));
+	scene.Switch(MY_MODEL_OBJECT, s, false);                      // hidden: must not be uploaded
+	const int b = scene.AddCube(1.5f);
+	scene.ChgMtl(b, scene.MtlLiby[2]);
+	scene.MovePos(MY_MODEL_OBJECT, b, Vertex(3.0f, 0, 1));
+	scene.cam.move(1.5f, 0.5f, 3.0f);
+	scene.cam.yaw(12.0f);
+	scene.cam.pitch(-8.0f);
+}
+
+// camera inside a glass sphere, looking out through it at a mesh
+template<class SceneT> inline void build_t_inside(SceneT &scene, const SceneArgs &a)
+{
+	SceneArgs b = a;
+	if (b.n <= 0) b.n = 24;
+	if (b.parts <= 0) b.parts = 2;
+	default_lights(scene);
+	scene.Lights[1].position = Vertex(4, 9, 14, 1.0f);
+	scene.AddPlane();
+	const int s = scene.AddSphere(2.0f);
+	scene.ChgMtl(s, scene.MtlLiby[4]);
+	scene.Objects[s]->position = Vertex(0, 4, 15);                // around the default camera
+	const int m = add_heightfield(scene, b, b.n, b.parts);
+	scene.ChgMtl(m, scene.MtlLiby[3]);
+	scene.MovePos(MY_MODEL_OBJECT, m, Vertex(0, 0, 4));
+}
+
 template<class SceneT> inline bool build(SceneT &scene, const SceneArgs &a)
 {
 	if (a.name == "c1") build_c1(scene, a);
@@ -277,6 +341,10 @@ template<class SceneT> inline bool build(SceneT &scene, const SceneArgs &a)
 	else if (a.name == "t_ballplane") build_t_ballplane(scene, a);
 	else if (a.name == "t_mesh") build_t_mesh(scene, a);
 	else if (a.name == "t_twomesh") build_t_twomesh(scene, a);
+	else if (a.name == "t_empty") build_t_empty(scene, a);
+	else if (a.name == "t_nolight") build_t_nolight(scene, a);
+	else if (a.name == "t_lights") build_t_lights(scene, a);
+	else if (a.name == "t_inside") build_t_inside(scene, a);
 	else return false;
 	return true;
 }

@@ -37,6 +37,19 @@ CASES = [
     ("t_twomesh", 640, 384, 3, 0, 0, 0x80),
     ("c3", 640, 384, 5, 96, 6, 0x80),
     ("c4", 640, 384, 6, 96, 6, 0x80),
+    ("t_empty", 256, 128, 2, 0, 0, 0x80),
+    ("t_nolight", 320, 192, 2, 0, 0, 0x80),
+    ("t_lights", 640, 384, 4, 0, 0, 0x80),
+    ("t_lights", 320, 192, 3, 0, 0, 0x07),
+    ("t_inside", 384, 256, 6, 0, 0, 0x80),
+    # the staged debug shaders (RayTracer.cpp:48-325), MY_MODEL_CHECK .. MY_MODEL_SHADOWTEST
+    ("t_mixed", 320, 192, 1, 0, 0, 0x01),
+    ("t_mesh", 320, 192, 1, 0, 0, 0x02),
+    ("t_mesh", 320, 192, 1, 0, 0, 0x03),
+    ("t_mesh", 320, 192, 1, 0, 0, 0x04),
+    ("t_lights", 320, 192, 1, 0, 0, 0x05),
+    ("t_lights", 320, 192, 1, 0, 0, 0x06),
+    ("t_mesh", 320, 192, 1, 0, 0, 0x06),
 ]
 SAVE_FRAMES = {("c1", 320, 200, 1), ("t_mixed", 320, 192, 8)}
 
