@@ -113,6 +113,8 @@ struct rt_ctx
 	double uploadMs = 0, buildMs = 0, renderMs = 0;
 	uint64_t uploadBytes = 0, frameH2D = 0, frameD2H = 0;
 	float levelFactor = 2.0f;
+	bool frameSched = true;         // one persistent launch per frame (k_frame); RT_B200_SCHED=waves selects per-level waves
+	uint32_t frameEpoch = 0;
 };
 
 extern "C" const char *rt_last_error(void) { return g_err.c_str(); }
@@ -148,6 +150,7 @@ extern "C" int rt_create(int device, rt_ctx **out)
 	c->S.tune = 0;
 	if (const char *v = getenv("RT_B200_LEAF_SIZE")) c->leafSize = (uint32_t)atoi(v);
 	if (const char *v = getenv("RT_B200_LEVEL_FACTOR")) c->levelFactor = (float)atof(v);
+	if (const char *v = getenv("RT_B200_SCHED")) c->frameSched = strcmp(v, "waves") != 0;
 	if (const char *v = getenv("RT_B200_TUNE")) c->S.tune = (uint32_t)atoi(v);
 	*out = c;
 	return RT_OK;
@@ -449,6 +452,8 @@ static int ensure_level(rt_ctx *c, uint32_t l, uint32_t cap, uint32_t lights)
 	L.capacity = 0;
 	CU(L.ray_o.reserve(cap)); CU(L.ray_d.reserve(cap)); CU(L.ray_meta.reserve(cap)); CU(L.hit_p.reserve(cap));
 	CU(L.hit_id.reserve(cap)); CU(L.color.reserve(cap)); CU(L.aux.reserve(cap)); CU(L.shadow.reserve((size_t)cap * (lights ? lights : 1))); CU(L.hit_list.reserve(cap)); CU(L.hit_n.reserve(cap)); CU(L.hit_uv.reserve(cap));
+	// k_frame recognises a written slot by the epoch in ray_meta: fresh memory must not look written
+	CU(cudaMemsetAsync(L.ray_meta.p, 0, sizeof(uint2) * L.ray_meta.cap, c->stream));
 	L.capacity = cap, L.lights = lights;
 	return RT_OK;
 }
@@ -532,9 +537,18 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 	}
 	{ int rc = ensure_level(c, maxLevel + 1, 1, 1); if (rc != RT_OK) return rc; }
 
+	if (++c->frameEpoch > 65535u)
+	{
+		// epoch wrap: forget every stamp so a slot written 65535 frames ago cannot look fresh
+		for (uint32_t l = 0; l <= maxLevel + 1; ++l)
+			if (c->levels[l].ray_meta.p) CU(cudaMemsetAsync(c->levels[l].ray_meta.p, 0, sizeof(uint2) * c->levels[l].ray_meta.cap, st));
+		c->frameEpoch = 1;
+	}
+	F.epoch = c->frameEpoch;
 	WaveState &Wv = *c->hWaveInit;
 	memset(&Wv, 0, sizeof Wv);
 	Wv.count[0] = nPix;
+	Wv.outstanding = (int)nPix;
 	CU(cudaMemcpyAsync(c->dFrame, c->hFrame, sizeof(FrameParams), cudaMemcpyHostToDevice, st));
 	CU(cudaMemcpyAsync(c->dWave, c->hWaveInit, sizeof(WaveState), cudaMemcpyHostToDevice, st));
 	c->frameH2D = sizeof(FrameParams) + sizeof(WaveState), c->frameD2H = sizeof(WaveState);
@@ -549,7 +563,11 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 		if (c->stageTiming) CU(cudaEventRecord(c->evStage[0], st));
 		LevelSet LS;
 		for (uint32_t l = 0; l <= maxLevel + 1; ++l) LS.l[l] = level_buf(c->levels[l]);
-		for (uint32_t l = 0; l <= maxLevel + 1 && p->type != RT_TYPE_CHECK; ++l)
+		if (c->frameSched && p->type != RT_TYPE_CHECK)
+		{
+			rtk_frame(st, c->S, c->dFrame, LS, c->dWave, nPix, c->sms, stats); ++launches;
+		}
+		for (uint32_t l = 0; l <= maxLevel + 1 && p->type != RT_TYPE_CHECK && !c->frameSched; ++l)
 		{
 			// staged shaders: only RTshd (type 6) shoots shadow rays
 			const bool traceOn = l <= maxLevel, shadowOn = l >= 1 && enabledLights > 0 && (!debugStage || p->type == RT_TYPE_SHADOW);
@@ -603,6 +621,8 @@ static int finish_frame(rt_ctx *c)
 		c->traceMs = a, c->shadeMs = d;
 		c->otherMs = c->renderMs - c->traceMs - c->shadeMs;
 	}
+	if (c->hWave->overflow == 2u)
+		return fail(RT_E_STATE, "the frame scheduler stopped making progress (k_frame gave up waiting); frame is incomplete");
 	if (c->hWave->overflow)
 		return fail(RT_E_LIMIT, "a ray level overflowed its queue (capacity factor %.2f); raise RT_B200_LEVEL_FACTOR", c->levelFactor);
 	c->frameValid = true;

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) k_raygen(const FrameParams *__restrict__ 
 		const F3 d = normalize(dir);
 		L.ray_o[i] = make_float4(F.cam_pos.x, F.cam_pos.y, F.cam_pos.z, 1.0f);
 		L.ray_d[i] = make_float4(d.x, d.y, d.z, 1.0f);
-		L.ray_meta[i] = make_uint2(RT_ID_NONE, (uint32_t)MY_RAY_BASERAY_);
+		L.ray_meta[i] = make_uint2(RT_ID_NONE, (uint32_t)MY_RAY_BASERAY_ | (F.epoch << 16));
 	}
 }
 
@@ -390,6 +390,238 @@ __global__ void __launch_bounds__(RT_BLOCK, 8) k_wave(SceneDev S, const FramePar
 	flush_stats<STATS>(ws, st);
 }
 
+// ---- whole-frame persistent scheduler ---------------------------------------------------------------
+//
+// One launch traces every ray of the frame.  Resident warps repeatedly take a batch of rays from
+// the shallowest level that has unconsumed rays, trace them (closest hit), spawn the reflect /
+// refract children into the next level's queue, and then trace the shadow rays of their own hits
+// right away (one round per enabled light, lane i keeps working on the surface it just found).
+// Level l+1 rays become visible to other warps the moment they are written, so the long rays of a
+// level no longer hold back the next level: the critical path of a frame is one pixel's ray chain,
+// not (levels x slowest ray).  That is what the per-level waves could not give, and what strong
+// scaling of a 1080p frame over several GPUs needs.
+//
+// Publication protocol.  A producer reserves slots with one atomicAdd on count[l+1] (and adds them
+// to `outstanding` at the same time), writes ray_o/ray_d, fences, and only then writes ray_meta,
+// whose upper 16 bits carry this frame's epoch.  A consumer that was handed slot i spins until that
+// epoch shows up (the producer is a running warp that is not waiting for anyone), fences, and reads
+// the slot through L2 (__ldcg: another SM wrote it).  `outstanding` never under-counts, so
+// "outstanding == 0" means the frame is complete and every warp may leave.
+__device__ __forceinline__ uint32_t vload(const uint32_t *p) { return *(const volatile uint32_t *)p; }
+
+template<bool STATS>
+__global__ void __launch_bounds__(RT_BLOCK, 8) k_frame(SceneDev S, const FrameParams *__restrict__ Fp, LevelSet LS, WaveState *ws)
+{
+	const FrameParams &F = *Fp;
+	const uint32_t lane = threadIdx.x & 31u;
+	const bool refraction = F.type != RT_TYPE_REFLECT;
+	const bool wantShadows = F.type != RT_TYPE_DEPTH && F.type != RT_TYPE_NORMAL && F.type != RT_TYPE_TEXTURE && F.type != RT_TYPE_MATERIAL;
+	TravStats st = { 0, 0, 0 };
+	uint32_t idleSpins = 0;
+	// Slots this warp has claimed but not traced yet.  A claim (one atomicAdd on head_trace[l]) may run
+	// past the rays published so far; such a slot stays owned by its lane, which polls it without
+	// blocking the lanes whose rays are ready, until it is published or the frame is over.
+	uint32_t pLevel = 0, pSlot = 0xFFFFFFFFu;
+	while (true)
+	{
+		if (__ballot_sync(0xffffffffu, pSlot != 0xFFFFFFFFu) == 0u)
+		{
+			// ---- claim: shallowest level with unclaimed rays (leader decides, broadcasts) ---------------
+			uint32_t level = 0xFFFFFFFFu, base = 0, nb = 0;
+			if (lane == 0)
+				for (uint32_t l = 0; l <= F.max_level; ++l)
+				{
+					uint32_t cnt = vload(&ws->count[l]);
+					cnt = cnt < LS.l[l].capacity ? cnt : LS.l[l].capacity;
+					const uint32_t h = vload(&ws->head_trace[l]);
+					if (h >= cnt)
+						continue;
+					uint32_t want = (cnt - h) >> 6;     // short queue: few rays per warp, so more warps share it
+					want = want < 2u ? 2u : (want > 32u ? 32u : want);
+					const uint32_t got = atomicAdd(&ws->head_trace[l], want);
+					if (got < LS.l[l].capacity)
+					{
+						level = l, base = got, nb = want;
+						break;
+					}
+				}
+			level = __shfl_sync(0xffffffffu, level, 0), base = __shfl_sync(0xffffffffu, base, 0), nb = __shfl_sync(0xffffffffu, nb, 0);
+			if (level != 0xFFFFFFFFu)
+			{
+				pLevel = level;
+				if (lane < nb && base + lane < LS.l[level].capacity) pSlot = base + lane;
+			}
+		}
+		const uint32_t level = pLevel;
+		const LevelBuf &L = LS.l[level];
+		const LevelBuf &N = LS.l[level + 1];
+		// which of the owned slots are published?
+		uint2 m = make_uint2(0, 0);
+		bool ready = false;
+		if (pSlot != 0xFFFFFFFFu)
+		{
+			m = __ldcg(&L.ray_meta[pSlot]);
+			ready = (m.y >> 16) == F.epoch;
+		}
+		const uint32_t readyMask = __ballot_sync(0xffffffffu, ready);
+		if (readyMask == 0u)
+		{
+			int out = 0;
+			if (lane == 0) out = *(volatile int *)&ws->outstanding;
+			out = __shfl_sync(0xffffffffu, out, 0);
+			if (out <= 0 || vload(&ws->overflow) == 2u)
+				break;   // nothing in flight any more: unpublished slots will never be written
+			if (++idleSpins > (1u << 22))
+			{
+				if (lane == 0) ws->overflow = 2u;   // scheduler stuck: fail loudly instead of hanging the GPU
+				break;
+			}
+			__nanosleep(idleSpins < 64u ? 100 : 1000);
+			continue;
+		}
+		idleSpins = 0;
+		const uint32_t nb = __popc(readyMask);
+		const float zNear = level == 0 ? F.zNear : 0.0f;
+		const bool deeper = level + 1 <= F.max_level;
+		const uint32_t i = ready ? pSlot : 0xFFFFFFFFu;
+		if (ready) pSlot = 0xFFFFFFFFu;
+
+		bool surface = false, wantFlec = false, wantFrac = false;
+		float4 co = make_float4(0, 0, 0, 0), cdFlec = co, cdFrac = co;
+		uint2 metaFlec = make_uint2(0, 0), metaFrac = metaFlec;
+		float fracRfr = 1.0f;
+		int4 aux = make_int4(-1, -1, -1, 0);
+		F3 P = f3(0, 0, 0);
+		uint32_t newobj = RT_ID_NONE;
+		if (i != 0xFFFFFFFFu)
+		{
+			__threadfence();   // the stamp was seen: order the payload reads after it
+			const float4 o4 = __ldcg(&L.ray_o[i]), d4 = __ldcg(&L.ray_d[i]);
+			RayD ray;
+			ray.o = f3(o4), ray.d = f3(d4), ray.mtlrfr = o4.w;
+			ray.skip = m.x, ray.type = (uint8_t)(m.y & 0xFF), ray.isInside = (uint8_t)((m.y >> 8) & 0xFF);
+			Best best = { 1e20f, RT_ID_NONE, ray.skip };
+			bool done = false;
+			const uint32_t nodes0 = st.nodes;
+			trace_scene<false, STATS>(S, ray, best, done, st);
+			if (STATS) atomicAdd(&ws->node_hist[min(11, 31 - __clz((int)(st.nodes - nodes0 + 1u)))], 1u);
+			P = ray.o + ray.d * best.t;
+			newobj = best.newobj;
+			L.hit_p[i] = make_float4(P.x, P.y, P.z, best.t);
+			L.hit_id[i] = make_uint2(best.id, best.newobj);
+			surface = !(best.t > F.zFar || best.t < zNear);
+			if (!surface)
+				L.color[i] = make_float4(0.0f, 0.0f, 0.0f, 1e20f);
+			else
+			{
+				const Surface sf = surface_attributes(S, ray, P, best.id);
+				L.hit_n[i] = make_float4(sf.N.x, sf.N.y, sf.N.z, __int_as_float(sf.mtl));
+				L.hit_uv[i] = make_float4(sf.tu, sf.tv, __int_as_float(sf.tex), 0.0f);
+				const float4 mP = ldg4(&S.materials[4 * sf.mtl + 3]);   // shiness, reflect, refract, rfr
+				const float bwc = d4.w;
+				aux.z = sf.mtl;
+				co = make_float4(P.x, P.y, P.z, 1.0f);
+				if (mP.y > 0.01f)
+				{
+					aux.w |= 1;
+					const float bw = bwc * mP.y;
+					if (deeper && !(bw < 1e-5f))
+					{
+						const float n_n = 2 * dot(ray.d, sf.N);
+						const F3 r = normalize(ray.d - sf.N * n_n);
+						wantFlec = true;
+						cdFlec = make_float4(r.x, r.y, r.z, bw);
+						metaFlec = make_uint2(best.newobj, (refraction ? (uint32_t)MY_RAY_REFLECTRAY_ : 0u) | (F.epoch << 16));
+					}
+				}
+				if (refraction && mP.z > 0.01f)
+				{
+					aux.w |= 2;
+					if (sf.isInside) aux.w |= 4;
+					const float nn = ray.mtlrfr / sf.rfr;
+					const float cosIn = -dot(ray.d, sf.N);
+					const float cosOut2 = 1.0f - (nn * nn) * (1.0f - cosIn * cosIn);
+					const float bw = bwc * mP.z;
+					if (!(cosOut2 < 0.0f) && deeper && !(bw < 1e-5f))
+					{
+						const F3 l2 = ray.d * nn, l1 = sf.N * (nn * cosIn - sqrtf(cosOut2));
+						const F3 r = normalize(l1 + l2);
+						wantFrac = true;
+						cdFrac = make_float4(r.x, r.y, r.z, bw);
+						metaFrac = make_uint2(best.newobj, (uint32_t)MY_RAY_REFRACTRAY_ | ((uint32_t)sf.isInside << 8) | (F.epoch << 16));
+						fracRfr = sf.rfr;
+					}
+				}
+			}
+		}
+
+		// ---- children: count them as outstanding BEFORE they can be consumed, then publish -------------
+		const uint32_t mf = __ballot_sync(0xffffffffu, wantFlec), mr = __ballot_sync(0xffffffffu, wantFrac);
+		const int nChildren = __popc(mf) + __popc(mr);
+		if (nChildren)
+		{
+			if (lane == 0) atomicAdd(&ws->outstanding, nChildren);
+			__syncwarp();
+			const uint32_t sFlec = warp_append(&ws->count[level + 1], wantFlec);
+			const uint32_t sFrac = warp_append(&ws->count[level + 1], wantFrac);
+			int dropped = 0;
+			if (wantFlec)
+			{
+				if (sFlec < N.capacity) { N.ray_o[sFlec] = co, N.ray_d[sFlec] = cdFlec; aux.x = (int)sFlec; }
+				else { ws->overflow = 1; ++dropped; }
+			}
+			if (wantFrac)
+			{
+				if (sFrac < N.capacity) { N.ray_o[sFrac] = make_float4(co.x, co.y, co.z, fracRfr), N.ray_d[sFrac] = cdFrac; aux.y = (int)sFrac; }
+				else { ws->overflow = 1; ++dropped; }
+			}
+			__threadfence();
+			if (wantFlec && sFlec < N.capacity) N.ray_meta[sFlec] = metaFlec;
+			if (wantFrac && sFrac < N.capacity) N.ray_meta[sFrac] = metaFrac;
+			if (dropped) atomicSub(&ws->outstanding, dropped);
+			if (lane == 0)
+			{
+				if (mf) atomicAdd(&ws->n_reflect, (unsigned long long)__popc(mf));
+				if (mr) atomicAdd(&ws->n_refract, (unsigned long long)__popc(mr));
+			}
+		}
+		if (i != 0xFFFFFFFFu)
+			L.aux[i] = aux;
+		const uint32_t hslot = warp_append(&ws->n_hit[level], surface);
+		if (surface)
+			L.hit_list[hslot] = i;
+
+		// ---- shadow rays of this batch's surfaces: one round per enabled light ---------------------------
+		if (wantShadows && __ballot_sync(0xffffffffu, surface))
+		{
+			for (uint32_t e = 0; e < F.n_enabled; ++e)
+			{
+				const uint32_t k = F.enabled_index[e];
+				if (surface)
+				{
+					RayD ray;
+					float dis, lum;
+					light_dir(F.lights[k], P, ray.d, dis, lum);
+					ray.o = P;
+					ray.mtlrfr = 1.0f;
+					ray.skip = newobj;
+					ray.type = (F.type == RT_TYPE_REFLECT || F.type == RT_TYPE_SHADOW) ? 0 : MY_RAY_SHADOWRAY_;
+					ray.isInside = 0;
+					Best best = { dis, RT_ID_NONE, RT_ID_NONE };
+					bool done = false;
+					const uint32_t nodes0 = st.nodes;
+					trace_scene<true, STATS>(S, ray, best, done, st);
+					if (STATS) atomicAdd(&ws->node_hist[12 + min(11, 31 - __clz((int)(st.nodes - nodes0 + 1u)))], 1u);
+					L.shadow[(size_t)k * L.capacity + i] = done ? 1 : 0;
+				}
+			}
+		}
+		__syncwarp();
+		if (lane == 0) atomicSub(&ws->outstanding, (int)nb);
+	}
+	flush_stats<STATS>(ws, st);
+}
+
 // ---- shading: light loop of every surface of every level ------------------------------------------
 
 __global__ void __launch_bounds__(128) k_shade(SceneDev S, const FrameParams *__restrict__ Fp, LevelSet LS, const WaveState *__restrict__ ws)
@@ -608,6 +840,14 @@ void rtk_wave(cudaStream_t st, const SceneDev &S, const FrameParams *F, const Le
 	const unsigned g = grid_for(maxItems, RT_BLOCK, sms * 8);   // persistent: 8 CTAs per SM
 	if (stats) k_wave<true><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
 	else k_wave<false><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+}
+
+void rtk_frame(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelSet &LS, WaveState *ws, uint32_t nPix, unsigned sms, bool stats)
+{
+	// every CTA must be resident (consumers wait for producers): 8 CTAs of 128 threads fit per SM
+	const unsigned g = grid_for(nPix, RT_BLOCK, sms * 8);
+	if (stats) k_frame<true><<<g, RT_BLOCK, 0, st>>>(S, F, LS, ws);
+	else k_frame<false><<<g, RT_BLOCK, 0, st>>>(S, F, LS, ws);
 }
 
 void rtk_shade(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelSet &LS, const WaveState *ws, uint32_t levels, uint32_t maxRays, unsigned sms)

@@ -32,8 +32,8 @@ struct WaveState
 	uint32_t count[RT_MAX_LEVELS + 2];   // rays queued per level
 	uint32_t n_hit[RT_MAX_LEVELS + 2];   // surfaces found per level (length of hit_list)
 	uint32_t head_trace[RT_MAX_LEVELS + 2], head_shadow[RT_MAX_LEVELS + 2];   // work-fetch cursors of the persistent warps
-	uint32_t overflow;                   // a level ran out of slots
-	uint32_t pad;
+	uint32_t overflow;                   // 1: a level ran out of slots, 2: the frame scheduler gave up waiting
+	int outstanding;                     // k_frame: rays reserved and not yet finished (0 = frame complete)
 	unsigned long long n_reflect, n_refract;
 	unsigned long long nodes_visited, tri_tests, prim_tests;
 	unsigned int node_hist[24];          // RT_FLAG_STATS: rays by floor(log2(nodes visited + 1)), closest-hit [0..11], shadow [12..23]
@@ -42,6 +42,8 @@ struct WaveState
 void rtk_raygen(cudaStream_t st, const FrameParams *F, const LevelBuf &L, uint32_t n, unsigned sms);
 void rtk_wave(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const LevelBuf &N, const LevelBuf &Lprev, WaveState *ws,
 	uint32_t level, bool traceOn, bool shadowOn, float zNear, uint32_t maxItems, unsigned sms, bool stats);
+// whole-frame persistent scheduler (all ray levels in one launch)
+void rtk_frame(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelSet &LS, WaveState *ws, uint32_t nPix, unsigned sms, bool stats);
 void rtk_shade(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelSet &LS, const WaveState *ws, uint32_t levels, uint32_t maxRays, unsigned sms);
 void rtk_debug(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, uint32_t n, uint8_t *out, unsigned sms);
 void rtk_combine(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const LevelBuf &N, const WaveState *ws,
