@@ -57,6 +57,7 @@ struct LevelStore
 	DevBuf<uint8_t> shadow;
 	DevBuf<uint32_t> hit_list;
 	uint32_t capacity = 0, lights = 0;
+	uint32_t dirtyHits = 0;   // hit_list entries that may be non-zero (k_frame needs them zero before a frame)
 	void release() { ray_o.release(), ray_d.release(), hit_p.release(), color.release(), ray_meta.release(), hit_id.release(), aux.release(), shadow.release(), hit_list.release(), hit_n.release(), hit_uv.release(); capacity = 0; }
 };
 
@@ -113,7 +114,8 @@ struct rt_ctx
 	double uploadMs = 0, buildMs = 0, renderMs = 0;
 	uint64_t uploadBytes = 0, frameH2D = 0, frameD2H = 0;
 	float levelFactor = 2.0f;
-	bool frameSched = true;         // one persistent launch per frame (k_frame); RT_B200_SCHED=waves selects per-level waves
+	int schedMode = 0;              // 0 auto, 1 k_frame (one persistent launch per frame), 2 per-level waves (RT_B200_SCHED=auto|frame|waves)
+	bool frameSched = false;        // what the last frame used
 	uint32_t frameEpoch = 0;
 };
 
@@ -150,7 +152,7 @@ extern "C" int rt_create(int device, rt_ctx **out)
 	c->S.tune = 0;
 	if (const char *v = getenv("RT_B200_LEAF_SIZE")) c->leafSize = (uint32_t)atoi(v);
 	if (const char *v = getenv("RT_B200_LEVEL_FACTOR")) c->levelFactor = (float)atof(v);
-	if (const char *v = getenv("RT_B200_SCHED")) c->frameSched = strcmp(v, "waves") != 0;
+	if (const char *v = getenv("RT_B200_SCHED")) c->schedMode = !strcmp(v, "frame") ? 1 : (!strcmp(v, "waves") ? 2 : 0);
 	if (const char *v = getenv("RT_B200_TUNE")) c->S.tune = (uint32_t)atoi(v);
 	*out = c;
 	return RT_OK;
@@ -454,6 +456,8 @@ static int ensure_level(rt_ctx *c, uint32_t l, uint32_t cap, uint32_t lights)
 	CU(L.hit_id.reserve(cap)); CU(L.color.reserve(cap)); CU(L.aux.reserve(cap)); CU(L.shadow.reserve((size_t)cap * (lights ? lights : 1))); CU(L.hit_list.reserve(cap)); CU(L.hit_n.reserve(cap)); CU(L.hit_uv.reserve(cap));
 	// k_frame recognises a written slot by the epoch in ray_meta: fresh memory must not look written
 	CU(cudaMemsetAsync(L.ray_meta.p, 0, sizeof(uint2) * L.ray_meta.cap, c->stream));
+	CU(cudaMemsetAsync(L.hit_list.p, 0, sizeof(uint32_t) * L.hit_list.cap, c->stream));
+	L.dirtyHits = 0;
 	L.capacity = cap, L.lights = lights;
 	return RT_OK;
 }
@@ -537,6 +541,12 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 	}
 	{ int rc = ensure_level(c, maxLevel + 1, 1, 1); if (rc != RT_OK) return rc; }
 
+	// Scheduler choice (measured): the whole-frame persistent kernel wins when the
+	// per-level queues are short next to the chip and rays are long and divergent (triangle meshes at
+	// <= ~3 M pixels per GPU: -13 % on c3, and it is what lets a 1080p frame scale over GPUs); the
+	// per-level waves win on big frames and on cheap analytic-primitive rays, where the scheduler's
+	// atomics and polling cost more than the tails they hide.
+	c->frameSched = c->schedMode == 1 || (c->schedMode == 0 && !c->models.empty() && c->nTris > 0 && nPix <= 3000000u);
 	if (++c->frameEpoch > 65535u)
 	{
 		// epoch wrap: forget every stamp so a slot written 65535 frames ago cannot look fresh
@@ -545,6 +555,14 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 		c->frameEpoch = 1;
 	}
 	F.epoch = c->frameEpoch;
+	// hit_list doubles as the publication flag of a surface (0 = not written): clear what the last frame used
+	for (uint32_t l = 0; l <= maxLevel + 1; ++l)
+	{
+		LevelStore &LV = c->levels[l];
+		if (LV.dirtyHits && LV.hit_list.p)
+			CU(cudaMemsetAsync(LV.hit_list.p, 0, sizeof(uint32_t) * std::min<size_t>(LV.dirtyHits, LV.hit_list.cap), st));
+		LV.dirtyHits = LV.capacity;   // until this frame's counts are known
+	}
 	WaveState &Wv = *c->hWaveInit;
 	memset(&Wv, 0, sizeof Wv);
 	Wv.count[0] = nPix;
@@ -611,6 +629,8 @@ static int finish_frame(rt_ctx *c)
 	CU(cudaEventElapsedTime(&ms, c->evStart, c->evStop));
 	c->renderMs = ms;
 	c->frameInFlight = false;
+	for (uint32_t l = 0; l <= RT_MAX_LEVELS + 1; ++l)
+		c->levels[l].dirtyHits = std::min(c->levels[l].capacity, c->hWave->n_hit[l]);
 	c->traceMs = c->shadowMs = c->shadeMs = c->otherMs = 0;
 	if (c->stageTiming && c->lastPixels)
 	{

@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(RT_BLOCK, 8) k_wave(SceneDev S, const FramePar
 			// queue appends: the whole warp takes part
 			const uint32_t hslot = warp_append(&ws->n_hit[level], surface);
 			if (surface)
-				L.hit_list[hslot] = i;
+				L.hit_list[hslot] = i + 1u;
 			const uint32_t sFlec = warp_append(&ws->count[level + 1], wantFlec);
 			if (wantFlec)
 			{
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(RT_BLOCK, 8) k_wave(SceneDev S, const FramePar
 			const uint32_t w = lane < batch ? base + lane : 0xFFFFFFFFu;
 			if (w < n)
 			{
-				const uint32_t k = F.enabled_index[w / nHit], i = Lprev.hit_list[w % nHit];
+				const uint32_t k = F.enabled_index[w / nHit], i = Lprev.hit_list[w % nHit] - 1u;
 				const float4 hp = Lprev.hit_p[i];
 				RayD ray;
 				float dis, lum;
@@ -418,37 +418,77 @@ __global__ void __launch_bounds__(RT_BLOCK, 8) k_frame(SceneDev S, const FramePa
 	const bool wantShadows = F.type != RT_TYPE_DEPTH && F.type != RT_TYPE_NORMAL && F.type != RT_TYPE_TEXTURE && F.type != RT_TYPE_MATERIAL;
 	TravStats st = { 0, 0, 0 };
 	uint32_t idleSpins = 0;
-	// Slots this warp has claimed but not traced yet.  A claim (one atomicAdd on head_trace[l]) may run
-	// past the rays published so far; such a slot stays owned by its lane, which polls it without
-	// blocking the lanes whose rays are ready, until it is published or the frame is over.
-	uint32_t pLevel = 0, pSlot = 0xFFFFFFFFu;
+	// Work this warp has claimed but not done yet.  A claim (one atomicAdd on a queue head) may run
+	// past what has been published so far; such a slot stays owned by its lane, which polls it without
+	// blocking the lanes whose work is ready, until it is published or the frame is over.
+	// pKind 0: closest-hit rays of level pLevel; pKind 1: shadow rays of level pLevel towards light pLight.
+	uint32_t pKind = 0, pLevel = 0, pLight = 0, pSlot = 0xFFFFFFFFu;
+	uint32_t hintKind = 0, hintLevel = 0, hintLight = 0;   // leader only: where the last claim succeeded
 	while (true)
 	{
 		if (__ballot_sync(0xffffffffu, pSlot != 0xFFFFFFFFu) == 0u)
 		{
-			// ---- claim: shallowest level with unclaimed rays (leader decides, broadcasts) ---------------
-			uint32_t level = 0xFFFFFFFFu, base = 0, nb = 0;
+			// ---- claim (leader decides, broadcasts): rays first (they create work), shallowest level
+			// first; then shadow rays, which are leaves of the dependency graph ---------------------------
+			uint32_t kind = 0xFFFFFFFFu, level = 0, light = 0, base = 0, nb = 0;
 			if (lane == 0)
-				for (uint32_t l = 0; l <= F.max_level; ++l)
+			{
+				// try where the last claim succeeded first (2 loads + 1 atomic), then scan
+				// Work is consumed while it is being produced, so queues are usually short; taking whatever
+				// is there would hand every warp 2-3 rays.  First pass: only full batches of 32; second
+				// pass (nothing full anywhere): whatever exists, so the tail of the frame still drains.
+				uint32_t minAvail = 32u;
+				auto claimRays = [&](uint32_t l) -> bool
 				{
 					uint32_t cnt = vload(&ws->count[l]);
 					cnt = cnt < LS.l[l].capacity ? cnt : LS.l[l].capacity;
 					const uint32_t h = vload(&ws->head_trace[l]);
-					if (h >= cnt)
-						continue;
-					uint32_t want = (cnt - h) >> 6;     // short queue: few rays per warp, so more warps share it
-					want = want < 2u ? 2u : (want > 32u ? 32u : want);
+					if (h >= cnt || cnt - h < minAvail)
+						return false;
+					uint32_t want = cnt - h;
+					want = want > 32u ? 32u : want;
 					const uint32_t got = atomicAdd(&ws->head_trace[l], want);
-					if (got < LS.l[l].capacity)
+					if (got >= LS.l[l].capacity)
+						return false;
+					kind = 0, level = l, base = got, nb = want;
+					return true;
+				};
+				auto claimShadow = [&](uint32_t l, uint32_t e) -> bool
+				{
+					const uint32_t cnt = vload(&ws->n_hit[l]);
+					const uint32_t h = vload(&ws->head_light[l][e]);
+					if (h >= cnt || cnt - h < minAvail)
+						return false;
+					uint32_t want = cnt - h;
+					want = want > 32u ? 32u : want;
+					const uint32_t got = atomicAdd(&ws->head_light[l][e], want);
+					if (got >= LS.l[l].capacity)
+						return false;
+					kind = 1, level = l, light = e, base = got, nb = want;
+					return true;
+				};
+				bool ok = false;
+				for (int pass = 0; pass < 2 && !ok; ++pass)
+				{
+					minAvail = pass == 0 ? 32u : 1u;
+					ok = hintKind == 0u ? claimRays(hintLevel) : false;
+					for (uint32_t l = 0; l <= F.max_level && !ok; ++l)
+						ok = claimRays(l);
+					if (wantShadows && !ok)
 					{
-						level = l, base = got, nb = want;
-						break;
+						if (hintKind == 1u) ok = claimShadow(hintLevel, hintLight);
+						for (uint32_t l = 0; l <= F.max_level && !ok; ++l)
+							for (uint32_t e = 0; e < F.n_enabled && !ok; ++e)
+								ok = claimShadow(l, e);
 					}
 				}
-			level = __shfl_sync(0xffffffffu, level, 0), base = __shfl_sync(0xffffffffu, base, 0), nb = __shfl_sync(0xffffffffu, nb, 0);
-			if (level != 0xFFFFFFFFu)
+				if (ok) hintKind = kind, hintLevel = level, hintLight = light;
+			}
+			kind = __shfl_sync(0xffffffffu, kind, 0), level = __shfl_sync(0xffffffffu, level, 0), light = __shfl_sync(0xffffffffu, light, 0);
+			base = __shfl_sync(0xffffffffu, base, 0), nb = __shfl_sync(0xffffffffu, nb, 0);
+			if (kind != 0xFFFFFFFFu)
 			{
-				pLevel = level;
+				pKind = kind, pLevel = level, pLight = light;
 				if (lane < nb && base + lane < LS.l[level].capacity) pSlot = base + lane;
 			}
 		}
@@ -457,11 +497,20 @@ __global__ void __launch_bounds__(RT_BLOCK, 8) k_frame(SceneDev S, const FramePa
 		const LevelBuf &N = LS.l[level + 1];
 		// which of the owned slots are published?
 		uint2 m = make_uint2(0, 0);
+		uint32_t hitEntry = 0;
 		bool ready = false;
 		if (pSlot != 0xFFFFFFFFu)
 		{
-			m = __ldcg(&L.ray_meta[pSlot]);
-			ready = (m.y >> 16) == F.epoch;
+			if (pKind == 0u)
+			{
+				m = __ldcg(&L.ray_meta[pSlot]);
+				ready = (m.y >> 16) == F.epoch;
+			}
+			else
+			{
+				hitEntry = __ldcg(&L.hit_list[pSlot]);
+				ready = hitEntry != 0u;
+			}
 		}
 		const uint32_t readyMask = __ballot_sync(0xffffffffu, ready);
 		if (readyMask == 0u)
@@ -476,11 +525,42 @@ __global__ void __launch_bounds__(RT_BLOCK, 8) k_frame(SceneDev S, const FramePa
 				if (lane == 0) ws->overflow = 2u;   // scheduler stuck: fail loudly instead of hanging the GPU
 				break;
 			}
-			__nanosleep(idleSpins < 64u ? 100 : 1000);
+			// back off quickly: idle warps poll the very cache lines the busy warps' atomics hit
+			__nanosleep(idleSpins < 4u ? 500 : (idleSpins < 16u ? 2000 : 8000));
 			continue;
 		}
 		idleSpins = 0;
 		const uint32_t nb = __popc(readyMask);
+
+		if (pKind == 1u)
+		{
+			// ---- shadow any-hit rays: a warp's lanes go to the same light from neighbouring surfaces ------
+			if (ready)
+			{
+				__threadfence();
+				const uint32_t i = hitEntry - 1u, k = F.enabled_index[pLight];
+				const float4 hp = __ldcg(&L.hit_p[i]);
+				RayD ray;
+				float dis, lum;
+				light_dir(F.lights[k], f3(hp), ray.d, dis, lum);
+				ray.o = f3(hp);
+				ray.mtlrfr = 1.0f;
+				ray.skip = __ldcg(&L.hit_id[i]).y;
+				ray.type = (F.type == RT_TYPE_REFLECT || F.type == RT_TYPE_SHADOW) ? 0 : MY_RAY_SHADOWRAY_;
+				ray.isInside = 0;
+				Best best = { dis, RT_ID_NONE, RT_ID_NONE };
+				bool done = false;
+				const uint32_t nodes0 = st.nodes;
+				trace_scene<true, STATS>(S, ray, best, done, st);
+				if (STATS) atomicAdd(&ws->node_hist[12 + min(11, 31 - __clz((int)(st.nodes - nodes0 + 1u)))], 1u);
+				L.shadow[(size_t)k * L.capacity + i] = done ? 1 : 0;
+				pSlot = 0xFFFFFFFFu;
+			}
+			__syncwarp();
+			if (lane == 0) atomicSub(&ws->outstanding, (int)nb);
+			continue;
+		}
+
 		const float zNear = level == 0 ? F.zNear : 0.0f;
 		const bool deeper = level + 1 <= F.max_level;
 		const uint32_t i = ready ? pSlot : 0xFFFFFFFFu;
@@ -491,8 +571,6 @@ __global__ void __launch_bounds__(RT_BLOCK, 8) k_frame(SceneDev S, const FramePa
 		uint2 metaFlec = make_uint2(0, 0), metaFrac = metaFlec;
 		float fracRfr = 1.0f;
 		int4 aux = make_int4(-1, -1, -1, 0);
-		F3 P = f3(0, 0, 0);
-		uint32_t newobj = RT_ID_NONE;
 		if (i != 0xFFFFFFFFu)
 		{
 			__threadfence();   // the stamp was seen: order the payload reads after it
@@ -505,8 +583,7 @@ __global__ void __launch_bounds__(RT_BLOCK, 8) k_frame(SceneDev S, const FramePa
 			const uint32_t nodes0 = st.nodes;
 			trace_scene<false, STATS>(S, ray, best, done, st);
 			if (STATS) atomicAdd(&ws->node_hist[min(11, 31 - __clz((int)(st.nodes - nodes0 + 1u)))], 1u);
-			P = ray.o + ray.d * best.t;
-			newobj = best.newobj;
+			const F3 P = ray.o + ray.d * best.t;
 			L.hit_p[i] = make_float4(P.x, P.y, P.z, best.t);
 			L.hit_id[i] = make_uint2(best.id, best.newobj);
 			surface = !(best.t > F.zFar || best.t < zNear);
@@ -555,24 +632,29 @@ __global__ void __launch_bounds__(RT_BLOCK, 8) k_frame(SceneDev S, const FramePa
 			}
 		}
 
-		// ---- children: count them as outstanding BEFORE they can be consumed, then publish -------------
-		const uint32_t mf = __ballot_sync(0xffffffffu, wantFlec), mr = __ballot_sync(0xffffffffu, wantFrac);
+		// ---- new work: count it as outstanding BEFORE it can be consumed, then publish ------------------
+		const uint32_t mf = __ballot_sync(0xffffffffu, wantFlec), mr = __ballot_sync(0xffffffffu, wantFrac), ms = __ballot_sync(0xffffffffu, surface);
 		const int nChildren = __popc(mf) + __popc(mr);
+		const int nShadow = wantShadows ? __popc(ms) * (int)F.n_enabled : 0;
+		// one atomic per batch: the new work is added before it is published, and this batch's own rays
+		// (all traced by now) are retired in the same operation
+		if (lane == 0 && nChildren + nShadow != (int)nb) atomicAdd(&ws->outstanding, nChildren + nShadow - (int)nb);
+		__syncwarp();
+		if (i != 0xFFFFFFFFu)
+			L.aux[i] = aux;
 		if (nChildren)
 		{
-			if (lane == 0) atomicAdd(&ws->outstanding, nChildren);
-			__syncwarp();
 			const uint32_t sFlec = warp_append(&ws->count[level + 1], wantFlec);
 			const uint32_t sFrac = warp_append(&ws->count[level + 1], wantFrac);
 			int dropped = 0;
 			if (wantFlec)
 			{
-				if (sFlec < N.capacity) { N.ray_o[sFlec] = co, N.ray_d[sFlec] = cdFlec; aux.x = (int)sFlec; }
+				if (sFlec < N.capacity) { N.ray_o[sFlec] = co, N.ray_d[sFlec] = cdFlec; L.aux[i].x = (int)sFlec; }
 				else { ws->overflow = 1; ++dropped; }
 			}
 			if (wantFrac)
 			{
-				if (sFrac < N.capacity) { N.ray_o[sFrac] = make_float4(co.x, co.y, co.z, fracRfr), N.ray_d[sFrac] = cdFrac; aux.y = (int)sFrac; }
+				if (sFrac < N.capacity) { N.ray_o[sFrac] = make_float4(co.x, co.y, co.z, fracRfr), N.ray_d[sFrac] = cdFrac; L.aux[i].y = (int)sFrac; }
 				else { ws->overflow = 1; ++dropped; }
 			}
 			__threadfence();
@@ -585,39 +667,11 @@ __global__ void __launch_bounds__(RT_BLOCK, 8) k_frame(SceneDev S, const FramePa
 				if (mr) atomicAdd(&ws->n_refract, (unsigned long long)__popc(mr));
 			}
 		}
-		if (i != 0xFFFFFFFFu)
-			L.aux[i] = aux;
+		// surfaces: hit_p / hit_id / hit_n are written; publish the compacted entry last
 		const uint32_t hslot = warp_append(&ws->n_hit[level], surface);
+		__threadfence();
 		if (surface)
-			L.hit_list[hslot] = i;
-
-		// ---- shadow rays of this batch's surfaces: one round per enabled light ---------------------------
-		if (wantShadows && __ballot_sync(0xffffffffu, surface))
-		{
-			for (uint32_t e = 0; e < F.n_enabled; ++e)
-			{
-				const uint32_t k = F.enabled_index[e];
-				if (surface)
-				{
-					RayD ray;
-					float dis, lum;
-					light_dir(F.lights[k], P, ray.d, dis, lum);
-					ray.o = P;
-					ray.mtlrfr = 1.0f;
-					ray.skip = newobj;
-					ray.type = (F.type == RT_TYPE_REFLECT || F.type == RT_TYPE_SHADOW) ? 0 : MY_RAY_SHADOWRAY_;
-					ray.isInside = 0;
-					Best best = { dis, RT_ID_NONE, RT_ID_NONE };
-					bool done = false;
-					const uint32_t nodes0 = st.nodes;
-					trace_scene<true, STATS>(S, ray, best, done, st);
-					if (STATS) atomicAdd(&ws->node_hist[12 + min(11, 31 - __clz((int)(st.nodes - nodes0 + 1u)))], 1u);
-					L.shadow[(size_t)k * L.capacity + i] = done ? 1 : 0;
-				}
-			}
-		}
-		__syncwarp();
-		if (lane == 0) atomicSub(&ws->outstanding, (int)nb);
+			L.hit_list[hslot] = i + 1u;
 	}
 	flush_stats<STATS>(ws, st);
 }
@@ -632,7 +686,7 @@ __global__ void __launch_bounds__(128) k_shade(SceneDev S, const FrameParams *__
 	const uint32_t n = ws->n_hit[level];
 	for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < n; h += gridDim.x * blockDim.x)
 	{
-		const uint32_t i = L.hit_list[h];
+		const uint32_t i = L.hit_list[h] - 1u;
 		const float4 hp = L.hit_p[i], hn = L.hit_n[i], huv = L.hit_uv[i];
 		const F3 P = f3(hp), Nn = f3(hn), rd = f3(L.ray_d[i]);
 		const int mtl = __float_as_int(hn.w), tex = __float_as_int(huv.z);

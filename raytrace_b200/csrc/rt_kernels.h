@@ -21,7 +21,7 @@ struct LevelBuf
 	uint8_t *shadow;     // [light][capacity]: 1 = occluded
 	float4 *hit_n;       // HitRes::normal.xyz, bits of the material index
 	float4 *hit_uv;      // HitRes::tcoord.u, .v, bits of the texture index (-1 none), unused
-	uint32_t *hit_list;  // compacted slots of the rays that found a surface inside [zNear, zFar]
+	uint32_t *hit_list;  // compacted (slot + 1) of the rays that found a surface inside [zNear, zFar]; 0 = not written yet
 	uint32_t capacity;
 };
 
@@ -32,6 +32,7 @@ struct WaveState
 	uint32_t count[RT_MAX_LEVELS + 2];   // rays queued per level
 	uint32_t n_hit[RT_MAX_LEVELS + 2];   // surfaces found per level (length of hit_list)
 	uint32_t head_trace[RT_MAX_LEVELS + 2], head_shadow[RT_MAX_LEVELS + 2];   // work-fetch cursors of the persistent warps
+	uint32_t head_light[RT_MAX_LEVELS + 2][RT_MAX_LIGHTS];                    // k_frame: shadow cursor per (level, enabled light)
 	uint32_t overflow;                   // 1: a level ran out of slots, 2: the frame scheduler gave up waiting
 	int outstanding;                     // k_frame: rays reserved and not yet finished (0 = frame complete)
 	unsigned long long n_reflect, n_refract;
