@@ -42,6 +42,8 @@ CONFIGS = {
     "c3": ("c3", 1920, 1080, 5, 0, 0, "1036800-triangle Model + plane, 2 lights, 1920x1080, depth 5, GPU LBVH"),
     "c4": ("c4", 3840, 2160, 8, 0, 0, "4147200-triangle Model + 64 glass + 6 mirror spheres + plane, 3840x2160, depth 8"),
 }
+# DRAM bytes per traversal launch measured once with `ncu --set full` (profiles/), keyed by (config, gpus)
+NCU_TRAFFIC = {("c3", 1): 827223040}
 REF_TILES = {"c1": 153, "c2": 12, "c3": 6, "c4": 2}   # 64x64 tiles per reference step (bounded sample)
 
 
@@ -303,7 +305,7 @@ def main():
         # flop model: 22 per child box (4 per 4-wide node), 47 per triangle test, 23 per analytic primitive
         flops = cs.nodes_visited * 4 * 22 + cs.tri_tests * 47 + cs.prim_tests * 23
         trav_ms = stage["traverse"] / args.steps
-        trav_launches = level + 2
+        trav_launches = 1 if cnt.launches <= level + 4 else level + 2   # whole-frame scheduler: one traversal launch per frame
         achieved = flops / (trav_ms * 1e-3) / 1e12 if trav_ms > 0 else 0.0
         queue_bytes = rays_local * 100   # ~100 B of ray/hit/node records written+read per ray
         line = {
@@ -317,9 +319,10 @@ def main():
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": float(e2e_s.item()) / args.steps * 1e3,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": {"bound": "fp32_issue", "kernel": "k_wave (closest-hit level l fused with shadow any-hit level l-1; all launches of a frame)", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "fp32_issue", "kernel": "k_frame (one persistent launch per frame: closest-hit + shadow traversal of all levels)" if trav_launches == 1 else "k_wave (closest-hit level l fused with shadow any-hit level l-1; all launches of a frame)", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": f"148 SMs x 128 lanes x {peak_src} (of measured)",
-                         "traffic": None, "launches_per_step": trav_launches, "avg_launch_ms": trav_ms / trav_launches,
+                         "traffic": NCU_TRAFFIC.get((args.config, world)), "traffic_source": "profiles/r1f_ncu_full_k_frame_c3.md (dram__bytes_read.sum + dram__bytes_write.sum of one k_frame launch)" if (args.config, world) in NCU_TRAFFIC else None,
+                         "launches_per_step": trav_launches, "avg_launch_ms": trav_ms / trav_launches,
                          "flops_per_step": flops, "nodes_per_ray": cs.nodes_visited / max(rays_local, 1), "tri_tests_per_ray": cs.tri_tests / max(rays_local, 1),
                          "stage_ms": {k: v / args.steps for k, v in stage.items()},
                          "hbm_secondary": {"queue_bytes_per_step": queue_bytes, "achieved_gbs": queue_bytes / (stage["render"] / args.steps * 1e-3) / 1e9,
