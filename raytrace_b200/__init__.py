@@ -79,6 +79,15 @@ class Scene:
     def camera_jitter(self, dx, dy):
         return rth.rth_scene_camera_jitter(self._h, dx, dy)
 
+    def camera_n(self):
+        v = (C.c_float * 4)()
+        rth.rth_scene_camera_get_n(self._h, v)
+        return tuple(v)
+
+    def set_camera_n(self, xyzw):
+        v = (C.c_float * 4)(*xyzw)
+        rth.rth_scene_camera_set_n(self._h, v)
+
     def camera_move(self, x, y, z):
         return rth.rth_scene_camera_move(self._h, x, y, z)
 

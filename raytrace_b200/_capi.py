@@ -127,6 +127,8 @@ RTH_SYMBOLS = {
     "rth_scene_camera_yaw": (C.c_int, [C.c_void_p, C.c_float]),
     "rth_scene_camera_pitch": (C.c_int, [C.c_void_p, C.c_float]),
     "rth_scene_camera_jitter": (C.c_int, [C.c_void_p, C.c_float, C.c_float]),
+    "rth_scene_camera_get_n": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "rth_scene_camera_set_n": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "rth_scene_flatten": (C.POINTER(SceneDesc), [C.c_void_p]),
     "rth_tracer_new": (C.c_void_p, [C.c_void_p, C.c_int]),
     "rth_tracer_free": (None, [C.c_void_p]),

@@ -64,8 +64,9 @@ struct LevelStore
 struct rt_ctx
 {
 	int device = 0, sms = 148;
-	cudaStream_t stream = nullptr;
+	cudaStream_t stream = nullptr, stopStream = nullptr;
 	bool ownStream = false;
+	uint32_t *hStopWord = nullptr;   // pinned constant 3 written into WaveState::overflow by rt_stop
 	cudaEvent_t evStart = nullptr, evStop = nullptr, evA = nullptr, evB = nullptr;
 	cudaEvent_t evStage[4 * (RT_MAX_LEVELS + 1) + 2];   // per level: before trace, after trace, after shadow, after shade; then combine begin/end
 	bool stageTiming = true;
@@ -140,6 +141,9 @@ extern "C" int rt_create(int device, rt_ctx **out)
 	c->device = device, c->sms = prop.multiProcessorCount;
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	c->ownStream = true;
+	CU(cudaStreamCreateWithFlags(&c->stopStream, cudaStreamNonBlocking));
+	CU(cudaMallocHost(&c->hStopWord, sizeof(uint32_t)));
+	*c->hStopWord = 3u;
 	CU(cudaEventCreate(&c->evStart)); CU(cudaEventCreate(&c->evStop)); CU(cudaEventCreate(&c->evA)); CU(cudaEventCreate(&c->evB));
 	for (auto &e : c->evStage) CU(cudaEventCreate(&e));
 	if (const char *v = getenv("RT_B200_STAGE_TIMING")) c->stageTiming = atoi(v) != 0;
@@ -149,11 +153,9 @@ extern "C" int rt_create(int device, rt_ctx **out)
 	CU(cudaMallocHost(&c->hWaveInit, sizeof(WaveState)));
 	CU(cudaMalloc(&c->dWave, sizeof(WaveState)));
 	memset(&c->S, 0, sizeof c->S);
-	c->S.tune = 0;
 	if (const char *v = getenv("RT_B200_LEAF_SIZE")) c->leafSize = (uint32_t)atoi(v);
 	if (const char *v = getenv("RT_B200_LEVEL_FACTOR")) c->levelFactor = (float)atof(v);
 	if (const char *v = getenv("RT_B200_SCHED")) c->schedMode = !strcmp(v, "frame") ? 1 : (!strcmp(v, "waves") ? 2 : 0);
-	if (const char *v = getenv("RT_B200_TUNE")) c->S.tune = (uint32_t)atoi(v);
 	*out = c;
 	return RT_OK;
 }
@@ -173,6 +175,7 @@ extern "C" void rt_destroy(rt_ctx *c)
 	cudaEventDestroy(c->evStart), cudaEventDestroy(c->evStop), cudaEventDestroy(c->evA), cudaEventDestroy(c->evB);
 	for (auto &e : c->evStage) cudaEventDestroy(e);
 	if (c->ownStream) cudaStreamDestroy(c->stream);
+	cudaStreamDestroy(c->stopStream), cudaFreeHost(c->hStopWord);
 	delete c;
 }
 
@@ -573,6 +576,7 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 	CU(cudaEventRecord(c->evStart, st));
 
 	const bool stats = (p->flags & RT_FLAG_STATS) != 0;
+	c->S.brute = (p->flags & RT_FLAG_BRUTE) ? 1u : 0u;
 	uint32_t launches = 0;
 	if (nPix)
 	{
@@ -641,6 +645,8 @@ static int finish_frame(rt_ctx *c)
 		c->traceMs = a, c->shadeMs = d;
 		c->otherMs = c->renderMs - c->traceMs - c->shadeMs;
 	}
+	if (c->hWave->overflow == 3u)
+		return RT_OK;   // stopped by rt_stop: incomplete frame, not an error (frameValid stays false)
 	if (c->hWave->overflow == 2u)
 		return fail(RT_E_STATE, "the frame scheduler stopped making progress (k_frame gave up waiting); frame is incomplete");
 	if (c->hWave->overflow)
@@ -672,11 +678,16 @@ extern "C" int rt_wait(rt_ctx *c, double *seconds)
 	return rc;
 }
 
-// A frame is a few milliseconds of queued kernels; stop() lets it drain (RayTracer::stop only
-// asks the workers to return early, RayTracer.cpp:698-701).
+// Cooperative cancel, like RayTracer::stop clearing isRun (RayTracer.cpp:698-701): a side stream
+// writes 3 into WaveState::overflow; the traversal warps look at that word every time they fetch
+// work and leave, so the frame ends within one batch.  The frame is then incomplete (rt_wait still
+// returns RT_OK, the pixels not reached keep whatever k_combine wrote from partial data).
 extern "C" int rt_stop(rt_ctx *c)
 {
 	if (!c) return fail(RT_E_INVALID, "rt_stop: ctx is NULL");
+	if (!c->frameInFlight) return RT_OK;
+	CU(cudaSetDevice(c->device));
+	CU(cudaMemcpyAsync(&c->dWave->overflow, c->hStopWord, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stopStream));
 	return RT_OK;
 }
 

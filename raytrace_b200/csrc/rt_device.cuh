@@ -143,7 +143,7 @@ struct SceneDev
 	const BvhNode4 *nodes4;
 	const SceneItem *items;
 	uint32_t n_items, n_prims, n_tris, n_parts;
-	uint32_t tune;               // bit0: prefetch child nodes (RT_B200_TUNE, development switch)
+	uint32_t brute;              // RT_FLAG_BRUTE: ignore the BVHs, test every primitive (diagnostic cross-check)
 };
 
 __device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }

@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(RT_BLOCK, 8) k_wave(SceneDev S, const FramePar
 		while (true)
 		{
 			const uint32_t base = warp_fetch(&ws->head_trace[level], batch);
-			if (base >= n)
+			if (base >= n || *(const volatile uint32_t *)&ws->overflow >= 2u)   // queue dry, or rt_stop
 				break;
 			const uint32_t lane = threadIdx.x & 31u;
 			const uint32_t i = lane < batch ? base + lane : 0xFFFFFFFFu;
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(RT_BLOCK, 8) k_wave(SceneDev S, const FramePar
 		while (true)
 		{
 			const uint32_t base = warp_fetch(&ws->head_shadow[lp], batch);
-			if (base >= n)
+			if (base >= n || *(const volatile uint32_t *)&ws->overflow >= 2u)
 				break;
 			const uint32_t lane = threadIdx.x & 31u;
 			const uint32_t w = lane < batch ? base + lane : 0xFFFFFFFFu;
@@ -518,8 +518,8 @@ __global__ void __launch_bounds__(RT_BLOCK, 8) k_frame(SceneDev S, const FramePa
 			int out = 0;
 			if (lane == 0) out = *(volatile int *)&ws->outstanding;
 			out = __shfl_sync(0xffffffffu, out, 0);
-			if (out <= 0 || vload(&ws->overflow) == 2u)
-				break;   // nothing in flight any more: unpublished slots will never be written
+			if (out <= 0 || vload(&ws->overflow) >= 2u)
+				break;   // nothing in flight any more (or the scheduler gave up / rt_stop): unpublished slots will never be written
 			if (++idleSpins > (1u << 22))
 			{
 				if (lane == 0) ws->overflow = 2u;   // scheduler stuck: fail loudly instead of hanging the GPU
@@ -530,6 +530,8 @@ __global__ void __launch_bounds__(RT_BLOCK, 8) k_frame(SceneDev S, const FramePa
 			continue;
 		}
 		idleSpins = 0;
+		if (vload(&ws->overflow) >= 2u)
+			break;   // rt_stop or scheduler abort
 		const uint32_t nb = __popc(readyMask);
 
 		if (pKind == 1u)

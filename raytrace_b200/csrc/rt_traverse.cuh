@@ -312,6 +312,17 @@ __device__ __forceinline__ void trace_scene(const SceneDev &S, const RayD &ray, 
 			if (STATS) ++st.prims;
 			test_prim<ANY>(S, ray, it.first, false, best, done);
 		}
+		else if (S.brute && it.kind == RT_ITEM_PRIMBVH)
+		{
+			// diagnostic: the run in object order, no BVH
+			for (uint32_t p = it.first; p < it.first + it.count; ++p)
+			{
+				if (STATS) ++st.prims;
+				test_prim<ANY>(S, ray, p, false, best, done);
+				if (ANY && done)
+					return;
+			}
+		}
 		else if (it.kind == RT_ITEM_PRIMBVH)
 		{
 			const uint32_t end = it.first + it.count;
@@ -336,6 +347,18 @@ __device__ __forceinline__ void trace_scene(const SceneDev &S, const RayD &ray, 
 			if (!(border_test(ray.o, ray.d, idir, f3(mn), f3(mx)) < best.t))
 				continue;
 			const uint32_t tb = __ldg(&M.tri_begin);
+			if (S.brute)
+			{
+				// diagnostic: every triangle of the model with the immediate culling replay, no BVH
+				const uint32_t te = tb + __ldg(&M.tri_count);
+				PartCache pc;
+				pc.part = 0xFFFFFFFFu, pc.mask = 0;
+				bool slow = false;
+				leaf_tris<ANY, false, STATS>(S, ray, idir, tb, te - tb, best.t, tb, te, pc, best, done, slow, st);
+				if (ANY && done)
+					return;
+				continue;
+			}
 			if (ANY)
 				traverse<true, true, false, STATS>(S, ray, idir, it.root, best.t, tb, tb + __ldg(&M.tri_count), best, done, st);
 			else

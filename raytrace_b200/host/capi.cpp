@@ -101,6 +101,19 @@ int rth_scene_camera_jitter(void *h, float dx, float dy)
 	return 0;
 }
 
+int rth_scene_camera_get_n(void *h, float *xyzw)
+{
+	const Camera &c = ((HostScene *)h)->scene.cam;
+	xyzw[0] = c.n.x, xyzw[1] = c.n.y, xyzw[2] = c.n.z, xyzw[3] = c.n.w;
+	return 0;
+}
+int rth_scene_camera_set_n(void *h, const float *xyzw)
+{
+	Camera &c = ((HostScene *)h)->scene.cam;
+	c.n.x = xyzw[0], c.n.y = xyzw[1], c.n.z = xyzw[2], c.n.w = xyzw[3];
+	return 0;
+}
+
 // flatten to the C-ABI description; the pointer stays valid until the next flatten/free
 const rt_scene_desc *rth_scene_flatten(void *h)
 {

@@ -67,6 +67,22 @@ def test_bvh_and_wavefront_are_deterministic(gpu_present):
     assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("name,n,parts,level", [("t_mesh", 0, 0, 4), ("c4", 48, 3, 6), ("c2", 12, 0, 4)])
+def test_bvh_equals_brute_force_on_the_gpu(gpu_present, name, n, parts, level):
+    # RT_FLAG_BRUTE tests every primitive with the same exact operators and no BVH: the LBVH (padded
+    # boxes, widened slab interval, cull-on-pop) must never lose a hit
+    sc = R.Scene(name, 384, 256, n, parts)
+    rt = R.RayTracer(sc)
+    rt.maxLevel = level
+    a = rt.render(R.MY_MODEL_RAYTRACE, flags=R.RT_FLAG_HIT_IDS)
+    ia, ca = rt.hit_ids(), rt.counters()
+    b = rt.render(R.MY_MODEL_RAYTRACE, flags=R.RT_FLAG_HIT_IDS | R.RT_FLAG_BRUTE)
+    ib, cb = rt.hit_ids(), rt.counters()
+    assert np.array_equal(a, b)
+    assert compare_ids(ia, ib) == (0, 0)
+    assert (ca.primary, ca.shadow, ca.reflect, ca.refract) == (cb.primary, cb.shadow, cb.reflect, cb.refract)
+
+
 def test_row_shards_assemble_to_the_full_frame(gpu_present):
     # interleaved 64-row tiles, tile % world == rank
     sc = R.Scene("t_mesh", 640, 512)
@@ -97,6 +113,34 @@ def test_scene_edits_reupload_incrementally(gpu_present):
         img = rt.render(R.MY_MODEL_RAYTRACE)
         oimg, _, _ = oracle_render(sc, 3, want_ids=False)
         assert_frames_match(img, oimg)
+
+
+def test_jittered_supersampling_matches_n_reference_renders(gpu_present):
+    # BASELINE config 5 at test size: 2x2 stratified samples, each quantised then averaged in integer
+    from raytrace_b200.supersample import render_supersampled, stratified_table
+    table = stratified_table(2, seed=0)
+    sc = R.Scene("t_mesh", 320, 192)
+    rt = R.RayTracer(sc)
+    rt.maxLevel = 3
+    gpu = render_supersampled(sc, lambda: rt.render(R.MY_MODEL_RAYTRACE), table)
+    ora = render_supersampled(sc, lambda: oracle_render(sc, 3, want_ids=False)[0], table)
+    assert np.array_equal(gpu, ora)
+    single = rt.render(R.MY_MODEL_RAYTRACE)
+    assert not np.array_equal(gpu, single)      # the jitter really moved the samples
+
+
+def test_stop_cancels_a_frame_and_the_next_frame_is_clean(gpu_present):
+    # RayTracer::stop (RayTracer.cpp:698-701): cooperative cancel; afterwards the tracer is reusable
+    sc = R.Scene("c4", 1920, 1080, 240, 15)
+    rt = R.RayTracer(sc)
+    rt.maxLevel = 8
+    ref = rt.render(R.MY_MODEL_RAYTRACE)
+    rt.start(R.MY_MODEL_RAYTRACE)
+    R.rth.rth_tracer_stop(rt._h)
+    rt.wait()
+    assert rt.isFinish
+    again = rt.render(R.MY_MODEL_RAYTRACE)
+    assert np.array_equal(again, ref)
 
 
 def test_full_size_c2_band_against_oracle(gpu_present):
