@@ -159,9 +159,9 @@ typedef struct
 {
 	uint32_t type;        /* RT_TYPE_* */
 	uint32_t max_level;   /* RayTracer::maxLevel; levels 0..max_level are traced (RayTracer.cpp:453) */
-	uint32_t rank, world; /* image-space shard: 64-row tile t is rendered iff t % world == rank; world=0 or 1 = whole frame */
+	uint32_t rank, world; /* image-space shard: row tile t is rendered iff t % world == rank; world=0 or 1 = whole frame */
 	uint32_t flags;       /* RT_FLAG_* */
-	uint32_t pad0;
+	uint32_t tile_rows;   /* height of a shard tile: 8, 16, 32 or 64 rows (0 = 64); finer tiles balance the ranks better */
 } rt_render_params;
 
 #define RT_FLAG_HIT_IDS   0x1   /* keep primary closest-hit identities for rt_read_hit_ids */

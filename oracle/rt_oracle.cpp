@@ -758,6 +758,7 @@ int rto_render(const rt_scene_desc *scene, const rt_render_params *params, uint8
 	const double dp = tan(cam.fovy * 3.1415926535897932384 / 360) / (height / 2);
 	const float zNear = cam.zNear, zFar = sqrt(2) * cam.zFar;
 	const uint32_t world = params->world > 1 ? params->world : 1, rank = params->world > 1 ? params->rank : 0;
+	const uint32_t tileRows = params->tile_rows ? params->tile_rows : 64u;
 	if (threads < 1) threads = 1;
 	std::atomic<int> nextRow(0);
 	std::vector<uint64_t> cnt((size_t)threads * 4, 0);
@@ -769,7 +770,7 @@ int rto_render(const rt_scene_desc *scene, const rt_render_params *params, uint8
 			const V4 cn = from(cam.n), cu = from(cam.u), cv = from(cam.v), cpos = from(cam.position);
 			for (int y = nextRow.fetch_add(1); y < blk_h * 64; y = nextRow.fetch_add(1))
 			{
-				if ((uint32_t)(y / 64) % world != rank)
+				if ((uint32_t)y / tileRows % world != rank)
 					continue;
 				for (int x = 0; x < blk_w * 64; ++x)
 				{
@@ -831,7 +832,7 @@ int rto_render(const rt_scene_desc *scene, const rt_render_params *params, uint8
 	if (ids)
 		for (int y = 0; y < height; ++y)
 			for (int x = 0; x < width; ++x)
-				if (y >= blk_h * 64 || x >= blk_w * 64 || (uint32_t)(y / 64) % world != rank)
+				if (y >= blk_h * 64 || x >= blk_w * 64 || (uint32_t)y / tileRows % world != rank)
 					ids[(size_t)y * width + x] = rt_hit_id{ -1, -1, -1, -1, 1e20f };
 	if (counters)
 	{

@@ -109,10 +109,10 @@ class RayTracer:
             rth.rth_tracer_free(self._h)
             self._h = None
 
-    def start(self, type=MY_MODEL_RAYTRACE, tnum=1, flags=0, rank=0, world=1):
+    def start(self, type=MY_MODEL_RAYTRACE, tnum=1, flags=0, rank=0, world=1, tile_rows=64):
         rth.rth_tracer_set_max_level(self._h, self.maxLevel)
         rth.rth_tracer_set_flags(self._h, flags)
-        rth.rth_tracer_set_shard(self._h, rank, world)
+        rth.rth_tracer_set_shard(self._h, rank, world, tile_rows)
         if rth.rth_tracer_start(self._h, type, tnum) != 0:
             raise RtError(rth.rth_last_error().decode())
 
@@ -177,8 +177,8 @@ class Context:
     def upload(self, desc):
         _check(rt.rt_upload_scene(self._h, desc), "rt_upload_scene")
 
-    def render_async(self, type=MY_MODEL_RAYTRACE, max_level=1, rank=0, world=1, flags=0):
-        p = RenderParams(type, max_level, rank, world, flags, 0)
+    def render_async(self, type=MY_MODEL_RAYTRACE, max_level=1, rank=0, world=1, flags=0, tile_rows=64):
+        p = RenderParams(type, max_level, rank, world, flags, tile_rows)
         _check(rt.rt_render_async(self._h, C.byref(p)), "rt_render_async")
 
     def wait(self) -> float:

@@ -71,7 +71,7 @@ class SceneDesc(C.Structure):
 
 class RenderParams(C.Structure):
     _fields_ = [("type", C.c_uint32), ("max_level", C.c_uint32), ("rank", C.c_uint32), ("world", C.c_uint32),
-                ("flags", C.c_uint32), ("pad0", C.c_uint32)]
+                ("flags", C.c_uint32), ("tile_rows", C.c_uint32)]
 
 
 class HitId(C.Structure):
@@ -141,7 +141,7 @@ RTH_SYMBOLS = {
     "rth_tracer_width": (C.c_int, [C.c_void_p]),
     "rth_tracer_height": (C.c_int, [C.c_void_p]),
     "rth_tracer_set_max_level": (None, [C.c_void_p, C.c_int]),
-    "rth_tracer_set_shard": (None, [C.c_void_p, C.c_int, C.c_int]),
+    "rth_tracer_set_shard": (None, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "rth_tracer_set_flags": (None, [C.c_void_p, C.c_uint]),
     "rth_tracer_read_hit_ids": (C.c_int, [C.c_void_p, C.POINTER(HitId)]),
     "rth_tracer_read_counters": (C.c_int, [C.c_void_p, C.POINTER(Counters)]),

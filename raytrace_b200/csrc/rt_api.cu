@@ -503,9 +503,13 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 	F.zNear = cam.zNear, F.zFar = (float)(sqrt(2) * cam.zFar);
 	F.width = W, F.height = H, F.blk_w = W / 64, F.blk_h = H / 64, F.half_w = W / 2, F.half_h = H / 2;
 	F.max_level = maxLevel, F.type = p->type, F.rank = rank, F.world = world;
+	const uint32_t tileRows = p->tile_rows ? p->tile_rows : 64u;
+	if (tileRows != 8u && tileRows != 16u && tileRows != 32u && tileRows != 64u)
+		return fail(RT_E_INVALID, "rt_render_async: tile_rows %u (must be 8, 16, 32 or 64)", tileRows);
+	F.tile_rows = tileRows;
 	uint32_t bands = 0;
-	for (uint32_t t = 0; t < (uint32_t)F.blk_h; ++t) if (t % world == rank) ++bands;
-	F.n_rows = bands * 64;
+	for (uint32_t t = 0; t < (uint32_t)F.blk_h * 64u / tileRows; ++t) if (t % world == rank) ++bands;
+	F.n_rows = bands * tileRows;
 	F.n_lights = (uint32_t)c->lights.size();
 	F.env_light = f4(c->envLight);
 	uint32_t enabledLights = 0;
@@ -753,8 +757,9 @@ extern "C" int rt_read_hit_ids(rt_ctx *c, rt_hit_id *ids)
 	for (uint32_t i = 0; i < n; ++i)
 	{
 		const uint32_t tile = i >> 6, in = i & 63u, tx = tile % tilesX, ty = tile / tilesX;
-		const uint32_t x = tx * 8u + (in & 7u), row = ty * 8u + (in >> 3), band = row >> 6;
-		const uint32_t y = ((band * world + rank) << 6) + (row & 63u);
+		const uint32_t tileRows = c->lastParams.tile_rows ? c->lastParams.tile_rows : 64u;
+		const uint32_t x = tx * 8u + (in & 7u), row = ty * 8u + (in >> 3), band = row / tileRows;
+		const uint32_t y = (band * world + rank) * tileRows + row % tileRows;
 		rt_hit_id id = { -1, -1, -1, -1, hp[i].w };
 		const uint32_t h = hid[i].y;
 		if (h != RT_ID_NONE)

@@ -72,7 +72,8 @@ struct FrameParams
 	uint32_t n_enabled;        // enabled lights, listed in light order
 	uint32_t enabled_index[RT_MAX_LIGHTS];
 	uint32_t epoch;            // 1..65535, stamps ray_meta so k_frame consumers can tell a written slot
-	uint32_t pad_[2];
+	uint32_t tile_rows;        // shard tile height (8..64 rows)
+	uint32_t pad_[1];
 	float4 env_light;
 	DevLight lights[RT_MAX_LIGHTS];
 };

@@ -33,8 +33,8 @@ __device__ __forceinline__ void slot_to_pixel(const FrameParams &F, uint32_t i, 
 	const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
 	x = (int)(tx * 8u + (in & 7u));
 	const uint32_t row = ty * 8u + (in >> 3);            // row among this shard's rows
-	const uint32_t band = row >> 6;                       // 64-row tile among this shard's tiles
-	y = (int)(((band * F.world + F.rank) << 6) + (row & 63u));
+	const uint32_t band = row / F.tile_rows;              // row tile among this shard's tiles
+	y = (int)((band * F.world + F.rank) * F.tile_rows + row % F.tile_rows);
 }
 
 __device__ __forceinline__ uint8_t put8(float c)
@@ -230,7 +230,7 @@ __device__ __forceinline__ Surface surface_attributes(const SceneDev &S, const R
 // ---- fused wave kernel: closest hit of level `level` + shadow rays of level `level - 1` -------------
 
 template<bool STATS>
-__global__ void __launch_bounds__(RT_BLOCK, 8) k_wave(SceneDev S, const FrameParams *__restrict__ Fp, LevelBuf L, LevelBuf N, LevelBuf Lprev,
+__global__ void __launch_bounds__(RT_BLOCK, RT_CTAS_PER_SM) k_wave(SceneDev S, const FrameParams *__restrict__ Fp, LevelBuf L, LevelBuf N, LevelBuf Lprev,
 	WaveState *ws, uint32_t level, uint32_t traceOn, uint32_t shadowOn, float zNear)
 {
 	const FrameParams &F = *Fp;
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(RT_BLOCK, 8) k_wave(SceneDev S, const FramePar
 __device__ __forceinline__ uint32_t vload(const uint32_t *p) { return *(const volatile uint32_t *)p; }
 
 template<bool STATS>
-__global__ void __launch_bounds__(RT_BLOCK, 8) k_frame(SceneDev S, const FrameParams *__restrict__ Fp, LevelSet LS, WaveState *ws)
+__global__ void __launch_bounds__(RT_BLOCK, RT_CTAS_PER_SM) k_frame(SceneDev S, const FrameParams *__restrict__ Fp, LevelSet LS, WaveState *ws)
 {
 	const FrameParams &F = *Fp;
 	const uint32_t lane = threadIdx.x & 31u;
@@ -893,7 +893,7 @@ void rtk_raygen(cudaStream_t st, const FrameParams *F, const LevelBuf &L, uint32
 void rtk_wave(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const LevelBuf &N, const LevelBuf &Lprev, WaveState *ws,
 	uint32_t level, bool traceOn, bool shadowOn, float zNear, uint32_t maxItems, unsigned sms, bool stats)
 {
-	const unsigned g = grid_for(maxItems, RT_BLOCK, sms * 8);   // persistent: 8 CTAs per SM
+	const unsigned g = grid_for(maxItems, RT_BLOCK, sms * RT_CTAS_PER_SM);   // persistent: all CTAs resident
 	if (stats) k_wave<true><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
 	else k_wave<false><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
 }
@@ -901,7 +901,7 @@ void rtk_wave(cudaStream_t st, const SceneDev &S, const FrameParams *F, const Le
 void rtk_frame(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelSet &LS, WaveState *ws, uint32_t nPix, unsigned sms, bool stats)
 {
 	// every CTA must be resident (consumers wait for producers): 8 CTAs of 128 threads fit per SM
-	const unsigned g = grid_for(nPix, RT_BLOCK, sms * 8);
+	const unsigned g = grid_for(nPix, RT_BLOCK, sms * RT_CTAS_PER_SM);
 	if (stats) k_frame<true><<<g, RT_BLOCK, 0, st>>>(S, F, LS, ws);
 	else k_frame<false><<<g, RT_BLOCK, 0, st>>>(S, F, LS, ws);
 }

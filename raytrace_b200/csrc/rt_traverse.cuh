@@ -17,6 +17,12 @@
 #include "rt_intersect.cuh"
 
 #define RT_BLOCK 128
+#ifndef RT_CULL_ON_POP
+#define RT_CULL_ON_POP 1
+#endif
+#ifndef RT_CTAS_PER_SM
+#define RT_CTAS_PER_SM 8
+#endif
 
 struct TravStats { uint32_t nodes, tris, prims; };
 
@@ -214,7 +220,9 @@ __device__ __forceinline__ void traverse(const SceneDev &S, const RayD &ray, con
 	bool slow = false;
 	const uint32_t idBefore = best.id;
 	int stack[RT_STACK];
+#if RT_CULL_ON_POP
 	float stackT[RT_STACK];   // entry distance of each stacked subtree (closest hit: culled again on pop)
+#endif
 	int sp = 0;
 	int cur = root;
 	// byte offsets of the near / far plane vectors inside a BvhNode4 for this ray's direction signs
@@ -244,18 +252,29 @@ __device__ __forceinline__ void traverse(const SceneDev &S, const RayD &ray, con
 			if (h3 && t3 < bt) bt = t3, bi = 3;
 			if (!(h0 | h1 | h2 | h3))
 			{
+#if RT_CULL_ON_POP
 				cur = RT_TRAV_DONE;
 				while (sp)
 				{
 					--sp;
 					if (ANY || stackT[sp] <= best.t) { cur = stack[sp]; break; }
 				}
+#else
+				cur = sp ? stack[--sp] : RT_TRAV_DONE;
+#endif
 				continue;
 			}
+#if RT_CULL_ON_POP
 			if (h0 && bi != 0) { stack[sp] = link.x; if (!ANY) stackT[sp] = t0; ++sp; }
 			if (h1 && bi != 1) { stack[sp] = link.y; if (!ANY) stackT[sp] = t1; ++sp; }
 			if (h2 && bi != 2) { stack[sp] = link.z; if (!ANY) stackT[sp] = t2; ++sp; }
 			if (h3 && bi != 3) { stack[sp] = link.w; if (!ANY) stackT[sp] = t3; ++sp; }
+#else
+			if (h0 && bi != 0) stack[sp++] = link.x;
+			if (h1 && bi != 1) stack[sp++] = link.y;
+			if (h2 && bi != 2) stack[sp++] = link.z;
+			if (h3 && bi != 3) stack[sp++] = link.w;
+#endif
 			cur = bi == 0 ? link.x : bi == 1 ? link.y : bi == 2 ? link.z : link.w;
 		}
 		if (cur == RT_TRAV_DONE)
@@ -274,12 +293,16 @@ __device__ __forceinline__ void traverse(const SceneDev &S, const RayD &ray, con
 			}
 		if (ANY && done)
 			return;
+#if RT_CULL_ON_POP
 		cur = RT_TRAV_DONE;
 		while (sp)
 		{
 			--sp;
 			if (ANY || stackT[sp] <= best.t) { cur = stack[sp]; break; }
 		}
+#else
+		cur = sp ? stack[--sp] : RT_TRAV_DONE;
+#endif
 	}
 	if (FAST)
 	{

@@ -89,7 +89,7 @@ void RayTracer::start(const uint8_t type, const int8_t)
 	rt_render_params rp;
 	memset(&rp, 0, sizeof rp);
 	rp.type = type, rp.max_level = maxLevel;
-	rp.rank = shardRank, rp.world = shardWorld, rp.flags = renderFlags;
+	rp.rank = shardRank, rp.world = shardWorld, rp.flags = renderFlags, rp.tile_rows = shardTileRows;
 	rc = rt_render_async(ctx, &rp);
 	if (rc != RT_OK)
 		fail("rt_render_async", rc);

@@ -46,6 +46,7 @@ public:
 	// ---- additions of this build (not in the reference) ----
 	int device = 0;                 // CUDA device ordinal used when the context is created
 	uint32_t shardRank = 0, shardWorld = 1;   // image-space shard rendered by this tracer
+	uint32_t shardTileRows = 64;              // rows per shard tile (8, 16, 32, 64)
 	uint32_t renderFlags = 0;       // RT_FLAG_* passed to the next start()
 	void reserveOutput(size_t bytes);          // frames beyond 2048x2048
 	void wait();                               // block until isFinish

@@ -142,7 +142,11 @@ const uint8_t *rth_tracer_output(void *t) { return ((RayTracer *)t)->output; }
 int rth_tracer_width(void *t) { return ((RayTracer *)t)->width; }
 int rth_tracer_height(void *t) { return ((RayTracer *)t)->height; }
 void rth_tracer_set_max_level(void *t, int level) { ((RayTracer *)t)->maxLevel = (uint8_t)level; }
-void rth_tracer_set_shard(void *t, int rank, int world) { ((RayTracer *)t)->shardRank = rank, ((RayTracer *)t)->shardWorld = world; }
+void rth_tracer_set_shard(void *t, int rank, int world, int tileRows)
+{
+	RayTracer *r = (RayTracer *)t;
+	r->shardRank = rank, r->shardWorld = world, r->shardTileRows = tileRows > 0 ? tileRows : 64;
+}
 void rth_tracer_set_flags(void *t, unsigned flags) { ((RayTracer *)t)->renderFlags = flags; }
 int rth_tracer_read_hit_ids(void *t, rt_hit_id *ids) { return ((RayTracer *)t)->readHitIds(ids) ? 0 : -1; }
 int rth_tracer_read_counters(void *t, rt_counters *c) { return ((RayTracer *)t)->readCounters(c) ? 0 : -1; }

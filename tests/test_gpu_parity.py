@@ -98,6 +98,20 @@ def test_row_shards_assemble_to_the_full_frame(gpu_present):
     assert total == cf.primary + cf.shadow + cf.reflect + cf.refract
 
 
+def test_fine_row_tiles_shard_identically(gpu_present):
+    # 8-row shard tiles (better balance than the reference's 64-row tiles) render the same pixels
+    sc = R.Scene("t_mesh", 448, 320)
+    full, _, cf, _ = gpu_frame(sc, 3, want_ids=False)
+    acc = np.full_like(full, 127)
+    for r in range(5):
+        part, ids, c, _ = gpu_frame(sc, 3, rank=r, world=5, tile_rows=8)
+        opart, oids, oc = oracle_render(sc, 3, rank=r, world=5, tile_rows=8)
+        assert np.array_equal(part, opart) and compare_ids(ids, oids) == (0, 0)
+        rows = [y for y in range(320) if (y // 8) % 5 == r]
+        acc[rows] = part[rows]
+    assert np.array_equal(acc, full)
+
+
 def test_scene_edits_reupload_incrementally(gpu_present):
     # MovePos / Switch / ChgMtl between frames (Scene.cpp:157-301): same tracer, new frame == oracle
     sc = R.Scene("t_mesh", 384, 256)
