@@ -57,7 +57,6 @@ struct LevelStore
 	DevBuf<uint8_t> shadow;
 	DevBuf<uint32_t> hit_list;
 	uint32_t capacity = 0, lights = 0;
-	uint32_t dirtyHits = 0;   // hit_list entries that may be non-zero (k_frame needs them zero before a frame)
 	void release() { ray_o.release(), ray_d.release(), hit_p.release(), color.release(), ray_meta.release(), hit_id.release(), aux.release(), shadow.release(), hit_list.release(), hit_n.release(), hit_uv.release(); capacity = 0; }
 };
 
@@ -460,7 +459,6 @@ static int ensure_level(rt_ctx *c, uint32_t l, uint32_t cap, uint32_t lights)
 	// k_frame recognises a written slot by the epoch in ray_meta: fresh memory must not look written
 	CU(cudaMemsetAsync(L.ray_meta.p, 0, sizeof(uint2) * L.ray_meta.cap, c->stream));
 	CU(cudaMemsetAsync(L.hit_list.p, 0, sizeof(uint32_t) * L.hit_list.cap, c->stream));
-	L.dirtyHits = 0;
 	L.capacity = cap, L.lights = lights;
 	return RT_OK;
 }
@@ -485,9 +483,11 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 	const uint32_t maxLevel = debugStage ? 0u : p->max_level;   // the staged shaders shade one level only
 	if (maxLevel >= RT_MAX_LEVELS) return fail(RT_E_LIMIT, "rt_render_async: max_level %u (limit %d)", maxLevel, RT_MAX_LEVELS - 1);
 	CU(cudaSetDevice(c->device));
-	// the previous frame must have drained completely (including the read-back of its WaveState)
-	// before the pinned staging buffers are rewritten
-	if (c->frameInFlight) { int rc = finish_frame(c); if (rc != RT_OK) return rc; }
+	// Back-to-back frames: the next frame may be enqueued while the previous one is still running.
+	// All that has to be over is the previous frame's H2D copies out of the pinned staging buffers
+	// (evStart is recorded right after them).  Status and counters are those of the LAST frame only;
+	// callers that want every frame checked call rt_wait between frames (RayTracer::start does).
+	if (c->frameInFlight) CU(cudaEventSynchronize(c->evStart));
 	cudaStream_t st = c->stream;
 	const rt_camera &cam = c->camera;
 	const int W = cam.width, H = cam.height;
@@ -562,14 +562,6 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 		c->frameEpoch = 1;
 	}
 	F.epoch = c->frameEpoch;
-	// hit_list doubles as the publication flag of a surface (0 = not written): clear what the last frame used
-	for (uint32_t l = 0; l <= maxLevel + 1; ++l)
-	{
-		LevelStore &LV = c->levels[l];
-		if (LV.dirtyHits && LV.hit_list.p)
-			CU(cudaMemsetAsync(LV.hit_list.p, 0, sizeof(uint32_t) * std::min<size_t>(LV.dirtyHits, LV.hit_list.cap), st));
-		LV.dirtyHits = LV.capacity;   // until this frame's counts are known
-	}
 	WaveState &Wv = *c->hWaveInit;
 	memset(&Wv, 0, sizeof Wv);
 	Wv.count[0] = nPix;
@@ -619,6 +611,11 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 			rtk_combine(st, c->S, c->dFrame, level_buf(c->levels[l]), level_buf(c->levels[l + 1]), c->dWave, (uint32_t)l, fb, c->levels[l].capacity, c->sms);
 			++launches;
 		}
+		if (p->type != RT_TYPE_CHECK)
+		{
+			// leave every hit_list zeroed for the next frame (k_frame reads 0 as "not published yet")
+			rtk_reset_hits(st, LS, c->dWave, maxLevel + 1, c->levels[0].capacity, c->sms); ++launches;
+		}
 	}
 	CU(cudaGetLastError());
 	CU(cudaEventRecord(c->evStop, st));
@@ -637,8 +634,6 @@ static int finish_frame(rt_ctx *c)
 	CU(cudaEventElapsedTime(&ms, c->evStart, c->evStop));
 	c->renderMs = ms;
 	c->frameInFlight = false;
-	for (uint32_t l = 0; l <= RT_MAX_LEVELS + 1; ++l)
-		c->levels[l].dirtyHits = std::min(c->levels[l].capacity, c->hWave->n_hit[l]);
 	c->traceMs = c->shadowMs = c->shadeMs = c->otherMs = 0;
 	if (c->stageTiming && c->lastPixels)
 	{

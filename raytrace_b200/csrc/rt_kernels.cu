@@ -825,6 +825,15 @@ __global__ void __launch_bounds__(128) k_debug(SceneDev S, const FrameParams *__
 	}
 }
 
+// ---- end of frame: hit_list doubles as the publication flag of a surface (0 = not written) --------
+__global__ void k_reset_hits(LevelSet LS, const WaveState *__restrict__ ws)
+{
+	const LevelBuf &L = LS.l[blockIdx.y];
+	const uint32_t n = ws->n_hit[blockIdx.y] < L.capacity ? ws->n_hit[blockIdx.y] : L.capacity;
+	for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < n; h += gridDim.x * blockDim.x)
+		L.hit_list[h] = 0u;
+}
+
 // ---- post-order combine --------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(256) k_combine(SceneDev S, const FrameParams *__restrict__ Fp, LevelBuf L, LevelBuf N,
@@ -915,6 +924,12 @@ void rtk_shade(cudaStream_t st, const SceneDev &S, const FrameParams *F, const L
 void rtk_debug(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, uint32_t n, uint8_t *out, unsigned sms)
 {
 	k_debug<<<grid_for(n, 128, sms * 16), 128, 0, st>>>(S, F, L, n, out);
+}
+
+void rtk_reset_hits(cudaStream_t st, const LevelSet &LS, const WaveState *ws, uint32_t levels, uint32_t maxRays, unsigned sms)
+{
+	const dim3 g(grid_for(maxRays, 256, sms * 4), levels);
+	k_reset_hits<<<g, 256, 0, st>>>(LS, ws);
 }
 
 void rtk_combine(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const LevelBuf &N, const WaveState *ws,
