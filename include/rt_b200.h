@@ -178,6 +178,27 @@ typedef struct
 	float distance;   /* HitRes::distance, 1e20 = miss */
 } rt_hit_id;
 
+/* Ray (3DElement.h:155-164) and HitRes (3DElement.h:166-183) as plain records, for rt_intersect_object */
+typedef struct
+{
+	rt_vec4 origin, direction;   /* direction must be unit length (the Ray constructor normalises) */
+	float mtlrfr;
+	uint32_t type;               /* MY_RAY_* */
+	uint32_t is_inside;          /* 0x00 / 0xFF */
+	uint32_t pad0;
+} rt_ray;
+
+typedef struct
+{
+	rt_vec4 position, normal;
+	float tu, tv;                /* HitRes::tcoord */
+	int32_t material, texture;   /* indices into the uploaded tables, -1 = none (HitRes::mtl / tex) */
+	rt_hit_id id;                /* HitRes::obj as an identity + HitRes::distance */
+	float rfr;
+	uint32_t is_inside;
+	uint32_t pad0;
+} rt_hit;
+
 typedef struct
 {
 	uint64_t primary, shadow, reflect, refract;      /* rays = closest-hit or any-hit queries */
@@ -226,6 +247,14 @@ int rt_set_output(rt_ctx *ctx, void *device_ptr, size_t bytes);
 /* page-locked host memory for RayTracer::output: rt_read_output into it runs at full PCIe speed */
 int rt_host_alloc(void **ptr, size_t bytes);
 int rt_host_free(void *ptr);
+
+/* B2: the per-primitive operator `HitRes DrawObject::intersect(const Ray&, const HitRes &hr, float min)`
+ * (3DElement.h:201) of object `object` of the uploaded scene, evaluated on the device for n rays:
+ * out[i] = in[i] on a miss, else the new hit with a strictly smaller distance.  in[i].id is hr.obj
+ * (the primitive to skip) and in[i].id.distance is hr.distance; `min` is the any-hit threshold of
+ * Model::intersect (Model.cpp:786).  Walks the object's primitives in the reference's own order
+ * (no BVH), so even the order-dependent early exit is reproduced.  Synchronous. */
+int rt_intersect_object(rt_ctx *ctx, uint32_t object, const rt_ray *rays, const rt_hit *in, float min, rt_hit *out, uint32_t n);
 
 /* diagnostics / parity taps */
 int rt_read_hit_ids(rt_ctx *ctx, rt_hit_id *ids /* width*height */);

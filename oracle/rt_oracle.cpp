@@ -843,6 +843,80 @@ int rto_render(const rt_scene_desc *scene, const rt_render_params *params, uint8
 	return RT_OK;
 }
 
+// DrawObject::intersect(ray, hr, min) of ONE object of the scene (3DElement.h:201), for n rays.
+// Mirrors rt_intersect_object of the product ABI; used by tests/test_gpu_parity.py.
+int rto_intersect_object(const rt_scene_desc *scene, uint32_t object, const rt_ray *rays, const rt_hit *in, float min, rt_hit *out, uint32_t n)
+{
+	if (!scene || !rays || !in || !out)
+		return RT_E_INVALID;
+	Prepared P;
+	prepare(*scene, P);
+	Tracer tr(P, 0);
+	auto encode = [&](const rt_hit_id &id) -> int64_t
+	{
+		if (id.object < 0) return OBJ_NONE;
+		for (uint32_t m = 0; m < scene->n_models; ++m)
+			if ((int32_t)scene->models[m].object == id.object)
+			{
+				if (id.sub < 0 || (uint32_t)id.sub >= scene->models[m].part_count || id.index < 0) return OBJ_NONE;
+				return tri_id(scene->parts[scene->models[m].part_begin + id.sub].tri_begin + (uint32_t)id.index, (uint32_t)(id.octant & 7));
+			}
+		for (uint32_t p = 0; p < scene->n_prims; ++p)
+			if ((int32_t)scene->prims[p].object == id.object && (int32_t)scene->prims[p].sub == id.sub) return prim_id(p);
+		return OBJ_NONE;
+	};
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		RayO ray;
+		ray.origin = from(rays[i].origin), ray.direction = from(rays[i].direction), ray.mtlrfr = rays[i].mtlrfr;
+		ray.type = (uint8_t)rays[i].type, ray.isInside = (uint8_t)rays[i].is_inside;
+		const int64_t skip = encode(in[i].id);
+		Hit hr(in[i].id.distance);
+		hr.obj = skip;
+		int64_t newobj = OBJ_NONE;
+		bool hit = false;
+		for (const Item &it : P.items)
+		{
+			const uint32_t obj = it.kind == 1 ? scene->models[it.index].object : scene->prims[it.index].object;
+			if (obj != object)
+				continue;
+			hr.obj = skip;   // a BallPlane compares every lattice slot with the caller's hr.obj
+			const float before = hr.distance;
+			hr = tr.intersect(it, ray, hr, min);
+			if (hr.distance < before) newobj = hr.obj, hit = true;
+		}
+		out[i] = in[i];
+		if (hit)
+		{
+			rt_hit &o = out[i];
+			o.position = rt_vec4{ hr.position.x, hr.position.y, hr.position.z, 0 };
+			o.normal = rt_vec4{ hr.normal.x, hr.normal.y, hr.normal.z, 0 };
+			o.tu = hr.tu, o.tv = hr.tv, o.material = hr.mtl, o.texture = hr.tex;
+			o.rfr = hr.rfr, o.is_inside = hr.isInside;
+			rt_hit_id id = { -1, -1, -1, -1, hr.distance };
+			if (newobj >> 40)
+			{
+				const uint32_t t = (uint32_t)(newobj & 0xffffffff);
+				for (uint32_t m = 0; m < scene->n_models && id.object < 0; ++m)
+					for (uint32_t p = 0; p < scene->models[m].part_count; ++p)
+					{
+						const rt_part &part = scene->parts[scene->models[m].part_begin + p];
+						if (t >= part.tri_begin && t < part.tri_begin + part.tri_count)
+						{
+							id.object = (int32_t)scene->models[m].object, id.sub = (int32_t)p;
+							id.index = (int32_t)(t - part.tri_begin), id.octant = (int32_t)((newobj >> 32) & 7);
+							break;
+						}
+					}
+			}
+			else if (newobj >= 0)
+				id.object = (int32_t)scene->prims[newobj].object, id.sub = (int32_t)scene->prims[newobj].sub;
+			o.id = id;
+		}
+	}
+	return RT_OK;
+}
+
 int rto_abi_version(void) { return RT_ABI_VERSION; }
 
 }  // extern "C"

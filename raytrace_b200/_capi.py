@@ -79,6 +79,17 @@ class HitId(C.Structure):
                 ("distance", C.c_float)]
 
 
+class Ray(C.Structure):
+    _fields_ = [("origin", Vec4), ("direction", Vec4), ("mtlrfr", C.c_float), ("type", C.c_uint32),
+                ("is_inside", C.c_uint32), ("pad0", C.c_uint32)]
+
+
+class Hit(C.Structure):
+    _fields_ = [("position", Vec4), ("normal", Vec4), ("tu", C.c_float), ("tv", C.c_float),
+                ("material", C.c_int32), ("texture", C.c_int32), ("id", HitId), ("rfr", C.c_float),
+                ("is_inside", C.c_uint32), ("pad0", C.c_uint32)]
+
+
 class Counters(C.Structure):
     _fields_ = [("primary", C.c_uint64), ("shadow", C.c_uint64), ("reflect", C.c_uint64), ("refract", C.c_uint64),
                 ("nodes_visited", C.c_uint64), ("tri_tests", C.c_uint64), ("prim_tests", C.c_uint64),
@@ -105,6 +116,7 @@ RT_SYMBOLS = {
     "rt_set_output": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "rt_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "rt_host_free": (C.c_int, [C.c_void_p]),
+    "rt_intersect_object": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(Ray), C.POINTER(Hit), C.c_float, C.POINTER(Hit), C.c_uint32]),
     "rt_read_hit_ids": (C.c_int, [C.c_void_p, C.POINTER(HitId)]),
     "rt_read_counters": (C.c_int, [C.c_void_p, C.POINTER(Counters)]),
 }
@@ -145,6 +157,7 @@ RTH_SYMBOLS = {
     "rth_tracer_set_flags": (None, [C.c_void_p, C.c_uint]),
     "rth_tracer_read_hit_ids": (C.c_int, [C.c_void_p, C.POINTER(HitId)]),
     "rth_tracer_read_counters": (C.c_int, [C.c_void_p, C.POINTER(Counters)]),
+    "rth_object_intersect": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Ray), C.POINTER(Hit), C.c_float]),
     "rth_tracer_context": (C.c_void_p, [C.c_void_p]),
 }
 

@@ -734,6 +734,83 @@ extern "C" int rt_set_output(rt_ctx *c, void *device_ptr, size_t bytes)
 	return RT_OK;
 }
 
+// identity <-> device id (RT_ID_NONE | prim flat index | RT_ID_TRI | oct<<28 | triangle)
+static uint32_t encode_id(const rt_ctx *c, const rt_hit_id &id)
+{
+	if (id.object < 0) return RT_ID_NONE;
+	for (const rt_model &M : c->models)
+		if ((int32_t)M.object == id.object)
+		{
+			if (id.sub < 0 || (uint32_t)id.sub >= M.part_count || id.index < 0) return RT_ID_NONE;
+			const rt_part &P = c->parts[M.part_begin + id.sub];
+			return RT_ID_TRI | ((uint32_t)(id.octant & 7) << 28) | (P.tri_begin + (uint32_t)id.index);
+		}
+	for (size_t p = 0; p < c->prims.size(); ++p)
+		if ((int32_t)c->prims[p].object == id.object && (int32_t)c->prims[p].sub == id.sub) return (uint32_t)p;
+	return RT_ID_NONE;
+}
+
+static rt_hit_id decode_id(const rt_ctx *c, uint32_t h, float distance)
+{
+	rt_hit_id id = { -1, -1, -1, -1, distance };
+	if (h == RT_ID_NONE) return id;
+	if (h & RT_ID_TRI)
+	{
+		const uint32_t t = h & 0x0FFFFFFFu;
+		for (const rt_model &M : c->models)
+			for (uint32_t q = 0; q < M.part_count; ++q)
+			{
+				const rt_part &P = c->parts[M.part_begin + q];
+				if (t >= P.tri_begin && t < P.tri_begin + P.tri_count)
+				{
+					id.object = (int32_t)M.object, id.sub = (int32_t)q, id.index = (int32_t)(t - P.tri_begin), id.octant = (int32_t)((h >> 28) & 7u);
+					return id;
+				}
+			}
+	}
+	else if (h < c->prims.size())
+		id.object = (int32_t)c->prims[h].object, id.sub = (int32_t)c->prims[h].sub;
+	return id;
+}
+
+extern "C" int rt_intersect_object(rt_ctx *c, uint32_t object, const rt_ray *rays, const rt_hit *in, float min, rt_hit *out, uint32_t n)
+{
+	if (!c || !rays || !in || !out) return fail(RT_E_INVALID, "rt_intersect_object: NULL argument");
+	if (!c->hasScene) return fail(RT_E_STATE, "rt_intersect_object: no scene uploaded");
+	CU(cudaSetDevice(c->device));
+	if (c->frameInFlight) { int rc = finish_frame(c); if (rc != RT_OK) return rc; }
+	uint32_t p0 = 0, p1 = 0;
+	int model = -1;
+	for (size_t p = 0; p < c->prims.size(); ++p)
+		if (c->prims[p].object == object) { if (p1 == 0) p0 = (uint32_t)p; p1 = (uint32_t)p + 1; }
+	for (size_t m = 0; m < c->models.size(); ++m)
+		if (c->models[m].object == object) model = (int)m;
+	if (p1 == 0 && model < 0) return fail(RT_E_INVALID, "rt_intersect_object: object %u is not part of the uploaded scene (hidden or out of range)", object);
+	std::vector<uint32_t> skip(n), ids(n);
+	for (uint32_t i = 0; i < n; ++i) skip[i] = encode_id(c, in[i].id);
+	DevBuf<uint8_t> dRays, dIn, dOut;
+	DevBuf<uint32_t> dSkip, dIds;
+	cudaStream_t st = c->stream;
+	static_assert(sizeof(rt_ray) == 48 && sizeof(rt_hit) == 80, "rt_ray / rt_hit layout");
+	CU(dRays.upload((const uint8_t *)rays, sizeof(rt_ray) * (size_t)n, st));
+	CU(dIn.upload((const uint8_t *)in, sizeof(rt_hit) * (size_t)n, st));
+	CU(dSkip.upload(skip.data(), n, st));
+	CU(dOut.reserve(sizeof(rt_hit) * (size_t)n));
+	CU(dIds.reserve(n));
+	rtk_intersect_object(st, c->S, p0, p1, model, dRays.p, dIn.p, dSkip.p, min, dIds.p, dOut.p, n);
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(out, dOut.p, sizeof(rt_hit) * (size_t)n, cudaMemcpyDeviceToHost, st));
+	CU(cudaMemcpyAsync(ids.data(), dIds.p, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	for (uint32_t i = 0; i < n; ++i)
+		if (ids[i] != RT_ID_NONE && out[i].id.distance < in[i].id.distance)
+			out[i].id = decode_id(c, ids[i], out[i].id.distance);
+		else
+			out[i] = in[i];
+	dRays.release(), dIn.release(), dOut.release(), dSkip.release(), dIds.release();
+	return RT_OK;
+}
+
 extern "C" int rt_read_hit_ids(rt_ctx *c, rt_hit_id *ids)
 {
 	if (!c || !ids) return fail(RT_E_INVALID, "rt_read_hit_ids: NULL argument");

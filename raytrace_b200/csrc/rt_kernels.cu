@@ -825,6 +825,85 @@ __global__ void __launch_bounds__(128) k_debug(SceneDev S, const FrameParams *__
 	}
 }
 
+// ---- B2: DrawObject::intersect of one object, reference order, no BVH ------------------------------
+struct DevRay { float4 origin, direction; float mtlrfr; uint32_t type, is_inside, pad0; };
+struct DevHit { float4 position, normal; float tu, tv; int material, texture; int id_object, id_sub, id_index, id_octant; float distance; float rfr; uint32_t is_inside, pad0; };
+
+__global__ void k_intersect_object(SceneDev S, uint32_t primBegin, uint32_t primEnd, int modelIndex, const DevRay *rays, const DevHit *in,
+	const uint32_t *skipIds, float minT, uint32_t *outIds, DevHit *out, uint32_t n)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	RayD ray;
+	ray.o = f3(rays[i].origin), ray.d = f3(rays[i].direction), ray.mtlrfr = rays[i].mtlrfr;
+	ray.skip = skipIds[i], ray.type = (uint8_t)rays[i].type, ray.isInside = (uint8_t)rays[i].is_inside;
+	const float hrDistance = in[i].distance;
+	Best best = { hrDistance, RT_ID_NONE, ray.skip };
+	bool done = false;
+	// Sphere / Box / Plane, and BallPlane as its 16 slots in loop order (Basic3DObject.cpp:486-552)
+	for (uint32_t p = primBegin; p < primEnd; ++p)
+		test_prim<false>(S, ray, p, false, best, done);
+	if (modelIndex >= 0)
+	{
+		// Model::intersect verbatim (Model.cpp:748-811): parts, enabled octants, triangles in file order
+		const DevModel &M = S.models[modelIndex];
+		const F3 idir = f3(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
+		float ans = border_test(ray.o, ray.d, idir, f3(M.border_min), f3(M.border_max));
+		if (ans < hrDistance)
+		{
+			ans = hrDistance;
+			bool stop = false;
+			for (uint32_t a = M.part_begin; a < M.part_begin + M.part_count && !stop; ++a)
+			{
+				const DevPart &P = S.parts[a];
+				uint32_t mask;
+				if (!(border_test_ex(ray.o, ray.d, idir, f3(P.box_min), f3(P.box_max), &mask) < hrDistance))
+					continue;
+				for (uint32_t b = 0; b < 8 && !stop; ++b)
+				{
+					if (!(mask & (1u << b)))
+						continue;
+					for (uint32_t k = 0; k < P.tri_count && !stop; ++k)
+					{
+						const uint32_t tri = P.tri_begin + k, slot = S.tri_slot[tri];
+						const float4 g0 = S.tri_geom[3 * slot], g1 = S.tri_geom[3 * slot + 1], g2 = S.tri_geom[3 * slot + 2];
+						if (!(__float_as_uint(g1.w) & (1u << b)))
+							continue;   // not in this octant's list
+						const uint32_t id = RT_ID_TRI | (b << 28) | tri;
+						if (ray.skip == id)
+							continue;
+						const float t = triangle_t(ray.o, ray.d, f3(g0), f3(g1), f3(g2), nullptr);
+						if (t < ans)
+						{
+							ans = t;
+							best.t = t, best.id = best.newobj = id;
+							if (t < minT)
+								stop = true;
+						}
+					}
+				}
+			}
+		}
+	}
+	outIds[i] = best.id;
+	DevHit h = in[i];
+	if (best.id != RT_ID_NONE && best.t < hrDistance)
+	{
+		const F3 P = ray.o + ray.d * best.t;
+		const Surface sf = surface_attributes(S, ray, P, best.id);
+		h.position = make_float4(P.x, P.y, P.z, 0), h.normal = make_float4(sf.N.x, sf.N.y, sf.N.z, 0);
+		h.tu = sf.tu, h.tv = sf.tv, h.material = sf.mtl, h.texture = sf.tex;
+		h.distance = best.t, h.rfr = sf.rfr, h.is_inside = sf.isInside;
+	}
+	out[i] = h;
+}
+
+void rtk_intersect_object(cudaStream_t st, const SceneDev &S, uint32_t primBegin, uint32_t primEnd, int modelIndex, const void *rays, const void *in,
+	const uint32_t *skipIds, float minT, uint32_t *outIds, void *out, uint32_t n)
+{
+	if (n) k_intersect_object<<<(n + 127) / 128, 128, 0, st>>>(S, primBegin, primEnd, modelIndex, (const DevRay *)rays, (const DevHit *)in, skipIds, minT, outIds, (DevHit *)out, n);
+}
+
 // ---- end of frame: hit_list doubles as the publication flag of a surface (0 = not written) --------
 __global__ void k_reset_hits(LevelSet LS, const WaveState *__restrict__ ws)
 {

@@ -2,6 +2,8 @@
 #include "SceneUpload.h"
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
+#include <mutex>
 #include <stdexcept>
 
 static void fail(const char *what, int code)
@@ -30,8 +32,17 @@ static void free_output(uint8_t *p, bool pinned)
 	else delete[] p;
 }
 
+// Every live RayTracer, so that DrawObject::intersect (which has no back pointer) can find the
+// device context its Scene is attached to.
+static std::mutex g_tracersMutex;
+static std::vector<RayTracer *> g_tracers;
+
 RayTracer::RayTracer(Scene &scene) : scene(&scene)
 {
+	{
+		std::lock_guard<std::mutex> lock(g_tracersMutex);
+		g_tracers.push_back(this);
+	}
 	outputBytes = (size_t)2048 * 2048 * 3;   // the reference's fixed framebuffer, RayTracer.cpp:603
 	output = new uint8_t[outputBytes];       // plain memory here (no CUDA call during static init);
 	memset(output, 127, outputBytes);        // swapped for page-locked memory by the first start()
@@ -39,6 +50,10 @@ RayTracer::RayTracer(Scene &scene) : scene(&scene)
 
 RayTracer::~RayTracer()
 {
+	{
+		std::lock_guard<std::mutex> lock(g_tracersMutex);
+		g_tracers.erase(std::remove(g_tracers.begin(), g_tracers.end(), this), g_tracers.end());
+	}
 	if (monitor.joinable())
 		monitor.join();
 	if (ctx)
@@ -135,10 +150,98 @@ bool RayTracer::readCounters(rt_counters *out)
 	return ctx && rt_read_counters(ctx, out) == RT_OK;
 }
 
-// DrawObject::intersect on the host: the operator lives on the GPU; a host-side caller gets a
-// clear failure instead of a silent CPU path.
-HitRes DrawObject::intersect(const Ray &, const HitRes &, const float)
+// ---- B2: the per-primitive operator, evaluated on the device ----------------------------------------
+// HitRes::obj of a Model hit cannot be a clTri address here (the octant lists live on the GPU); it is
+// an opaque tagged value that only has to survive a round trip through hr.obj.
+static const intptr_t kTriTag = (intptr_t)1 << 62;
+
+static intptr_t encodeObj(const Scene &scene, const rt_hit_id &id)
 {
-	throw std::runtime_error("raytrace_b200: DrawObject::intersect runs on the GPU only (see include/rt_b200.h); "
-		"there is no CPU implementation in this build");
+	if (id.object < 0 || id.object >= (int)scene.Objects.size()) return 0;
+	DrawObject *o = scene.Objects[id.object];
+	if (o->type == MY_OBJECT_MODEL)
+		return kTriTag | ((intptr_t)id.object << 33) | ((intptr_t)(id.octant & 7) << 30) | ((intptr_t)(id.sub & 0x7FFF) << 15) | (intptr_t)(id.index & 0x7FFF);
+	return (intptr_t)o + id.sub;   // Sphere/Box/Plane: this; BallPlane: this + cnt (Basic3DObject.cpp:538)
+}
+
+static rt_hit_id decodeObj(const Scene &scene, intptr_t obj, float distance)
+{
+	rt_hit_id id = { -1, -1, -1, -1, distance };
+	if (obj & kTriTag)
+	{
+		id.object = (int32_t)((obj >> 33) & 0xFFFF), id.octant = (int32_t)((obj >> 30) & 7);
+		id.sub = (int32_t)((obj >> 15) & 0x7FFF), id.index = (int32_t)(obj & 0x7FFF);
+		return id;
+	}
+	for (size_t i = 0; i < scene.Objects.size(); ++i)
+	{
+		const intptr_t base = (intptr_t)scene.Objects[i];
+		const intptr_t span = scene.Objects[i]->type == MY_OBJECT_BALLPLANE ? 16 : 0;
+		if (obj >= base && obj <= base + span)
+		{
+			id.object = (int32_t)i, id.sub = (int32_t)(obj - base);
+			return id;
+		}
+	}
+	return id;
+}
+
+HitRes RayTracer::intersectObject(uint32_t index, const Ray &ray, const HitRes &hr, const float min)
+{
+	wait();
+	ensureContext();
+	for (DrawObject *o : scene->Objects)
+		if (o->bShow)
+			o->RTPrepare();
+	rt_scene_desc desc;
+	flattener->flatten(*scene, desc);
+	int rc = rt_upload_scene(ctx, &desc);   // no-op when nothing changed since the last frame
+	if (rc != RT_OK)
+		fail("rt_upload_scene", rc);
+	rt_ray r;
+	memset(&r, 0, sizeof r);
+	r.origin = rt_vec4{ ray.origin.x, ray.origin.y, ray.origin.z, ray.origin.w };
+	r.direction = rt_vec4{ ray.direction.x, ray.direction.y, ray.direction.z, ray.direction.w };
+	r.mtlrfr = ray.mtlrfr, r.type = ray.type, r.is_inside = ray.isInside;
+	rt_hit in, out;
+	memset(&in, 0, sizeof in);
+	in.material = in.texture = -1;
+	in.id = decodeObj(*scene, hr.obj, hr.distance);
+	rc = rt_intersect_object(ctx, index, &r, &in, min, &out, 1);
+	if (rc != RT_OK)
+		fail("rt_intersect_object", rc);
+	if (!(out.id.distance < hr.distance))
+		return hr;   // `return hr` of every reference operator
+	HitRes nh(out.id.distance);
+	nh.position = Vertex(out.position.x, out.position.y, out.position.z);
+	nh.normal.x = out.normal.x, nh.normal.y = out.normal.y, nh.normal.z = out.normal.z;
+	nh.tcoord = Coord2D(out.tu, out.tv);
+	nh.mtl = out.material >= 0 ? const_cast<Material *>(flattener->materialPtrs[out.material]) : nullptr;
+	nh.tex = out.texture >= 0 ? const_cast<Texture *>(flattener->texturePtrs[out.texture]) : nullptr;
+	nh.obj = encodeObj(*scene, out.id);
+	nh.rfr = out.rfr, nh.isInside = (uint8_t)out.is_inside;
+	return nh;
+}
+
+// DrawObject::intersect (3DElement.h:201).  The operator of every shipped primitive lives on the GPU:
+// the call is forwarded, for this one ray, to the device context of the RayTracer whose Scene holds
+// the object.  An object that belongs to no such Scene cannot be evaluated: loud failure, no CPU path.
+HitRes DrawObject::intersect(const Ray &ray, const HitRes &hr, const float min)
+{
+	RayTracer *owner = nullptr;
+	uint32_t index = 0;
+	{
+		std::lock_guard<std::mutex> lock(g_tracersMutex);
+		for (RayTracer *t : g_tracers)
+		{
+			const std::vector<DrawObject *> &objs = t->attachedScene()->Objects;
+			for (size_t i = 0; i < objs.size() && !owner; ++i)
+				if (objs[i] == this) owner = t, index = (uint32_t)i;
+			if (owner) break;
+		}
+	}
+	if (!owner)
+		throw std::runtime_error("raytrace_b200: DrawObject::intersect needs the object to be in a Scene that has a RayTracer "
+			"(the operator runs on the GPU, include/rt_b200.h rt_intersect_object); there is no CPU implementation");
+	return owner->intersectObject(index, ray, hr, min);
 }

@@ -53,4 +53,7 @@ public:
 	bool readHitIds(rt_hit_id *ids);           // primary closest-hit identities of the last frame
 	bool readCounters(rt_counters *out);
 	rt_ctx *context() { ensureContext(); return ctx; }
+	// DrawObject::intersect of Objects[index], evaluated on the device (rt_intersect_object)
+	HitRes intersectObject(uint32_t index, const Ray &ray, const HitRes &hr, const float min);
+	Scene *attachedScene() const { return scene; }
 };

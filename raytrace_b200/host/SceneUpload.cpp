@@ -9,6 +9,7 @@ uint32_t SceneFlattener::addMaterial(const Material &m)
 	r.ambient = v4(m.ambient), r.diffuse = v4(m.diffuse), r.specular = v4(m.specular), r.emission = v4(m.emission);
 	r.shiness = m.shiness, r.reflect = m.reflect, r.refract = m.refract, r.rfr = m.rfr;
 	materials.push_back(r);
+	materialPtrs.push_back(&m);
 	return (uint32_t)materials.size() - 1;
 }
 
@@ -23,12 +24,13 @@ int32_t SceneFlattener::addTexture(const Texture &t)
 	texels.insert(texels.end(), t.data, t.data + (size_t)t.w * t.h * 3);
 	texels.insert(texels.end(), 4, 0);
 	textures.push_back(r);
+	texturePtrs.push_back(&t);
 	return (int32_t)textures.size() - 1;
 }
 
 void SceneFlattener::flatten(const Scene &scene, rt_scene_desc &desc)
 {
-	lights.clear(), materials.clear(), textures.clear(), texels.clear();
+	lights.clear(), materials.clear(), textures.clear(), texels.clear(), materialPtrs.clear(), texturePtrs.clear();
 	prims.clear(), models.clear(), parts.clear();
 
 	memset(&desc, 0, sizeof desc);

@@ -12,6 +12,11 @@ public:
 	// Heavy triangle arrays are only rebuilt when some Model's epoch changed.
 	void flatten(const Scene &scene, rt_scene_desc &desc);
 
+	// what the material / texture indices of the last flatten() refer to (for mapping device hits
+	// back to HitRes::mtl / HitRes::tex pointers)
+	std::vector<const Material *> materialPtrs;
+	std::vector<const Texture *> texturePtrs;
+
 private:
 	std::vector<rt_light> lights;
 	std::vector<rt_material> materials;

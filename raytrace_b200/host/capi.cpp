@@ -150,6 +150,39 @@ void rth_tracer_set_shard(void *t, int rank, int world, int tileRows)
 void rth_tracer_set_flags(void *t, unsigned flags) { ((RayTracer *)t)->renderFlags = flags; }
 int rth_tracer_read_hit_ids(void *t, rt_hit_id *ids) { return ((RayTracer *)t)->readHitIds(ids) ? 0 : -1; }
 int rth_tracer_read_counters(void *t, rt_counters *c) { return ((RayTracer *)t)->readCounters(c) ? 0 : -1; }
+// B2 through the C++ classes: scene.Objects[index]->intersect(ray, hr, min).  `hit` is in/out: on
+// entry hit->id / hit->id.distance describe hr (obj + distance), on exit the returned HitRes.
+int rth_object_intersect(void *scene, int index, const rt_ray *ray, rt_hit *hit, float min)
+{
+	return guarded([&]
+	{
+		Scene &s = ((HostScene *)scene)->scene;
+		if (index < 0 || index >= (int)s.Objects.size()) throw std::runtime_error("object index out of range");
+		Ray r(Vertex(ray->origin.x, ray->origin.y, ray->origin.z, ray->origin.w),
+			Normal(ray->direction.x, ray->direction.y, ray->direction.z, ray->direction.w), (uint8_t)ray->type);
+		r.mtlrfr = ray->mtlrfr, r.isInside = (uint8_t)ray->is_inside;
+		HitRes hr(hit->id.distance);
+		// hr.obj: rebuild the pointer-style identity the classes use
+		if (hit->id.object >= 0 && hit->id.object < (int)s.Objects.size())
+		{
+			DrawObject *o = s.Objects[hit->id.object];
+			hr.obj = o->type == MY_OBJECT_MODEL
+				? ((intptr_t)1 << 62) | ((intptr_t)hit->id.object << 33) | ((intptr_t)(hit->id.octant & 7) << 30) | ((intptr_t)(hit->id.sub & 0x7FFF) << 15) | (intptr_t)(hit->id.index & 0x7FFF)
+				: (intptr_t)o + hit->id.sub;
+		}
+		const HitRes res = s.Objects[index]->intersect(r, hr, min);
+		hit->id.distance = res.distance;
+		if (res.distance < hr.distance)
+		{
+			hit->position = rt_vec4{ res.position.x, res.position.y, res.position.z, 0 };
+			hit->normal = rt_vec4{ res.normal.x, res.normal.y, res.normal.z, 0 };
+			hit->tu = res.tcoord.u, hit->tv = res.tcoord.v, hit->rfr = res.rfr, hit->is_inside = res.isInside;
+			hit->material = res.mtl ? 1 : -1, hit->texture = res.tex ? 1 : -1;   // presence only: pointers do not cross the shim
+			hit->id.object = -2;   // identity is pointer-valued on this path; tests compare geometry
+		}
+	});
+}
+
 void *rth_tracer_context(void *t)
 {
 	void *c = nullptr;
