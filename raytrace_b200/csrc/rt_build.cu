@@ -1,12 +1,16 @@
-// GPU LBVH build: Morton codes -> radix sort -> Karras (2012) hierarchy -> bottom-up refit that
-// emits 64-byte two-child nodes.  Replaces the reference's per-frame, single-threaded octant
+// GPU LBVH build: Morton codes -> radix sort (hand-written LSD, 8 bits per pass) -> Karras (2012)
+// hierarchy -> bottom-up refit that emits 64-byte two-child nodes -> collapse to 4-wide nodes.  Replaces the reference's per-frame, single-threaded octant
 // binning (Model::RTPrepare, /root/reference/Model.cpp:402-480); the octant membership itself is
 // still computed (bit-exactly) per triangle in k_prepare_tris because the traversal replays the
 // reference's culling predicate with it.
 #include "rt_kernels.h"
 #include "rt_intersect.cuh"
-#include <cub/device/device_radix_sort.cuh>
 #include <cstdio>
+
+// radix sort tiling (see radix_sort_pairs)
+#define RS_THREADS 256
+#define RS_ROUNDS 16
+#define RS_TILE (RS_THREADS * RS_ROUNDS)
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
 
@@ -15,8 +19,7 @@ struct BuildScratch
 	uint32_t cap = 0;
 	unsigned long long *keysIn = nullptr, *keysOut = nullptr;
 	uint32_t *valsIn = nullptr, *valsOut = nullptr;
-	void *cubTemp = nullptr;
-	size_t cubBytes = 0;
+	uint32_t *sortHist = nullptr;   // radix sort: [256 digits][blocks] counts, then exclusive offsets
 	int *bounds = nullptr;          // 6 ordered-int floats: min xyz, max xyz
 	int *parentOfInternal = nullptr, *parentOfLeaf = nullptr;
 	int2 *children = nullptr;       // per internal: left, right (>=0 internal, <0: ~leaf)
@@ -29,7 +32,7 @@ struct BuildScratch
 void rtb_free_scratch(BuildScratch *s)
 {
 	if (!s) return;
-	cudaFree(s->keysIn), cudaFree(s->keysOut), cudaFree(s->valsIn), cudaFree(s->valsOut), cudaFree(s->cubTemp);
+	cudaFree(s->keysIn), cudaFree(s->keysOut), cudaFree(s->valsIn), cudaFree(s->valsOut), cudaFree(s->sortHist);
 	cudaFree(s->bounds), cudaFree(s->parentOfInternal), cudaFree(s->parentOfLeaf), cudaFree(s->children), cudaFree(s->range);
 	cudaFree(s->flags), cudaFree(s->ilo), cudaFree(s->ihi), cudaFree(s->height);
 	delete s;
@@ -41,7 +44,7 @@ static int ensure_scratch(BuildScratch **ps, uint32_t n)
 	BuildScratch *s = *ps;
 	if (n <= s->cap) return 0;
 	BuildScratch fresh;
-	cudaFree(s->keysIn), cudaFree(s->keysOut), cudaFree(s->valsIn), cudaFree(s->valsOut), cudaFree(s->cubTemp);
+	cudaFree(s->keysIn), cudaFree(s->keysOut), cudaFree(s->valsIn), cudaFree(s->valsOut), cudaFree(s->sortHist);
 	cudaFree(s->bounds), cudaFree(s->parentOfInternal), cudaFree(s->parentOfLeaf), cudaFree(s->children), cudaFree(s->range);
 	cudaFree(s->flags), cudaFree(s->ilo), cudaFree(s->ihi), cudaFree(s->height);
 	*s = fresh;
@@ -50,9 +53,7 @@ static int ensure_scratch(BuildScratch **ps, uint32_t n)
 	CK(cudaMalloc(&s->keysOut, sizeof(unsigned long long) * cap));
 	CK(cudaMalloc(&s->valsIn, sizeof(uint32_t) * cap));
 	CK(cudaMalloc(&s->valsOut, sizeof(uint32_t) * cap));
-	s->cubBytes = 0;
-	cub::DeviceRadixSort::SortPairs(nullptr, s->cubBytes, s->keysIn, s->keysOut, s->valsIn, s->valsOut, (int)cap);
-	CK(cudaMalloc(&s->cubTemp, s->cubBytes));
+	CK(cudaMalloc(&s->sortHist, sizeof(uint32_t) * 256 * ((cap + RS_TILE - 1) / RS_TILE + 1)));
 	CK(cudaMalloc(&s->bounds, sizeof(int) * 8));
 	CK(cudaMalloc(&s->parentOfInternal, sizeof(int) * cap));
 	CK(cudaMalloc(&s->parentOfLeaf, sizeof(int) * cap));
@@ -198,6 +199,110 @@ __global__ void k_morton(const float4 *lo, const float4 *hi, uint32_t n, const i
 	const unsigned long long qz = (unsigned long long)fminf(fmaxf(fz * scale, 0.0f), scale);
 	keys[i] = spread21(qx) << 2 | spread21(qy) << 1 | spread21(qz);
 	vals[i] = i;
+}
+
+// ---- radix sort of (64-bit Morton key, 32-bit index) pairs ------------------------------------------
+// Least-significant-digit first, 8 bits per pass, 8 passes, stable.  Per pass: (1) every block
+// histograms its tile of RS_TILE keys, (2) one block turns the [digit][block] counts into exclusive
+// offsets, (3) every block re-reads its tile in order and scatters: within a round of 256 keys a
+// key's rank is (keys with its digit in earlier warps of the round) + (earlier lanes of its warp
+// with that digit, __match_any_sync), on top of the block's running offset for the digit.
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const unsigned long long *keys, uint32_t n, int shift, uint32_t *hist, uint32_t nBlocks)
+{
+	__shared__ uint32_t h[256];
+	h[threadIdx.x] = 0;
+	__syncthreads();
+	const uint32_t base = blockIdx.x * RS_TILE;
+	for (uint32_t r = 0; r < RS_ROUNDS; ++r)
+	{
+		const uint32_t i = base + r * RS_THREADS + threadIdx.x;
+		if (i < n) atomicAdd(&h[(uint32_t)(keys[i] >> shift) & 255u], 1u);
+	}
+	__syncthreads();
+	hist[threadIdx.x * nBlocks + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(1024) k_rs_scan(uint32_t *hist, uint32_t total)
+{
+	// exclusive prefix sum over `total` = 256 * nBlocks counters (digit-major), one block
+	__shared__ uint32_t part[1024];
+	const uint32_t per = (total + 1023u) / 1024u;
+	const uint32_t lo = threadIdx.x * per, hi = min(lo + per, total);
+	uint32_t sum = 0;
+	for (uint32_t i = lo; i < hi; ++i) sum += hist[i];
+	part[threadIdx.x] = sum;
+	__syncthreads();
+	for (uint32_t off = 1; off < 1024; off <<= 1)
+	{
+		const uint32_t v = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+		__syncthreads();
+		part[threadIdx.x] += v;
+		__syncthreads();
+	}
+	uint32_t run = part[threadIdx.x] - sum;
+	for (uint32_t i = lo; i < hi; ++i)
+	{
+		const uint32_t c = hist[i];
+		hist[i] = run;
+		run += c;
+	}
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const unsigned long long *keysIn, const uint32_t *valsIn, unsigned long long *keysOut,
+	uint32_t *valsOut, uint32_t n, int shift, const uint32_t *hist, uint32_t nBlocks)
+{
+	__shared__ uint32_t offset[256];           // next free output slot per digit for this block
+	__shared__ uint32_t warpCount[8][256];     // per round: keys per (warp, digit)
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	offset[threadIdx.x] = hist[threadIdx.x * nBlocks + blockIdx.x];
+	const uint32_t base = blockIdx.x * RS_TILE;
+	for (uint32_t r = 0; r < RS_ROUNDS; ++r)
+	{
+		for (uint32_t w = 0; w < 8; ++w) warpCount[w][threadIdx.x] = 0;
+		__syncthreads();
+		const uint32_t i = base + r * RS_THREADS + threadIdx.x;
+		const bool valid = i < n;
+		unsigned long long key = 0;
+		uint32_t val = 0, digit = 0xFFFFFFFFu;
+		if (valid) key = keysIn[i], val = valsIn[i], digit = (uint32_t)(key >> shift) & 255u;
+		const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+		const uint32_t rankInWarp = __popc(peers & ((1u << lane) - 1u));
+		if (valid && rankInWarp == 0) warpCount[warp][digit] = __popc(peers);
+		__syncthreads();
+		uint32_t before = 0;
+		if (valid)
+		{
+			for (uint32_t w = 0; w < warp; ++w) before += warpCount[w][digit];
+			const uint32_t dst = offset[digit] + before + rankInWarp;
+			keysOut[dst] = key, valsOut[dst] = val;
+		}
+		__syncthreads();
+		uint32_t add = 0;
+		for (uint32_t w = 0; w < 8; ++w) add += warpCount[w][threadIdx.x];
+		offset[threadIdx.x] += add;
+		__syncthreads();
+	}
+}
+
+static void radix_sort_pairs(cudaStream_t st, BuildScratch *s, uint32_t n)
+{
+	const uint32_t nBlocks = (n + RS_TILE - 1) / RS_TILE;
+	unsigned long long *kin = s->keysIn, *kout = s->keysOut;
+	uint32_t *vin = s->valsIn, *vout = s->valsOut;
+	for (int pass = 0; pass < 8; ++pass)
+	{
+		const int shift = 8 * pass;
+		k_rs_hist<<<nBlocks, RS_THREADS, 0, st>>>(kin, n, shift, s->sortHist, nBlocks);
+		k_rs_scan<<<1, 1024, 0, st>>>(s->sortHist, 256u * nBlocks);
+		k_rs_scatter<<<nBlocks, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, shift, s->sortHist, nBlocks);
+		unsigned long long *tk = kin; kin = kout; kout = tk;
+		uint32_t *tv = vin; vin = vout; vout = tv;
+	}
+	// 8 passes: the sorted data are back in the buffers the sort started from; the callers read
+	// keysOut / valsOut, so swap the names
+	unsigned long long *tk = s->keysIn; s->keysIn = s->keysOut; s->keysOut = tk;
+	uint32_t *tv = s->valsIn; s->valsIn = s->valsOut; s->valsOut = tv;
 }
 
 // ---- Karras hierarchy ----------------------------------------------------------------------------
@@ -375,8 +480,7 @@ int rtb_build(cudaStream_t st, BuildScratch **scratch, const float4 *box_lo, con
 	k_init_bounds<<<1, 32, 0, st>>>(s->bounds);
 	k_bounds<<<blocks < 1024 ? blocks : 1024, 256, 0, st>>>(box_lo, box_hi, n, s->bounds);
 	k_morton<<<blocks, 256, 0, st>>>(box_lo, box_hi, n, s->bounds, s->keysIn, s->valsIn);
-	size_t bytes = s->cubBytes;
-	CK(cub::DeviceRadixSort::SortPairs(s->cubTemp, bytes, s->keysIn, s->keysOut, s->valsIn, s->valsOut, (int)n, 0, 63, st));
+	radix_sort_pairs(st, s, n);   // result in keysOut / valsOut
 	k_copy_order<<<blocks, 256, 0, st>>>(s->valsOut, n, leafOrder);
 	if (n <= leafSize)
 	{

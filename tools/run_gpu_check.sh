@@ -1,1 +1,2 @@
-timeout 900 python -m pytest tests/test_gpu_intersect_operator.py -x -q -m gpu 2>&1 | tail -15
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -2
+python tools/perf_probe.py c3 c4 2>&1 | cut -c1-330
