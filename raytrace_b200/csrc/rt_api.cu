@@ -887,6 +887,9 @@ extern "C" int rt_read_counters(rt_ctx *c, rt_counters *out)
 		fprintf(stderr, "\n                                          shadow:");
 		for (int b = 12; b < 24; ++b) fprintf(stderr, " %u", W.node_hist[b]);
 		fprintf(stderr, "\n");
+		if (W.lane_cap[0] || W.lane_cap[1])
+			fprintf(stderr, "lane utilisation bound (sum nodes / 32 x longest lane per batch): closest %.3f shadow %.3f\n",
+				W.lane_cap[0] ? (double)W.lane_sum[0] / (double)W.lane_cap[0] : 0.0, W.lane_cap[1] ? (double)W.lane_sum[1] / (double)W.lane_cap[1] : 0.0);
 	}
 	out->render_ms = c->renderMs;
 	out->trace_ms = c->traceMs, out->shadow_ms = c->shadowMs, out->shade_ms = c->shadeMs, out->other_ms = c->otherMs;

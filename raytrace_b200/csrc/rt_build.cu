@@ -6,6 +6,8 @@
 #include "rt_kernels.h"
 #include "rt_intersect.cuh"
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
 // radix sort tiling (see radix_sort_pairs)
 #define RS_THREADS 256
@@ -185,12 +187,17 @@ __device__ __forceinline__ unsigned long long spread21(unsigned long long v)
 	return v;
 }
 
-__global__ void k_morton(const float4 *lo, const float4 *hi, uint32_t n, const int *b, unsigned long long *keys, uint32_t *vals)
+// cube != 0: all three axes are quantised with the LARGEST extent, so Morton cells are cubes in world
+// space.  Per-axis normalisation (cube == 0) splits a flat mesh (a height field) by height as often as
+// by x and z, which yields sibling boxes that overlap almost completely in the ground plane.
+__global__ void k_morton(const float4 *lo, const float4 *hi, uint32_t n, const int *b, unsigned long long *keys, uint32_t *vals, int cube)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const float bx = ord2f(b[0]), by = ord2f(b[1]), bz = ord2f(b[2]);
-	const float ex = fmaxf(ord2f(b[3]) - bx, 1e-30f), ey = fmaxf(ord2f(b[4]) - by, 1e-30f), ez = fmaxf(ord2f(b[5]) - bz, 1e-30f);
+	float ex = fmaxf(ord2f(b[3]) - bx, 1e-30f), ey = fmaxf(ord2f(b[4]) - by, 1e-30f), ez = fmaxf(ord2f(b[5]) - bz, 1e-30f);
+	if (cube)
+		ex = ey = ez = fmaxf(ex, fmaxf(ey, ez));
 	const float4 l = lo[i], h = hi[i];
 	const float scale = 2097151.0f;   // 2^21 - 1
 	const float fx = (0.5f * (l.x + h.x) - bx) / ex, fy = (0.5f * (l.y + h.y) - by) / ey, fz = (0.5f * (l.z + h.z) - bz) / ez;
@@ -479,7 +486,8 @@ int rtb_build(cudaStream_t st, BuildScratch **scratch, const float4 *box_lo, con
 	const unsigned blocks = (n + 255) / 256;
 	k_init_bounds<<<1, 32, 0, st>>>(s->bounds);
 	k_bounds<<<blocks < 1024 ? blocks : 1024, 256, 0, st>>>(box_lo, box_hi, n, s->bounds);
-	k_morton<<<blocks, 256, 0, st>>>(box_lo, box_hi, n, s->bounds, s->keysIn, s->valsIn);
+	static const int mortonCube = []{ const char *e = getenv("RT_B200_MORTON"); return (e && !strcmp(e, "axis")) ? 0 : 1; }();
+	k_morton<<<blocks, 256, 0, st>>>(box_lo, box_hi, n, s->bounds, s->keysIn, s->valsIn, mortonCube);
 	radix_sort_pairs(st, s, n);   // result in keysOut / valsOut
 	k_copy_order<<<blocks, 256, 0, st>>>(s->valsOut, n, leafOrder);
 	if (n <= leafSize)

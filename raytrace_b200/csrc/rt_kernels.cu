@@ -21,6 +21,7 @@
 // arithmetic is bit-identical to the recursive evaluation order.
 #include "rt_traverse.cuh"
 #include "rt_kernels.h"
+#include <cstdlib>
 
 // ---- helpers -------------------------------------------------------------------------------------
 
@@ -93,6 +94,24 @@ __device__ __forceinline__ void flush_stats(WaveState *ws, const TravStats &st)
 		atomicAdd(&ws->nodes_visited, n);
 		atomicAdd(&ws->tri_tests, t);
 		atomicAdd(&ws->prim_tests, p);
+	}
+}
+
+// RT_FLAG_STATS: SIMT utilisation a batch could reach at best = sum of the lanes' node visits / (32 x the longest lane)
+template<bool STATS>
+__device__ __forceinline__ void lane_stats(WaveState *ws, uint32_t kind, uint32_t mine)
+{
+	if (!STATS) return;
+	uint32_t s = mine, m = mine;
+	for (int o = 16; o > 0; o >>= 1)
+	{
+		s += __shfl_xor_sync(0xffffffffu, s, o);
+		m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+	}
+	if ((threadIdx.x & 31) == 0)
+	{
+		atomicAdd(&ws->lane_sum[kind], (unsigned long long)s);
+		atomicAdd(&ws->lane_cap[kind], 32ull * m);
 	}
 }
 
@@ -229,8 +248,8 @@ __device__ __forceinline__ Surface surface_attributes(const SceneDev &S, const R
 
 // ---- fused wave kernel: closest hit of level `level` + shadow rays of level `level - 1` -------------
 
-template<bool STATS>
-__global__ void __launch_bounds__(RT_BLOCK, RT_CTAS_PER_SM) k_wave(SceneDev S, const FrameParams *__restrict__ Fp, LevelBuf L, LevelBuf N, LevelBuf Lprev,
+template<bool STATS, int CTAS>
+__global__ void __launch_bounds__(RT_BLOCK, CTAS) k_wave(SceneDev S, const FrameParams *__restrict__ Fp, LevelBuf L, LevelBuf N, LevelBuf Lprev,
 	WaveState *ws, uint32_t level, uint32_t traceOn, uint32_t shadowOn, float zNear)
 {
 	const FrameParams &F = *Fp;
@@ -409,8 +428,8 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_CTAS_PER_SM) k_wave(SceneDev S, c
 // "outstanding == 0" means the frame is complete and every warp may leave.
 __device__ __forceinline__ uint32_t vload(const uint32_t *p) { return *(const volatile uint32_t *)p; }
 
-template<bool STATS>
-__global__ void __launch_bounds__(RT_BLOCK, RT_CTAS_PER_SM) k_frame(SceneDev S, const FrameParams *__restrict__ Fp, LevelSet LS, WaveState *ws)
+template<bool STATS, int CTAS>
+__global__ void __launch_bounds__(RT_BLOCK, CTAS) k_frame(SceneDev S, const FrameParams *__restrict__ Fp, LevelSet LS, WaveState *ws)
 {
 	const FrameParams &F = *Fp;
 	const uint32_t lane = threadIdx.x & 31u;
@@ -423,69 +442,56 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_CTAS_PER_SM) k_frame(SceneDev S, 
 	// blocking the lanes whose work is ready, until it is published or the frame is over.
 	// pKind 0: closest-hit rays of level pLevel; pKind 1: shadow rays of level pLevel towards light pLight.
 	uint32_t pKind = 0, pLevel = 0, pLight = 0, pSlot = 0xFFFFFFFFu;
-	uint32_t hintKind = 0, hintLevel = 0, hintLight = 0;   // leader only: where the last claim succeeded
 	while (true)
 	{
 		if (__ballot_sync(0xffffffffu, pSlot != 0xFFFFFFFFu) == 0u)
 		{
-			// ---- claim (leader decides, broadcasts): rays first (they create work), shallowest level
-			// first; then shadow rays, which are leaves of the dependency graph ---------------------------
+			// ---- claim: the 32 lanes look at one queue each (rays of level q, then shadow rays per (level,
+			// light)), so a claim costs one L2 round trip however many queues there are; the first queue in
+			// that order wins -- rays before shadow rays (rays create work), shallowest level first.  Work is
+			// consumed while it is being produced, so queues are usually short and taking whatever is there
+			// would hand every warp 2-3 rays: pass 0 only takes full batches of 32, pass 1 (nothing full
+			// anywhere) whatever exists, so the tail of the frame still drains. ----------------------------
 			uint32_t kind = 0xFFFFFFFFu, level = 0, light = 0, base = 0, nb = 0;
-			if (lane == 0)
-			{
-				// try where the last claim succeeded first (2 loads + 1 atomic), then scan
-				// Work is consumed while it is being produced, so queues are usually short; taking whatever
-				// is there would hand every warp 2-3 rays.  First pass: only full batches of 32; second
-				// pass (nothing full anywhere): whatever exists, so the tail of the frame still drains.
-				uint32_t minAvail = 32u;
-				auto claimRays = [&](uint32_t l) -> bool
+			const uint32_t nL = F.max_level + 1u, nQ = nL + (wantShadows ? nL * F.n_enabled : 0u);
+			for (int pass = 0; pass < 2 && kind == 0xFFFFFFFFu; ++pass)
+				for (uint32_t q0 = 0; q0 < nQ && kind == 0xFFFFFFFFu; q0 += 32u)
 				{
-					uint32_t cnt = vload(&ws->count[l]);
-					cnt = cnt < LS.l[l].capacity ? cnt : LS.l[l].capacity;
-					const uint32_t h = vload(&ws->head_trace[l]);
-					if (h >= cnt || cnt - h < minAvail)
-						return false;
-					uint32_t want = cnt - h;
-					want = want > 32u ? 32u : want;
-					const uint32_t got = atomicAdd(&ws->head_trace[l], want);
-					if (got >= LS.l[l].capacity)
-						return false;
-					kind = 0, level = l, base = got, nb = want;
-					return true;
-				};
-				auto claimShadow = [&](uint32_t l, uint32_t e) -> bool
-				{
-					const uint32_t cnt = vload(&ws->n_hit[l]);
-					const uint32_t h = vload(&ws->head_light[l][e]);
-					if (h >= cnt || cnt - h < minAvail)
-						return false;
-					uint32_t want = cnt - h;
-					want = want > 32u ? 32u : want;
-					const uint32_t got = atomicAdd(&ws->head_light[l][e], want);
-					if (got >= LS.l[l].capacity)
-						return false;
-					kind = 1, level = l, light = e, base = got, nb = want;
-					return true;
-				};
-				bool ok = false;
-				for (int pass = 0; pass < 2 && !ok; ++pass)
-				{
-					minAvail = pass == 0 ? 32u : 1u;
-					ok = hintKind == 0u ? claimRays(hintLevel) : false;
-					for (uint32_t l = 0; l <= F.max_level && !ok; ++l)
-						ok = claimRays(l);
-					if (wantShadows && !ok)
+					const uint32_t q = q0 + lane;
+					uint32_t avail = 0, qLevel = 0, qLight = 0, cap = 0;
+					uint32_t *head = nullptr;
+					if (q < nQ)
 					{
-						if (hintKind == 1u) ok = claimShadow(hintLevel, hintLight);
-						for (uint32_t l = 0; l <= F.max_level && !ok; ++l)
-							for (uint32_t e = 0; e < F.n_enabled && !ok; ++e)
-								ok = claimShadow(l, e);
+						uint32_t cnt;
+						if (q < nL)
+							qLevel = q, cnt = vload(&ws->count[q]), head = &ws->head_trace[q];
+						else
+						{
+							qLevel = (q - nL) / F.n_enabled, qLight = (q - nL) % F.n_enabled;
+							cnt = vload(&ws->n_hit[qLevel]), head = &ws->head_light[qLevel][qLight];
+						}
+						cap = LS.l[qLevel].capacity;
+						cnt = cnt < cap ? cnt : cap;
+						const uint32_t h = vload(head);
+						avail = h < cnt ? cnt - h : 0u;
+					}
+					uint32_t cand = __ballot_sync(0xffffffffu, pass == 0 ? avail >= 32u : avail > 0u);
+					while (cand && kind == 0xFFFFFFFFu)
+					{
+						const uint32_t src = __ffs((int)cand) - 1u;
+						cand &= cand - 1u;
+						uint32_t got = 0;
+						const uint32_t want = avail > 32u ? 32u : avail;
+						if (lane == src) got = atomicAdd(head, want);
+						got = __shfl_sync(0xffffffffu, got, src);
+						if (got < __shfl_sync(0xffffffffu, cap, src))
+						{
+							kind = src + q0 < nL ? 0u : 1u;
+							level = __shfl_sync(0xffffffffu, qLevel, src), light = __shfl_sync(0xffffffffu, qLight, src);
+							base = got, nb = __shfl_sync(0xffffffffu, want, src);
+						}
 					}
 				}
-				if (ok) hintKind = kind, hintLevel = level, hintLight = light;
-			}
-			kind = __shfl_sync(0xffffffffu, kind, 0), level = __shfl_sync(0xffffffffu, level, 0), light = __shfl_sync(0xffffffffu, light, 0);
-			base = __shfl_sync(0xffffffffu, base, 0), nb = __shfl_sync(0xffffffffu, nb, 0);
 			if (kind != 0xFFFFFFFFu)
 			{
 				pKind = kind, pLevel = level, pLight = light;
@@ -537,6 +543,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_CTAS_PER_SM) k_frame(SceneDev S, 
 		if (pKind == 1u)
 		{
 			// ---- shadow any-hit rays: a warp's lanes go to the same light from neighbouring surfaces ------
+			uint32_t myNodes = 0;
 			if (ready)
 			{
 				__threadfence();
@@ -555,10 +562,12 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_CTAS_PER_SM) k_frame(SceneDev S, 
 				const uint32_t nodes0 = st.nodes;
 				trace_scene<true, STATS>(S, ray, best, done, st);
 				if (STATS) atomicAdd(&ws->node_hist[12 + min(11, 31 - __clz((int)(st.nodes - nodes0 + 1u)))], 1u);
+				if (STATS) myNodes = st.nodes - nodes0;
 				L.shadow[(size_t)k * L.capacity + i] = done ? 1 : 0;
 				pSlot = 0xFFFFFFFFu;
 			}
 			__syncwarp();
+			lane_stats<STATS>(ws, 1, myNodes);
 			if (lane == 0) atomicSub(&ws->outstanding, (int)nb);
 			continue;
 		}
@@ -573,6 +582,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_CTAS_PER_SM) k_frame(SceneDev S, 
 		uint2 metaFlec = make_uint2(0, 0), metaFrac = metaFlec;
 		float fracRfr = 1.0f;
 		int4 aux = make_int4(-1, -1, -1, 0);
+		uint32_t myNodes = 0;
 		if (i != 0xFFFFFFFFu)
 		{
 			__threadfence();   // the stamp was seen: order the payload reads after it
@@ -585,6 +595,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_CTAS_PER_SM) k_frame(SceneDev S, 
 			const uint32_t nodes0 = st.nodes;
 			trace_scene<false, STATS>(S, ray, best, done, st);
 			if (STATS) atomicAdd(&ws->node_hist[min(11, 31 - __clz((int)(st.nodes - nodes0 + 1u)))], 1u);
+			if (STATS) myNodes = st.nodes - nodes0;
 			const F3 P = ray.o + ray.d * best.t;
 			L.hit_p[i] = make_float4(P.x, P.y, P.z, best.t);
 			L.hit_id[i] = make_uint2(best.id, best.newobj);
@@ -634,6 +645,8 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_CTAS_PER_SM) k_frame(SceneDev S, 
 			}
 		}
 
+		__syncwarp();
+		lane_stats<STATS>(ws, 0, myNodes);
 		// ---- new work: count it as outstanding BEFORE it can be consumed, then publish ------------------
 		const uint32_t mf = __ballot_sync(0xffffffffu, wantFlec), mr = __ballot_sync(0xffffffffu, wantFrac), ms = __ballot_sync(0xffffffffu, surface);
 		const int nChildren = __popc(mf) + __popc(mr);
@@ -978,20 +991,38 @@ void rtk_raygen(cudaStream_t st, const FrameParams *F, const LevelBuf &L, uint32
 	k_raygen<<<grid_for(n, 256, sms * 16), 256, 0, st>>>(F, L, n);
 }
 
+// Resident CTAs of 128 threads per SM for the traversal kernels: 8 (64 registers), 10 (48) or 12 (40).
+// The kernels wait on memory latency rather than on issue slots, so more warps can pay for more spills.
+static int traversal_ctas_per_sm()
+{
+	static const int v = []{ const char *e = getenv("RT_B200_OCC"); const int o = e ? atoi(e) : RT_CTAS_PER_SM; return (o == 4 || o == 6 || o == 10 || o == 12) ? o : RT_CTAS_PER_SM; }();
+	return v;
+}
+
 void rtk_wave(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const LevelBuf &N, const LevelBuf &Lprev, WaveState *ws,
 	uint32_t level, bool traceOn, bool shadowOn, float zNear, uint32_t maxItems, unsigned sms, bool stats)
 {
-	const unsigned g = grid_for(maxItems, RT_BLOCK, sms * RT_CTAS_PER_SM);   // persistent: all CTAs resident
-	if (stats) k_wave<true><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
-	else k_wave<false><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+	const int occ = traversal_ctas_per_sm();
+	const unsigned g = grid_for(maxItems, RT_BLOCK, sms * occ);   // persistent: all CTAs resident
+	if (stats) k_wave<true, RT_CTAS_PER_SM><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+	else if (occ == 4) k_wave<false, 4><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+	else if (occ == 6) k_wave<false, 6><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+	else if (occ == 10) k_wave<false, 10><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+	else if (occ == 12) k_wave<false, 12><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+	else k_wave<false, RT_CTAS_PER_SM><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
 }
 
 void rtk_frame(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelSet &LS, WaveState *ws, uint32_t nPix, unsigned sms, bool stats)
 {
 	// every CTA must be resident (consumers wait for producers): 8 CTAs of 128 threads fit per SM
-	const unsigned g = grid_for(nPix, RT_BLOCK, sms * RT_CTAS_PER_SM);
-	if (stats) k_frame<true><<<g, RT_BLOCK, 0, st>>>(S, F, LS, ws);
-	else k_frame<false><<<g, RT_BLOCK, 0, st>>>(S, F, LS, ws);
+	const int occ = traversal_ctas_per_sm();
+	const unsigned g = grid_for(nPix, RT_BLOCK, sms * occ);
+	if (stats) k_frame<true, RT_CTAS_PER_SM><<<g, RT_BLOCK, 0, st>>>(S, F, LS, ws);
+	else if (occ == 4) k_frame<false, 4><<<g, RT_BLOCK, 0, st>>>(S, F, LS, ws);
+	else if (occ == 6) k_frame<false, 6><<<g, RT_BLOCK, 0, st>>>(S, F, LS, ws);
+	else if (occ == 10) k_frame<false, 10><<<g, RT_BLOCK, 0, st>>>(S, F, LS, ws);
+	else if (occ == 12) k_frame<false, 12><<<g, RT_BLOCK, 0, st>>>(S, F, LS, ws);
+	else k_frame<false, RT_CTAS_PER_SM><<<g, RT_BLOCK, 0, st>>>(S, F, LS, ws);
 }
 
 void rtk_shade(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelSet &LS, const WaveState *ws, uint32_t levels, uint32_t maxRays, unsigned sms)

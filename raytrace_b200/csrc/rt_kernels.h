@@ -37,6 +37,7 @@ struct WaveState
 	int outstanding;                     // k_frame: rays reserved and not yet finished (0 = frame complete)
 	unsigned long long n_reflect, n_refract;
 	unsigned long long nodes_visited, tri_tests, prim_tests;
+	unsigned long long lane_sum[2], lane_cap[2];   // RT_FLAG_STATS (k_frame): per batch, sum of node visits / 32 x longest lane; [0] closest, [1] shadow
 	unsigned int node_hist[24];          // RT_FLAG_STATS: rays by floor(log2(nodes visited + 1)), closest-hit [0..11], shadow [12..23]
 };
 

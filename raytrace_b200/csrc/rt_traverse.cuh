@@ -202,12 +202,10 @@ __device__ __forceinline__ void test_prim(const SceneDev &S, const RayD &ray, ui
 
 // BVH walk shared by Models (triangle leaves) and runs of analytic primitives (prim leaves).
 //
-// "while-while" shape (Aila & Laine 2009): every lane first descends through inner nodes until it
-// holds a leaf (or has finished); lanes that already hold a leaf wait at the end of the inner
-// loop, so the long, divergent leaf code runs once per warp iteration with as many lanes as
-// possible instead of interleaving with box tests.  The stack lives in local memory (L1-resident,
-// one 128-byte line per depth and warp) so no shared memory is reserved and occupancy is bound by
-// registers only.
+// Inner-node steps and leaf steps are separate warp-wide phases (the long, divergent leaf code never
+// interleaves with box tests); which phase runs next is voted per step, see below.  The stack lives
+// in local memory (L1-resident, one 128-byte line per depth and warp) so no shared memory is
+// reserved and occupancy is bound by registers only.
 #define RT_TRAV_DONE (-1)   // never a valid leaf code: that would be first = 2^28-1, count = 8
 
 template<bool ANY, bool TRIS, bool FAST, bool STATS>
@@ -229,81 +227,99 @@ __device__ __forceinline__ void traverse(const SceneDev &S, const RayD &ray, con
 	const uint32_t sx = __float_as_uint(ray.d.x) >> 31, sy = __float_as_uint(ray.d.y) >> 31, sz = __float_as_uint(ray.d.z) >> 31;
 	const uint32_t onx = sx ? 48u : 0u, ony = sy ? 64u : 16u, onz = sz ? 80u : 32u;
 	const uint32_t ofx = sx ? 0u : 48u, ofy = sy ? 16u : 64u, ofz = sz ? 32u : 80u;
+	// Phase voting.  The lanes that entered together decide every step, by majority, whether the warp
+	// runs ONE inner-node step or ONE leaf step; a lane in the minority keeps its node / leaf for a
+	// later step.  The classic while-while shape (every lane descends until it holds a leaf, then all
+	// leaves are tested) makes each round as long as the slowest descent of 32 lanes: measured on C3,
+	// 7 of 32 lanes were active in the node code although the lanes' total lengths alone allow 19.
+	const uint32_t wmask = __activemask();
 	while (true)
 	{
-		while (cur >= 0)
-		{
-			const char *n = (const char *)&S.nodes4[cur];
-			const float4 nx = ldg4((const float4 *)(n + onx)), ny = ldg4((const float4 *)(n + ony)), nz = ldg4((const float4 *)(n + onz));
-			const float4 fx = ldg4((const float4 *)(n + ofx)), fy = ldg4((const float4 *)(n + ofy)), fz = ldg4((const float4 *)(n + ofz));
-			const int4 link = __ldg((const int4 *)(n + 96));
-			if (STATS) ++st.nodes;
-			float t0, t1, t2, t3;
-			const bool h0 = slab_hit_nf(nx.x, ny.x, nz.x, fx.x, fy.x, fz.x, ray.o, idir, best.t, t0);
-			const bool h1 = slab_hit_nf(nx.y, ny.y, nz.y, fx.y, fy.y, fz.y, ray.o, idir, best.t, t1);
-			const bool h2 = slab_hit_nf(nx.z, ny.z, nz.z, fx.z, fy.z, fz.z, ray.o, idir, best.t, t2);
-			const bool h3 = slab_hit_nf(nx.w, ny.w, nz.w, fx.w, fy.w, fz.w, ray.o, idir, best.t, t3);
-			// nearest hit child first, the other hit children go on the stack
-			const float inf = __int_as_float(0x7f800000);
-			float bt = h0 ? t0 : inf;
-			int bi = 0;
-			if (h1 && t1 < bt) bt = t1, bi = 1;
-			if (h2 && t2 < bt) bt = t2, bi = 2;
-			if (h3 && t3 < bt) bt = t3, bi = 3;
-			if (!(h0 | h1 | h2 | h3))
-			{
-#if RT_CULL_ON_POP
-				cur = RT_TRAV_DONE;
-				while (sp)
-				{
-					--sp;
-					if (ANY || stackT[sp] <= best.t) { cur = stack[sp]; break; }
-				}
-#else
-				cur = sp ? stack[--sp] : RT_TRAV_DONE;
-#endif
-				continue;
-			}
-#if RT_CULL_ON_POP
-			if (h0 && bi != 0) { stack[sp] = link.x; if (!ANY) stackT[sp] = t0; ++sp; }
-			if (h1 && bi != 1) { stack[sp] = link.y; if (!ANY) stackT[sp] = t1; ++sp; }
-			if (h2 && bi != 2) { stack[sp] = link.z; if (!ANY) stackT[sp] = t2; ++sp; }
-			if (h3 && bi != 3) { stack[sp] = link.w; if (!ANY) stackT[sp] = t3; ++sp; }
-#else
-			if (h0 && bi != 0) stack[sp++] = link.x;
-			if (h1 && bi != 1) stack[sp++] = link.y;
-			if (h2 && bi != 2) stack[sp++] = link.z;
-			if (h3 && bi != 3) stack[sp++] = link.w;
-#endif
-			cur = bi == 0 ? link.x : bi == 1 ? link.y : bi == 2 ? link.z : link.w;
-		}
-		if (cur == RT_TRAV_DONE)
+		const bool atNode = cur >= 0, atLeaf = cur < 0 && cur != RT_TRAV_DONE;
+		const uint32_t mN = __ballot_sync(wmask, atNode), mL = __ballot_sync(wmask, atLeaf);
+		if ((mN | mL) == 0u)
 			break;
-		const uint32_t first = ((uint32_t)cur & 0x7FFFFFFFu) >> 3, count = ((uint32_t)cur & 7u) + 1u;
-		if (TRIS)
-			leaf_tris<ANY, FAST, STATS>(S, ray, idir, first, count, hr_distance, rangeBegin, rangeEnd, pc, best, done, slow, st);
-		else
-			for (uint32_t k = 0; k < count; ++k)
-			{
-				const uint32_t p = __ldg(&S.bvh_prims[first + k]);
-				if (p < winLo || p >= winHi)
-					continue;
-				if (STATS) ++st.prims;
-				test_prim<ANY>(S, ray, p, !(best.id & RT_ID_TRI) && best.id >= rangeBegin, best, done);
-			}
-		if (ANY && done)
-			return;
-#if RT_CULL_ON_POP
-		cur = RT_TRAV_DONE;
-		while (sp)
+		if (__popc(mN) >= __popc(mL))
 		{
-			--sp;
-			if (ANY || stackT[sp] <= best.t) { cur = stack[sp]; break; }
-		}
+			if (atNode)
+			{
+				const char *n = (const char *)&S.nodes4[cur];
+				const float4 nx = ldg4((const float4 *)(n + onx)), ny = ldg4((const float4 *)(n + ony)), nz = ldg4((const float4 *)(n + onz));
+				const float4 fx = ldg4((const float4 *)(n + ofx)), fy = ldg4((const float4 *)(n + ofy)), fz = ldg4((const float4 *)(n + ofz));
+				const int4 link = __ldg((const int4 *)(n + 96));
+				if (STATS) ++st.nodes;
+				float t0, t1, t2, t3;
+				const bool h0 = slab_hit_nf(nx.x, ny.x, nz.x, fx.x, fy.x, fz.x, ray.o, idir, best.t, t0);
+				const bool h1 = slab_hit_nf(nx.y, ny.y, nz.y, fx.y, fy.y, fz.y, ray.o, idir, best.t, t1);
+				const bool h2 = slab_hit_nf(nx.z, ny.z, nz.z, fx.z, fy.z, fz.z, ray.o, idir, best.t, t2);
+				const bool h3 = slab_hit_nf(nx.w, ny.w, nz.w, fx.w, fy.w, fz.w, ray.o, idir, best.t, t3);
+				// nearest hit child first, the other hit children go on the stack
+				const float inf = __int_as_float(0x7f800000);
+				float bt = h0 ? t0 : inf;
+				int bi = 0;
+				if (h1 && t1 < bt) bt = t1, bi = 1;
+				if (h2 && t2 < bt) bt = t2, bi = 2;
+				if (h3 && t3 < bt) bt = t3, bi = 3;
+				if (!(h0 | h1 | h2 | h3))
+				{
+#if RT_CULL_ON_POP
+					cur = RT_TRAV_DONE;
+					while (sp)
+					{
+						--sp;
+						if (ANY || stackT[sp] <= best.t) { cur = stack[sp]; break; }
+					}
 #else
-		cur = sp ? stack[--sp] : RT_TRAV_DONE;
+					cur = sp ? stack[--sp] : RT_TRAV_DONE;
 #endif
+				}
+				else
+				{
+#if RT_CULL_ON_POP
+					if (h0 && bi != 0) { stack[sp] = link.x; if (!ANY) stackT[sp] = t0; ++sp; }
+					if (h1 && bi != 1) { stack[sp] = link.y; if (!ANY) stackT[sp] = t1; ++sp; }
+					if (h2 && bi != 2) { stack[sp] = link.z; if (!ANY) stackT[sp] = t2; ++sp; }
+					if (h3 && bi != 3) { stack[sp] = link.w; if (!ANY) stackT[sp] = t3; ++sp; }
+#else
+					if (h0 && bi != 0) stack[sp++] = link.x;
+					if (h1 && bi != 1) stack[sp++] = link.y;
+					if (h2 && bi != 2) stack[sp++] = link.z;
+					if (h3 && bi != 3) stack[sp++] = link.w;
+#endif
+					cur = bi == 0 ? link.x : bi == 1 ? link.y : bi == 2 ? link.z : link.w;
+				}
+			}
+		}
+		else if (atLeaf)
+		{
+			const uint32_t first = ((uint32_t)cur & 0x7FFFFFFFu) >> 3, count = ((uint32_t)cur & 7u) + 1u;
+			if (TRIS)
+				leaf_tris<ANY, FAST, STATS>(S, ray, idir, first, count, hr_distance, rangeBegin, rangeEnd, pc, best, done, slow, st);
+			else
+				for (uint32_t k = 0; k < count; ++k)
+				{
+					const uint32_t p = __ldg(&S.bvh_prims[first + k]);
+					if (p < winLo || p >= winHi)
+						continue;
+					if (STATS) ++st.prims;
+					test_prim<ANY>(S, ray, p, !(best.id & RT_ID_TRI) && best.id >= rangeBegin, best, done);
+				}
+			cur = RT_TRAV_DONE;
+			if (ANY && done)
+				sp = 0;   // occluded: nothing else to look at, but stay in the vote until the other lanes are through
+#if RT_CULL_ON_POP
+			while (sp)
+			{
+				--sp;
+				if (ANY || stackT[sp] <= best.t) { cur = stack[sp]; break; }
+			}
+#else
+			if (sp) cur = stack[--sp];
+#endif
+		}
 	}
+	if (ANY && done)
+		return;
 	if (FAST)
 	{
 		// one replay per ray, executed by the whole warp together
