@@ -221,6 +221,15 @@ int rt_create(int device, rt_ctx **out);
 void rt_destroy(rt_ctx *ctx);
 /* optional: run on a caller-provided cudaStream_t (e.g. torch's current stream) */
 int rt_set_stream(rt_ctx *ctx, void *cuda_stream);
+/* Several frames in flight on one GPU (the reference renders one frame at a time, RayTracer.cpp:614-696;
+ * its idiom for more is one RayTracer per view over the same Scene, RayTracer.cpp:600).  A shared
+ * pipeline renders its PARENT's resident scene -- device tables and BVHs are aliased, not copied --
+ * on its own stream with its own ray queues and framebuffer, so frame k+1 fills the SMs that the long
+ * ray chains at the end of frame k leave idle.  The parent must outlive it; upload to the parent only. */
+int rt_create_shared(rt_ctx *parent, rt_ctx **out);
+/* resident traversal CTAs per SM this pipeline may occupy (1..8, 0 = all): pipelines that run
+ * concurrently split the 8 slots between them */
+int rt_set_sm_share(rt_ctx *ctx, int ctas_per_sm);
 
 /* replaces the per-start scene walk + Model::RTPrepare (RayTracer.cpp:621-625, Model.cpp:402-480):
  * copies the description to SoA device buffers and (re)builds the LBVHs when geometry changed */

@@ -106,6 +106,8 @@ RT_SYMBOLS = {
     "rt_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "rt_destroy": (None, [C.c_void_p]),
     "rt_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rt_create_shared": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "rt_set_sm_share": (C.c_int, [C.c_void_p, C.c_int]),
     "rt_upload_scene": (C.c_int, [C.c_void_p, C.POINTER(SceneDesc)]),
     "rt_render_async": (C.c_int, [C.c_void_p, C.POINTER(RenderParams)]),
     "rt_poll": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)]),

@@ -117,6 +117,11 @@ struct rt_ctx
 	int schedMode = 0;              // 0 auto, 1 k_frame (one persistent launch per frame), 2 per-level waves (RT_B200_SCHED=auto|frame|waves)
 	bool frameSched = false;        // what the last frame used
 	uint32_t frameEpoch = 0;
+	// several frames in flight on one GPU: a pipeline created by rt_create_shared renders its parent's
+	// resident scene (device tables and BVH are NOT copied), on its own stream with its own ray queues
+	rt_ctx *sceneFrom = nullptr;
+	uint64_t sceneVersion = 0, adoptedVersion = 0;
+	unsigned ctasPerSm = 0;         // resident traversal CTAs per SM this pipeline may use (0 = all 8), rt_set_sm_share
 };
 
 extern "C" const char *rt_last_error(void) { return g_err.c_str(); }
@@ -159,6 +164,39 @@ extern "C" int rt_create(int device, rt_ctx **out)
 	return RT_OK;
 }
 
+extern "C" int rt_create_shared(rt_ctx *parent, rt_ctx **out)
+{
+	if (!parent || !out) return fail(RT_E_INVALID, "rt_create_shared: NULL argument");
+	if (parent->sceneFrom) return fail(RT_E_INVALID, "rt_create_shared: the parent is itself a shared pipeline");
+	int rc = rt_create(parent->device, out);
+	if (rc != RT_OK) return rc;
+	(*out)->sceneFrom = parent;
+	return RT_OK;
+}
+
+extern "C" int rt_set_sm_share(rt_ctx *c, int ctas_per_sm)
+{
+	if (!c) return fail(RT_E_INVALID, "rt_set_sm_share: ctx is NULL");
+	if (ctas_per_sm < 0 || ctas_per_sm > 8) return fail(RT_E_INVALID, "rt_set_sm_share: %d CTAs per SM (0 = default, 1..8)", ctas_per_sm);
+	c->ctasPerSm = (unsigned)ctas_per_sm;
+	return RT_OK;
+}
+
+// A shared pipeline looks at its parent's scene: host-side tables are copied (small), device tables are
+// aliased.  rt_upload_scene leaves the parent's stream synchronised whenever it touched device memory,
+// so the aliases are valid for kernels on any stream as soon as the upload call has returned.
+static void adopt_scene(rt_ctx *c)
+{
+	const rt_ctx *p = c->sceneFrom;
+	if (!p || c->adoptedVersion == p->sceneVersion) return;
+	c->hasScene = p->hasScene, c->geometryEpoch = p->geometryEpoch;
+	c->prims = p->prims, c->models = p->models, c->parts = p->parts, c->lights = p->lights;
+	c->camera = p->camera, c->envLight = p->envLight, c->anyRefract = p->anyRefract, c->nTris = p->nTris;
+	c->S = p->S, c->bvhNodes = p->bvhNodes, c->bvhDepth = p->bvhDepth, c->leafSize = p->leafSize;
+	c->adoptedVersion = p->sceneVersion;
+	c->frameValid = false;
+}
+
 extern "C" void rt_destroy(rt_ctx *c)
 {
 	if (!c) return;
@@ -198,6 +236,7 @@ template<class T> static bool same(const std::vector<T> &a, const T *b, size_t n
 
 extern "C" int rt_upload_scene(rt_ctx *c, const rt_scene_desc *s)
 {
+	if (c && c->sceneFrom) return fail(RT_E_STATE, "rt_upload_scene: this pipeline shares its parent's scene (rt_create_shared); upload to the parent");
 	if (!c || !s) return fail(RT_E_INVALID, "rt_upload_scene: NULL argument");
 	CU(cudaSetDevice(c->device));
 	if (c->frameInFlight) { CU(cudaEventSynchronize(c->evB)); c->frameInFlight = false; }
@@ -446,6 +485,7 @@ extern "C" int rt_upload_scene(rt_ctx *c, const rt_scene_desc *s)
 	}
 	c->hasScene = true;
 	c->frameValid = false;
+	++c->sceneVersion;
 	return RT_OK;
 }
 
@@ -476,6 +516,7 @@ static int finish_frame(rt_ctx *c);
 extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 {
 	if (!c || !p) return fail(RT_E_INVALID, "rt_render_async: NULL argument");
+	adopt_scene(c);
 	if (!c->hasScene) return fail(RT_E_STATE, "rt_render_async: no scene uploaded");
 	if (p->type != RT_TYPE_RAYTRACE && (p->type < RT_TYPE_CHECK || p->type > RT_TYPE_REFRACT))
 		return fail(RT_E_INVALID, "rt_render_async: unknown render type 0x%x (RayTracer.h:5-13)", p->type);
@@ -507,6 +548,14 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 	if (tileRows != 8u && tileRows != 16u && tileRows != 32u && tileRows != 64u)
 		return fail(RT_E_INVALID, "rt_render_async: tile_rows %u (must be 8, 16, 32 or 64)", tileRows);
 	F.tile_rows = tileRows;
+	{
+		static const int dfs = []{ const char *e = getenv("RT_B200_CLAIM"); return (e && !strcmp(e, "dfs")) ? 1 : 0; }();
+		static const int retire = []{ const char *e = getenv("RT_B200_RETIRE"); return (e && !atoi(e)) ? 0 : 1; }();
+		F.sched_flags = (uint32_t)dfs | ((uint32_t)retire << 1);
+		F.sms = (uint32_t)c->sms;
+		static const int retireRays = []{ const char *e = getenv("RT_B200_RETIRE_RAYS"); const int v = e ? atoi(e) : 16; return v > 0 ? v : 16; }();
+		F.retire_rays = (uint32_t)retireRays;
+	}
 	uint32_t bands = 0;
 	for (uint32_t t = 0; t < (uint32_t)F.blk_h * 64u / tileRows; ++t) if (t % world == rank) ++bands;
 	F.n_rows = bands * tileRows;
@@ -583,7 +632,7 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 		for (uint32_t l = 0; l <= maxLevel + 1; ++l) LS.l[l] = level_buf(c->levels[l]);
 		if (c->frameSched && p->type != RT_TYPE_CHECK)
 		{
-			rtk_frame(st, c->S, c->dFrame, LS, c->dWave, nPix, c->sms, stats); ++launches;
+			rtk_frame(st, c->S, c->dFrame, LS, c->dWave, nPix, c->sms, stats, c->ctasPerSm); ++launches;
 		}
 		for (uint32_t l = 0; l <= maxLevel + 1 && p->type != RT_TYPE_CHECK && !c->frameSched; ++l)
 		{
@@ -593,7 +642,7 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 			const float zNear = l == 0 ? F.zNear : 0.0f;
 			uint32_t items = traceOn ? c->levels[l].capacity : 0;
 			if (shadowOn) items = std::max(items, (uint32_t)std::min<uint64_t>((uint64_t)c->levels[l - 1].capacity * enabledLights, 0x7FFFFFFFu));
-			rtk_wave(st, c->S, c->dFrame, LS.l[l], LS.l[traceOn ? l + 1 : l], LS.l[l ? l - 1 : 0], c->dWave, l, traceOn, shadowOn, zNear, items, c->sms, stats);
+			rtk_wave(st, c->S, c->dFrame, LS.l[l], LS.l[traceOn ? l + 1 : l], LS.l[l ? l - 1 : 0], c->dWave, l, traceOn, shadowOn, zNear, items, c->sms, stats, c->ctasPerSm);
 			++launches;
 		}
 		if (c->stageTiming) CU(cudaEventRecord(c->evStage[1], st));
@@ -887,6 +936,18 @@ extern "C" int rt_read_counters(rt_ctx *c, rt_counters *out)
 		fprintf(stderr, "\n                                          shadow:");
 		for (int b = 12; b < 24; ++b) fprintf(stderr, " %u", W.node_hist[b]);
 		fprintf(stderr, "\n");
+		if (W.t0)
+		{
+			fprintf(stderr, "k_frame timeline: rays started per 16.4 us bin; columns: closest L0..L7 | shadow L0..L7\n");
+			int last = 127;
+			while (last > 0) { bool any = false; for (int k = 0; k < 16; ++k) any |= W.timeline[last][k] != 0; if (any) break; --last; }
+			for (int b = 0; b <= last; ++b)
+			{
+				fprintf(stderr, "%5.0f us:", b * 16.384);
+				for (int k = 0; k < 16; ++k) fprintf(stderr, k == 8 ? " | %6u" : " %6u", W.timeline[b][k]);
+				fprintf(stderr, "\n");
+			}
+		}
 		if (W.lane_cap[0] || W.lane_cap[1])
 			fprintf(stderr, "lane utilisation bound (sum nodes / 32 x longest lane per batch): closest %.3f shadow %.3f\n",
 				W.lane_cap[0] ? (double)W.lane_sum[0] / (double)W.lane_cap[0] : 0.0, W.lane_cap[1] ? (double)W.lane_sum[1] / (double)W.lane_cap[1] : 0.0);

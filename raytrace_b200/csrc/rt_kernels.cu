@@ -170,6 +170,18 @@ __device__ __forceinline__ uint32_t warp_append(uint32_t *counter, bool want)
 	return want ? base + __popc(m & ((1u << lane) - 1u)) : 0xFFFFFFFFu;
 }
 
+// the same for a converged subset `grp` of the warp (lanes that left the traversal together)
+__device__ __forceinline__ uint32_t group_append(uint32_t *counter, bool want, uint32_t grp)
+{
+	const uint32_t m = __ballot_sync(grp, want);
+	if (m == 0) return 0xFFFFFFFFu;
+	const uint32_t lane = threadIdx.x & 31u, leader = __ffs((int)m) - 1;
+	uint32_t base = 0;
+	if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+	base = __shfl_sync(grp, base, leader);
+	return want ? base + __popc(m & ((1u << lane) - 1u)) : 0xFFFFFFFFu;
+}
+
 // light k as seen from P: direction p2l and occlusion range (RayTracer.cpp:482-503)
 __device__ __forceinline__ void light_dir(const DevLight &lit, const F3 &P, F3 &p2l, float &dis, float &lum)
 {
@@ -442,8 +454,14 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_frame(SceneDev S, const Fram
 	// blocking the lanes whose work is ready, until it is published or the frame is over.
 	// pKind 0: closest-hit rays of level pLevel; pKind 1: shadow rays of level pLevel towards light pLight.
 	uint32_t pKind = 0, pLevel = 0, pLight = 0, pSlot = 0xFFFFFFFFu;
+	uint32_t statNodes = 0, statKind = 0;   // RT_FLAG_STATS: node visits of the lane's last ray
 	while (true)
 	{
+		if (STATS)
+		{
+			if (__ballot_sync(0xffffffffu, statNodes != 0u)) lane_stats<STATS>(ws, statKind, statNodes);
+			statNodes = 0;
+		}
 		if (__ballot_sync(0xffffffffu, pSlot != 0xFFFFFFFFu) == 0u)
 		{
 			// ---- claim: the 32 lanes look at one queue each (rays of level q, then shadow rays per (level,
@@ -464,7 +482,10 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_frame(SceneDev S, const Fram
 					{
 						uint32_t cnt;
 						if (q < nL)
-							qLevel = q, cnt = vload(&ws->count[q]), head = &ws->head_trace[q];
+						{
+							qLevel = (F.sched_flags & 1u) ? nL - 1u - q : q;
+							cnt = vload(&ws->count[qLevel]), head = &ws->head_trace[qLevel];
+						}
 						else
 						{
 							qLevel = (q - nL) / F.n_enabled, qLight = (q - nL) % F.n_enabled;
@@ -526,6 +547,14 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_frame(SceneDev S, const Fram
 			out = __shfl_sync(0xffffffffu, out, 0);
 			if (out <= 0 || vload(&ws->overflow) >= 2u)
 				break;   // nothing in flight any more (or the scheduler gave up / rt_stop): unpublished slots will never be written
+			// Retire: when the frame runs thin (a few long ray chains are left), a CTA that owns nothing and
+			// finds nothing leaves for good if fewer than `retire_rays` rays per CTA would remain for it -- high CTA
+			// indices first, the first `sms` CTAs never.  `outstanding` never under-counts and a ray tree is
+			// bounded by max_level, so whoever stays can always finish the frame.  Leaving frees the SM slots
+			// for the next frame's kernels (frames in flight) and thins out the pollers of the queue heads.
+			if ((F.sched_flags & 2u) && blockIdx.x >= F.sms && out < (int)((blockIdx.x - F.sms + 1u) * F.retire_rays)
+				&& __ballot_sync(0xffffffffu, pSlot != 0xFFFFFFFFu) == 0u)
+				break;
 			if (++idleSpins > (1u << 22))
 			{
 				if (lane == 0) ws->overflow = 2u;   // scheduler stuck: fail loudly instead of hanging the GPU
@@ -539,11 +568,19 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_frame(SceneDev S, const Fram
 		if (vload(&ws->overflow) >= 2u)
 			break;   // rt_stop or scheduler abort
 		const uint32_t nb = __popc(readyMask);
+		if (STATS && lane == 0)
+		{
+			unsigned long long now;
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+			unsigned long long t0 = atomicCAS(&ws->t0, 0ull, now);
+			if (t0 == 0ull) t0 = now;
+			const unsigned long long bin = (now - t0) >> 14;
+			atomicAdd(&ws->timeline[bin < 127ull ? bin : 127ull][(pKind ? 8u : 0u) + (pLevel < 7u ? pLevel : 7u)], nb);
+		}
 
 		if (pKind == 1u)
 		{
 			// ---- shadow any-hit rays: a warp's lanes go to the same light from neighbouring surfaces ------
-			uint32_t myNodes = 0;
 			if (ready)
 			{
 				__threadfence();
@@ -562,12 +599,11 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_frame(SceneDev S, const Fram
 				const uint32_t nodes0 = st.nodes;
 				trace_scene<true, STATS>(S, ray, best, done, st);
 				if (STATS) atomicAdd(&ws->node_hist[12 + min(11, 31 - __clz((int)(st.nodes - nodes0 + 1u)))], 1u);
-				if (STATS) myNodes = st.nodes - nodes0;
+				if (STATS) statNodes = st.nodes - nodes0, statKind = 1;
 				L.shadow[(size_t)k * L.capacity + i] = done ? 1 : 0;
 				pSlot = 0xFFFFFFFFu;
 			}
 			__syncwarp();
-			lane_stats<STATS>(ws, 1, myNodes);
 			if (lane == 0) atomicSub(&ws->outstanding, (int)nb);
 			continue;
 		}
@@ -577,14 +613,13 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_frame(SceneDev S, const Fram
 		const uint32_t i = ready ? pSlot : 0xFFFFFFFFu;
 		if (ready) pSlot = 0xFFFFFFFFu;
 
-		bool surface = false, wantFlec = false, wantFrac = false;
-		float4 co = make_float4(0, 0, 0, 0), cdFlec = co, cdFrac = co;
-		uint2 metaFlec = make_uint2(0, 0), metaFrac = metaFlec;
-		float fracRfr = 1.0f;
-		int4 aux = make_int4(-1, -1, -1, 0);
-		uint32_t myNodes = 0;
 		if (i != 0xFFFFFFFFu)
 		{
+			bool surface = false, wantFlec = false, wantFrac = false;
+			float4 co = make_float4(0, 0, 0, 0), cdFlec = co, cdFrac = co;
+			uint2 metaFlec = make_uint2(0, 0), metaFrac = metaFlec;
+			float fracRfr = 1.0f;
+			int4 aux = make_int4(-1, -1, -1, 0);
 			__threadfence();   // the stamp was seen: order the payload reads after it
 			const float4 o4 = __ldcg(&L.ray_o[i]), d4 = __ldcg(&L.ray_d[i]);
 			RayD ray;
@@ -593,9 +628,14 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_frame(SceneDev S, const Fram
 			Best best = { 1e20f, RT_ID_NONE, ray.skip };
 			bool done = false;
 			const uint32_t nodes0 = st.nodes;
-			trace_scene<false, STATS>(S, ray, best, done, st);
+			// EARLY: lanes whose ray is through leave the walk of the last scene item in groups, a few steps
+			// after they finish, instead of waiting for the longest ray of the batch.  Everything below runs
+			// per such group, so a ray's children and its shadow work are published when IT is done: the
+			// frame's critical path is a chain of single rays, not a chain of batch maxima (measured on an
+			// eighth of the C3 frame: 0.91 -> see DESIGN.md).
+			trace_scene<false, STATS, true>(S, ray, best, done, st);
 			if (STATS) atomicAdd(&ws->node_hist[min(11, 31 - __clz((int)(st.nodes - nodes0 + 1u)))], 1u);
-			if (STATS) myNodes = st.nodes - nodes0;
+			if (STATS) statNodes = st.nodes - nodes0, statKind = 0;
 			const F3 P = ray.o + ray.d * best.t;
 			L.hit_p[i] = make_float4(P.x, P.y, P.z, best.t);
 			L.hit_id[i] = make_uint2(best.id, best.newobj);
@@ -643,50 +683,50 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_frame(SceneDev S, const Fram
 					}
 				}
 			}
-		}
 
-		__syncwarp();
-		lane_stats<STATS>(ws, 0, myNodes);
-		// ---- new work: count it as outstanding BEFORE it can be consumed, then publish ------------------
-		const uint32_t mf = __ballot_sync(0xffffffffu, wantFlec), mr = __ballot_sync(0xffffffffu, wantFrac), ms = __ballot_sync(0xffffffffu, surface);
-		const int nChildren = __popc(mf) + __popc(mr);
-		const int nShadow = wantShadows ? __popc(ms) * (int)F.n_enabled : 0;
-		// one atomic per batch: the new work is added before it is published, and this batch's own rays
-		// (all traced by now) are retired in the same operation
-		if (lane == 0 && nChildren + nShadow != (int)nb) atomicAdd(&ws->outstanding, nChildren + nShadow - (int)nb);
-		__syncwarp();
-		if (i != 0xFFFFFFFFu)
+			// ---- new work: count it as outstanding BEFORE it can be consumed, then publish.  `grp` is whatever
+			// set of lanes arrives here together; any partition of the batch into such groups is correct, each
+			// group retires its own rays and adds its own children / shadow work in one atomic. ---------------
+			const uint32_t grp = __activemask();
+			const uint32_t gLeader = __ffs((int)grp) - 1;
+			const uint32_t mf = __ballot_sync(grp, wantFlec), mr = __ballot_sync(grp, wantFrac), ms = __ballot_sync(grp, surface);
+			const int nChildren = __popc(mf) + __popc(mr);
+			const int nShadow = wantShadows ? __popc(ms) * (int)F.n_enabled : 0;
+			const int nMine = __popc(grp);
+			if (lane == gLeader && nChildren + nShadow != nMine) atomicAdd(&ws->outstanding, nChildren + nShadow - nMine);
+			__syncwarp(grp);
+			if (nChildren)
+			{
+				const uint32_t sFlec = group_append(&ws->count[level + 1], wantFlec, grp);
+				const uint32_t sFrac = group_append(&ws->count[level + 1], wantFrac, grp);
+				int dropped = 0;
+				if (wantFlec)
+				{
+					if (sFlec < N.capacity) { N.ray_o[sFlec] = co, N.ray_d[sFlec] = cdFlec; aux.x = (int)sFlec; }
+					else { ws->overflow = 1; ++dropped; }
+				}
+				if (wantFrac)
+				{
+					if (sFrac < N.capacity) { N.ray_o[sFrac] = make_float4(co.x, co.y, co.z, fracRfr), N.ray_d[sFrac] = cdFrac; aux.y = (int)sFrac; }
+					else { ws->overflow = 1; ++dropped; }
+				}
+				__threadfence();
+				if (wantFlec && sFlec < N.capacity) N.ray_meta[sFlec] = metaFlec;
+				if (wantFrac && sFrac < N.capacity) N.ray_meta[sFrac] = metaFrac;
+				if (dropped) atomicSub(&ws->outstanding, dropped);
+				if (lane == gLeader)
+				{
+					if (mf) atomicAdd(&ws->n_reflect, (unsigned long long)__popc(mf));
+					if (mr) atomicAdd(&ws->n_refract, (unsigned long long)__popc(mr));
+				}
+			}
 			L.aux[i] = aux;
-		if (nChildren)
-		{
-			const uint32_t sFlec = warp_append(&ws->count[level + 1], wantFlec);
-			const uint32_t sFrac = warp_append(&ws->count[level + 1], wantFrac);
-			int dropped = 0;
-			if (wantFlec)
-			{
-				if (sFlec < N.capacity) { N.ray_o[sFlec] = co, N.ray_d[sFlec] = cdFlec; L.aux[i].x = (int)sFlec; }
-				else { ws->overflow = 1; ++dropped; }
-			}
-			if (wantFrac)
-			{
-				if (sFrac < N.capacity) { N.ray_o[sFrac] = make_float4(co.x, co.y, co.z, fracRfr), N.ray_d[sFrac] = cdFrac; L.aux[i].y = (int)sFrac; }
-				else { ws->overflow = 1; ++dropped; }
-			}
+			// surfaces: hit_p / hit_id / hit_n are written; publish the compacted entry last
+			const uint32_t hslot = group_append(&ws->n_hit[level], surface, grp);
 			__threadfence();
-			if (wantFlec && sFlec < N.capacity) N.ray_meta[sFlec] = metaFlec;
-			if (wantFrac && sFrac < N.capacity) N.ray_meta[sFrac] = metaFrac;
-			if (dropped) atomicSub(&ws->outstanding, dropped);
-			if (lane == 0)
-			{
-				if (mf) atomicAdd(&ws->n_reflect, (unsigned long long)__popc(mf));
-				if (mr) atomicAdd(&ws->n_refract, (unsigned long long)__popc(mr));
-			}
+			if (surface)
+				L.hit_list[hslot] = i + 1u;
 		}
-		// surfaces: hit_p / hit_id / hit_n are written; publish the compacted entry last
-		const uint32_t hslot = warp_append(&ws->n_hit[level], surface);
-		__threadfence();
-		if (surface)
-			L.hit_list[hslot] = i + 1u;
 	}
 	flush_stats<STATS>(ws, st);
 }
@@ -1000,10 +1040,10 @@ static int traversal_ctas_per_sm()
 }
 
 void rtk_wave(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const LevelBuf &N, const LevelBuf &Lprev, WaveState *ws,
-	uint32_t level, bool traceOn, bool shadowOn, float zNear, uint32_t maxItems, unsigned sms, bool stats)
+	uint32_t level, bool traceOn, bool shadowOn, float zNear, uint32_t maxItems, unsigned sms, bool stats, unsigned ctasPerSm)
 {
 	const int occ = traversal_ctas_per_sm();
-	const unsigned g = grid_for(maxItems, RT_BLOCK, sms * occ);   // persistent: all CTAs resident
+	const unsigned g = grid_for(maxItems, RT_BLOCK, sms * (ctasPerSm && (int)ctasPerSm < occ ? ctasPerSm : occ));   // persistent: all CTAs resident
 	if (stats) k_wave<true, RT_CTAS_PER_SM><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
 	else if (occ == 4) k_wave<false, 4><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
 	else if (occ == 6) k_wave<false, 6><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
@@ -1012,11 +1052,12 @@ void rtk_wave(cudaStream_t st, const SceneDev &S, const FrameParams *F, const Le
 	else k_wave<false, RT_CTAS_PER_SM><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
 }
 
-void rtk_frame(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelSet &LS, WaveState *ws, uint32_t nPix, unsigned sms, bool stats)
+void rtk_frame(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelSet &LS, WaveState *ws, uint32_t nPix, unsigned sms, bool stats, unsigned ctasPerSm)
 {
 	// every CTA must be resident (consumers wait for producers): 8 CTAs of 128 threads fit per SM
 	const int occ = traversal_ctas_per_sm();
-	const unsigned g = grid_for(nPix, RT_BLOCK, sms * occ);
+	// a pipeline that shares the GPU with other frames in flight takes only its share of the resident CTA slots
+	const unsigned g = grid_for(nPix, RT_BLOCK, sms * (ctasPerSm && (int)ctasPerSm < occ ? ctasPerSm : occ));
 	if (stats) k_frame<true, RT_CTAS_PER_SM><<<g, RT_BLOCK, 0, st>>>(S, F, LS, ws);
 	else if (occ == 4) k_frame<false, 4><<<g, RT_BLOCK, 0, st>>>(S, F, LS, ws);
 	else if (occ == 6) k_frame<false, 6><<<g, RT_BLOCK, 0, st>>>(S, F, LS, ws);

@@ -38,14 +38,16 @@ struct WaveState
 	unsigned long long n_reflect, n_refract;
 	unsigned long long nodes_visited, tri_tests, prim_tests;
 	unsigned long long lane_sum[2], lane_cap[2];   // RT_FLAG_STATS (k_frame): per batch, sum of node visits / 32 x longest lane; [0] closest, [1] shadow
+	unsigned long long t0;               // RT_FLAG_STATS (k_frame): %globaltimer of the first batch
+	unsigned int timeline[128][16];      // RT_FLAG_STATS (k_frame): rays started per 16.4 us bin; column = level (closest) / 8 + level (shadow)
 	unsigned int node_hist[24];          // RT_FLAG_STATS: rays by floor(log2(nodes visited + 1)), closest-hit [0..11], shadow [12..23]
 };
 
 void rtk_raygen(cudaStream_t st, const FrameParams *F, const LevelBuf &L, uint32_t n, unsigned sms);
 void rtk_wave(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const LevelBuf &N, const LevelBuf &Lprev, WaveState *ws,
-	uint32_t level, bool traceOn, bool shadowOn, float zNear, uint32_t maxItems, unsigned sms, bool stats);
+	uint32_t level, bool traceOn, bool shadowOn, float zNear, uint32_t maxItems, unsigned sms, bool stats, unsigned ctasPerSm = 0);
 // whole-frame persistent scheduler (all ray levels in one launch)
-void rtk_frame(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelSet &LS, WaveState *ws, uint32_t nPix, unsigned sms, bool stats);
+void rtk_frame(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelSet &LS, WaveState *ws, uint32_t nPix, unsigned sms, bool stats, unsigned ctasPerSm = 0);
 void rtk_shade(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelSet &LS, const WaveState *ws, uint32_t levels, uint32_t maxRays, unsigned sms);
 void rtk_debug(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, uint32_t n, uint8_t *out, unsigned sms);
 void rtk_intersect_object(cudaStream_t st, const SceneDev &S, uint32_t primBegin, uint32_t primEnd, int modelIndex, const void *rays, const void *in,

@@ -208,7 +208,11 @@ __device__ __forceinline__ void test_prim(const SceneDev &S, const RayD &ray, ui
 // reserved and occupancy is bound by registers only.
 #define RT_TRAV_DONE (-1)   // never a valid leaf code: that would be first = 2^28-1, count = 8
 
-template<bool ANY, bool TRIS, bool FAST, bool STATS>
+#ifndef RT_EARLY_HOLD
+#define RT_EARLY_HOLD 4u   // EARLY: steps a finished lane waits for others to finish before the group leaves
+#endif
+
+template<bool ANY, bool TRIS, bool FAST, bool STATS, bool EARLY = false>
 __device__ __forceinline__ void traverse(const SceneDev &S, const RayD &ray, const F3 &idir, int root,
 	float hr_distance, uint32_t rangeBegin, uint32_t rangeEnd, Best &best, bool &done, TravStats &st,
 	uint32_t winLo = 0u, uint32_t winHi = 0xFFFFFFFFu)
@@ -232,13 +236,28 @@ __device__ __forceinline__ void traverse(const SceneDev &S, const RayD &ray, con
 	// later step.  The classic while-while shape (every lane descends until it holds a leaf, then all
 	// leaves are tested) makes each round as long as the slowest descent of 32 lanes: measured on C3,
 	// 7 of 32 lanes were active in the node code although the lanes' total lengths alone allow 19.
-	const uint32_t wmask = __activemask();
+	//
+	// EARLY (whole-frame scheduler, last scene item of a closest-hit ray): lanes that are through do not
+	// wait for the longest ray of the batch; they leave together once one of them has idled for
+	// RT_EARLY_HOLD steps, and the caller publishes their results while the rest keeps walking.
+	uint32_t wmask = __activemask();
+	uint32_t waited = 0;
 	while (true)
 	{
 		const bool atNode = cur >= 0, atLeaf = cur < 0 && cur != RT_TRAV_DONE;
 		const uint32_t mN = __ballot_sync(wmask, atNode), mL = __ballot_sync(wmask, atLeaf);
 		if ((mN | mL) == 0u)
 			break;
+		if (EARLY && (mN | mL) != wmask)
+		{
+			const bool idle = !(atNode || atLeaf);
+			if (idle) ++waited;
+			if (__ballot_sync(wmask, idle && waited >= RT_EARLY_HOLD))
+			{
+				wmask = mN | mL;
+				if (idle) break;
+			}
+		}
 		if (__popc(mN) >= __popc(mL))
 		{
 			if (atNode)
@@ -339,7 +358,7 @@ __device__ __forceinline__ void traverse(const SceneDev &S, const RayD &ray, con
 
 // The scene walk in Objects order.  Closest hit: best starts at (1e20, NONE).  Any-hit: best.t
 // starts at the light distance and `done` reports occlusion.
-template<bool ANY, bool STATS>
+template<bool ANY, bool STATS, bool EARLY = false>
 __device__ __forceinline__ void trace_scene(const SceneDev &S, const RayD &ray, Best &best, bool &done, TravStats &st)
 {
 	const F3 idir = f3(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
@@ -375,6 +394,8 @@ __device__ __forceinline__ void trace_scene(const SceneDev &S, const RayD &ray, 
 				test_prim<ANY>(S, ray, ray.skip, false, best, done);
 				traverse<ANY, false, false, STATS>(S, ray, idir, it.root, best.t, it.first, end, best, done, st, ray.skip + 1u, end);
 			}
+			else if (EARLY && i + 1u == S.n_items)
+				traverse<ANY, false, false, STATS, EARLY>(S, ray, idir, it.root, best.t, it.first, end, best, done, st);
 			else
 				traverse<ANY, false, false, STATS>(S, ray, idir, it.root, best.t, it.first, end, best, done, st);
 		}
@@ -403,7 +424,10 @@ __device__ __forceinline__ void trace_scene(const SceneDev &S, const RayD &ray, 
 			else
 			{
 				const Best before = best;
-				traverse<false, true, true, STATS>(S, ray, idir, it.root, before.t, tb, tb + __ldg(&M.tri_count), best, done, st);
+				if (EARLY && i + 1u == S.n_items)
+					traverse<false, true, true, STATS, EARLY>(S, ray, idir, it.root, before.t, tb, tb + __ldg(&M.tri_count), best, done, st);
+				else
+					traverse<false, true, true, STATS>(S, ray, idir, it.root, before.t, tb, tb + __ldg(&M.tri_count), best, done, st);
 				if (best.t < 0.0f)
 				{
 					best = before;

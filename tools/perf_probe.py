@@ -15,6 +15,8 @@ CFG = {
     "c3s": ("c3", 1920, 1080, 5, 240, 15),
 }
 names = sys.argv[1:] or ["c2", "c3"]
+WORLD = int(os.environ.get("RT_PROBE_WORLD", "1"))   # render only shard 0 of WORLD (8-row tiles): the per-GPU share of a multi-GPU frame
+SHARD = dict(rank=0, world=WORLD, tile_rows=8) if WORLD > 1 else {}
 for nm in names:
     name, w, h, level, n, parts = CFG[nm]
     t0 = time.time()
@@ -22,12 +24,12 @@ for nm in names:
     t_build = time.time() - t0
     rt = R.RayTracer(sc)
     rt.maxLevel = level
-    rt.render(R.MY_MODEL_RAYTRACE, flags=R.RT_FLAG_STATS)
+    rt.render(R.MY_MODEL_RAYTRACE, flags=R.RT_FLAG_STATS, **SHARD)
     cs = rt.counters()
     best = None
     for _ in range(5):
         t0 = time.time()
-        rt.start(R.MY_MODEL_RAYTRACE)
+        rt.start(R.MY_MODEL_RAYTRACE, **SHARD)
         rt.wait()
         wall = time.time() - t0
         c = rt.counters()
@@ -36,7 +38,7 @@ for nm in names:
     c, wall = best
     total = c.primary + c.shadow + c.reflect + c.refract
     flops = cs.nodes_visited * 4 * 22 + cs.tri_tests * 47 + cs.prim_tests * 23
-    print(json.dumps({"cfg": nm, "leaf": os.environ.get("RT_B200_LEAF_SIZE", "2"), "scene_s": round(t_build, 1), "rays": total,
+    print(json.dumps({"cfg": nm, "world": WORLD, "leaf": os.environ.get("RT_B200_LEAF_SIZE", "2"), "scene_s": round(t_build, 1), "rays": total,
                       "rays_per_px": round(total / max(c.primary, 1), 2),
                       "render_ms": round(c.render_ms, 3), "start_to_finish_ms": round(wall * 1e3, 3), "mrays_s": round(total / c.render_ms / 1e3, 1),
                       "trace_ms": round(c.trace_ms, 3), "shadow_ms": round(c.shadow_ms, 3), "shade_ms": round(c.shade_ms, 3), "other_ms": round(c.other_ms, 3),

@@ -1,2 +1,4 @@
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -2
-for o in 8 10 12; do echo "--- RT_B200_OCC=$o"; RT_B200_OCC=$o python tools/perf_probe.py c3 c2 c4 2>&1 | cut -c1-200; done
+for r in 64 256 1024 4096; do echo "--- RT_B200_RETIRE_RAYS=$r"
+RT_B200_RETIRE_RAYS=$r RT_PIPE_SHARE="0" RT_PIPE_M="1 2 3" python tools/pipe_probe.py c3 1 2>&1 | tail -3
+RT_B200_RETIRE_RAYS=$r RT_PIPE_SHARE="0" RT_PIPE_M="1 2 4" python tools/pipe_probe.py c3 8 2>&1 | tail -3
+done
