@@ -8,10 +8,16 @@ One "step" = one frame of the named configuration (default c3: 1920x1080, 1 036 
 is quoted on).  A ray = one closest-hit or one shadow any-hit query.
 
   value    whole-job Mrays/s with the scene resident in HBM: K frames enqueued through the C ABI
-           (rt_render_async), timed with CUDA events on the launching stream, max over ranks.
+           (rt_render_async) round-robin over M frame pipelines per GPU (rt_create_shared: one
+           resident scene, M frames in flight, each pipeline on its own stream with a share of the resident
+           traversal CTAs per SM), timed with CUDA events that bracket all streams, max over ranks.
+           Every frame is rendered completely; `config.ms_per_frame_alone` is the latency of ONE
+           frame with nothing else in flight.
   e2e      same metric through the reference-facing call RayTracer::start() with HOST buffers:
            every step re-flattens the Scene, uploads the per-frame tables (H2D) and reads the
-           RGB8 frame back into RayTracer::output (D2H) inside the timed region.
+           RGB8 frame back into RayTracer::output (D2H) inside the timed region.  M RayTracer
+           objects over the one Scene (the reference's idiom for several views) keep M frames in
+           flight; step k waits for step k-M on the same tracer before it starts.
   roofline FP32-issue roofline of the traversal kernel (k_wave, all launches of a frame): algorithmic FLOPs
            from device counters (DESIGN.md "flop model") / their CUDA-event time, against
            148 SMs x 128 lanes x sm_max_mhz of MEASURED_PEAKS.json (1 lane-instr = 1 flop because the
@@ -174,6 +180,8 @@ def main():
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipelines", type=int, default=0, help="frames in flight per GPU (0 = 3 at N=1, 4 at N>1)")
+    ap.add_argument("--sm-share", type=int, default=-1, help="resident traversal CTAs per SM per pipeline (-1 = 4 at N=1, 2 at N>1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     cfg = CONFIGS[args.config]
@@ -201,31 +209,52 @@ def main():
     tmpdir = f"/tmp/rt_bench_{rank}"
     os.makedirs(tmpdir, exist_ok=True)
     sc = R.Scene(scene, w, h, n, parts, tmpdir=tmpdir)
-    rt = R.RayTracer(sc, device=local)           # the drop-in surface (used for e2e)
-    rt.maxLevel = level
-    h_ctx = C.c_void_p(rt.context())             # the tracer's C-ABI context, reused for the resident-scene loop
 
     def ck(rc, what):
         if rc != 0:
             raise RuntimeError(f"{what}: {R.rt.rt_last_error().decode()}")
 
-    # everything (kernels, copies, NCCL) on torch's current stream so torch events see it
-    stream = torch.cuda.current_stream(dev)
-    ck(R.rt.rt_set_stream(h_ctx, C.c_void_p(stream.cuda_stream)), "rt_set_stream")
-    frame = torch.full((h, w, 3), 127, dtype=torch.uint8, device=dev)
-    ck(R.rt.rt_set_output(h_ctx, C.c_void_p(frame.data_ptr()), frame.numel()), "rt_set_output")
-    desc_ptr = sc.flatten()
-    ck(R.rt.rt_upload_scene(h_ctx, desc_ptr), "rt_upload_scene")
+    # ---- frame pipelines: one resident scene, M frames in flight ---------------------------------
+    M = args.pipelines if args.pipelines > 0 else (3 if world == 1 else 4)
+    share = args.sm_share if args.sm_share >= 0 else (4 if world == 1 else 2)
+    main = torch.cuda.current_stream(dev)
+    owner = C.c_void_p()
+    ck(R.rt.rt_create(local, C.byref(owner)), "rt_create")
+    ck(R.rt.rt_set_stream(owner, C.c_void_p(main.cuda_stream)), "rt_set_stream")
+    ck(R.rt.rt_upload_scene(owner, sc.flatten()), "rt_upload_scene")      # H2D of the scene + LBVH build, once
     tile_rows = 8 if world > 1 else 64           # fine interleave balances the ranks (sky rows are cheap)
     params = R.RenderParams(R.MY_MODEL_RAYTRACE, level, rank, world, 0, tile_rows)
-
     from raytrace_b200.distributed import FrameGather
-    gather = FrameGather(w, h, rank, world, dev, tile_rows) if world > 1 else None
+    pipes = []
+    for _ in range(M):
+        hnd = C.c_void_p()
+        ck(R.rt.rt_create_shared(owner, C.byref(hnd)), "rt_create_shared")
+        st = torch.cuda.Stream(dev)
+        ck(R.rt.rt_set_stream(hnd, C.c_void_p(st.cuda_stream)), "rt_set_stream")
+        ck(R.rt.rt_set_sm_share(hnd, share if M > 1 else 0), "rt_set_sm_share")
+        frame = torch.full((h, w, 3), 127, dtype=torch.uint8, device=dev)
+        ck(R.rt.rt_set_output(hnd, C.c_void_p(frame.data_ptr()), frame.numel()), "rt_set_output")
+        pipes.append({"ctx": hnd, "stream": st, "frame": frame,
+                      "gather": FrameGather(w, h, rank, world, dev, tile_rows) if world > 1 else None})
 
-    def step():
-        ck(R.rt.rt_render_async(h_ctx, C.byref(params)), "rt_render_async")
-        if gather is not None:
-            gather.gather(frame)   # NCCL: this rank's 64-row bands -> rank 0, de-interleaved there
+    def step(k):
+        p = pipes[k % M]
+        ck(R.rt.rt_render_async(p["ctx"], C.byref(params)), "rt_render_async")
+        if p["gather"] is not None:
+            with torch.cuda.stream(p["stream"]):
+                p["gather"].gather(p["frame"])   # NCCL: this rank's row tiles -> rank 0, de-interleaved there
+
+    def fork():
+        ev = torch.cuda.Event()
+        ev.record(main)
+        for p in pipes:
+            p["stream"].wait_event(ev)
+
+    def join():
+        for p in pipes:
+            ev = torch.cuda.Event()
+            ev.record(p["stream"])
+            main.wait_event(ev)
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -234,34 +263,33 @@ def main():
             torch.cuda.synchronize(dev)
 
     # ---- warm-up + one counted frame (ray totals are deterministic per configuration) ----------
-    for _ in range(args.warmup):
-        step()
+    fork()
+    for k in range(max(args.warmup, M)):
+        step(k)
+    join()
     sync_all()
     cnt = R.Counters()
-    ck(R.rt.rt_read_counters(h_ctx, C.byref(cnt)), "rt_read_counters")
+    ck(R.rt.rt_read_counters(pipes[0]["ctx"], C.byref(cnt)), "rt_read_counters")
     rays_local = cnt.primary + cnt.shadow + cnt.reflect + cnt.refract
-    launches_per_step = cnt.launches + (0 if world == 1 else 0)
+    launches_per_step = cnt.launches
     rays_t = torch.tensor([rays_local], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(rays_t)
     rays_total = int(rays_t.item())
 
-    # ---- timed region: exactly K steps, CUDA events on the launching stream, max over ranks -----
+    # ---- timed region: exactly K steps, CUDA events bracketing every pipeline stream, max over ranks
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
+    e0.record(main)
+    fork()
+    for k in range(args.steps):
+        step(k)
+    join()
+    e1.record(main)
     sync_all()
-    # per-stage split from the library's own CUDA events (last timed frame, scaled to K steps)
-    ck(R.rt.rt_read_counters(h_ctx, C.byref(cnt)), "rt_read_counters")
-    # (closest-hit and shadow queries share the fused wave kernels: "traverse")
-    stage = {"traverse": cnt.trace_ms * args.steps, "shade": cnt.shade_ms * args.steps,
-             "other": cnt.other_ms * args.steps, "render": cnt.render_ms * args.steps}
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -277,36 +305,57 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     value = rays_total * args.steps / (ms_total * 1e-3) / 1e6
 
-    # ---- traversal statistics for the roofline (one extra, untimed, counted frame) ---------------
+    # ---- one frame alone (latency, per-stage split from the library's own CUDA events) and one
+    #      counted frame for the roofline; both untimed ------------------------------------------------
+    p0 = pipes[0]["ctx"]
+    ck(R.rt.rt_set_sm_share(p0, 0), "rt_set_sm_share")
+    for _ in range(2):
+        ck(R.rt.rt_render_async(p0, C.byref(params)), "rt_render_async")
+        ck(R.rt.rt_read_counters(p0, C.byref(cnt)), "rt_read_counters")
+    stage = {"traverse": cnt.trace_ms, "shade": cnt.shade_ms, "other": cnt.other_ms, "render": cnt.render_ms}
     pstats = R.RenderParams(R.MY_MODEL_RAYTRACE, level, rank, world, R.RT_FLAG_STATS, tile_rows)
-    ck(R.rt.rt_render_async(h_ctx, C.byref(pstats)), "rt_render_async(stats)")
+    ck(R.rt.rt_render_async(p0, C.byref(pstats)), "rt_render_async(stats)")
     cs = R.Counters()
-    ck(R.rt.rt_read_counters(h_ctx, C.byref(cs)), "rt_read_counters")
+    ck(R.rt.rt_read_counters(p0, C.byref(cs)), "rt_read_counters")
+    torch.cuda.synchronize(dev)
+    for p in pipes:
+        R.rt.rt_destroy(p["ctx"])
+    R.rt.rt_destroy(owner)
 
     # ---- e2e: RayTracer::start() with host buffers (flatten + H2D tables + render + D2H frame) ----
-    ck(R.rt.rt_set_output(h_ctx, None, 0), "rt_set_output")
-    for _ in range(2):
-        rt.start(R.MY_MODEL_RAYTRACE, rank=rank, world=world, tile_rows=tile_rows)
-        rt.wait()
+    tracers = []
+    for _ in range(M):
+        t = R.RayTracer(sc, device=local)        # the drop-in surface; tracers of one Scene share its residency
+        t.maxLevel = level
+        t.smShare = share if M > 1 else 0
+        tracers.append(t)
+    for k in range(2 * M):
+        tracers[k % M].wait()
+        tracers[k % M].start(R.MY_MODEL_RAYTRACE, rank=rank, world=world, tile_rows=tile_rows)
+    for t in tracers:
+        t.wait()
     sync_all()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        rt.start(R.MY_MODEL_RAYTRACE, rank=rank, world=world, tile_rows=tile_rows)
-        rt.wait()
+    for k in range(args.steps):
+        t = tracers[k % M]
+        t.wait()                                 # frame k-M is in RayTracer::output
+        t.start(R.MY_MODEL_RAYTRACE, rank=rank, world=world, tile_rows=tile_rows)
+    for t in tracers:
+        t.wait()
     torch.cuda.synchronize(dev)
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = rays_total * args.steps / float(e2e_s.item()) / 1e6
-    ce = rt.counters()                           # bytes the library itself copied for the last start()
+    ce = tracers[0].counters()                   # bytes the library itself copied for the last start()
     h2d, d2h = int(ce.h2d_bytes), int(ce.d2h_bytes)
 
     if rank == 0:
         peak, peak_src, hbm_peak = sm_peak_fp32_tflops()
         # flop model: 22 per child box (4 per 4-wide node), 47 per triangle test, 23 per analytic primitive
         flops = cs.nodes_visited * 4 * 22 + cs.tri_tests * 47 + cs.prim_tests * 23
-        trav_ms = stage["traverse"] / args.steps
-        trav_launches = 1 if cnt.launches <= level + 4 else level + 2   # whole-frame scheduler: one traversal launch per frame
+        trav_ms = stage["traverse"]
+        trav_launches = 1 if cnt.launches <= level + 5 else level + 2   # whole-frame scheduler: one traversal launch per frame
         achieved = flops / (trav_ms * 1e-3) / 1e12 if trav_ms > 0 else 0.0
         queue_bytes = rays_local * 100   # ~100 B of ray/hit/node records written+read per ray
         line = {
@@ -316,7 +365,8 @@ def main():
             "config": {"workload": f"{args.config}: {desc}", "rays_per_frame": rays_total, "pixels": w * (h // 64 * 64) if w % 64 == 0 else (w // 64 * 64) * (h // 64 * 64),
                        "l2_policy": "per-frame working set (ray/hit/node queues + BVH + triangles, > 500 MB touched per frame) exceeds the 126 MB L2; no flush needed",
                        "parallelism": f"image-space: interleaved {tile_rows}-row tiles over {world} GPUs, NCCL gather of RGB8 tiles to rank 0" if world > 1 else "single GPU",
-                       "ms_per_frame_kernels_only": stage["render"] / args.steps},
+                       "frames_in_flight": M, "traversal_ctas_per_sm_per_pipeline": (share if M > 1 and share else 8),
+                       "ms_per_frame_alone": stage["render"]},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": float(e2e_s.item()) / args.steps * 1e3,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches_per_step * args.steps,
@@ -325,8 +375,8 @@ def main():
                          "traffic": NCU_TRAFFIC.get((args.config, world)), "traffic_source": "profiles/r1f_ncu_full_k_frame_c3.md (dram__bytes_read.sum + dram__bytes_write.sum of one k_frame launch)" if (args.config, world) in NCU_TRAFFIC else None,
                          "launches_per_step": trav_launches, "avg_launch_ms": trav_ms / trav_launches,
                          "flops_per_step": flops, "nodes_per_ray": cs.nodes_visited / max(rays_local, 1), "tri_tests_per_ray": cs.tri_tests / max(rays_local, 1),
-                         "stage_ms": {k: v / args.steps for k, v in stage.items()},
-                         "hbm_secondary": {"queue_bytes_per_step": queue_bytes, "achieved_gbs": queue_bytes / (stage["render"] / args.steps * 1e-3) / 1e9,
+                         "stage_ms_one_frame_alone": stage,
+                         "hbm_secondary": {"queue_bytes_per_step": queue_bytes, "achieved_gbs": queue_bytes / (stage["render"] * 1e-3) / 1e9,
                                            "peak_gbs": hbm_peak}},
             "clocks": clocks, "per_rank": per_rank,
             "build": {"upload_ms": cs.upload_ms, "lbvh_build_ms": cs.build_ms, "bvh_nodes": cs.bvh_nodes, "bvh_depth": cs.bvh_depth},

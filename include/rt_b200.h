@@ -225,7 +225,8 @@ int rt_set_stream(rt_ctx *ctx, void *cuda_stream);
  * its idiom for more is one RayTracer per view over the same Scene, RayTracer.cpp:600).  A shared
  * pipeline renders its PARENT's resident scene -- device tables and BVHs are aliased, not copied --
  * on its own stream with its own ray queues and framebuffer, so frame k+1 fills the SMs that the long
- * ray chains at the end of frame k leave idle.  The parent must outlive it; upload to the parent only. */
+ * ray chains at the end of frame k leave idle.  The parent must outlive it; rt_upload_scene on a shared
+ * pipeline uploads to the parent (and so changes what every pipeline of that parent renders next). */
 int rt_create_shared(rt_ctx *parent, rt_ctx **out);
 /* resident traversal CTAs per SM this pipeline may occupy (1..8, 0 = all): pipelines that run
  * concurrently split the 8 slots between them */

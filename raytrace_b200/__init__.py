@@ -103,6 +103,7 @@ class RayTracer:
         self.scene = scene
         self._h = rth.rth_tracer_new(scene._h, device)
         self.maxLevel = 1
+        self.smShare = 0   # resident traversal CTAs per SM (0 = all 8); set when several tracers of one Scene run concurrently
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -111,6 +112,7 @@ class RayTracer:
 
     def start(self, type=MY_MODEL_RAYTRACE, tnum=1, flags=0, rank=0, world=1, tile_rows=64):
         rth.rth_tracer_set_max_level(self._h, self.maxLevel)
+        rth.rth_tracer_set_sm_share(self._h, self.smShare)
         rth.rth_tracer_set_flags(self._h, flags)
         rth.rth_tracer_set_shard(self._h, rank, world, tile_rows)
         if rth.rth_tracer_start(self._h, type, tnum) != 0:

@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_DIR = os.path.join(_HERE, "lib")
+LIB_DIR = os.environ.get("RT_B200_LIBDIR") or os.path.join(_HERE, "lib")   # RT_B200_LIBDIR: A/B builds during development
 
 
 class Vec4(C.Structure):
@@ -157,6 +157,7 @@ RTH_SYMBOLS = {
     "rth_tracer_set_max_level": (None, [C.c_void_p, C.c_int]),
     "rth_tracer_set_shard": (None, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "rth_tracer_set_flags": (None, [C.c_void_p, C.c_uint]),
+    "rth_tracer_set_sm_share": (None, [C.c_void_p, C.c_int]),
     "rth_tracer_read_hit_ids": (C.c_int, [C.c_void_p, C.POINTER(HitId)]),
     "rth_tracer_read_counters": (C.c_int, [C.c_void_p, C.POINTER(Counters)]),
     "rth_object_intersect": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Ray), C.POINTER(Hit), C.c_float]),

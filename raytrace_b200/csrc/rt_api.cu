@@ -120,7 +120,8 @@ struct rt_ctx
 	// several frames in flight on one GPU: a pipeline created by rt_create_shared renders its parent's
 	// resident scene (device tables and BVH are NOT copied), on its own stream with its own ray queues
 	rt_ctx *sceneFrom = nullptr;
-	uint64_t sceneVersion = 0, adoptedVersion = 0;
+	uint64_t sceneVersion = 0, adoptedVersion = 0;     // bumped by every rt_upload_scene of the parent
+	uint64_t tablesVersion = 0, adoptedTables = 0;     // bumped when prims / models / parts changed
 	unsigned ctasPerSm = 0;         // resident traversal CTAs per SM this pipeline may use (0 = all 8), rt_set_sm_share
 };
 
@@ -167,7 +168,7 @@ extern "C" int rt_create(int device, rt_ctx **out)
 extern "C" int rt_create_shared(rt_ctx *parent, rt_ctx **out)
 {
 	if (!parent || !out) return fail(RT_E_INVALID, "rt_create_shared: NULL argument");
-	if (parent->sceneFrom) return fail(RT_E_INVALID, "rt_create_shared: the parent is itself a shared pipeline");
+	if (parent->sceneFrom) parent = parent->sceneFrom;   // a sibling of a shared pipeline: same scene owner
 	int rc = rt_create(parent->device, out);
 	if (rc != RT_OK) return rc;
 	(*out)->sceneFrom = parent;
@@ -190,9 +191,12 @@ static void adopt_scene(rt_ctx *c)
 	const rt_ctx *p = c->sceneFrom;
 	if (!p || c->adoptedVersion == p->sceneVersion) return;
 	c->hasScene = p->hasScene, c->geometryEpoch = p->geometryEpoch;
-	c->prims = p->prims, c->models = p->models, c->parts = p->parts, c->lights = p->lights;
+	if (c->adoptedTables != p->tablesVersion || c->adoptedVersion == 0)
+		c->prims = p->prims, c->models = p->models, c->parts = p->parts, c->adoptedTables = p->tablesVersion;
+	c->lights = p->lights;
 	c->camera = p->camera, c->envLight = p->envLight, c->anyRefract = p->anyRefract, c->nTris = p->nTris;
 	c->S = p->S, c->bvhNodes = p->bvhNodes, c->bvhDepth = p->bvhDepth, c->leafSize = p->leafSize;
+	c->uploadMs = p->uploadMs, c->buildMs = p->buildMs, c->uploadBytes = p->uploadBytes;
 	c->adoptedVersion = p->sceneVersion;
 	c->frameValid = false;
 }
@@ -236,7 +240,7 @@ template<class T> static bool same(const std::vector<T> &a, const T *b, size_t n
 
 extern "C" int rt_upload_scene(rt_ctx *c, const rt_scene_desc *s)
 {
-	if (c && c->sceneFrom) return fail(RT_E_STATE, "rt_upload_scene: this pipeline shares its parent's scene (rt_create_shared); upload to the parent");
+	if (c && c->sceneFrom) return rt_upload_scene(c->sceneFrom, s);   // a shared pipeline has no scene of its own
 	if (!c || !s) return fail(RT_E_INVALID, "rt_upload_scene: NULL argument");
 	CU(cudaSetDevice(c->device));
 	if (c->frameInFlight) { CU(cudaEventSynchronize(c->evB)); c->frameInFlight = false; }
@@ -326,6 +330,8 @@ extern "C" int rt_upload_scene(rt_ctx *c, const rt_scene_desc *s)
 		CU(cudaStreamSynchronize(st));
 	}
 
+	if (primsChanged || modelsChanged)
+		++c->tablesVersion;
 	if (primsChanged || modelsChanged)
 	{
 		// ---- analytic primitives ------------------------------------------------------------------
@@ -824,6 +830,7 @@ static rt_hit_id decode_id(const rt_ctx *c, uint32_t h, float distance)
 
 extern "C" int rt_intersect_object(rt_ctx *c, uint32_t object, const rt_ray *rays, const rt_hit *in, float min, rt_hit *out, uint32_t n)
 {
+	if (c) adopt_scene(c);
 	if (!c || !rays || !in || !out) return fail(RT_E_INVALID, "rt_intersect_object: NULL argument");
 	if (!c->hasScene) return fail(RT_E_STATE, "rt_intersect_object: no scene uploaded");
 	CU(cudaSetDevice(c->device));
@@ -862,6 +869,7 @@ extern "C" int rt_intersect_object(rt_ctx *c, uint32_t object, const rt_ray *ray
 
 extern "C" int rt_read_hit_ids(rt_ctx *c, rt_hit_id *ids)
 {
+	if (c) adopt_scene(c);
 	if (!c || !ids) return fail(RT_E_INVALID, "rt_read_hit_ids: NULL argument");
 	if (c->frameInFlight) { int rc = finish_frame(c); if (rc != RT_OK) return rc; }
 	if (!c->frameValid) return fail(RT_E_STATE, "rt_read_hit_ids: no finished frame");
@@ -913,6 +921,7 @@ extern "C" int rt_read_hit_ids(rt_ctx *c, rt_hit_id *ids)
 
 extern "C" int rt_read_counters(rt_ctx *c, rt_counters *out)
 {
+	if (c) adopt_scene(c);
 	if (!c || !out) return fail(RT_E_INVALID, "rt_read_counters: NULL argument");
 	if (c->frameInFlight) { int rc = finish_frame(c); if (rc != RT_OK) return rc; }
 	memset(out, 0, sizeof *out);

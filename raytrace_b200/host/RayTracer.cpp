@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
+#include <map>
 #include <mutex>
 #include <stdexcept>
 
@@ -32,6 +33,17 @@ static void free_output(uint8_t *p, bool pinned)
 	else delete[] p;
 }
 
+// One per (Scene, device): the context that holds the uploaded scene, and the flattener that feeds it.
+struct SceneResidency
+{
+	rt_ctx *parent = nullptr;
+	SceneFlattener flattener;
+	std::mutex mutex;   // flatten + upload of concurrent start() calls
+	~SceneResidency() { if (parent) rt_destroy(parent); }
+};
+static std::mutex g_residencyMutex;
+static std::map<std::pair<const Scene *, int>, std::weak_ptr<SceneResidency>> g_residency;
+
 // Every live RayTracer, so that DrawObject::intersect (which has no back pointer) can find the
 // device context its Scene is attached to.
 static std::mutex g_tracersMutex;
@@ -57,8 +69,8 @@ RayTracer::~RayTracer()
 	if (monitor.joinable())
 		monitor.join();
 	if (ctx)
-		rt_destroy(ctx);
-	delete flattener;
+		rt_destroy(ctx);       // the pipeline first, then (with the last tracer of the Scene) the residency
+	residency.reset();
 	if (output) free_output(output, outputPinned);
 }
 
@@ -66,10 +78,26 @@ void RayTracer::ensureContext()
 {
 	if (ctx)
 		return;
-	const int rc = rt_create(device, &ctx);
+	{
+		std::lock_guard<std::mutex> lock(g_residencyMutex);
+		std::weak_ptr<SceneResidency> &slot = g_residency[std::make_pair((const Scene *)scene, device)];
+		residency = slot.lock();
+		if (!residency)
+		{
+			residency = std::make_shared<SceneResidency>();
+			const int rc = rt_create(device, &residency->parent);
+			if (rc != RT_OK)
+			{
+				residency.reset();
+				fail("rt_create", rc);
+			}
+			slot = residency;
+		}
+	}
+	const int rc = rt_create_shared(residency->parent, &ctx);
 	if (rc != RT_OK)
-		fail("rt_create", rc);
-	flattener = new SceneFlattener();
+		fail("rt_create_shared", rc);
+	flattener = &residency->flattener;
 }
 
 void RayTracer::reserveOutput(size_t bytes)
@@ -96,11 +124,20 @@ void RayTracer::start(const uint8_t type, const int8_t)
 		if (o->bShow)
 			o->RTPrepare();
 
-	rt_scene_desc desc;
-	flattener->flatten(*scene, desc);
-	int rc = rt_upload_scene(ctx, &desc);
+	int rc;
+	{
+		// unchanged tables are not re-sent; while another tracer of this Scene has a frame in flight the
+		// scene must not change (the reference's rule, main.cpp:258,344), so the upload is then a no-op
+		std::lock_guard<std::mutex> lock(residency->mutex);
+		rt_scene_desc desc;
+		flattener->flatten(*scene, desc);
+		rc = rt_upload_scene(residency->parent, &desc);
+	}
 	if (rc != RT_OK)
 		fail("rt_upload_scene", rc);
+	rc = rt_set_sm_share(ctx, smShare);
+	if (rc != RT_OK)
+		fail("rt_set_sm_share", rc);
 	rt_render_params rp;
 	memset(&rp, 0, sizeof rp);
 	rp.type = type, rp.max_level = maxLevel;
@@ -193,9 +230,13 @@ HitRes RayTracer::intersectObject(uint32_t index, const Ray &ray, const HitRes &
 	for (DrawObject *o : scene->Objects)
 		if (o->bShow)
 			o->RTPrepare();
-	rt_scene_desc desc;
-	flattener->flatten(*scene, desc);
-	int rc = rt_upload_scene(ctx, &desc);   // no-op when nothing changed since the last frame
+	int rc;
+	{
+		std::lock_guard<std::mutex> lock(residency->mutex);
+		rt_scene_desc desc;
+		flattener->flatten(*scene, desc);
+		rc = rt_upload_scene(residency->parent, &desc);   // no-op when nothing changed since the last frame
+	}
 	if (rc != RT_OK)
 		fail("rt_upload_scene", rc);
 	rt_ray r;

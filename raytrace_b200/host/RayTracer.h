@@ -6,6 +6,7 @@
 #pragma once
 #include "Scene.h"
 #include "../../include/rt_b200.h"
+#include <memory>
 #include <thread>
 
 #define MY_MODEL_CHECK 0x1
@@ -19,10 +20,15 @@
 #define MY_MODEL_RAYTRACE 0x80
 
 class SceneFlattener;
+struct SceneResidency;
 
 class RayTracer
 {
 	Scene *scene;
+	// The Scene's device residency (flattened tables, triangles, BVHs) is shared by every RayTracer over
+	// the same Scene on the same GPU; each RayTracer owns one frame pipeline on it (rt_create_shared),
+	// so several RayTracers can have frames in flight at once without a second copy of the scene.
+	std::shared_ptr<SceneResidency> residency;
 	rt_ctx *ctx = nullptr;
 	SceneFlattener *flattener = nullptr;
 	std::thread monitor;
@@ -48,6 +54,7 @@ public:
 	uint32_t shardRank = 0, shardWorld = 1;   // image-space shard rendered by this tracer
 	uint32_t shardTileRows = 64;              // rows per shard tile (8, 16, 32, 64)
 	uint32_t renderFlags = 0;       // RT_FLAG_* passed to the next start()
+	int smShare = 0;                // resident traversal CTAs per SM of this tracer's pipeline (0 = all 8), for tracers that run concurrently
 	void reserveOutput(size_t bytes);          // frames beyond 2048x2048
 	void wait();                               // block until isFinish
 	bool readHitIds(rt_hit_id *ids);           // primary closest-hit identities of the last frame

@@ -1,4 +1,2 @@
-for r in 64 256 1024 4096; do echo "--- RT_B200_RETIRE_RAYS=$r"
-RT_B200_RETIRE_RAYS=$r RT_PIPE_SHARE="0" RT_PIPE_M="1 2 3" python tools/pipe_probe.py c3 1 2>&1 | tail -3
-RT_B200_RETIRE_RAYS=$r RT_PIPE_SHARE="0" RT_PIPE_M="1 2 4" python tools/pipe_probe.py c3 8 2>&1 | tail -3
-done
+python bench.py --steps 60 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c3_n1_r1g.json 2> gpurun_out/bench_err.log; tail -3 gpurun_out/bench_err.log; cut -c1-1500 gpurun_out/bench_c3_n1_r1g.json
+python bench.py --steps 60 --warmup 3 --no-cpu-baseline --pipelines 1 2>&1 | cut -c1-400
