@@ -355,7 +355,7 @@ def main():
         # flop model: 22 per child box (4 per 4-wide node), 47 per triangle test, 23 per analytic primitive
         flops = cs.nodes_visited * 4 * 22 + cs.tri_tests * 47 + cs.prim_tests * 23
         trav_ms = stage["traverse"]
-        trav_launches = 1 if cnt.launches <= level + 5 else level + 2   # whole-frame scheduler: one traversal launch per frame
+        trav_launches = 1 if cnt.frame_sched else level + 2   # whole-frame scheduler: one traversal launch per frame
         achieved = flops / (trav_ms * 1e-3) / 1e12 if trav_ms > 0 else 0.0
         queue_bytes = rays_local * 100   # ~100 B of ray/hit/node records written+read per ray
         line = {

@@ -167,6 +167,7 @@ typedef struct
 #define RT_FLAG_HIT_IDS   0x1   /* keep primary closest-hit identities for rt_read_hit_ids */
 #define RT_FLAG_STATS     0x2   /* count BVH node visits / primitive tests (slower kernels) */
 #define RT_FLAG_BRUTE     0x4   /* diagnostic: ignore the BVHs, test every primitive (small scenes) */
+#define RT_FLAG_COMBINE_LEVELS 0x8 /* diagnostic: colour combine as one pass per ray level instead of the one-launch tree walk */
 
 /* primary closest-hit identity, the GPU-side meaning of HitRes::obj (3DElement.h:174) */
 typedef struct
@@ -208,7 +209,7 @@ typedef struct
 	double upload_ms, build_ms;                      /* last scene upload / LBVH build */
 	uint32_t launches;                               /* kernels launched for the last frame */
 	uint32_t bvh_nodes, bvh_depth;
-	uint32_t pad0;
+	uint32_t frame_sched;                            /* 1: the last frame used the whole-frame persistent kernel, 0: per-level waves */
 	uint64_t h2d_bytes;    /* host->device bytes of the last rt_upload_scene + rt_render_async */
 	uint64_t d2h_bytes;    /* device->host bytes of the last frame (counters + rt_read_output) */
 } rt_counters;

@@ -95,7 +95,7 @@ class Counters(C.Structure):
                 ("nodes_visited", C.c_uint64), ("tri_tests", C.c_uint64), ("prim_tests", C.c_uint64),
                 ("render_ms", C.c_double), ("trace_ms", C.c_double), ("shadow_ms", C.c_double),
                 ("shade_ms", C.c_double), ("other_ms", C.c_double), ("upload_ms", C.c_double), ("build_ms", C.c_double),
-                ("launches", C.c_uint32), ("bvh_nodes", C.c_uint32), ("bvh_depth", C.c_uint32), ("pad0", C.c_uint32),
+                ("launches", C.c_uint32), ("bvh_nodes", C.c_uint32), ("bvh_depth", C.c_uint32), ("frame_sched", C.c_uint32),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 

@@ -73,7 +73,7 @@ struct FrameParams
 	uint32_t enabled_index[RT_MAX_LIGHTS];
 	uint32_t epoch;            // 1..65535, stamps ray_meta so k_frame consumers can tell a written slot
 	uint32_t tile_rows;        // shard tile height (8..64 rows)
-	uint32_t sched_flags;      // k_frame: bit 0 = ray queues are claimed deepest level first, bit 1 = idle CTAs retire when the frame runs thin
+	uint32_t sched_flags;      // k_frame: bit 0 = ray queues are claimed deepest level first, bit 1 = idle CTAs retire when the frame runs thin, bit 2 = level-0 rays are generated inside k_frame
 	uint32_t sms;              // SM count (k_frame: CTAs below this index never retire)
 	uint32_t retire_rays;      // k_frame: CTA i >= sms retires when idle and outstanding < (i - sms + 1) * retire_rays
 	uint32_t pad_[2];

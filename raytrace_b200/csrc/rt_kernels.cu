@@ -117,6 +117,16 @@ __device__ __forceinline__ void lane_stats(WaveState *ws, uint32_t kind, uint32_
 
 // ---- ray generation ------------------------------------------------------------------------------
 
+// RayTracer::parallelRT, RayTracer.cpp:20-27: dir = cam.n + cam.u*(xcur*dp) + cam.v*(ycur*dp), then Ray() normalises
+__device__ __forceinline__ F3 primary_dir(const FrameParams &F, uint32_t i)
+{
+	int x, y;
+	slot_to_pixel(F, i, x, y);
+	const int xcur = x - F.half_w, ycur = y - F.half_h;
+	const float sx = (float)(xcur * F.dp), sy = (float)(ycur * F.dp);
+	return normalize((f3(F.cam_n) + f3(F.cam_u) * sx) + f3(F.cam_v) * sy);
+}
+
 __global__ void __launch_bounds__(256) k_raygen(const FrameParams *__restrict__ Fp, LevelBuf L, uint32_t n)
 {
 	const FrameParams &F = *Fp;
@@ -447,6 +457,7 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_frame(SceneDev S, const Fram
 	const uint32_t lane = threadIdx.x & 31u;
 	const bool refraction = F.type != RT_TYPE_REFLECT;
 	const bool wantShadows = F.type != RT_TYPE_DEPTH && F.type != RT_TYPE_NORMAL && F.type != RT_TYPE_TEXTURE && F.type != RT_TYPE_MATERIAL;
+	const bool genPrimary = (F.sched_flags & 4u) != 0u;   // level-0 rays are generated here, k_raygen did not run
 	TravStats st = { 0, 0, 0 };
 	uint32_t idleSpins = 0;
 	// Work this warp has claimed but not done yet.  A claim (one atomicAdd on a queue head) may run
@@ -530,8 +541,13 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_frame(SceneDev S, const Fram
 		{
 			if (pKind == 0u)
 			{
-				m = __ldcg(&L.ray_meta[pSlot]);
-				ready = (m.y >> 16) == F.epoch;
+				if (level == 0u && genPrimary)
+					m = make_uint2(RT_ID_NONE, (uint32_t)MY_RAY_BASERAY_ | (F.epoch << 16)), ready = true;   // made in place below
+				else
+				{
+					m = __ldcg(&L.ray_meta[pSlot]);
+					ready = (m.y >> 16) == F.epoch;
+				}
 			}
 			else
 			{
@@ -620,8 +636,18 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_frame(SceneDev S, const Fram
 			uint2 metaFlec = make_uint2(0, 0), metaFrac = metaFlec;
 			float fracRfr = 1.0f;
 			int4 aux = make_int4(-1, -1, -1, 0);
-			__threadfence();   // the stamp was seen: order the payload reads after it
-			const float4 o4 = __ldcg(&L.ray_o[i]), d4 = __ldcg(&L.ray_d[i]);
+			float4 o4, d4;
+			if (level == 0u && genPrimary)
+			{
+				// primary rays never exist in memory: no k_raygen launch, no 40-byte record written and read back
+				const F3 d = primary_dir(F, i);
+				o4 = make_float4(F.cam_pos.x, F.cam_pos.y, F.cam_pos.z, 1.0f), d4 = make_float4(d.x, d.y, d.z, 1.0f);
+			}
+			else
+			{
+				__threadfence();   // the stamp was seen: order the payload reads after it
+				o4 = __ldcg(&L.ray_o[i]), d4 = __ldcg(&L.ray_d[i]);
+			}
 			RayD ray;
 			ray.o = f3(o4), ray.d = f3(d4), ray.mtlrfr = o4.w;
 			ray.skip = m.x, ray.type = (uint8_t)(m.y & 0xFF), ray.isInside = (uint8_t)((m.y >> 8) & 0xFF);
@@ -647,6 +673,8 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_frame(SceneDev S, const Fram
 				const Surface sf = surface_attributes(S, ray, P, best.id);
 				L.hit_n[i] = make_float4(sf.N.x, sf.N.y, sf.N.z, __int_as_float(sf.mtl));
 				L.hit_uv[i] = make_float4(sf.tu, sf.tv, __int_as_float(sf.tex), 0.0f);
+				if (level == 0u && genPrimary)
+					L.ray_d[i] = d4;   // the view direction of a surface is read again by k_shade
 				const float4 mP = ldg4(&S.materials[4 * sf.mtl + 3]);   // shiness, reflect, refract, rfr
 				const float bwc = d4.w;
 				aux.z = sf.mtl;
@@ -733,7 +761,7 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_frame(SceneDev S, const Fram
 
 // ---- shading: light loop of every surface of every level ------------------------------------------
 
-__global__ void __launch_bounds__(128) k_shade(SceneDev S, const FrameParams *__restrict__ Fp, LevelSet LS, const WaveState *__restrict__ ws)
+__global__ void __launch_bounds__(128) k_shade(SceneDev S, const FrameParams *__restrict__ Fp, LevelSet LS, const WaveState *__restrict__ ws, uint32_t resetHits)
 {
 	const FrameParams &F = *Fp;
 	const uint32_t level = blockIdx.y;
@@ -774,6 +802,8 @@ __global__ void __launch_bounds__(128) k_shade(SceneDev S, const FrameParams *__
 		}
 		const F3 c_all = mixmul(vc, mix_vd + mix_va) + mix_vsc;
 		L.color[i] = make_float4(c_all.x, c_all.y, c_all.z, hp.w);
+		if (resetHits)
+			L.hit_list[h] = 0u;   // every entry is read exactly once, here: leave the list zeroed for the next frame (k_frame reads 0 as "not published")
 	}
 }
 
@@ -1017,6 +1047,95 @@ __global__ void __launch_bounds__(256) k_combine(SceneDev S, const FrameParams *
 	}
 }
 
+// The same combine as ONE launch: a thread per pixel walks its own ray tree (children are linked by
+// aux.x / aux.y) depth first with an explicit stack and evaluates exactly the expression order of
+// k_combine -- reflect child first, then the refract child -- so the colours are bit-identical to the
+// level-by-level passes; nothing is written back to the levels.
+struct ResolveFrame
+{
+	F3 c;
+	float alpha, kr, kt;
+	int4 aux;
+};
+
+__global__ void __launch_bounds__(256) k_resolve(SceneDev S, const FrameParams *__restrict__ Fp, LevelSet LS, const WaveState *__restrict__ ws, uint8_t *__restrict__ out)
+{
+	const FrameParams &F = *Fp;
+	const uint32_t n = ws->count[0] < LS.l[0].capacity ? ws->count[0] : LS.l[0].capacity;
+	for (uint32_t px = blockIdx.x * blockDim.x + threadIdx.x; px < n; px += gridDim.x * blockDim.x)
+	{
+		ResolveFrame st[RT_MAX_LEVELS + 1];
+		int stage[RT_MAX_LEVELS + 1];
+		int d = 0;
+		uint32_t enter = px;      // slot to enter at depth d, or 0xFFFFFFFF when returning
+		float4 ret = make_float4(0, 0, 0, 0);
+		while (true)
+		{
+			if (enter != 0xFFFFFFFFu)
+			{
+				const LevelBuf &L = LS.l[d];
+				const float4 color = L.color[enter];
+				ResolveFrame &f = st[d];
+				f.aux = L.aux[enter];
+				f.c = f3(color), f.alpha = color.w;
+				if (f.aux.z >= 0 && (f.aux.w & 3))
+				{
+					const float4 mP = ldg4(&S.materials[4 * f.aux.z + 3]);
+					f.kr = mP.y, f.kt = mP.z;
+					stage[d] = 0;
+				}
+				else
+					stage[d] = 4;
+				enter = 0xFFFFFFFFu;
+			}
+			ResolveFrame &f = st[d];
+			int sg = stage[d];
+			if (sg == 0)
+			{
+				sg = 2;
+				if (f.aux.w & 1)
+				{
+					f.c = f.c * (1 - f.kr);
+					if (f.aux.x >= 0) { stage[d] = 1; enter = (uint32_t)f.aux.x; ++d; continue; }
+				}
+			}
+			if (sg == 1)
+			{
+				f.c = f.c + f3(ret) * f.kr;
+				sg = 2;
+			}
+			if (sg == 2)
+			{
+				sg = 4;
+				if (f.aux.w & 2)
+				{
+					f.c = f.c * (1 - f.kt);
+					if (f.aux.y >= 0) { stage[d] = 3; enter = (uint32_t)f.aux.y; ++d; continue; }
+				}
+			}
+			if (sg == 3)
+			{
+				F3 vcf = f3(1, 1, 1);
+				if (f.aux.w & 4)
+				{
+					// Beer's law on the way out of the medium, RayTracer.cpp:585-590
+					const F3 e = (f3(ldg4(&S.materials[4 * f.aux.z + 1])) * 0.15f) * (-ret.w);
+					vcf = f3(exp_ref(e.x), exp_ref(e.y), exp_ref(e.z));
+				}
+				f.c = f.c + mixmul(f3(ret), vcf) * f.kt;
+			}
+			ret = make_float4(f.c.x, f.c.y, f.c.z, f.alpha);
+			if (d == 0)
+				break;
+			--d;
+		}
+		int x, y;
+		slot_to_pixel(F, px, x, y);
+		uint8_t *o = out + ((size_t)y * F.width + x) * 3;
+		o[0] = put8(ret.x), o[1] = put8(ret.y), o[2] = put8(ret.z);
+	}
+}
+
 // ---- launchers -----------------------------------------------------------------------------------
 
 static inline unsigned grid_for(uint32_t n, unsigned block, unsigned maxBlocks)
@@ -1066,10 +1185,10 @@ void rtk_frame(cudaStream_t st, const SceneDev &S, const FrameParams *F, const L
 	else k_frame<false, RT_CTAS_PER_SM><<<g, RT_BLOCK, 0, st>>>(S, F, LS, ws);
 }
 
-void rtk_shade(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelSet &LS, const WaveState *ws, uint32_t levels, uint32_t maxRays, unsigned sms)
+void rtk_shade(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelSet &LS, const WaveState *ws, uint32_t levels, uint32_t maxRays, unsigned sms, bool resetHits)
 {
 	const dim3 g(grid_for(maxRays, 128, sms * 8), levels);
-	k_shade<<<g, 128, 0, st>>>(S, F, LS, ws);
+	k_shade<<<g, 128, 0, st>>>(S, F, LS, ws, resetHits ? 1u : 0u);
 }
 
 void rtk_debug(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, uint32_t n, uint8_t *out, unsigned sms)
@@ -1081,6 +1200,11 @@ void rtk_reset_hits(cudaStream_t st, const LevelSet &LS, const WaveState *ws, ui
 {
 	const dim3 g(grid_for(maxRays, 256, sms * 4), levels);
 	k_reset_hits<<<g, 256, 0, st>>>(LS, ws);
+}
+
+void rtk_resolve(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelSet &LS, const WaveState *ws, uint8_t *out, uint32_t nPix, unsigned sms)
+{
+	k_resolve<<<grid_for(nPix, 256, sms * 32), 256, 0, st>>>(S, F, LS, ws, out);
 }
 
 void rtk_combine(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const LevelBuf &N, const WaveState *ws,

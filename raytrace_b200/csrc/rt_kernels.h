@@ -48,7 +48,9 @@ void rtk_wave(cudaStream_t st, const SceneDev &S, const FrameParams *F, const Le
 	uint32_t level, bool traceOn, bool shadowOn, float zNear, uint32_t maxItems, unsigned sms, bool stats, unsigned ctasPerSm = 0);
 // whole-frame persistent scheduler (all ray levels in one launch)
 void rtk_frame(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelSet &LS, WaveState *ws, uint32_t nPix, unsigned sms, bool stats, unsigned ctasPerSm = 0);
-void rtk_shade(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelSet &LS, const WaveState *ws, uint32_t levels, uint32_t maxRays, unsigned sms);
+void rtk_shade(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelSet &LS, const WaveState *ws, uint32_t levels, uint32_t maxRays, unsigned sms, bool resetHits = false);
+// one-launch post-order combine of every pixel's ray tree + Color::put (same arithmetic as rtk_combine level by level)
+void rtk_resolve(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelSet &LS, const WaveState *ws, uint8_t *out, uint32_t nPix, unsigned sms);
 void rtk_debug(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, uint32_t n, uint8_t *out, unsigned sms);
 void rtk_intersect_object(cudaStream_t st, const SceneDev &S, uint32_t primBegin, uint32_t primEnd, int modelIndex, const void *rays, const void *in,
 	const uint32_t *skipIds, float minT, uint32_t *outIds, void *out, uint32_t n);

@@ -1,0 +1,103 @@
+"""GPU tests of the frame pipelines (several frames in flight over one resident scene) and of the
+fused frame kernels (ray generation inside k_frame, one-launch combine)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import raytrace_b200 as R
+from parity_util import oracle_render
+
+pytestmark = pytest.mark.gpu
+rt = R.rt
+
+
+def ck(rc):
+    assert rc == 0, rt.rt_last_error().decode()
+
+
+def read(ctx, w, h):
+    out = np.empty((h, w, 3), dtype=np.uint8)
+    ck(rt.rt_wait(ctx, None))
+    ck(rt.rt_read_output(ctx, out.ctypes.data_as(C.c_void_p), w * 3))
+    return out
+
+
+def test_shared_pipelines_render_the_parents_scene_concurrently(gpu_present):
+    w, h, level = 512, 384, 4
+    sc = R.Scene("t_mesh", w, h)
+    oimg, _, oc = oracle_render(sc, level, want_ids=False)
+    parent = C.c_void_p()
+    ck(rt.rt_create(0, C.byref(parent)))
+    ck(rt.rt_upload_scene(parent, sc.flatten()))
+    pipes = []
+    for share in (4, 2, 1, 0):
+        p = C.c_void_p()
+        ck(rt.rt_create_shared(parent, C.byref(p)))
+        ck(rt.rt_set_sm_share(p, share))
+        pipes.append(p)
+    params = R.RenderParams(R.MY_MODEL_RAYTRACE, level, 0, 1, 0, 64)
+    for rep in range(3):                       # 12 frames, 4 in flight at any time
+        for p in pipes:
+            ck(rt.rt_render_async(p, C.byref(params)))
+    for p in pipes:
+        assert np.array_equal(read(p, w, h), oimg)
+        c = R.Counters()
+        ck(rt.rt_read_counters(p, C.byref(c)))
+        assert c.primary + c.shadow + c.reflect + c.refract == oc.primary + oc.shadow + oc.reflect + oc.refract
+    # a scene edit uploaded through ANY pipeline reaches all of them (they alias the parent's tables)
+    sc.move(R.MY_MODEL_OBJECT, 2, 0.4, 0.0, -0.6)       # moves the mesh: clTri + BVH rebuilt on the device
+    ck(rt.rt_upload_scene(pipes[1], sc.flatten()))
+    oimg2, _, _ = oracle_render(sc, level, want_ids=False)
+    assert not np.array_equal(oimg2, oimg)
+    for p in pipes:
+        ck(rt.rt_render_async(p, C.byref(params)))
+    for p in pipes:
+        assert np.array_equal(read(p, w, h), oimg2)
+    assert rt.rt_set_sm_share(pipes[0], 9) != 0
+    for p in pipes:
+        rt.rt_destroy(p)
+    rt.rt_destroy(parent)
+
+
+def test_tracers_of_one_scene_share_residency_and_overlap(gpu_present):
+    # the reference's idiom for several views: one RayTracer per view over the same Scene
+    w, h, level = 448, 320, 3
+    sc = R.Scene("t_mixed", w, h)
+    oimg, _, _ = oracle_render(sc, level, want_ids=False)
+    tracers = [R.RayTracer(sc) for _ in range(3)]
+    for t in tracers:
+        t.maxLevel = level
+        t.smShare = 2
+    for rep in range(2):
+        for t in tracers:
+            t.wait()
+            t.start(R.MY_MODEL_RAYTRACE)
+    for t in tracers:
+        assert np.array_equal(t.output(), oimg)
+    # only the first start() uploaded the scene; the others found it resident
+    assert tracers[0].counters().bvh_nodes == tracers[2].counters().bvh_nodes
+
+
+@pytest.mark.parametrize("scene,level", [("t_mesh", 5), ("c4", 6), ("c2", 3), ("c3", 5), ("t_mixed", 4)])
+def test_tree_walk_combine_equals_level_by_level_combine(gpu_present, scene, level):
+    w, h = 384, 256
+    sc = R.Scene(scene, w, h, {"c2": 6, "c4": 48, "c3": 48}.get(scene, 0), 3 if scene in ("c3", "c4") else 0)
+    a = R.RayTracer(sc)
+    a.maxLevel = level
+    one = a.render(R.MY_MODEL_RAYTRACE)
+    lv = a.render(R.MY_MODEL_RAYTRACE, flags=R.RT_FLAG_COMBINE_LEVELS)
+    assert np.array_equal(one, lv)
+    assert a.counters().launches > 3                   # the diagnostic flag really took the level-by-level path
+
+
+def test_whole_frame_scheduler_launches_three_kernels(gpu_present, monkeypatch):
+    monkeypatch.setenv("RT_B200_SCHED", "frame")
+    sc = R.Scene("c3", 320, 256, 48, 3)                # mirror mesh + plane: no refraction, every ray tree is a chain
+    t = R.RayTracer(sc)
+    t.maxLevel = 5
+    img = t.render(R.MY_MODEL_RAYTRACE)
+    c = t.counters()
+    assert c.frame_sched == 1 and c.launches == 3      # k_frame (makes its own primary rays), k_shade, k_resolve
+    oimg, _, _ = oracle_render(sc, 5, want_ids=False)
+    assert np.array_equal(img, oimg)
