@@ -450,6 +450,16 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_wave(SceneDev S, const Frame
 // "outstanding == 0" means the frame is complete and every warp may leave.
 __device__ __forceinline__ uint32_t vload(const uint32_t *p) { return *(const volatile uint32_t *)p; }
 
+// queue q of the claim scan -> level | light << 8: ray queues first (shallowest or deepest level first),
+// then the shadow queues by (level, light)
+__device__ __forceinline__ uint32_t queue_code(uint32_t q, uint32_t nL, uint32_t nEnabled, uint32_t schedFlags)
+{
+	if (q < nL)
+		return (schedFlags & 1u) ? nL - 1u - q : q;
+	const uint32_t s = q - nL, e = nEnabled ? nEnabled : 1u;
+	return (s / e) | ((s % e) << 8);
+}
+
 template<bool STATS, int CTAS>
 __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_frame(SceneDev S, const FrameParams *__restrict__ Fp, LevelSet LS, WaveState *ws)
 {
@@ -465,6 +475,8 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_frame(SceneDev S, const Fram
 	// blocking the lanes whose work is ready, until it is published or the frame is over.
 	// pKind 0: closest-hit rays of level pLevel; pKind 1: shadow rays of level pLevel towards light pLight.
 	uint32_t pKind = 0, pLevel = 0, pLight = 0, pSlot = 0xFFFFFFFFu;
+	const uint32_t nL = F.max_level + 1u, nQ = nL + (wantShadows ? nL * F.n_enabled : 0u);
+	const uint32_t myQueue = queue_code(lane, nL, F.n_enabled, F.sched_flags);
 	uint32_t statNodes = 0, statKind = 0;   // RT_FLAG_STATS: node visits of the lane's last ray
 	while (true)
 	{
@@ -482,7 +494,6 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_frame(SceneDev S, const Fram
 			// would hand every warp 2-3 rays: pass 0 only takes full batches of 32, pass 1 (nothing full
 			// anywhere) whatever exists, so the tail of the frame still drains. ----------------------------
 			uint32_t kind = 0xFFFFFFFFu, level = 0, light = 0, base = 0, nb = 0;
-			const uint32_t nL = F.max_level + 1u, nQ = nL + (wantShadows ? nL * F.n_enabled : 0u);
 			for (int pass = 0; pass < 2 && kind == 0xFFFFFFFFu; ++pass)
 				for (uint32_t q0 = 0; q0 < nQ && kind == 0xFFFFFFFFu; q0 += 32u)
 				{
@@ -492,16 +503,13 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_frame(SceneDev S, const Fram
 					if (q < nQ)
 					{
 						uint32_t cnt;
+						// which queue this lane looks at: decoded once per frame for the first 32 queues (myQueue)
+						const uint32_t code = q0 == 0u ? myQueue : queue_code(q, nL, F.n_enabled, F.sched_flags);
+						qLevel = code & 0xFFu, qLight = code >> 8;
 						if (q < nL)
-						{
-							qLevel = (F.sched_flags & 1u) ? nL - 1u - q : q;
 							cnt = vload(&ws->count[qLevel]), head = &ws->head_trace[qLevel];
-						}
 						else
-						{
-							qLevel = (q - nL) / F.n_enabled, qLight = (q - nL) % F.n_enabled;
 							cnt = vload(&ws->n_hit[qLevel]), head = &ws->head_light[qLevel][qLight];
-						}
 						cap = LS.l[qLevel].capacity;
 						cnt = cnt < cap ? cnt : cap;
 						const uint32_t h = vload(head);
