@@ -180,6 +180,8 @@ def main():
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: how the row tiles reach rank 0 -- one-sided NVLink peer copies on the copy engines (rt_push_rows) or an NCCL gather")
     ap.add_argument("--pipelines", type=int, default=0, help="frames in flight per GPU (0 = 3 at N=1, 4 at N>1)")
     ap.add_argument("--sm-share", type=int, default=-1, help="resident traversal CTAs per SM per pipeline (-1 = 4 at N=1, 2 at N>1)")
     args = ap.parse_args()
@@ -224,7 +226,8 @@ def main():
     ck(R.rt.rt_upload_scene(owner, sc.flatten()), "rt_upload_scene")      # H2D of the scene + LBVH build, once
     tile_rows = 8 if world > 1 else 64           # fine interleave balances the ranks (sky rows are cheap)
     params = R.RenderParams(R.MY_MODEL_RAYTRACE, level, rank, world, 0, tile_rows)
-    from raytrace_b200.distributed import FrameGather
+    from raytrace_b200.distributed import FrameGather, FrameLanding
+    p2p = world > 1 and args.gather == "p2p"
     pipes = []
     for _ in range(M):
         hnd = C.c_void_p()
@@ -232,15 +235,25 @@ def main():
         st = torch.cuda.Stream(dev)
         ck(R.rt.rt_set_stream(hnd, C.c_void_p(st.cuda_stream)), "rt_set_stream")
         ck(R.rt.rt_set_sm_share(hnd, share if M > 1 else 0), "rt_set_sm_share")
-        frame = torch.full((h, w, 3), 127, dtype=torch.uint8, device=dev)
-        ck(R.rt.rt_set_output(hnd, C.c_void_p(frame.data_ptr()), frame.numel()), "rt_set_output")
-        pipes.append({"ctx": hnd, "stream": st, "frame": frame,
-                      "gather": FrameGather(w, h, rank, world, dev, tile_rows) if world > 1 else None})
+        frame, landing = None, None
+        if p2p:
+            # rank 0 renders straight into the landing buffer the other ranks push their rows to
+            landing = FrameLanding(hnd, w, h, rank, world)
+            if rank == 0:
+                ptr, nbytes = landing.device_ptr()
+                ck(R.rt.rt_set_output(hnd, C.c_void_p(ptr), nbytes), "rt_set_output")
+        if frame is None and not (p2p and rank == 0):
+            frame = torch.full((h, w, 3), 127, dtype=torch.uint8, device=dev)
+            ck(R.rt.rt_set_output(hnd, C.c_void_p(frame.data_ptr()), frame.numel()), "rt_set_output")
+        pipes.append({"ctx": hnd, "stream": st, "frame": frame, "landing": landing,
+                      "gather": FrameGather(w, h, rank, world, dev, tile_rows) if world > 1 and not p2p else None})
 
     def step(k):
         p = pipes[k % M]
         ck(R.rt.rt_render_async(p["ctx"], C.byref(params)), "rt_render_async")
-        if p["gather"] is not None:
+        if p["landing"] is not None:
+            p["landing"].push(p["ctx"])          # NVLink P2P: this rank's row tiles -> their place in rank 0's frame (copy engines) + signal
+        elif p["gather"] is not None:
             with torch.cuda.stream(p["stream"]):
                 p["gather"].gather(p["frame"])   # NCCL: this rank's row tiles -> rank 0, de-interleaved there
 
@@ -318,7 +331,11 @@ def main():
     cs = R.Counters()
     ck(R.rt.rt_read_counters(p0, C.byref(cs)), "rt_read_counters")
     torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()                           # nobody unmaps a landing buffer another rank may still push to
     for p in pipes:
+        if p["landing"] is not None:
+            p["landing"].close()
         R.rt.rt_destroy(p["ctx"])
     R.rt.rt_destroy(owner)
 
@@ -364,7 +381,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.config}: {desc}", "rays_per_frame": rays_total, "pixels": w * (h // 64 * 64) if w % 64 == 0 else (w // 64 * 64) * (h // 64 * 64),
                        "l2_policy": "per-frame working set (ray/hit/node queues + BVH + triangles, > 500 MB touched per frame) exceeds the 126 MB L2; no flush needed",
-                       "parallelism": f"image-space: interleaved {tile_rows}-row tiles over {world} GPUs, NCCL gather of RGB8 tiles to rank 0" if world > 1 else "single GPU",
+                       "parallelism": (f"image-space: interleaved {tile_rows}-row tiles over {world} GPUs, " + ("row tiles pushed into rank 0's frame over NVLink P2P (copy engines, put with signal; NCCL only ships the IPC handles)" if p2p else "NCCL gather of RGB8 tiles to rank 0")) if world > 1 else "single GPU",
                        "frames_in_flight": M, "traversal_ctas_per_sm_per_pipeline": (share if M > 1 and share else 8),
                        "ms_per_frame_alone": stage["render"]},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": float(e2e_s.item()) / args.steps * 1e3,

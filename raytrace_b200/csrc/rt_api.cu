@@ -788,6 +788,148 @@ extern "C" int rt_output_device(rt_ctx *c, void **ptr, size_t *bytes)
 	return RT_OK;
 }
 
+// ---- NVLink frame gather without SM work: one-sided put with signal ----------------------------------
+// The traversal kernels are persistent and fill every SM, so a gather that needs kernels of its own
+// (pack, NCCL send/recv, unpack) queues behind them.  Here the destination rank exposes a frame-sized
+// "landing" buffer over CUDA IPC; every rank copies its row tiles straight to their final offsets in
+// it with ONE strided peer-to-peer copy on the copy engines (tiles of one rank are `world` tiles
+// apart in both frames), then writes the frame's sequence number into its flag word behind the data;
+// the destination waits for the flags with a stream wait-value.  No pack, no unpack, no SM.
+struct rt_landing
+{
+	uint8_t *base = nullptr;      // frame bytes, then 64 flag words (one per rank)
+	size_t frameBytes = 0;
+	int width = 0, height = 0, device = 0;
+	bool owner = false;
+	uint64_t *hSeq = nullptr;     // pinned ring: source of the flag copies when stream mem-ops are unavailable
+};
+#define RT_LANDING_FLAGS 64
+#define RT_LANDING_RING 4096
+
+typedef int (*StreamValue64Fn)(cudaStream_t, unsigned long long, unsigned long long, unsigned int);
+static StreamValue64Fn driver_fn(const char *name)
+{
+	void *fn = nullptr;
+	cudaDriverEntryPointQueryResult q;
+	if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+	{
+		cudaGetLastError();
+		return nullptr;
+	}
+	return (StreamValue64Fn)fn;
+}
+
+extern "C" int rt_landing_create(rt_ctx *c, int width, int height, rt_landing **out, void *ipc_handle64)
+{
+	if (!c || !out || !ipc_handle64 || width <= 0 || height <= 0) return fail(RT_E_INVALID, "rt_landing_create: bad argument");
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+	CU(cudaSetDevice(c->device));
+	rt_landing *L = new rt_landing();
+	L->frameBytes = (size_t)width * height * 3, L->width = width, L->height = height, L->device = c->device, L->owner = true;
+	const size_t total = ((L->frameBytes + 255) & ~(size_t)255) + RT_LANDING_FLAGS * sizeof(uint64_t);
+	if (cudaMalloc(&L->base, total) != cudaSuccess) { delete L; return fail(RT_E_CUDA, "rt_landing_create: cudaMalloc of %zu bytes failed", total); }
+	CU(cudaMemset(L->base, 127, L->frameBytes));
+	CU(cudaMemset(L->base + ((L->frameBytes + 255) & ~(size_t)255), 0, RT_LANDING_FLAGS * sizeof(uint64_t)));
+	CU(cudaHostAlloc(&L->hSeq, RT_LANDING_RING * sizeof(uint64_t), cudaHostAllocDefault));
+	CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)ipc_handle64, L->base));
+	*out = L;
+	return RT_OK;
+}
+
+extern "C" int rt_landing_open(rt_ctx *c, int width, int height, const void *ipc_handle64, rt_landing **out)
+{
+	if (!c || !out || !ipc_handle64 || width <= 0 || height <= 0) return fail(RT_E_INVALID, "rt_landing_open: bad argument");
+	CU(cudaSetDevice(c->device));
+	rt_landing *L = new rt_landing();
+	L->frameBytes = (size_t)width * height * 3, L->width = width, L->height = height, L->device = c->device, L->owner = false;
+	cudaIpcMemHandle_t h;
+	memcpy(&h, ipc_handle64, sizeof h);
+	void *p = nullptr;
+	if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+	{
+		const cudaError_t e = cudaGetLastError();
+		delete L;
+		return fail(RT_E_CUDA, "rt_landing_open: cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+	}
+	L->base = (uint8_t *)p;
+	CU(cudaHostAlloc(&L->hSeq, RT_LANDING_RING * sizeof(uint64_t), cudaHostAllocDefault));
+	*out = L;
+	return RT_OK;
+}
+
+extern "C" void rt_landing_close(rt_landing *L)
+{
+	if (!L) return;
+	cudaSetDevice(L->device);
+	if (L->owner) cudaFree(L->base);
+	else cudaIpcCloseMemHandle(L->base);
+	cudaFreeHost(L->hSeq);
+	delete L;
+}
+
+extern "C" int rt_landing_ptr(rt_landing *L, void **device_ptr, size_t *bytes)
+{
+	if (!L || !device_ptr) return fail(RT_E_INVALID, "rt_landing_ptr: NULL argument");
+	*device_ptr = L->base;
+	if (bytes) *bytes = L->frameBytes;
+	return RT_OK;
+}
+
+static uint64_t *landing_flags(rt_landing *L) { return (uint64_t *)(L->base + ((L->frameBytes + 255) & ~(size_t)255)); }
+
+extern "C" int rt_push_rows(rt_ctx *c, rt_landing *L, uint64_t seq)
+{
+	if (!c || !L) return fail(RT_E_INVALID, "rt_push_rows: NULL argument");
+	if (!c->fb) return fail(RT_E_STATE, "rt_push_rows: nothing rendered yet");
+	if (c->outW != L->width || c->outH != L->height) return fail(RT_E_INVALID, "rt_push_rows: frame is %dx%d, landing buffer %dx%d", c->outW, c->outH, L->width, L->height);
+	CU(cudaSetDevice(c->device));
+	const rt_render_params &p = c->lastParams;
+	const uint32_t world = p.world > 1 ? p.world : 1, rank = p.world > 1 ? p.rank : 0;
+	if (rank >= RT_LANDING_FLAGS) return fail(RT_E_LIMIT, "rt_push_rows: rank %u (landing buffers hold %d flags)", rank, RT_LANDING_FLAGS);
+	const uint32_t tileRows = p.tile_rows ? p.tile_rows : 64u;
+	const size_t tileBytes = (size_t)tileRows * c->outW * 3;
+	const uint32_t tiles = (uint32_t)(c->outH / 64) * 64u / tileRows;
+	const uint32_t mine = tiles > rank ? (tiles - rank + world - 1) / world : 0;
+	cudaStream_t st = c->stream;
+	if (mine && c->fb != L->base)
+		CU(cudaMemcpy2DAsync(L->base + rank * tileBytes, world * tileBytes, c->fb + rank * tileBytes, world * tileBytes, tileBytes, mine, cudaMemcpyDeviceToDevice, st));
+	// the flag goes out behind the data on the same stream
+	static const StreamValue64Fn writeValue = driver_fn("cuStreamWriteValue64");
+	uint64_t *flag = landing_flags(L) + rank;
+	if (!writeValue || writeValue(st, (unsigned long long)(uintptr_t)flag, seq, 0u) != 0)
+	{
+		{ static bool told = false; if (!told) { told = true; fprintf(stderr, "raytrace_b200: cuStreamWriteValue64 unavailable (%s), rt_push_rows signals with a copy\n", writeValue ? "call failed" : "no entry point"); } }
+		uint64_t *src = &L->hSeq[seq % RT_LANDING_RING];
+		*src = seq;
+		CU(cudaMemcpyAsync(flag, src, sizeof(uint64_t), cudaMemcpyDefault, st));
+	}
+	return RT_OK;
+}
+
+extern "C" int rt_landing_wait(rt_ctx *c, rt_landing *L, uint64_t seq, uint32_t world)
+{
+	if (!c || !L) return fail(RT_E_INVALID, "rt_landing_wait: NULL argument");
+	if (world > RT_LANDING_FLAGS) return fail(RT_E_LIMIT, "rt_landing_wait: world %u", world);
+	CU(cudaSetDevice(c->device));
+	static const StreamValue64Fn waitValue = driver_fn("cuStreamWaitValue64");
+	for (uint32_t r = 0; r < world; ++r)
+	{
+		uint64_t *flag = landing_flags(L) + r;
+		// CU_STREAM_WAIT_VALUE_GEQ (0) | CU_STREAM_WAIT_VALUE_FLUSH (1 << 30): the peers' row data is visible once the flag is
+		// (a peer's flag is written by a stream operation that starts only after its row copy has completed)
+		if (waitValue && waitValue(c->stream, (unsigned long long)(uintptr_t)flag, seq, 0u | (1u << 30)) == 0)
+			continue;
+		if (waitValue && waitValue(c->stream, (unsigned long long)(uintptr_t)flag, seq, 0u) == 0)   // device cannot flush remote writes: plain >= wait
+			continue;
+		// no stream mem-ops: wait on the host (still no kernel)
+		{ static bool told = false; if (!told) { told = true; fprintf(stderr, "raytrace_b200: cuStreamWaitValue64 unavailable (%s), rt_landing_wait falls back to a host wait\n", waitValue ? "call failed" : "no entry point"); } }
+		CU(cudaStreamSynchronize(c->stream));
+		uint64_t v = 0;
+		do CU(cudaMemcpy(&v, flag, sizeof v, cudaMemcpyDeviceToHost)); while (v < seq);
+	}
+	return RT_OK;
+}
+
 extern "C" int rt_host_alloc(void **ptr, size_t bytes)
 {
 	if (!ptr) return fail(RT_E_INVALID, "rt_host_alloc: ptr is NULL");

@@ -5,6 +5,8 @@ smaller tiles balance the ranks better); tile t is rendered by rank t % world.  
 collective is one gather of the finished RGB8 bands to rank 0 per frame (NCCL over NVLink on GPUs,
 gloo in the CPU tests).  Everything here is plumbing on torch tensors; the kernels live in csrc/.
 """
+import ctypes as C
+
 import torch
 import torch.distributed as dist
 
@@ -48,3 +50,47 @@ class FrameGather:
             if nb:
                 out[r::self.world].copy_(self.parts[r][:nb])
         return self.full
+
+
+class FrameLanding:
+    """One-sided gather over NVLink (include/rt_b200.h rt_landing_*): the destination rank owns a
+    frame-sized device buffer that every other rank maps over CUDA IPC; after a frame each rank
+    copies its row tiles straight to their final place in it (one strided peer copy on the copy
+    engines) and signals with a sequence number.  torch.distributed only ships the 64-byte handle."""
+
+    def __init__(self, ctx, width: int, height: int, rank: int, world: int, dst: int = 0):
+        from ._capi import rt
+
+        def _check(rc, what):
+            if rc != 0:
+                raise RuntimeError(f"{what} failed ({rc}): {rt.rt_last_error().decode()}")
+        self._rt, self._check = rt, _check
+        self.rank, self.world, self.dst, self.seq = rank, world, dst, 0
+        self._h = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        if rank == dst:
+            _check(rt.rt_landing_create(ctx, width, height, C.byref(self._h), handle), "rt_landing_create")
+        box = [bytes(handle) if rank == dst else None]
+        if world > 1:
+            dist.broadcast_object_list(box, src=dst)
+        if rank != dst:
+            buf = (C.c_ubyte * 64).from_buffer_copy(box[0])
+            _check(rt.rt_landing_open(ctx, width, height, buf, C.byref(self._h)), "rt_landing_open")
+
+    def device_ptr(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._check(self._rt.rt_landing_ptr(self._h, C.byref(p), C.byref(n)), "rt_landing_ptr")
+        return p.value, n.value
+
+    def push(self, ctx):
+        """Enqueue, behind the frame just rendered on `ctx`, the copy of this rank's rows + the signal;
+        on the destination rank also the wait for every rank's signal."""
+        self.seq += 1
+        self._check(self._rt.rt_push_rows(ctx, self._h, self.seq), "rt_push_rows")
+        if self.rank == self.dst:
+            self._check(self._rt.rt_landing_wait(ctx, self._h, self.seq, self.world), "rt_landing_wait")
+
+    def close(self):
+        if self._h:
+            self._rt.rt_landing_close(self._h)
+            self._h = C.c_void_p()

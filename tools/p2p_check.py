@@ -1,0 +1,96 @@
+"""torchrun helper: N ranks render their row tiles of one frame; the tiles reach rank 0 (a) through
+the one-sided NVLink landing buffer (rt_push_rows) and (b) through the NCCL gather; rank 0 compares
+both with its own full-frame render.  Exit code 0 = identical.  Used by tests/test_gpu_multi.py."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import raytrace_b200 as R
+from raytrace_b200.distributed import FrameGather, FrameLanding
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+w, h, level, tile_rows = 640, 448, 4, 8
+os.makedirs(f"/tmp/rt_p2p_{rank}", exist_ok=True)
+sc = R.Scene("c3", w, h, 96, 6, tmpdir=f"/tmp/rt_p2p_{rank}")
+
+
+def ck(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what}: {R.rt.rt_last_error().decode()}")
+
+
+owner = C.c_void_p()
+ck(R.rt.rt_create(local, C.byref(owner)), "rt_create")
+ck(R.rt.rt_upload_scene(owner, sc.flatten()), "rt_upload_scene")
+ok = True
+full = None
+if rank == 0:
+    ck(R.rt.rt_render_async(owner, C.byref(R.RenderParams(R.MY_MODEL_RAYTRACE, level, 0, 1, 0, 64))), "render full")
+    full = np.empty((h, w, 3), dtype=np.uint8)
+    ck(R.rt.rt_wait(owner, None), "rt_wait")
+    ck(R.rt.rt_read_output(owner, full.ctypes.data_as(C.c_void_p), w * 3), "rt_read_output")
+pipes = []
+for i in range(2):
+    p = C.c_void_p()
+    ck(R.rt.rt_create_shared(owner, C.byref(p)), "rt_create_shared")
+    st = torch.cuda.Stream(dev)
+    ck(R.rt.rt_set_stream(p, C.c_void_p(st.cuda_stream)), "rt_set_stream")
+    landing = FrameLanding(p, w, h, rank, world)
+    frame = None
+    if rank == 0:
+        ptr, nbytes = landing.device_ptr()
+        ck(R.rt.rt_set_output(p, C.c_void_p(ptr), nbytes), "rt_set_output")
+    else:
+        frame = torch.full((h, w, 3), 127, dtype=torch.uint8, device=dev)
+        ck(R.rt.rt_set_output(p, C.c_void_p(frame.data_ptr()), frame.numel()), "rt_set_output")
+    pipes.append((p, st, landing, frame))
+params = R.RenderParams(R.MY_MODEL_RAYTRACE, level, rank, world, 0, tile_rows)
+for k in range(6):                      # 3 frames per pipeline, 2 in flight
+    p, st, landing, frame = pipes[k % 2]
+    ck(R.rt.rt_render_async(p, C.byref(params)), "rt_render_async")
+    landing.push(p)
+for p, st, landing, frame in pipes:
+    ck(R.rt.rt_wait(p, None), "rt_wait")
+    st.synchronize()
+torch.cuda.synchronize(dev)
+dist.barrier()
+if rank == 0:
+    for p, st, landing, frame in pipes:
+        ptr, nbytes = landing.device_ptr()
+        got = np.empty((h, w, 3), dtype=np.uint8)
+        ck(R.rt.rt_read_output(p, got.ctypes.data_as(C.c_void_p), w * 3), "rt_read_output")   # the pipeline's output IS the landing buffer
+        same = bool(np.array_equal(got, full))
+        print("p2p landing == full frame:", same, flush=True)
+        ok = ok and same
+# (b) NCCL gather of the same shards
+p, st, landing, frame = pipes[0]
+if rank == 0:
+    frame = torch.full((h, w, 3), 127, dtype=torch.uint8, device=dev)
+    ck(R.rt.rt_set_output(p, C.c_void_p(frame.data_ptr()), frame.numel()), "rt_set_output")
+g = FrameGather(w, h, rank, world, dev, tile_rows)
+ck(R.rt.rt_render_async(p, C.byref(params)), "rt_render_async")
+with torch.cuda.stream(st):
+    out = g.gather(frame)
+st.synchronize()
+if rank == 0:
+    same = bool(np.array_equal(out.cpu().numpy(), full))
+    print("nccl gather == full frame:", same, flush=True)
+    ok = ok and same
+dist.barrier()
+for p, st, landing, frame in pipes:
+    landing.close()
+    R.rt.rt_destroy(p)
+R.rt.rt_destroy(owner)
+flag = torch.tensor([1 if ok else 0], device=dev)
+dist.broadcast(flag, 0)
+dist.destroy_process_group()
+sys.exit(0 if int(flag.item()) == 1 else 1)
