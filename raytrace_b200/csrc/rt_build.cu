@@ -474,6 +474,96 @@ __global__ void k_copy_order(const uint32_t *sorted, uint32_t n, uint32_t *out)
 	if (i < n) out[i] = sorted[i];
 }
 
+// ---- collapse to 4-wide nodes, surface-area guided ---------------------------------------------------
+// Top-down, one launch per level of the 4-wide tree.  A 4-wide node starts with the two children of
+// its binary node and keeps opening the inner child with the LARGEST surface area (the one a ray
+// is most likely to enter anyway) until it has four children or only leaves are left.  Compared with
+// "every even-depth node adopts its grandchildren" this fills the four slots where the fixed pattern
+// leaves one empty next to every leaf child, and it cuts across the binary tree where the LBVH split
+// was lopsided.  Nodes are allocated in breadth-first order, so the top of the tree is contiguous.
+struct Collapse4Args
+{
+	const BvhNode *nodes;      // binary nodes, links are global indices (leaves < 0)
+	BvhNode4 *nodes4;
+	const int2 *frontier;      // (binary node, 4-wide slot), both global indices
+	int2 *next;
+	uint32_t *counters;        // [level] = frontier length of level + 1, [127] = slots handed out
+	uint32_t level, nodeBase;
+};
+
+__device__ __forceinline__ float box_area(const float *lo, const float *hi)
+{
+	const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+	return dx * dy + dy * dz + dz * dx;
+}
+
+__device__ __forceinline__ void node_child(const BvhNode &n, int side, float *lo, float *hi, int &link)
+{
+	if (side == 0) lo[0] = n.a.x, lo[1] = n.a.y, lo[2] = n.a.z, hi[0] = n.a.w, hi[1] = n.b.x, hi[2] = n.b.y, link = n.link.x;
+	else lo[0] = n.b.z, lo[1] = n.b.w, lo[2] = n.c.x, hi[0] = n.c.y, hi[1] = n.c.z, hi[2] = n.c.w, link = n.link.y;
+}
+
+__global__ void k_collapse4_sah(Collapse4Args a)
+{
+	const uint32_t nFrontier = a.level == 0 ? 1u : a.counters[a.level - 1];
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nFrontier; i += gridDim.x * blockDim.x)
+	{
+		const int2 item = a.level == 0 ? make_int2((int)a.nodeBase, (int)a.nodeBase) : a.frontier[i];
+		float lo[4][3], hi[4][3];
+		int link[4];
+		const BvhNode root = a.nodes[item.x];
+		node_child(root, 0, lo[0], hi[0], link[0]);
+		node_child(root, 1, lo[1], hi[1], link[1]);
+		int m = 2;
+		while (m < 4)
+		{
+			int best = -1;
+			float bestArea = -1.0f;
+			for (int k = 0; k < m; ++k)
+				if (link[k] >= 0)
+				{
+					const float ar = box_area(lo[k], hi[k]);
+					if (ar > bestArea) bestArea = ar, best = k;
+				}
+			if (best < 0) break;
+			const BvhNode c = a.nodes[link[best]];
+			node_child(c, 0, lo[best], hi[best], link[best]);
+			node_child(c, 1, lo[m], hi[m], link[m]);
+			++m;
+		}
+		int inner = 0;
+		for (int k = 0; k < m; ++k) inner += link[k] >= 0;
+		if (inner)
+		{
+			const uint32_t slot0 = atomicAdd(&a.counters[127], (uint32_t)inner);
+			const uint32_t q0 = atomicAdd(&a.counters[a.level], (uint32_t)inner);
+			int j = 0;
+			for (int k = 0; k < m; ++k)
+				if (link[k] >= 0)
+				{
+					const int slot = (int)(a.nodeBase + 1u + slot0 + (uint32_t)j);
+					a.next[q0 + j] = make_int2(link[k], slot);
+					link[k] = slot;
+					++j;
+				}
+		}
+		// unused slot: a point far away -- |t| ~ 3e38/|d| on every axis always misses
+		const float far = 3.0e38f;
+		for (int k = m; k < 4; ++k)
+			lo[k][0] = lo[k][1] = lo[k][2] = hi[k][0] = hi[k][1] = hi[k][2] = far, link[k] = 0x7FFFFFFF;
+		BvhNode4 o;
+		o.lox = make_float4(lo[0][0], lo[1][0], lo[2][0], lo[3][0]);
+		o.loy = make_float4(lo[0][1], lo[1][1], lo[2][1], lo[3][1]);
+		o.loz = make_float4(lo[0][2], lo[1][2], lo[2][2], lo[3][2]);
+		o.hix = make_float4(hi[0][0], hi[1][0], hi[2][0], hi[3][0]);
+		o.hiy = make_float4(hi[0][1], hi[1][1], hi[2][1], hi[3][1]);
+		o.hiz = make_float4(hi[0][2], hi[1][2], hi[2][2], hi[3][2]);
+		o.link = make_int4(link[0], link[1], link[2], link[3]);
+		o.pad = make_int4(0, 0, 0, 0);
+		a.nodes4[item.y] = o;
+	}
+}
+
 int rtb_build(cudaStream_t st, BuildScratch **scratch, const float4 *box_lo, const float4 *box_hi, uint32_t n,
 	uint32_t leafSize, BvhNode *nodes, BvhNode4 *nodes4, uint32_t nodeBase, uint32_t leafBase, uint32_t *leafOrder, BvhBuildResult *res)
 {
@@ -504,10 +594,28 @@ int rtb_build(cudaStream_t st, BuildScratch **scratch, const float4 *box_lo, con
 	a.ilo = s->ilo, a.ihi = s->ihi, a.height = s->height, a.nodes = nodes;
 	a.nodeBase = nodeBase, a.leafBase = leafBase, a.leafSize = leafSize, a.n = (int)n;
 	k_refit<<<blocks, 256, 0, st>>>(a);
-	k_collapse4<<<blocks, 256, 0, st>>>(nodes, nodes4, s->parentOfInternal, nodeBase, (int)n - 1);
 	uint32_t depth = 0;
 	CK(cudaMemcpyAsync(&depth, s->height, sizeof depth, cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));
+	static const int collapseSah = []{ const char *e = getenv("RT_B200_COLLAPSE"); return (e && !strcmp(e, "even")) ? 0 : 1; }();
+	if (!collapseSah)
+		k_collapse4<<<blocks, 256, 0, st>>>(nodes, nodes4, s->parentOfInternal, nodeBase, (int)n - 1);
+	else
+	{
+		// children / range / flags are free again after the refit: frontier ping-pong and counters
+		CK(cudaMemsetAsync(s->flags, 0, sizeof(uint32_t) * 128, st));
+		Collapse4Args ca;
+		ca.nodes = nodes, ca.nodes4 = nodes4, ca.counters = s->flags, ca.nodeBase = nodeBase;
+		const unsigned cblocks = blocks < 2048 ? blocks : 2048;
+		for (uint32_t level = 0; level < depth && level < 120; ++level)   // a 4-wide level consumes at least one binary level
+		{
+			ca.level = level;
+			ca.frontier = (level & 1) ? s->range : s->children;
+			ca.next = (level & 1) ? s->children : s->range;
+			k_collapse4_sah<<<level < 4 ? 1 : cblocks, 256, 0, st>>>(ca);
+		}
+		CK(cudaStreamSynchronize(st));
+	}
 	res->root = (int)nodeBase;
 	res->nodesUsed = n - 1;
 	res->depth = depth;
