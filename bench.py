@@ -18,15 +18,19 @@ is quoted on).  A ray = one closest-hit or one shadow any-hit query (SURVEY.md 8
            RGB8 frame back into RayTracer::output (D2H) inside the timed region.  M RayTracer
            objects over the one Scene (the reference's idiom for several views) keep M frames in
            flight; step k waits for step k-M on the same tracer before it starts.
-  roofline FP32-issue roofline of the traversal kernel (k_wave, all launches of a frame): algorithmic FLOPs
-           from device counters (DESIGN.md "flop model") / their CUDA-event time, against
+  roofline FP32-issue roofline of the traversal kernel (k_frame, or the k_wave launches of a frame):
+           algorithmic FLOPs from device counters (DESIGN.md "flop model") / the kernel's CUDA-event
+           time in a frame rendered alone right after the timed region (inside it the launches of
+           different pipelines overlap, so a per-launch time is not defined there), against
            148 SMs x 128 lanes x sm_max_mhz of MEASURED_PEAKS.json (1 lane-instr = 1 flop because the
            parity path is unfused); HBM figures are reported beside it as the secondary bound.
   cpu_baseline  the reference's own CPU tracer (oracle/_ref/ref_render, else the oracle port) on
            the box's host cores, on a bounded tile sample of the same workload.
 
-N > 1 (torchrun): the frame is split into interleaved 64-row tiles (tile % N == rank), the scene is
-replicated, and the RGB8 rows are gathered to rank 0 over NCCL each step ("strong" scaling).
+N > 1 (torchrun): the frame is split into interleaved 8-row tiles (tile % N == rank), the scene is
+replicated, and every step each rank's rows are delivered into rank 0's frame ("strong" scaling):
+by default with one-sided NVLink peer copies on the copy engines (rt_push_rows; torch.distributed /
+NCCL only carries the IPC handles, barriers and timing reductions), with --gather nccl by an NCCL gather.
 `--impl reference` times the reference CPU tracer itself (rank 0 only).
 """
 import argparse
@@ -49,7 +53,7 @@ CONFIGS = {
     "c4": ("c4", 3840, 2160, 8, 0, 0, "4147200-triangle Model + 64 glass + 6 mirror spheres + plane, 3840x2160, depth 8"),
 }
 # DRAM bytes per traversal launch measured once with `ncu --set full` (profiles/), keyed by (config, gpus)
-NCU_TRAFFIC = {("c3", 1): 827223040}
+NCU_TRAFFIC = {("c3", 1): 736713216}
 REF_TILES = {"c1": 153, "c2": 12, "c3": 6, "c4": 2}   # 64x64 tiles per reference step (bounded sample)
 
 
@@ -217,8 +221,12 @@ def main():
             raise RuntimeError(f"{what}: {R.rt.rt_last_error().decode()}")
 
     # ---- frame pipelines: one resident scene, M frames in flight ---------------------------------
-    M = args.pipelines if args.pipelines > 0 else (3 if world == 1 else 4)
-    share = args.sm_share if args.sm_share >= 0 else (4 if world == 1 else 2)
+    # defaults from the sweeps in profiles/r1g_pipelines_sweep_c3.txt: the smaller a GPU's share of the frame,
+    # the more frames have to be in flight to keep its SMs busy; frames beyond ~3 M pixels per GPU run
+    # the per-level wave kernels, which want the whole GPU each (one pipeline)
+    big = w * h // world > 3_000_000
+    M = args.pipelines if args.pipelines > 0 else (1 if big else 3 if world == 1 else 4 if world < 8 else 8)
+    share = args.sm_share if args.sm_share >= 0 else (0 if M == 1 else 4 if world == 1 else 2 if world < 8 else 1)
     main = torch.cuda.current_stream(dev)
     owner = C.c_void_p()
     ck(R.rt.rt_create(local, C.byref(owner)), "rt_create")
@@ -389,7 +397,7 @@ def main():
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "fp32_issue", "kernel": "k_frame (one persistent launch per frame: closest-hit + shadow traversal of all levels)" if trav_launches == 1 else "k_wave (closest-hit level l fused with shadow any-hit level l-1; all launches of a frame)", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": f"148 SMs x 128 lanes x {peak_src} (of measured)",
-                         "traffic": NCU_TRAFFIC.get((args.config, world)), "traffic_source": "profiles/r1f_ncu_full_k_frame_c3.md (dram__bytes_read.sum + dram__bytes_write.sum of one k_frame launch)" if (args.config, world) in NCU_TRAFFIC else None,
+                         "traffic": NCU_TRAFFIC.get((args.config, world)), "traffic_source": "profiles/r1h_ncu_full_k_frame_c3.md (dram__bytes_read.sum + dram__bytes_write.sum of one k_frame launch)" if (args.config, world) in NCU_TRAFFIC else None,
                          "launches_per_step": trav_launches, "avg_launch_ms": trav_ms / trav_launches,
                          "flops_per_step": flops, "nodes_per_ray": cs.nodes_visited / max(rays_local, 1), "tri_tests_per_ray": cs.tri_tests / max(rays_local, 1),
                          "stage_ms_one_frame_alone": stage,
