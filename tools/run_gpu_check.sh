@@ -1,9 +1,4 @@
-set -x
-python bench.py --steps 100 --warmup 3 > gpurun_out/r1h_bench_c3_n1.json 2> gpurun_out/r1h_bench_c3_n1.err
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r1h_bench_ref_c3.json 2>/dev/null
-python bench.py --config c2 --steps 100 --warmup 3 --no-cpu-baseline > gpurun_out/r1h_bench_c2_n1.json 2>/dev/null
-python bench.py --config c4 --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r1h_bench_c4_n1.json 2>/dev/null
-python bench.py --config c1 --steps 100 --warmup 3 --no-cpu-baseline > gpurun_out/r1h_bench_c1_n1.json 2>/dev/null
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1h.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench_r1h.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_frame -s 4 -c 1 -o gpurun_out/prof_frame_r1h -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --pipelines 1 > gpurun_out/ncu_full_r1h.log 2>&1
-for f in gpurun_out/r1h_bench_*.json; do echo $f; cut -c1-260 $f; done
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+echo "--- refill on"; python tools/perf_probe.py c3 2>&1 | cut -c1-330; RT_PIPE_SHARE="4" RT_PIPE_M="3" python tools/pipe_probe.py c3 1 2>&1 | tail -1
+echo "--- refill off"; RT_B200_REFILL=0 python tools/perf_probe.py c3 2>&1 | cut -c1-330; RT_B200_REFILL=0 RT_PIPE_SHARE="4" RT_PIPE_M="3" python tools/pipe_probe.py c3 1 2>&1 | tail -1
+ncu --metrics smsp__thread_inst_executed_per_inst_executed.ratio,smsp__inst_executed.sum,gpu__time_duration.sum,smsp__issue_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:k_frame -s 4 -c 1 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --pipelines 1 2>&1 | grep -E "ratio|inst_executed|duration|issue_active"
