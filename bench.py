@@ -70,12 +70,42 @@ def sm_peak_fp32_tflops():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons during the timed region (B200_PROFILING.md clocks line).  Sampled
+    through NVML in a thread (the same counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*`
+    prints, without a second process polling the GPU); falls back to an `nvidia-smi -lms` loop."""
+
+    NAMES = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.thread, self.stop_flag, self.src = index, [], None, None, False, None
+
+    def _nvml_loop(self, nv, h):
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((float(sm), float(mx), int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.src = "nvml"
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.src = "nvidia-smi"
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
@@ -86,19 +116,26 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            r = [x.strip() for x in line.split(",")]
+            if len(r) >= 7 and r[0].replace(".", "").isdigit() and r[1].replace(".", "").isdigit():
+                bits = sum(b for b, i in ((0x8, 3), (0x40, 4), (0x20, 5), (0x4, 6)) if r[i].lower().startswith("active"))
+                self.rows.append((float(r[0]), float(r[1]), bits))
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=1.0)
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples"], "samples": 0, "source": self.src}
+        sm = sorted(r[0] for r in self.rows)
+        bits = 0
+        for r in self.rows:
+            bits |= r[2]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(r[1] for r in self.rows),
+                "reasons": sorted(n for b, n in self.NAMES.items() if bits & b), "samples": len(sm), "source": self.src}
 
 
 def run_reference(args, cfg):
@@ -254,13 +291,14 @@ def main():
             frame = torch.full((h, w, 3), 127, dtype=torch.uint8, device=dev)
             ck(R.rt.rt_set_output(hnd, C.c_void_p(frame.data_ptr()), frame.numel()), "rt_set_output")
         pipes.append({"ctx": hnd, "stream": st, "frame": frame, "landing": landing,
+                      "consumer": torch.cuda.Stream(dev) if p2p and rank == 0 else None,   # where the assembled frame becomes visible
                       "gather": FrameGather(w, h, rank, world, dev, tile_rows) if world > 1 and not p2p else None})
 
     def step(k):
         p = pipes[k % M]
         ck(R.rt.rt_render_async(p["ctx"], C.byref(params)), "rt_render_async")
         if p["landing"] is not None:
-            p["landing"].push(p["ctx"])          # NVLink P2P: this rank's row tiles -> their place in rank 0's frame (copy engines) + signal
+            p["landing"].push(p["ctx"], p["consumer"])   # NVLink P2P: this rank's row tiles -> their place in rank 0's frame (copy engines) + signal
         elif p["gather"] is not None:
             with torch.cuda.stream(p["stream"]):
                 p["gather"].gather(p["frame"])   # NCCL: this rank's row tiles -> rank 0, de-interleaved there
@@ -273,9 +311,11 @@ def main():
 
     def join():
         for p in pipes:
-            ev = torch.cuda.Event()
-            ev.record(p["stream"])
-            main.wait_event(ev)
+            for st in (p["stream"], p["consumer"]):
+                if st is not None:
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    main.wait_event(ev)
 
     def sync_all():
         torch.cuda.synchronize(dev)

@@ -261,7 +261,8 @@ int rt_set_output(rt_ctx *ctx, void *device_ptr, size_t bytes);
  * handle, shipped to the other processes by the caller, e.g. torch.distributed), every rank maps it
  * (rt_landing_open) and, after rt_render_async, rt_push_rows copies its row tiles to their final
  * offsets with one strided peer copy on the copy engines and then writes `seq` to its flag word;
- * rt_landing_wait makes the destination's stream wait until ranks 0..world-1 delivered `seq`.
+ * rt_landing_wait makes a stream of the destination (the consumer's, or the pipeline's own) wait until
+ * ranks 0..world-1 delivered `seq`.
  * The landing buffer of the destination rank may also be its own rt_set_output target (then its own
  * rows need no copy).  A buffer may be pushed to again only when its consumer is done with it. */
 typedef struct rt_landing rt_landing;
@@ -270,7 +271,7 @@ int rt_landing_open(rt_ctx *ctx, int width, int height, const void *ipc_handle64
 void rt_landing_close(rt_landing *landing);
 int rt_landing_ptr(rt_landing *landing, void **device_ptr, size_t *bytes);
 int rt_push_rows(rt_ctx *ctx, rt_landing *landing, uint64_t seq);
-int rt_landing_wait(rt_ctx *ctx, rt_landing *landing, uint64_t seq, uint32_t world);
+int rt_landing_wait(rt_ctx *ctx, rt_landing *landing, uint64_t seq, uint32_t world, void *consumer_stream /* NULL: ctx's stream */);
 
 /* page-locked host memory for RayTracer::output: rt_read_output into it runs at full PCIe speed */
 int rt_host_alloc(void **ptr, size_t bytes);

@@ -906,24 +906,27 @@ extern "C" int rt_push_rows(rt_ctx *c, rt_landing *L, uint64_t seq)
 	return RT_OK;
 }
 
-extern "C" int rt_landing_wait(rt_ctx *c, rt_landing *L, uint64_t seq, uint32_t world)
+extern "C" int rt_landing_wait(rt_ctx *c, rt_landing *L, uint64_t seq, uint32_t world, void *consumer_stream)
 {
 	if (!c || !L) return fail(RT_E_INVALID, "rt_landing_wait: NULL argument");
 	if (world > RT_LANDING_FLAGS) return fail(RT_E_LIMIT, "rt_landing_wait: world %u", world);
 	CU(cudaSetDevice(c->device));
+	// the peers' rows never overlap the rows this rank renders, so the pipeline itself need not wait:
+	// a consumer that reads the assembled frame on its own stream passes that stream here
+	cudaStream_t st = consumer_stream ? (cudaStream_t)consumer_stream : c->stream;
 	static const StreamValue64Fn waitValue = driver_fn("cuStreamWaitValue64");
 	for (uint32_t r = 0; r < world; ++r)
 	{
 		uint64_t *flag = landing_flags(L) + r;
 		// CU_STREAM_WAIT_VALUE_GEQ (0) | CU_STREAM_WAIT_VALUE_FLUSH (1 << 30): the peers' row data is visible once the flag is
 		// (a peer's flag is written by a stream operation that starts only after its row copy has completed)
-		if (waitValue && waitValue(c->stream, (unsigned long long)(uintptr_t)flag, seq, 0u | (1u << 30)) == 0)
+		if (waitValue && waitValue(st, (unsigned long long)(uintptr_t)flag, seq, 0u | (1u << 30)) == 0)
 			continue;
-		if (waitValue && waitValue(c->stream, (unsigned long long)(uintptr_t)flag, seq, 0u) == 0)   // device cannot flush remote writes: plain >= wait
+		if (waitValue && waitValue(st, (unsigned long long)(uintptr_t)flag, seq, 0u) == 0)   // device cannot flush remote writes: plain >= wait
 			continue;
 		// no stream mem-ops: wait on the host (still no kernel)
 		{ static bool told = false; if (!told) { told = true; fprintf(stderr, "raytrace_b200: cuStreamWaitValue64 unavailable (%s), rt_landing_wait falls back to a host wait\n", waitValue ? "call failed" : "no entry point"); } }
-		CU(cudaStreamSynchronize(c->stream));
+		CU(cudaStreamSynchronize(st));
 		uint64_t v = 0;
 		do CU(cudaMemcpy(&v, flag, sizeof v, cudaMemcpyDeviceToHost)); while (v < seq);
 	}

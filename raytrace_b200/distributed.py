@@ -6,6 +6,7 @@ collective is one gather of the finished RGB8 bands to rank 0 per frame (NCCL ov
 gloo in the CPU tests).  Everything here is plumbing on torch tensors; the kernels live in csrc/.
 """
 import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -82,13 +83,15 @@ class FrameLanding:
         self._check(self._rt.rt_landing_ptr(self._h, C.byref(p), C.byref(n)), "rt_landing_ptr")
         return p.value, n.value
 
-    def push(self, ctx):
+    def push(self, ctx, consumer_stream=None):
         """Enqueue, behind the frame just rendered on `ctx`, the copy of this rank's rows + the signal;
-        on the destination rank also the wait for every rank's signal."""
+        on the destination rank also the wait for every rank's signal -- on `consumer_stream` (a
+        torch.cuda.Stream: whoever reads the assembled frame) or, if None, on the pipeline's own stream."""
         self.seq += 1
         self._check(self._rt.rt_push_rows(ctx, self._h, self.seq), "rt_push_rows")
-        if self.rank == self.dst:
-            self._check(self._rt.rt_landing_wait(ctx, self._h, self.seq, self.world), "rt_landing_wait")
+        if self.rank == self.dst and not os.environ.get("RT_DIAG_NO_LANDING_WAIT"):
+            cs = C.c_void_p(consumer_stream.cuda_stream) if consumer_stream is not None else None
+            self._check(self._rt.rt_landing_wait(ctx, self._h, self.seq, self.world, cs), "rt_landing_wait")
 
     def close(self):
         if self._h:
