@@ -43,3 +43,12 @@ clean:
 	rm -rf $(P)/lib $(P)/bin oracle/liboracle.so
 
 .PHONY: all ref clean
+
+# A/B builds during development: `make variant NAME=n256 VFLAGS="-DRT_NODE_FETCH=1"` builds
+# raytrace_b200/lib_n256/{librt_b200.so,librt_host.so}; select it with RT_B200_LIBDIR=raytrace_b200/lib_n256
+variant:
+	@mkdir -p $(P)/lib_$(NAME)
+	for f in rt_api rt_kernels rt_build; do $(NVCC) $(NVFLAGS) $(VFLAGS) -c $(P)/csrc/$$f.cu -o $(P)/lib_$(NAME)/$$f.o 2> $(P)/lib_$(NAME)/$$f.o.ptxas.log || { cat $(P)/lib_$(NAME)/$$f.o.ptxas.log; exit 1; }; done
+	$(NVCC) $(ARCH) -shared -o $(P)/lib_$(NAME)/librt_b200.so $(P)/lib_$(NAME)/rt_api.o $(P)/lib_$(NAME)/rt_kernels.o $(P)/lib_$(NAME)/rt_build.o
+	$(CXX) $(HOSTFLAGS) -shared -o $(P)/lib_$(NAME)/librt_host.so $(HSRC) -L$(P)/lib_$(NAME) -lrt_b200 -Wl,-rpath,'$$ORIGIN' -lpthread
+.PHONY: variant

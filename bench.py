@@ -28,7 +28,7 @@ is quoted on).  A ray = one closest-hit or one shadow any-hit query (SURVEY.md 8
            the box's host cores, on a bounded tile sample of the same workload.
 
 N > 1 (torchrun): the frame is split into interleaved 8-row tiles (tile % N == rank), the scene is
-replicated, and every step each rank's rows are delivered into rank 0's frame ("strong" scaling):
+replicated (boustrophedon tile order by default, --shard-order), and every step each rank's rows are delivered into rank 0's frame ("strong" scaling):
 by default with one-sided NVLink peer copies on the copy engines (rt_push_rows; torch.distributed /
 NCCL only carries the IPC handles, barriers and timing reductions), with --gather nccl by an NCCL gather.
 `--impl reference` times the reference CPU tracer itself (rank 0 only).
@@ -223,6 +223,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: how the row tiles reach rank 0 -- one-sided NVLink peer copies on the copy engines (rt_push_rows) or an NCCL gather")
+    ap.add_argument("--shard-order", default="serpentine", choices=["serpentine", "modulo"],
+                    help="N>1: which rank renders row tile t -- boustrophedon (RT_FLAG_SERPENTINE, evens out the ray-cost gradient down the image) or t %% N")
     ap.add_argument("--pipelines", type=int, default=0, help="frames in flight per GPU (0 = 3 at N=1, 4 at N>1)")
     ap.add_argument("--sm-share", type=int, default=-1, help="resident traversal CTAs per SM per pipeline (-1 = 4 at N=1, 2 at N>1)")
     args = ap.parse_args()
@@ -270,7 +272,9 @@ def main():
     ck(R.rt.rt_set_stream(owner, C.c_void_p(main.cuda_stream)), "rt_set_stream")
     ck(R.rt.rt_upload_scene(owner, sc.flatten()), "rt_upload_scene")      # H2D of the scene + LBVH build, once
     tile_rows = 8 if world > 1 else 64           # fine interleave balances the ranks (sky rows are cheap)
-    params = R.RenderParams(R.MY_MODEL_RAYTRACE, level, rank, world, 0, tile_rows)
+    serp = world > 1 and args.shard_order == "serpentine"
+    shard_flags = R.RT_FLAG_SERPENTINE if serp else 0
+    params = R.RenderParams(R.MY_MODEL_RAYTRACE, level, rank, world, shard_flags, tile_rows)
     from raytrace_b200.distributed import FrameGather, FrameLanding
     p2p = world > 1 and args.gather == "p2p"
     pipes = []
@@ -292,7 +296,7 @@ def main():
             ck(R.rt.rt_set_output(hnd, C.c_void_p(frame.data_ptr()), frame.numel()), "rt_set_output")
         pipes.append({"ctx": hnd, "stream": st, "frame": frame, "landing": landing,
                       "consumer": torch.cuda.Stream(dev) if p2p and rank == 0 else None,   # where the assembled frame becomes visible
-                      "gather": FrameGather(w, h, rank, world, dev, tile_rows) if world > 1 and not p2p else None})
+                      "gather": FrameGather(w, h, rank, world, dev, tile_rows, serp) if world > 1 and not p2p else None})
 
     def step(k):
         p = pipes[k % M]
@@ -374,7 +378,7 @@ def main():
         ck(R.rt.rt_render_async(p0, C.byref(params)), "rt_render_async")
         ck(R.rt.rt_read_counters(p0, C.byref(cnt)), "rt_read_counters")
     stage = {"traverse": cnt.trace_ms, "shade": cnt.shade_ms, "other": cnt.other_ms, "render": cnt.render_ms}
-    pstats = R.RenderParams(R.MY_MODEL_RAYTRACE, level, rank, world, R.RT_FLAG_STATS, tile_rows)
+    pstats = R.RenderParams(R.MY_MODEL_RAYTRACE, level, rank, world, R.RT_FLAG_STATS | shard_flags, tile_rows)
     ck(R.rt.rt_render_async(p0, C.byref(pstats)), "rt_render_async(stats)")
     cs = R.Counters()
     ck(R.rt.rt_read_counters(p0, C.byref(cs)), "rt_read_counters")
@@ -396,7 +400,7 @@ def main():
         tracers.append(t)
     for k in range(2 * M):
         tracers[k % M].wait()
-        tracers[k % M].start(R.MY_MODEL_RAYTRACE, rank=rank, world=world, tile_rows=tile_rows)
+        tracers[k % M].start(R.MY_MODEL_RAYTRACE, flags=shard_flags, rank=rank, world=world, tile_rows=tile_rows)
     for t in tracers:
         t.wait()
     sync_all()
@@ -404,7 +408,7 @@ def main():
     for k in range(args.steps):
         t = tracers[k % M]
         t.wait()                                 # frame k-M is in RayTracer::output
-        t.start(R.MY_MODEL_RAYTRACE, rank=rank, world=world, tile_rows=tile_rows)
+        t.start(R.MY_MODEL_RAYTRACE, flags=shard_flags, rank=rank, world=world, tile_rows=tile_rows)
     for t in tracers:
         t.wait()
     torch.cuda.synchronize(dev)
@@ -429,7 +433,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.config}: {desc}", "rays_per_frame": rays_total, "pixels": w * (h // 64 * 64) if w % 64 == 0 else (w // 64 * 64) * (h // 64 * 64),
                        "l2_policy": "per-frame working set (ray/hit/node queues + BVH + triangles, > 500 MB touched per frame) exceeds the 126 MB L2; no flush needed",
-                       "parallelism": (f"image-space: interleaved {tile_rows}-row tiles over {world} GPUs, " + ("row tiles pushed into rank 0's frame over NVLink P2P (copy engines, put with signal; NCCL only ships the IPC handles)" if p2p else "NCCL gather of RGB8 tiles to rank 0")) if world > 1 else "single GPU",
+                       "parallelism": (f"image-space: interleaved {tile_rows}-row tiles over {world} GPUs ({'boustrophedon' if serp else 'modulo'} order), " + ("row tiles pushed into rank 0's frame over NVLink P2P (copy engines, put with signal; NCCL only ships the IPC handles)" if p2p else "NCCL gather of RGB8 tiles to rank 0")) if world > 1 else "single GPU",
                        "frames_in_flight": M, "traversal_ctas_per_sm_per_pipeline": (share if M > 1 and share else 8),
                        "ms_per_frame_alone": stage["render"]},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": float(e2e_s.item()) / args.steps * 1e3,

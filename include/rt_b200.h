@@ -159,7 +159,7 @@ typedef struct
 {
 	uint32_t type;        /* RT_TYPE_* */
 	uint32_t max_level;   /* RayTracer::maxLevel; levels 0..max_level are traced (RayTracer.cpp:453) */
-	uint32_t rank, world; /* image-space shard: row tile t is rendered iff t % world == rank; world=0 or 1 = whole frame */
+	uint32_t rank, world; /* image-space shard: row tile t is rendered iff t % world == rank (RT_FLAG_SERPENTINE: see below); world=0 or 1 = whole frame */
 	uint32_t flags;       /* RT_FLAG_* */
 	uint32_t tile_rows;   /* height of a shard tile: 8, 16, 32 or 64 rows (0 = 64); finer tiles balance the ranks better */
 } rt_render_params;
@@ -168,6 +168,10 @@ typedef struct
 #define RT_FLAG_STATS     0x2   /* count BVH node visits / primitive tests (slower kernels) */
 #define RT_FLAG_BRUTE     0x4   /* diagnostic: ignore the BVHs, test every primitive (small scenes) */
 #define RT_FLAG_COMBINE_LEVELS 0x8 /* diagnostic: colour combine as one pass per ray level instead of the one-launch tree walk */
+/* shard order: the tiles of group g = t / world go to ranks 0..world-1 for even g and world-1..0 for odd g
+ * (boustrophedon), so a ray-cost gradient down the image (sky rows cheap, floor rows expensive) averages
+ * out per rank instead of giving rank 0 the expensive tile of every group */
+#define RT_FLAG_SERPENTINE 0x10
 
 /* primary closest-hit identity, the GPU-side meaning of HitRes::obj (3DElement.h:174) */
 typedef struct
@@ -249,6 +253,10 @@ int rt_stop(rt_ctx *ctx);
  * Only floor(W/64)*64 x floor(H/64)*64 pixels are rendered, the rest is 127 (RayTracer.cpp:13,620).
  * With world > 1 only this rank's rows are valid. */
 int rt_read_output(rt_ctx *ctx, uint8_t *rgb, size_t stride);
+/* same destination layout, but copies only the rows the last frame's shard rendered (world > 1: 1/world of the
+ * D2H bytes); every other row of `rgb` is left as it is (RayTracer pre-fills `output` with 127 like the
+ * reference constructor, RayTracer.cpp:603-606).  world <= 1: identical to rt_read_output. */
+int rt_read_output_rows(rt_ctx *ctx, uint8_t *rgb, size_t stride);
 /* device-resident framebuffer of the last frame (for NCCL gathers / zero-copy consumers) */
 int rt_output_device(rt_ctx *ctx, void **device_ptr, size_t *bytes);
 /* render into a caller-owned device buffer of >= 3*width*height bytes (e.g. a torch tensor that is

@@ -759,6 +759,14 @@ int rto_render(const rt_scene_desc *scene, const rt_render_params *params, uint8
 	const float zNear = cam.zNear, zFar = sqrt(2) * cam.zFar;
 	const uint32_t world = params->world > 1 ? params->world : 1, rank = params->world > 1 ? params->rank : 0;
 	const uint32_t tileRows = params->tile_rows ? params->tile_rows : 64u;
+	// which rank renders image row y (include/rt_b200.h: tile t -> rank t % world; RT_FLAG_SERPENTINE deals the
+	// odd groups of `world` tiles in reverse order)
+	const bool serpentine = (params->flags & RT_FLAG_SERPENTINE) && world > 1;
+	auto ownerOfRow = [=](uint32_t y) -> uint32_t
+	{
+		const uint32_t t = y / tileRows, g = t / world, i = t % world;
+		return (serpentine && (g & 1u)) ? world - 1u - i : i;
+	};
 	if (threads < 1) threads = 1;
 	std::atomic<int> nextRow(0);
 	std::vector<uint64_t> cnt((size_t)threads * 4, 0);
@@ -770,7 +778,7 @@ int rto_render(const rt_scene_desc *scene, const rt_render_params *params, uint8
 			const V4 cn = from(cam.n), cu = from(cam.u), cv = from(cam.v), cpos = from(cam.position);
 			for (int y = nextRow.fetch_add(1); y < blk_h * 64; y = nextRow.fetch_add(1))
 			{
-				if ((uint32_t)y / tileRows % world != rank)
+				if (ownerOfRow((uint32_t)y) != rank)
 					continue;
 				for (int x = 0; x < blk_w * 64; ++x)
 				{
@@ -832,7 +840,7 @@ int rto_render(const rt_scene_desc *scene, const rt_render_params *params, uint8
 	if (ids)
 		for (int y = 0; y < height; ++y)
 			for (int x = 0; x < width; ++x)
-				if (y >= blk_h * 64 || x >= blk_w * 64 || (uint32_t)y / tileRows % world != rank)
+				if (y >= blk_h * 64 || x >= blk_w * 64 || ownerOfRow((uint32_t)y) != rank)
 					ids[(size_t)y * width + x] = rt_hit_id{ -1, -1, -1, -1, 1e20f };
 	if (counters)
 	{

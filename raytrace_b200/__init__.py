@@ -16,7 +16,7 @@ MY_MODEL_CHECK, MY_MODEL_DEPTHTEST, MY_MODEL_NORMALTEST, MY_MODEL_TEXTURETEST = 
 MY_MODEL_MATERIALTEST, MY_MODEL_SHADOWTEST, MY_MODEL_REFLECTTEST, MY_MODEL_REFRACTTEST = 5, 6, 7, 8
 MY_MODEL_RAYTRACE = 0x80
 MY_MODEL_LIGHT, MY_MODEL_OBJECT = 1, 2
-RT_FLAG_HIT_IDS, RT_FLAG_STATS, RT_FLAG_BRUTE, RT_FLAG_COMBINE_LEVELS = 1, 2, 4, 8
+RT_FLAG_HIT_IDS, RT_FLAG_STATS, RT_FLAG_BRUTE, RT_FLAG_COMBINE_LEVELS, RT_FLAG_SERPENTINE = 1, 2, 4, 8, 16
 
 HIT_DTYPE = np.dtype([("object", "<i4"), ("sub", "<i4"), ("index", "<i4"), ("octant", "<i4"), ("distance", "<f4")])
 

@@ -114,6 +114,7 @@ RT_SYMBOLS = {
     "rt_wait": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "rt_stop": (C.c_int, [C.c_void_p]),
     "rt_read_output": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "rt_read_output_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "rt_output_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "rt_set_output": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "rt_landing_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p]),

@@ -2,6 +2,7 @@
 // side + LBVH builds) and the per-frame wavefront schedule.  Host-side glue only; every per-ray
 // operation runs in the kernels of rt_kernels.cu.  There is deliberately no CPU path here.
 #include "rt_kernels.h"
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -124,7 +125,8 @@ struct rt_ctx
 	uint64_t tablesVersion = 0, adoptedTables = 0;     // bumped when prims / models / parts changed
 	const uint8_t *fillPtr = nullptr;   // what the framebuffer was last filled with 127 for
 	int fillW = 0, fillH = 0;
-	uint32_t fillRank = 0, fillWorld = 0, fillTile = 0;
+	uint32_t fillRank = 0, fillWorld = 0, fillTile = 0, fillSerp = 0;
+	uint32_t keepSalt = 0;      // rotates which CTAs of k_frame are pinned, per pipeline (RT_B200_KEEP_DIV)
 	unsigned ctasPerSm = 0;         // resident traversal CTAs per SM this pipeline may use (0 = all 8), rt_set_sm_share
 };
 
@@ -164,6 +166,7 @@ extern "C" int rt_create(int device, rt_ctx **out)
 	if (const char *v = getenv("RT_B200_LEAF_SIZE")) c->leafSize = (uint32_t)atoi(v);
 	if (const char *v = getenv("RT_B200_LEVEL_FACTOR")) c->levelFactor = (float)atof(v);
 	if (const char *v = getenv("RT_B200_SCHED")) c->schedMode = !strcmp(v, "frame") ? 1 : (!strcmp(v, "waves") ? 2 : 0);
+	{ static std::atomic<uint32_t> created{0}; c->keepSalt = created.fetch_add(1u); }
 	*out = c;
 	return RT_OK;
 }
@@ -421,7 +424,7 @@ extern "C" int rt_upload_scene(rt_ctx *c, const rt_scene_desc *s)
 		CU(c->nodes4.reserve(nodeBudget + 1));
 		CU(c->bvhPrims.reserve(primLeafSlots + 1));
 		CU(c->triGeomOrig.reserve(3 * (size_t)s->n_tris + 1));
-		CU(c->triGeom.reserve(3 * (size_t)s->n_tris + 1));
+		CU(c->triGeom.reserve(RT_TRI_F4 * (size_t)s->n_tris + 1));
 		CU(c->triSlot.reserve(s->n_tris + 1));
 		uint32_t maxBoxes = 1;
 		for (const SceneItem &it : items)
@@ -564,9 +567,15 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 		F.sms = (uint32_t)c->sms;
 		static const int retireRays = []{ const char *e = getenv("RT_B200_RETIRE_RAYS"); const int v = e ? atoi(e) : 16; return v > 0 ? v : 16; }();
 		F.retire_rays = (uint32_t)retireRays;
+		// RT_B200_KEEP_DIV=d: with d > 1 only every d-th CTA of k_frame is pinned until the frame is complete, the
+		// others leave when the frame runs thin -- also when a pipeline's share is one CTA per SM (small shards,
+		// many frames in flight), where "the first `sms` CTAs stay" pins the whole grid through the frame's tail
+		static const int keepDiv = []{ const char *e = getenv("RT_B200_KEEP_DIV"); const int v = e ? atoi(e) : 1; return v > 1 ? v : 1; }();
+		F.keep_div = (uint32_t)keepDiv, F.keep_salt = c->keepSalt;
 	}
+	F.serpentine = (p->flags & RT_FLAG_SERPENTINE) && world > 1 ? 1u : 0u;
 	uint32_t bands = 0;
-	for (uint32_t t = 0; t < (uint32_t)F.blk_h * 64u / tileRows; ++t) if (t % world == rank) ++bands;
+	while (shard_tile(bands, rank, world, F.serpentine) < (uint32_t)F.blk_h * 64u / tileRows) ++bands;
 	F.n_rows = bands * tileRows;
 	F.n_lights = (uint32_t)c->lights.size();
 	F.env_light = f4(c->envLight);
@@ -597,8 +606,9 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 	c->outW = W, c->outH = H, c->fb = fb;
 	// RayTracer.cpp:620 greys the whole buffer at every start(); the rendered region is overwritten by
 	// every frame, so the fill is only repeated when the buffer, the frame size or the shard changes
-	if (fb != c->fillPtr || W != c->fillW || H != c->fillH || rank != c->fillRank || world != c->fillWorld || tileRows != c->fillTile)
+	if (fb != c->fillPtr || W != c->fillW || H != c->fillH || rank != c->fillRank || world != c->fillWorld || tileRows != c->fillTile || F.serpentine != c->fillSerp)
 	{
+		c->fillSerp = F.serpentine;
 		CU(cudaMemsetAsync(fb, 127, (size_t)W * H * 3, st));
 		c->fillPtr = fb, c->fillW = W, c->fillH = H, c->fillRank = rank, c->fillWorld = world, c->fillTile = tileRows;
 	}
@@ -779,6 +789,55 @@ extern "C" int rt_read_output(rt_ctx *c, uint8_t *rgb, size_t stride)
 	return RT_OK;
 }
 
+// The rows the last frame's shard rendered, device framebuffer -> `dst` (a full-frame buffer with `stride`
+// bytes per row), as strided 2-D copies on the copy engines: the tiles of a rank are `world` tiles apart
+// (one copy), with RT_FLAG_SERPENTINE the even and the odd tile groups are each 2*world tiles apart (two).
+// A "row" of such a copy is one tile (tile_rows image rows) when dst is as dense as the framebuffer.
+static int copy_shard_rows(rt_ctx *c, uint8_t *dst, size_t stride, cudaMemcpyKind kind, cudaStream_t st, size_t *bytesOut)
+{
+	const rt_render_params &p = c->lastParams;
+	const uint32_t world = p.world > 1 ? p.world : 1, rank = p.world > 1 ? p.rank : 0;
+	const uint32_t serp = (p.flags & RT_FLAG_SERPENTINE) && world > 1 ? 1u : 0u;
+	const uint32_t tileRows = p.tile_rows ? p.tile_rows : 64u;
+	const size_t row = (size_t)c->outW * 3;
+	const uint32_t tiles = (uint32_t)(c->outH / 64) * 64u / tileRows;
+	uint32_t mine = 0;
+	while (shard_tile(mine, rank, world, serp) < tiles) ++mine;
+	size_t bytes = 0;
+	// family f: tiles k = f, f + step, f + 2*step ... of this shard are equally spaced in the frame
+	const uint32_t step = serp ? 2u : 1u;
+	for (uint32_t f = 0; f < step && f < mine; ++f)
+	{
+		const uint32_t count = (mine - f + step - 1u) / step;
+		const size_t first = (size_t)shard_tile(f, rank, world, serp) * tileRows;        // first image row of the family
+		const size_t pitchRows = (size_t)step * world * tileRows;                        // image rows between two of its tiles
+		if (stride == row)
+			CU(cudaMemcpy2DAsync(dst + first * row, pitchRows * row, c->fb + first * row, pitchRows * row, tileRows * row, count, kind, st));
+		else
+			for (uint32_t t = 0; t < count; ++t)
+				CU(cudaMemcpy2DAsync(dst + (first + t * pitchRows) * stride, stride, c->fb + (first + t * pitchRows) * row, row, row, tileRows, kind, st));
+		bytes += (size_t)count * tileRows * row;
+	}
+	if (bytesOut) *bytesOut = bytes;
+	return RT_OK;
+}
+
+extern "C" int rt_read_output_rows(rt_ctx *c, uint8_t *rgb, size_t stride)
+{
+	if (!c || !rgb) return fail(RT_E_INVALID, "rt_read_output_rows: NULL argument");
+	if (c->lastParams.world <= 1) return rt_read_output(c, rgb, stride);
+	if (c->frameInFlight) { int rc = finish_frame(c); if (rc != RT_OK) return rc; }
+	if (!c->fb) return fail(RT_E_STATE, "rt_read_output_rows: nothing rendered yet");
+	CU(cudaSetDevice(c->device));
+	if (stride < (size_t)c->outW * 3) return fail(RT_E_INVALID, "rt_read_output_rows: stride %zu < %zu", stride, (size_t)c->outW * 3);
+	size_t bytes = 0;
+	int rc = copy_shard_rows(c, rgb, stride, cudaMemcpyDeviceToHost, c->stream, &bytes);
+	if (rc != RT_OK) return rc;
+	c->frameD2H += bytes;
+	CU(cudaStreamSynchronize(c->stream));
+	return RT_OK;
+}
+
 extern "C" int rt_output_device(rt_ctx *c, void **ptr, size_t *bytes)
 {
 	if (!c || !ptr) return fail(RT_E_INVALID, "rt_output_device: NULL argument");
@@ -886,13 +945,12 @@ extern "C" int rt_push_rows(rt_ctx *c, rt_landing *L, uint64_t seq)
 	const rt_render_params &p = c->lastParams;
 	const uint32_t world = p.world > 1 ? p.world : 1, rank = p.world > 1 ? p.rank : 0;
 	if (rank >= RT_LANDING_FLAGS) return fail(RT_E_LIMIT, "rt_push_rows: rank %u (landing buffers hold %d flags)", rank, RT_LANDING_FLAGS);
-	const uint32_t tileRows = p.tile_rows ? p.tile_rows : 64u;
-	const size_t tileBytes = (size_t)tileRows * c->outW * 3;
-	const uint32_t tiles = (uint32_t)(c->outH / 64) * 64u / tileRows;
-	const uint32_t mine = tiles > rank ? (tiles - rank + world - 1) / world : 0;
 	cudaStream_t st = c->stream;
-	if (mine && c->fb != L->base)
-		CU(cudaMemcpy2DAsync(L->base + rank * tileBytes, world * tileBytes, c->fb + rank * tileBytes, world * tileBytes, tileBytes, mine, cudaMemcpyDeviceToDevice, st));
+	if (c->fb != L->base)
+	{
+		int rc = copy_shard_rows(c, L->base, (size_t)c->outW * 3, cudaMemcpyDeviceToDevice, st, nullptr);
+		if (rc != RT_OK) return rc;
+	}
 	// the flag goes out behind the data on the same stream
 	static const StreamValue64Fn writeValue = driver_fn("cuStreamWriteValue64");
 	uint64_t *flag = landing_flags(L) + rank;
@@ -1054,7 +1112,7 @@ extern "C" int rt_read_hit_ids(rt_ctx *c, rt_hit_id *ids)
 		const uint32_t tile = i >> 6, in = i & 63u, tx = tile % tilesX, ty = tile / tilesX;
 		const uint32_t tileRows = c->lastParams.tile_rows ? c->lastParams.tile_rows : 64u;
 		const uint32_t x = tx * 8u + (in & 7u), row = ty * 8u + (in >> 3), band = row / tileRows;
-		const uint32_t y = (band * world + rank) * tileRows + row % tileRows;
+		const uint32_t y = shard_tile(band, rank, world, (c->lastParams.flags & RT_FLAG_SERPENTINE) && world > 1) * tileRows + row % tileRows;
 		rt_hit_id id = { -1, -1, -1, -1, hp[i].w };
 		const uint32_t h = hid[i].y;
 		if (h != RT_ID_NONE)

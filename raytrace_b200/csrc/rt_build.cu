@@ -631,9 +631,9 @@ __global__ void k_scatter_tris(const float4 *geomOrig, const uint32_t *leafOrder
 	if (sIdx >= n) return;
 	const uint32_t orig = origBase + leafOrder[sIdx];   // leafOrder holds indices local to this model
 	const uint32_t slot = leafBase + sIdx;
-	geomLeaf[3 * slot] = geomOrig[3 * orig];
-	geomLeaf[3 * slot + 1] = geomOrig[3 * orig + 1];
-	geomLeaf[3 * slot + 2] = geomOrig[3 * orig + 2];
+	geomLeaf[RT_TRI_F4 * (size_t)slot] = geomOrig[3 * orig];
+	geomLeaf[RT_TRI_F4 * (size_t)slot + 1] = geomOrig[3 * orig + 1];
+	geomLeaf[RT_TRI_F4 * (size_t)slot + 2] = geomOrig[3 * orig + 2];
 	triSlot[orig] = slot;
 }
 

@@ -75,8 +75,11 @@ struct FrameParams
 	uint32_t tile_rows;        // shard tile height (8..64 rows)
 	uint32_t sched_flags;      // k_frame: bit 0 = ray queues are claimed deepest level first, bit 1 = idle CTAs retire when the frame runs thin, bit 2 = level-0 rays are generated inside k_frame
 	uint32_t sms;              // SM count (k_frame: CTAs below this index never retire)
-	uint32_t retire_rays;      // k_frame: CTA i >= sms retires when idle and outstanding < (i - sms + 1) * retire_rays
-	uint32_t pad_[2];
+	uint32_t retire_rays;      // k_frame: a CTA that may retire does so when idle and outstanding < (i + 1) * retire_rays  (keep_div == 1: (i - sms + 1))
+	uint32_t serpentine;       // RT_FLAG_SERPENTINE: odd tile groups are dealt to the ranks in reverse order
+	uint32_t keep_div;         // k_frame retire policy: 1 = CTAs below `sms` never retire; d > 1 = only every d-th CTA is kept
+	uint32_t keep_salt;        //   (CTA i is kept iff (i + i / sms + keep_salt) % d == 0: spread over the SMs, rotated per pipeline)
+	uint32_t pad_[3];
 	float4 env_light;
 	DevLight lights[RT_MAX_LIGHTS];
 };
@@ -99,6 +102,12 @@ struct DevModel
 	uint32_t object, pad0, pad1, pad2;
 };
 
+// global row tile of the k-th tile of a shard (include/rt_b200.h rt_render_params, RT_FLAG_SERPENTINE)
+__host__ __device__ __forceinline__ uint32_t shard_tile(uint32_t k, uint32_t rank, uint32_t world, uint32_t serpentine)
+{
+	return k * world + ((serpentine && (k & 1u)) ? world - 1u - rank : rank);
+}
+
 struct DevPart
 {
 	float4 box_min, box_max;         // borders + position (Model.cpp:418-419)
@@ -117,9 +126,26 @@ struct BvhNode   // 64 bytes: both children's boxes + links, fetched as 4 x 128-
 // 4-wide node used by the traversal kernels: the two children of each child of a binary LBVH node
 // (collapsed on the GPU, rt_build.cu k_collapse4).  SoA so that one float4 holds the same plane of
 // all four child boxes; 7 x 128-bit loads, 128-byte aligned.  Unused slots carry a degenerate far-away box that no ray hits.
+// RT_NODE_FETCH selects how a lane fetches its node (all variants read the same planes, only the data
+// movement differs -- measured A/B in DESIGN.md "L1 wavefronts"):
+//   0  seven LDG.128, near/far planes addressed by the ray's direction signs (lo* then hi*)
+//   1  three LDG.256 (sm_100 256-bit loads: lo|hi of one axis per load) + one LDG.128, near/far by select
+#ifndef RT_NODE_FETCH
+#define RT_NODE_FETCH 0
+#endif
+// RT_TRI_FETCH: 0 = 48-byte triangle records in leaf order, three LDG.128; 1 = records padded to 64 bytes
+// (32-byte aligned), two LDG.256
+#ifndef RT_TRI_FETCH
+#define RT_TRI_FETCH 0
+#endif
+#define RT_TRI_F4 (RT_TRI_FETCH == 1 ? 4 : 3)   // float4 per leaf-order triangle record
 struct BvhNode4
 {
+#if RT_NODE_FETCH == 1
+	float4 lox, hix, loy, hiy, loz, hiz;
+#else
 	float4 lox, loy, loz, hix, hiy, hiz;
+#endif
 	int4 link;     // per child: >=0 node index, <0 leaf code 0x80000000 | first<<3 | (count-1)
 	int4 pad;
 };
@@ -151,3 +177,22 @@ struct SceneDev
 };
 
 __device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
+// one leaf-order triangle record: e1|id, e2|part<<8|octants, p0|-
+__device__ __forceinline__ void load_tri(const float4 *tri_geom, uint32_t slot, float4 &g0, float4 &g1, float4 &g2);
+// 256-bit read-only load (LDG.E.256, sm_100+): two float4 from a 32-byte aligned address, ONE L1 wavefront
+__device__ __forceinline__ void ldg8(const void *p, float4 &a, float4 &b)
+{
+	asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		: "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+
+__device__ __forceinline__ void load_tri(const float4 *tri_geom, uint32_t slot, float4 &g0, float4 &g1, float4 &g2)
+{
+#if RT_TRI_FETCH == 1
+	float4 pad;
+	ldg8(&tri_geom[4 * (size_t)slot], g0, g1);
+	ldg8(&tri_geom[4 * (size_t)slot + 2], g2, pad);
+#else
+	g0 = ldg4(&tri_geom[3 * (size_t)slot]), g1 = ldg4(&tri_geom[3 * (size_t)slot + 1]), g2 = ldg4(&tri_geom[3 * (size_t)slot + 2]);
+#endif
+}

@@ -35,7 +35,7 @@ __device__ __forceinline__ void slot_to_pixel(const FrameParams &F, uint32_t i, 
 	x = (int)(tx * 8u + (in & 7u));
 	const uint32_t row = ty * 8u + (in >> 3);            // row among this shard's rows
 	const uint32_t band = row / F.tile_rows;              // row tile among this shard's tiles
-	y = (int)((band * F.world + F.rank) * F.tile_rows + row % F.tile_rows);
+	y = (int)(shard_tile(band, F.rank, F.world, F.serpentine) * F.tile_rows + row % F.tile_rows);
 }
 
 __device__ __forceinline__ uint8_t put8(float c)
@@ -231,7 +231,8 @@ __device__ __forceinline__ Surface surface_attributes(const SceneDev &S, const R
 	{
 		// Model::intersect epilogue, Model.cpp:794-807
 		const uint32_t tri = id & 0x0FFFFFFFu, slot = __ldg(&S.tri_slot[tri]);
-		const float4 g0 = ldg4(&S.tri_geom[3 * slot]), g1 = ldg4(&S.tri_geom[3 * slot + 1]), g2 = ldg4(&S.tri_geom[3 * slot + 2]);
+		float4 g0, g1, g2;
+		load_tri(S.tri_geom, slot, g0, g1, g2);
 		F3 bary = f3(0, 0, 0);
 		triangle_t(ray.o, ray.d, f3(g0), f3(g1), f3(g2), &bary);
 		const F3 n0 = f3(ldg4(&S.tri_norms[3 * tri])), n1 = f3(ldg4(&S.tri_norms[3 * tri + 1])), n2 = f3(ldg4(&S.tri_norms[3 * tri + 2]));
@@ -450,6 +451,51 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_wave(SceneDev S, const Frame
 // "outstanding == 0" means the frame is complete and every warp may leave.
 __device__ __forceinline__ uint32_t vload(const uint32_t *p) { return *(const volatile uint32_t *)p; }
 
+// Release / acquire without wiping the L1.  __threadfence() is MEMBAR.SC.GPU + CCTL.IVALL on sm_100: the
+// CCTL invalidates every L1 line of the SM, and k_frame fences several times per batch of 32 rays -- with
+// 32 resident warps that flushed the SM's L1 (BVH nodes, triangles) every few hundred cycles.  Neither
+// side needs the invalidate: producers only have to make their payload visible before the stamp
+// (st.release.gpu = MEMBAR.ALL.GPU + strong store, no CCTL), and consumers read stamp and payload
+// through L2 (ld.cg), so ordering the two loads (CTA-scope fence, MEMBAR.ALL.CTA) is enough.
+// RT_LIGHT_FENCE=0 restores the __threadfence() pairs (A/B).
+#ifndef RT_LIGHT_FENCE
+#define RT_LIGHT_FENCE 1
+#endif
+__device__ __forceinline__ void consumer_fence()
+{
+#if RT_LIGHT_FENCE
+	asm volatile("fence.acq_rel.cta;" ::: "memory");
+#else
+	__threadfence();
+#endif
+}
+struct Publisher
+{
+	bool released = false;   // this lane's payload stores are already ordered before what it publishes next
+	__device__ __forceinline__ void store(uint2 *p, uint2 v)
+	{
+#if RT_LIGHT_FENCE
+		if (!released) asm volatile("st.release.gpu.global.v2.u32 [%0], {%1, %2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
+		else asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
+#else
+		if (!released) __threadfence();
+		*p = v;
+#endif
+		released = true;
+	}
+	__device__ __forceinline__ void store(uint32_t *p, uint32_t v)
+	{
+#if RT_LIGHT_FENCE
+		if (!released) asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+		else asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+#else
+		if (!released) __threadfence();
+		*p = v;
+#endif
+		released = true;
+	}
+};
+
 // queue q of the claim scan -> level | light << 8: ray queues first (shallowest or deepest level first),
 // then the shadow queues by (level, light)
 __device__ __forceinline__ uint32_t queue_code(uint32_t q, uint32_t nL, uint32_t nEnabled, uint32_t schedFlags)
@@ -576,7 +622,9 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_frame(SceneDev S, const Fram
 			// indices first, the first `sms` CTAs never.  `outstanding` never under-counts and a ray tree is
 			// bounded by max_level, so whoever stays can always finish the frame.  Leaving frees the SM slots
 			// for the next frame's kernels (frames in flight) and thins out the pollers of the queue heads.
-			if ((F.sched_flags & 2u) && blockIdx.x >= F.sms && out < (int)((blockIdx.x - F.sms + 1u) * F.retire_rays)
+			const bool mayRetire = F.keep_div <= 1u ? blockIdx.x >= F.sms : (blockIdx.x + blockIdx.x / F.sms + F.keep_salt) % F.keep_div != 0u;
+			const uint32_t retireRank = F.keep_div <= 1u ? blockIdx.x - F.sms : blockIdx.x;
+			if ((F.sched_flags & 2u) && mayRetire && out < (int)((retireRank + 1u) * F.retire_rays)
 				&& __ballot_sync(0xffffffffu, pSlot != 0xFFFFFFFFu) == 0u)
 				break;
 			if (++idleSpins > (1u << 22))
@@ -607,7 +655,7 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_frame(SceneDev S, const Fram
 			// ---- shadow any-hit rays: a warp's lanes go to the same light from neighbouring surfaces ------
 			if (ready)
 			{
-				__threadfence();
+				consumer_fence();
 				const uint32_t i = hitEntry - 1u, k = F.enabled_index[pLight];
 				const float4 hp = __ldcg(&L.hit_p[i]);
 				RayD ray;
@@ -653,7 +701,7 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_frame(SceneDev S, const Fram
 			}
 			else
 			{
-				__threadfence();   // the stamp was seen: order the payload reads after it
+				consumer_fence();   // the stamp was seen: order the payload reads after it
 				o4 = __ldcg(&L.ray_o[i]), d4 = __ldcg(&L.ray_d[i]);
 			}
 			RayD ray;
@@ -731,10 +779,11 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_frame(SceneDev S, const Fram
 			const int nMine = __popc(grp);
 			if (lane == gLeader && nChildren + nShadow != nMine) atomicAdd(&ws->outstanding, nChildren + nShadow - nMine);
 			__syncwarp(grp);
+			uint32_t sFlec = 0xFFFFFFFFu, sFrac = 0xFFFFFFFFu;
 			if (nChildren)
 			{
-				const uint32_t sFlec = group_append(&ws->count[level + 1], wantFlec, grp);
-				const uint32_t sFrac = group_append(&ws->count[level + 1], wantFrac, grp);
+				sFlec = group_append(&ws->count[level + 1], wantFlec, grp);
+				sFrac = group_append(&ws->count[level + 1], wantFrac, grp);
 				int dropped = 0;
 				if (wantFlec)
 				{
@@ -746,9 +795,6 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_frame(SceneDev S, const Fram
 					if (sFrac < N.capacity) { N.ray_o[sFrac] = make_float4(co.x, co.y, co.z, fracRfr), N.ray_d[sFrac] = cdFrac; aux.y = (int)sFrac; }
 					else { ws->overflow = 1; ++dropped; }
 				}
-				__threadfence();
-				if (wantFlec && sFlec < N.capacity) N.ray_meta[sFlec] = metaFlec;
-				if (wantFrac && sFrac < N.capacity) N.ray_meta[sFrac] = metaFrac;
 				if (dropped) atomicSub(&ws->outstanding, dropped);
 				if (lane == gLeader)
 				{
@@ -757,11 +803,13 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_frame(SceneDev S, const Fram
 				}
 			}
 			L.aux[i] = aux;
-			// surfaces: hit_p / hit_id / hit_n are written; publish the compacted entry last
 			const uint32_t hslot = group_append(&ws->n_hit[level], surface, grp);
-			__threadfence();
-			if (surface)
-				L.hit_list[hslot] = i + 1u;
+			// ---- publish: everything a consumer reads (child payloads, hit_p / hit_id / hit_n) is written; ONE
+			// release point per lane, then the stamps of the children and the compacted surface entry ---------
+			Publisher pub;
+			if (wantFlec && sFlec < N.capacity) pub.store(&N.ray_meta[sFlec], metaFlec);
+			if (wantFrac && sFrac < N.capacity) pub.store(&N.ray_meta[sFrac], metaFrac);
+			if (surface) pub.store(&L.hit_list[hslot], i + 1u);
 		}
 	}
 	flush_stats<STATS>(ws, st);
@@ -957,7 +1005,8 @@ __global__ void k_intersect_object(SceneDev S, uint32_t primBegin, uint32_t prim
 					for (uint32_t k = 0; k < P.tri_count && !stop; ++k)
 					{
 						const uint32_t tri = P.tri_begin + k, slot = S.tri_slot[tri];
-						const float4 g0 = S.tri_geom[3 * slot], g1 = S.tri_geom[3 * slot + 1], g2 = S.tri_geom[3 * slot + 2];
+						float4 g0, g1, g2;
+						load_tri(S.tri_geom, slot, g0, g1, g2);
 						if (!(__float_as_uint(g1.w) & (1u << b)))
 							continue;   // not in this octant's list
 						const uint32_t id = RT_ID_TRI | (b << 28) | tri;

@@ -122,9 +122,8 @@ __device__ __forceinline__ void leaf_tris(const SceneDev &S, const RayD &ray, co
 {
 	for (uint32_t k = 0; k < count; ++k)
 	{
-		const float4 g0 = ldg4(&S.tri_geom[3 * (first + k)]);
-		const float4 g1 = ldg4(&S.tri_geom[3 * (first + k) + 1]);
-		const float4 g2 = ldg4(&S.tri_geom[3 * (first + k) + 2]);
+		float4 g0, g1, g2;
+		load_tri(S.tri_geom, first + k, g0, g1, g2);
 		if (STATS) ++st.tris;
 		const float t = triangle_t(ray.o, ray.d, f3(g0), f3(g1), f3(g2), nullptr);
 		if (ANY ? !(t < best.t) : !(t <= best.t && t < 1e20f))
@@ -229,8 +228,10 @@ __device__ __forceinline__ void traverse(const SceneDev &S, const RayD &ray, con
 	int cur = root;
 	// byte offsets of the near / far plane vectors inside a BvhNode4 for this ray's direction signs
 	const uint32_t sx = __float_as_uint(ray.d.x) >> 31, sy = __float_as_uint(ray.d.y) >> 31, sz = __float_as_uint(ray.d.z) >> 31;
+#if RT_NODE_FETCH == 0
 	const uint32_t onx = sx ? 48u : 0u, ony = sy ? 64u : 16u, onz = sz ? 80u : 32u;
 	const uint32_t ofx = sx ? 0u : 48u, ofy = sy ? 16u : 64u, ofz = sz ? 32u : 80u;
+#endif
 	// Phase voting.  The lanes that entered together decide every step, by majority, whether the warp
 	// runs ONE inner-node step or ONE leaf step; a lane in the minority keeps its node / leaf for a
 	// later step.  The classic while-while shape (every lane descends until it holds a leaf, then all
@@ -263,8 +264,15 @@ __device__ __forceinline__ void traverse(const SceneDev &S, const RayD &ray, con
 			if (atNode)
 			{
 				const char *n = (const char *)&S.nodes4[cur];
+#if RT_NODE_FETCH == 1
+				float4 lx, hx, ly, hy, lz, hz;
+				ldg8(n, lx, hx), ldg8(n + 32, ly, hy), ldg8(n + 64, lz, hz);
+				const float4 nx = sx ? hx : lx, ny = sy ? hy : ly, nz = sz ? hz : lz;
+				const float4 fx = sx ? lx : hx, fy = sy ? ly : hy, fz = sz ? lz : hz;
+#else
 				const float4 nx = ldg4((const float4 *)(n + onx)), ny = ldg4((const float4 *)(n + ony)), nz = ldg4((const float4 *)(n + onz));
 				const float4 fx = ldg4((const float4 *)(n + ofx)), fy = ldg4((const float4 *)(n + ofy)), fz = ldg4((const float4 *)(n + ofz));
+#endif
 				const int4 link = __ldg((const int4 *)(n + 96));
 				if (STATS) ++st.nodes;
 				float t0, t1, t2, t3;

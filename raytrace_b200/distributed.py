@@ -1,7 +1,8 @@
 """Image-space sharding across GPUs.
 
 The frame is cut into row tiles of 8..64 rows (64 = the reference's tile height, RayTracer.cpp:13;
-smaller tiles balance the ranks better); tile t is rendered by rank t % world.  Pixels are independent, so there is no exchange while tracing: the only
+smaller tiles balance the ranks better); tile t is rendered by rank t % world (or, RT_FLAG_SERPENTINE, in
+boustrophedon order).  Pixels are independent, so there is no exchange while tracing: the only
 collective is one gather of the finished RGB8 bands to rank 0 per frame (NCCL over NVLink on GPUs,
 gloo in the CPU tests).  Everything here is plumbing on torch tensors; the kernels live in csrc/.
 """
@@ -12,17 +13,28 @@ import torch
 import torch.distributed as dist
 
 
-def bands_of(rank: int, world: int, height: int, tile_rows: int = 64):
-    """Row tiles rendered by `rank`: tile t (tile_rows rows) belongs to rank t % world.  Only the
-    floor(H/64)*64 rendered rows are tiled, the rest of the frame stays 127."""
-    return list(range(rank, (height // 64) * 64 // tile_rows, world))
+def bands_of(rank: int, world: int, height: int, tile_rows: int = 64, serpentine: bool = False):
+    """Row tiles rendered by `rank`: tile t (tile_rows rows) belongs to rank t % world; with `serpentine`
+    (RT_FLAG_SERPENTINE) the odd groups of `world` tiles are dealt in reverse order, which evens out a
+    ray-cost gradient down the image.  Only the floor(H/64)*64 rendered rows are tiled, the rest stays 127."""
+    n = (height // 64) * 64 // tile_rows
+    if not serpentine or world <= 1:
+        return list(range(rank, n, world))
+    out, k = [], 0
+    while True:
+        t = k * world + (world - 1 - rank if k & 1 else rank)
+        if t >= n:
+            return out
+        out.append(t)
+        k += 1
 
 
 class FrameGather:
     """Pre-allocated buffers + the per-frame gather of one rank's bands to rank 0."""
 
-    def __init__(self, width: int, height: int, rank: int, world: int, device, tile_rows: int = 64):
+    def __init__(self, width: int, height: int, rank: int, world: int, device, tile_rows: int = 64, serpentine: bool = False):
         self.w, self.h, self.rank, self.world, self.tile_rows = width, height, rank, world, tile_rows
+        self.bands = [torch.tensor(bands_of(r, world, height, tile_rows, serpentine), dtype=torch.long, device=device) for r in range(world)]
         self.blk_h = (height // 64) * 64 // tile_rows      # number of row tiles in the frame
         self.band_bytes = tile_rows * width * 3
         self.max_bands = (self.blk_h + world - 1) // world
@@ -36,9 +48,9 @@ class FrameGather:
     def gather(self, frame: torch.Tensor):
         """frame: this rank's (H, W, 3) uint8 framebuffer (only its own bands are valid).
         Returns the assembled frame on rank 0, None elsewhere."""
-        n_mine = len(bands_of(self.rank, self.world, self.h, self.tile_rows))
+        n_mine = len(self.bands[self.rank])
         if n_mine:
-            self.mine[:n_mine].copy_(self._bands_view(frame)[self.rank::self.world])
+            torch.index_select(self._bands_view(frame), 0, self.bands[self.rank], out=self.mine[:n_mine])
         if self.world > 1:
             dist.gather(self.mine, self.parts, dst=0)
         elif self.rank == 0:
@@ -47,9 +59,9 @@ class FrameGather:
             return None
         out = self._bands_view(self.full)
         for r in range(self.world):
-            nb = len(bands_of(r, self.world, self.h, self.tile_rows))
+            nb = len(self.bands[r])
             if nb:
-                out[r::self.world].copy_(self.parts[r][:nb])
+                out.index_copy_(0, self.bands[r], self.parts[r][:nb])
         return self.full
 
 

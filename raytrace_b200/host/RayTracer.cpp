@@ -146,13 +146,22 @@ void RayTracer::start(const uint8_t type, const int8_t)
 	if (rc != RT_OK)
 		fail("rt_render_async", rc);
 
+	// A shard (shardWorld > 1) reads back only the rows it rendered once `output` holds a frame of the same
+	// shard layout: the other rows are the 127 fill of RayTracer.cpp:620 and do not change.  The first frame
+	// of a layout is read back whole.  Decided here, not in the monitor thread, from the values this
+	// start() latched.
+	const uint64_t key = ((uint64_t)shardRank << 48) ^ ((uint64_t)shardWorld << 32) ^ ((uint64_t)shardTileRows << 24) ^ ((uint64_t)(renderFlags & RT_FLAG_SERPENTINE) << 16)
+		^ ((uint64_t)width << 40) ^ (uint64_t)height ^ ((uint64_t)(uintptr_t)output << 1);
+	const bool rowsOnly = shardWorld > 1 && key == outputShardKey;
+	outputShardKey = shardWorld > 1 ? key : 0;
+
 	// the monitor thread of RayTracer.cpp:674-695: waits for the frame, publishes it
-	monitor = std::thread([this]
+	monitor = std::thread([this, rowsOnly]
 	{
 		double seconds = 0.0;
 		int rc = rt_wait(ctx, &seconds);
 		if (rc == RT_OK)
-			rc = rt_read_output(ctx, output, (size_t)width * 3);
+			rc = rowsOnly ? rt_read_output_rows(ctx, output, (size_t)width * 3) : rt_read_output(ctx, output, (size_t)width * 3);
 		if (rc != RT_OK)
 		{
 			fprintf(stderr, "raytrace_b200: frame failed (%d): %s\n", rc, rt_last_error());

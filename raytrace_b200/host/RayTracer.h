@@ -54,6 +54,7 @@ public:
 	uint32_t shardRank = 0, shardWorld = 1;   // image-space shard rendered by this tracer
 	uint32_t shardTileRows = 64;              // rows per shard tile (8, 16, 32, 64)
 	uint32_t renderFlags = 0;       // RT_FLAG_* passed to the next start()
+	uint64_t outputShardKey = 0;    // shard layout of the frame `output` holds (0 = whole frame / nothing): same layout again -> only its rows are read back
 	int smShare = 0;                // resident traversal CTAs per SM of this tracer's pipeline (0 = all 8), for tracers that run concurrently
 	void reserveOutput(size_t bytes);          // frames beyond 2048x2048
 	void wait();                               // block until isFinish

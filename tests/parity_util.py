@@ -35,7 +35,7 @@ def oracle_lib():
     return _oracle
 
 
-def oracle_render(scene, max_level, type=0x80, want_ids=True, threads=None, rank=0, world=1, tile_rows=64):
+def oracle_render(scene, max_level, type=0x80, want_ids=True, threads=None, rank=0, world=1, tile_rows=64, flags=0):
     """-> (image HxWx3 u8, ids HxW structured or None, Counters)"""
     import raytrace_b200 as R
     lib = oracle_lib()
@@ -44,7 +44,7 @@ def oracle_render(scene, max_level, type=0x80, want_ids=True, threads=None, rank
     out = np.empty((h, w, 3), np.uint8)
     ids = np.zeros(w * h, R.HIT_DTYPE) if want_ids else None
     cnt = R.Counters()
-    p = R.RenderParams(type, max_level, rank, world, 0, tile_rows)
+    p = R.RenderParams(type, max_level, rank, world, flags, tile_rows)
     rc = lib.rto_render(d, C.byref(p), out.ctypes.data, ids.ctypes.data if want_ids else None, C.byref(cnt),
                         threads or min(32, os.cpu_count() or 1))
     assert rc == 0, rc

@@ -29,7 +29,8 @@ def case_id(c):
 def gpu_frame(sc, level, typ=R.MY_MODEL_RAYTRACE, want_ids=True, **kw):
     rt = R.RayTracer(sc)
     rt.maxLevel = level
-    img = rt.render(typ, flags=R.RT_FLAG_HIT_IDS if want_ids else 0, **kw)
+    flags = kw.pop("flags", 0) | (R.RT_FLAG_HIT_IDS if want_ids else 0)
+    img = rt.render(typ, flags=flags, **kw)
     ids = rt.hit_ids() if want_ids else None
     return img, ids, rt.counters(), rt
 
@@ -110,6 +111,51 @@ def test_fine_row_tiles_shard_identically(gpu_present):
         rows = [y for y in range(320) if (y // 8) % 5 == r]
         acc[rows] = part[rows]
     assert np.array_equal(acc, full)
+
+
+def test_serpentine_shards_and_row_readback(gpu_present):
+    # RT_FLAG_SERPENTINE deals odd tile groups in reverse rank order; rt_read_output_rows copies only the
+    # shard's rows (both tile families) and leaves the rest of the host frame alone
+    import ctypes as C
+    from raytrace_b200.distributed import bands_of
+    sc = R.Scene("t_mesh", 448, 320)
+    full, _, cf, _ = gpu_frame(sc, 3, want_ids=False)
+    acc = np.full_like(full, 127)
+    total = 0
+    for tile_rows, world in ((8, 4), (16, 3)):
+        acc[:] = 127
+        total = 0
+        for r in range(world):
+            part, ids, c, _ = gpu_frame(sc, 3, rank=r, world=world, tile_rows=tile_rows, flags=R.RT_FLAG_SERPENTINE)
+            opart, oids, oc = oracle_render(sc, 3, rank=r, world=world, tile_rows=tile_rows, flags=R.RT_FLAG_SERPENTINE)
+            assert np.array_equal(part, opart) and compare_ids(ids, oids) == (0, 0)
+            tiles = bands_of(r, world, 320, tile_rows, serpentine=True)
+            rows = [y for y in range(320) if y // tile_rows in tiles]
+            acc[rows] = part[rows]
+            total += c.primary + c.shadow + c.reflect + c.refract
+        assert np.array_equal(acc, full)
+        assert total == cf.primary + cf.shadow + cf.reflect + cf.refract
+    # row read-back through the C ABI: a poisoned host frame keeps its poison outside the shard's rows
+    rt = R.RayTracer(sc)
+    rt.maxLevel = 3
+    for flags in (0, R.RT_FLAG_SERPENTINE):
+        rt.render(R.MY_MODEL_RAYTRACE, flags=flags, rank=1, world=4, tile_rows=8)
+        host = np.full((320, 448, 3), 99, np.uint8)
+        assert R.rt.rt_read_output_rows(C.c_void_p(rt.context()), host.ctypes.data_as(C.c_void_p), 448 * 3) == 0
+        tiles = bands_of(1, 4, 320, 8, serpentine=bool(flags))
+        rows = [y for y in range(320) if y // 8 in tiles]
+        other = [y for y in range(320) if y // 8 not in tiles]
+        assert np.array_equal(host[rows], full[rows]) and (host[other] == 99).all()
+        wide = np.full((320, 448 * 3 + 64), 99, np.uint8)     # padded destination rows (stride > 3*width)
+        assert R.rt.rt_read_output_rows(C.c_void_p(rt.context()), wide.ctypes.data_as(C.c_void_p), 448 * 3 + 64) == 0
+        assert np.array_equal(wide[rows, :448 * 3].reshape(-1, 448, 3), full[rows]) and (wide[other] == 99).all() and (wide[:, 448 * 3:] == 99).all()
+    # one RayTracer re-used across shard layouts: the first frame of a layout is read back whole, repeats only
+    # their rows, and RayTracer::output always equals the oracle's frame of that shard
+    for kw in (dict(), dict(rank=1, world=4, tile_rows=8), dict(rank=1, world=4, tile_rows=8), dict(rank=2, world=4, tile_rows=8),
+               dict(rank=2, world=4, tile_rows=8, flags=R.RT_FLAG_SERPENTINE), dict(rank=2, world=4, tile_rows=8, flags=R.RT_FLAG_SERPENTINE), dict()):
+        img = rt.render(R.MY_MODEL_RAYTRACE, **kw)
+        oimg, _, _ = oracle_render(sc, 3, want_ids=False, **kw)
+        assert np.array_equal(img, oimg), kw
 
 
 def test_scene_edits_reupload_incrementally(gpu_present):

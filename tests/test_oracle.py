@@ -69,3 +69,23 @@ def test_oracle_row_shards_tile_the_frame():
         total += c.primary + c.shadow + c.reflect + c.refract
     assert np.array_equal(acc, full)
     assert total == cfull.primary + cfull.shadow + cfull.reflect + cfull.refract
+
+
+def test_oracle_serpentine_shards_tile_the_frame():
+    # RT_FLAG_SERPENTINE: odd groups of `world` tiles go to the ranks in reverse order
+    from raytrace_b200.distributed import bands_of
+    sc = R.Scene("t_mixed", 320, 256)
+    full, _, cfull = oracle_render(sc, 2, want_ids=False)
+    acc = np.full_like(full, 127)
+    seen = []
+    for r in range(3):
+        part, _, c = oracle_render(sc, 2, want_ids=False, rank=r, world=3, tile_rows=16, flags=R.RT_FLAG_SERPENTINE)
+        tiles = bands_of(r, 3, 256, 16, serpentine=True)
+        seen += tiles
+        rows = [y for y in range(256) if y // 16 in tiles]
+        other = [y for y in range(256) if y // 16 not in tiles]
+        assert (part[other] == 127).all()
+        acc[rows] = part[rows]
+    assert sorted(seen) == list(range(16))
+    assert bands_of(0, 3, 256, 16, serpentine=True) == [0, 5, 6, 11, 12] and bands_of(2, 3, 256, 16, serpentine=True) == [2, 3, 8, 9, 14, 15]
+    assert np.array_equal(acc, full)

@@ -20,7 +20,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, w, h, level, out_path, tile_rows):
+def _worker(rank, world, port, w, h, level, out_path, tile_rows, serpentine):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
@@ -30,28 +30,30 @@ def _worker(rank, world, port, w, h, level, out_path, tile_rows):
     from raytrace_b200.distributed import FrameGather, bands_of
 
     sc = R.Scene("t_mixed", w, h)
-    part, _, cnt = oracle_render(sc, level, want_ids=False, threads=2, rank=rank, world=world, tile_rows=tile_rows)
-    g = FrameGather(w, h, rank, world, torch.device("cpu"), tile_rows)
+    part, _, cnt = oracle_render(sc, level, want_ids=False, threads=2, rank=rank, world=world, tile_rows=tile_rows,
+                                 flags=R.RT_FLAG_SERPENTINE if serpentine else 0)
+    g = FrameGather(w, h, rank, world, torch.device("cpu"), tile_rows, serpentine)
     full = g.gather(torch.from_numpy(part.copy()))
     rays = torch.tensor([cnt.primary + cnt.shadow + cnt.reflect + cnt.refract], dtype=torch.int64)
     dist.all_reduce(rays)
     if rank == 0:
         np.save(out_path, full.numpy())
         np.save(out_path + ".rays.npy", rays.numpy())
-    assert bands_of(rank, world, h, tile_rows) == [t for t in range((h // 64) * 64 // tile_rows) if t % world == rank]
+    if not serpentine:
+        assert bands_of(rank, world, h, tile_rows) == [t for t in range((h // 64) * 64 // tile_rows) if t % world == rank]
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,tile_rows", [(2, 64), (3, 64), (3, 8)])
-def test_bands_gather_to_the_full_frame(tmp_path, world, tile_rows):
+@pytest.mark.parametrize("world,tile_rows,serpentine", [(2, 64, False), (3, 64, False), (3, 8, False), (2, 8, True), (3, 16, True)])
+def test_bands_gather_to_the_full_frame(tmp_path, world, tile_rows, serpentine):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import raytrace_b200 as R
     from parity_util import oracle_render
 
     w, h, level = 256, 330, 3   # 5 bands of 64 rows + 10 never-rendered rows: uneven split on purpose
     out = str(tmp_path / "full.npy")
-    mp.spawn(_worker, args=(world, _free_port(), w, h, level, out, tile_rows), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), w, h, level, out, tile_rows, serpentine), nprocs=world, join=True)
     full = np.load(out)
     sc = R.Scene("t_mixed", w, h)
     ref, _, cnt = oracle_render(sc, level, want_ids=False, threads=2)

@@ -53,7 +53,8 @@ for i in range(2):
         frame = torch.full((h, w, 3), 127, dtype=torch.uint8, device=dev)
         ck(R.rt.rt_set_output(p, C.c_void_p(frame.data_ptr()), frame.numel()), "rt_set_output")
     pipes.append((p, st, landing, frame))
-params = R.RenderParams(R.MY_MODEL_RAYTRACE, level, rank, world, 0, tile_rows)
+SERP = os.environ.get("RT_P2P_SERPENTINE", "1") != "0"       # boustrophedon shard order (RT_FLAG_SERPENTINE), as bench.py uses it
+params = R.RenderParams(R.MY_MODEL_RAYTRACE, level, rank, world, R.RT_FLAG_SERPENTINE if SERP else 0, tile_rows)
 for k in range(6):                      # 3 frames per pipeline, 2 in flight
     p, st, landing, frame = pipes[k % 2]
     ck(R.rt.rt_render_async(p, C.byref(params)), "rt_render_async")
@@ -76,7 +77,7 @@ p, st, landing, frame = pipes[0]
 if rank == 0:
     frame = torch.full((h, w, 3), 127, dtype=torch.uint8, device=dev)
     ck(R.rt.rt_set_output(p, C.c_void_p(frame.data_ptr()), frame.numel()), "rt_set_output")
-g = FrameGather(w, h, rank, world, dev, tile_rows)
+g = FrameGather(w, h, rank, world, dev, tile_rows, SERP)
 ck(R.rt.rt_render_async(p, C.byref(params)), "rt_render_async")
 with torch.cuda.stream(st):
     out = g.gather(frame)

@@ -24,7 +24,9 @@ for nm in names:
     t_build = time.time() - t0
     rt = R.RayTracer(sc)
     rt.maxLevel = level
-    rt.render(R.MY_MODEL_RAYTRACE, flags=R.RT_FLAG_STATS, **SHARD)
+    img = rt.render(R.MY_MODEL_RAYTRACE, flags=R.RT_FLAG_STATS, **SHARD)
+    import hashlib
+    frame_hash = hashlib.sha1(img.tobytes()).hexdigest()[:16]
     cs = rt.counters()
     best = None
     for _ in range(5):
@@ -38,7 +40,7 @@ for nm in names:
     c, wall = best
     total = c.primary + c.shadow + c.reflect + c.refract
     flops = cs.nodes_visited * 4 * 22 + cs.tri_tests * 47 + cs.prim_tests * 23
-    print(json.dumps({"cfg": nm, "world": WORLD, "leaf": os.environ.get("RT_B200_LEAF_SIZE", "2"), "scene_s": round(t_build, 1), "rays": total,
+    print(json.dumps({"cfg": nm, "lib": os.path.basename(os.environ.get("RT_B200_LIBDIR", "lib")), "frame_sha1": frame_hash, "world": WORLD, "leaf": os.environ.get("RT_B200_LEAF_SIZE", "2"), "scene_s": round(t_build, 1), "rays": total,
                       "rays_per_px": round(total / max(c.primary, 1), 2),
                       "render_ms": round(c.render_ms, 3), "start_to_finish_ms": round(wall * 1e3, 3), "mrays_s": round(total / c.render_ms / 1e3, 1),
                       "trace_ms": round(c.trace_ms, 3), "shadow_ms": round(c.shadow_ms, 3), "shade_ms": round(c.shade_ms, 3), "other_ms": round(c.other_ms, 3),
