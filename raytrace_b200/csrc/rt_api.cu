@@ -3,6 +3,7 @@
 // operation runs in the kernels of rt_kernels.cu.  There is deliberately no CPU path here.
 #include "rt_kernels.h"
 #include <atomic>
+#include <thread>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -67,7 +68,7 @@ struct rt_ctx
 	cudaStream_t stream = nullptr, stopStream = nullptr;
 	bool ownStream = false;
 	uint32_t *hStopWord = nullptr;   // pinned constant 3 written into WaveState::overflow by rt_stop
-	cudaEvent_t evStart = nullptr, evStop = nullptr, evA = nullptr, evB = nullptr;
+	cudaEvent_t evStart = nullptr, evStop = nullptr, evA = nullptr, evB = nullptr, evRead = nullptr;
 	cudaEvent_t evStage[4 * (RT_MAX_LEVELS + 1) + 2];   // per level: before trace, after trace, after shadow, after shade; then combine begin/end
 	bool stageTiming = true;
 	double traceMs = 0, shadowMs = 0, shadeMs = 0, otherMs = 0;
@@ -154,7 +155,7 @@ extern "C" int rt_create(int device, rt_ctx **out)
 	CU(cudaStreamCreateWithFlags(&c->stopStream, cudaStreamNonBlocking));
 	CU(cudaMallocHost(&c->hStopWord, sizeof(uint32_t)));
 	*c->hStopWord = 3u;
-	CU(cudaEventCreate(&c->evStart)); CU(cudaEventCreate(&c->evStop)); CU(cudaEventCreate(&c->evA)); CU(cudaEventCreate(&c->evB));
+	CU(cudaEventCreate(&c->evStart)); CU(cudaEventCreate(&c->evStop)); CU(cudaEventCreate(&c->evA)); CU(cudaEventCreate(&c->evB)); CU(cudaEventCreateWithFlags(&c->evRead, cudaEventDisableTiming));
 	for (auto &e : c->evStage) CU(cudaEventCreate(&e));
 	if (const char *v = getenv("RT_B200_STAGE_TIMING")) c->stageTiming = atoi(v) != 0;
 	CU(cudaMallocHost(&c->hFrame, sizeof(FrameParams)));
@@ -219,7 +220,7 @@ extern "C" void rt_destroy(rt_ctx *c)
 	c->dModels.release(), c->dParts.release(), c->nodes.release(), c->nodes4.release(), c->items.release(), c->out.release();
 	rtb_free_scratch(c->scratch);
 	cudaFreeHost(c->hFrame), cudaFree(c->dFrame), cudaFreeHost(c->hWave), cudaFreeHost(c->hWaveInit), cudaFree(c->dWave);
-	cudaEventDestroy(c->evStart), cudaEventDestroy(c->evStop), cudaEventDestroy(c->evA), cudaEventDestroy(c->evB);
+	cudaEventDestroy(c->evStart), cudaEventDestroy(c->evStop), cudaEventDestroy(c->evA), cudaEventDestroy(c->evB), cudaEventDestroy(c->evRead);
 	for (auto &e : c->evStage) cudaEventDestroy(e);
 	if (c->ownStream) cudaStreamDestroy(c->stream);
 	cudaStreamDestroy(c->stopStream), cudaFreeHost(c->hStopWord);
@@ -711,10 +712,23 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 	return RT_OK;
 }
 
+// Wait for an event without monopolising a core: a few polls, then poll + yield.  RayTracer keeps one monitor
+// thread per frame in flight (RayTracer.cpp:674-695 has one too); with 8 ranks x 8 frames on a 32-core
+// host cudaEventSynchronize's busy wait starved the threads that enqueue the next frames.
+static cudaError_t wait_event(cudaEvent_t ev)
+{
+	for (unsigned spins = 0;; ++spins)
+	{
+		const cudaError_t e = cudaEventQuery(ev);
+		if (e != cudaErrorNotReady) return e;
+		if (spins >= 32u) std::this_thread::yield();
+	}
+}
+
 static int finish_frame(rt_ctx *c)
 {
 	CU(cudaSetDevice(c->device));
-	CU(cudaEventSynchronize(c->evB));
+	CU(wait_event(c->evB));
 	float ms = 0;
 	CU(cudaEventElapsedTime(&ms, c->evStart, c->evStop));
 	c->renderMs = ms;
@@ -785,7 +799,8 @@ extern "C" int rt_read_output(rt_ctx *c, uint8_t *rgb, size_t stride)
 	if (stride < row) return fail(RT_E_INVALID, "rt_read_output: stride %zu < %zu", stride, row);
 	CU(cudaMemcpy2DAsync(rgb, stride, c->fb, row, row, (size_t)c->outH, cudaMemcpyDeviceToHost, c->stream));
 	c->frameD2H += row * (size_t)c->outH;
-	CU(cudaStreamSynchronize(c->stream));
+	CU(cudaEventRecord(c->evRead, c->stream));
+	CU(wait_event(c->evRead));
 	return RT_OK;
 }
 
@@ -834,7 +849,8 @@ extern "C" int rt_read_output_rows(rt_ctx *c, uint8_t *rgb, size_t stride)
 	int rc = copy_shard_rows(c, rgb, stride, cudaMemcpyDeviceToHost, c->stream, &bytes);
 	if (rc != RT_OK) return rc;
 	c->frameD2H += bytes;
-	CU(cudaStreamSynchronize(c->stream));
+	CU(cudaEventRecord(c->evRead, c->stream));
+	CU(wait_event(c->evRead));
 	return RT_OK;
 }
 

@@ -521,6 +521,7 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_frame(SceneDev S, const Fram
 	// blocking the lanes whose work is ready, until it is published or the frame is over.
 	// pKind 0: closest-hit rays of level pLevel; pKind 1: shadow rays of level pLevel towards light pLight.
 	uint32_t pKind = 0, pLevel = 0, pLight = 0, pSlot = 0xFFFFFFFFu;
+	const uint32_t nPix0 = (uint32_t)F.blk_w * 64u * F.n_rows;   // level-0 slots of this frame
 	const uint32_t nL = F.max_level + 1u, nQ = nL + (wantShadows ? nL * F.n_enabled : 0u);
 	const uint32_t myQueue = queue_code(lane, nL, F.n_enabled, F.sched_flags);
 	uint32_t statNodes = 0, statKind = 0;   // RT_FLAG_STATS: node visits of the lane's last ray
@@ -596,7 +597,12 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_frame(SceneDev S, const Fram
 			if (pKind == 0u)
 			{
 				if (level == 0u && genPrimary)
-					m = make_uint2(RT_ID_NONE, (uint32_t)MY_RAY_BASERAY_ | (F.epoch << 16)), ready = true;   // made in place below
+				{
+					// made in place below.  Two warps that race for the last batch can both be handed slots; the
+					// loser's lie past the frame (the level's capacity may be larger than this frame): not rays
+					if (pSlot < nPix0) m = make_uint2(RT_ID_NONE, (uint32_t)MY_RAY_BASERAY_ | (F.epoch << 16)), ready = true;
+					else pSlot = 0xFFFFFFFFu;
+				}
 				else
 				{
 					m = __ldcg(&L.ray_meta[pSlot]);
