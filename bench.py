@@ -145,7 +145,9 @@ def run_reference(args, cfg):
         return
     scene, w, h, level, n, parts, desc = cfg
     cores = min(32, os.cpu_count() or 1)   # the reference hard-caps at 32 threads (RayTracer.h:22)
-    tiles = REF_TILES[args.config]
+    # bounded sample: REF_TILES tiles per step at 20 steps, fewer tiles per step for longer runs, so that the
+    # whole run stays within a few minutes whatever K is
+    tiles = max(1, min(REF_TILES[args.config], round(REF_TILES[args.config] * 20 / max(args.steps + args.warmup, 1))))
     ref = os.path.join(ROOT, "oracle", "_ref", "ref_render")
     if os.path.exists(ref):
         kind = "reference"
@@ -216,7 +218,7 @@ def cpu_baseline(args, cfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)   # frames; with M frames in flight a short run is dominated by pipeline fill and drain
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -225,8 +227,10 @@ def main():
                     help="N>1: how the row tiles reach rank 0 -- one-sided NVLink peer copies on the copy engines (rt_push_rows) or an NCCL gather")
     ap.add_argument("--shard-order", default="serpentine", choices=["serpentine", "modulo"],
                     help="N>1: which rank renders row tile t -- boustrophedon (RT_FLAG_SERPENTINE, evens out the ray-cost gradient down the image) or t %% N")
-    ap.add_argument("--pipelines", type=int, default=0, help="frames in flight per GPU (0 = 3 at N=1, 4 at N>1)")
-    ap.add_argument("--sm-share", type=int, default=-1, help="resident traversal CTAs per SM per pipeline (-1 = 4 at N=1, 2 at N>1)")
+    ap.add_argument("--pipelines", type=int, default=0, help="launches in flight per GPU (0 = 3; 1 for frames that run the wave kernels)")
+    ap.add_argument("--sm-share", type=int, default=-1, help="resident traversal CTAs per SM per pipeline (-1 = 4 when several pipelines share the GPU)")
+    ap.add_argument("--batch", type=int, default=0,
+                    help="frames per launch (rt_render_batch_async: the frames of a batch share the ray queues); 0 = N, so that a launch always traces one full frame's worth of pixels per GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     cfg = CONFIGS[args.config]
@@ -264,8 +268,15 @@ def main():
     # the more frames have to be in flight to keep its SMs busy; frames beyond ~3 M pixels per GPU run
     # the per-level wave kernels, which want the whole GPU each (one pipeline)
     big = w * h // world > 3_000_000
-    M = args.pipelines if args.pipelines > 0 else (1 if big else 3 if world == 1 else 4 if world < 8 else 8)
-    share = args.sm_share if args.sm_share >= 0 else (0 if M == 1 else 4 if world == 1 else 2 if world < 8 else 1)
+    # frames per launch: about 8 M pixels per launch and GPU (sweeps in profiles/r1i_batch_sweep_c3.txt: launches of
+    # that size run the per-level wave kernels with queues long enough that their tails do not matter, and two
+    # launches in flight cover each other's level boundaries)
+    pix_rank = (w // 64 * 64) * (h // 64 * 64) // world
+    B = args.batch if args.batch > 0 else (1 if big else max(1, min(64, round(8_000_000 / max(pix_rank, 1)))))
+    M = args.pipelines if args.pipelines > 0 else (1 if big else 2)
+    share = args.sm_share if args.sm_share >= 0 else 0
+    M_e2e = 1 if big else 3 if world == 1 else 4 if world < 8 else 8          # RayTracer objects (one frame each) in flight for the e2e leg
+    share_e2e = 0 if M_e2e == 1 else 4 if world == 1 else 2 if world < 8 else 1
     main = torch.cuda.current_stream(dev)
     owner = C.c_void_p()
     ck(R.rt.rt_create(local, C.byref(owner)), "rt_create")
@@ -284,28 +295,41 @@ def main():
         st = torch.cuda.Stream(dev)
         ck(R.rt.rt_set_stream(hnd, C.c_void_p(st.cuda_stream)), "rt_set_stream")
         ck(R.rt.rt_set_sm_share(hnd, share if M > 1 else 0), "rt_set_sm_share")
-        frame, landing = None, None
-        if p2p:
-            # rank 0 renders straight into the landing buffer the other ranks push their rows to
-            landing = FrameLanding(hnd, w, h, rank, world)
-            if rank == 0:
-                ptr, nbytes = landing.device_ptr()
-                ck(R.rt.rt_set_output(hnd, C.c_void_p(ptr), nbytes), "rt_set_output")
-        if frame is None and not (p2p and rank == 0):
-            frame = torch.full((h, w, 3), 127, dtype=torch.uint8, device=dev)
-            ck(R.rt.rt_set_output(hnd, C.c_void_p(frame.data_ptr()), frame.numel()), "rt_set_output")
-        pipes.append({"ctx": hnd, "stream": st, "frame": frame, "landing": landing,
-                      "consumer": torch.cuda.Stream(dev) if p2p and rank == 0 else None,   # where the assembled frame becomes visible
+        frames, landings, outs = [], [], (C.c_void_p * B)()
+        for f in range(B):
+            frame, landing = None, None
+            if p2p:
+                # rank 0 renders straight into the landing buffer the other ranks push their rows to
+                landing = FrameLanding(hnd, w, h, rank, world)
+                if rank == 0:
+                    outs[f] = landing.device_ptr()[0]
+            if not (p2p and rank == 0):
+                frame = torch.full((h, w, 3), 127, dtype=torch.uint8, device=dev)
+                outs[f] = frame.data_ptr()
+            frames.append(frame), landings.append(landing)
+        pipes.append({"ctx": hnd, "stream": st, "frames": frames, "landings": landings, "outs": outs,
+                      "consumer": torch.cuda.Stream(dev) if p2p and rank == 0 else None,   # where the assembled frames become visible
                       "gather": FrameGather(w, h, rank, world, dev, tile_rows, serp) if world > 1 and not p2p else None})
 
-    def step(k):
-        p = pipes[k % M]
-        ck(R.rt.rt_render_async(p["ctx"], C.byref(params)), "rt_render_async")
-        if p["landing"] is not None:
-            p["landing"].push(p["ctx"], p["consumer"])   # NVLink P2P: this rank's row tiles -> their place in rank 0's frame (copy engines) + signal
-        elif p["gather"] is not None:
-            with torch.cuda.stream(p["stream"]):
-                p["gather"].gather(p["frame"])   # NCCL: this rank's row tiles -> rank 0, de-interleaved there
+    def launch(j, nb):
+        """batch j: nb <= B frames in ONE launch on pipeline j % M, then every frame's rows go to rank 0"""
+        p = pipes[j % M]
+        ck(R.rt.rt_render_batch_async(p["ctx"], C.byref(params), nb, None, p["outs"]), "rt_render_batch_async")
+        for f in range(nb):
+            if p["landings"][f] is not None:
+                p["landings"][f].push(p["ctx"], p["consumer"], frame=f)   # NVLink P2P: this rank's row tiles -> their place in rank 0's frame (copy engines) + signal
+            elif p["gather"] is not None:
+                with torch.cuda.stream(p["stream"]):
+                    p["gather"].gather(p["frames"][f])   # NCCL: this rank's row tiles -> rank 0, de-interleaved there
+
+    def run(nframes):
+        """nframes frames, B per launch (the last launch may hold fewer), round-robin over the M pipelines"""
+        j, left = 0, nframes
+        while left > 0:
+            nb = min(B, left)
+            launch(j, nb)
+            j, left = j + 1, left - nb
+        return j
 
     def fork():
         ev = torch.cuda.Event()
@@ -327,16 +351,15 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    # ---- warm-up + one counted frame (ray totals are deterministic per configuration) ----------
+    # ---- warm-up + one counted launch (ray totals are deterministic per configuration) ----------
     fork()
-    for k in range(max(args.warmup, M)):
-        step(k)
+    run(max(args.warmup, M) * B)                 # whole batches only, every pipeline at least once
     join()
     sync_all()
     cnt = R.Counters()
     ck(R.rt.rt_read_counters(pipes[0]["ctx"], C.byref(cnt)), "rt_read_counters")
-    rays_local = cnt.primary + cnt.shadow + cnt.reflect + cnt.refract
-    launches_per_step = cnt.launches
+    rays_local = (cnt.primary + cnt.shadow + cnt.reflect + cnt.refract) // B    # the frames of a batch are identical here
+    launches_per_batch = cnt.launches
     rays_t = torch.tensor([rays_local], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(rays_t)
@@ -350,8 +373,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(main)
     fork()
-    for k in range(args.steps):
-        step(k)
+    n_launches = run(args.steps)
     join()
     e1.record(main)
     sync_all()
@@ -370,43 +392,49 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     value = rays_total * args.steps / (ms_total * 1e-3) / 1e6
 
-    # ---- one frame alone (latency, per-stage split from the library's own CUDA events) and one
-    #      counted frame for the roofline; both untimed ------------------------------------------------
+    # ---- one launch alone (per-stage split from the library's own CUDA events), one counted launch for the
+    #      roofline, and one single frame alone (latency); all untimed ----------------------------------
     p0 = pipes[0]["ctx"]
     ck(R.rt.rt_set_sm_share(p0, 0), "rt_set_sm_share")
     for _ in range(2):
-        ck(R.rt.rt_render_async(p0, C.byref(params)), "rt_render_async")
+        ck(R.rt.rt_render_batch_async(p0, C.byref(params), B, None, pipes[0]["outs"]), "rt_render_batch_async")
         ck(R.rt.rt_read_counters(p0, C.byref(cnt)), "rt_read_counters")
     stage = {"traverse": cnt.trace_ms, "shade": cnt.shade_ms, "other": cnt.other_ms, "render": cnt.render_ms}
     pstats = R.RenderParams(R.MY_MODEL_RAYTRACE, level, rank, world, R.RT_FLAG_STATS | shard_flags, tile_rows)
-    ck(R.rt.rt_render_async(p0, C.byref(pstats)), "rt_render_async(stats)")
+    ck(R.rt.rt_render_batch_async(p0, C.byref(pstats), B, None, pipes[0]["outs"]), "rt_render_batch_async(stats)")
     cs = R.Counters()
     ck(R.rt.rt_read_counters(p0, C.byref(cs)), "rt_read_counters")
+    c1 = R.Counters()
+    for _ in range(2):
+        ck(R.rt.rt_render_async(p0, C.byref(params)), "rt_render_async")
+        ck(R.rt.rt_read_counters(p0, C.byref(c1)), "rt_read_counters")
+    ms_frame_alone = c1.render_ms
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()                           # nobody unmaps a landing buffer another rank may still push to
     for p in pipes:
-        if p["landing"] is not None:
-            p["landing"].close()
+        for landing in p["landings"]:
+            if landing is not None:
+                landing.close()
         R.rt.rt_destroy(p["ctx"])
     R.rt.rt_destroy(owner)
 
     # ---- e2e: RayTracer::start() with host buffers (flatten + H2D tables + render + D2H frame) ----
     tracers = []
-    for _ in range(M):
+    for _ in range(M_e2e):
         t = R.RayTracer(sc, device=local)        # the drop-in surface; tracers of one Scene share its residency
         t.maxLevel = level
-        t.smShare = share if M > 1 else 0
+        t.smShare = share_e2e if M_e2e > 1 else 0
         tracers.append(t)
-    for k in range(2 * M):
-        tracers[k % M].wait()
-        tracers[k % M].start(R.MY_MODEL_RAYTRACE, flags=shard_flags, rank=rank, world=world, tile_rows=tile_rows)
+    for k in range(2 * M_e2e):
+        tracers[k % M_e2e].wait()
+        tracers[k % M_e2e].start(R.MY_MODEL_RAYTRACE, flags=shard_flags, rank=rank, world=world, tile_rows=tile_rows)
     for t in tracers:
         t.wait()
     sync_all()
     t0 = time.perf_counter()
     for k in range(args.steps):
-        t = tracers[k % M]
+        t = tracers[k % M_e2e]
         t.wait()                                 # frame k-M is in RayTracer::output
         t.start(R.MY_MODEL_RAYTRACE, flags=shard_flags, rank=rank, world=world, tile_rows=tile_rows)
     for t in tracers:
@@ -426,7 +454,7 @@ def main():
         trav_ms = stage["traverse"]
         trav_launches = 1 if cnt.frame_sched else level + 2   # whole-frame scheduler: one traversal launch per frame
         achieved = flops / (trav_ms * 1e-3) / 1e12 if trav_ms > 0 else 0.0
-        queue_bytes = rays_local * 100   # ~100 B of ray/hit/node records written+read per ray
+        queue_bytes = rays_local * B * 100   # ~100 B of ray/hit/node records written+read per ray, B frames per launch
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -434,17 +462,18 @@ def main():
             "config": {"workload": f"{args.config}: {desc}", "rays_per_frame": rays_total, "pixels": w * (h // 64 * 64) if w % 64 == 0 else (w // 64 * 64) * (h // 64 * 64),
                        "l2_policy": "per-frame working set (ray/hit/node queues + BVH + triangles, > 500 MB touched per frame) exceeds the 126 MB L2; no flush needed",
                        "parallelism": (f"image-space: interleaved {tile_rows}-row tiles over {world} GPUs ({'boustrophedon' if serp else 'modulo'} order), " + ("row tiles pushed into rank 0's frame over NVLink P2P (copy engines, put with signal; NCCL only ships the IPC handles)" if p2p else "NCCL gather of RGB8 tiles to rank 0")) if world > 1 else "single GPU",
-                       "frames_in_flight": M, "traversal_ctas_per_sm_per_pipeline": (share if M > 1 and share else 8),
-                       "ms_per_frame_alone": stage["render"]},
+                       "frames_per_launch": B, "launches_in_flight": M, "frames_in_flight": B * M, "traversal_ctas_per_sm_per_pipeline": (share if M > 1 and share else 8),
+                       "e2e_frames_in_flight": M_e2e,
+                       "ms_per_launch_alone": stage["render"], "ms_per_frame_alone": ms_frame_alone},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": float(e2e_s.item()) / args.steps * 1e3,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches_per_step * args.steps,
-            "roofline": {"bound": "fp32_issue", "kernel": "k_frame (one persistent launch per frame: closest-hit + shadow traversal of all levels)" if trav_launches == 1 else "k_wave (closest-hit level l fused with shadow any-hit level l-1; all launches of a frame)", "achieved": achieved, "peak": peak,
+            "gpu_launches": launches_per_batch * n_launches,
+            "roofline": {"bound": "fp32_issue", "kernel": "k_frame (one persistent launch per frame: closest-hit + shadow traversal of all levels)" if trav_launches == 1 else "k_wave (closest-hit level l fused with shadow any-hit level l-1; the level+2 launches of one batch of frames)", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": f"148 SMs x 128 lanes x {peak_src} (of measured)",
                          "traffic": NCU_TRAFFIC.get((args.config, world)), "traffic_source": "profiles/r1h_ncu_full_k_frame_c3.md (dram__bytes_read.sum + dram__bytes_write.sum of one k_frame launch)" if (args.config, world) in NCU_TRAFFIC else None,
                          "launches_per_step": trav_launches, "avg_launch_ms": trav_ms / trav_launches,
-                         "flops_per_step": flops, "nodes_per_ray": cs.nodes_visited / max(rays_local, 1), "tri_tests_per_ray": cs.tri_tests / max(rays_local, 1),
-                         "stage_ms_one_frame_alone": stage,
+                         "flops_per_step": flops, "nodes_per_ray": cs.nodes_visited / max(rays_local * B, 1), "tri_tests_per_ray": cs.tri_tests / max(rays_local * B, 1),
+                         "stage_ms_one_launch_alone": stage,
                          "hbm_secondary": {"queue_bytes_per_step": queue_bytes, "achieved_gbs": queue_bytes / (stage["render"] * 1e-3) / 1e9,
                                            "peak_gbs": hbm_peak}},
             "clocks": clocks, "per_rank": per_rank,

@@ -243,6 +243,16 @@ int rt_upload_scene(rt_ctx *ctx, const rt_scene_desc *scene);
 
 /* replaces RayTracer::start's thread fan-out (RayTracer.cpp:626-695): enqueues one frame, returns at once */
 int rt_render_async(rt_ctx *ctx, const rt_render_params *params);
+/* A batch of frames of the uploaded scene in ONE launch: frame f is seen through cameras[f] (NULL: the uploaded
+ * camera for every frame; only position and orientation may differ from it) and lands in device_outputs[f]
+ * (caller-owned device buffers of >= 3*width*height bytes each; NULL: library-owned, read with
+ * rt_read_batch_output).  The reference renders one frame per start() with a thread pool that shares one tile
+ * counter (RayTracer.cpp:626-672); here the frames of a batch share the ray queues the same way, so the thin
+ * tail of a frame's ray trees is paid once per batch -- what makes 1/8-frame shards on 8 GPUs efficient.
+ * n_frames <= 64.  rt_wait / rt_poll / rt_read_counters then refer to the whole batch. */
+int rt_render_batch_async(rt_ctx *ctx, const rt_render_params *params, uint32_t n_frames, const rt_camera *cameras, void *const *device_outputs);
+/* frame `frame` of the last batch -> host; rows_only != 0 copies only the shard's rows (see rt_read_output_rows) */
+int rt_read_batch_output(rt_ctx *ctx, uint32_t frame, uint8_t *rgb, size_t stride, int rows_only);
 /* replaces the isFinish / useTime polling protocol (RayTracer.h:47-48) */
 int rt_poll(rt_ctx *ctx, int *done, double *seconds);
 int rt_wait(rt_ctx *ctx, double *seconds);
@@ -279,6 +289,7 @@ int rt_landing_open(rt_ctx *ctx, int width, int height, const void *ipc_handle64
 void rt_landing_close(rt_landing *landing);
 int rt_landing_ptr(rt_landing *landing, void **device_ptr, size_t *bytes);
 int rt_push_rows(rt_ctx *ctx, rt_landing *landing, uint64_t seq);
+int rt_push_batch_rows(rt_ctx *ctx, uint32_t frame, rt_landing *landing, uint64_t seq);   /* the same for frame `frame` of the last batch */
 int rt_landing_wait(rt_ctx *ctx, rt_landing *landing, uint64_t seq, uint32_t world, void *consumer_stream /* NULL: ctx's stream */);
 
 /* page-locked host memory for RayTracer::output: rt_read_output into it runs at full PCIe speed */

@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 
 from . import _capi
-from ._capi import Counters, HitId, RenderParams, SceneDesc, rt, rth
+from ._capi import Camera, Counters, HitId, RenderParams, SceneDesc, rt, rth
 
 # RayTracer::start `type` codes (RayTracer.h:5-13 of the reference)
 MY_MODEL_CHECK, MY_MODEL_DEPTHTEST, MY_MODEL_NORMALTEST, MY_MODEL_TEXTURETEST = 1, 2, 3, 4

@@ -115,6 +115,9 @@ RT_SYMBOLS = {
     "rt_stop": (C.c_int, [C.c_void_p]),
     "rt_read_output": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "rt_read_output_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "rt_render_batch_async": (C.c_int, [C.c_void_p, C.POINTER(RenderParams), C.c_uint32, C.POINTER(Camera), C.POINTER(C.c_void_p)]),
+    "rt_read_batch_output": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_int]),
+    "rt_push_batch_rows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]),
     "rt_output_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "rt_set_output": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "rt_landing_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p]),

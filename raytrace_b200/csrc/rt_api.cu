@@ -127,6 +127,10 @@ struct rt_ctx
 	const uint8_t *fillPtr = nullptr;   // what the framebuffer was last filled with 127 for
 	int fillW = 0, fillH = 0;
 	uint32_t fillRank = 0, fillWorld = 0, fillTile = 0, fillSerp = 0;
+	std::vector<DevBuf<uint8_t>> batchOut;   // library-owned framebuffers of batch frames (rt_render_batch_async without outputs)
+	std::vector<uint8_t *> batchFill;        // which buffer each batch slot was last greyed for
+	uint32_t lastBatch = 1;                  // frames of the last launch
+	uint8_t *lastOuts[RT_MAX_BATCH] = {};    // their framebuffers
 	uint32_t keepSalt = 0;      // rotates which CTAs of k_frame are pinned, per pipeline (RT_B200_KEEP_DIV)
 	unsigned ctasPerSm = 0;         // resident traversal CTAs per SM this pipeline may use (0 = all 8), rt_set_sm_share
 };
@@ -218,6 +222,7 @@ extern "C" void rt_destroy(rt_ctx *c)
 	c->boxLo.release(), c->boxHi.release(), c->partMid.release(), c->partPos.release(), c->primMeta.release(), c->textures.release(), c->texels.release();
 	c->triTcoords.release(), c->bvhPrims.release(), c->triSlot.release(), c->triPart.release(), c->leafOrder.release();
 	c->dModels.release(), c->dParts.release(), c->nodes.release(), c->nodes4.release(), c->items.release(), c->out.release();
+	for (auto &b : c->batchOut) b.release();
 	rtb_free_scratch(c->scratch);
 	cudaFreeHost(c->hFrame), cudaFree(c->dFrame), cudaFreeHost(c->hWave), cudaFreeHost(c->hWaveInit), cudaFree(c->dWave);
 	cudaEventDestroy(c->evStart), cudaEventDestroy(c->evStop), cudaEventDestroy(c->evA), cudaEventDestroy(c->evB), cudaEventDestroy(c->evRead);
@@ -526,7 +531,20 @@ static LevelBuf level_buf(const LevelStore &L)
 
 static int finish_frame(rt_ctx *c);
 
+static int render_frames(rt_ctx *c, const rt_render_params *p, uint32_t nFrames, const rt_camera *cams, void *const *outs);
+
 extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
+{
+	return render_frames(c, p, 1, nullptr, nullptr);
+}
+
+extern "C" int rt_render_batch_async(rt_ctx *c, const rt_render_params *p, uint32_t n_frames, const rt_camera *cameras, void *const *device_outputs)
+{
+	if (n_frames < 1 || n_frames > RT_MAX_BATCH) return fail(RT_E_LIMIT, "rt_render_batch_async: %u frames (1..%d)", n_frames, RT_MAX_BATCH);
+	return render_frames(c, p, n_frames, cameras, device_outputs);
+}
+
+static int render_frames(rt_ctx *c, const rt_render_params *p, uint32_t nFrames, const rt_camera *cams, void *const *outs)
 {
 	if (!c || !p) return fail(RT_E_INVALID, "rt_render_async: NULL argument");
 	adopt_scene(c);
@@ -534,6 +552,8 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 	if (p->type != RT_TYPE_RAYTRACE && (p->type < RT_TYPE_CHECK || p->type > RT_TYPE_REFRACT))
 		return fail(RT_E_INVALID, "rt_render_async: unknown render type 0x%x (RayTracer.h:5-13)", p->type);
 	const bool debugStage = p->type >= RT_TYPE_CHECK && p->type <= RT_TYPE_SHADOW;
+	if (nFrames > 1 && (debugStage || (p->flags & RT_FLAG_HIT_IDS)))
+		return fail(RT_E_INVALID, "rt_render_batch_async: the staged debug shaders and RT_FLAG_HIT_IDS render one frame at a time");
 	const uint32_t maxLevel = debugStage ? 0u : p->max_level;   // the staged shaders shade one level only
 	if (maxLevel >= RT_MAX_LEVELS) return fail(RT_E_LIMIT, "rt_render_async: max_level %u (limit %d)", maxLevel, RT_MAX_LEVELS - 1);
 	CU(cudaSetDevice(c->device));
@@ -546,6 +566,9 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 	const rt_camera &cam = c->camera;
 	const int W = cam.width, H = cam.height;
 	if (W <= 0 || H <= 0) return fail(RT_E_INVALID, "rt_render_async: camera is %dx%d", W, H);
+	for (uint32_t f = 0; cams && f < nFrames; ++f)
+		if (cams[f].width != W || cams[f].height != H || cams[f].fovy != cam.fovy || cams[f].zNear != cam.zNear || cams[f].zFar != cam.zFar)
+			return fail(RT_E_INVALID, "rt_render_batch_async: camera %u differs from the uploaded camera in size, fovy or depth range (only position and orientation may vary inside a batch)", f);
 	const uint32_t world = p->world > 1 ? p->world : 1, rank = p->world > 1 ? p->rank : 0;
 	if (rank >= world) return fail(RT_E_INVALID, "rt_render_async: rank %u of world %u", rank, world);
 
@@ -590,10 +613,37 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 		if (l.enabled) F.enabled_index[enabledLights++] = k;
 	}
 	F.n_enabled = enabledLights;
-	const uint32_t nPix = (uint32_t)F.blk_w * 64u * F.n_rows;
+	const uint32_t nPixFrame = (uint32_t)F.blk_w * 64u * F.n_rows;
+	if ((uint64_t)nPixFrame * nFrames > 0x7FFFFFFFull) return fail(RT_E_LIMIT, "rt_render_batch_async: %u frames of %u pixels", nFrames, nPixFrame);
+	const uint32_t nPix = nPixFrame * nFrames;
+	F.batch = nFrames, F.pix_per_frame = nPixFrame;
 
 	// framebuffer: margins stay 127 (RayTracer.cpp:620)
 	uint8_t *fb;
+	if (nFrames > 1 || outs)
+	{
+		// a batch: one framebuffer per frame, the caller's or the library's (rt_read_batch_output)
+		if (c->batchOut.size() < nFrames) c->batchOut.resize(nFrames);
+		if (c->batchFill.size() < nFrames) c->batchFill.resize(nFrames, nullptr);
+		const bool shardChanged = W != c->fillW || H != c->fillH || rank != c->fillRank || world != c->fillWorld || tileRows != c->fillTile || F.serpentine != c->fillSerp;
+		for (uint32_t f = 0; f < nFrames; ++f)
+		{
+			uint8_t *o = outs ? (uint8_t *)outs[f] : nullptr;
+			if (outs && !o) return fail(RT_E_INVALID, "rt_render_batch_async: device_outputs[%u] is NULL", f);
+			if (!o) { CU(c->batchOut[f].reserve((size_t)W * H * 3)); o = c->batchOut[f].p; }
+			if (shardChanged || c->batchFill[f] != o)
+			{
+				CU(cudaMemsetAsync(o, 127, (size_t)W * H * 3, st));
+				c->batchFill[f] = o;
+			}
+			F.frames[f].out = o;
+		}
+		c->fillW = W, c->fillH = H, c->fillRank = rank, c->fillWorld = world, c->fillTile = tileRows, c->fillSerp = F.serpentine, c->fillPtr = nullptr;
+		fb = F.frames[0].out;
+		c->outW = W, c->outH = H, c->fb = fb;
+	}
+	else
+	{
 	if (c->extOut)
 	{
 		if (c->extOutBytes < (size_t)W * H * 3) return fail(RT_E_INVALID, "rt_render_async: external framebuffer holds %zu bytes, frame needs %zu", c->extOutBytes, (size_t)W * H * 3);
@@ -612,6 +662,14 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 		c->fillSerp = F.serpentine;
 		CU(cudaMemsetAsync(fb, 127, (size_t)W * H * 3, st));
 		c->fillPtr = fb, c->fillW = W, c->fillH = H, c->fillRank = rank, c->fillWorld = world, c->fillTile = tileRows;
+		for (auto &b : c->batchFill) b = nullptr;   // the shard the batch buffers were greyed for is no longer current
+	}
+	F.frames[0].out = fb;
+	}
+	for (uint32_t f = 0; f < nFrames; ++f)
+	{
+		const rt_camera &cf = cams ? cams[f] : cam;
+		F.frames[f].cam_u = f4(cf.u), F.frames[f].cam_v = f4(cf.v), F.frames[f].cam_n = f4(cf.n), F.frames[f].cam_pos = f4(cf.position);
 	}
 
 	const bool refr = c->anyRefract && p->type != RT_TYPE_REFLECT;
@@ -707,7 +765,8 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 	CU(cudaEventRecord(c->evStop, st));
 	CU(cudaMemcpyAsync(c->hWave, c->dWave, sizeof(WaveState), cudaMemcpyDeviceToHost, st));
 	CU(cudaEventRecord(c->evB, st));
-	c->lastParams = *p, c->lastPixels = nPix, c->lastLaunches = launches, c->lastMaxLevel = maxLevel;
+	c->lastParams = *p, c->lastPixels = nPix, c->lastLaunches = launches, c->lastMaxLevel = maxLevel, c->lastBatch = nFrames;
+	for (uint32_t f = 0; f < nFrames; ++f) c->lastOuts[f] = F.frames[f].out;
 	c->frameInFlight = true, c->frameValid = false;
 	return RT_OK;
 }
@@ -808,7 +867,7 @@ extern "C" int rt_read_output(rt_ctx *c, uint8_t *rgb, size_t stride)
 // bytes per row), as strided 2-D copies on the copy engines: the tiles of a rank are `world` tiles apart
 // (one copy), with RT_FLAG_SERPENTINE the even and the odd tile groups are each 2*world tiles apart (two).
 // A "row" of such a copy is one tile (tile_rows image rows) when dst is as dense as the framebuffer.
-static int copy_shard_rows(rt_ctx *c, uint8_t *dst, size_t stride, cudaMemcpyKind kind, cudaStream_t st, size_t *bytesOut)
+static int copy_shard_rows(rt_ctx *c, const uint8_t *src, uint8_t *dst, size_t stride, cudaMemcpyKind kind, cudaStream_t st, size_t *bytesOut)
 {
 	const rt_render_params &p = c->lastParams;
 	const uint32_t world = p.world > 1 ? p.world : 1, rank = p.world > 1 ? p.rank : 0;
@@ -827,10 +886,10 @@ static int copy_shard_rows(rt_ctx *c, uint8_t *dst, size_t stride, cudaMemcpyKin
 		const size_t first = (size_t)shard_tile(f, rank, world, serp) * tileRows;        // first image row of the family
 		const size_t pitchRows = (size_t)step * world * tileRows;                        // image rows between two of its tiles
 		if (stride == row)
-			CU(cudaMemcpy2DAsync(dst + first * row, pitchRows * row, c->fb + first * row, pitchRows * row, tileRows * row, count, kind, st));
+			CU(cudaMemcpy2DAsync(dst + first * row, pitchRows * row, src + first * row, pitchRows * row, tileRows * row, count, kind, st));
 		else
 			for (uint32_t t = 0; t < count; ++t)
-				CU(cudaMemcpy2DAsync(dst + (first + t * pitchRows) * stride, stride, c->fb + (first + t * pitchRows) * row, row, row, tileRows, kind, st));
+				CU(cudaMemcpy2DAsync(dst + (first + t * pitchRows) * stride, stride, src + (first + t * pitchRows) * row, row, row, tileRows, kind, st));
 		bytes += (size_t)count * tileRows * row;
 	}
 	if (bytesOut) *bytesOut = bytes;
@@ -846,8 +905,31 @@ extern "C" int rt_read_output_rows(rt_ctx *c, uint8_t *rgb, size_t stride)
 	CU(cudaSetDevice(c->device));
 	if (stride < (size_t)c->outW * 3) return fail(RT_E_INVALID, "rt_read_output_rows: stride %zu < %zu", stride, (size_t)c->outW * 3);
 	size_t bytes = 0;
-	int rc = copy_shard_rows(c, rgb, stride, cudaMemcpyDeviceToHost, c->stream, &bytes);
+	int rc = copy_shard_rows(c, c->fb, rgb, stride, cudaMemcpyDeviceToHost, c->stream, &bytes);
 	if (rc != RT_OK) return rc;
+	c->frameD2H += bytes;
+	CU(cudaEventRecord(c->evRead, c->stream));
+	CU(wait_event(c->evRead));
+	return RT_OK;
+}
+
+extern "C" int rt_read_batch_output(rt_ctx *c, uint32_t frame, uint8_t *rgb, size_t stride, int rows_only)
+{
+	if (!c || !rgb) return fail(RT_E_INVALID, "rt_read_batch_output: NULL argument");
+	if (c->frameInFlight) { int rc = finish_frame(c); if (rc != RT_OK) return rc; }
+	if (!c->fb) return fail(RT_E_STATE, "rt_read_batch_output: nothing rendered yet");
+	if (frame >= c->lastBatch) return fail(RT_E_INVALID, "rt_read_batch_output: frame %u of a batch of %u", frame, c->lastBatch);
+	CU(cudaSetDevice(c->device));
+	const size_t row = (size_t)c->outW * 3;
+	if (stride < row) return fail(RT_E_INVALID, "rt_read_batch_output: stride %zu < %zu", stride, row);
+	size_t bytes = row * (size_t)c->outH;
+	if (rows_only && c->lastParams.world > 1)
+	{
+		int rc = copy_shard_rows(c, c->lastOuts[frame], rgb, stride, cudaMemcpyDeviceToHost, c->stream, &bytes);
+		if (rc != RT_OK) return rc;
+	}
+	else
+		CU(cudaMemcpy2DAsync(rgb, stride, c->lastOuts[frame], row, row, (size_t)c->outH, cudaMemcpyDeviceToHost, c->stream));
 	c->frameD2H += bytes;
 	CU(cudaEventRecord(c->evRead, c->stream));
 	CU(wait_event(c->evRead));
@@ -952,7 +1034,17 @@ extern "C" int rt_landing_ptr(rt_landing *L, void **device_ptr, size_t *bytes)
 
 static uint64_t *landing_flags(rt_landing *L) { return (uint64_t *)(L->base + ((L->frameBytes + 255) & ~(size_t)255)); }
 
-extern "C" int rt_push_rows(rt_ctx *c, rt_landing *L, uint64_t seq)
+static int push_rows(rt_ctx *c, rt_landing *L, uint64_t seq, uint32_t frame);
+
+extern "C" int rt_push_rows(rt_ctx *c, rt_landing *L, uint64_t seq) { return push_rows(c, L, seq, 0); }
+
+extern "C" int rt_push_batch_rows(rt_ctx *c, uint32_t frame, rt_landing *L, uint64_t seq)
+{
+	if (c && frame >= c->lastBatch) return fail(RT_E_INVALID, "rt_push_batch_rows: frame %u of a batch of %u", frame, c->lastBatch);
+	return push_rows(c, L, seq, frame);
+}
+
+static int push_rows(rt_ctx *c, rt_landing *L, uint64_t seq, uint32_t frame)
 {
 	if (!c || !L) return fail(RT_E_INVALID, "rt_push_rows: NULL argument");
 	if (!c->fb) return fail(RT_E_STATE, "rt_push_rows: nothing rendered yet");
@@ -962,9 +1054,10 @@ extern "C" int rt_push_rows(rt_ctx *c, rt_landing *L, uint64_t seq)
 	const uint32_t world = p.world > 1 ? p.world : 1, rank = p.world > 1 ? p.rank : 0;
 	if (rank >= RT_LANDING_FLAGS) return fail(RT_E_LIMIT, "rt_push_rows: rank %u (landing buffers hold %d flags)", rank, RT_LANDING_FLAGS);
 	cudaStream_t st = c->stream;
-	if (c->fb != L->base)
+	const uint8_t *src = c->lastBatch > 1 || frame ? c->lastOuts[frame] : c->fb;
+	if (src != L->base)
 	{
-		int rc = copy_shard_rows(c, L->base, (size_t)c->outW * 3, cudaMemcpyDeviceToDevice, st, nullptr);
+		int rc = copy_shard_rows(c, src, L->base, (size_t)c->outW * 3, cudaMemcpyDeviceToDevice, st, nullptr);
 		if (rc != RT_OK) return rc;
 	}
 	// the flag goes out behind the data on the same stream

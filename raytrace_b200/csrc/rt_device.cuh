@@ -56,7 +56,19 @@ struct DevLight
 	uint32_t type, enabled, pad0, pad1;
 };
 
-// per-frame constants (device memory, rewritten by every rt_render_async)
+// A launch traces a BATCH of frames of one scene (rt_render_batch_async; rt_render_async = a batch of one): same
+// size, lights, depth and shard, one camera and one framebuffer per frame.  The frames share the ray queues --
+// level-0 slot s belongs to frame s / pix_per_frame -- so every warp serves every frame and the thin tail of
+// the ray trees is paid once per batch instead of once per frame.
+#define RT_MAX_BATCH 64
+struct BatchFrame
+{
+	float4 cam_u, cam_v, cam_n, cam_pos;
+	uint8_t *out;              // RGB8 framebuffer of this frame (device)
+	uint64_t pad_;
+};
+
+// per-launch constants (device memory, rewritten by every rt_render_async)
 struct FrameParams
 {
 	float4 cam_u, cam_v, cam_n, cam_pos;
@@ -79,10 +91,22 @@ struct FrameParams
 	uint32_t serpentine;       // RT_FLAG_SERPENTINE: odd tile groups are dealt to the ranks in reverse order
 	uint32_t keep_div;         // k_frame retire policy: 1 = CTAs below `sms` never retire; d > 1 = only every d-th CTA is kept
 	uint32_t keep_salt;        //   (CTA i is kept iff (i + i / sms + keep_salt) % d == 0: spread over the SMs, rotated per pipeline)
-	uint32_t pad_[3];
+	uint32_t batch;            // frames in this launch (1..RT_MAX_BATCH)
+	uint32_t pix_per_frame;    // level-0 slots of one frame
+	uint32_t pad_[1];
 	float4 env_light;
 	DevLight lights[RT_MAX_LIGHTS];
+	BatchFrame frames[RT_MAX_BATCH];
 };
+
+// level-0 slot -> frame of the batch; `i` becomes the slot inside that frame
+__device__ __forceinline__ uint32_t frame_of(const FrameParams &F, uint32_t &i)
+{
+	if (F.batch <= 1u) return 0u;
+	const uint32_t f = i / F.pix_per_frame;
+	i -= f * F.pix_per_frame;
+	return f;
+}
 
 struct SceneItem   // one entry of the scene-order walk (RayTracer.cpp:458)
 {

@@ -118,13 +118,24 @@ __device__ __forceinline__ void lane_stats(WaveState *ws, uint32_t kind, uint32_
 // ---- ray generation ------------------------------------------------------------------------------
 
 // RayTracer::parallelRT, RayTracer.cpp:20-27: dir = cam.n + cam.u*(xcur*dp) + cam.v*(ycur*dp), then Ray() normalises
-__device__ __forceinline__ F3 primary_dir(const FrameParams &F, uint32_t i)
+__device__ __forceinline__ F3 primary_dir(const FrameParams &F, uint32_t i, F3 &origin)
 {
+	const BatchFrame &B = F.frames[frame_of(F, i)];
 	int x, y;
 	slot_to_pixel(F, i, x, y);
 	const int xcur = x - F.half_w, ycur = y - F.half_h;
 	const float sx = (float)(xcur * F.dp), sy = (float)(ycur * F.dp);
-	return normalize((f3(F.cam_n) + f3(F.cam_u) * sx) + f3(F.cam_v) * sy);
+	origin = f3(B.cam_pos);
+	return normalize((f3(B.cam_n) + f3(B.cam_u) * sx) + f3(B.cam_v) * sy);
+}
+
+// level-0 slot -> address of its pixel in the framebuffer of its frame
+__device__ __forceinline__ uint8_t *pixel_of(const FrameParams &F, uint32_t i)
+{
+	const BatchFrame &B = F.frames[frame_of(F, i)];
+	int x, y;
+	slot_to_pixel(F, i, x, y);
+	return B.out + ((size_t)y * F.width + x) * 3;
 }
 
 __global__ void __launch_bounds__(256) k_raygen(const FrameParams *__restrict__ Fp, LevelBuf L, uint32_t n)
@@ -132,14 +143,9 @@ __global__ void __launch_bounds__(256) k_raygen(const FrameParams *__restrict__ 
 	const FrameParams &F = *Fp;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
 	{
-		int x, y;
-		slot_to_pixel(F, i, x, y);
-		const int xcur = x - F.half_w, ycur = y - F.half_h;
-		const float sx = (float)(xcur * F.dp), sy = (float)(ycur * F.dp);
-		// dir = cam.n + cam.u*(xcur*dp) + cam.v*(ycur*dp), then Ray() normalises
-		const F3 dir = (f3(F.cam_n) + f3(F.cam_u) * sx) + f3(F.cam_v) * sy;
-		const F3 d = normalize(dir);
-		L.ray_o[i] = make_float4(F.cam_pos.x, F.cam_pos.y, F.cam_pos.z, 1.0f);
+		F3 o;
+		const F3 d = primary_dir(F, i, o);
+		L.ray_o[i] = make_float4(o.x, o.y, o.z, 1.0f);
 		L.ray_d[i] = make_float4(d.x, d.y, d.z, 1.0f);
 		L.ray_meta[i] = make_uint2(RT_ID_NONE, (uint32_t)MY_RAY_BASERAY_ | (F.epoch << 16));
 	}
@@ -521,7 +527,7 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_frame(SceneDev S, const Fram
 	// blocking the lanes whose work is ready, until it is published or the frame is over.
 	// pKind 0: closest-hit rays of level pLevel; pKind 1: shadow rays of level pLevel towards light pLight.
 	uint32_t pKind = 0, pLevel = 0, pLight = 0, pSlot = 0xFFFFFFFFu;
-	const uint32_t nPix0 = (uint32_t)F.blk_w * 64u * F.n_rows;   // level-0 slots of this frame
+	const uint32_t nPix0 = F.pix_per_frame * F.batch;   // level-0 slots of this launch (all frames of the batch)
 	const uint32_t nL = F.max_level + 1u, nQ = nL + (wantShadows ? nL * F.n_enabled : 0u);
 	const uint32_t myQueue = queue_code(lane, nL, F.n_enabled, F.sched_flags);
 	uint32_t statNodes = 0, statKind = 0;   // RT_FLAG_STATS: node visits of the lane's last ray
@@ -702,8 +708,9 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_frame(SceneDev S, const Fram
 			if (level == 0u && genPrimary)
 			{
 				// primary rays never exist in memory: no k_raygen launch, no 40-byte record written and read back
-				const F3 d = primary_dir(F, i);
-				o4 = make_float4(F.cam_pos.x, F.cam_pos.y, F.cam_pos.z, 1.0f), d4 = make_float4(d.x, d.y, d.z, 1.0f);
+				F3 o;
+				const F3 d = primary_dir(F, i, o);
+				o4 = make_float4(o.x, o.y, o.z, 1.0f), d4 = make_float4(d.x, d.y, d.z, 1.0f);
 			}
 			else
 			{
@@ -1102,9 +1109,7 @@ __global__ void __launch_bounds__(256) k_combine(SceneDev S, const FrameParams *
 		}
 		if (level == 0)
 		{
-			int x, y;
-			slot_to_pixel(F, i, x, y);
-			uint8_t *o = out + ((size_t)y * F.width + x) * 3;
+			uint8_t *o = pixel_of(F, i);
 			o[0] = put8(color.x), o[1] = put8(color.y), o[2] = put8(color.z);
 		}
 	}
@@ -1192,9 +1197,7 @@ __global__ void __launch_bounds__(256) k_resolve(SceneDev S, const FrameParams *
 				break;
 			--d;
 		}
-		int x, y;
-		slot_to_pixel(F, px, x, y);
-		uint8_t *o = out + ((size_t)y * F.width + x) * 3;
+		uint8_t *o = pixel_of(F, px);
 		o[0] = put8(ret.x), o[1] = put8(ret.y), o[2] = put8(ret.z);
 	}
 }

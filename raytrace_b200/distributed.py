@@ -95,12 +95,15 @@ class FrameLanding:
         self._check(self._rt.rt_landing_ptr(self._h, C.byref(p), C.byref(n)), "rt_landing_ptr")
         return p.value, n.value
 
-    def push(self, ctx, consumer_stream=None):
+    def push(self, ctx, consumer_stream=None, frame=None):
         """Enqueue, behind the frame just rendered on `ctx`, the copy of this rank's rows + the signal;
         on the destination rank also the wait for every rank's signal -- on `consumer_stream` (a
         torch.cuda.Stream: whoever reads the assembled frame) or, if None, on the pipeline's own stream."""
         self.seq += 1
-        self._check(self._rt.rt_push_rows(ctx, self._h, self.seq), "rt_push_rows")
+        if frame is None:
+            self._check(self._rt.rt_push_rows(ctx, self._h, self.seq), "rt_push_rows")
+        else:   # frame `frame` of the batch just enqueued on ctx (rt_render_batch_async)
+            self._check(self._rt.rt_push_batch_rows(ctx, frame, self._h, self.seq), "rt_push_batch_rows")
         if self.rank == self.dst and not os.environ.get("RT_DIAG_NO_LANDING_WAIT"):
             cs = C.c_void_p(consumer_stream.cuda_stream) if consumer_stream is not None else None
             self._check(self._rt.rt_landing_wait(ctx, self._h, self.seq, self.world, cs), "rt_landing_wait")

@@ -101,3 +101,56 @@ def test_whole_frame_scheduler_launches_three_kernels(gpu_present, monkeypatch):
     assert c.frame_sched == 1 and c.launches == 3      # k_frame (makes its own primary rays), k_shade, k_resolve
     oimg, _, _ = oracle_render(sc, 5, want_ids=False)
     assert np.array_equal(img, oimg)
+
+
+@pytest.mark.parametrize("scene,level", [("t_mesh", 4), ("t_mixed", 3)])
+def test_frame_batches_equal_single_frames(gpu_present, scene, level):
+    # rt_render_batch_async: B frames with B cameras share one launch and one set of ray queues; every frame must
+    # equal the frame rendered alone through that camera (== the oracle), whole and as a shard
+    w, h = 448, 320
+    sc = R.Scene(scene, w, h)
+    cams = (R.Camera * 3)()
+    singles, rays = [], 0
+    for f, mv in enumerate(((0.0, 0.0, 0.0), (0.6, -0.3, 1.0), (-0.8, 0.4, 0.5))):
+        sc.camera_move(*mv)
+        cams[f] = sc.flatten().contents.camera
+        oimg, _, oc = oracle_render(sc, level, want_ids=False)
+        singles.append(oimg)
+        rays += oc.primary + oc.shadow + oc.reflect + oc.refract
+    assert not np.array_equal(singles[0], singles[1])
+    ctx = C.c_void_p()
+    ck(rt.rt_create(0, C.byref(ctx)))
+    ck(rt.rt_upload_scene(ctx, sc.flatten()))
+    params = R.RenderParams(R.MY_MODEL_RAYTRACE, level, 0, 1, 0, 64)
+    for rep in range(2):                     # twice: the second batch reuses greyed buffers and zeroed hit lists
+        ck(rt.rt_render_batch_async(ctx, C.byref(params), 3, cams, None))
+        ck(rt.rt_wait(ctx, None))
+        for f in range(3):
+            out = np.empty((h, w, 3), dtype=np.uint8)
+            ck(rt.rt_read_batch_output(ctx, f, out.ctypes.data_as(C.c_void_p), w * 3, 0))
+            assert np.array_equal(out, singles[f]), (rep, f)
+        c = R.Counters()
+        ck(rt.rt_read_counters(ctx, C.byref(c)))
+        assert c.primary + c.shadow + c.reflect + c.refract == rays
+    # a batch of shards (serpentine 8-row tiles, rank 1 of 3): rows of the shard equal the single frames, the rest stays 127
+    from raytrace_b200.distributed import bands_of
+    sparams = R.RenderParams(R.MY_MODEL_RAYTRACE, level, 1, 3, R.RT_FLAG_SERPENTINE, 8)
+    ck(rt.rt_render_batch_async(ctx, C.byref(sparams), 3, cams, None))
+    tiles = bands_of(1, 3, h, 8, serpentine=True)
+    rows = [y for y in range(h) if y // 8 in tiles]
+    other = [y for y in range(h) if y // 8 not in tiles]
+    for f in range(3):
+        out = np.empty((h, w, 3), dtype=np.uint8)
+        ck(rt.rt_read_batch_output(ctx, f, out.ctypes.data_as(C.c_void_p), w * 3, 0))
+        assert np.array_equal(out[rows], singles[f][rows]) and (out[other] == 127).all()
+        part = np.full((h, w, 3), 99, np.uint8)
+        ck(rt.rt_read_batch_output(ctx, f, part.ctypes.data_as(C.c_void_p), w * 3, 1))
+        assert np.array_equal(part[rows], singles[f][rows]) and (part[other] == 99).all()
+    # a single frame after a batch still works (framebuffer and fill bookkeeping)
+    ck(rt.rt_render_async(ctx, C.byref(params)))
+    assert np.array_equal(read(ctx, w, h), singles[2])
+    # limits
+    assert rt.rt_render_batch_async(ctx, C.byref(params), 65, None, None) != 0
+    hid = R.RenderParams(R.MY_MODEL_RAYTRACE, level, 0, 1, R.RT_FLAG_HIT_IDS, 64)
+    assert rt.rt_render_batch_async(ctx, C.byref(hid), 2, None, None) != 0
+    rt.rt_destroy(ctx)

@@ -72,6 +72,27 @@ if rank == 0:
         same = bool(np.array_equal(got, full))
         print("p2p landing == full frame:", same, flush=True)
         ok = ok and same
+# (a2) a BATCH of two frames in one launch (rt_render_batch_async), each frame pushed into its own landing buffer
+p0 = pipes[0][0]
+outs = (C.c_void_p * 2)()
+for f in range(2):
+    outs[f] = pipes[f][2].device_ptr()[0] if rank == 0 else pipes[f][3].data_ptr()
+for k in range(2):
+    ck(R.rt.rt_render_batch_async(p0, C.byref(params), 2, None, outs), "rt_render_batch_async")
+    for f in range(2):
+        pipes[f][2].push(p0, frame=f)
+ck(R.rt.rt_wait(p0, None), "rt_wait")
+pipes[0][1].synchronize()
+torch.cuda.synchronize(dev)
+dist.barrier()
+if rank == 0:
+    for f in range(2):
+        got = np.empty((h, w, 3), dtype=np.uint8)
+        ck(R.rt.rt_read_batch_output(p0, f, got.ctypes.data_as(C.c_void_p), w * 3, 0), "rt_read_batch_output")
+        same = bool(np.array_equal(got, full))
+        print(f"batched p2p landing {f} == full frame:", same, flush=True)
+        ok = ok and same
+dist.barrier()
 # (b) NCCL gather of the same shards
 p, st, landing, frame = pipes[0]
 if rank == 0:

@@ -17,6 +17,7 @@ CFG = {"c2": ("c2", 1920, 1080, 5), "c3": ("c3", 1920, 1080, 5), "c4": ("c4", 38
 name, w, h, level = CFG[sys.argv[1] if len(sys.argv) > 1 else "c3"]
 world = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 steps = int(os.environ.get("RT_PIPE_STEPS", "60"))
+BATCH = int(os.environ.get("RT_PIPE_BATCH", "1"))   # frames per launch (rt_render_batch_async)
 
 
 def ck(rc, what):
@@ -42,22 +43,28 @@ for M in [int(x) for x in os.environ.get("RT_PIPE_M", "1 2 3 4").split()]:
     for share in [int(x) for x in os.environ.get("RT_PIPE_SHARE", "0").split()]:
         for p in pipes[:M]:
             ck(R.rt.rt_set_sm_share(p, share), "rt_set_sm_share")
+        def enqueue(p):
+            if BATCH > 1:
+                ck(R.rt.rt_render_batch_async(p, C.byref(params), BATCH, None, None), "rt_render_batch_async")
+            else:
+                ck(R.rt.rt_render_async(p, C.byref(params)), "rt_render_async")
         for p in pipes[:M]:
-            ck(R.rt.rt_render_async(p, C.byref(params)), "rt_render_async")
+            enqueue(p)
         same = True
         for p in pipes[:M]:
             ck(R.rt.rt_wait(p, None), "rt_wait")
-            out = np.empty((h, w, 3), dtype=np.uint8)
-            ck(R.rt.rt_read_output(p, out.ctypes.data_as(C.c_void_p), w * 3), "rt_read_output")
-            same = same and bool((out == ref).all())
+            for f in range(BATCH):
+                out = np.empty((h, w, 3), dtype=np.uint8)
+                ck(R.rt.rt_read_batch_output(p, f, out.ctypes.data_as(C.c_void_p), w * 3, 0), "rt_read_batch_output")
+                same = same and bool((out == ref).all())
         best = None
         for rep in range(3):
             t0 = time.perf_counter()
             for k in range(steps):
-                ck(R.rt.rt_render_async(pipes[k % M], C.byref(params)), "rt_render_async")
+                enqueue(pipes[k % M])
             for p in pipes[:M]:
                 ck(R.rt.rt_wait(p, None), "rt_wait")
             dt = time.perf_counter() - t0
             best = dt if best is None or dt < best else best
-        print(json.dumps({"cfg": name, "world": world, "pipelines": M, "ctas_per_sm": share, "frames_identical": same,
-                          "ms_per_frame": round(best / steps * 1e3, 4), "mrays_s": round(rays * steps / best / 1e6, 1)}), flush=True)
+        print(json.dumps({"cfg": name, "world": world, "batch": BATCH, "pipelines": M, "ctas_per_sm": share, "sched": os.environ.get("RT_B200_SCHED", "auto"), "frames_identical": same,
+                          "ms_per_frame": round(best / (steps * BATCH) * 1e3, 4), "mrays_s": round(rays * steps * BATCH / best / 1e6, 1)}), flush=True)
