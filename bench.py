@@ -7,21 +7,23 @@ One "step" = one frame of the named configuration (default c3: 1920x1080, 1 036 
 + ground plane, 2 lights, shadows + reflection depth 5 -- the configuration BASELINE.json's target
 is quoted on).  A ray = one closest-hit or one shadow any-hit query.
 
-  value    whole-job Mrays/s with the scene resident in HBM: K frames enqueued through the C ABI
-           (rt_render_async) round-robin over M frame pipelines per GPU (rt_create_shared: one
-           resident scene, M frames in flight, each pipeline on its own stream with a share of the resident
-           traversal CTAs per SM), timed with CUDA events that bracket all streams, max over ranks.
-           Every frame is rendered completely; `config.ms_per_frame_alone` is the latency of ONE
-           frame with nothing else in flight.
+  value    whole-job Mrays/s with the scene resident in HBM: K frames enqueued through the C ABI, B frames
+           per launch (rt_render_batch_async: the frames of a launch share the ray queues, so every warp
+           serves every frame and the thin tail of the ray trees is paid once per launch; B is chosen so
+           that a launch holds ~8 M pixels per GPU: 4 frames on one GPU, 32 eighth-frame shards on eight)
+           and M = 2 launches in flight per GPU (rt_create_shared pipelines over one resident scene, each on
+           its own stream), timed with CUDA events that bracket all streams, max over ranks.  Every frame is
+           rendered completely and lands in its own framebuffer; `config.ms_per_frame_alone` is the
+           latency of ONE frame with nothing else in flight, `ms_per_launch_alone` that of one batch.
   e2e      same metric through the reference-facing call RayTracer::start() with HOST buffers:
            every step re-flattens the Scene, uploads the per-frame tables (H2D) and reads the
            RGB8 frame back into RayTracer::output (D2H) inside the timed region.  M RayTracer
            objects over the one Scene (the reference's idiom for several views) keep M frames in
            flight; step k waits for step k-M on the same tracer before it starts.
-  roofline FP32-issue roofline of the traversal kernel (k_frame, or the k_wave launches of a frame):
-           algorithmic FLOPs from device counters (DESIGN.md "flop model") / the kernel's CUDA-event
-           time in a frame rendered alone right after the timed region (inside it the launches of
-           different pipelines overlap, so a per-launch time is not defined there), against
+  roofline FP32-issue roofline of the traversal kernels of one launch (the level+2 k_wave launches of a
+           batch, or one k_frame): algorithmic FLOPs from device counters (DESIGN.md "flop model") / the
+           kernels' CUDA-event time in a launch run alone right after the timed region (inside it the
+           launches of the pipelines overlap, so a per-launch time is not defined there), against
            148 SMs x 128 lanes x sm_max_mhz of MEASURED_PEAKS.json (1 lane-instr = 1 flop because the
            parity path is unfused); HBM figures are reported beside it as the secondary bound.
   cpu_baseline  the reference's own CPU tracer (oracle/_ref/ref_render, else the oracle port) on
@@ -29,7 +31,7 @@ is quoted on).  A ray = one closest-hit or one shadow any-hit query (SURVEY.md 8
 
 N > 1 (torchrun): the frame is split into interleaved 8-row tiles (tile % N == rank), the scene is
 replicated (boustrophedon tile order by default, --shard-order), and every step each rank's rows are delivered into rank 0's frame ("strong" scaling):
-by default with one-sided NVLink peer copies on the copy engines (rt_push_rows; torch.distributed /
+by default with one-sided NVLink peer copies on the copy engines (rt_push_batch_rows; torch.distributed /
 NCCL only carries the IPC handles, barriers and timing reductions), with --gather nccl by an NCCL gather.
 `--impl reference` times the reference CPU tracer itself (rank 0 only).
 """
@@ -52,8 +54,10 @@ CONFIGS = {
     "c3": ("c3", 1920, 1080, 5, 0, 0, "1036800-triangle Model + plane, 2 lights, 1920x1080, depth 5, GPU LBVH"),
     "c4": ("c4", 3840, 2160, 8, 0, 0, "4147200-triangle Model + 64 glass + 6 mirror spheres + plane, 3840x2160, depth 8"),
 }
-# DRAM bytes per traversal launch measured once with `ncu --set full` (profiles/), keyed by (config, gpus)
-NCU_TRAFFIC = {("c3", 1): 736713216}
+# DRAM bytes of the traversal kernels of one launch (k_wave x level+2, or one k_frame) measured once with
+# `ncu --set full` (profiles/), keyed by (config, gpus, frames per launch)
+NCU_TRAFFIC = {("c3", 1, 4): (3312490751, "profiles/r1i_ncu_full_k_wave_batch_c3.md (dram__bytes_read.sum + dram__bytes_write.sum over the 7 k_wave launches of one batch of 4 frames)"),
+               ("c3", 1, 1): (736713216, "profiles/r1h_ncu_full_k_frame_c3.md (dram__bytes_read.sum + dram__bytes_write.sum of one k_frame launch)")}
 REF_TILES = {"c1": 153, "c2": 12, "c3": 6, "c4": 2}   # 64x64 tiles per reference step (bounded sample)
 
 
@@ -470,7 +474,7 @@ def main():
             "gpu_launches": launches_per_batch * n_launches,
             "roofline": {"bound": "fp32_issue", "kernel": "k_frame (one persistent launch per frame: closest-hit + shadow traversal of all levels)" if trav_launches == 1 else "k_wave (closest-hit level l fused with shadow any-hit level l-1; the level+2 launches of one batch of frames)", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": f"148 SMs x 128 lanes x {peak_src} (of measured)",
-                         "traffic": NCU_TRAFFIC.get((args.config, world)), "traffic_source": "profiles/r1h_ncu_full_k_frame_c3.md (dram__bytes_read.sum + dram__bytes_write.sum of one k_frame launch)" if (args.config, world) in NCU_TRAFFIC else None,
+                         "traffic": NCU_TRAFFIC.get((args.config, world, B), (None, None))[0], "traffic_source": NCU_TRAFFIC.get((args.config, world, B), (None, None))[1],
                          "launches_per_step": trav_launches, "avg_launch_ms": trav_ms / trav_launches,
                          "flops_per_step": flops, "nodes_per_ray": cs.nodes_visited / max(rays_local * B, 1), "tri_tests_per_ray": cs.tri_tests / max(rays_local * B, 1),
                          "stage_ms_one_launch_alone": stage,
