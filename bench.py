@@ -275,10 +275,13 @@ def main():
     # frames per launch: about 8 M pixels per launch and GPU (sweeps in profiles/r1i_batch_sweep_c3.txt: launches of
     # that size run the per-level wave kernels with queues long enough that their tails do not matter, and two
     # launches in flight cover each other's level boundaries)
+    # Scenes of analytic primitives only (c1, c2) trace 12-17 Grays/s: their launches are bound by the ray-queue
+    # traffic, which stays closer to the L2 with one frame per launch; they keep three single frames in flight.
     pix_rank = (w // 64 * 64) * (h // 64 * 64) // world
-    B = args.batch if args.batch > 0 else (1 if big else max(1, min(64, round(8_000_000 / max(pix_rank, 1)))))
-    M = args.pipelines if args.pipelines > 0 else (1 if big else 2)
-    share = args.sm_share if args.sm_share >= 0 else 0
+    mesh = args.config in ("c3", "c4")
+    B = args.batch if args.batch > 0 else (1 if big or not mesh else max(1, min(64, round(8_000_000 / max(pix_rank, 1)))))
+    M = args.pipelines if args.pipelines > 0 else (1 if big else 2 if B > 1 else 3)
+    share = args.sm_share if args.sm_share >= 0 else (0 if M == 1 or B > 1 else 4)
     M_e2e = 1 if big else 3 if world == 1 else 4 if world < 8 else 8          # RayTracer objects (one frame each) in flight for the e2e leg
     share_e2e = 0 if M_e2e == 1 else 4 if world == 1 else 2 if world < 8 else 1
     main = torch.cuda.current_stream(dev)
@@ -475,8 +478,8 @@ def main():
             "roofline": {"bound": "fp32_issue", "kernel": "k_frame (one persistent launch per frame: closest-hit + shadow traversal of all levels)" if trav_launches == 1 else "k_wave (closest-hit level l fused with shadow any-hit level l-1; the level+2 launches of one batch of frames)", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": f"148 SMs x 128 lanes x {peak_src} (of measured)",
                          "traffic": NCU_TRAFFIC.get((args.config, world, B), (None, None))[0], "traffic_source": NCU_TRAFFIC.get((args.config, world, B), (None, None))[1],
-                         "launches_per_step": trav_launches, "avg_launch_ms": trav_ms / trav_launches,
-                         "flops_per_step": flops, "nodes_per_ray": cs.nodes_visited / max(rays_local * B, 1), "tri_tests_per_ray": cs.tri_tests / max(rays_local * B, 1),
+                         "kernel_launches_per_batch": trav_launches, "frames_per_batch": B, "avg_launch_ms": trav_ms / trav_launches,
+                         "flops_per_step": flops / B, "flops_per_launch": flops, "nodes_per_ray": cs.nodes_visited / max(rays_local * B, 1), "tri_tests_per_ray": cs.tri_tests / max(rays_local * B, 1),
                          "stage_ms_one_launch_alone": stage,
                          "hbm_secondary": {"queue_bytes_per_step": queue_bytes, "achieved_gbs": queue_bytes / (stage["render"] * 1e-3) / 1e9,
                                            "peak_gbs": hbm_peak}},
