@@ -282,8 +282,14 @@ def main():
     B = args.batch if args.batch > 0 else (1 if big or not mesh else max(1, min(64, round(8_000_000 / max(pix_rank, 1)))))
     M = args.pipelines if args.pipelines > 0 else (1 if big else 2 if B > 1 else 3)
     share = args.sm_share if args.sm_share >= 0 else (0 if M == 1 or B > 1 else 4)
-    M_e2e = 1 if big else 3 if world == 1 else 4 if world < 8 else 8          # RayTracer objects (one frame each) in flight for the e2e leg
-    share_e2e = 0 if M_e2e == 1 else 4 if world == 1 else 2 if world < 8 else 1
+    # e2e leg: RayTracer objects over the one Scene, one frame each per start(), each with its own pipeline and
+    # monitor thread (they overlap the read-backs best).  RT_BENCH_COALESCE=1 switches the tracers to throughput
+    # mode (RayTracer::coalesce: 3 x B tracers feed the Scene's three batch workers, which render what is
+    # waiting in one launch) -- measured slower at N = 1 and 2 (3 520 against 3 655, 6 393 against 6 689
+    # Mrays/s: collecting the starts and reading the frames back serialise per worker), so it is not the default.
+    coalesce = B > 1 and bool(os.environ.get("RT_BENCH_COALESCE"))
+    M_e2e = 1 if big else (min(48, 3 * B) if coalesce else 3 if world == 1 else 4 if world < 8 else 8)
+    share_e2e = 0 if M_e2e == 1 or coalesce else 4 if world == 1 else 2 if world < 8 else 1
     main = torch.cuda.current_stream(dev)
     owner = C.c_void_p()
     ck(R.rt.rt_create(local, C.byref(owner)), "rt_create")
@@ -432,6 +438,7 @@ def main():
         t = R.RayTracer(sc, device=local)        # the drop-in surface; tracers of one Scene share its residency
         t.maxLevel = level
         t.smShare = share_e2e if M_e2e > 1 else 0
+        t.coalesce = coalesce
         tracers.append(t)
     for k in range(2 * M_e2e):
         tracers[k % M_e2e].wait()
@@ -470,7 +477,7 @@ def main():
                        "l2_policy": "per-frame working set (ray/hit/node queues + BVH + triangles, > 500 MB touched per frame) exceeds the 126 MB L2; no flush needed",
                        "parallelism": (f"image-space: interleaved {tile_rows}-row tiles over {world} GPUs ({'boustrophedon' if serp else 'modulo'} order), " + ("row tiles pushed into rank 0's frame over NVLink P2P (copy engines, put with signal; NCCL only ships the IPC handles)" if p2p else "NCCL gather of RGB8 tiles to rank 0")) if world > 1 else "single GPU",
                        "frames_per_launch": B, "launches_in_flight": M, "frames_in_flight": B * M, "traversal_ctas_per_sm_per_pipeline": (share if M > 1 and share else 8),
-                       "e2e_frames_in_flight": M_e2e,
+                       "e2e_frames_in_flight": M_e2e, "e2e_coalesced_starts": coalesce,
                        "ms_per_launch_alone": stage["render"], "ms_per_frame_alone": ms_frame_alone},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": float(e2e_s.item()) / args.steps * 1e3,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

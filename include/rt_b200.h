@@ -251,7 +251,8 @@ int rt_render_async(rt_ctx *ctx, const rt_render_params *params);
  * tail of a frame's ray trees is paid once per batch -- what makes 1/8-frame shards on 8 GPUs efficient.
  * n_frames <= 64.  rt_wait / rt_poll / rt_read_counters then refer to the whole batch. */
 int rt_render_batch_async(rt_ctx *ctx, const rt_render_params *params, uint32_t n_frames, const rt_camera *cameras, void *const *device_outputs);
-/* frame `frame` of the last batch -> host; rows_only != 0 copies only the shard's rows (see rt_read_output_rows) */
+/* frame `frame` of the last batch -> host.  rows_only bit 0: copy only the shard's rows (see rt_read_output_rows);
+ * bit 1: enqueue the copy and return -- a later call without bit 1 waits for all of them (they run in order) */
 int rt_read_batch_output(rt_ctx *ctx, uint32_t frame, uint8_t *rgb, size_t stride, int rows_only);
 /* replaces the isFinish / useTime polling protocol (RayTracer.h:47-48) */
 int rt_poll(rt_ctx *ctx, int *done, double *seconds);

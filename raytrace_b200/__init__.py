@@ -104,6 +104,7 @@ class RayTracer:
         self._h = rth.rth_tracer_new(scene._h, device)
         self.maxLevel = 1
         self.smShare = 0   # resident traversal CTAs per SM (0 = all 8); set when several tracers of one Scene run concurrently
+        self.coalesce = False   # throughput mode: frames of this Scene's tracers that wait together are rendered in one launch (host/RayTracer.h)
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -114,6 +115,7 @@ class RayTracer:
         rth.rth_tracer_set_max_level(self._h, self.maxLevel)
         rth.rth_tracer_set_sm_share(self._h, self.smShare)
         rth.rth_tracer_set_flags(self._h, flags)
+        rth.rth_tracer_set_coalesce(self._h, 1 if self.coalesce else 0)
         rth.rth_tracer_set_shard(self._h, rank, world, tile_rows)
         if rth.rth_tracer_start(self._h, type, tnum) != 0:
             raise RtError(rth.rth_last_error().decode())

@@ -167,6 +167,7 @@ RTH_SYMBOLS = {
     "rth_tracer_set_max_level": (None, [C.c_void_p, C.c_int]),
     "rth_tracer_set_shard": (None, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "rth_tracer_set_flags": (None, [C.c_void_p, C.c_uint]),
+    "rth_tracer_set_coalesce": (None, [C.c_void_p, C.c_int]),
     "rth_tracer_set_sm_share": (None, [C.c_void_p, C.c_int]),
     "rth_tracer_read_hit_ids": (C.c_int, [C.c_void_p, C.POINTER(HitId)]),
     "rth_tracer_read_counters": (C.c_int, [C.c_void_p, C.POINTER(Counters)]),

@@ -923,7 +923,7 @@ extern "C" int rt_read_batch_output(rt_ctx *c, uint32_t frame, uint8_t *rgb, siz
 	const size_t row = (size_t)c->outW * 3;
 	if (stride < row) return fail(RT_E_INVALID, "rt_read_batch_output: stride %zu < %zu", stride, row);
 	size_t bytes = row * (size_t)c->outH;
-	if (rows_only && c->lastParams.world > 1)
+	if ((rows_only & 1) && c->lastParams.world > 1)
 	{
 		int rc = copy_shard_rows(c, c->lastOuts[frame], rgb, stride, cudaMemcpyDeviceToHost, c->stream, &bytes);
 		if (rc != RT_OK) return rc;
@@ -931,6 +931,8 @@ extern "C" int rt_read_batch_output(rt_ctx *c, uint32_t frame, uint8_t *rgb, siz
 	else
 		CU(cudaMemcpy2DAsync(rgb, stride, c->lastOuts[frame], row, row, (size_t)c->outH, cudaMemcpyDeviceToHost, c->stream));
 	c->frameD2H += bytes;
+	if (rows_only & 2)
+		return RT_OK;   // enqueued only: a later call without this bit (same stream, in order) completes them all
 	CU(cudaEventRecord(c->evRead, c->stream));
 	CU(wait_event(c->evRead));
 	return RT_OK;

@@ -3,8 +3,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
 #include <map>
 #include <mutex>
+#include <vector>
 #include <stdexcept>
 
 static void fail(const char *what, int code)
@@ -33,13 +37,141 @@ static void free_output(uint8_t *p, bool pinned)
 	else delete[] p;
 }
 
+// A frame a coalescing tracer asked for: rendered by a batch worker together with whatever else is waiting.
+struct FrameRequest
+{
+	RayTracer *tracer;
+	rt_camera camera;        // the Scene's camera as start() saw it
+	rt_render_params rp;
+	bool rowsOnly;
+};
+
 // One per (Scene, device): the context that holds the uploaded scene, and the flattener that feeds it.
 struct SceneResidency
 {
 	rt_ctx *parent = nullptr;
 	SceneFlattener flattener;
 	std::mutex mutex;   // flatten + upload of concurrent start() calls
-	~SceneResidency() { if (parent) rt_destroy(parent); }
+
+	// ---- batch workers (RayTracer::coalesce): two pipelines on the resident scene, each renders the frames
+	// that are waiting when it becomes free in one launch, so two launches are in flight ----
+	static constexpr int kWorkers = 3;
+	static constexpr size_t kMaxBatch = 64;
+	std::mutex qMutex;
+	std::condition_variable qCv;
+	std::deque<FrameRequest> pending;
+	std::thread workers[kWorkers];
+	rt_ctx *workerCtx[kWorkers] = {};
+	bool workersUp = false, quit = false;
+	int coalescers = 0;       // tracers of this Scene in throughput mode (sizes the coalescing window)
+
+	static bool sameLaunch(const FrameRequest &a, const FrameRequest &b)
+	{
+		return a.rp.type == b.rp.type && a.rp.max_level == b.rp.max_level && a.rp.rank == b.rp.rank && a.rp.world == b.rp.world
+			&& a.rp.flags == b.rp.flags && a.rp.tile_rows == b.rp.tile_rows && a.camera.width == b.camera.width && a.camera.height == b.camera.height
+			&& a.camera.fovy == b.camera.fovy && a.camera.zNear == b.camera.zNear && a.camera.zFar == b.camera.zFar;
+	}
+
+	void workerLoop(int w)
+	{
+		std::vector<FrameRequest> batch;
+		std::vector<rt_camera> cams;
+		while (true)
+		{
+			batch.clear();
+			{
+				std::unique_lock<std::mutex> lock(qMutex);
+				qCv.wait(lock, [this] { return quit || !pending.empty(); });
+				if (pending.empty())
+					return;   // quit
+				// Coalescing window: a caller that keeps T tracers in flight restarts them one after the other,
+				// a few tens of microseconds apart; a worker that took the first request at once would launch
+				// batches of one.  Wait while requests keep arriving, up to this worker's share of the tracers.
+				const size_t want = std::max<size_t>(1, std::min(kMaxBatch, (size_t)(coalescers + kWorkers - 1) / kWorkers));
+				while (!quit && pending.size() < want)
+				{
+					const size_t before = pending.size();
+					qCv.wait_for(lock, std::chrono::microseconds(250));
+					if (pending.size() == before)
+						break;   // nothing new within the window
+				}
+				if (pending.empty())
+					continue;   // the other worker took them
+				batch.push_back(pending.front());
+				pending.pop_front();
+				// everything behind it that can share the launch, in arrival order
+				for (auto it = pending.begin(); it != pending.end() && batch.size() < want;)
+					if (sameLaunch(batch[0], *it)) { batch.push_back(*it); it = pending.erase(it); }
+					else ++it;
+			}
+			cams.clear();
+			for (const FrameRequest &r : batch) cams.push_back(r.camera);
+			rt_ctx *c = workerCtx[w];
+			double seconds = 0.0;
+			int rc;
+			{
+				// the launch adopts the parent's scene tables: not while a start() is uploading into them
+				std::lock_guard<std::mutex> lock(mutex);
+				rc = rt_render_batch_async(c, &batch[0].rp, (uint32_t)batch.size(), cams.data(), nullptr);
+			}
+			if (rc == RT_OK) rc = rt_wait(c, &seconds);
+			// all copies enqueued back to back, one wait (the last call completes them all)
+			for (size_t f = 0; f < batch.size() && rc == RT_OK; ++f)
+				rc = rt_read_batch_output(c, (uint32_t)f, batch[f].tracer->output, (size_t)batch[f].camera.width * 3,
+					(batch[f].rowsOnly ? 1 : 0) | (f + 1 < batch.size() ? 2 : 0));
+			if (rc != RT_OK)
+			{
+				fprintf(stderr, "raytrace_b200: batch of %zu frames failed (%d): %s\n", batch.size(), rc, rt_last_error());
+				abort();
+			}
+			for (const FrameRequest &r : batch)
+				r.tracer->completeFrame(seconds, c);
+		}
+	}
+
+	// -> the worker pipelines exist (created on first use)
+	int ensureWorkers()
+	{
+		std::lock_guard<std::mutex> lock(qMutex);
+		if (workersUp) return RT_OK;
+		for (int w = 0; w < kWorkers; ++w)
+		{
+			const int rc = rt_create_shared(parent, &workerCtx[w]);
+			if (rc != RT_OK) return rc;
+		}
+		for (int w = 0; w < kWorkers; ++w)
+			workers[w] = std::thread([this, w] { workerLoop(w); });
+		workersUp = true;
+		return RT_OK;
+	}
+
+	void enqueue(const FrameRequest &r)
+	{
+		{
+			std::lock_guard<std::mutex> lock(qMutex);
+			pending.push_back(r);
+		}
+		qCv.notify_all();
+	}
+	void addCoalescer(int d)
+	{
+		std::lock_guard<std::mutex> lock(qMutex);
+		coalescers += d;
+	}
+
+	rt_ctx *workerContext(int w) const { return workerCtx[w]; }
+
+	~SceneResidency()
+	{
+		{
+			std::lock_guard<std::mutex> lock(qMutex);
+			quit = true;
+		}
+		qCv.notify_all();
+		for (auto &t : workers) if (t.joinable()) t.join();
+		for (rt_ctx *c : workerCtx) if (c) rt_destroy(c);
+		if (parent) rt_destroy(parent);
+	}
 };
 static std::mutex g_residencyMutex;
 static std::map<std::pair<const Scene *, int>, std::weak_ptr<SceneResidency>> g_residency;
@@ -66,8 +198,8 @@ RayTracer::~RayTracer()
 		std::lock_guard<std::mutex> lock(g_tracersMutex);
 		g_tracers.erase(std::remove(g_tracers.begin(), g_tracers.end(), this), g_tracers.end());
 	}
-	if (monitor.joinable())
-		monitor.join();
+	wait();
+	if (countedAsCoalescer && residency) residency->addCoalescer(-1);
 	if (ctx)
 		rt_destroy(ctx);       // the pipeline first, then (with the last tracer of the Scene) the residency
 	residency.reset();
@@ -111,10 +243,21 @@ void RayTracer::reserveOutput(size_t bytes)
 	output = alloc_output(outputBytes, outputPinned);
 }
 
+void RayTracer::completeFrame(double seconds, rt_ctx *renderedBy)
+{
+	{
+		std::lock_guard<std::mutex> lock(doneMutex);
+		useTime = seconds;
+		lastCtx = renderedBy;
+		queued = false;
+		isFinish = true;
+	}
+	doneCv.notify_all();
+}
+
 void RayTracer::start(const uint8_t type, const int8_t)
 {
-	if (monitor.joinable())
-		monitor.join();
+	wait();
 	isFinish = false;
 	width = scene->cam.width;
 	height = scene->cam.height;
@@ -125,35 +268,56 @@ void RayTracer::start(const uint8_t type, const int8_t)
 			o->RTPrepare();
 
 	int rc;
+	rt_camera frameCamera;
 	{
 		// unchanged tables are not re-sent; while another tracer of this Scene has a frame in flight the
 		// scene must not change (the reference's rule, main.cpp:258,344), so the upload is then a no-op
 		std::lock_guard<std::mutex> lock(residency->mutex);
 		rt_scene_desc desc;
 		flattener->flatten(*scene, desc);
+		frameCamera = desc.camera;
 		rc = rt_upload_scene(residency->parent, &desc);
 	}
 	if (rc != RT_OK)
 		fail("rt_upload_scene", rc);
-	rc = rt_set_sm_share(ctx, smShare);
-	if (rc != RT_OK)
-		fail("rt_set_sm_share", rc);
 	rt_render_params rp;
 	memset(&rp, 0, sizeof rp);
 	rp.type = type, rp.max_level = maxLevel;
 	rp.rank = shardRank, rp.world = shardWorld, rp.flags = renderFlags, rp.tile_rows = shardTileRows;
-	rc = rt_render_async(ctx, &rp);
-	if (rc != RT_OK)
-		fail("rt_render_async", rc);
-
-	// A shard (shardWorld > 1) reads back only the rows it rendered once `output` holds a frame of the same
-	// shard layout: the other rows are the 127 fill of RayTracer.cpp:620 and do not change.  The first frame
-	// of a layout is read back whole.  Decided here, not in the monitor thread, from the values this
-	// start() latched.
 	const uint64_t key = ((uint64_t)shardRank << 48) ^ ((uint64_t)shardWorld << 32) ^ ((uint64_t)shardTileRows << 24) ^ ((uint64_t)(renderFlags & RT_FLAG_SERPENTINE) << 16)
 		^ ((uint64_t)width << 40) ^ (uint64_t)height ^ ((uint64_t)(uintptr_t)output << 1);
 	const bool rowsOnly = shardWorld > 1 && key == outputShardKey;
 	outputShardKey = shardWorld > 1 ? key : 0;
+
+	if (coalesce && type == MY_MODEL_RAYTRACE && !(renderFlags & (RT_FLAG_HIT_IDS | RT_FLAG_STATS | RT_FLAG_BRUTE)))
+	{
+		// throughput mode: the Scene's batch workers render this frame together with whatever else is waiting
+		rc = residency->ensureWorkers();
+		if (rc != RT_OK)
+			fail("rt_create_shared (batch worker)", rc);
+		if (!countedAsCoalescer) residency->addCoalescer(1), countedAsCoalescer = true;
+		FrameRequest r;
+		r.tracer = this, r.camera = frameCamera, r.rp = rp, r.rowsOnly = rowsOnly;
+		{
+			std::lock_guard<std::mutex> lock(doneMutex);
+			queued = true;
+		}
+		lastCtx = nullptr;
+		residency->enqueue(r);
+		return;
+	}
+
+	rc = rt_set_sm_share(ctx, smShare);
+	if (rc != RT_OK)
+		fail("rt_set_sm_share", rc);
+	rc = rt_render_async(ctx, &rp);
+	if (rc != RT_OK)
+		fail("rt_render_async", rc);
+	lastCtx = ctx;
+
+	// (rowsOnly, above: a shard reads back only the rows it rendered once `output` holds a frame of the same
+	// shard layout -- the other rows are the 127 fill of RayTracer.cpp:620 and do not change; the first frame of
+	// a layout is read back whole.  Decided in start(), not in the monitor thread, from the values it latched.)
 
 	// the monitor thread of RayTracer.cpp:674-695: waits for the frame, publishes it
 	monitor = std::thread([this, rowsOnly]
@@ -176,12 +340,17 @@ void RayTracer::stop()
 {
 	if (ctx)
 		rt_stop(ctx);
+	if (residency && queued)   // a coalesced frame: cancel the launches of both batch workers (cooperative, like isRun = false)
+		for (int w = 0; w < SceneResidency::kWorkers; ++w)
+			if (residency->workerContext(w)) rt_stop(residency->workerContext(w));
 }
 
 void RayTracer::wait()
 {
 	if (monitor.joinable())
 		monitor.join();
+	std::unique_lock<std::mutex> lock(doneMutex);
+	doneCv.wait(lock, [this] { return !queued; });
 }
 
 bool RayTracer::readHitIds(rt_hit_id *ids)
@@ -193,7 +362,9 @@ bool RayTracer::readHitIds(rt_hit_id *ids)
 bool RayTracer::readCounters(rt_counters *out)
 {
 	wait();
-	return ctx && rt_read_counters(ctx, out) == RT_OK;
+	// a coalesced frame: the totals of the launch it was part of, valid until that batch worker starts its next launch
+	rt_ctx *c = lastCtx ? lastCtx : ctx;
+	return c && rt_read_counters(c, out) == RT_OK;
 }
 
 // ---- B2: the per-primitive operator, evaluated on the device ----------------------------------------

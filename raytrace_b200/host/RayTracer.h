@@ -6,7 +6,9 @@
 #pragma once
 #include "Scene.h"
 #include "../../include/rt_b200.h"
+#include <condition_variable>
 #include <memory>
+#include <mutex>
 #include <thread>
 
 #define MY_MODEL_CHECK 0x1
@@ -32,8 +34,13 @@ class RayTracer
 	rt_ctx *ctx = nullptr;
 	SceneFlattener *flattener = nullptr;
 	std::thread monitor;
+	rt_ctx *lastCtx = nullptr;      // the pipeline that rendered the last frame (own, or a batch worker's)
 	size_t outputBytes;
 	bool outputPinned = false;
+	std::mutex doneMutex;           // coalesced frames: completion is signalled, not joined
+	std::condition_variable doneCv;
+	bool queued = false;            // a coalesced frame of this tracer is waiting or rendering
+	bool countedAsCoalescer = false;
 	void ensureContext();
 public:
 	GLuint texID = 0;
@@ -56,6 +63,14 @@ public:
 	uint32_t renderFlags = 0;       // RT_FLAG_* passed to the next start()
 	uint64_t outputShardKey = 0;    // shard layout of the frame `output` holds (0 = whole frame / nothing): same layout again -> only its rows are read back
 	int smShare = 0;                // resident traversal CTAs per SM of this tracer's pipeline (0 = all 8), for tracers that run concurrently
+	// Throughput mode.  With `coalesce` set, start() does not launch this tracer's own pipeline: the frame is
+	// queued at the Scene's device residency, whose three batch workers render whatever frames of the Scene's
+	// tracers are waiting -- each through the camera its start() saw -- in ONE launch (rt_render_batch_async:
+	// the frames share the ray queues) and hand every tracer its frame.  Same start()/isFinish/output
+	// protocol; useTime is the time of the launch the frame was part of, readCounters() that launch's totals.
+	// RAYTRACE frames without RT_FLAG_HIT_IDS only; anything else takes the tracer's own pipeline.
+	bool coalesce = false;
+	void completeFrame(double seconds, rt_ctx *renderedBy);        // called by a batch worker when this tracer's frame is in `output`
 	void reserveOutput(size_t bytes);          // frames beyond 2048x2048
 	void wait();                               // block until isFinish
 	bool readHitIds(rt_hit_id *ids);           // primary closest-hit identities of the last frame

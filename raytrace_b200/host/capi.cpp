@@ -148,6 +148,7 @@ void rth_tracer_set_shard(void *t, int rank, int world, int tileRows)
 	r->shardRank = rank, r->shardWorld = world, r->shardTileRows = tileRows > 0 ? tileRows : 64;
 }
 void rth_tracer_set_flags(void *t, unsigned flags) { ((RayTracer *)t)->renderFlags = flags; }
+void rth_tracer_set_coalesce(void *t, int on) { ((RayTracer *)t)->coalesce = on != 0; }
 void rth_tracer_set_sm_share(void *t, int ctasPerSm) { ((RayTracer *)t)->smShare = ctasPerSm; }
 int rth_tracer_read_hit_ids(void *t, rt_hit_id *ids) { return ((RayTracer *)t)->readHitIds(ids) ? 0 : -1; }
 int rth_tracer_read_counters(void *t, rt_counters *c) { return ((RayTracer *)t)->readCounters(c) ? 0 : -1; }

@@ -154,3 +154,45 @@ def test_frame_batches_equal_single_frames(gpu_present, scene, level):
     hid = R.RenderParams(R.MY_MODEL_RAYTRACE, level, 0, 1, R.RT_FLAG_HIT_IDS, 64)
     assert rt.rt_render_batch_async(ctx, C.byref(hid), 2, None, None) != 0
     rt.rt_destroy(ctx)
+
+
+def test_coalescing_tracers_render_their_own_frames(gpu_present):
+    # RayTracer::coalesce: start() calls of several tracers of one Scene are rendered together by the Scene's
+    # batch workers (one launch, shared ray queues), each through the camera its start() saw; every tracer
+    # still gets exactly its own frame, and start()/isFinish/output behave as before
+    w, h, level = 384, 256, 3
+    sc = R.Scene("t_mesh", w, h)
+    twin = R.Scene("t_mesh", w, h)            # the same camera path, walked ahead of time for the oracle frames
+    moves = [(0.1 * (k % 6 + 1), -0.05 * (k % 6 + 1), 0.2) for k in range(18)]
+    expect = []
+    for mv in moves:
+        twin.camera_move(*mv)
+        expect.append(oracle_render(twin, level, want_ids=False)[0])
+    tracers = []
+    for _ in range(6):
+        t = R.RayTracer(sc)
+        t.maxLevel = level
+        t.coalesce = True
+        tracers.append(t)
+    for k, mv in enumerate(moves):            # 18 start() calls back to back: frames pile up and share launches
+        t = tracers[k % 6]
+        t.wait()
+        if k >= 6:
+            assert np.array_equal(t.output(), expect[k - 6])       # the tracer's previous frame, before it is overwritten
+        sc.camera_move(*mv)                   # every start() sees another camera
+        t.start(R.MY_MODEL_RAYTRACE)
+    for k, t in enumerate(tracers):
+        t.wait()
+        assert t.isFinish and t.useTime > 0
+        assert np.array_equal(t.output(), expect[12 + k])
+    # a shard through the coalescing path (rows-only read-back from the second frame on) and a tracer that opts out
+    t = tracers[0]
+    for rep in range(2):
+        img = t.render(R.MY_MODEL_RAYTRACE, flags=R.RT_FLAG_SERPENTINE, rank=1, world=3, tile_rows=8)
+        oimg, _, _ = oracle_render(sc, level, want_ids=False, rank=1, world=3, tile_rows=8, flags=R.RT_FLAG_SERPENTINE)
+        assert np.array_equal(img, oimg)
+    t.coalesce = False
+    img = t.render(R.MY_MODEL_RAYTRACE)
+    assert np.array_equal(img, oracle_render(sc, level, want_ids=False)[0])
+    ids_img = tracers[1].render(R.MY_MODEL_RAYTRACE, flags=R.RT_FLAG_HIT_IDS)     # taps take the tracer's own pipeline
+    assert np.array_equal(ids_img, img) and tracers[1].hit_ids().shape == (h, w)
