@@ -532,6 +532,9 @@ static LevelBuf level_buf(const LevelStore &L)
 static int finish_frame(rt_ctx *c);
 
 static int render_frames(rt_ctx *c, const rt_render_params *p, uint32_t nFrames, const rt_camera *cams, void *const *outs);
+#ifndef RT_WAVE_GENPRIMARY_DEFAULT
+#define RT_WAVE_GENPRIMARY_DEFAULT 0   // k_wave(0) makes the primary rays itself (RT_B200_WAVE_GENPRIMARY=1): off until measured on a B200
+#endif
 
 extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 {
@@ -695,7 +698,10 @@ static int render_frames(rt_ctx *c, const rt_render_params *p, uint32_t nFrames,
 		c->frameEpoch = 1;
 	}
 	F.epoch = c->frameEpoch;
-	const bool genPrimary = c->frameSched && p->type != RT_TYPE_CHECK;
+	// level-0 rays are made inside the traversal kernels (k_frame always; k_wave(0) for the ray-traced types --
+	// the staged debug shaders keep k_raygen, k_debug reads the stored rays)
+	static const int waveGen = []{ const char *e = getenv("RT_B200_WAVE_GENPRIMARY"); return e ? atoi(e) : RT_WAVE_GENPRIMARY_DEFAULT; }();
+	const bool genPrimary = (c->frameSched || (waveGen && !debugStage)) && p->type != RT_TYPE_CHECK;
 	if (genPrimary) F.sched_flags |= 4u;
 	WaveState &Wv = *c->hWaveInit;
 	memset(&Wv, 0, sizeof Wv);

@@ -305,7 +305,17 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_wave(SceneDev S, const Frame
 			int4 aux = make_int4(-1, -1, -1, 0);
 			if (i < n)
 			{
-				const RayD ray = load_ray(L, i);
+				// primary rays are made here (sched_flags bit 2: k_raygen did not run): no 40-byte record written
+				// by one kernel and read back by the next
+				const bool made = level == 0u && (F.sched_flags & 4u);
+				RayD ray;
+				if (made)
+				{
+					ray.d = primary_dir(F, i, ray.o);
+					ray.mtlrfr = 1.0f, ray.skip = RT_ID_NONE, ray.type = MY_RAY_BASERAY_, ray.isInside = 0;
+				}
+				else
+					ray = load_ray(L, i);
 				Best best = { 1e20f, RT_ID_NONE, ray.skip };
 				bool done = false;
 				const uint32_t nodes0 = st.nodes;
@@ -324,7 +334,9 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_wave(SceneDev S, const Frame
 					L.hit_n[i] = make_float4(sf.N.x, sf.N.y, sf.N.z, __int_as_float(sf.mtl));
 					L.hit_uv[i] = make_float4(sf.tu, sf.tv, __int_as_float(sf.tex), 0.0f);
 					const float4 mP = ldg4(&S.materials[4 * sf.mtl + 3]);   // shiness, reflect, refract, rfr
-					const float bwc = L.ray_d[i].w;
+					const float bwc = made ? 1.0f : L.ray_d[i].w;
+					if (made)
+						L.ray_d[i] = make_float4(ray.d.x, ray.d.y, ray.d.z, 1.0f);   // the view direction of a surface is read again by k_shade
 					aux.z = sf.mtl;
 					co = make_float4(P.x, P.y, P.z, 1.0f);
 					if (mP.y > 0.01f)
