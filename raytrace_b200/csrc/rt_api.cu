@@ -533,7 +533,7 @@ static int finish_frame(rt_ctx *c);
 
 static int render_frames(rt_ctx *c, const rt_render_params *p, uint32_t nFrames, const rt_camera *cams, void *const *outs);
 #ifndef RT_WAVE_GENPRIMARY_DEFAULT
-#define RT_WAVE_GENPRIMARY_DEFAULT 0   // k_wave(0) makes the primary rays itself (RT_B200_WAVE_GENPRIMARY=1): off until measured on a B200
+#define RT_WAVE_GENPRIMARY_DEFAULT 1   // k_wave(0) makes the primary rays itself (RT_B200_WAVE_GENPRIMARY=0: k_raygen writes them first); C3 +1.5 %, C2 +1.9 %
 #endif
 
 extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
