@@ -282,13 +282,17 @@ def main():
     B = args.batch if args.batch > 0 else (1 if big or not mesh else max(1, min(64, round(8_000_000 / max(pix_rank, 1)))))
     M = args.pipelines if args.pipelines > 0 else (1 if big else 2 if B > 1 else 3)
     share = args.sm_share if args.sm_share >= 0 else (0 if M == 1 or B > 1 else 4)
-    # e2e leg: RayTracer objects over the one Scene, one frame each per start(), each with its own pipeline and
-    # monitor thread (they overlap the read-backs best).  RT_BENCH_COALESCE=1 switches the tracers to throughput
-    # mode (RayTracer::coalesce: 3 x B tracers feed the Scene's three batch workers, which render what is
-    # waiting in one launch) -- measured slower at N = 1 and 2 (3 520 against 3 655, 6 393 against 6 689
-    # Mrays/s: collecting the starts and reading the frames back serialise per worker), so it is not the default.
-    coalesce = B > 1 and bool(os.environ.get("RT_BENCH_COALESCE"))
-    M_e2e = 1 if big else (min(48, 3 * B) if coalesce else 3 if world == 1 else 4 if world < 8 else 8)
+    # e2e leg: RayTracer objects over the one Scene, one frame each per start().  With frame batches (B > 1) on one
+    # GPU the tracers run in throughput mode (RayTracer::coalesce): 4 x B of them feed the Scene's three batch
+    # workers, which render what is waiting -- B frames per launch, a quarter of the tracers always waiting so
+    # that the next launch is ready when one is delivered -- and hand every tracer its frame (C3: 4 191 against
+    # 3 616 Mrays/s with one pipeline per tracer).  N > 1 keeps one pipeline per tracer (4 / 4 / 8 in flight at
+    # N = 2 / 4 / 8): the one coalesced run on two GPUs (32 tracers, 8 shards per launch) came out at 666 against
+    # 6 689 Mrays/s and could not be investigated in this round.  RT_BENCH_COALESCE=0 / k forces it off / on
+    # with k x B tracers.
+    env_c = os.environ.get("RT_BENCH_COALESCE")
+    coalesce = B > 1 and (env_c != "0") and (world == 1 or bool(env_c))
+    M_e2e = 1 if big else (min(64, int(env_c or "4") * B) if coalesce else 3 if world == 1 else 4 if world < 8 else 8)
     share_e2e = 0 if M_e2e == 1 or coalesce else 4 if world == 1 else 2 if world < 8 else 1
     main = torch.cuda.current_stream(dev)
     owner = C.c_void_p()

@@ -55,13 +55,27 @@ struct SceneResidency
 
 	// ---- batch workers (RayTracer::coalesce): two pipelines on the resident scene, each renders the frames
 	// that are waiting when it becomes free in one launch, so two launches are in flight ----
-	static constexpr int kWorkers = 3;
+	static constexpr int kWorkers = 8;   // at most; nWorkers are started
 	static constexpr size_t kMaxBatch = 64;
 	std::mutex qMutex;
 	std::condition_variable qCv;
 	std::deque<FrameRequest> pending;
 	std::thread workers[kWorkers];
 	rt_ctx *workerCtx[kWorkers] = {};
+	// RT_B200_COALESCE_WORKERS: batch pipelines (launches that can be in flight or delivering), default 3;
+	// RT_B200_COALESCE_DIV: a launch takes up to (coalescing tracers / div) frames, default workers + 1, so that a
+	// quarter of the tracers is always waiting: a worker that has just delivered finds its next launch ready
+	// instead of waiting for its own tracers to be restarted.  With div = workers every tracer is in flight at
+	// once, the workers fall into step and all read back at the same time with nothing rendering (C3, one
+	// GPU, 4 frames per launch: 3 520 Mrays/s against 4 191 with 16 tracers, 3 workers, div 4).
+	int nWorkers = envInt("RT_B200_COALESCE_WORKERS", 3, 1, kWorkers);
+	int wantDiv = envInt("RT_B200_COALESCE_DIV", 0, 0, 64);
+	static int envInt(const char *name, int dflt, int lo, int hi)
+	{
+		const char *e = getenv(name);
+		const int v = e ? atoi(e) : dflt;
+		return v < lo ? lo : v > hi ? hi : v;
+	}
 	bool workersUp = false, quit = false;
 	int coalescers = 0;       // tracers of this Scene in throughput mode (sizes the coalescing window)
 
@@ -87,7 +101,8 @@ struct SceneResidency
 				// Coalescing window: a caller that keeps T tracers in flight restarts them one after the other,
 				// a few tens of microseconds apart; a worker that took the first request at once would launch
 				// batches of one.  Wait while requests keep arriving, up to this worker's share of the tracers.
-				const size_t want = std::max<size_t>(1, std::min(kMaxBatch, (size_t)(coalescers + kWorkers - 1) / kWorkers));
+				const int div = wantDiv > 0 ? wantDiv : nWorkers + 1;
+				const size_t want = std::max<size_t>(1, std::min(kMaxBatch, (size_t)(coalescers + div - 1) / div));
 				while (!quit && pending.size() < want)
 				{
 					const size_t before = pending.size();
@@ -134,12 +149,12 @@ struct SceneResidency
 	{
 		std::lock_guard<std::mutex> lock(qMutex);
 		if (workersUp) return RT_OK;
-		for (int w = 0; w < kWorkers; ++w)
+		for (int w = 0; w < nWorkers; ++w)
 		{
 			const int rc = rt_create_shared(parent, &workerCtx[w]);
 			if (rc != RT_OK) return rc;
 		}
-		for (int w = 0; w < kWorkers; ++w)
+		for (int w = 0; w < nWorkers; ++w)
 			workers[w] = std::thread([this, w] { workerLoop(w); });
 		workersUp = true;
 		return RT_OK;
