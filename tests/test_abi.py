@@ -87,3 +87,31 @@ def test_ballplane_expands_to_16_spheres():
     d = sc.flatten().contents
     subs = [d.prims[i].sub for i in range(d.n_prims) if d.prims[i].object == 1]
     assert subs == list(range(1, 17))
+
+
+def test_batch_and_shard_entry_points_reject_bad_arguments_without_touching_a_gpu():
+    # the entry points added for frame batches and shard read-back validate before any CUDA call
+    rt = _capi.rt
+    p = R.RenderParams(R.MY_MODEL_RAYTRACE, 1, 0, 1, 0, 64)
+    assert rt.rt_render_batch_async(None, C.byref(p), 2, None, None) != 0
+    assert rt.rt_render_batch_async(None, C.byref(p), 0, None, None) != 0 and b"frames" in rt.rt_last_error()
+    assert rt.rt_render_batch_async(None, C.byref(p), 65, None, None) != 0 and b"frames" in rt.rt_last_error()
+    buf = (C.c_uint8 * 16)()
+    assert rt.rt_read_batch_output(None, 0, buf, 12, 0) != 0
+    assert rt.rt_read_output_rows(None, buf, 12) != 0
+    assert rt.rt_push_batch_rows(None, 0, None, 1) != 0
+
+
+def test_serpentine_tile_order_is_a_balanced_partition():
+    # RT_FLAG_SERPENTINE as the host side states it (distributed.bands_of): every tile exactly once, tile counts
+    # differ by at most one, and the tile-index sums (a linear cost gradient down the image) are equal
+    # whenever the tile count is a multiple of 2 * world
+    from raytrace_b200.distributed import bands_of
+    for world, tile_rows, h in ((8, 8, 1080), (4, 8, 1080), (3, 16, 330), (2, 64, 576), (5, 8, 320)):
+        n = (h // 64) * 64 // tile_rows
+        parts = [bands_of(r, world, h, tile_rows, serpentine=True) for r in range(world)]
+        assert sorted(t for p in parts for t in p) == list(range(n))
+        assert max(map(len, parts)) - min(map(len, parts)) <= 1
+        if n % (2 * world) == 0:
+            assert len({sum(p) for p in parts}) == 1
+        assert [t // world for t in parts[0]] == list(range(len(parts[0])))      # one tile per group of `world`
