@@ -3,37 +3,38 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--config c3] [--impl b200|reference]
 
-One "step" = one frame of the named configuration (default c3: 1920x1080, 1 036 800-triangle Model
-+ ground plane, 2 lights, shadows + reflection depth 5 -- the configuration BASELINE.json's target
-is quoted on).  A ray = one closest-hit or one shadow any-hit query.
+One "step" = one pass of the hot path over one BATCH of synthetic input: the `step_frames` frames (32 for c3) of a
+camera orbit around the named configuration's scene (default c3: 1920x1080, 1 036 800-triangle Model + ground
+plane, 2 lights, shadows + reflection depth 5 -- the configuration BASELINE.json's target is quoted on).  Every
+frame of a step has its own camera (scenes.h orbit_camera; camera 0 is the configuration's own camera) and its
+own framebuffer.  The step is the same whatever N is ("scaling": "strong"): N GPUs render 1/N of every frame
+each.  A ray = one closest-hit or one shadow any-hit query.
 
-  value    whole-job Mrays/s with the scene resident in HBM: K frames enqueued through the C ABI, B frames
-           per launch (rt_render_batch_async: the frames of a launch share the ray queues, so every warp
-           serves every frame and the thin tail of the ray trees is paid once per launch; B is chosen so
-           that a launch holds ~8 M pixels per GPU: 4 frames on one GPU, 32 eighth-frame shards on eight)
-           and M = 2 launches in flight per GPU (rt_create_shared pipelines over one resident scene, each on
-           its own stream), timed with CUDA events that bracket all streams, max over ranks.  Every frame is
-           rendered completely and lands in its own framebuffer; `config.ms_per_frame_alone` is the
-           latency of ONE frame with nothing else in flight, `ms_per_launch_alone` that of one batch.
-  e2e      same metric through the reference-facing call RayTracer::start() with HOST buffers:
-           every step re-flattens the Scene, uploads the per-frame tables (H2D) and reads the
-           RGB8 frame back into RayTracer::output (D2H) inside the timed region.  M RayTracer
-           objects over the one Scene (the reference's idiom for several views) keep M frames in
-           flight; step k waits for step k-M on the same tracer before it starts.
-  roofline FP32-issue roofline of the traversal kernels of one launch (the level+2 k_wave launches of a
-           batch, or one k_frame): algorithmic FLOPs from device counters (DESIGN.md "flop model") / the
-           kernels' CUDA-event time in a launch run alone right after the timed region (inside it the
-           launches of the pipelines overlap, so a per-launch time is not defined there), against
-           148 SMs x 128 lanes x sm_max_mhz of MEASURED_PEAKS.json (1 lane-instr = 1 flop because the
-           parity path is unfused); HBM figures are reported beside it as the secondary bound.
-  cpu_baseline  the reference's own CPU tracer (oracle/_ref/ref_render, else the oracle port) on
-           the box's host cores, on a bounded tile sample of the same workload.
+  value    whole-job Mrays/s with the scene resident in HBM: K steps enqueued through the C ABI, B frames per
+           launch (rt_render_batch_async: the frames of a launch share the ray queues, so every warp serves
+           every frame and the thin tail of the ray trees is paid once per launch; B is chosen so that a launch
+           holds ~8 M pixels per GPU: 4 frames on one GPU, 32 eighth-frame shards on eight) and M = 2 launches
+           in flight per GPU (rt_create_shared pipelines over one resident scene, each on its own stream), timed
+           with CUDA events that bracket all streams, max over ranks.
+  latency  `ms_per_frame_alone`: ONE frame (camera 0) with nothing else in flight, per N (the whole-frame
+           scheduler k_frame); `ms_per_launch_alone`: one launch of B frames alone.
+  e2e      same metric through the reference-facing call RayTracer::start() with HOST buffers: every frame of
+           every step re-flattens the Scene with that frame's camera, uploads the per-frame tables (H2D) and
+           reads the RGB8 frame back into RayTracer::output (D2H) inside the timed region.
+  frame_check  after the timed region the first launch of a step is rendered once more through the very same
+           call sequence and frame 0 (camera 0; at N > 1 the frame assembled on rank 0) is hashed and compared
+           with the hash of the UNMODIFIED reference's full frame (tests/golden/fullsize.json); every frame of that
+           launch is also compared with the same camera rendered alone (other scheduler, no batch).
+  roofline FP32-issue roofline of the traversal kernels of one launch: algorithmic FLOPs from device counters
+           (DESIGN.md "flop model") / the kernels' CUDA-event time in a launch run alone right after the timed
+           region, against 148 SMs x 128 lanes x sm_max_mhz of MEASURED_PEAKS.json.
+  cpu_baseline  the reference's own CPU tracer (oracle/_ref/ref_render) on the box's host cores: ONE FULL FRAME of
+           the configuration through RayTracer::start() (wall and the reference's own useTime); its frame hash is
+           compared with the GPU frame of the same run.
 
-N > 1 (torchrun): the frame is split into interleaved 8-row tiles (tile % N == rank), the scene is
-replicated (boustrophedon tile order by default, --shard-order), and every step each rank's rows are delivered into rank 0's frame ("strong" scaling):
-by default with one-sided NVLink peer copies on the copy engines (rt_push_batch_rows; torch.distributed /
-NCCL only carries the IPC handles, barriers and timing reductions), with --gather nccl by an NCCL gather.
-`--impl reference` times the reference CPU tracer itself (rank 0 only).
+N > 1 (torchrun): interleaved 8-row tiles, boustrophedon order, scene replicated; every frame's rows are delivered
+into rank 0's frame by one-sided NVLink peer copies (rt_push_batch_rows) or, with --gather nccl, an NCCL gather.
+`--impl reference` times the reference CPU tracer itself (rank 0 only) on a stratified tile sample per step.
 """
 import argparse
 import ctypes as C
@@ -48,17 +49,39 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CONFIGS = {
-    # name: (scene, width, height, maxLevel, n, parts, description)
-    "c1": ("c1", 1088, 576, 1, 0, 0, "reference default scene (plane + sphere, 2 lights), 1088x576, depth 1"),
-    "c2": ("c2", 1920, 1080, 5, 0, 0, "1024 spheres + plane, 4 point lights, 1920x1080, depth 5"),
-    "c3": ("c3", 1920, 1080, 5, 0, 0, "1036800-triangle Model + plane, 2 lights, 1920x1080, depth 5, GPU LBVH"),
-    "c4": ("c4", 3840, 2160, 8, 0, 0, "4147200-triangle Model + 64 glass + 6 mirror spheres + plane, 3840x2160, depth 8"),
+    # name: (scene, width, height, maxLevel, n, parts, frames per step, description)
+    "c1": ("c1", 1088, 576, 1, 0, 0, 32, "reference default scene (plane + sphere, 2 lights), 1088x576, depth 1"),
+    "c2": ("c2", 1920, 1080, 5, 0, 0, 32, "1024 spheres + plane, 4 point lights, 1920x1080, depth 5"),
+    "c3": ("c3", 1920, 1080, 5, 0, 0, 32, "1036800-triangle Model + plane, 2 lights, 1920x1080, depth 5, GPU LBVH"),
+    "c4": ("c4", 3840, 2160, 8, 0, 0, 4, "4147200-triangle Model + 64 glass + 6 mirror spheres + plane, 3840x2160, depth 8"),
 }
-# DRAM bytes of the traversal kernels of one launch (k_wave x level+2, or one k_frame) measured once with
-# `ncu --set full` (profiles/), keyed by (config, gpus, frames per launch)
-NCU_TRAFFIC = {("c3", 1, 4): (3312490751, "profiles/r1i_ncu_full_k_wave_batch_c3.md (dram__bytes_read.sum + dram__bytes_write.sum over the 7 k_wave launches of one batch of 4 frames)"),
-               ("c3", 1, 1): (736713216, "profiles/r1h_ncu_full_k_frame_c3.md (dram__bytes_read.sum + dram__bytes_write.sum of one k_frame launch)")}
-REF_TILES = {"c1": 153, "c2": 12, "c3": 6, "c4": 2}   # 64x64 tiles per reference step (bounded sample)
+
+
+def workload_config(name):
+    """The `config` object of the JSON line -- identical for both arms (the driver compares them)."""
+    scene, w, h, level, n, parts, sframes, desc = CONFIGS[name]
+    return {"workload": f"{name}: {desc}", "step": f"{sframes} frames of a {sframes}-camera orbit around the scene (camera 0 = the configuration's own camera), one framebuffer per frame",
+            "step_frames": sframes, "pixels_per_frame": (w // 64 * 64) * (h // 64 * 64),
+            "l2_policy": "per-step working set (ray/hit queues of ~8 M pixels per launch + BVH + triangles, > 2 GB touched per launch) exceeds the 126 MB L2; no flush needed"}
+
+
+def golden_fullsize(name):
+    try:
+        return json.load(open(os.path.join(ROOT, "tests", "golden", "fullsize.json"))).get(name)
+    except Exception:
+        return None
+
+
+def ncu_traffic(name, world, B):
+    """DRAM bytes of the traversal kernels of one launch from the committed ncu capture of THIS source state
+    (profiles/ncu_traffic.json, written by tools/ncu_traffic.py from an `ncu --set full` report); None when no capture
+    matches the configuration."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        e = t.get(f"{name}:n{world}:b{B}")
+        return (e["bytes_per_launch"], e["source"]) if e else (None, None)
+    except Exception:
+        return (None, None)
 
 
 def sm_peak_fp32_tflops():
@@ -142,79 +165,102 @@ class ClockSampler:
                 "reasons": sorted(n for b, n in self.NAMES.items() if bits & b), "samples": len(sm), "source": self.src}
 
 
-def run_reference(args, cfg):
-    """--impl reference: the reference's own CPU tracer on the host cores (rank 0 only)."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "ref_render")
+
+
+def ref_cmd(name, threads, *extra):
+    scene, w, h, level, n, parts, sframes, desc = CONFIGS[name]
+    return [REF_BIN, "--scene", scene, "--width", str(w), "--height", str(h), "--level", str(level), "--n", str(n), "--parts", str(parts),
+            "--threads", str(threads), "--tmpdir", "/tmp", *[str(x) for x in extra]]
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU tracer on the host cores (rank 0 only).
+
+    Each step traces a STRATIFIED sample of 64x64 tiles (every k-th tile of the frame in row-major tile order, so
+    all tile rows are covered) of one frame of the orbit -- step s uses camera s of the orbit -- through the
+    reference's per-pixel entry RTfrac on all host threads (64-pixel rows handed out one at a time, so every
+    thread works).  The reference's single-threaded per-frame RTPrepare is timed apart and charged in proportion:
+    step seconds = trace_s + prepare_s * sample_tiles / frame_tiles, which is what a full frame costs per tile.
+    The sample size is calibrated so that the whole --steps/--warmup run takes about 2.5 minutes."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    scene, w, h, level, n, parts, desc = cfg
+    name = args.config
+    scene, w, h, level, n, parts, sframes, desc = CONFIGS[name]
     cores = min(32, os.cpu_count() or 1)   # the reference hard-caps at 32 threads (RayTracer.h:22)
-    # bounded sample: REF_TILES tiles per step at 20 steps, fewer tiles per step for longer runs, so that the
-    # whole run stays within a few minutes whatever K is
-    tiles = max(1, min(REF_TILES[args.config], round(REF_TILES[args.config] * 20 / max(args.steps + args.warmup, 1))))
-    ref = os.path.join(ROOT, "oracle", "_ref", "ref_render")
-    if os.path.exists(ref):
+    frame_tiles = (w // 64) * (h // 64)
+    passes = max(args.steps + args.warmup, 1)
+    if os.path.exists(REF_BIN):
         kind = "reference"
-        out = subprocess.check_output([ref, "--scene", scene, "--width", str(w), "--height", str(h), "--level", str(level), "--n", str(n),
-                                       "--parts", str(parts), "--threads", str(cores), "--tiles", str(tiles), "--counts",
-                                       "--repeat", str(args.steps), "--warmup", str(args.warmup)]).decode()
-        j = json.loads(out.strip().splitlines()[-1])
-        secs, rays, px = j["step_s"], j["rays_per_step"], j["pixels"]
+        cal_tiles = min(frame_tiles, max(4, frame_tiles // 40))
+        cal = json.loads(subprocess.check_output(ref_cmd(name, cores, "--tiles", cal_tiles, "--stratified", "--repeat", 1)).decode().strip().splitlines()[-1])
+        per_tile = max(cal["step_s"][0] / cal_tiles, 1e-6)
+        tiles = int(max(4, min(frame_tiles, round(150.0 / passes / per_tile))))
+        j = json.loads(subprocess.check_output(ref_cmd(name, cores, "--tiles", tiles, "--stratified", "--counts", "--orbit", sframes,
+                                                       "--repeat", args.steps, "--warmup", args.warmup)).decode().strip().splitlines()[-1])
+        frac = tiles / frame_tiles
+        secs = [t + p * frac for t, p in zip(j["step_s"], j["prepare_s"])]
+        rays, px = j["rays_per_step"], j["pixels"]
+        sample = (f"{tiles} of {frame_tiles} 64x64 tiles, stratified over the {w}x{h} frame ({px} px, {rays} rays in the counted pass), one orbit camera per step, "
+                  f"{cores} threads; step seconds = trace + RTPrepare ({sum(j['prepare_s']) / len(j['prepare_s']):.3f} s per frame) x {frac:.3f}")
     else:
         kind = "port"
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import raytrace_b200 as R
         from parity_util import oracle_render
         sc = R.Scene(scene, w, h, n, parts)
-        world = max(1, (h // 64) * (w // 64) // tiles)
-        world = min(world, h // 64)
+        world = 16
         secs = []
         for s in range(args.warmup + args.steps):
             t0 = time.time()
-            _, _, c = oracle_render(sc, level, want_ids=False, threads=cores, rank=0, world=world)
+            _, _, c = oracle_render(sc, level, want_ids=False, threads=cores, rank=s % world, world=world, tile_rows=8)
             if s >= args.warmup:
                 secs.append(time.time() - t0)
         rays, px = c.primary + c.shadow + c.reflect + c.refract, c.primary
+        sample = f"oracle port (oracle/rt_oracle.cpp), interleaved 8-row tiles rank s%16 of 16 ({px} px, {rays} rays) of the {w}x{h} frame per step, {cores} threads"
     total = sum(secs)
     mrays = rays * len(secs) / total / 1e6
-    sample = f"{tiles} seeded 64x64 tiles ({px} px, {rays} rays) of the {w}x{h} frame per step, {cores} threads"
     line = {"impl": "reference", "metric": "Mrays/s", "value": mrays, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total / len(secs) * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.config}: {desc}", "sample": sample},
+            "config": workload_config(name),
             "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline(args, cfg):
-    """Bounded reference sample timed beside the GPU numbers (rank 0, N=1 only)."""
-    scene, w, h, level, n, parts, desc = cfg
+def cpu_baseline(args, gpu_hash):
+    """One FULL frame of the configuration (camera 0) through the reference's RayTracer::start() on the host cores
+    (rank 0, N=1 only): wall start()->isFinish, the reference's own useTime, and the frame hash."""
+    name = args.config
+    scene, w, h, level, n, parts, sframes, desc = CONFIGS[name]
     cores = min(32, os.cpu_count() or 1)
-    tiles = REF_TILES[args.config]
-    ref = os.path.join(ROOT, "oracle", "_ref", "ref_render")
+    rays_frame = (golden_fullsize(name) or {}).get("rays", {}).get("total")
     try:
-        if os.path.exists(ref):
-            out = subprocess.check_output([ref, "--scene", scene, "--width", str(w), "--height", str(h), "--level", str(level), "--n", str(n),
-                                           "--parts", str(parts), "--threads", str(cores), "--tiles", str(tiles), "--counts",
-                                           "--repeat", "2", "--warmup", "1"], timeout=900).decode()
-            j = json.loads(out.strip().splitlines()[-1])
-            v = j["rays_per_step"] * len(j["step_s"]) / sum(j["step_s"]) / 1e6
-            return {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "reference",
-                    "sample": f"{tiles} seeded 64x64 tiles ({j['pixels']} px, {j['rays_per_step']} rays) of the {w}x{h} frame, 2 timed passes after 1 warm-up"}
+        if os.path.exists(REF_BIN) and name != "c4":
+            j = json.loads(subprocess.check_output(ref_cmd(name, cores, "--repeat", 1), timeout=1500).decode().strip().splitlines()[-1])
+            wall, use = j["wall_s"][0], j["useTime_s"][0]
+            return {"value": rays_frame / wall / 1e6 if rays_frame else None, "unit": "Mrays/s", "cores": cores, "kind": "reference",
+                    "sample": f"one full {w}x{h} frame through the reference's RayTracer::start() ({rays_frame} rays): wall {wall:.2f} s, useTime {use:.2f} s",
+                    "wall_s": wall, "useTime_s": use, "frame_hash": j["hash"], "same_frame_as_gpu": (j["hash"] == gpu_hash) if gpu_hash else None}
+        if os.path.exists(REF_BIN):
+            # c4: a full frame is ~an hour of CPU -- stratified tiles through the per-pixel entry, labelled as such (SURVEY 8d)
+            frame_tiles, tiles = (w // 64) * (h // 64), 60
+            j = json.loads(subprocess.check_output(ref_cmd(name, cores, "--tiles", tiles, "--stratified", "--counts", "--repeat", 1), timeout=1500).decode().strip().splitlines()[-1])
+            secs = j["step_s"][0] + j["prepare_s"][0] * tiles / frame_tiles
+            return {"value": j["rays_per_step"] / secs / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "reference",
+                    "sample": f"{tiles} of {frame_tiles} 64x64 tiles stratified over the {w}x{h} frame ({j['rays_per_step']} rays), trace {j['step_s'][0]:.2f} s + RTPrepare {j['prepare_s'][0]:.2f} s x {tiles / frame_tiles:.3f}"}
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import raytrace_b200 as R
         from parity_util import oracle_render
         sc = R.Scene(scene, w, h, n, parts)
-        world = min(h // 64, max(1, (h // 64) * (w // 64) // tiles))
-        oracle_render(sc, level, want_ids=False, threads=cores, rank=0, world=world)
         t0 = time.time()
-        _, _, c = oracle_render(sc, level, want_ids=False, threads=cores, rank=0, world=world)
+        _, _, c = oracle_render(sc, level, want_ids=False, threads=cores, rank=3, world=16, tile_rows=8)
         dt = time.time() - t0
         rays = c.primary + c.shadow + c.reflect + c.refract
         return {"value": rays / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
-                "sample": f"row bands rank 0 of {world} ({c.primary} px, {rays} rays) of the {w}x{h} frame, 1 timed pass after 1 warm-up"}
+                "sample": f"oracle port, interleaved 8-row tiles rank 3 of 16 ({c.primary} px, {rays} rays) of the {w}x{h} frame, 1 pass"}
     except Exception as e:   # a baseline failure must not hide the GPU numbers
         return {"value": None, "unit": "Mrays/s", "cores": cores, "kind": "unavailable", "sample": repr(e)[:200]}
 
@@ -222,24 +268,23 @@ def cpu_baseline(args, cfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)   # frames; with M frames in flight a short run is dominated by pipeline fill and drain
+    ap.add_argument("--steps", type=int, default=20)    # a step is a batch of `step_frames` frames (32 for c3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the RayTracer::start() leg (profiling runs)")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: how the row tiles reach rank 0 -- one-sided NVLink peer copies on the copy engines (rt_push_rows) or an NCCL gather")
     ap.add_argument("--shard-order", default="serpentine", choices=["serpentine", "modulo"],
                     help="N>1: which rank renders row tile t -- boustrophedon (RT_FLAG_SERPENTINE, evens out the ray-cost gradient down the image) or t %% N")
-    ap.add_argument("--pipelines", type=int, default=0, help="launches in flight per GPU (0 = 3; 1 for frames that run the wave kernels)")
-    ap.add_argument("--sm-share", type=int, default=-1, help="resident traversal CTAs per SM per pipeline (-1 = 4 when several pipelines share the GPU)")
-    ap.add_argument("--batch", type=int, default=0,
-                    help="frames per launch (rt_render_batch_async: the frames of a batch share the ray queues); 0 = N, so that a launch always traces one full frame's worth of pixels per GPU")
+    ap.add_argument("--pipelines", type=int, default=0, help="launches in flight per GPU (0 = auto)")
+    ap.add_argument("--sm-share", type=int, default=-1, help="resident traversal CTAs per SM per pipeline (-1 = auto)")
+    ap.add_argument("--batch", type=int, default=0, help="frames per launch (0 = about 8 M pixels per launch and GPU)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    cfg = CONFIGS[args.config]
     if args.impl == "reference":
-        return run_reference(args, cfg)
+        return run_reference(args)
 
     import numpy as np
     import torch
@@ -257,47 +302,36 @@ def main():
     else:
         torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    scene, w, h, level, n, parts, desc = cfg
+    scene, w, h, level, n, parts, S, desc = CONFIGS[args.config]
 
     tmpdir = f"/tmp/rt_bench_{rank}"
     os.makedirs(tmpdir, exist_ok=True)
     sc = R.Scene(scene, w, h, n, parts, tmpdir=tmpdir)
+    cams = (R.Camera * S)()
+    for k in range(S):
+        cams[k] = sc.orbit_camera(k, S)
 
     def ck(rc, what):
         if rc != 0:
             raise RuntimeError(f"{what}: {R.rt.rt_last_error().decode()}")
 
-    # ---- frame pipelines: one resident scene, M frames in flight ---------------------------------
-    # defaults from the sweeps in profiles/r1g_pipelines_sweep_c3.txt: the smaller a GPU's share of the frame,
-    # the more frames have to be in flight to keep its SMs busy; frames beyond ~3 M pixels per GPU run
-    # the per-level wave kernels, which want the whole GPU each (one pipeline)
+    # ---- frame pipelines: one resident scene, M launches in flight, B frames per launch -----------------
+    # about 8 M pixels per launch and GPU (sweeps in profiles/r1i_batch_sweep_c3.txt: launches of that size run the
+    # per-level wave kernels with queues long enough that their tails do not matter, and two launches in flight
+    # cover each other's level boundaries).  Scenes of analytic primitives only (c1, c2) trace 12-17 Grays/s: their
+    # launches are bound by the ray-queue traffic, which stays closer to the L2 with one frame per launch; they keep
+    # three single frames in flight.  A frame beyond ~3 M pixels per GPU (c4) is a launch of its own.
     big = w * h // world > 3_000_000
-    # frames per launch: about 8 M pixels per launch and GPU (sweeps in profiles/r1i_batch_sweep_c3.txt: launches of
-    # that size run the per-level wave kernels with queues long enough that their tails do not matter, and two
-    # launches in flight cover each other's level boundaries)
-    # Scenes of analytic primitives only (c1, c2) trace 12-17 Grays/s: their launches are bound by the ray-queue
-    # traffic, which stays closer to the L2 with one frame per launch; they keep three single frames in flight.
     pix_rank = (w // 64 * 64) * (h // 64 * 64) // world
     mesh = args.config in ("c3", "c4")
-    B = args.batch if args.batch > 0 else (1 if big or not mesh else max(1, min(64, round(8_000_000 / max(pix_rank, 1)))))
+    B = args.batch if args.batch > 0 else (1 if big or not mesh else max(1, min(64, S, round(8_000_000 / max(pix_rank, 1)))))
     M = args.pipelines if args.pipelines > 0 else (1 if big else 2 if B > 1 else 3)
     share = args.sm_share if args.sm_share >= 0 else (0 if M == 1 or B > 1 else 4)
-    # e2e leg: RayTracer objects over the one Scene, one frame each per start().  With frame batches (B > 1) on one
-    # GPU the tracers run in throughput mode (RayTracer::coalesce): 4 x B of them feed the Scene's three batch
-    # workers, which render what is waiting -- B frames per launch, a quarter of the tracers always waiting so
-    # that the next launch is ready when one is delivered -- and hand every tracer its frame (C3: 4 191 against
-    # 3 616 Mrays/s with one pipeline per tracer).  N > 1 keeps one pipeline per tracer (4 / 4 / 8 in flight at
-    # N = 2 / 4 / 8): the one coalesced run on two GPUs (32 tracers, 8 shards per launch) came out at 666 against
-    # 6 689 Mrays/s and could not be investigated in this round.  RT_BENCH_COALESCE=0 / k forces it off / on
-    # with k x B tracers.
-    env_c = os.environ.get("RT_BENCH_COALESCE")
-    coalesce = B > 1 and (env_c != "0") and (world == 1 or bool(env_c))
-    M_e2e = 1 if big else (min(64, int(env_c or "4") * B) if coalesce else 3 if world == 1 else 4 if world < 8 else 8)
-    share_e2e = 0 if M_e2e == 1 or coalesce else 4 if world == 1 else 2 if world < 8 else 1
-    main = torch.cuda.current_stream(dev)
+    L = (S + B - 1) // B                         # launches per step
+    main_stream = torch.cuda.current_stream(dev)
     owner = C.c_void_p()
     ck(R.rt.rt_create(local, C.byref(owner)), "rt_create")
-    ck(R.rt.rt_set_stream(owner, C.c_void_p(main.cuda_stream)), "rt_set_stream")
+    ck(R.rt.rt_set_stream(owner, C.c_void_p(main_stream.cuda_stream)), "rt_set_stream")
     ck(R.rt.rt_upload_scene(owner, sc.flatten()), "rt_upload_scene")      # H2D of the scene + LBVH build, once
     tile_rows = 8 if world > 1 else 64           # fine interleave balances the ranks (sky rows are cheap)
     serp = world > 1 and args.shard_order == "serpentine"
@@ -324,33 +358,39 @@ def main():
                 frame = torch.full((h, w, 3), 127, dtype=torch.uint8, device=dev)
                 outs[f] = frame.data_ptr()
             frames.append(frame), landings.append(landing)
-        pipes.append({"ctx": hnd, "stream": st, "frames": frames, "landings": landings, "outs": outs,
+        pipes.append({"ctx": hnd, "stream": st, "frames": frames, "landings": landings, "outs": outs, "assembled": [None] * B,
                       "consumer": torch.cuda.Stream(dev) if p2p and rank == 0 else None,   # where the assembled frames become visible
                       "gather": FrameGather(w, h, rank, world, dev, tile_rows, serp) if world > 1 and not p2p else None})
 
-    def launch(j, nb):
-        """batch j: nb <= B frames in ONE launch on pipeline j % M, then every frame's rows go to rank 0"""
-        p = pipes[j % M]
-        ck(R.rt.rt_render_batch_async(p["ctx"], C.byref(params), nb, None, p["outs"]), "rt_render_batch_async")
+    def cam_ptr(first):
+        return C.cast(C.byref(cams, first * C.sizeof(R.Camera)), C.POINTER(R.Camera))
+
+    def launch(gj, j):
+        """launch j of a step (frames j*B .. of the orbit) as global launch gj, on pipeline gj % M: ONE launch, then
+        every frame's rows go to rank 0"""
+        p = pipes[gj % M]
+        first = j * B
+        nb = min(B, S - first)
+        ck(R.rt.rt_render_batch_async(p["ctx"], C.byref(params), nb, cam_ptr(first), p["outs"]), "rt_render_batch_async")
         for f in range(nb):
             if p["landings"][f] is not None:
                 p["landings"][f].push(p["ctx"], p["consumer"], frame=f)   # NVLink P2P: this rank's row tiles -> their place in rank 0's frame (copy engines) + signal
             elif p["gather"] is not None:
                 with torch.cuda.stream(p["stream"]):
-                    p["gather"].gather(p["frames"][f])   # NCCL: this rank's row tiles -> rank 0, de-interleaved there
+                    p["assembled"][f] = p["gather"].gather(p["frames"][f])   # NCCL: this rank's row tiles -> rank 0, de-interleaved there
+        return p, nb
 
-    def run(nframes):
-        """nframes frames, B per launch (the last launch may hold fewer), round-robin over the M pipelines"""
-        j, left = 0, nframes
-        while left > 0:
-            nb = min(B, left)
-            launch(j, nb)
-            j, left = j + 1, left - nb
-        return j
+    state = {"gj": 0}
+
+    def run(nsteps):
+        for _ in range(nsteps):
+            for j in range(L):
+                launch(state["gj"], j)
+                state["gj"] += 1
 
     def fork():
         ev = torch.cuda.Event()
-        ev.record(main)
+        ev.record(main_stream)
         for p in pipes:
             p["stream"].wait_event(ev)
 
@@ -360,7 +400,7 @@ def main():
                 if st is not None:
                     ev = torch.cuda.Event()
                     ev.record(st)
-                    main.wait_event(ev)
+                    main_stream.wait_event(ev)
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -368,64 +408,117 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    # ---- warm-up + one counted launch (ray totals are deterministic per configuration) ----------
+    # ---- warm-up, then one counted step (ray totals are deterministic per configuration and shard) --------
     fork()
-    run(max(args.warmup, M) * B)                 # whole batches only, every pipeline at least once
+    run(args.warmup)
     join()
     sync_all()
     cnt = R.Counters()
-    ck(R.rt.rt_read_counters(pipes[0]["ctx"], C.byref(cnt)), "rt_read_counters")
-    rays_local = (cnt.primary + cnt.shadow + cnt.reflect + cnt.refract) // B    # the frames of a batch are identical here
-    launches_per_batch = cnt.launches
-    rays_t = torch.tensor([rays_local], dtype=torch.int64, device=dev)
+    rays_step_local, launches_per_launch = 0, 0
+    for j in range(L):
+        p, nb = launch(state["gj"], j)
+        state["gj"] += 1
+        ck(R.rt.rt_read_counters(p["ctx"], C.byref(cnt)), "rt_read_counters")      # waits for that launch
+        rays_step_local += cnt.primary + cnt.shadow + cnt.reflect + cnt.refract
+        launches_per_launch = cnt.launches
+    sync_all()
+    rays_t = torch.tensor([rays_step_local], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(rays_t)
-    rays_total = int(rays_t.item())
+    rays_step = int(rays_t.item())
 
-    # ---- timed region: exactly K steps, CUDA events bracketing every pipeline stream, max over ranks
+    # ---- timed region: exactly K steps, CUDA events bracketing every pipeline stream, max over ranks ------
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(main)
+    e0.record(main_stream)
     fork()
-    n_launches = run(args.steps)
+    run(args.steps)
     join()
-    e1.record(main)
+    e1.record(main_stream)
     sync_all()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     # per-rank view (load balance of the image-space shards)
-    mine_t = torch.tensor([e0.elapsed_time(e1) / args.steps, float(rays_local)], dtype=torch.float64, device=dev)
+    mine_t = torch.tensor([e0.elapsed_time(e1) / args.steps, float(rays_step_local)], dtype=torch.float64, device=dev)
     per_rank = [torch.zeros_like(mine_t) for _ in range(world)]
     if world > 1:
         dist.all_gather(per_rank, mine_t)
     else:
         per_rank = [mine_t]
-    per_rank = [{"rank": r, "ms_per_step": float(t[0].item()), "rays_per_frame": int(t[1].item())} for r, t in enumerate(per_rank)]
+    per_rank = [{"rank": r, "ms_per_step": float(t[0].item()), "rays_per_step": int(t[1].item())} for r, t in enumerate(per_rank)]
+    slow = max(per_rank, key=lambda r: r["ms_per_step"])
     clocks = sampler.stop() if rank == 0 else None
-    value = rays_total * args.steps / (ms_total * 1e-3) / 1e6
+    value = rays_step * args.steps / (ms_total * 1e-3) / 1e6
+
+    # ---- frame check: launch 0 of a step once more through the same call sequence; frame 0 (camera 0, assembled on
+    #      rank 0) against the unmodified reference's full-frame hash, every frame of the launch against the same
+    #      camera rendered alone ------------------------------------------------------------------------------
+    fork()
+    pchk, nb0 = launch(0, 0)                      # pipeline 0
+    join()
+    sync_all()
+    ck(R.rt.rt_wait(pchk["ctx"], None), "rt_wait")
+    gold = golden_fullsize(args.config)
+    frame_check = {"frame": "camera 0 of the orbit = the configuration's own camera; rendered after the timed region by the same call sequence as every timed launch"}
+    batch_frames = []
+    for f in range(nb0):
+        host = np.empty((h, w, 3), dtype=np.uint8)
+        if world > 1 and rank == 0 and not p2p:
+            host = pchk["assembled"][f].cpu().numpy()
+        else:
+            ck(R.rt.rt_read_batch_output(pchk["ctx"], f, host.ctypes.data_as(C.c_void_p), w * 3, 0), "rt_read_batch_output")
+        batch_frames.append(host)
+    if rank == 0:
+        frame_check["hash"] = R.fnv1a64(batch_frames[0])
+        frame_check["expected"] = gold["hash"] if gold else None
+        frame_check["expected_source"] = "tests/golden/fullsize.json: the unmodified reference's full frame (tests/golden/make_fullsize.py)" if gold else "no golden hash for this configuration"
+        frame_check["ok"] = bool(gold and frame_check["hash"] == gold["hash"])
+    # the same cameras rendered alone (one frame per launch: other scheduler for mesh frames <= 3 M pixels), this rank's rows
+    p0 = pipes[0]["ctx"]
+    ck(R.rt.rt_set_sm_share(p0, 0), "rt_set_sm_share")
+    from raytrace_b200.distributed import bands_of
+    rows = np.array([y for y in range(h // 64 * 64) if (y // tile_rows) in set(bands_of(rank, world, h, tile_rows, serp))]) if world > 1 else np.arange(h)
+    same_alone = True
+    c1 = R.Counters()
+    for f in range(nb0):
+        ck(R.rt.rt_render_batch_async(p0, C.byref(params), 1, cam_ptr(f), None), "rt_render_batch_async(1)")
+        alone = np.empty((h, w, 3), dtype=np.uint8)
+        ck(R.rt.rt_read_batch_output(p0, 0, alone.ctypes.data_as(C.c_void_p), w * 3, 0), "rt_read_batch_output")
+        same_alone = same_alone and bool(np.array_equal(alone[rows], batch_frames[f][rows]))
+    ck(R.rt.rt_read_counters(p0, C.byref(c1)), "rt_read_counters")
+    alone_sched = "k_frame" if c1.frame_sched else "k_wave"
+    ok_t = torch.tensor([1 if same_alone else 0], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        frame_check["batch_frames_equal_frames_rendered_alone"] = bool(ok_t.item())
+        frame_check["alone_scheduler"] = alone_sched
+        frame_check["status"] = "ok" if frame_check["ok"] and frame_check["batch_frames_equal_frames_rendered_alone"] else "MISMATCH"
 
     # ---- one launch alone (per-stage split from the library's own CUDA events), one counted launch for the
     #      roofline, and one single frame alone (latency); all untimed ----------------------------------
-    p0 = pipes[0]["ctx"]
-    ck(R.rt.rt_set_sm_share(p0, 0), "rt_set_sm_share")
     for _ in range(2):
-        ck(R.rt.rt_render_batch_async(p0, C.byref(params), B, None, pipes[0]["outs"]), "rt_render_batch_async")
+        ck(R.rt.rt_render_batch_async(p0, C.byref(params), min(B, S), cam_ptr(0), pipes[0]["outs"]), "rt_render_batch_async")
         ck(R.rt.rt_read_counters(p0, C.byref(cnt)), "rt_read_counters")
     stage = {"traverse": cnt.trace_ms, "shade": cnt.shade_ms, "other": cnt.other_ms, "render": cnt.render_ms}
+    rays_launch0 = cnt.primary + cnt.shadow + cnt.reflect + cnt.refract
+    wave_sched = not cnt.frame_sched
     pstats = R.RenderParams(R.MY_MODEL_RAYTRACE, level, rank, world, R.RT_FLAG_STATS | shard_flags, tile_rows)
-    ck(R.rt.rt_render_batch_async(p0, C.byref(pstats), B, None, pipes[0]["outs"]), "rt_render_batch_async(stats)")
+    ck(R.rt.rt_render_batch_async(p0, C.byref(pstats), min(B, S), cam_ptr(0), pipes[0]["outs"]), "rt_render_batch_async(stats)")
     cs = R.Counters()
     ck(R.rt.rt_read_counters(p0, C.byref(cs)), "rt_read_counters")
-    c1 = R.Counters()
-    for _ in range(2):
-        ck(R.rt.rt_render_async(p0, C.byref(params)), "rt_render_async")
+    for _ in range(3):
+        ck(R.rt.rt_render_batch_async(p0, C.byref(params), 1, cam_ptr(0), None), "rt_render_batch_async(1)")
         ck(R.rt.rt_read_counters(p0, C.byref(c1)), "rt_read_counters")
-    ms_frame_alone = c1.render_ms
+    alone_t = torch.tensor([c1.render_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(alone_t, op=dist.ReduceOp.MAX)
+    ms_frame_alone = float(alone_t.item())
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()                           # nobody unmaps a landing buffer another rank may still push to
@@ -437,68 +530,90 @@ def main():
     R.rt.rt_destroy(owner)
 
     # ---- e2e: RayTracer::start() with host buffers (flatten + H2D tables + render + D2H frame) ----
-    tracers = []
-    for _ in range(M_e2e):
-        t = R.RayTracer(sc, device=local)        # the drop-in surface; tracers of one Scene share its residency
-        t.maxLevel = level
-        t.smShare = share_e2e if M_e2e > 1 else 0
-        t.coalesce = coalesce
-        tracers.append(t)
-    for k in range(2 * M_e2e):
-        tracers[k % M_e2e].wait()
-        tracers[k % M_e2e].start(R.MY_MODEL_RAYTRACE, flags=shard_flags, rank=rank, world=world, tile_rows=tile_rows)
-    for t in tracers:
-        t.wait()
-    sync_all()
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        t = tracers[k % M_e2e]
-        t.wait()                                 # frame k-M is in RayTracer::output
-        t.start(R.MY_MODEL_RAYTRACE, flags=shard_flags, rank=rank, world=world, tile_rows=tile_rows)
-    for t in tracers:
-        t.wait()
-    torch.cuda.synchronize(dev)
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = rays_total * args.steps / float(e2e_s.item()) / 1e6
-    ce = tracers[0].counters()                   # bytes the library itself copied for the last start()
-    h2d, d2h = int(ce.h2d_bytes), int(ce.d2h_bytes)
+    # Tracers of the one Scene (the reference's idiom for several views).  With frame batches on one GPU they run in
+    # throughput mode (RayTracer::coalesce): the Scene's batch workers render whatever start() calls are waiting in ONE
+    # launch, each frame through the camera its start() saw.  Every start() of step s, frame f is preceded by putting
+    # orbit camera f into the Scene (Scene::cam.position, as the reference's UI moves its camera between frames).
+    e2e = None
+    if not args.no_e2e:
+        env_c = os.environ.get("RT_BENCH_COALESCE")
+        coalesce = B > 1 and (env_c != "0")
+        M_e2e = 1 if big else (min(64, int(env_c or "4") * B) if coalesce else 3 if world == 1 else 4 if world < 8 else 8)
+        share_e2e = 0 if M_e2e == 1 or coalesce else 4 if world == 1 else 2 if world < 8 else 1
+        tracers = []
+        for _ in range(M_e2e):
+            t = R.RayTracer(sc, device=local)        # the drop-in surface; tracers of one Scene share its residency
+            t.maxLevel = level
+            t.smShare = share_e2e if M_e2e > 1 else 0
+            t.coalesce = coalesce
+            tracers.append(t)
+
+        def e2e_frames(nframes, k0=0):
+            for k in range(k0, k0 + nframes):
+                t = tracers[k % M_e2e]
+                t.wait()                             # that tracer's previous frame is in RayTracer::output
+                cpos = cams[k % S].position
+                sc.set_camera_position(cpos.x, cpos.y, cpos.z)
+                t.start(R.MY_MODEL_RAYTRACE, flags=shard_flags, rank=rank, world=world, tile_rows=tile_rows)
+            for t in tracers:
+                t.wait()
+
+        e2e_frames(max(2 * M_e2e, S))
+        sync_all()
+        up0, dn0, up1, dn1 = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        R.rt.rt_transfer_totals(C.byref(up0), C.byref(dn0))      # bytes the library itself copies, counted where it enqueues them
+        t0 = time.perf_counter()
+        e2e_frames(args.steps * S)
+        torch.cuda.synchronize(dev)
+        e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        R.rt.rt_transfer_totals(C.byref(up1), C.byref(dn1))
+        if world > 1:
+            dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+        e2e = {"value": rays_step * args.steps / float(e2e_s.item()) / 1e6, "unit": "Mrays/s", "ms_per_step": float(e2e_s.item()) / args.steps * 1e3,
+               "h2d_bytes_per_step": (up1.value - up0.value) // args.steps, "d2h_bytes_per_step": (dn1.value - dn0.value) // args.steps,
+               "bytes_counted_on": "rank 0" if world > 1 else "the one GPU",
+               "calls_per_step": S, "tracers_in_flight": M_e2e, "coalesced_starts": coalesce}
+        del tracers
 
     if rank == 0:
         peak, peak_src, hbm_peak = sm_peak_fp32_tflops()
         # flop model: 22 per child box (4 per 4-wide node), 47 per triangle test, 23 per analytic primitive
         flops = cs.nodes_visited * 4 * 22 + cs.tri_tests * 47 + cs.prim_tests * 23
         trav_ms = stage["traverse"]
-        trav_launches = 1 if cnt.frame_sched else level + 2   # whole-frame scheduler: one traversal launch per frame
+        trav_launches = level + 2 if wave_sched else 1   # whole-frame scheduler: one traversal launch per frame
         achieved = flops / (trav_ms * 1e-3) / 1e12 if trav_ms > 0 else 0.0
-        queue_bytes = rays_local * B * 100   # ~100 B of ray/hit/node records written+read per ray, B frames per launch
+        queue_bytes = rays_launch0 * 100   # ~100 B of ray/hit/node records written+read per ray
+        traffic, traffic_src = ncu_traffic(args.config, world, min(B, S))
+        cfg = workload_config(args.config)
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.config}: {desc}", "rays_per_frame": rays_total, "pixels": w * (h // 64 * 64) if w % 64 == 0 else (w // 64 * 64) * (h // 64 * 64),
-                       "l2_policy": "per-frame working set (ray/hit/node queues + BVH + triangles, > 500 MB touched per frame) exceeds the 126 MB L2; no flush needed",
-                       "parallelism": (f"image-space: interleaved {tile_rows}-row tiles over {world} GPUs ({'boustrophedon' if serp else 'modulo'} order), " + ("row tiles pushed into rank 0's frame over NVLink P2P (copy engines, put with signal; NCCL only ships the IPC handles)" if p2p else "NCCL gather of RGB8 tiles to rank 0")) if world > 1 else "single GPU",
-                       "frames_per_launch": B, "launches_in_flight": M, "frames_in_flight": B * M, "traversal_ctas_per_sm_per_pipeline": (share if M > 1 and share else 8),
-                       "e2e_frames_in_flight": M_e2e, "e2e_coalesced_starts": coalesce,
-                       "ms_per_launch_alone": stage["render"], "ms_per_frame_alone": ms_frame_alone},
-            "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": float(e2e_s.item()) / args.steps * 1e3,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches_per_batch * n_launches,
-            "roofline": {"bound": "fp32_issue", "kernel": "k_frame (one persistent launch per frame: closest-hit + shadow traversal of all levels)" if trav_launches == 1 else "k_wave (closest-hit level l fused with shadow any-hit level l-1; the level+2 launches of one batch of frames)", "achieved": achieved, "peak": peak,
+            "config": cfg,
+            "ms_per_frame": ms_total / args.steps / S,
+            "run": {"rays_per_step": rays_step, "rays_per_frame_mean": rays_step / S,
+                    "parallelism": (f"image-space: interleaved {tile_rows}-row tiles over {world} GPUs ({'boustrophedon' if serp else 'modulo'} order), " + ("row tiles pushed into rank 0's frame over NVLink P2P (copy engines, put with signal; NCCL only ships the IPC handles)" if p2p else "NCCL gather of RGB8 tiles to rank 0")) if world > 1 else "single GPU",
+                    "frames_per_launch": B, "launches_per_step": L, "launches_in_flight": M, "traversal_ctas_per_sm_per_pipeline": (share if M > 1 and share else 8),
+                    "slowest_rank": slow["rank"], "slowest_rank_ms_per_step": slow["ms_per_step"]},
+            "latency": {"ms_per_frame_alone": ms_frame_alone, "scheduler": alone_sched, "ms_per_launch_alone": stage["render"], "frames_per_launch": min(B, S),
+                        "note": "one frame (camera 0) with nothing else in flight, max over ranks; the stream figure above overlaps launches"},
+            "frame_check": frame_check,
+            "gpu_launches": launches_per_launch * L * args.steps,
+            "roofline": {"bound": "fp32_issue", "kernel": "k_wave (closest-hit level l fused with shadow any-hit level l-1; the level+2 launches of one batch of frames)" if wave_sched else "k_frame (one persistent launch: closest-hit + shadow traversal of all levels)", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": f"148 SMs x 128 lanes x {peak_src} (of measured)",
-                         "traffic": NCU_TRAFFIC.get((args.config, world, B), (None, None))[0], "traffic_source": NCU_TRAFFIC.get((args.config, world, B), (None, None))[1],
-                         "kernel_launches_per_batch": trav_launches, "frames_per_batch": B, "avg_launch_ms": trav_ms / trav_launches,
-                         "flops_per_step": flops / B, "flops_per_launch": flops, "nodes_per_ray": cs.nodes_visited / max(rays_local * B, 1), "tri_tests_per_ray": cs.tri_tests / max(rays_local * B, 1),
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel_launches_per_batch": trav_launches, "frames_per_batch": min(B, S), "avg_launch_ms": trav_ms / trav_launches,
+                         "flops_per_launch": flops, "nodes_per_ray": cs.nodes_visited / max(rays_launch0, 1), "tri_tests_per_ray": cs.tri_tests / max(rays_launch0, 1),
                          "stage_ms_one_launch_alone": stage,
-                         "hbm_secondary": {"queue_bytes_per_step": queue_bytes, "achieved_gbs": queue_bytes / (stage["render"] * 1e-3) / 1e9,
+                         "hbm_secondary": {"queue_bytes_per_launch": queue_bytes, "achieved_gbs": queue_bytes / (stage["render"] * 1e-3) / 1e9,
                                            "peak_gbs": hbm_peak}},
             "clocks": clocks, "per_rank": per_rank,
             "build": {"upload_ms": cs.upload_ms, "lbvh_build_ms": cs.build_ms, "bvh_nodes": cs.bvh_nodes, "bvh_depth": cs.bvh_depth},
         }
+        if e2e is not None:
+            line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args, cfg)
+            line["cpu_baseline"] = cpu_baseline(args, frame_check.get("hash"))
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -308,6 +308,10 @@ int rt_intersect_object(rt_ctx *ctx, uint32_t object, const rt_ray *rays, const 
 /* diagnostics / parity taps */
 int rt_read_hit_ids(rt_ctx *ctx, rt_hit_id *ids /* width*height */);
 int rt_read_counters(rt_ctx *ctx, rt_counters *out);
+/* bytes this library has copied host->device / device->host in this process so far (every context: scene uploads,
+ * per-launch tables and counters, frame read-backs).  A caller that brackets a region with two calls gets the bytes
+ * that crossed the bus inside it (bench.py's e2e leg). */
+int rt_transfer_totals(uint64_t *h2d_bytes, uint64_t *d2h_bytes);
 
 #ifdef __cplusplus
 }

@@ -35,5 +35,6 @@ $CXX $FLAGS -c "$REF/Scene.cpp" -o "$TMP/Scene.o" &
 $CXX $FLAGS -c "$REF/RayTracer.cpp" -o "$TMP/RayTracer.o" &
 $CXX $FLAGS -fno-access-control -DRT_ARM_REFERENCE -I "$HERE" -c "$HERE/../tools/render_main.cpp" -o "$TMP/render_main.o" &
 wait
-$CXX -o "$OUT/ref_render" "$TMP"/*.o -lpthread
+$CXX -o "$OUT/ref_render.new" "$TMP"/*.o -lpthread
+mv -f "$OUT/ref_render.new" "$OUT/ref_render"   # atomic: a running ref_render keeps its old image
 echo "built $OUT/ref_render"

@@ -12,6 +12,7 @@
 #pragma once
 #include <atomic>
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <thread>
 #include <vector>
@@ -139,8 +140,18 @@ inline void primary_ids(Scene &scene, RayTracer &rt, int width, int height, HitI
 	for (auto &t : pool) t.join();
 }
 
-// `tiles` seeded 64x64 tiles, traced pixel by pixel through RTfrac/RTflec on `threads` threads.
-inline long render_tiles(Scene &scene, RayTracer &rt, int width, int height, int tiles, int seed, int threads, int type, Counts *counts)
+// Bounded CPU sample: `tiles` 64x64 tiles traced pixel by pixel through RTfrac/RTflec on `threads` threads.
+//   seed >= 0: seeded random tiles;  seed < 0: STRATIFIED -- tile k of the sample is tile floor((k + 0.5) * nblk / tiles)
+//   of the frame in row-major tile order, so every sample covers all tile rows evenly (sky rows are cheap, mesh
+//   rows expensive: a handful of random tiles is not ray-count representative).
+// Work is handed out per 64-pixel ROW of a tile (one atomic per row), so min(threads, 64 * tiles) threads work --
+// the reference's own parallelRT hands out whole tiles (RayTracer.cpp:28-33), which is fine for a full frame of
+// hundreds of tiles but leaves most threads idle on a small sample.
+// RTPrepare (single-threaded in the reference, once per start(), RayTracer.cpp:622-627) runs first and is timed
+// separately: *prepare_s.  A caller that extrapolates to a frame charges it ONCE per frame, i.e.
+// frame_s ~= prepare_s + trace_s * (frame tiles / sample tiles).
+inline long render_tiles(Scene &scene, RayTracer &rt, int width, int height, int tiles, int seed, int threads, int type, Counts *counts,
+	double *prepare_s = nullptr, double *trace_s = nullptr)
 {
 	CountingProxy *proxy = nullptr;
 	if (counts)
@@ -149,19 +160,26 @@ inline long render_tiles(Scene &scene, RayTracer &rt, int width, int height, int
 		scene.Objects.insert(scene.Objects.begin(), proxy);
 	}
 	rt.width = width, rt.height = height;
+	const auto t0 = std::chrono::steady_clock::now();
 	for (auto dobj : scene.Objects)
 		if (dobj->bShow) dobj->RTPrepare();
+	const auto t1 = std::chrono::steady_clock::now();
 	const Camera &cam = scene.cam;
 	const int blk_h = height / 64, blk_w = width / 64, nblk = blk_h * blk_w;
+	if (tiles > nblk) tiles = nblk;
 	std::vector<int> order(nblk);
 	for (int i = 0; i < nblk; ++i) order[i] = i;
-	unsigned long long s = 0x9E3779B97F4A7C15ULL ^ (unsigned long long)seed;
-	for (int i = nblk - 1; i > 0; --i)
+	if (seed >= 0)
 	{
-		s = s * 6364136223846793005ULL + 1442695040888963407ULL;
-		std::swap(order[i], order[(int)((s >> 33) % (unsigned)(i + 1))]);
+		unsigned long long s = 0x9E3779B97F4A7C15ULL ^ (unsigned long long)seed;
+		for (int i = nblk - 1; i > 0; --i)
+		{
+			s = s * 6364136223846793005ULL + 1442695040888963407ULL;
+			std::swap(order[i], order[(int)((s >> 33) % (unsigned)(i + 1))]);
+		}
 	}
-	if (tiles > nblk) tiles = nblk;
+	else
+		for (int k = 0; k < tiles; ++k) order[k] = (int)(((long long)(2 * k + 1) * nblk) / (2 * tiles));
 	const double dp = tan(cam.fovy * PI / 360) / (height / 2);
 	const float zNear = cam.zNear, zFar = sqrt(2)*cam.zFar;
 	std::atomic<int> next(0);
@@ -170,22 +188,25 @@ inline long render_tiles(Scene &scene, RayTracer &rt, int width, int height, int
 		pool.emplace_back([&]
 		{
 			HitRes base;
-			for (int k = next.fetch_add(1); k < tiles; k = next.fetch_add(1))
+			for (int k = next.fetch_add(1); k < tiles * 64; k = next.fetch_add(1))
 			{
-				const int bx = order[k] % blk_w, by = order[k] / blk_w;
-				for (int y = by * 64; y < by * 64 + 64; ++y)
-					for (int x = bx * 64; x < bx * 64 + 64; ++x)
-					{
-						const int xcur = x - width / 2, ycur = y - height / 2;
-						Vertex dir = cam.n + cam.u*(xcur*dp) + cam.v*(ycur*dp);
-						Ray baseray(cam.position, dir, MY_RAY_BASERAY);
-						Color c = (type == MY_MODEL_REFLECTTEST) ? rt.RTflec(zNear, zFar, baseray, 0, 1.0f, base)
-							: rt.RTfrac(zNear, zFar, baseray, 0, 1.0f, base);
-						c.put(rt.output + ((size_t)y * width + x) * 3);
-					}
+				const int tile = order[k >> 6], bx = tile % blk_w, by = tile / blk_w;
+				const int y = by * 64 + (k & 63);
+				for (int x = bx * 64; x < bx * 64 + 64; ++x)
+				{
+					const int xcur = x - width / 2, ycur = y - height / 2;
+					Vertex dir = cam.n + cam.u*(xcur*dp) + cam.v*(ycur*dp);
+					Ray baseray(cam.position, dir, MY_RAY_BASERAY);
+					Color c = (type == MY_MODEL_REFLECTTEST) ? rt.RTflec(zNear, zFar, baseray, 0, 1.0f, base)
+						: rt.RTfrac(zNear, zFar, baseray, 0, 1.0f, base);
+					c.put(rt.output + ((size_t)y * width + x) * 3);
+				}
 			}
 		});
 	for (auto &t : pool) t.join();
+	const auto t2 = std::chrono::steady_clock::now();
+	if (prepare_s) *prepare_s = std::chrono::duration<double>(t1 - t0).count();
+	if (trace_s) *trace_s = std::chrono::duration<double>(t2 - t1).count();
 	if (proxy)
 	{
 		scene.Objects.erase(scene.Objects.begin());

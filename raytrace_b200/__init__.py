@@ -88,6 +88,21 @@ class Scene:
         v = (C.c_float * 4)(*xyzw)
         rth.rth_scene_camera_set_n(self._h, v)
 
+    def orbit_camera(self, k, K) -> Camera:
+        """camera k of the K-camera orbit around the scene's current camera (scenes.h orbit_camera); camera 0 is the
+        scene's own camera.  The Scene is not changed."""
+        c = Camera()
+        rth.rth_scene_orbit_camera(self._h, k, K, C.byref(c))
+        return c
+
+    def camera(self) -> Camera:
+        c = Camera()
+        rth.rth_scene_camera_get(self._h, C.byref(c))
+        return c
+
+    def set_camera_position(self, x, y, z):
+        return rth.rth_scene_camera_set_position(self._h, x, y, z)
+
     def camera_move(self, x, y, z):
         return rth.rth_scene_camera_move(self._h, x, y, z)
 
@@ -131,9 +146,20 @@ class RayTracer:
     def wait(self):
         rth.rth_tracer_wait(self._h)
 
+    @property
+    def failed(self):
+        """the last frame ended with an error (isFinish is true, output keeps the previous frame); see lastError"""
+        return bool(rth.rth_tracer_failed(self._h))
+
+    @property
+    def lastError(self):
+        return rth.rth_tracer_last_error(self._h).decode(errors="replace")
+
     def output(self) -> np.ndarray:
         """RayTracer::output as an (H, W, 3) uint8 array, row 0 = bottom."""
         self.wait()
+        if self.failed:
+            raise RtError(f"frame failed: {self.lastError}")
         w, h = rth.rth_tracer_width(self._h), rth.rth_tracer_height(self._h)
         ptr = rth.rth_tracer_output(self._h)
         return np.ctypeslib.as_array(ptr, shape=(h, w, 3)).copy()

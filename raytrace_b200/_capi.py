@@ -131,6 +131,7 @@ RT_SYMBOLS = {
     "rt_intersect_object": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(Ray), C.POINTER(Hit), C.c_float, C.POINTER(Hit), C.c_uint32]),
     "rt_read_hit_ids": (C.c_int, [C.c_void_p, C.POINTER(HitId)]),
     "rt_read_counters": (C.c_int, [C.c_void_p, C.POINTER(Counters)]),
+    "rt_transfer_totals": (C.c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
 }
 
 RTH_SYMBOLS = {
@@ -151,6 +152,9 @@ RTH_SYMBOLS = {
     "rth_scene_camera_yaw": (C.c_int, [C.c_void_p, C.c_float]),
     "rth_scene_camera_pitch": (C.c_int, [C.c_void_p, C.c_float]),
     "rth_scene_camera_jitter": (C.c_int, [C.c_void_p, C.c_float, C.c_float]),
+    "rth_scene_orbit_camera": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(Camera)]),
+    "rth_scene_camera_get": (C.c_int, [C.c_void_p, C.POINTER(Camera)]),
+    "rth_scene_camera_set_position": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float]),
     "rth_scene_camera_get_n": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "rth_scene_camera_set_n": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "rth_scene_flatten": (C.POINTER(SceneDesc), [C.c_void_p]),
@@ -158,6 +162,8 @@ RTH_SYMBOLS = {
     "rth_tracer_free": (None, [C.c_void_p]),
     "rth_tracer_start": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "rth_tracer_stop": (None, [C.c_void_p]),
+    "rth_tracer_failed": (C.c_int, [C.c_void_p]),
+    "rth_tracer_last_error": (C.c_char_p, [C.c_void_p]),
     "rth_tracer_is_finished": (C.c_int, [C.c_void_p]),
     "rth_tracer_wait": (None, [C.c_void_p]),
     "rth_tracer_use_time": (C.c_double, [C.c_void_p]),

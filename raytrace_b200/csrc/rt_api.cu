@@ -3,6 +3,7 @@
 // operation runs in the kernels of rt_kernels.cu.  There is deliberately no CPU path here.
 #include "rt_kernels.h"
 #include <atomic>
+#include <mutex>
 #include <thread>
 #include <cmath>
 #include <cstdarg>
@@ -13,6 +14,18 @@
 #include <vector>
 
 static thread_local std::string g_err;
+static std::atomic<uint64_t> g_h2dTotal{0}, g_d2hTotal{0};   // rt_transfer_totals
+// landing buffers this process owns: rt_landing_create leaves them filled with 127, and their rows belong to the
+// peers as much as to the owner -- a pipeline that renders straight into one must NOT grey it again (that fill
+// would not be ordered against the peers' one-sided row copies and could wipe rows that already landed)
+static std::mutex g_landingMutex;
+static std::vector<const uint8_t *> g_landingBases;
+static bool is_landing_base(const uint8_t *p)
+{
+	std::lock_guard<std::mutex> lock(g_landingMutex);
+	for (const uint8_t *b : g_landingBases) if (b == p) return true;
+	return false;
+}
 
 static int fail(int code, const char *fmt, ...)
 {
@@ -44,6 +57,7 @@ template<class T> struct DevBuf
 	cudaError_t upload(const T *src, size_t n, cudaStream_t st, uint64_t *bytes = nullptr)
 	{
 		if (bytes) *bytes += n * sizeof(T);
+		g_h2dTotal += n * sizeof(T);
 		cudaError_t e = reserve(n);
 		if (e != cudaSuccess || n == 0) return e;
 		return cudaMemcpyAsync(p, src, n * sizeof(T), cudaMemcpyHostToDevice, st);
@@ -67,7 +81,8 @@ struct rt_ctx
 	int device = 0, sms = 148;
 	cudaStream_t stream = nullptr, stopStream = nullptr;
 	bool ownStream = false;
-	uint32_t *hStopWord = nullptr;   // pinned constant 3 written into WaveState::overflow by rt_stop
+	uint32_t *hStopWord = nullptr;   // pinned ring of epochs: rt_stop copies the running frame's epoch into WaveState::stop_epoch
+	uint32_t stopSlot = 0;
 	cudaEvent_t evStart = nullptr, evStop = nullptr, evA = nullptr, evB = nullptr, evRead = nullptr;
 	cudaEvent_t evStage[4 * (RT_MAX_LEVELS + 1) + 2];   // per level: before trace, after trace, after shadow, after shade; then combine begin/end
 	bool stageTiming = true;
@@ -116,8 +131,13 @@ struct rt_ctx
 	double uploadMs = 0, buildMs = 0, renderMs = 0;
 	uint64_t uploadBytes = 0, frameH2D = 0, frameD2H = 0;
 	float levelFactor = 2.0f;
+	uint32_t minCap[RT_MAX_LEVELS + 2] = {};   // per-level queue capacities learnt from overflowing frames (finish_frame regrows and re-renders)
+	uint32_t regrowTries = 0;
+	std::vector<rt_camera> lastCams;           // the last launch's arguments, kept for that re-render
+	bool lastCamsGiven = false, lastOutsGiven = false;
 	int schedMode = 0;              // 0 auto, 1 k_frame (one persistent launch per frame), 2 per-level waves (RT_B200_SCHED=auto|frame|waves)
 	bool frameSched = false;        // what the last frame used
+	int waveGen = 1;                // k_wave(0) makes the primary rays itself (RT_B200_WAVE_GENPRIMARY=0: k_raygen writes them first)
 	uint32_t frameEpoch = 0;
 	// several frames in flight on one GPU: a pipeline created by rt_create_shared renders its parent's
 	// resident scene (device tables and BVH are NOT copied), on its own stream with its own ray queues
@@ -134,6 +154,10 @@ struct rt_ctx
 	uint32_t keepSalt = 0;      // rotates which CTAs of k_frame are pinned, per pipeline (RT_B200_KEEP_DIV)
 	unsigned ctasPerSm = 0;         // resident traversal CTAs per SM this pipeline may use (0 = all 8), rt_set_sm_share
 };
+
+#ifndef RT_WAVE_GENPRIMARY_DEFAULT
+#define RT_WAVE_GENPRIMARY_DEFAULT 1   // k_wave(0) makes the primary rays itself (RT_B200_WAVE_GENPRIMARY=0: k_raygen writes them first); C3 +1.5 %, C2 +1.9 %
+#endif
 
 extern "C" const char *rt_last_error(void) { return g_err.c_str(); }
 extern "C" int rt_abi_version(void) { return RT_ABI_VERSION; }
@@ -157,8 +181,7 @@ extern "C" int rt_create(int device, rt_ctx **out)
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	c->ownStream = true;
 	CU(cudaStreamCreateWithFlags(&c->stopStream, cudaStreamNonBlocking));
-	CU(cudaMallocHost(&c->hStopWord, sizeof(uint32_t)));
-	*c->hStopWord = 3u;
+	CU(cudaMallocHost(&c->hStopWord, 64 * sizeof(uint32_t)));
 	CU(cudaEventCreate(&c->evStart)); CU(cudaEventCreate(&c->evStop)); CU(cudaEventCreate(&c->evA)); CU(cudaEventCreate(&c->evB)); CU(cudaEventCreateWithFlags(&c->evRead, cudaEventDisableTiming));
 	for (auto &e : c->evStage) CU(cudaEventCreate(&e));
 	if (const char *v = getenv("RT_B200_STAGE_TIMING")) c->stageTiming = atoi(v) != 0;
@@ -171,6 +194,8 @@ extern "C" int rt_create(int device, rt_ctx **out)
 	if (const char *v = getenv("RT_B200_LEAF_SIZE")) c->leafSize = (uint32_t)atoi(v);
 	if (const char *v = getenv("RT_B200_LEVEL_FACTOR")) c->levelFactor = (float)atof(v);
 	if (const char *v = getenv("RT_B200_SCHED")) c->schedMode = !strcmp(v, "frame") ? 1 : (!strcmp(v, "waves") ? 2 : 0);
+	c->waveGen = RT_WAVE_GENPRIMARY_DEFAULT;
+	if (const char *v = getenv("RT_B200_WAVE_GENPRIMARY")) c->waveGen = atoi(v);
 	{ static std::atomic<uint32_t> created{0}; c->keepSalt = created.fetch_add(1u); }
 	*out = c;
 	return RT_OK;
@@ -250,6 +275,8 @@ template<class T> static bool same(const std::vector<T> &a, const T *b, size_t n
 	return a.size() == n && (n == 0 || memcmp(a.data(), b, n * sizeof(T)) == 0);
 }
 
+static int upload_scene_tables(rt_ctx *c, const rt_scene_desc *s, bool hadScene);
+
 extern "C" int rt_upload_scene(rt_ctx *c, const rt_scene_desc *s)
 {
 	if (c && c->sceneFrom) return rt_upload_scene(c->sceneFrom, s);   // a shared pipeline has no scene of its own
@@ -284,6 +311,28 @@ extern "C" int rt_upload_scene(rt_ctx *c, const rt_scene_desc *s)
 	}
 	if (triCheck != s->n_tris) return fail(RT_E_INVALID, "rt_upload_scene: parts cover %u triangles, n_tris = %u", triCheck, s->n_tris);
 
+	// From here on device tables are touched: a failure leaves them half-written (buffers may have been freed by a
+	// reserve), so after one the context has NO scene until a later upload succeeds; shared pipelines see the new
+	// version, re-adopt and refuse to render.
+	const bool hadScene = c->hasScene;
+	const int rc = upload_scene_tables(c, s, hadScene);
+	if (rc != RT_OK)
+	{
+		c->hasScene = false;
+		++c->sceneVersion;
+		memset(&c->S, 0, sizeof c->S);
+		c->geometryEpoch = 0, c->nTris = 0;   // force a full re-upload next time
+		c->matCache.clear(), c->texCache.clear(), c->texelCache.clear(), c->prims.clear(), c->models.clear(), c->parts.clear();
+		return rc;
+	}
+	c->hasScene = true;
+	c->frameValid = false;
+	++c->sceneVersion;
+	return RT_OK;
+}
+
+static int upload_scene_tables(rt_ctx *c, const rt_scene_desc *s, bool hadScene)
+{
 	cudaStream_t st = c->stream;
 	CU(cudaEventRecord(c->evA, st));
 	c->uploadBytes = 0;
@@ -319,9 +368,9 @@ extern "C" int rt_upload_scene(rt_ctx *c, const rt_scene_desc *s)
 	}
 
 	// ---- what changed? ------------------------------------------------------------------------
-	const bool trisChanged = !c->hasScene || s->geometry_epoch == 0 || s->geometry_epoch != c->geometryEpoch || s->n_tris != c->nTris;
+	const bool trisChanged = !hadScene || s->geometry_epoch == 0 || s->geometry_epoch != c->geometryEpoch || s->n_tris != c->nTris;
 	const bool modelsChanged = trisChanged || !same(c->models, s->models, s->n_models) || !same(c->parts, s->parts, s->n_parts);
-	const bool primsChanged = !c->hasScene || !same(c->prims, s->prims, s->n_prims);
+	const bool primsChanged = !hadScene || !same(c->prims, s->prims, s->n_prims);
 	if (trisChanged && s->n_tris && (!s->tri_points || !s->tri_norms || !s->tri_tcoords))
 		return fail(RT_E_INVALID, "rt_upload_scene: geometry changed but triangle arrays are NULL");
 	c->prims.assign(s->prims, s->prims + s->n_prims);
@@ -501,9 +550,6 @@ extern "C" int rt_upload_scene(rt_ctx *c, const rt_scene_desc *s)
 		cudaEventElapsedTime(&ms, c->evA, c->evStop);
 		c->uploadMs = ms;
 	}
-	c->hasScene = true;
-	c->frameValid = false;
-	++c->sceneVersion;
 	return RT_OK;
 }
 
@@ -532,9 +578,6 @@ static LevelBuf level_buf(const LevelStore &L)
 static int finish_frame(rt_ctx *c);
 
 static int render_frames(rt_ctx *c, const rt_render_params *p, uint32_t nFrames, const rt_camera *cams, void *const *outs);
-#ifndef RT_WAVE_GENPRIMARY_DEFAULT
-#define RT_WAVE_GENPRIMARY_DEFAULT 1   // k_wave(0) makes the primary rays itself (RT_B200_WAVE_GENPRIMARY=0: k_raygen writes them first); C3 +1.5 %, C2 +1.9 %
-#endif
 
 extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 {
@@ -636,7 +679,7 @@ static int render_frames(rt_ctx *c, const rt_render_params *p, uint32_t nFrames,
 			if (!o) { CU(c->batchOut[f].reserve((size_t)W * H * 3)); o = c->batchOut[f].p; }
 			if (shardChanged || c->batchFill[f] != o)
 			{
-				CU(cudaMemsetAsync(o, 127, (size_t)W * H * 3, st));
+				if (!is_landing_base(o)) CU(cudaMemsetAsync(o, 127, (size_t)W * H * 3, st));   // a landing buffer is born grey and shared with the peers' row copies
 				c->batchFill[f] = o;
 			}
 			F.frames[f].out = o;
@@ -678,7 +721,8 @@ static int render_frames(rt_ctx *c, const rt_render_params *p, uint32_t nFrames,
 	const bool refr = c->anyRefract && p->type != RT_TYPE_REFLECT;
 	for (uint32_t l = 0; l <= maxLevel; ++l)
 	{
-		const uint32_t cap = l == 0 || !refr ? nPix : (uint32_t)std::min<double>((double)nPix * c->levelFactor, 4.0e9);
+		uint32_t cap = l == 0 || !refr ? nPix : (uint32_t)std::min<double>((double)nPix * c->levelFactor, 4.0e9);
+		if (l > 0 && c->minCap[l] > cap) cap = c->minCap[l];
 		int rc = ensure_level(c, l, cap ? cap : 1, F.n_lights);
 		if (rc != RT_OK) return rc;
 	}
@@ -693,15 +737,14 @@ static int render_frames(rt_ctx *c, const rt_render_params *p, uint32_t nFrames,
 	if (++c->frameEpoch > 65535u)
 	{
 		// epoch wrap: forget every stamp so a slot written 65535 frames ago cannot look fresh
-		for (uint32_t l = 0; l <= maxLevel + 1; ++l)
-			if (c->levels[l].ray_meta.p) CU(cudaMemsetAsync(c->levels[l].ray_meta.p, 0, sizeof(uint2) * c->levels[l].ray_meta.cap, st));
+		for (LevelStore &L : c->levels)   // every allocated level, also those deeper than this frame's max_level
+			if (L.ray_meta.p) CU(cudaMemsetAsync(L.ray_meta.p, 0, sizeof(uint2) * L.ray_meta.cap, st));
 		c->frameEpoch = 1;
 	}
 	F.epoch = c->frameEpoch;
 	// level-0 rays are made inside the traversal kernels (k_frame always; k_wave(0) for the ray-traced types --
 	// the staged debug shaders keep k_raygen, k_debug reads the stored rays)
-	static const int waveGen = []{ const char *e = getenv("RT_B200_WAVE_GENPRIMARY"); return e ? atoi(e) : RT_WAVE_GENPRIMARY_DEFAULT; }();
-	const bool genPrimary = (c->frameSched || (waveGen && !debugStage)) && p->type != RT_TYPE_CHECK;
+	const bool genPrimary = (c->frameSched || (c->waveGen && !debugStage)) && p->type != RT_TYPE_CHECK;
 	if (genPrimary) F.sched_flags |= 4u;
 	WaveState &Wv = *c->hWaveInit;
 	memset(&Wv, 0, sizeof Wv);
@@ -710,6 +753,7 @@ static int render_frames(rt_ctx *c, const rt_render_params *p, uint32_t nFrames,
 	CU(cudaMemcpyAsync(c->dFrame, c->hFrame, sizeof(FrameParams), cudaMemcpyHostToDevice, st));
 	CU(cudaMemcpyAsync(c->dWave, c->hWaveInit, sizeof(WaveState), cudaMemcpyHostToDevice, st));
 	c->frameH2D = sizeof(FrameParams) + sizeof(WaveState), c->frameD2H = sizeof(WaveState);
+	g_h2dTotal += c->frameH2D, g_d2hTotal += c->frameD2H;
 	CU(cudaEventRecord(c->evStart, st));
 
 	const bool stats = (p->flags & RT_FLAG_STATS) != 0;
@@ -771,6 +815,8 @@ static int render_frames(rt_ctx *c, const rt_render_params *p, uint32_t nFrames,
 	CU(cudaEventRecord(c->evStop, st));
 	CU(cudaMemcpyAsync(c->hWave, c->dWave, sizeof(WaveState), cudaMemcpyDeviceToHost, st));
 	CU(cudaEventRecord(c->evB, st));
+	if (cams && cams != c->lastCams.data()) c->lastCams.assign(cams, cams + nFrames);
+	c->lastCamsGiven = cams != nullptr, c->lastOutsGiven = outs != nullptr;
 	c->lastParams = *p, c->lastPixels = nPix, c->lastLaunches = launches, c->lastMaxLevel = maxLevel, c->lastBatch = nFrames;
 	for (uint32_t f = 0; f < nFrames; ++f) c->lastOuts[f] = F.frames[f].out;
 	c->frameInFlight = true, c->frameValid = false;
@@ -808,12 +854,37 @@ static int finish_frame(rt_ctx *c)
 		c->traceMs = a, c->shadeMs = d;
 		c->otherMs = c->renderMs - c->traceMs - c->shadeMs;
 	}
-	if (c->hWave->overflow == 3u)
+	if (c->hWave->stop_epoch == c->frameEpoch)
+	{
+		c->regrowTries = 0;
 		return RT_OK;   // stopped by rt_stop: incomplete frame, not an error (frameValid stays false)
+	}
 	if (c->hWave->overflow == 2u)
 		return fail(RT_E_STATE, "the frame scheduler stopped making progress (k_frame gave up waiting); frame is incomplete");
 	if (c->hWave->overflow)
-		return fail(RT_E_LIMIT, "a ray level overflowed its queue (capacity factor %.2f); raise RT_B200_LEVEL_FACTOR", c->levelFactor);
+	{
+		// A ray level ran out of slots: with refraction a ray tree can hold 2^l rays at level l, the queues are sized
+		// for levelFactor x pixels.  WaveState::count[l] kept counting past the capacity, so it says what level l needs;
+		// the levels below an overflowing one were starved, they are grown by the same ratio.  Then the frame is
+		// rendered again, transparently (the caller sees one longer frame).
+		if (c->regrowTries >= RT_MAX_LEVELS + 2)
+			return fail(RT_E_LIMIT, "a ray level still overflows its queue after %u regrows", c->regrowTries);
+		double ratio = 1.0;
+		for (uint32_t l = 1; l <= c->lastMaxLevel; ++l)
+		{
+			const uint64_t cap = c->levels[l].capacity, need = c->hWave->count[l];
+			if (need > cap) ratio = std::max(ratio, (double)need / (double)std::max<uint64_t>(cap, 1));
+			const uint64_t want = std::max<uint64_t>(need + need / 8 + 1024, (uint64_t)((double)cap * ratio) + 1024);
+			if (need > cap || ratio > 1.0) c->minCap[l] = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(c->minCap[l], want), 0xFFFFFFF0ull);
+		}
+		++c->regrowTries;
+		const rt_render_params p = c->lastParams;
+		const uint32_t nb = c->lastBatch;
+		int rc = render_frames(c, &p, nb, c->lastCamsGiven ? c->lastCams.data() : nullptr, c->lastOutsGiven ? (void *const *)c->lastOuts : nullptr);
+		if (rc != RT_OK) return rc;
+		return finish_frame(c);
+	}
+	c->regrowTries = 0;
 	c->frameValid = true;
 	return RT_OK;
 }
@@ -842,15 +913,19 @@ extern "C" int rt_wait(rt_ctx *c, double *seconds)
 }
 
 // Cooperative cancel, like RayTracer::stop clearing isRun (RayTracer.cpp:698-701): a side stream
-// writes 3 into WaveState::overflow; the traversal warps look at that word every time they fetch
-// work and leave, so the frame ends within one batch.  The frame is then incomplete (rt_wait still
-// returns RT_OK, the pixels not reached keep whatever k_combine wrote from partial data).
+// writes the running frame's epoch into WaveState::stop_epoch; the traversal warps look at that word every
+// time they fetch work and leave when it names THEIR frame, so the frame ends within one batch.  A stop that
+// lands late -- after the next frame's state was initialised -- names an epoch that is no longer running and
+// cancels nothing.  The cancelled frame is incomplete (rt_wait still returns RT_OK, frameValid stays false; the
+// pixels not reached keep whatever k_combine wrote from partial data).
 extern "C" int rt_stop(rt_ctx *c)
 {
 	if (!c) return fail(RT_E_INVALID, "rt_stop: ctx is NULL");
 	if (!c->frameInFlight) return RT_OK;
 	CU(cudaSetDevice(c->device));
-	CU(cudaMemcpyAsync(&c->dWave->overflow, c->hStopWord, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stopStream));
+	uint32_t *src = &c->hStopWord[c->stopSlot++ & 63u];
+	*src = c->frameEpoch;
+	CU(cudaMemcpyAsync(&c->dWave->stop_epoch, src, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stopStream));
 	return RT_OK;
 }
 
@@ -864,6 +939,7 @@ extern "C" int rt_read_output(rt_ctx *c, uint8_t *rgb, size_t stride)
 	if (stride < row) return fail(RT_E_INVALID, "rt_read_output: stride %zu < %zu", stride, row);
 	CU(cudaMemcpy2DAsync(rgb, stride, c->fb, row, row, (size_t)c->outH, cudaMemcpyDeviceToHost, c->stream));
 	c->frameD2H += row * (size_t)c->outH;
+	g_d2hTotal += row * (size_t)c->outH;
 	CU(cudaEventRecord(c->evRead, c->stream));
 	CU(wait_event(c->evRead));
 	return RT_OK;
@@ -914,6 +990,7 @@ extern "C" int rt_read_output_rows(rt_ctx *c, uint8_t *rgb, size_t stride)
 	int rc = copy_shard_rows(c, c->fb, rgb, stride, cudaMemcpyDeviceToHost, c->stream, &bytes);
 	if (rc != RT_OK) return rc;
 	c->frameD2H += bytes;
+	g_d2hTotal += bytes;
 	CU(cudaEventRecord(c->evRead, c->stream));
 	CU(wait_event(c->evRead));
 	return RT_OK;
@@ -937,6 +1014,7 @@ extern "C" int rt_read_batch_output(rt_ctx *c, uint32_t frame, uint8_t *rgb, siz
 	else
 		CU(cudaMemcpy2DAsync(rgb, stride, c->lastOuts[frame], row, row, (size_t)c->outH, cudaMemcpyDeviceToHost, c->stream));
 	c->frameD2H += bytes;
+	g_d2hTotal += bytes;
 	if (rows_only & 2)
 		return RT_OK;   // enqueued only: a later call without this bit (same stream, in order) completes them all
 	CU(cudaEventRecord(c->evRead, c->stream));
@@ -997,6 +1075,7 @@ extern "C" int rt_landing_create(rt_ctx *c, int width, int height, rt_landing **
 	CU(cudaMemset(L->base + ((L->frameBytes + 255) & ~(size_t)255), 0, RT_LANDING_FLAGS * sizeof(uint64_t)));
 	CU(cudaHostAlloc(&L->hSeq, RT_LANDING_RING * sizeof(uint64_t), cudaHostAllocDefault));
 	CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)ipc_handle64, L->base));
+	{ std::lock_guard<std::mutex> lock(g_landingMutex); g_landingBases.push_back(L->base); }
 	*out = L;
 	return RT_OK;
 }
@@ -1026,7 +1105,11 @@ extern "C" void rt_landing_close(rt_landing *L)
 {
 	if (!L) return;
 	cudaSetDevice(L->device);
-	if (L->owner) cudaFree(L->base);
+	if (L->owner)
+	{
+		{ std::lock_guard<std::mutex> lock(g_landingMutex); for (auto &b : g_landingBases) if (b == L->base) { b = g_landingBases.back(); g_landingBases.pop_back(); break; } }
+		cudaFree(L->base);
+	}
 	else cudaIpcCloseMemHandle(L->base);
 	cudaFreeHost(L->hSeq);
 	delete L;
@@ -1257,6 +1340,13 @@ extern "C" int rt_read_hit_ids(rt_ctx *c, rt_hit_id *ids)
 		}
 		ids[(size_t)y * W + x] = id;
 	}
+	return RT_OK;
+}
+
+extern "C" int rt_transfer_totals(uint64_t *h2d, uint64_t *d2h)
+{
+	if (h2d) *h2d = g_h2dTotal.load();
+	if (d2h) *d2h = g_d2hTotal.load();
 	return RT_OK;
 }
 

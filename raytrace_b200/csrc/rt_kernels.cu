@@ -275,6 +275,12 @@ __device__ __forceinline__ Surface surface_attributes(const SceneDev &S, const R
 	return s;
 }
 
+// cooperative cancel / scheduler abort, looked at whenever a warp fetches work
+__device__ __forceinline__ bool frame_cancelled(const WaveState *ws, const FrameParams &F)
+{
+	return *(const volatile uint32_t *)&ws->overflow >= 2u || *(const volatile uint32_t *)&ws->stop_epoch == F.epoch;
+}
+
 // ---- fused wave kernel: closest hit of level `level` + shadow rays of level `level - 1` -------------
 
 template<bool STATS, int CTAS>
@@ -294,7 +300,7 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_wave(SceneDev S, const Frame
 		while (true)
 		{
 			const uint32_t base = warp_fetch(&ws->head_trace[level], batch);
-			if (base >= n || *(const volatile uint32_t *)&ws->overflow >= 2u)   // queue dry, or rt_stop
+			if (base >= n || frame_cancelled(ws, F))   // queue dry, or rt_stop
 				break;
 			const uint32_t lane = threadIdx.x & 31u;
 			const uint32_t i = lane < batch ? base + lane : 0xFFFFFFFFu;
@@ -422,7 +428,7 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_wave(SceneDev S, const Frame
 		while (true)
 		{
 			const uint32_t base = warp_fetch(&ws->head_shadow[lp], batch);
-			if (base >= n || *(const volatile uint32_t *)&ws->overflow >= 2u)
+			if (base >= n || frame_cancelled(ws, F))
 				break;
 			const uint32_t lane = threadIdx.x & 31u;
 			const uint32_t w = lane < batch ? base + lane : 0xFFFFFFFFu;
@@ -639,7 +645,7 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_frame(SceneDev S, const Fram
 			int out = 0;
 			if (lane == 0) out = *(volatile int *)&ws->outstanding;
 			out = __shfl_sync(0xffffffffu, out, 0);
-			if (out <= 0 || vload(&ws->overflow) >= 2u)
+			if (out <= 0 || frame_cancelled(ws, F))
 				break;   // nothing in flight any more (or the scheduler gave up / rt_stop): unpublished slots will never be written
 			// Retire: when the frame runs thin (a few long ray chains are left), a CTA that owns nothing and
 			// finds nothing leaves for good if fewer than `retire_rays` rays per CTA would remain for it -- high CTA
@@ -661,7 +667,7 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_frame(SceneDev S, const Fram
 			continue;
 		}
 		idleSpins = 0;
-		if (vload(&ws->overflow) >= 2u)
+		if (frame_cancelled(ws, F))
 			break;   // rt_stop or scheduler abort
 		const uint32_t nb = __popc(readyMask);
 		if (STATS && lane == 0)

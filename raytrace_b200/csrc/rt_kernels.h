@@ -34,6 +34,7 @@ struct WaveState
 	uint32_t head_trace[RT_MAX_LEVELS + 2], head_shadow[RT_MAX_LEVELS + 2];   // work-fetch cursors of the persistent warps
 	uint32_t head_light[RT_MAX_LEVELS + 2][RT_MAX_LIGHTS];                    // k_frame: shadow cursor per (level, enabled light)
 	uint32_t overflow;                   // 1: a level ran out of slots, 2: the frame scheduler gave up waiting
+	uint32_t stop_epoch;                 // rt_stop: the epoch of the frame to cancel (a late-landing stop of an older frame matches nothing)
 	int outstanding;                     // k_frame: rays reserved and not yet finished (0 = frame complete)
 	unsigned long long n_reflect, n_refract;
 	unsigned long long nodes_visited, tri_tests, prim_tests;

@@ -86,10 +86,15 @@ struct SceneResidency
 			&& a.camera.fovy == b.camera.fovy && a.camera.zNear == b.camera.zNear && a.camera.zFar == b.camera.zFar;
 	}
 
+	static double nowS() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 	void workerLoop(int w)
 	{
 		std::vector<FrameRequest> batch;
 		std::vector<rt_camera> cams;
+		const bool trace = getenv("RT_B200_COALESCE_TRACE") != nullptr;
+		double tFirst = 0, tLaunch = 0, tRendered = 0;
+		size_t wantLast = 0;
 		while (true)
 		{
 			batch.clear();
@@ -103,6 +108,7 @@ struct SceneResidency
 				// batches of one.  Wait while requests keep arriving, up to this worker's share of the tracers.
 				const int div = wantDiv > 0 ? wantDiv : nWorkers + 1;
 				const size_t want = std::max<size_t>(1, std::min(kMaxBatch, (size_t)(coalescers + div - 1) / div));
+				wantLast = want, tFirst = nowS();
 				while (!quit && pending.size() < want)
 				{
 					const size_t before = pending.size();
@@ -124,20 +130,29 @@ struct SceneResidency
 			rt_ctx *c = workerCtx[w];
 			double seconds = 0.0;
 			int rc;
+			tLaunch = nowS();
 			{
 				// the launch adopts the parent's scene tables: not while a start() is uploading into them
 				std::lock_guard<std::mutex> lock(mutex);
 				rc = rt_render_batch_async(c, &batch[0].rp, (uint32_t)batch.size(), cams.data(), nullptr);
 			}
 			if (rc == RT_OK) rc = rt_wait(c, &seconds);
+			tRendered = nowS();
 			// all copies enqueued back to back, one wait (the last call completes them all)
 			for (size_t f = 0; f < batch.size() && rc == RT_OK; ++f)
 				rc = rt_read_batch_output(c, (uint32_t)f, batch[f].tracer->output, (size_t)batch[f].camera.width * 3,
 					(batch[f].rowsOnly ? 1 : 0) | (f + 1 < batch.size() ? 2 : 0));
+			if (trace)
+				fprintf(stderr, "raytrace_b200 coalesce[w%d]: %zu frames (want %zu), waited %.3f ms for the batch, render+wait %.3f ms (device %.3f ms), read-back %.3f ms\n",
+					w, batch.size(), wantLast, (tLaunch - tFirst) * 1e3, (tRendered - tLaunch) * 1e3, seconds * 1e3, (nowS() - tRendered) * 1e3);
 			if (rc != RT_OK)
 			{
-				fprintf(stderr, "raytrace_b200: batch of %zu frames failed (%d): %s\n", batch.size(), rc, rt_last_error());
-				abort();
+				// no abort: every tracer of the batch gets its frame back as failed (isFinish, failed, lastError)
+				const std::string err = rt_last_error();
+				fprintf(stderr, "raytrace_b200: batch of %zu frames failed (%d): %s\n", batch.size(), rc, err.c_str());
+				for (const FrameRequest &r : batch)
+					r.tracer->completeFrame(seconds, c, err.c_str());
+				continue;
 			}
 			for (const FrameRequest &r : batch)
 				r.tracer->completeFrame(seconds, c);
@@ -167,6 +182,16 @@ struct SceneResidency
 			pending.push_back(r);
 		}
 		qCv.notify_all();
+	}
+	// RayTracer::stop of a coalescing tracer: a request that is still waiting is taken out of the queue (-> true, the
+	// caller completes it as cancelled); one that is already part of a launch is left alone -- the launch holds other
+	// tracers' frames too, so it is never stopped, the frame is simply delivered (a cooperative cancel may finish)
+	bool cancelPending(RayTracer *t)
+	{
+		std::lock_guard<std::mutex> lock(qMutex);
+		for (auto it = pending.begin(); it != pending.end(); ++it)
+			if (it->tracer == t) { pending.erase(it); return true; }
+		return false;
 	}
 	void addCoalescer(int d)
 	{
@@ -258,10 +283,11 @@ void RayTracer::reserveOutput(size_t bytes)
 	output = alloc_output(outputBytes, outputPinned);
 }
 
-void RayTracer::completeFrame(double seconds, rt_ctx *renderedBy)
+void RayTracer::completeFrame(double seconds, rt_ctx *renderedBy, const char *error)
 {
 	{
 		std::lock_guard<std::mutex> lock(doneMutex);
+		if (error) lastError = error, failed = true;
 		useTime = seconds;
 		lastCtx = renderedBy;
 		queued = false;
@@ -273,6 +299,7 @@ void RayTracer::completeFrame(double seconds, rt_ctx *renderedBy)
 void RayTracer::start(const uint8_t type, const int8_t)
 {
 	wait();
+	failed = false, lastError.clear();
 	isFinish = false;
 	width = scene->cam.width;
 	height = scene->cam.height;
@@ -343,8 +370,10 @@ void RayTracer::start(const uint8_t type, const int8_t)
 			rc = rowsOnly ? rt_read_output_rows(ctx, output, (size_t)width * 3) : rt_read_output(ctx, output, (size_t)width * 3);
 		if (rc != RT_OK)
 		{
-			fprintf(stderr, "raytrace_b200: frame failed (%d): %s\n", rc, rt_last_error());
-			abort();
+			// no abort: the frame ends, flagged (the reference's start() has no error channel; `failed` is ours)
+			lastError = rt_last_error();
+			fprintf(stderr, "raytrace_b200: frame failed (%d): %s\n", rc, lastError.c_str());
+			failed = true;
 		}
 		useTime = seconds;
 		isFinish = true;
@@ -353,11 +382,17 @@ void RayTracer::start(const uint8_t type, const int8_t)
 
 void RayTracer::stop()
 {
+	if (residency && queued)
+	{
+		// a coalesced frame: cancel THIS request only.  Still waiting -> taken out of the queue and completed as
+		// cancelled (output untouched); already in a launch -> that launch also holds other tracers' frames and is
+		// never stopped, the frame is delivered normally.
+		if (residency->cancelPending(this))
+			completeFrame(0.0, nullptr);
+		return;
+	}
 	if (ctx)
-		rt_stop(ctx);
-	if (residency && queued)   // a coalesced frame: cancel the launches of both batch workers (cooperative, like isRun = false)
-		for (int w = 0; w < SceneResidency::kWorkers; ++w)
-			if (residency->workerContext(w)) rt_stop(residency->workerContext(w));
+		rt_stop(ctx);   // own pipeline: cooperative cancel of the running frame (names its epoch; a late stop cancels nothing)
 }
 
 void RayTracer::wait()

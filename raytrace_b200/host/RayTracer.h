@@ -9,6 +9,7 @@
 #include <condition_variable>
 #include <memory>
 #include <mutex>
+#include <string>
 #include <thread>
 
 #define MY_MODEL_CHECK 0x1
@@ -57,6 +58,11 @@ public:
 	void stop();
 
 	// ---- additions of this build (not in the reference) ----
+	// The reference's start() cannot fail.  Here a frame can (device error, out of memory while a ray level is
+	// regrown): the frame then ends like any other -- isFinish becomes true, `output` keeps its previous content --
+	// with `failed` set and the library's message in `lastError`; the next start() clears both.
+	volatile bool failed = false;
+	std::string lastError;
 	int device = 0;                 // CUDA device ordinal used when the context is created
 	uint32_t shardRank = 0, shardWorld = 1;   // image-space shard rendered by this tracer
 	uint32_t shardTileRows = 64;              // rows per shard tile (8, 16, 32, 64)
@@ -70,7 +76,7 @@ public:
 	// protocol; useTime is the time of the launch the frame was part of, readCounters() that launch's totals.
 	// RAYTRACE frames without RT_FLAG_HIT_IDS only; anything else takes the tracer's own pipeline.
 	bool coalesce = false;
-	void completeFrame(double seconds, rt_ctx *renderedBy);        // called by a batch worker when this tracer's frame is in `output`
+	void completeFrame(double seconds, rt_ctx *renderedBy, const char *error = nullptr);   // called by a batch worker when this tracer's frame is in `output` (or failed / was cancelled)
 	void reserveOutput(size_t bytes);          // frames beyond 2048x2048
 	void wait();                               // block until isFinish
 	bool readHitIds(rt_hit_id *ids);           // primary closest-hit identities of the last frame

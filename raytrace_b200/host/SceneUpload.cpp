@@ -28,6 +28,14 @@ int32_t SceneFlattener::addTexture(const Texture &t)
 	return (int32_t)textures.size() - 1;
 }
 
+void SceneFlattener::cameraRecord(const Camera &cam, rt_camera &out)
+{
+	memset(&out, 0, sizeof out);
+	out.u = v4(cam.u), out.v = v4(cam.v), out.n = v4(cam.n), out.position = v4(cam.position);
+	out.width = cam.width, out.height = cam.height;
+	out.fovy = cam.fovy, out.zNear = cam.zNear, out.zFar = cam.zFar;
+}
+
 void SceneFlattener::flatten(const Scene &scene, rt_scene_desc &desc)
 {
 	lights.clear(), materials.clear(), textures.clear(), texels.clear(), materialPtrs.clear(), texturePtrs.clear();
@@ -35,9 +43,7 @@ void SceneFlattener::flatten(const Scene &scene, rt_scene_desc &desc)
 
 	memset(&desc, 0, sizeof desc);
 	const Camera &cam = scene.cam;
-	desc.camera.u = v4(cam.u), desc.camera.v = v4(cam.v), desc.camera.n = v4(cam.n), desc.camera.position = v4(cam.position);
-	desc.camera.width = cam.width, desc.camera.height = cam.height;
-	desc.camera.fovy = cam.fovy, desc.camera.zNear = cam.zNear, desc.camera.zFar = cam.zFar;
+	cameraRecord(cam, desc.camera);
 	desc.env_light = v4(scene.EnvLight);
 
 	for (const Light &l : scene.Lights)

@@ -11,6 +11,8 @@ public:
 	// Fills `desc` with pointers into this object's storage (valid until the next flatten()).
 	// Heavy triangle arrays are only rebuilt when some Model's epoch changed.
 	void flatten(const Scene &scene, rt_scene_desc &desc);
+	// the C-ABI record of a Camera (3DElement.h:225-237)
+	static void cameraRecord(const Camera &cam, rt_camera &out);
 
 	// what the material / texture indices of the last flatten() refer to (for mapping device hits
 	// back to HitRes::mtl / HitRes::tex pointers)

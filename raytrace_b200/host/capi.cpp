@@ -101,6 +101,24 @@ int rth_scene_camera_jitter(void *h, float dx, float dy)
 	return 0;
 }
 
+// camera k of the K-camera orbit around the scene's CURRENT camera (scenes.h orbit_camera), as the C-ABI
+// record rt_render_batch_async takes; the Scene itself is not changed
+int rth_scene_orbit_camera(void *h, int k, int K, rt_camera *out)
+{
+	const Camera c = rtscenes::orbit_camera(((HostScene *)h)->scene.cam, k, K);
+	SceneFlattener::cameraRecord(c, *out);
+	return 0;
+}
+// ... and the same camera put INTO the scene (start() then renders through it); `base` is restored by k = 0 of
+// a second call only if the caller kept it: callers pass the base camera they read with rth_scene_camera_get
+int rth_scene_camera_get(void *h, rt_camera *out) { SceneFlattener::cameraRecord(((HostScene *)h)->scene.cam, *out); return 0; }
+int rth_scene_camera_set_position(void *h, float x, float y, float z)
+{
+	Camera &c = ((HostScene *)h)->scene.cam;
+	c.position.x = x, c.position.y = y, c.position.z = z;
+	return 0;
+}
+
 int rth_scene_camera_get_n(void *h, float *xyzw)
 {
 	const Camera &c = ((HostScene *)h)->scene.cam;
@@ -135,6 +153,8 @@ void *rth_tracer_new(void *scene, int device)
 void rth_tracer_free(void *t) { delete (RayTracer *)t; }
 int rth_tracer_start(void *t, int type, int tnum) { return guarded([&] { ((RayTracer *)t)->start((uint8_t)type, (int8_t)tnum); }); }
 void rth_tracer_stop(void *t) { ((RayTracer *)t)->stop(); }
+int rth_tracer_failed(void *t) { return ((RayTracer *)t)->failed ? 1 : 0; }
+const char *rth_tracer_last_error(void *t) { return ((RayTracer *)t)->lastError.c_str(); }
 int rth_tracer_is_finished(void *t) { return ((RayTracer *)t)->isFinish ? 1 : 0; }
 void rth_tracer_wait(void *t) { ((RayTracer *)t)->wait(); }
 double rth_tracer_use_time(void *t) { return ((RayTracer *)t)->useTime; }

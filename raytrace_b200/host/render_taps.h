@@ -33,7 +33,7 @@ inline Counts count_rays(Scene &, RayTracer &rt, int, int)
 	return o;
 }
 
-inline long render_tiles(Scene &, RayTracer &, int, int, int, int, int, int, Counts *)
+inline long render_tiles(Scene &, RayTracer &, int, int, int, int, int, int, Counts *, double * = nullptr, double * = nullptr)
 {
 	fprintf(stderr, "--tiles is a CPU-baseline sampling mode of the reference arm only\n");
 	exit(2);

@@ -19,4 +19,5 @@ def test_p2p_landing_and_nccl_gather_assemble_the_full_frame(gpu_present):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
                         "--master-port", "29533", os.path.join(ROOT, "tools", "p2p_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "first p2p landing == full frame: True" in r.stdout and "first p2p landing == full frame: False" not in r.stdout
     assert "p2p landing == full frame: True" in r.stdout and "nccl gather == full frame: True" in r.stdout

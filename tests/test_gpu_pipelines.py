@@ -196,3 +196,49 @@ def test_coalescing_tracers_render_their_own_frames(gpu_present):
     assert np.array_equal(img, oracle_render(sc, level, want_ids=False)[0])
     ids_img = tracers[1].render(R.MY_MODEL_RAYTRACE, flags=R.RT_FLAG_HIT_IDS)     # taps take the tracer's own pipeline
     assert np.array_equal(ids_img, img) and tracers[1].hit_ids().shape == (h, w)
+
+
+@pytest.mark.parametrize("sched", ["waves", "frame"])
+def test_overflowing_ray_levels_regrow_and_rerender(gpu_present, monkeypatch, sched):
+    # with refraction a level can hold more rays than levelFactor x pixels.  The queues are deliberately
+    # undersized here (factor 0.2: the camera sits inside a glass sphere, every pixel reflects AND refracts); the
+    # library must regrow them from the counts of the overflowing frame and render it again, not fail or abort.
+    monkeypatch.setenv("RT_B200_LEVEL_FACTOR", "0.2")
+    monkeypatch.setenv("RT_B200_SCHED", sched)
+    sc = R.Scene("t_inside", 384, 256)
+    t = R.RayTracer(sc)
+    t.maxLevel = 6
+    img = t.render(R.MY_MODEL_RAYTRACE)
+    assert not t.failed
+    oimg, _, oc = oracle_render(sc, 6, want_ids=False)
+    assert np.array_equal(img, oimg)
+    c = t.counters()
+    assert (c.primary, c.shadow, c.reflect, c.refract) == (oc.primary, oc.shadow, oc.reflect, oc.refract)
+    assert oc.reflect + oc.refract > 0.2 * oc.primary * 2          # the undersized queues really overflowed
+    assert np.array_equal(t.render(R.MY_MODEL_RAYTRACE), oimg)      # the learnt capacities stay: no second regrow needed
+
+
+def test_stop_of_a_coalescing_tracer_leaves_the_others_alone(gpu_present):
+    # stop() of one coalescing tracer must cancel only its own request -- never a launch that also
+    # holds other tracers' frames
+    w, h, level = 384, 256, 4
+    sc = R.Scene("t_mesh", w, h)
+    oimg = oracle_render(sc, level, want_ids=False)[0]
+    tracers = []
+    for _ in range(6):
+        t = R.RayTracer(sc)
+        t.maxLevel = level
+        t.coalesce = True
+        tracers.append(t)
+    for rep in range(4):
+        for t in tracers:
+            t.start(R.MY_MODEL_RAYTRACE)
+        R.rth.rth_tracer_stop(tracers[rep % 6]._h)           # cancelled while waiting, or delivered if already in a launch
+        R.rth.rth_tracer_stop(tracers[(rep + 3) % 6]._h)
+        for k, t in enumerate(tracers):
+            t.wait()
+            assert t.isFinish and not t.failed
+            if k not in (rep % 6, (rep + 3) % 6):
+                assert np.array_equal(t.output(), oimg), (rep, k)
+    for t in tracers:                                        # every tracer, the stopped ones too, renders correctly afterwards
+        assert np.array_equal(t.render(R.MY_MODEL_RAYTRACE), oimg)

@@ -55,23 +55,35 @@ for i in range(2):
     pipes.append((p, st, landing, frame))
 SERP = os.environ.get("RT_P2P_SERPENTINE", "1") != "0"       # boustrophedon shard order (RT_FLAG_SERPENTINE), as bench.py uses it
 params = R.RenderParams(R.MY_MODEL_RAYTRACE, level, rank, world, R.RT_FLAG_SERPENTINE if SERP else 0, tile_rows)
+def check_landings(label):
+    """rank 0: every pipeline's landing buffer (its own rows + the peers' pushes) against the full-frame render"""
+    global ok
+    for p, st, landing, frame in pipes:
+        ck(R.rt.rt_wait(p, None), "rt_wait")
+        st.synchronize()
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    if rank == 0:
+        for p, st, landing, frame in pipes:
+            got = np.empty((h, w, 3), dtype=np.uint8)
+            ck(R.rt.rt_read_output(p, got.ctypes.data_as(C.c_void_p), w * 3), "rt_read_output")   # the pipeline's output IS the landing buffer
+            same = bool(np.array_equal(got, full))
+            print(f"{label} == full frame:", same, flush=True)
+            ok = ok and same
+    dist.barrier()
+
+
 for k in range(6):                      # 3 frames per pipeline, 2 in flight
+    if k == 0 and rank == 0:
+        import time
+        time.sleep(0.3)                 # the peers' rows of the FIRST frame land before rank 0 has enqueued anything: nothing
+                                        # rank 0 does for its first frame (no grey fill of a landing buffer) may wipe them
     p, st, landing, frame = pipes[k % 2]
     ck(R.rt.rt_render_async(p, C.byref(params)), "rt_render_async")
     landing.push(p)
-for p, st, landing, frame in pipes:
-    ck(R.rt.rt_wait(p, None), "rt_wait")
-    st.synchronize()
-torch.cuda.synchronize(dev)
-dist.barrier()
-if rank == 0:
-    for p, st, landing, frame in pipes:
-        ptr, nbytes = landing.device_ptr()
-        got = np.empty((h, w, 3), dtype=np.uint8)
-        ck(R.rt.rt_read_output(p, got.ctypes.data_as(C.c_void_p), w * 3), "rt_read_output")   # the pipeline's output IS the landing buffer
-        same = bool(np.array_equal(got, full))
-        print("p2p landing == full frame:", same, flush=True)
-        ok = ok and same
+    if k == 1:
+        check_landings("first p2p landing")
+check_landings("p2p landing")
 # (a2) a BATCH of two frames in one launch (rt_render_batch_async), each frame pushed into its own landing buffer
 p0 = pipes[0][0]
 outs = (C.c_void_p * 2)()

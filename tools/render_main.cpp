@@ -11,7 +11,7 @@
 //
 //   render --scene c1 --width 1088 --height 576 --level 1 [--type 0x80] [--threads 8]
 //          [--n N] [--parts P] [--repeat K] [--out f.rgb] [--ids f.bin] [--counts]
-//          [--tiles K --seed S] [--tmpdir D] [--gpus N]
+//          [--tiles K --seed S | --tiles K --stratified] [--orbit K [--orbit-k k]] [--tmpdir D] [--gpus N]
 // prints one JSON line on stdout.
 #include "Scene.h"
 #include "RayTracer.h"
@@ -45,7 +45,7 @@ int main(int argc, char **argv)
 {
 	rtscenes::SceneArgs sa;
 	int width = 1088, height = 576, level = 1, type = MY_MODEL_RAYTRACE, threads = 8, repeat = 1;
-	int tiles = 0, seed = 0, warmup = 0;
+	int tiles = 0, seed = 0, warmup = 0, orbit = 0, orbitK = 0;
 	bool counts = false;
 	std::string out, ids;
 	for (int i = 1; i < argc; ++i)
@@ -67,7 +67,10 @@ int main(int argc, char **argv)
 		else if (k == "--counts") counts = true;
 		else if (k == "--tiles") tiles = atoi(val());
 		else if (k == "--seed") seed = atoi(val());
+		else if (k == "--stratified") seed = -1;   // tiles spread evenly over the frame instead of seeded random ones
 		else if (k == "--warmup") warmup = atoi(val());
+		else if (k == "--orbit") orbit = atoi(val());       // pass r renders camera r % orbit of the orbit (scenes.h orbit_camera)
+		else if (k == "--orbit-k") orbitK = atoi(val());    // first camera of the orbit to render
 		else if (k == "--gpus") rt_taps::set_gpus(atoi(val()));
 		else { fprintf(stderr, "unknown option %s\n", k.c_str()); return 2; }
 	}
@@ -82,17 +85,21 @@ int main(int argc, char **argv)
 
 	std::vector<double> walls, uses;
 	rt_taps::Counts cnt;
+	const Camera baseCam = scene.cam;
 	if (tiles > 0)
 	{
 		// bounded CPU sample: `tiles` seeded 64x64 tiles through the per-pixel entry, `warmup`
 		// untimed + `repeat` timed passes over the same tiles; rays counted in one extra pass
+		// step_s = trace seconds of the sample, prepare_s = the reference's per-frame RTPrepare (timed apart: a
+		// frame pays it once, a sample must not be charged all of it -- see render_taps.h)
 		long px = 0;
+		std::vector<double> prepares;
 		for (int r = 0; r < warmup + repeat; ++r)
 		{
-			double t0 = now_s();
-			px = rt_taps::render_tiles(scene, rayt, width, height, tiles, seed, threads, type, nullptr);
-			double t1 = now_s();
-			if (r >= warmup) walls.push_back(t1 - t0);
+			double prep = 0, trace = 0;
+			if (orbit > 0) scene.cam = rtscenes::orbit_camera(baseCam, orbitK + r, orbit);
+			px = rt_taps::render_tiles(scene, rayt, width, height, tiles, seed, threads, type, nullptr, &prep, &trace);
+			if (r >= warmup) walls.push_back(trace), prepares.push_back(prep);
 		}
 		unsigned long long rays = 0;
 		if (counts)
@@ -103,11 +110,14 @@ int main(int argc, char **argv)
 		printf("{\"scene\":\"%s\",\"arm\":\"%s\",\"w\":%d,\"h\":%d,\"level\":%d,\"threads\":%d,\"tiles\":%d,\"pixels\":%ld,\"rays_per_step\":%llu,\"hash\":\"%016llx\",\"step_s\":[",
 			sa.name.c_str(), rt_taps::arm(), width, height, level, threads, tiles, px, rays, (unsigned long long)fnv1a64(rayt.output, need));
 		for (size_t i = 0; i < walls.size(); ++i) printf("%s%.6f", i ? "," : "", walls[i]);
-		printf("]}\n");
+		printf("],\"prepare_s\":[");
+		for (size_t i = 0; i < prepares.size(); ++i) printf("%s%.6f", i ? "," : "", prepares[i]);
+		printf("],\"frame_tiles\":%d,\"stratified\":%s}\n", (width / 64) * (height / 64), seed < 0 ? "true" : "false");
 		return 0;
 	}
 	for (int r = 0; r < repeat; ++r)
 	{
+		if (orbit > 0) scene.cam = rtscenes::orbit_camera(baseCam, orbitK + r, orbit);
 		double t0 = now_s();
 		rayt.start((uint8_t)type, (int8_t)threads);
 		while (!rayt.isFinish) std::this_thread::sleep_for(std::chrono::microseconds(200));
