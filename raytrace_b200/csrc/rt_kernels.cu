@@ -20,6 +20,7 @@
 // c = c*(1-kr) + c_refl*kr ; c = c*(1-kt) + (c_refr (*) beer)*kt sequence, so the colour
 // arithmetic is bit-identical to the recursive evaluation order.
 #include "rt_traverse.cuh"
+#include "rt_async.cuh"
 #include "rt_kernels.h"
 #include <cstdlib>
 
@@ -451,6 +452,364 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_wave(SceneDev S, const Frame
 				if (STATS) atomicAdd(&ws->node_hist[12 + min(11, 31 - __clz((int)(st.nodes - nodes0 + 1u)))], 1u);
 				Lprev.shadow[(size_t)k * Lprev.capacity + i] = done ? 1 : 0;
 			}
+		}
+	}
+	flush_stats<STATS>(ws, st);
+}
+
+// ---- lane-asynchronous wave kernel ---------------------------------------------------------------------
+// Same work as k_wave -- closest hit of level `level` (+ surface attributes, child rays) and the shadow rays of
+// level `level - 1` -- with the walk of rt_async.cuh: lanes take rays out of a per-warp pool one by one, finished
+// rays wait in the pool for an epilogue that runs 32 at a time.
+
+// One finished closest-hit ray: hit record, early cut, surface attributes, child rays, queue appends (the epilogue
+// of k_wave's phase A).  Called by ALL 32 lanes (lanes without a ray pass valid = false): appends are warp-aggregated.
+__device__ __forceinline__ void trace_epilogue(const SceneDev &S, const FrameParams &F, const LevelBuf &L, const LevelBuf &N, WaveState *ws,
+	uint32_t level, float zNear, bool valid, uint32_t i, const RayD &ray, float bwc, bool made, const Best &best)
+{
+	const bool refraction = F.type != RT_TYPE_REFLECT;
+	const bool deeper = level + 1 <= F.max_level;
+	bool surface = false, wantFlec = false, wantFrac = false;
+	float4 co = make_float4(0, 0, 0, 0), cdFlec = co, cdFrac = co;
+	uint2 metaFlec = make_uint2(0, 0), metaFrac = metaFlec;
+	float fracRfr = 1.0f;
+	int4 aux = make_int4(-1, -1, -1, 0);
+	if (valid)
+	{
+		const F3 P = ray.o + ray.d * best.t;
+		L.hit_p[i] = make_float4(P.x, P.y, P.z, best.t);
+		L.hit_id[i] = make_uint2(best.id, best.newobj);
+		// early cut of RayTracer.cpp:467-468: no surface -> Color(false), no light loop, no children
+		surface = !(best.t > F.zFar || best.t < zNear);
+		if (!surface)
+			L.color[i] = make_float4(0.0f, 0.0f, 0.0f, 1e20f);
+		else
+		{
+			const Surface sf = surface_attributes(S, ray, P, best.id);
+			L.hit_n[i] = make_float4(sf.N.x, sf.N.y, sf.N.z, __int_as_float(sf.mtl));
+			L.hit_uv[i] = make_float4(sf.tu, sf.tv, __int_as_float(sf.tex), 0.0f);
+			const float4 mP = ldg4(&S.materials[4 * sf.mtl + 3]);   // shiness, reflect, refract, rfr
+			if (made)
+				L.ray_d[i] = make_float4(ray.d.x, ray.d.y, ray.d.z, 1.0f);   // the view direction of a surface is read again by k_shade
+			aux.z = sf.mtl;
+			co = make_float4(P.x, P.y, P.z, 1.0f);
+			if (mP.y > 0.01f)
+			{
+				// reflection, RayTracer.cpp:548-563
+				aux.w |= 1;
+				const float bw = bwc * mP.y;
+				if (deeper && !(bw < 1e-5f))
+				{
+					const float n_n = 2 * dot(ray.d, sf.N);
+					const F3 r = normalize(ray.d - sf.N * n_n);
+					wantFlec = true;
+					cdFlec = make_float4(r.x, r.y, r.z, bw);
+					metaFlec = make_uint2(best.newobj, refraction ? (uint32_t)MY_RAY_REFLECTRAY_ : 0u);
+				}
+			}
+			if (refraction && mP.z > 0.01f)
+			{
+				// refraction, RayTracer.cpp:565-583
+				aux.w |= 2;
+				if (sf.isInside) aux.w |= 4;
+				const float nn = ray.mtlrfr / sf.rfr;
+				const float cosIn = -dot(ray.d, sf.N);
+				const float cosOut2 = 1.0f - (nn * nn) * (1.0f - cosIn * cosIn);
+				const float bw = bwc * mP.z;
+				if (!(cosOut2 < 0.0f) && deeper && !(bw < 1e-5f))
+				{
+					const F3 l2 = ray.d * nn, l1 = sf.N * (nn * cosIn - sqrtf(cosOut2));
+					const F3 r = normalize(l1 + l2);
+					wantFrac = true;
+					cdFrac = make_float4(r.x, r.y, r.z, bw);
+					metaFrac = make_uint2(best.newobj, (uint32_t)MY_RAY_REFRACTRAY_ | ((uint32_t)sf.isInside << 8));
+					fracRfr = sf.rfr;
+				}
+			}
+		}
+	}
+	const uint32_t hslot = warp_append(&ws->n_hit[level], surface);
+	if (surface)
+		L.hit_list[hslot] = i + 1u;
+	const uint32_t sFlec = warp_append(&ws->count[level + 1], wantFlec);
+	if (wantFlec)
+	{
+		if (sFlec < N.capacity)
+		{
+			N.ray_o[sFlec] = co, N.ray_d[sFlec] = cdFlec, N.ray_meta[sFlec] = metaFlec;
+			aux.x = (int)sFlec;
+		}
+		else
+			ws->overflow = 1;
+	}
+	const uint32_t sFrac = warp_append(&ws->count[level + 1], wantFrac);
+	if (wantFrac)
+	{
+		if (sFrac < N.capacity)
+		{
+			N.ray_o[sFrac] = make_float4(co.x, co.y, co.z, fracRfr), N.ray_d[sFrac] = cdFrac, N.ray_meta[sFrac] = metaFrac;
+			aux.y = (int)sFrac;
+		}
+		else
+			ws->overflow = 1;
+	}
+	if (valid)
+		L.aux[i] = aux;
+	const uint32_t mf = __ballot_sync(0xffffffffu, wantFlec), mr = __ballot_sync(0xffffffffu, wantFrac);
+	if ((threadIdx.x & 31) == 0)
+	{
+		if (mf) atomicAdd(&ws->n_reflect, (unsigned long long)__popc(mf));
+		if (mr) atomicAdd(&ws->n_refract, (unsigned long long)__popc(mr));
+	}
+}
+
+__device__ __forceinline__ uint32_t pool_count(const uint32_t *p) { return *(const volatile uint32_t *)p; }
+
+// lanes of `grp` whose ray is through hand in their pool entry, lanes without a ray take one; -> nothing left to take
+template<bool ANY>
+__device__ __forceinline__ bool pool_exchange(WarpPool &P, Lane &Ln, uint32_t grp, bool fin, float firstT)
+{
+	const uint32_t lane = threadIdx.x & 31u, lt = lanemask_lt(), leader = __ffs((int)grp) - 1;
+	if (!ANY)
+	{
+		const uint32_t mFin = __ballot_sync(grp, fin);
+		if (mFin)
+		{
+			const uint32_t nD = pool_count(&P.nDone);
+			if (fin)
+			{
+				PoolEntry &E = P.e[Ln.entry];
+				E.t = Ln.bt, E.id = Ln.bid, E.newobj = Ln.bnew;
+				P.doneQ[nD + __popc(mFin & lt)] = (uint8_t)Ln.entry;
+				Ln.flags = 0;
+			}
+			__syncwarp(grp);
+			if (lane == leader) P.nDone = nD + __popc(mFin);
+		}
+	}
+	const bool need = !(Ln.flags & LF_HAS);
+	const uint32_t mNeed = __ballot_sync(grp, need);
+	if (!mNeed)
+		return false;
+	const uint32_t nR = pool_count(&P.nReady);
+	if (!nR)
+		return false;
+	const uint32_t r = __popc(mNeed & lt);
+	if (need && r < nR)
+	{
+		const uint32_t e = ANY ? nR - 1u - r : (uint32_t)P.readyQ[nR - 1u - r];
+		lane_take(Ln, P.e[e], e);
+		if (ANY)
+		{
+			Ln.entry = P.e[e].slot;            // shadow rays: where the occlusion flag goes
+			Ln.bt = P.e[e].o.w;                // light distance
+			Ln.bid = Ln.bnew = RT_ID_NONE;
+		}
+		else
+			Ln.bt = firstT, Ln.bid = RT_ID_NONE, Ln.bnew = Ln.skip;
+	}
+	__syncwarp(grp);
+	const uint32_t taken = __popc(mNeed) < nR ? __popc(mNeed) : nR;
+	if (lane == leader) P.nReady = nR - taken;
+	__syncwarp(grp);
+	return true;
+}
+
+template<bool STATS, int CTAS>
+__global__ void __launch_bounds__(RT_BLOCK, CTAS) k_wave_async(SceneDev S, const FrameParams *__restrict__ Fp, LevelBuf L, LevelBuf N, LevelBuf Lprev,
+	WaveState *ws, uint32_t level, uint32_t traceOn, uint32_t shadowOn, float zNear)
+{
+	__shared__ WarpPool pools[RT_BLOCK / 32];
+	WarpPool &P = pools[threadIdx.x >> 5];
+	const FrameParams &F = *Fp;
+	const uint32_t lane = threadIdx.x & 31u;
+	TravStats st = { 0, 0, 0 };
+
+	// ---- phase A: closest hit + surface attributes + children ------------------------------------
+	if (traceOn)
+	{
+		const uint32_t n = ws->count[level] < L.capacity ? ws->count[level] : L.capacity;
+		const uint32_t batch = fetch_batch(n);
+		const bool made = level == 0u && (F.sched_flags & 4u);   // primary rays are made at refill (k_raygen did not run)
+		pool_init(P);
+		uint2 stack[RT_STACK];
+		Lane Ln;
+		Ln.flags = 0, Ln.cur = RT_TRAV_DONE, Ln.sp = 0, Ln.item = 0, Ln.entry = 0;
+		bool dry = n == 0u;
+		while (true)
+		{
+			const bool has = (Ln.flags & LF_HAS) != 0u;
+			const bool atNode = has && Ln.cur >= 0, atLeaf = has && Ln.cur < 0 && Ln.cur != RT_TRAV_DONE;
+			const uint32_t nReady = pool_count(&P.nReady), nDone = pool_count(&P.nDone);
+			const bool wantAdv = (has && Ln.cur == RT_TRAV_DONE) || (!has && nReady > 0u);
+			const uint32_t mN = __ballot_sync(0xffffffffu, atNode), mL = __ballot_sync(0xffffffffu, atLeaf), mA = __ballot_sync(0xffffffffu, wantAdv);
+			const uint32_t busy = __ballot_sync(0xffffffffu, has);
+			const bool starving = nReady == 0u && !dry && (32 - __popc(busy) >= RT_REFILL_IDLE || busy == 0u);
+			const bool lastFlush = busy == 0u && nReady == 0u && dry && nDone > 0u;
+			if (nDone >= 32u || starving || lastFlush)
+			{
+				// ---- service: the epilogue of the finished rays, 32 at a time, then 32 new rays into the pool ----
+				uint32_t nD = nDone, nR = nReady, nF = pool_count(&P.nFree);
+				while (nD >= 32u || (nD > 0u && (starving || lastFlush)))
+				{
+					const uint32_t cnt = nD < 32u ? nD : 32u;
+					const bool valid = lane < cnt;
+					const uint32_t e = valid ? (uint32_t)P.doneQ[nD - cnt + lane] : 0u;
+					const PoolEntry &E = P.e[e];
+					const float4 o4 = E.o, d4 = E.d;
+					RayD ray;
+					ray.o = f3(o4), ray.d = f3(d4), ray.mtlrfr = o4.w, ray.skip = E.skip;
+					ray.type = (uint8_t)(E.meta & 0xFFu), ray.isInside = (uint8_t)((E.meta >> 8) & 0xFFu);
+					const Best best = { E.t, E.id, E.newobj };
+					trace_epilogue(S, F, L, N, ws, level, zNear, valid, E.slot, ray, d4.w, made, best);
+					if (valid) P.freeQ[nF + lane] = (uint8_t)e;
+					nF += cnt, nD -= cnt;
+				}
+				if (!dry && nR < 16u && nF > 0u)
+				{
+					const uint32_t want = batch < nF ? batch : nF;
+					const uint32_t base = warp_fetch(&ws->head_trace[level], want);
+					if (base >= n || frame_cancelled(ws, F))
+						dry = true, nR = frame_cancelled(ws, F) ? 0u : nR;
+					else
+					{
+						const uint32_t cnt = want < n - base ? want : n - base;
+						if (lane < cnt)
+						{
+							const uint32_t i = base + lane, e = (uint32_t)P.freeQ[nF - 1u - lane];
+							PoolEntry &E = P.e[e];
+							if (made)
+							{
+								F3 o;
+								const F3 d = primary_dir(F, i, o);
+								E.o = make_float4(o.x, o.y, o.z, 1.0f), E.d = make_float4(d.x, d.y, d.z, 1.0f);
+								E.skip = RT_ID_NONE, E.meta = (uint32_t)MY_RAY_BASERAY_;
+							}
+							else
+							{
+								const uint2 m = L.ray_meta[i];
+								E.o = L.ray_o[i], E.d = L.ray_d[i];
+								E.skip = m.x, E.meta = m.y & 0xFFFFu;
+							}
+							E.slot = i;
+							P.readyQ[nR + lane] = (uint8_t)e;
+						}
+						nF -= cnt, nR += cnt;
+						if (base + want >= n) dry = true;
+					}
+				}
+				__syncwarp();
+				if (lane == 0) P.nDone = nD, P.nReady = nR, P.nFree = nF;
+				__syncwarp();
+				continue;
+			}
+			if ((mN | mL | mA) == 0u)
+				break;
+			const int cN = __popc(mN), cL = __popc(mL), cA = __popc(mA);
+			if (cN >= cL && cN >= cA)
+			{
+				if (atNode) node_step<false, STATS>(S, Ln, stack, st);
+			}
+			else if (cL >= cA)
+			{
+				if (atLeaf) leaf_step<false, STATS>(S, Ln, stack, st);
+			}
+			else if (wantAdv)
+			{
+				__syncwarp(mA);
+				for (int round = 0; round < 2; ++round)
+				{
+					bool fin = false;
+					if ((Ln.flags & LF_HAS) && Ln.cur == RT_TRAV_DONE)
+						fin = advance_items<false, STATS>(S, Ln, st);
+					if (!pool_exchange<false>(P, Ln, mA, fin, 1e20f))
+						break;
+				}
+			}
+			__syncwarp();
+		}
+	}
+
+	// ---- phase B: shadow any-hit of the previous level's surfaces -----------------------------------
+	if (shadowOn)
+	{
+		__syncwarp();
+		const uint32_t lp = level - 1u;
+		const uint32_t nHit = ws->n_hit[lp];
+		const uint32_t n = nHit * F.n_enabled;
+		const uint32_t batch = fetch_batch(n);
+		const uint32_t rayType = (F.type == RT_TYPE_REFLECT || F.type == RT_TYPE_SHADOW) ? 0u : (uint32_t)MY_RAY_SHADOWRAY_;
+		if (lane == 0) P.nReady = 0, P.nDone = 0, P.nFree = 0;
+		__syncwarp();
+		int stack[RT_STACK];
+		Lane Ln;
+		Ln.flags = 0, Ln.cur = RT_TRAV_DONE, Ln.sp = 0, Ln.item = 0, Ln.entry = 0;
+		bool dry = n == 0u;
+		while (true)
+		{
+			const bool has = (Ln.flags & LF_HAS) != 0u;
+			const bool atNode = has && Ln.cur >= 0, atLeaf = has && Ln.cur < 0 && Ln.cur != RT_TRAV_DONE;
+			const uint32_t nReady = pool_count(&P.nReady);
+			const bool wantAdv = (has && Ln.cur == RT_TRAV_DONE) || (!has && nReady > 0u);
+			const uint32_t mN = __ballot_sync(0xffffffffu, atNode), mL = __ballot_sync(0xffffffffu, atLeaf), mA = __ballot_sync(0xffffffffu, wantAdv);
+			const uint32_t busy = __ballot_sync(0xffffffffu, has);
+			if (nReady == 0u && !dry && (32 - __popc(busy) >= RT_REFILL_IDLE || busy == 0u))
+			{
+				// ---- refill: 32 shadow rays set up by the whole warp (light direction, occlusion range) ----
+				const uint32_t base = warp_fetch(&ws->head_shadow[lp], batch);
+				uint32_t nR = 0;
+				if (base >= n || frame_cancelled(ws, F))
+					dry = true;
+				else
+				{
+					const uint32_t cnt = batch < n - base ? batch : n - base;
+					if (lane < cnt)
+					{
+						const uint32_t w = base + lane;
+						const uint32_t k = F.enabled_index[w / nHit], i = Lprev.hit_list[w % nHit] - 1u;
+						const float4 hp = Lprev.hit_p[i];
+						F3 dir;
+						float dis, lum;
+						light_dir(F.lights[k], f3(hp), dir, dis, lum);
+						PoolEntry &E = P.e[lane];
+						E.o = make_float4(hp.x, hp.y, hp.z, dis), E.d = make_float4(dir.x, dir.y, dir.z, 0.0f);
+						E.skip = Lprev.hit_id[i].y, E.meta = rayType;
+						E.slot = k * Lprev.capacity + i;
+					}
+					nR = cnt;
+					if (base + batch >= n) dry = true;
+				}
+				__syncwarp();
+				if (lane == 0) P.nReady = nR;
+				__syncwarp();
+				continue;
+			}
+			if ((mN | mL | mA) == 0u)
+				break;
+			const int cN = __popc(mN), cL = __popc(mL), cA = __popc(mA);
+			if (cN >= cL && cN >= cA)
+			{
+				if (atNode) node_step<true, STATS>(S, Ln, stack, st);
+			}
+			else if (cL >= cA)
+			{
+				if (atLeaf) leaf_step<true, STATS>(S, Ln, stack, st);
+			}
+			else if (wantAdv)
+			{
+				__syncwarp(mA);
+				for (int round = 0; round < 2; ++round)
+				{
+					if ((Ln.flags & LF_HAS) && Ln.cur == RT_TRAV_DONE && advance_items<true, STATS>(S, Ln, st))
+					{
+						Lprev.shadow[Ln.entry] = (Ln.flags & LF_OCCL) ? 1 : 0;
+						Ln.flags = 0;
+					}
+					if (!pool_exchange<true>(P, Ln, mA, false, 0.0f))
+						break;
+				}
+			}
+			__syncwarp();
 		}
 	}
 	flush_stats<STATS>(ws, st);
@@ -1243,10 +1602,18 @@ static int traversal_ctas_per_sm()
 }
 
 void rtk_wave(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const LevelBuf &N, const LevelBuf &Lprev, WaveState *ws,
-	uint32_t level, bool traceOn, bool shadowOn, float zNear, uint32_t maxItems, unsigned sms, bool stats, unsigned ctasPerSm)
+	uint32_t level, bool traceOn, bool shadowOn, float zNear, uint32_t maxItems, unsigned sms, bool stats, unsigned ctasPerSm, bool async)
 {
 	const int occ = traversal_ctas_per_sm();
 	const unsigned g = grid_for(maxItems, RT_BLOCK, sms * (ctasPerSm && (int)ctasPerSm < occ ? ctasPerSm : occ));   // persistent: all CTAs resident
+	if (async)
+	{
+		// lane-asynchronous walk (rt_async.cuh); shadow destinations are 32-bit indices there
+		if (stats) k_wave_async<true, RT_CTAS_PER_SM><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+		else if (occ == 6) k_wave_async<false, 6><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+		else k_wave_async<false, RT_CTAS_PER_SM><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+		return;
+	}
 	if (stats) k_wave<true, RT_CTAS_PER_SM><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
 	else if (occ == 4) k_wave<false, 4><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
 	else if (occ == 6) k_wave<false, 6><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);

@@ -68,6 +68,31 @@ __device__ __forceinline__ bool slab_hit_nf(float nx, float ny, float nz, float 
 	return t0 <= t1 * 1.0000005f;
 }
 
+// FMA form of the same test: (plane - o) * id  ==  plane * id + (-(o * id)), one FFMA per plane instead of FADD + FMUL
+// (24 instead of 48 FP instructions per 4-wide node; the box test is the busiest code of the traversal kernels).
+// The product o * id is rounded once per ray, so every plane distance carries an ABSOLUTE error of up to
+// |o * id| * 2^-24 on top of the FFMA's own rounding; `eps` (2^-22 * max over the axes of |o * id|, computed once per
+// ray) widens the interval by more than both.  The test stays a conservative cull: it may keep a box the exact test
+// would drop, never the other way round.  Rays for which eps is not small (a direction component that is zero or
+// nearly zero: id = inf or huge, e.g. the centre column / centre row of every frame) use the exact form above; the
+// choice is made per warp step (RT_SLAB_FMA_OK), so the branch is uniform.
+__device__ __forceinline__ bool slab_hit_fma(float nx, float ny, float nz, float fx, float fy, float fz,
+	const F3 &oi, const F3 &id, float tbest, float eps, float &tnear)
+{
+	const float ax = __fmaf_rn(nx, id.x, oi.x), ay = __fmaf_rn(ny, id.y, oi.y), az = __fmaf_rn(nz, id.z, oi.z);
+	const float bx = __fmaf_rn(fx, id.x, oi.x), by = __fmaf_rn(fy, id.y, oi.y), bz = __fmaf_rn(fz, id.z, oi.z);
+	const float t0 = fmaxf(fmaxf(ax, ay), fmaxf(az, 0.0f));
+	const float t1 = fminf(fminf(bx, by), fminf(bz, tbest));
+	tnear = t0;
+	return t0 <= __fmaf_rn(t1, 1.0000005f, eps);
+}
+// Measured (profiles/r2_fma_slab_ab.txt): -5 % warp instructions in the wave kernels, +1 % rays/s, k_frame 4 % slower
+// (four more live registers at the 64-register cap) -- the walk waits on node loads, not on issue slots.  Off by default.
+#ifndef RT_SLAB_FMA
+#define RT_SLAB_FMA 0
+#endif
+#define RT_SLAB_EPS_MAX 0.01f   // rays whose eps is not below this (or NaN) take the exact form
+
 // Per-ray cache of the reference's part-level predicate (BorderTestEx), so the replay costs one
 // evaluation per (ray, part) that produces a candidate.
 struct PartCache
@@ -205,6 +230,14 @@ __device__ __forceinline__ void test_prim(const SceneDev &S, const RayD &ray, ui
 // interleaves with box tests); which phase runs next is voted per step, see below.  The stack lives
 // in local memory (L1-resident, one 128-byte line per depth and warp) so no shared memory is
 // reserved and occupancy is bound by registers only.
+template<bool ANY> struct StackSlot { typedef uint2 T; };
+template<> struct StackSlot<true> { typedef int T; };
+__device__ __forceinline__ void slot_put(int &s, int link, float) { s = link; }
+__device__ __forceinline__ void slot_put(uint2 &s, int link, float t) { s = make_uint2((uint32_t)link, __float_as_uint(t)); }
+__device__ __forceinline__ int slot_link(const int &s) { return s; }
+__device__ __forceinline__ int slot_link(const uint2 &s) { return (int)s.x; }
+__device__ __forceinline__ float slot_t(const int &) { return 0.0f; }
+__device__ __forceinline__ float slot_t(const uint2 &s) { return __uint_as_float(s.y); }
 #define RT_TRAV_DONE (-1)   // never a valid leaf code: that would be first = 2^28-1, count = 8
 
 #ifndef RT_EARLY_HOLD
@@ -220,10 +253,9 @@ __device__ __forceinline__ void traverse(const SceneDev &S, const RayD &ray, con
 	pc.part = 0xFFFFFFFFu, pc.mask = 0;
 	bool slow = false;
 	const uint32_t idBefore = best.id;
-	int stack[RT_STACK];
-#if RT_CULL_ON_POP
-	float stackT[RT_STACK];   // entry distance of each stacked subtree (closest hit: culled again on pop)
-#endif
+	// closest hit: link + entry distance of each stacked subtree in ONE 64-bit slot (one STL.64 per push, one LDL.64
+	// per pop; the subtree is culled again on pop); any-hit: links only
+	typename StackSlot<ANY>::T stack[RT_STACK];
 	int sp = 0;
 	int cur = root;
 	// byte offsets of the near / far plane vectors inside a BvhNode4 for this ray's direction signs
@@ -243,6 +275,19 @@ __device__ __forceinline__ void traverse(const SceneDev &S, const RayD &ray, con
 	// RT_EARLY_HOLD steps, and the caller publishes their results while the rest keeps walking.
 	uint32_t wmask = __activemask();
 	uint32_t waited = 0;
+#if RT_SLAB_FMA
+	const F3 oi = f3(-(ray.o.x * idir.x), -(ray.o.y * idir.y), -(ray.o.z * idir.z));
+	float eps = fmaxf(fmaxf(fabsf(oi.x), fabsf(oi.y)), fabsf(oi.z)) * 2.4e-7f;
+	// every axis is checked on its own: fmaxf drops a NaN (0 * inf: an origin coordinate of exactly 0 with a direction
+	// component of exactly 0 -- the centre column of a frame whose camera sits at x = 0), and such an axis would then
+	// constrain nothing in the FMA form
+	const float lim = RT_SLAB_EPS_MAX / 2.4e-7f;
+	const bool fmaOk = fabsf(oi.x) < lim && fabsf(oi.y) < lim && fabsf(oi.z) < lim;
+	if (!fmaOk) eps = 0.0f;   // such a lane only ever runs the exact form (the lanes that entered together all take it)
+	const bool useFma = __ballot_sync(wmask, !fmaOk) == 0u;
+#else
+	const float eps = 0.0f;
+#endif
 	while (true)
 	{
 		const bool atNode = cur >= 0, atLeaf = cur < 0 && cur != RT_TRAV_DONE;
@@ -276,10 +321,23 @@ __device__ __forceinline__ void traverse(const SceneDev &S, const RayD &ray, con
 				const int4 link = __ldg((const int4 *)(n + 96));
 				if (STATS) ++st.nodes;
 				float t0, t1, t2, t3;
-				const bool h0 = slab_hit_nf(nx.x, ny.x, nz.x, fx.x, fy.x, fz.x, ray.o, idir, best.t, t0);
-				const bool h1 = slab_hit_nf(nx.y, ny.y, nz.y, fx.y, fy.y, fz.y, ray.o, idir, best.t, t1);
-				const bool h2 = slab_hit_nf(nx.z, ny.z, nz.z, fx.z, fy.z, fz.z, ray.o, idir, best.t, t2);
-				const bool h3 = slab_hit_nf(nx.w, ny.w, nz.w, fx.w, fy.w, fz.w, ray.o, idir, best.t, t3);
+				bool h0, h1, h2, h3;
+#if RT_SLAB_FMA
+				if (useFma)
+				{
+					h0 = slab_hit_fma(nx.x, ny.x, nz.x, fx.x, fy.x, fz.x, oi, idir, best.t, eps, t0);
+					h1 = slab_hit_fma(nx.y, ny.y, nz.y, fx.y, fy.y, fz.y, oi, idir, best.t, eps, t1);
+					h2 = slab_hit_fma(nx.z, ny.z, nz.z, fx.z, fy.z, fz.z, oi, idir, best.t, eps, t2);
+					h3 = slab_hit_fma(nx.w, ny.w, nz.w, fx.w, fy.w, fz.w, oi, idir, best.t, eps, t3);
+				}
+				else
+#endif
+				{
+					h0 = slab_hit_nf(nx.x, ny.x, nz.x, fx.x, fy.x, fz.x, ray.o, idir, best.t, t0);
+					h1 = slab_hit_nf(nx.y, ny.y, nz.y, fx.y, fy.y, fz.y, ray.o, idir, best.t, t1);
+					h2 = slab_hit_nf(nx.z, ny.z, nz.z, fx.z, fy.z, fz.z, ray.o, idir, best.t, t2);
+					h3 = slab_hit_nf(nx.w, ny.w, nz.w, fx.w, fy.w, fz.w, ray.o, idir, best.t, t3);
+				}
 				// nearest hit child first, the other hit children go on the stack
 				const float inf = __int_as_float(0x7f800000);
 				float bt = h0 ? t0 : inf;
@@ -289,30 +347,19 @@ __device__ __forceinline__ void traverse(const SceneDev &S, const RayD &ray, con
 				if (h3 && t3 < bt) bt = t3, bi = 3;
 				if (!(h0 | h1 | h2 | h3))
 				{
-#if RT_CULL_ON_POP
 					cur = RT_TRAV_DONE;
 					while (sp)
 					{
-						--sp;
-						if (ANY || stackT[sp] <= best.t) { cur = stack[sp]; break; }
+						const typename StackSlot<ANY>::T e = stack[--sp];
+						if (ANY || slot_t(e) <= best.t + eps) { cur = slot_link(e); break; }
 					}
-#else
-					cur = sp ? stack[--sp] : RT_TRAV_DONE;
-#endif
 				}
 				else
 				{
-#if RT_CULL_ON_POP
-					if (h0 && bi != 0) { stack[sp] = link.x; if (!ANY) stackT[sp] = t0; ++sp; }
-					if (h1 && bi != 1) { stack[sp] = link.y; if (!ANY) stackT[sp] = t1; ++sp; }
-					if (h2 && bi != 2) { stack[sp] = link.z; if (!ANY) stackT[sp] = t2; ++sp; }
-					if (h3 && bi != 3) { stack[sp] = link.w; if (!ANY) stackT[sp] = t3; ++sp; }
-#else
-					if (h0 && bi != 0) stack[sp++] = link.x;
-					if (h1 && bi != 1) stack[sp++] = link.y;
-					if (h2 && bi != 2) stack[sp++] = link.z;
-					if (h3 && bi != 3) stack[sp++] = link.w;
-#endif
+					if (h0 && bi != 0) slot_put(stack[sp++], link.x, t0);
+					if (h1 && bi != 1) slot_put(stack[sp++], link.y, t1);
+					if (h2 && bi != 2) slot_put(stack[sp++], link.z, t2);
+					if (h3 && bi != 3) slot_put(stack[sp++], link.w, t3);
 					cur = bi == 0 ? link.x : bi == 1 ? link.y : bi == 2 ? link.z : link.w;
 				}
 			}
@@ -334,15 +381,11 @@ __device__ __forceinline__ void traverse(const SceneDev &S, const RayD &ray, con
 			cur = RT_TRAV_DONE;
 			if (ANY && done)
 				sp = 0;   // occluded: nothing else to look at, but stay in the vote until the other lanes are through
-#if RT_CULL_ON_POP
 			while (sp)
 			{
-				--sp;
-				if (ANY || stackT[sp] <= best.t) { cur = stack[sp]; break; }
+				const typename StackSlot<ANY>::T e = stack[--sp];
+				if (ANY || slot_t(e) <= best.t + eps) { cur = slot_link(e); break; }
 			}
-#else
-			if (sp) cur = stack[--sp];
-#endif
 		}
 	}
 	if (ANY && done)

@@ -332,16 +332,17 @@ template<class SceneT> inline void build_t_inside(SceneT &scene, const SceneArgs
 }
 
 // ---- camera orbit: the frame stream of the throughput benchmark ----------------------------------------
-// Camera k of K: the scene's own camera dollied along a closed path (Camera::move only -- translations along
-// u, v, n, 3DElement.cpp:585-590 -- so both arms compute it with the same float additions).  Camera 0 is
-// exactly `base`: its frame is the configuration's own frame (the one the golden hashes pin).
+// Camera k of K: the scene's own camera dollied along a small closed path -- up to 1 unit to either side, 0.5 up and
+// 1 forward, so the frames stay close to the configuration's own view and cost -- with Camera::move only
+// (translations along u, v, n, 3DElement.cpp:585-590: both arms compute it with the same float additions).
+// Camera 0 is exactly `base`: its frame is the configuration's own frame (the one the golden hashes pin).
 template<class CameraT> inline CameraT orbit_camera(const CameraT &base, int k, int K)
 {
 	CameraT c = base;
 	if (K > 1 && k % K != 0)
 	{
 		const double a = 2.0 * 3.14159265358979323846 * (k % K) / K;
-		c.move((float)(2.0 * sin(a)), (float)(0.6 * (1.0 - cos(a))), (float)(1.5 * (1.0 - cos(a))));
+		c.move((float)(1.0 * sin(a)), (float)(0.25 * (1.0 - cos(a))), (float)(0.5 * (1.0 - cos(a))));
 	}
 	return c;
 }
