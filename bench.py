@@ -54,12 +54,19 @@ CONFIGS = {
     "c2": ("c2", 1920, 1080, 5, 0, 0, 32, "1024 spheres + plane, 4 point lights, 1920x1080, depth 5"),
     "c3": ("c3", 1920, 1080, 5, 0, 0, 32, "1036800-triangle Model + plane, 2 lights, 1920x1080, depth 5, GPU LBVH"),
     "c4": ("c4", 3840, 2160, 8, 0, 0, 4, "4147200-triangle Model + 64 glass + 6 mirror spheres + plane, 3840x2160, depth 8"),
+    # BASELINE configs[4]: the c4 scene at 8K, 16 jittered samples per pixel accumulated on the GPU; a step is ONE frame
+    "c5": ("c5", 7680, 4320, 8, 0, 0, 1, "c4 scene at 7680x4320, 16 jittered samples per pixel (4x4 stratified table, seed 0), integer mean of the quantised samples, depth 8"),
 }
+SPP_SIDE = {"c5": 4}
 
 
 def workload_config(name):
     """The `config` object of the JSON line -- identical for both arms (the driver compares them)."""
     scene, w, h, level, n, parts, sframes, desc = CONFIGS[name]
+    if name in SPP_SIDE:
+        return {"workload": f"{name}: {desc}", "step": "one supersampled frame", "step_frames": 1, "samples_per_pixel": SPP_SIDE[name] ** 2,
+                "pixels_per_frame": (w // 64 * 64) * (h // 64 * 64),
+                "l2_policy": "every band launch holds ~8 M sample rays per level (> 1 GB of queues) plus a 640 MB BVH: far beyond the 126 MB L2; no flush needed"}
     return {"workload": f"{name}: {desc}", "step": f"{sframes} frames of a {sframes}-camera orbit around the scene (camera 0 = the configuration's own camera), one framebuffer per frame",
             "step_frames": sframes, "pixels_per_frame": (w // 64 * 64) * (h // 64 * 64),
             "l2_policy": "per-step working set (ray/hit queues of ~8 M pixels per launch + BVH + triangles, > 2 GB touched per launch) exceeds the 126 MB L2; no flush needed"}
@@ -178,7 +185,7 @@ def run_reference(args):
     """--impl reference: the reference's own CPU tracer on the host cores (rank 0 only).
 
     Each step traces a STRATIFIED sample of 64x64 tiles (every k-th tile of the frame in row-major tile order, so
-    all tile rows are covered) of one frame of the orbit -- step s uses camera s of the orbit -- through the
+    all tile rows are covered) of one frame of the orbit -- the K timed steps are spread evenly over the orbit's cameras -- through the
     reference's per-pixel entry RTfrac on all host threads (64-pixel rows handed out one at a time, so every
     thread works).  The reference's single-threaded per-frame RTPrepare is timed apart and charged in proportion:
     step seconds = trace_s + prepare_s * sample_tiles / frame_tiles, which is what a full frame costs per tile.
@@ -200,8 +207,8 @@ def run_reference(args):
                                                        "--repeat", args.steps, "--warmup", args.warmup)).decode().strip().splitlines()[-1])
         frac = tiles / frame_tiles
         secs = [t + p * frac for t, p in zip(j["step_s"], j["prepare_s"])]
-        rays, px = j["rays_per_step"], j["pixels"]
-        sample = (f"{tiles} of {frame_tiles} 64x64 tiles, stratified over the {w}x{h} frame ({px} px, {rays} rays in the counted pass), one orbit camera per step, "
+        rays, px = sum(j["rays_s"]) / len(j["rays_s"]), j["pixels"]      # every timed pass counts its own rays
+        sample = (f"{tiles} of {frame_tiles} 64x64 tiles, stratified over the {w}x{h} frame ({px} px, {rays:.0f} rays per step on average), one orbit camera per step (spread evenly over the orbit), "
                   f"{cores} threads; step seconds = trace + RTPrepare ({sum(j['prepare_s']) / len(j['prepare_s']):.3f} s per frame) x {frac:.3f}")
     else:
         kind = "port"
@@ -238,14 +245,15 @@ def cpu_baseline(args, gpu_hash):
     cores = min(32, os.cpu_count() or 1)
     rays_frame = (golden_fullsize(name) or {}).get("rays", {}).get("total")
     try:
-        if os.path.exists(REF_BIN) and name != "c4":
+        if os.path.exists(REF_BIN) and name not in ("c4", "c5"):
             j = json.loads(subprocess.check_output(ref_cmd(name, cores, "--repeat", 1), timeout=1500).decode().strip().splitlines()[-1])
             wall, use = j["wall_s"][0], j["useTime_s"][0]
             return {"value": rays_frame / wall / 1e6 if rays_frame else None, "unit": "Mrays/s", "cores": cores, "kind": "reference",
                     "sample": f"one full {w}x{h} frame through the reference's RayTracer::start() ({rays_frame} rays): wall {wall:.2f} s, useTime {use:.2f} s",
                     "wall_s": wall, "useTime_s": use, "frame_hash": j["hash"], "same_frame_as_gpu": (j["hash"] == gpu_hash) if gpu_hash else None}
         if os.path.exists(REF_BIN):
-            # c4: a full frame is ~an hour of CPU -- stratified tiles through the per-pixel entry, labelled as such
+            # c4 / c5: a full frame is hours of CPU -- stratified tiles through the per-pixel entry, labelled as such (SURVEY
+            # 8d); c5's samples are reference frames of their own, so one sample per pixel gives the same rays/s
             frame_tiles, tiles = (w // 64) * (h // 64), 60
             j = json.loads(subprocess.check_output(ref_cmd(name, cores, "--tiles", tiles, "--stratified", "--counts", "--repeat", 1), timeout=1500).decode().strip().splitlines()[-1])
             secs = j["step_s"][0] + j["prepare_s"][0] * tiles / frame_tiles
@@ -263,6 +271,172 @@ def cpu_baseline(args, gpu_hash):
                 "sample": f"oracle port, interleaved 8-row tiles rank 3 of 16 ({c.primary} px, {rays} rays) of the {w}x{h} frame, 1 pass"}
     except Exception as e:   # a baseline failure must not hide the GPU numbers
         return {"value": None, "unit": "Mrays/s", "cores": cores, "kind": "unavailable", "sample": repr(e)[:200]}
+
+
+def bench_supersampled(args, sc, rank, world, local, dev, dist):
+    """c5: 7680x4320, 16 jittered samples per pixel, image-space shards over N GPUs.  One step = one frame through
+    rt_render_supersampled (the samples of a band of row tiles are one frame batch + an integer-mean kernel, band after
+    band, nothing leaves the GPU), then this rank's rows go to rank 0's frame over NVLink (rt_push_rows)."""
+    import numpy as np
+    import torch
+
+    import raytrace_b200 as R
+    from raytrace_b200.distributed import FrameLanding, bands_of
+    from raytrace_b200.supersample import device_table
+    scene, w, h, level, n, parts, S, desc = CONFIGS[args.config]
+    table = device_table(SPP_SIDE[args.config], 0)
+    ns = len(table)
+    cams = (R.Camera * ns)()
+    for k, (dx, dy) in enumerate(table):
+        cams[k] = sc.jittered_camera(dx, dy)
+
+    def ck(rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what}: {R.rt.rt_last_error().decode()}")
+
+    main_stream = torch.cuda.current_stream(dev)
+    ctx = C.c_void_p()
+    ck(R.rt.rt_create(local, C.byref(ctx)), "rt_create")
+    ck(R.rt.rt_set_stream(ctx, C.c_void_p(main_stream.cuda_stream)), "rt_set_stream")
+    ck(R.rt.rt_upload_scene(ctx, sc.flatten()), "rt_upload_scene")
+    tile_rows = 8 if world > 1 else 64
+    serp = world > 1 and args.shard_order == "serpentine"
+    flags = R.RT_FLAG_SERPENTINE if serp else 0
+    params = R.RenderParams(R.MY_MODEL_RAYTRACE, level, rank, world, flags, tile_rows, 0, 0)
+    landing = FrameLanding(ctx, w, h, rank, world) if world > 1 else None
+    if landing is not None and rank == 0:
+        ptr, nbytes = landing.device_ptr()
+        ck(R.rt.rt_set_output(ctx, C.c_void_p(ptr), nbytes), "rt_set_output")
+
+    def frame():
+        ck(R.rt.rt_render_supersampled(ctx, C.byref(params), ns, cams), "rt_render_supersampled")
+        if landing is not None:
+            landing.push(ctx)
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(max(1, min(args.warmup, 2))):     # a frame is seconds of GPU time: two warm-up frames at most
+        frame()
+    sync_all()
+    cnt = R.Counters()
+    ck(R.rt.rt_read_counters(ctx, C.byref(cnt)), "rt_read_counters")
+    rays_local = cnt.primary + cnt.shadow + cnt.reflect + cnt.refract
+    launches = cnt.launches
+    rays_t = torch.tensor([rays_local], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(rays_t)
+    rays_frame = int(rays_t.item())
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(main_stream)
+    for _ in range(args.steps):
+        frame()
+    e1.record(main_stream)
+    sync_all()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    mine_t = torch.tensor([e0.elapsed_time(e1) / args.steps, float(rays_local)], dtype=torch.float64, device=dev)
+    per_rank = [torch.zeros_like(mine_t) for _ in range(world)]
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_gather(per_rank, mine_t)
+    else:
+        per_rank = [mine_t]
+    per_rank = [{"rank": r, "ms_per_step": float(t[0].item()), "rays_per_step": int(t[1].item())} for r, t in enumerate(per_rank)]
+    ms_total = float(ms.item())
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- frame check: the first band of this rank's shard, sample by sample (tile window, one frame per launch), meaned on
+    #      the host, against the same rows of the frame the device accumulated
+    got = np.empty((h, w, 3), dtype=np.uint8)
+    ck(R.rt.rt_read_output(ctx, got.ctypes.data_as(C.c_void_p), w * 3), "rt_read_output")
+    frame_hash = R.fnv1a64(got) if rank == 0 else None      # rank 0: the assembled frame (its landing buffer)
+    mine = bands_of(rank, world, h, tile_rows, serp)
+    ntile = max(1, 64 // tile_rows)
+    rows = np.array([y for t in mine[:ntile] for y in range(t * tile_rows, (t + 1) * tile_rows)])
+    probe = C.c_void_p()
+    ck(R.rt.rt_create_shared(ctx, C.byref(probe)), "rt_create_shared")
+    acc = np.zeros((len(rows), w, 3), dtype=np.uint32)
+    one = np.empty((h, w, 3), dtype=np.uint8)
+    win = R.RenderParams(R.MY_MODEL_RAYTRACE, level, rank, world, flags, tile_rows, 0, ntile)
+    for k in range(ns):
+        ck(R.rt.rt_render_batch_async(probe, C.byref(win), 1, C.cast(C.byref(cams, k * C.sizeof(R.Camera)), C.POINTER(R.Camera)), None), "rt_render_batch_async")
+        ck(R.rt.rt_read_batch_output(probe, 0, one.ctypes.data_as(C.c_void_p), w * 3, 0), "rt_read_batch_output")
+        acc += one[rows]
+    same = bool(np.array_equal((acc // ns).astype(np.uint8), got[rows]))
+    R.rt.rt_destroy(probe)
+    ok_t = torch.tensor([1 if same else 0], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+    # ---- roofline of one counted frame (stats kernels), untimed
+    pstats = R.RenderParams(R.MY_MODEL_RAYTRACE, level, rank, world, flags | R.RT_FLAG_STATS, tile_rows, 0, 0)
+    ck(R.rt.rt_render_supersampled(ctx, C.byref(params), ns, cams), "rt_render_supersampled")
+    ck(R.rt.rt_read_counters(ctx, C.byref(cnt)), "rt_read_counters")
+    stage = {"traverse": cnt.trace_ms, "shade": cnt.shade_ms, "other": cnt.other_ms, "render": cnt.render_ms}
+    ck(R.rt.rt_render_supersampled(ctx, C.byref(pstats), ns, cams), "rt_render_supersampled(stats)")
+    cs = R.Counters()
+    ck(R.rt.rt_read_counters(ctx, C.byref(cs)), "rt_read_counters")
+    sync_all()
+    if landing is not None:
+        landing.close()
+    R.rt.rt_destroy(ctx)
+    # ---- e2e: RayTracer::start() with `samples` set, host frame buffer (D2H of this rank's rows every step)
+    e2e = None
+    if not args.no_e2e:
+        t = R.RayTracer(sc, device=local)
+        t.maxLevel = level
+        t.set_samples(table)
+        kw = dict(flags=flags, rank=rank, world=world, tile_rows=tile_rows)
+        t.render(R.MY_MODEL_RAYTRACE, **kw)
+        t.render(R.MY_MODEL_RAYTRACE, **kw)
+        sync_all()
+        up0, dn0, up1, dn1 = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        R.rt.rt_transfer_totals(C.byref(up0), C.byref(dn0))
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            t.start(R.MY_MODEL_RAYTRACE, **kw)
+            t.wait()
+        e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        R.rt.rt_transfer_totals(C.byref(up1), C.byref(dn1))
+        if world > 1:
+            dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+        e2e = {"value": rays_frame * args.steps / float(e2e_s.item()) / 1e6, "unit": "Mrays/s", "ms_per_step": float(e2e_s.item()) / args.steps * 1e3,
+               "h2d_bytes_per_step": (up1.value - up0.value) // args.steps, "d2h_bytes_per_step": (dn1.value - dn0.value) // args.steps,
+               "bytes_counted_on": "rank 0" if world > 1 else "the one GPU", "calls_per_step": 1}
+        del t
+    if rank == 0:
+        peak, peak_src, hbm_peak = sm_peak_fp32_tflops()
+        flops = cs.nodes_visited * 4 * 22 + cs.tri_tests * 47 + cs.prim_tests * 23
+        achieved = flops / (stage["traverse"] * 1e-3) / 1e12 if stage["traverse"] > 0 else 0.0
+        slow = max(per_rank, key=lambda r: r["ms_per_step"])
+        line = {"metric": "Mrays/s", "value": rays_frame * args.steps / (ms_total * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": workload_config(args.config), "ms_per_frame": ms_total / args.steps,
+                "run": {"rays_per_step": rays_frame, "sample_rays_per_pixel": rays_frame / ((w // 64 * 64) * (h // 64 * 64)),
+                        "parallelism": f"image-space: interleaved {tile_rows}-row tiles over {world} GPUs, rows pushed into rank 0's frame over NVLink P2P" if world > 1 else "single GPU",
+                        "kernel_launches_per_frame": launches, "slowest_rank": slow["rank"], "slowest_rank_ms_per_step": slow["ms_per_step"]},
+                "frame_check": {"what": "rows of the first band of every rank's shard: device-accumulated mean == host mean of the 16 samples rendered one per launch",
+                                "ok": bool(ok_t.item()), "status": "ok" if ok_t.item() else "MISMATCH", "frame_hash": frame_hash,
+                                "expected": None, "expected_source": "no CPU frame at this size (16 x 33 M pixels at depth 8 is days of reference time); the definition is pinned at test size by tests/test_gpu_timed_path.py"},
+                "gpu_launches": launches * args.steps,
+                "roofline": {"bound": "fp32_issue", "kernel": "k_wave (the band launches of one supersampled frame)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                             "frac": achieved / peak, "peak_source": f"148 SMs x 128 lanes x {peak_src} (of measured)", "traffic": None,
+                             "flops_per_launch": flops, "nodes_per_ray": cs.nodes_visited / max(rays_local, 1), "tri_tests_per_ray": cs.tri_tests / max(rays_local, 1),
+                             "stage_ms_one_frame": stage},
+                "clocks": clocks, "per_rank": per_rank,
+                "build": {"upload_ms": cs.upload_ms, "lbvh_build_ms": cs.build_ms, "bvh_nodes": cs.bvh_nodes, "bvh_depth": cs.bvh_depth}}
+        if e2e is not None:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, None)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():
@@ -307,6 +481,8 @@ def main():
     tmpdir = f"/tmp/rt_bench_{rank}"
     os.makedirs(tmpdir, exist_ok=True)
     sc = R.Scene(scene, w, h, n, parts, tmpdir=tmpdir)
+    if args.config in SPP_SIDE:
+        return bench_supersampled(args, sc, rank, world, local, dev, dist)
     cams = (R.Camera * S)()
     for k in range(S):
         cams[k] = sc.orbit_camera(k, S)
@@ -548,18 +724,26 @@ def main():
             t.coalesce = coalesce
             tracers.append(t)
 
+        host = {"wait": 0.0, "start": 0.0, "calls": 0}
+
         def e2e_frames(nframes, k0=0):
             for k in range(k0, k0 + nframes):
                 t = tracers[k % M_e2e]
+                a = time.perf_counter()
                 t.wait()                             # that tracer's previous frame is in RayTracer::output
+                b = time.perf_counter()
                 cpos = cams[k % S].position
                 sc.set_camera_position(cpos.x, cpos.y, cpos.z)
                 t.start(R.MY_MODEL_RAYTRACE, flags=shard_flags, rank=rank, world=world, tile_rows=tile_rows)
+                host["wait"] += b - a
+                host["start"] += time.perf_counter() - b
+                host["calls"] += 1
             for t in tracers:
                 t.wait()
 
         e2e_frames(max(2 * M_e2e, S))
         sync_all()
+        host.update(wait=0.0, start=0.0, calls=0)
         up0, dn0, up1, dn1 = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
         R.rt.rt_transfer_totals(C.byref(up0), C.byref(dn0))      # bytes the library itself copies, counted where it enqueues them
         t0 = time.perf_counter()
@@ -572,7 +756,8 @@ def main():
         e2e = {"value": rays_step * args.steps / float(e2e_s.item()) / 1e6, "unit": "Mrays/s", "ms_per_step": float(e2e_s.item()) / args.steps * 1e3,
                "h2d_bytes_per_step": (up1.value - up0.value) // args.steps, "d2h_bytes_per_step": (dn1.value - dn0.value) // args.steps,
                "bytes_counted_on": "rank 0" if world > 1 else "the one GPU",
-               "calls_per_step": S, "tracers_in_flight": M_e2e, "coalesced_starts": coalesce}
+               "calls_per_step": S, "tracers_in_flight": M_e2e, "coalesced_starts": coalesce,
+               "host_us_per_start_call": host["start"] / max(host["calls"], 1) * 1e6, "host_us_waiting_per_call": host["wait"] / max(host["calls"], 1) * 1e6}
         del tracers
 
     if rank == 0:

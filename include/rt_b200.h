@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define RT_ABI_VERSION 1
+#define RT_ABI_VERSION 2   /* 2: rt_render_params gained the tile window, rt_render_supersampled, rt_transfer_totals */
 
 /* error codes */
 #define RT_OK            0
@@ -162,6 +162,8 @@ typedef struct
 	uint32_t rank, world; /* image-space shard: row tile t is rendered iff t % world == rank (RT_FLAG_SERPENTINE: see below); world=0 or 1 = whole frame */
 	uint32_t flags;       /* RT_FLAG_* */
 	uint32_t tile_rows;   /* height of a shard tile: 8, 16, 32 or 64 rows (0 = 64); finer tiles balance the ranks better */
+	uint32_t tile_first;  /* window into the shard's own tiles: only its tiles tile_first .. tile_first + tile_count - 1 (counted in */
+	uint32_t tile_count;  /* the order it owns them, top row of the frame last) are rendered; tile_count = 0: all of them */
 } rt_render_params;
 
 #define RT_FLAG_HIT_IDS   0x1   /* keep primary closest-hit identities for rt_read_hit_ids */
@@ -216,6 +218,8 @@ typedef struct
 	uint32_t frame_sched;                            /* 1: the last frame used the whole-frame persistent kernel, 0: per-level waves */
 	uint64_t h2d_bytes;    /* host->device bytes of the last rt_upload_scene + rt_render_async */
 	uint64_t d2h_bytes;    /* device->host bytes of the last frame (counters + rt_read_output) */
+	uint32_t bvh_refit;    /* 1: the last rt_upload_scene refitted the Model BVHs (position-only edit) instead of rebuilding them; build_ms is then the refit */
+	uint32_t pad0;
 } rt_counters;
 
 const char *rt_last_error(void);
@@ -254,6 +258,17 @@ int rt_render_batch_async(rt_ctx *ctx, const rt_render_params *params, uint32_t 
 /* frame `frame` of the last batch -> host.  rows_only bit 0: copy only the shard's rows (see rt_read_output_rows);
  * bit 1: enqueue the copy and return -- a later call without bit 1 waits for all of them (they run in order) */
 int rt_read_batch_output(rt_ctx *ctx, uint32_t frame, uint8_t *rgb, size_t stride, int rows_only);
+/* Jittered supersampling (BASELINE configs[4]: 16 samples per pixel): sample s of every pixel is seen through
+ * sample_cameras[s] -- the caller's camera with its forward vector offset by a sub-pixel step, n' = n + u*(dx*dp) +
+ * v*(dy*dp), the way primary rays are made in RayTracer.cpp:20-27 -- every sample is quantised by Color::put
+ * (3DElement.cpp:463-468) exactly like a frame of its own, and the frame is the INTEGER mean of the n_samples bytes per
+ * channel (floor), i.e. bit-identical to averaging n_samples reference renders.  On the device the samples of a band of
+ * row tiles are ONE frame batch (they share the ray queues) followed by an averaging kernel; a frame too large for one
+ * launch (8K x 16 spp = 527 M primary rays) is walked band by band with the tile window of rt_render_params, so the
+ * sample accumulation never leaves the GPU.  The result lands in the context's framebuffer (rt_read_output,
+ * rt_set_output, rt_push_rows work as after rt_render_async); counters are summed over the bands.  Synchronous.
+ * n_samples <= 64. */
+int rt_render_supersampled(rt_ctx *ctx, const rt_render_params *params, uint32_t n_samples, const rt_camera *sample_cameras);
 /* replaces the isFinish / useTime polling protocol (RayTracer.h:47-48) */
 int rt_poll(rt_ctx *ctx, int *done, double *seconds);
 int rt_wait(rt_ctx *ctx, double *seconds);

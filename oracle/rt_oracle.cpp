@@ -762,9 +762,14 @@ int rto_render(const rt_scene_desc *scene, const rt_render_params *params, uint8
 	// which rank renders image row y (include/rt_b200.h: tile t -> rank t % world; RT_FLAG_SERPENTINE deals the
 	// odd groups of `world` tiles in reverse order)
 	const bool serpentine = (params->flags & RT_FLAG_SERPENTINE) && world > 1;
+	// tile window (rt_render_params::tile_first / tile_count): only the shard's own tiles first .. first + count - 1;
+	// a row outside it has no owner here
+	const uint32_t tileFirst = params->tile_first, tileCount = params->tile_count;
 	auto ownerOfRow = [=](uint32_t y) -> uint32_t
 	{
 		const uint32_t t = y / tileRows, g = t / world, i = t % world;
+		if (g < tileFirst || (tileCount && g >= tileFirst + tileCount))
+			return 0xFFFFFFFFu;   // tile g*world + .. is the g-th tile of whichever rank owns it
 		return (serpentine && (g & 1u)) ? world - 1u - i : i;
 	};
 	if (threads < 1) threads = 1;

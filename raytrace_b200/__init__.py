@@ -103,6 +103,12 @@ class Scene:
     def set_camera_position(self, x, y, z):
         return rth.rth_scene_camera_set_position(self._h, x, y, z)
 
+    def jittered_camera(self, dx, dy) -> Camera:
+        """the sample camera of sub-pixel offset (dx, dy) (scenes.h jittered_camera); the Scene is not changed"""
+        c = Camera()
+        rth.rth_scene_jittered_camera(self._h, dx, dy, C.byref(c))
+        return c
+
     def camera_move(self, x, y, z):
         return rth.rth_scene_camera_move(self._h, x, y, z)
 
@@ -119,6 +125,7 @@ class RayTracer:
         self._h = rth.rth_tracer_new(scene._h, device)
         self.maxLevel = 1
         self.smShare = 0   # resident traversal CTAs per SM (0 = all 8); set when several tracers of one Scene run concurrently
+        self.progressiveBands = 0   # display mode: the frame is rendered band by band, `output` fills in while !isFinish (host/RayTracer.h)
         self.coalesce = False   # throughput mode: frames of this Scene's tracers that wait together are rendered in one launch (host/RayTracer.h)
 
     def __del__(self):
@@ -126,11 +133,17 @@ class RayTracer:
             rth.rth_tracer_free(self._h)
             self._h = None
 
+    def set_samples(self, table):
+        """jittered supersampling: `table` = [(dx, dy), ...] sub-pixel offsets (host/RayTracer.h `samples`); [] = one sample"""
+        flat = (C.c_float * (2 * len(table)))(*[v for dxy in table for v in dxy])
+        rth.rth_tracer_set_samples(self._h, len(table), flat)
+
     def start(self, type=MY_MODEL_RAYTRACE, tnum=1, flags=0, rank=0, world=1, tile_rows=64):
         rth.rth_tracer_set_max_level(self._h, self.maxLevel)
         rth.rth_tracer_set_sm_share(self._h, self.smShare)
         rth.rth_tracer_set_flags(self._h, flags)
         rth.rth_tracer_set_coalesce(self._h, 1 if self.coalesce else 0)
+        rth.rth_tracer_set_progressive(self._h, self.progressiveBands)
         rth.rth_tracer_set_shard(self._h, rank, world, tile_rows)
         if rth.rth_tracer_start(self._h, type, tnum) != 0:
             raise RtError(rth.rth_last_error().decode())
@@ -145,6 +158,15 @@ class RayTracer:
 
     def wait(self):
         rth.rth_tracer_wait(self._h)
+
+    @property
+    def bandsDone(self):
+        return rth.rth_tracer_bands_done(self._h)
+
+    def peek_output(self) -> np.ndarray:
+        """RayTracer::output as it stands right now, without waiting (progressive display reads it while !isFinish)"""
+        w, h = rth.rth_tracer_width(self._h), rth.rth_tracer_height(self._h)
+        return np.ctypeslib.as_array(rth.rth_tracer_output(self._h), shape=(h, w, 3)).copy()
 
     @property
     def failed(self):
@@ -207,8 +229,8 @@ class Context:
     def upload(self, desc):
         _check(rt.rt_upload_scene(self._h, desc), "rt_upload_scene")
 
-    def render_async(self, type=MY_MODEL_RAYTRACE, max_level=1, rank=0, world=1, flags=0, tile_rows=64):
-        p = RenderParams(type, max_level, rank, world, flags, tile_rows)
+    def render_async(self, type=MY_MODEL_RAYTRACE, max_level=1, rank=0, world=1, flags=0, tile_rows=64, tile_first=0, tile_count=0):
+        p = RenderParams(type, max_level, rank, world, flags, tile_rows, tile_first, tile_count)
         _check(rt.rt_render_async(self._h, C.byref(p)), "rt_render_async")
 
     def wait(self) -> float:

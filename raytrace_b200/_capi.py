@@ -71,7 +71,7 @@ class SceneDesc(C.Structure):
 
 class RenderParams(C.Structure):
     _fields_ = [("type", C.c_uint32), ("max_level", C.c_uint32), ("rank", C.c_uint32), ("world", C.c_uint32),
-                ("flags", C.c_uint32), ("tile_rows", C.c_uint32)]
+                ("flags", C.c_uint32), ("tile_rows", C.c_uint32), ("tile_first", C.c_uint32), ("tile_count", C.c_uint32)]
 
 
 class HitId(C.Structure):
@@ -96,7 +96,7 @@ class Counters(C.Structure):
                 ("render_ms", C.c_double), ("trace_ms", C.c_double), ("shadow_ms", C.c_double),
                 ("shade_ms", C.c_double), ("other_ms", C.c_double), ("upload_ms", C.c_double), ("build_ms", C.c_double),
                 ("launches", C.c_uint32), ("bvh_nodes", C.c_uint32), ("bvh_depth", C.c_uint32), ("frame_sched", C.c_uint32),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("bvh_refit", C.c_uint32), ("pad0", C.c_uint32)]
 
 
 # every symbol include/rt_b200.h declares: name -> (restype, argtypes)
@@ -110,6 +110,7 @@ RT_SYMBOLS = {
     "rt_set_sm_share": (C.c_int, [C.c_void_p, C.c_int]),
     "rt_upload_scene": (C.c_int, [C.c_void_p, C.POINTER(SceneDesc)]),
     "rt_render_async": (C.c_int, [C.c_void_p, C.POINTER(RenderParams)]),
+    "rt_render_supersampled": (C.c_int, [C.c_void_p, C.POINTER(RenderParams), C.c_uint32, C.POINTER(Camera)]),
     "rt_poll": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "rt_wait": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "rt_stop": (C.c_int, [C.c_void_p]),
@@ -173,6 +174,11 @@ RTH_SYMBOLS = {
     "rth_tracer_set_max_level": (None, [C.c_void_p, C.c_int]),
     "rth_tracer_set_shard": (None, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "rth_tracer_set_flags": (None, [C.c_void_p, C.c_uint]),
+    "rth_tracer_set_samples": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
+    "rth_stratified_table": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "rth_scene_jittered_camera": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.POINTER(Camera)]),
+    "rth_tracer_set_progressive": (None, [C.c_void_p, C.c_int]),
+    "rth_tracer_bands_done": (C.c_int, [C.c_void_p]),
     "rth_tracer_set_coalesce": (None, [C.c_void_p, C.c_int]),
     "rth_tracer_set_sm_share": (None, [C.c_void_p, C.c_int]),
     "rth_tracer_read_hit_ids": (C.c_int, [C.c_void_p, C.POINTER(HitId)]),

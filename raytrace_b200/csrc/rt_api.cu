@@ -108,7 +108,10 @@ struct rt_ctx
 	DevBuf<int4> primMeta, textures;
 	DevBuf<uint8_t> texels;
 	DevBuf<float2> triTcoords;
-	DevBuf<uint32_t> bvhPrims, triSlot, triPart, leafOrder;
+	DevBuf<uint32_t> bvhPrims, triSlot, triPart, leafOrder, leafOrderAll;
+	std::vector<std::vector<uint32_t>> modelLevels;   // per model: 4-wide nodes per tree level (rtb_refit4)
+	std::vector<uint32_t> modelNodeBase;
+	bool lastUploadRefit = false;
 	DevBuf<DevModel> dModels;
 	DevBuf<DevPart> dParts;
 	DevBuf<BvhNode> nodes;      // binary LBVH (build-time only)
@@ -126,7 +129,9 @@ struct rt_ctx
 	int outW = 0, outH = 0;
 	uint8_t *fb = nullptr;          // framebuffer of the last frame (c->out or extOut)
 	rt_render_params lastParams;
-	uint32_t lastPixels = 0, lastLaunches = 0, lastMaxLevel = 0;
+	uint32_t lastPixels = 0, lastLaunches = 0, lastMaxLevel = 0, lastTileFirst = 0;
+	rt_counters ssTotals;           // rt_render_supersampled: ray counts and times summed over the bands of the last frame
+	bool ssValid = false;
 	bool frameInFlight = false, frameValid = false;
 	double uploadMs = 0, buildMs = 0, renderMs = 0;
 	uint64_t uploadBytes = 0, frameH2D = 0, frameD2H = 0;
@@ -145,6 +150,10 @@ struct rt_ctx
 	rt_ctx *sceneFrom = nullptr;
 	uint64_t sceneVersion = 0, adoptedVersion = 0;     // bumped by every rt_upload_scene of the parent
 	uint64_t tablesVersion = 0, adoptedTables = 0;     // bumped when prims / models / parts changed
+	const uint8_t *ssFillPtr = nullptr; // rt_render_supersampled: the target it last greyed
+	int ssFillW = 0, ssFillH = 0;
+	uint64_t ssFillShard = ~0ull;
+	bool regrewLastFrame = false;       // finish_frame regrew a ray level and rendered the launch again
 	const uint8_t *fillPtr = nullptr;   // what the framebuffer was last filled with 127 for
 	int fillW = 0, fillH = 0;
 	uint32_t fillRank = 0, fillWorld = 0, fillTile = 0, fillSerp = 0;
@@ -183,7 +192,7 @@ extern "C" int rt_create(int device, rt_ctx **out)
 	c->ownStream = true;
 	CU(cudaStreamCreateWithFlags(&c->stopStream, cudaStreamNonBlocking));
 	CU(cudaMallocHost(&c->hStopWord, 64 * sizeof(uint32_t)));
-	CU(cudaEventCreate(&c->evStart)); CU(cudaEventCreate(&c->evStop)); CU(cudaEventCreate(&c->evA)); CU(cudaEventCreate(&c->evB)); CU(cudaEventCreateWithFlags(&c->evRead, cudaEventDisableTiming));
+	CU(cudaEventCreate(&c->evStart)); CU(cudaEventCreate(&c->evStop)); CU(cudaEventCreate(&c->evA)); CU(cudaEventCreateWithFlags(&c->evB, cudaEventBlockingSync)); CU(cudaEventCreateWithFlags(&c->evRead, cudaEventDisableTiming | cudaEventBlockingSync));
 	for (auto &e : c->evStage) CU(cudaEventCreate(&e));
 	if (const char *v = getenv("RT_B200_STAGE_TIMING")) c->stageTiming = atoi(v) != 0;
 	CU(cudaMallocHost(&c->hFrame, sizeof(FrameParams)));
@@ -247,7 +256,7 @@ extern "C" void rt_destroy(rt_ctx *c)
 	for (auto &l : c->levels) l.release();
 	c->primGeom.release(), c->materials.release(), c->triPoints.release(), c->triNorms.release(), c->triGeomOrig.release(), c->triGeom.release();
 	c->boxLo.release(), c->boxHi.release(), c->partMid.release(), c->partPos.release(), c->primMeta.release(), c->textures.release(), c->texels.release();
-	c->triTcoords.release(), c->bvhPrims.release(), c->triSlot.release(), c->triPart.release(), c->leafOrder.release();
+	c->triTcoords.release(), c->bvhPrims.release(), c->triSlot.release(), c->triPart.release(), c->leafOrder.release(), c->leafOrderAll.release();
 	c->dModels.release(), c->dParts.release(), c->nodes.release(), c->nodes4.release(), c->items.release(), c->out.release();
 	for (auto &b : c->batchOut) b.release();
 	rtb_free_scratch(c->scratch);
@@ -375,6 +384,29 @@ static int upload_scene_tables(rt_ctx *c, const rt_scene_desc *s, bool hadScene)
 	const bool primsChanged = !hadScene || !same(c->prims, s->prims, s->n_prims);
 	if (trisChanged && s->n_tris && (!s->tri_points || !s->tri_norms || !s->tri_tcoords))
 		return fail(RT_E_INVALID, "rt_upload_scene: geometry changed but triangle arrays are NULL");
+	// Position-only edit (Scene::MovePos of a Model, Scene.cpp:248): same triangles, same parts, same objects -- only
+	// rt_model::position differs.  The reference's RTPrepare then merely re-translates its bounds (Model.cpp:404,418-419);
+	// here the BVHs keep their topology and are REFITTED (rtb_refit4) instead of rebuilt.
+	std::vector<uint32_t> movedModels;
+	bool refitOnly = false;
+	{
+		static const int allow = []{ const char *e = getenv("RT_B200_REFIT"); return (e && !atoi(e)) ? 0 : 1; }();
+		if (allow && hadScene && !trisChanged && !primsChanged && modelsChanged && c->models.size() == s->n_models
+			&& same(c->parts, s->parts, s->n_parts) && c->modelLevels.size() == s->n_models)
+		{
+			refitOnly = true;
+			for (uint32_t m = 0; m < s->n_models && refitOnly; ++m)
+			{
+				rt_model a = c->models[m], b = s->models[m];
+				const bool moved = memcmp(&a.position, &b.position, sizeof a.position) != 0;
+				a.position = b.position;
+				if (memcmp(&a, &b, sizeof a) != 0) refitOnly = false;                     // something besides the position changed
+				else if (moved && c->modelLevels[m].empty() && b.part_count) refitOnly = false;   // no level table (tiny or legacy-collapsed tree)
+				else if (moved) movedModels.push_back(m);
+			}
+		}
+	}
+	c->lastUploadRefit = false;
 	c->prims.assign(s->prims, s->prims + s->n_prims);
 	c->models.assign(s->models, s->models + s->n_models);
 	c->parts.assign(s->parts, s->parts + s->n_parts);
@@ -395,7 +427,59 @@ static int upload_scene_tables(rt_ctx *c, const rt_scene_desc *s, bool hadScene)
 
 	if (primsChanged || modelsChanged)
 		++c->tablesVersion;
-	if (primsChanged || modelsChanged)
+	if (refitOnly)
+	{
+		// ---- refit: new translated bounds, new clTri records (p0 + position, octant membership), same trees ----
+		cudaEvent_t b0 = c->evB;
+		CU(cudaEventRecord(b0, st));
+		std::vector<DevModel> dm(s->n_models);
+		std::vector<DevPart> dp(s->n_parts);
+		std::vector<float4> pos(s->n_parts);
+		for (uint32_t m = 0; m < s->n_models; ++m)
+		{
+			const rt_model &M = s->models[m];
+			memset(&dm[m], 0, sizeof(DevModel));
+			dm[m].border_min = f4(addv(M.ver_min, M.position)), dm[m].border_max = f4(addv(M.ver_max, M.position));
+			dm[m].part_begin = M.part_begin, dm[m].part_count = M.part_count, dm[m].object = M.object;
+			uint32_t tb = 0xFFFFFFFFu, tc = 0;
+			for (uint32_t q = 0; q < M.part_count; ++q)
+			{
+				const rt_part &P = s->parts[M.part_begin + q];
+				if (tb == 0xFFFFFFFFu) tb = P.tri_begin;
+				tc += P.tri_count;
+				DevPart &D = dp[M.part_begin + q];
+				D.box_min = f4(addv(P.border_min, M.position)), D.box_max = f4(addv(P.border_max, M.position));
+				D.tri_begin = P.tri_begin, D.tri_count = P.tri_count, D.material = P.material, D.texture = P.texture;
+				pos[M.part_begin + q] = f4(M.position);
+			}
+			dm[m].tri_begin = tb == 0xFFFFFFFFu ? 0 : tb, dm[m].tri_count = tc;
+		}
+		CU(c->dModels.upload(dm.data(), dm.size(), st, ub));
+		CU(c->dParts.upload(dp.data(), dp.size(), st, ub));
+		CU(c->partPos.upload(pos.data(), pos.size(), st, ub));
+		for (uint32_t m : movedModels)
+		{
+			const DevModel &M = dm[m];
+			if (M.tri_count == 0) continue;
+			TriPrepArgs a;
+			a.points = c->triPoints.p + 3 * (size_t)M.tri_begin, a.models = c->dModels.p, a.parts = c->dParts.p;
+			a.tri_part = c->triPart.p + M.tri_begin, a.part_mid_pos = c->partMid.p, a.part_position = c->partPos.p;
+			a.tri_geom_orig = c->triGeomOrig.p + 3 * (size_t)M.tri_begin, a.box_lo = c->boxLo.p, a.box_hi = c->boxHi.p, a.n = M.tri_count;
+			a.id_base = M.tri_begin;
+			rtb_prepare_tris(st, a);
+			rtb_scatter_tris(st, c->triGeomOrig.p, c->leafOrderAll.p + M.tri_begin, M.tri_begin, M.tri_begin, M.tri_count, c->triGeom.p, c->triSlot.p);
+			const std::vector<uint32_t> &lv = c->modelLevels[m];
+			rtb_refit4(st, c->nodes4.p, c->modelNodeBase[m], lv.data(), (uint32_t)lv.size(), c->boxLo.p, c->boxHi.p, c->leafOrderAll.p);
+		}
+		CU(cudaGetLastError());
+		CU(cudaEventRecord(c->evStop, st));
+		CU(cudaStreamSynchronize(st));
+		float ms = 0;
+		cudaEventElapsedTime(&ms, b0, c->evStop);
+		c->buildMs = ms;
+		c->lastUploadRefit = true;
+	}
+	else if (primsChanged || modelsChanged)
 	{
 		// ---- analytic primitives ------------------------------------------------------------------
 		std::vector<float4> pg(4 * (size_t)s->n_prims);
@@ -483,6 +567,9 @@ static int upload_scene_tables(rt_ctx *c, const rt_scene_desc *s, bool hadScene)
 		CU(c->triGeomOrig.reserve(3 * (size_t)s->n_tris + 1));
 		CU(c->triGeom.reserve(RT_TRI_F4 * (size_t)s->n_tris + 1));
 		CU(c->triSlot.reserve(s->n_tris + 1));
+		CU(c->leafOrderAll.reserve(s->n_tris + 1));
+		c->modelLevels.assign(s->n_models, std::vector<uint32_t>());
+		c->modelNodeBase.assign(s->n_models, 0u);
 		uint32_t maxBoxes = 1;
 		for (const SceneItem &it : items)
 			maxBoxes = std::max(maxBoxes, it.kind == RT_ITEM_MODEL ? dm[it.first].tri_count : it.count);
@@ -520,6 +607,10 @@ static int upload_scene_tables(rt_ctx *c, const rt_scene_desc *s, bool hadScene)
 				int rc = rtb_build(st, &c->scratch, c->boxLo.p, c->boxHi.p, M.tri_count, c->leafSize, c->nodes.p, c->nodes4.p, nodeCursor, M.tri_begin, c->leafOrder.p, &res);
 				if (rc) return fail(RT_E_CUDA, "LBVH build (model %u) failed: %s", it.first, cudaGetErrorString((cudaError_t)rc));
 				rtb_scatter_tris(st, c->triGeomOrig.p, c->leafOrder.p, M.tri_begin, M.tri_begin, M.tri_count, c->triGeom.p, c->triSlot.p);
+				// kept for refits after position-only edits: the leaf order (global slot -> model-local triangle) and the level table
+				CU(cudaMemcpyAsync(c->leafOrderAll.p + M.tri_begin, c->leafOrder.p, sizeof(uint32_t) * M.tri_count, cudaMemcpyDeviceToDevice, st));
+				c->modelLevels[it.first].assign(res.levelNodes, res.levelNodes + res.nLevels);
+				c->modelNodeBase[it.first] = nodeCursor;
 				it.root = res.root, it.count = M.tri_count;
 				nodeCursor += res.nodesUsed;
 				c->bvhDepth = std::max(c->bvhDepth, res.depth);
@@ -648,6 +739,10 @@ static int render_frames(rt_ctx *c, const rt_render_params *p, uint32_t nFrames,
 	F.serpentine = (p->flags & RT_FLAG_SERPENTINE) && world > 1 ? 1u : 0u;
 	uint32_t bands = 0;
 	while (shard_tile(bands, rank, world, F.serpentine) < (uint32_t)F.blk_h * 64u / tileRows) ++bands;
+	// tile window (rt_render_params::tile_first / tile_count): a band of the shard's own tiles
+	F.tile_first = p->tile_first < bands ? p->tile_first : bands;
+	if (p->tile_count) bands = std::min(bands - F.tile_first, p->tile_count);
+	else bands -= F.tile_first;
 	F.n_rows = bands * tileRows;
 	F.n_lights = (uint32_t)c->lights.size();
 	F.env_light = f4(c->envLight);
@@ -708,7 +803,7 @@ static int render_frames(rt_ctx *c, const rt_render_params *p, uint32_t nFrames,
 	if (fb != c->fillPtr || W != c->fillW || H != c->fillH || rank != c->fillRank || world != c->fillWorld || tileRows != c->fillTile || F.serpentine != c->fillSerp)
 	{
 		c->fillSerp = F.serpentine;
-		CU(cudaMemsetAsync(fb, 127, (size_t)W * H * 3, st));
+		if (!is_landing_base(fb)) CU(cudaMemsetAsync(fb, 127, (size_t)W * H * 3, st));   // a landing buffer is born grey; its other rows belong to the peers' one-sided copies
 		c->fillPtr = fb, c->fillW = W, c->fillH = H, c->fillRank = rank, c->fillWorld = world, c->fillTile = tileRows;
 		for (auto &b : c->batchFill) b = nullptr;   // the shard the batch buffers were greyed for is no longer current
 	}
@@ -821,6 +916,7 @@ static int render_frames(rt_ctx *c, const rt_render_params *p, uint32_t nFrames,
 	CU(cudaEventRecord(c->evB, st));
 	if (cams && cams != c->lastCams.data()) c->lastCams.assign(cams, cams + nFrames);
 	c->lastCamsGiven = cams != nullptr, c->lastOutsGiven = outs != nullptr;
+	c->lastTileFirst = F.tile_first, c->ssValid = false;
 	c->lastParams = *p, c->lastPixels = nPix, c->lastLaunches = launches, c->lastMaxLevel = maxLevel, c->lastBatch = nFrames;
 	for (uint32_t f = 0; f < nFrames; ++f) c->lastOuts[f] = F.frames[f].out;
 	c->frameInFlight = true, c->frameValid = false;
@@ -832,17 +928,21 @@ static int render_frames(rt_ctx *c, const rt_render_params *p, uint32_t nFrames,
 // host cudaEventSynchronize's busy wait starved the threads that enqueue the next frames.
 static cudaError_t wait_event(cudaEvent_t ev)
 {
-	for (unsigned spins = 0;; ++spins)
+	// a short spin for frames that are about to finish, then sleep in the driver: evB / evRead are created with
+	// cudaEventBlockingSync, so cudaEventSynchronize parks the thread instead of burning a core per frame in flight
+	// (8 ranks x (3 batch workers + monitor threads) on a 16-32 core host starved the threads that enqueue frames)
+	for (unsigned spins = 0; spins < 64u; ++spins)
 	{
 		const cudaError_t e = cudaEventQuery(ev);
 		if (e != cudaErrorNotReady) return e;
-		if (spins >= 32u) std::this_thread::yield();
 	}
+	return cudaEventSynchronize(ev);
 }
 
 static int finish_frame(rt_ctx *c)
 {
 	CU(cudaSetDevice(c->device));
+	if (c->regrowTries == 0) c->regrewLastFrame = false;
 	CU(wait_event(c->evB));
 	float ms = 0;
 	CU(cudaEventElapsedTime(&ms, c->evStart, c->evStop));
@@ -882,6 +982,7 @@ static int finish_frame(rt_ctx *c)
 			if (need > cap || ratio > 1.0) c->minCap[l] = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(c->minCap[l], want), 0xFFFFFFF0ull);
 		}
 		++c->regrowTries;
+		c->regrewLastFrame = true;
 		const rt_render_params p = c->lastParams;
 		const uint32_t nb = c->lastBatch;
 		int rc = render_frames(c, &p, nb, c->lastCamsGiven ? c->lastCams.data() : nullptr, c->lastOutsGiven ? (void *const *)c->lastOuts : nullptr);
@@ -890,6 +991,98 @@ static int finish_frame(rt_ctx *c)
 	}
 	c->regrowTries = 0;
 	c->frameValid = true;
+	return RT_OK;
+}
+
+// Pixels (x samples) one band launch may hold: the wave kernels run best with millions of rays per queue, and the
+// ray-level buffers of a launch are ~140 bytes per slot and level.
+static uint32_t supersample_budget()
+{
+	const char *e = getenv("RT_B200_SS_PIXELS");   // read per frame: tests shrink it to force several bands
+	const long n = e ? atol(e) : 8000000L;
+	return (uint32_t)(n > 4096 ? n : 4096);
+}
+
+extern "C" int rt_render_supersampled(rt_ctx *c, const rt_render_params *p, uint32_t n_samples, const rt_camera *cams)
+{
+	if (!c || !p || !cams) return fail(RT_E_INVALID, "rt_render_supersampled: NULL argument");
+	if (n_samples < 1 || n_samples > RT_MAX_BATCH) return fail(RT_E_LIMIT, "rt_render_supersampled: %u samples per pixel (1..%d)", n_samples, RT_MAX_BATCH);
+	if (p->type != RT_TYPE_RAYTRACE && p->type != RT_TYPE_REFLECT && p->type != RT_TYPE_REFRACT)
+		return fail(RT_E_INVALID, "rt_render_supersampled: only the ray-traced types are supersampled");
+	if (p->flags & RT_FLAG_HIT_IDS) return fail(RT_E_INVALID, "rt_render_supersampled: RT_FLAG_HIT_IDS needs a single sample");
+	if (p->tile_first || p->tile_count) return fail(RT_E_INVALID, "rt_render_supersampled: the tile window is used internally; pass 0");
+	adopt_scene(c);
+	if (!c->hasScene) return fail(RT_E_STATE, "rt_render_supersampled: no scene uploaded");
+	CU(cudaSetDevice(c->device));
+	if (c->frameInFlight) { int rc = finish_frame(c); if (rc != RT_OK) return rc; }
+	const int W = c->camera.width, H = c->camera.height;
+	if (W <= 0 || H <= 0) return fail(RT_E_INVALID, "rt_render_supersampled: camera is %dx%d", W, H);
+	const uint32_t world = p->world > 1 ? p->world : 1, rank = p->world > 1 ? p->rank : 0;
+	if (rank >= world) return fail(RT_E_INVALID, "rt_render_supersampled: rank %u of world %u", rank, world);
+	const uint32_t tileRows = p->tile_rows ? p->tile_rows : 64u;
+	if (tileRows != 8u && tileRows != 16u && tileRows != 32u && tileRows != 64u)
+		return fail(RT_E_INVALID, "rt_render_supersampled: tile_rows %u (must be 8, 16, 32 or 64)", tileRows);
+	const uint32_t serp = (p->flags & RT_FLAG_SERPENTINE) && world > 1 ? 1u : 0u;
+	uint32_t mine = 0;
+	while (shard_tile(mine, rank, world, serp) < (uint32_t)(H / 64) * 64u / tileRows) ++mine;
+	// target framebuffer: the caller's (rt_set_output) or the library's, greyed once like a frame's
+	uint8_t *fb;
+	if (c->extOut)
+	{
+		if (c->extOutBytes < (size_t)W * H * 3) return fail(RT_E_INVALID, "rt_render_supersampled: external framebuffer holds %zu bytes, frame needs %zu", c->extOutBytes, (size_t)W * H * 3);
+		fb = c->extOut;
+	}
+	else
+	{
+		CU(c->out.reserve((size_t)W * H * 3));
+		fb = c->out.p;
+	}
+	const uint64_t shardKey = ((uint64_t)rank << 40) | ((uint64_t)world << 16) | ((uint64_t)tileRows << 4) | serp;
+	if (fb != c->ssFillPtr || W != c->ssFillW || H != c->ssFillH || shardKey != c->ssFillShard)
+	{
+		// RayTracer.cpp:620 greys the whole buffer at every start(); the shard's rows are overwritten by every frame, so
+		// the fill is only repeated when the buffer, the frame size or the shard changes
+		if (!is_landing_base(fb)) CU(cudaMemsetAsync(fb, 127, (size_t)W * H * 3, c->stream));
+		c->ssFillPtr = fb, c->ssFillW = W, c->ssFillH = H, c->ssFillShard = shardKey;
+	}
+	c->fillPtr = nullptr;   // a later single frame into the same buffer greys it again (other rows may hold averaged pixels)
+	// band = as many of the shard's tiles as fit the budget with n_samples frames in the batch
+	const uint64_t tilePix = (uint64_t)(W / 64) * 64u * tileRows;
+	uint32_t tilesPerBand = (uint32_t)std::max<uint64_t>(1, supersample_budget() / std::max<uint64_t>(1, tilePix * n_samples));
+	rt_counters tot;
+	memset(&tot, 0, sizeof tot);
+	rt_render_params bp = *p;
+	for (uint32_t k0 = 0; k0 < mine; k0 += tilesPerBand)
+	{
+		const uint32_t kc = std::min(tilesPerBand, mine - k0);
+		bp.tile_first = k0, bp.tile_count = kc;
+		int rc = render_frames(c, &bp, n_samples, cams, nullptr);      // the samples of the band: one batch, library-owned sample frames
+		if (rc != RT_OK) return rc;
+		rtk_average(c->stream, c->lastOuts, n_samples, fb, W, tileRows, k0, kc, rank, world, serp, c->sms);
+		CU(cudaGetLastError());
+		rc = finish_frame(c);                                         // counters of this band (and a regrow + re-render if a level overflowed)
+		if (rc != RT_OK) return rc;
+		if (c->regrewLastFrame)
+		{
+			// the band was rendered again after the averaging kernel had been enqueued: average the final sample frames
+			rtk_average(c->stream, c->lastOuts, n_samples, fb, W, tileRows, k0, kc, rank, world, serp, c->sms);
+			CU(cudaGetLastError());
+		}
+		if (!c->frameValid) break;                                    // rt_stop
+		rt_counters bc;
+		c->ssValid = false;
+		rc = rt_read_counters(c, &bc);
+		if (rc != RT_OK) return rc;
+		tot.primary += bc.primary, tot.shadow += bc.shadow, tot.reflect += bc.reflect, tot.refract += bc.refract;
+		tot.nodes_visited += bc.nodes_visited, tot.tri_tests += bc.tri_tests, tot.prim_tests += bc.prim_tests;
+		tot.render_ms += bc.render_ms, tot.trace_ms += bc.trace_ms, tot.shade_ms += bc.shade_ms, tot.other_ms += bc.other_ms;
+		tot.launches += bc.launches + 1;
+	}
+	CU(cudaStreamSynchronize(c->stream));
+	c->ssTotals = tot, c->ssValid = c->frameValid;
+	c->lastParams = *p, c->lastTileFirst = 0, c->lastBatch = 1;   // read-backs and row pushes see the whole shard in `fb`
+	c->lastOuts[0] = fb, c->fb = fb, c->outW = W, c->outH = H;
+	c->renderMs = tot.render_ms;
 	return RT_OK;
 }
 
@@ -963,13 +1156,18 @@ static int copy_shard_rows(rt_ctx *c, const uint8_t *src, uint8_t *dst, size_t s
 	const uint32_t tiles = (uint32_t)(c->outH / 64) * 64u / tileRows;
 	uint32_t mine = 0;
 	while (shard_tile(mine, rank, world, serp) < tiles) ++mine;
+	// the tile window of the last frame (rt_render_params::tile_first / tile_count): only those tiles were rendered
+	const uint32_t k0 = p.tile_first < mine ? p.tile_first : mine;
+	const uint32_t k1 = p.tile_count ? std::min(mine, k0 + p.tile_count) : mine;
 	size_t bytes = 0;
 	// family f: tiles k = f, f + step, f + 2*step ... of this shard are equally spaced in the frame
 	const uint32_t step = serp ? 2u : 1u;
-	for (uint32_t f = 0; f < step && f < mine; ++f)
+	for (uint32_t f = 0; f < step; ++f)
 	{
-		const uint32_t count = (mine - f + step - 1u) / step;
-		const size_t first = (size_t)shard_tile(f, rank, world, serp) * tileRows;        // first image row of the family
+		const uint32_t kf = k0 + ((f + step - k0 % step) % step);      // first tile >= k0 of this family
+		if (kf >= k1) continue;
+		const uint32_t count = (k1 - kf + step - 1u) / step;
+		const size_t first = (size_t)shard_tile(kf, rank, world, serp) * tileRows;       // first image row of the family
 		const size_t pitchRows = (size_t)step * world * tileRows;                        // image rows between two of its tiles
 		if (stride == row)
 			CU(cudaMemcpy2DAsync(dst + first * row, pitchRows * row, src + first * row, pitchRows * row, tileRows * row, count, kind, st));
@@ -985,7 +1183,7 @@ static int copy_shard_rows(rt_ctx *c, const uint8_t *src, uint8_t *dst, size_t s
 extern "C" int rt_read_output_rows(rt_ctx *c, uint8_t *rgb, size_t stride)
 {
 	if (!c || !rgb) return fail(RT_E_INVALID, "rt_read_output_rows: NULL argument");
-	if (c->lastParams.world <= 1) return rt_read_output(c, rgb, stride);
+	if (c->lastParams.world <= 1 && !c->lastParams.tile_first && !c->lastParams.tile_count) return rt_read_output(c, rgb, stride);
 	if (c->frameInFlight) { int rc = finish_frame(c); if (rc != RT_OK) return rc; }
 	if (!c->fb) return fail(RT_E_STATE, "rt_read_output_rows: nothing rendered yet");
 	CU(cudaSetDevice(c->device));
@@ -1361,6 +1559,7 @@ extern "C" int rt_read_counters(rt_ctx *c, rt_counters *out)
 	if (c->frameInFlight) { int rc = finish_frame(c); if (rc != RT_OK) return rc; }
 	memset(out, 0, sizeof *out);
 	out->upload_ms = c->uploadMs, out->build_ms = c->buildMs, out->bvh_nodes = c->bvhNodes, out->bvh_depth = c->bvhDepth;
+	out->bvh_refit = (c->sceneFrom ? c->sceneFrom->lastUploadRefit : c->lastUploadRefit) ? 1u : 0u;
 	out->h2d_bytes = c->uploadBytes + c->frameH2D, out->d2h_bytes = c->frameD2H;
 	if (!c->frameValid) return RT_OK;
 	const WaveState &W = *c->hWave;
@@ -1395,6 +1594,14 @@ extern "C" int rt_read_counters(rt_ctx *c, rt_counters *out)
 		if (W.lane_cap[0] || W.lane_cap[1])
 			fprintf(stderr, "lane utilisation bound (sum nodes / 32 x longest lane per batch): closest %.3f shadow %.3f\n",
 				W.lane_cap[0] ? (double)W.lane_sum[0] / (double)W.lane_cap[0] : 0.0, W.lane_cap[1] ? (double)W.lane_sum[1] / (double)W.lane_cap[1] : 0.0);
+	}
+	if (c->ssValid)
+	{
+		out->primary = c->ssTotals.primary, out->shadow = c->ssTotals.shadow, out->reflect = c->ssTotals.reflect, out->refract = c->ssTotals.refract;
+		out->nodes_visited = c->ssTotals.nodes_visited, out->tri_tests = c->ssTotals.tri_tests, out->prim_tests = c->ssTotals.prim_tests;
+		out->render_ms = c->ssTotals.render_ms, out->trace_ms = c->ssTotals.trace_ms, out->shade_ms = c->ssTotals.shade_ms, out->other_ms = c->ssTotals.other_ms;
+		out->launches = c->ssTotals.launches, out->frame_sched = c->frameSched ? 1u : 0u;
+		return RT_OK;
 	}
 	out->render_ms = c->renderMs;
 	out->trace_ms = c->traceMs, out->shadow_ms = c->shadowMs, out->shade_ms = c->shadeMs, out->other_ms = c->otherMs;

@@ -567,6 +567,7 @@ __global__ void k_collapse4_sah(Collapse4Args a)
 int rtb_build(cudaStream_t st, BuildScratch **scratch, const float4 *box_lo, const float4 *box_hi, uint32_t n,
 	uint32_t leafSize, BvhNode *nodes, BvhNode4 *nodes4, uint32_t nodeBase, uint32_t leafBase, uint32_t *leafOrder, BvhBuildResult *res)
 {
+	res->nLevels = 0;
 	if (n == 0) { res->root = 0, res->nodesUsed = 0, res->depth = 0; return 0; }
 	if (leafSize < 1) leafSize = 1;
 	if (leafSize > 8) leafSize = 8;
@@ -614,12 +615,75 @@ int rtb_build(cudaStream_t st, BuildScratch **scratch, const float4 *box_lo, con
 			ca.next = (level & 1) ? s->children : s->range;
 			k_collapse4_sah<<<level < 4 ? 1 : cblocks, 256, 0, st>>>(ca);
 		}
+		// nodes per 4-wide level, for later refits: level 0 is the root, level k + 1 holds counters[k] nodes
+		uint32_t counters[128];
+		CK(cudaMemcpyAsync(counters, s->flags, sizeof counters, cudaMemcpyDeviceToHost, st));
 		CK(cudaStreamSynchronize(st));
+		res->nLevels = 1, res->levelNodes[0] = 1;
+		for (uint32_t level = 0; level < depth && level < 120 && counters[level]; ++level)
+			res->levelNodes[res->nLevels++] = counters[level];
 	}
 	res->root = (int)nodeBase;
 	res->nodesUsed = n - 1;
 	res->depth = depth;
 	return (int)cudaGetLastError();
+}
+
+// ---- refit of the 4-wide tree (position-only edits) --------------------------------------------------
+__global__ void k_refit4_level(BvhNode4 *nodes4, uint32_t begin, uint32_t count, const float4 *box_lo, const float4 *box_hi, const uint32_t *leafOrder)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count) return;
+	BvhNode4 n = nodes4[begin + i];
+	const int link[4] = { n.link.x, n.link.y, n.link.z, n.link.w };
+	float lo[4][3], hi[4][3];
+	for (int k = 0; k < 4; ++k)
+	{
+		const float inf = __int_as_float(0x7f800000);
+		float l0 = inf, l1 = inf, l2 = inf, h0 = -inf, h1 = -inf, h2 = -inf;
+		if (link[k] == 0x7FFFFFFF)
+			l0 = l1 = l2 = h0 = h1 = h2 = 3.0e38f;   // unused slot: stays the far-away point
+		else if (link[k] < 0)
+		{
+			const uint32_t first = ((uint32_t)link[k] & 0x7FFFFFFFu) >> 3, cnt = ((uint32_t)link[k] & 7u) + 1u;
+			for (uint32_t s = first; s < first + cnt; ++s)
+			{
+				const uint32_t t = leafOrder[s];
+				const float4 a = box_lo[t], b = box_hi[t];
+				l0 = fminf(l0, a.x), l1 = fminf(l1, a.y), l2 = fminf(l2, a.z), h0 = fmaxf(h0, b.x), h1 = fmaxf(h1, b.y), h2 = fmaxf(h2, b.z);
+			}
+		}
+		else
+		{
+			const BvhNode4 c = nodes4[link[k]];   // a deeper level: already refitted
+			const int cl[4] = { c.link.x, c.link.y, c.link.z, c.link.w };
+			const float clo[3][4] = { { c.lox.x, c.lox.y, c.lox.z, c.lox.w }, { c.loy.x, c.loy.y, c.loy.z, c.loy.w }, { c.loz.x, c.loz.y, c.loz.z, c.loz.w } };
+			const float chi[3][4] = { { c.hix.x, c.hix.y, c.hix.z, c.hix.w }, { c.hiy.x, c.hiy.y, c.hiy.z, c.hiy.w }, { c.hiz.x, c.hiz.y, c.hiz.z, c.hiz.w } };
+			for (int j = 0; j < 4; ++j)
+				if (cl[j] != 0x7FFFFFFF)
+					l0 = fminf(l0, clo[0][j]), l1 = fminf(l1, clo[1][j]), l2 = fminf(l2, clo[2][j]), h0 = fmaxf(h0, chi[0][j]), h1 = fmaxf(h1, chi[1][j]), h2 = fmaxf(h2, chi[2][j]);
+		}
+		lo[k][0] = l0, lo[k][1] = l1, lo[k][2] = l2, hi[k][0] = h0, hi[k][1] = h1, hi[k][2] = h2;
+	}
+	n.lox = make_float4(lo[0][0], lo[1][0], lo[2][0], lo[3][0]);
+	n.loy = make_float4(lo[0][1], lo[1][1], lo[2][1], lo[3][1]);
+	n.loz = make_float4(lo[0][2], lo[1][2], lo[2][2], lo[3][2]);
+	n.hix = make_float4(hi[0][0], hi[1][0], hi[2][0], hi[3][0]);
+	n.hiy = make_float4(hi[0][1], hi[1][1], hi[2][1], hi[3][1]);
+	n.hiz = make_float4(hi[0][2], hi[1][2], hi[2][2], hi[3][2]);
+	nodes4[begin + i] = n;
+}
+
+void rtb_refit4(cudaStream_t st, BvhNode4 *nodes4, uint32_t nodeBase, const uint32_t *levelNodes, uint32_t nLevels,
+	const float4 *box_lo, const float4 *box_hi, const uint32_t *leafOrder)
+{
+	// slots: level 0 at nodeBase, level k >= 1 behind the levels before it; deepest level first
+	uint32_t begin[129];
+	begin[0] = nodeBase;
+	for (uint32_t k = 0; k < nLevels; ++k) begin[k + 1] = begin[k] + levelNodes[k];
+	for (int k = (int)nLevels - 1; k >= 0; --k)
+		if (levelNodes[k])
+			k_refit4_level<<<(levelNodes[k] + 127) / 128, 128, 0, st>>>(nodes4, begin[k], levelNodes[k], box_lo, box_hi, leafOrder);
 }
 
 // ---- leaf-order scatter --------------------------------------------------------------------------

@@ -93,7 +93,7 @@ struct FrameParams
 	uint32_t keep_salt;        //   (CTA i is kept iff (i + i / sms + keep_salt) % d == 0: spread over the SMs, rotated per pipeline)
 	uint32_t batch;            // frames in this launch (1..RT_MAX_BATCH)
 	uint32_t pix_per_frame;    // level-0 slots of one frame
-	uint32_t pad_[1];
+	uint32_t tile_first;       // first of the shard's own tiles that this launch renders (rt_render_params::tile_first)
 	float4 env_light;
 	DevLight lights[RT_MAX_LIGHTS];
 	BatchFrame frames[RT_MAX_BATCH];

@@ -23,6 +23,7 @@
 #include "rt_async.cuh"
 #include "rt_kernels.h"
 #include <cstdlib>
+#include <algorithm>
 
 // ---- helpers -------------------------------------------------------------------------------------
 
@@ -35,7 +36,7 @@ __device__ __forceinline__ void slot_to_pixel(const FrameParams &F, uint32_t i, 
 	const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
 	x = (int)(tx * 8u + (in & 7u));
 	const uint32_t row = ty * 8u + (in >> 3);            // row among this shard's rows
-	const uint32_t band = row / F.tile_rows;              // row tile among this shard's tiles
+	const uint32_t band = row / F.tile_rows + F.tile_first;   // row tile among this shard's tiles
 	y = (int)(shard_tile(band, F.rank, F.world, F.serpentine) * F.tile_rows + row % F.tile_rows);
 }
 
@@ -1577,6 +1578,60 @@ __global__ void __launch_bounds__(256) k_resolve(SceneDev S, const FrameParams *
 		uint8_t *o = pixel_of(F, px);
 		o[0] = put8(ret.x), o[1] = put8(ret.y), o[2] = put8(ret.z);
 	}
+}
+
+// ---- supersampling: integer mean of the sample frames (rt_render_supersampled) ------------------------
+// out[b] = (sum over the n sample frames of frame_s[b]) / n for every byte of the `rows` image rows that start at byte
+// offset rowStart[t] (one entry per row tile of the band): each sample was quantised by Color::put on its own, the mean
+// truncates -- the arithmetic of averaging n reference renders in integer.  32-bit lanes of four bytes when the row
+// pitch allows it.
+struct AverageArgs
+{
+	const uint8_t *frames[RT_MAX_BATCH];
+	uint8_t *out;
+	uint32_t n, tiles, tileBytes;         // samples, row tiles of this band, bytes per row tile (tile_rows * 3 * width)
+	uint32_t tileFirst, rank, world, serpentine, tileRows;
+	size_t rowPitch;                      // 3 * width
+};
+
+__global__ void __launch_bounds__(256) k_average(AverageArgs A)
+{
+	const bool words = (A.tileBytes & 3u) == 0u && (A.rowPitch & 3u) == 0u;
+	const uint32_t per = words ? A.tileBytes >> 2 : A.tileBytes;
+	const uint64_t total = (uint64_t)per * A.tiles;
+	for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < total; w += (uint64_t)gridDim.x * blockDim.x)
+	{
+		const uint32_t t = (uint32_t)(w / per), in = (uint32_t)(w % per);
+		const size_t off = (size_t)shard_tile(A.tileFirst + t, A.rank, A.world, A.serpentine) * A.tileRows * A.rowPitch + (words ? (size_t)in * 4u : in);
+		if (words)
+		{
+			uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+			for (uint32_t f = 0; f < A.n; ++f)
+			{
+				const uint32_t v = *(const uint32_t *)(A.frames[f] + off);
+				s0 += v & 0xFFu, s1 += (v >> 8) & 0xFFu, s2 += (v >> 16) & 0xFFu, s3 += v >> 24;
+			}
+			*(uint32_t *)(A.out + off) = (s0 / A.n) | ((s1 / A.n) << 8) | ((s2 / A.n) << 16) | ((s3 / A.n) << 24);
+		}
+		else
+		{
+			uint32_t s0 = 0;
+			for (uint32_t f = 0; f < A.n; ++f) s0 += A.frames[f][off];
+			A.out[off] = (uint8_t)(s0 / A.n);
+		}
+	}
+}
+
+void rtk_average(cudaStream_t st, const uint8_t *const *frames, uint32_t n, uint8_t *out, int width, uint32_t tileRows, uint32_t tileFirst, uint32_t tiles,
+	uint32_t rank, uint32_t world, uint32_t serpentine, unsigned sms)
+{
+	if (!tiles || !n) return;
+	AverageArgs A;
+	for (uint32_t f = 0; f < n; ++f) A.frames[f] = frames[f];
+	A.out = out, A.n = n, A.tiles = tiles, A.rowPitch = (size_t)width * 3, A.tileBytes = (uint32_t)(tileRows * A.rowPitch);
+	A.tileFirst = tileFirst, A.rank = rank, A.world = world, A.serpentine = serpentine, A.tileRows = tileRows;
+	const uint64_t work = (uint64_t)(A.tileBytes / 4u + 1u) * tiles;
+	k_average<<<(unsigned)std::min<uint64_t>((work + 255) / 256, (uint64_t)sms * 16), 256, 0, st>>>(A);
 }
 
 // ---- launchers -----------------------------------------------------------------------------------

@@ -56,6 +56,9 @@ void rtk_debug(cudaStream_t st, const SceneDev &S, const FrameParams *F, const L
 void rtk_intersect_object(cudaStream_t st, const SceneDev &S, uint32_t primBegin, uint32_t primEnd, int modelIndex, const void *rays, const void *in,
 	const uint32_t *skipIds, float minT, uint32_t *outIds, void *out, uint32_t n);
 void rtk_reset_hits(cudaStream_t st, const LevelSet &LS, const WaveState *ws, uint32_t levels, uint32_t maxRays, unsigned sms);
+// integer mean of n sample frames over `tiles` row tiles of a shard, starting at its tile `tileFirst` (rt_render_supersampled)
+void rtk_average(cudaStream_t st, const uint8_t *const *frames, uint32_t n, uint8_t *out, int width, uint32_t tileRows, uint32_t tileFirst, uint32_t tiles,
+	uint32_t rank, uint32_t world, uint32_t serpentine, unsigned sms);
 void rtk_combine(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const LevelBuf &N, const WaveState *ws,
 	uint32_t level, uint8_t *out, uint32_t maxRays, unsigned sms);
 
@@ -92,11 +95,22 @@ void rtb_prim_boxes(cudaStream_t st, const PrimBoxArgs &a);
 // Builds one LBVH over boxes [0,n): Morton codes of box centres -> radix sort -> Karras
 // hierarchy -> bottom-up refit, emitting 64-byte BvhNodes at nodes[nodeBase ...) and the leaf
 // order.  Returns the root link (node index, or a leaf code when n <= leafSize) and tree depth.
-struct BvhBuildResult { int root; uint32_t nodesUsed; uint32_t depth; };
+struct BvhBuildResult
+{
+	int root; uint32_t nodesUsed; uint32_t depth;
+	// 4-wide nodes per level of the collapsed tree (breadth-first slots: level 0 = the root at nodeBase, level k >= 1 the
+	// next levelNodes[k] slots); nLevels = 0 when the tree was not collapsed level by level.  What rtb_refit4 walks.
+	uint32_t nLevels; uint32_t levelNodes[128];
+};
 int rtb_build(cudaStream_t st, BuildScratch **scratch, const float4 *box_lo, const float4 *box_hi, uint32_t n,
 	uint32_t leafSize, BvhNode *nodes, BvhNode4 *nodes4, uint32_t nodeBase, uint32_t leafBase, uint32_t *leafOrder /* out: leaf slot -> input index */,
 	BvhBuildResult *res);
 void rtb_free_scratch(BuildScratch *s);
+// Refit instead of rebuild (Model::RTPrepare after a MovePos only re-translates bounds, Model.cpp:404,418-419): the
+// 4-wide tree of a model keeps its topology and leaf order, every node's child boxes are recomputed bottom-up, level by
+// level, from the new per-triangle boxes.  leafOrder: global leaf slot -> index into box_lo / box_hi.
+void rtb_refit4(cudaStream_t st, BvhNode4 *nodes4, uint32_t nodeBase, const uint32_t *levelNodes, uint32_t nLevels,
+	const float4 *box_lo, const float4 *box_hi, const uint32_t *leafOrder);
 
 // tri_geom (leaf order) = tri_geom_orig[leafOrder]; tri_slot[orig] = leaf slot
 void rtb_scatter_tris(cudaStream_t st, const float4 *geomOrig, const uint32_t *leafOrder, uint32_t leafBase, uint32_t origBase, uint32_t n,

@@ -11,6 +11,17 @@
 #include <vector>
 #include <stdexcept>
 
+// sample camera of a sub-pixel offset: n' = n + u*(dx*dp) + v*(dy*dp), not re-normalised (scenes.h jittered_camera restates
+// it for both arms; RayTracer.cpp:20-27 is where the reference adds the same multiples of u and v per pixel)
+static Camera rtscenes_jittered(const Camera &base, float dx, float dy)
+{
+	Camera c = base;
+	const double dp = tan(c.fovy * PI / 360) / (c.height / 2);
+	const Vertex n = c.n + c.u * (float)(dx * dp) + c.v * (float)(dy * dp);
+	c.n.x = n.x, c.n.y = n.y, c.n.z = n.z, c.n.w = n.w;
+	return c;
+}
+
 static void fail(const char *what, int code)
 {
 	// The B200 path has no CPU fallback: any library error is fatal and loud.
@@ -331,7 +342,7 @@ void RayTracer::start(const uint8_t type, const int8_t)
 	const bool rowsOnly = shardWorld > 1 && key == outputShardKey;
 	outputShardKey = shardWorld > 1 ? key : 0;
 
-	if (coalesce && type == MY_MODEL_RAYTRACE && !(renderFlags & (RT_FLAG_HIT_IDS | RT_FLAG_STATS | RT_FLAG_BRUTE)))
+	if (coalesce && samples.size() <= 1 && progressiveBands <= 1 && type == MY_MODEL_RAYTRACE && !(renderFlags & (RT_FLAG_HIT_IDS | RT_FLAG_STATS | RT_FLAG_BRUTE)))
 	{
 		// throughput mode: the Scene's batch workers render this frame together with whatever else is waiting
 		rc = residency->ensureWorkers();
@@ -352,10 +363,74 @@ void RayTracer::start(const uint8_t type, const int8_t)
 	rc = rt_set_sm_share(ctx, smShare);
 	if (rc != RT_OK)
 		fail("rt_set_sm_share", rc);
+	lastCtx = ctx;
+	if (samples.size() > 1 && (type == MY_MODEL_RAYTRACE || type == MY_MODEL_REFLECTTEST || type == MY_MODEL_REFRACTTEST))
+	{
+		// n samples per pixel: the band loop of rt_render_supersampled is synchronous, so it runs in the monitor thread
+		std::vector<rt_camera> cams;
+		for (const auto &dxy : samples)
+		{
+			rt_camera c;
+			SceneFlattener::cameraRecord(rtscenes_jittered(scene->cam, dxy.first, dxy.second), c);
+			cams.push_back(c);
+		}
+		monitor = std::thread([this, rowsOnly, rp, cams]
+		{
+			const auto t0 = std::chrono::steady_clock::now();
+			int rc = rt_render_supersampled(ctx, &rp, (uint32_t)cams.size(), cams.data());
+			if (rc == RT_OK)
+				rc = rowsOnly ? rt_read_output_rows(ctx, output, (size_t)width * 3) : rt_read_output(ctx, output, (size_t)width * 3);
+			if (rc != RT_OK)
+			{
+				lastError = rt_last_error();
+				fprintf(stderr, "raytrace_b200: supersampled frame failed (%d): %s\n", rc, lastError.c_str());
+				failed = true;
+			}
+			useTime = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+			isFinish = true;
+		});
+		return;
+	}
+	if (progressiveBands > 1)
+	{
+		// the shard's own tiles, k-th tile = k * world + (rank, or world - 1 - rank in the odd groups of a boustrophedon shard)
+		const uint32_t world = shardWorld > 1 ? shardWorld : 1, rank = shardWorld > 1 ? shardRank : 0;
+		const bool serp = (renderFlags & RT_FLAG_SERPENTINE) && world > 1;
+		const uint32_t tilesInFrame = (uint32_t)(height / 64) * 64u / shardTileRows;
+		uint32_t mine = 0;
+		while (mine * world + ((serp && (mine & 1u)) ? world - 1u - rank : rank) < tilesInFrame) ++mine;
+		const uint32_t per = std::max<uint32_t>(1, (mine + (uint32_t)progressiveBands - 1) / (uint32_t)progressiveBands);
+		bandsDone = 0;
+		memset(output, 127, (size_t)width * height * 3);      // RayTracer.cpp:620: every start() greys the frame, the bands then fill it in
+		monitor = std::thread([this, rp, mine, per]
+		{
+			double total = 0.0;
+			int rc = RT_OK;
+			for (uint32_t k0 = 0; k0 < mine && rc == RT_OK; k0 += per)
+			{
+				rt_render_params band = rp;
+				band.tile_first = k0, band.tile_count = std::min(per, mine - k0);
+				double seconds = 0.0;
+				rc = rt_render_async(ctx, &band);
+				if (rc == RT_OK) rc = rt_wait(ctx, &seconds);
+				if (rc == RT_OK) rc = rt_read_output_rows(ctx, output, (size_t)width * 3);   // only the band's rows
+				total += seconds;
+				if (rc == RT_OK) bandsDone = bandsDone + 1;
+			}
+			if (rc != RT_OK)
+			{
+				lastError = rt_last_error();
+				fprintf(stderr, "raytrace_b200: progressive frame failed (%d): %s\n", rc, lastError.c_str());
+				failed = true;
+			}
+			useTime = total;
+			isFinish = true;
+		});
+		return;
+	}
 	rc = rt_render_async(ctx, &rp);
 	if (rc != RT_OK)
 		fail("rt_render_async", rc);
-	lastCtx = ctx;
 
 	// (rowsOnly, above: a shard reads back only the rows it rendered once `output` holds a frame of the same
 	// shard layout -- the other rows are the 127 fill of RayTracer.cpp:620 and do not change; the first frame of

@@ -10,6 +10,8 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <utility>
+#include <vector>
 #include <thread>
 
 #define MY_MODEL_CHECK 0x1
@@ -76,6 +78,18 @@ public:
 	// protocol; useTime is the time of the launch the frame was part of, readCounters() that launch's totals.
 	// RAYTRACE frames without RT_FLAG_HIT_IDS only; anything else takes the tracer's own pipeline.
 	bool coalesce = false;
+	// Jittered supersampling (BASELINE configs[4]; not in the reference, whose frames are one sample per pixel): with
+	// `samples` holding n > 1 sub-pixel offsets (dx, dy) in [0,1)^2, start() renders n frames through the camera with
+	// its forward vector offset by (dx, dy) pixels -- each quantised by Color::put like a frame of its own -- and
+	// `output` receives their integer mean per channel, accumulated on the GPU (rt_render_supersampled).  Identical to
+	// averaging n start() calls of the reference with the same offsets.
+	std::vector<std::pair<float, float>> samples;
+	// Progressive display (main.cpp:207-208, 246-254: the reference's UI blits `output` every 50 ms while !isFinish and sees
+	// the 64x64 tiles fill in).  With progressiveBands = k > 1 the frame is rendered as k bands of its row tiles, one after
+	// the other, and every band is copied into `output` as soon as it is complete; bandsDone counts them.  Same pixels as
+	// one launch; smaller launches, so it is a display mode, not a throughput mode (own pipeline, one sample per pixel).
+	int progressiveBands = 0;
+	volatile int bandsDone = 0;
 	void completeFrame(double seconds, rt_ctx *renderedBy, const char *error = nullptr);   // called by a batch worker when this tracer's frame is in `output` (or failed / was cancelled)
 	void reserveOutput(size_t bytes);          // frames beyond 2048x2048
 	void wait();                               // block until isFinish

@@ -119,6 +119,21 @@ int rth_scene_camera_set_position(void *h, float x, float y, float z)
 	return 0;
 }
 
+// the jittered sample camera of (dx, dy) as a C-ABI record; the Scene is not changed
+int rth_scene_jittered_camera(void *h, float dx, float dy, rt_camera *out)
+{
+	SceneFlattener::cameraRecord(rtscenes::jittered_camera(((HostScene *)h)->scene.cam, dx, dy), *out);
+	return 0;
+}
+// side*side (dx, dy) pairs of the fixed stratified table (scenes.h stratified_table)
+int rth_stratified_table(int side, int seed, float *out)
+{
+	std::vector<float> t;
+	rtscenes::stratified_table(side, seed, t);
+	for (size_t i = 0; i < t.size(); ++i) out[i] = t[i];
+	return (int)t.size() / 2;
+}
+
 int rth_scene_camera_get_n(void *h, float *xyzw)
 {
 	const Camera &c = ((HostScene *)h)->scene.cam;
@@ -168,6 +183,16 @@ void rth_tracer_set_shard(void *t, int rank, int world, int tileRows)
 	r->shardRank = rank, r->shardWorld = world, r->shardTileRows = tileRows > 0 ? tileRows : 64;
 }
 void rth_tracer_set_flags(void *t, unsigned flags) { ((RayTracer *)t)->renderFlags = flags; }
+// RayTracer::samples: n (dx, dy) sub-pixel offsets; n = 0 or 1 sample at (0, 0) = the plain frame
+int rth_tracer_set_samples(void *t, int n, const float *dxdy)
+{
+	RayTracer *r = (RayTracer *)t;
+	r->samples.clear();
+	for (int i = 0; i < n; ++i) r->samples.push_back(std::make_pair(dxdy[2 * i], dxdy[2 * i + 1]));
+	return 0;
+}
+void rth_tracer_set_progressive(void *t, int bands) { ((RayTracer *)t)->progressiveBands = bands; }
+int rth_tracer_bands_done(void *t) { return ((RayTracer *)t)->bandsDone; }
 void rth_tracer_set_coalesce(void *t, int on) { ((RayTracer *)t)->coalesce = on != 0; }
 void rth_tracer_set_sm_share(void *t, int ctasPerSm) { ((RayTracer *)t)->smShare = ctasPerSm; }
 int rth_tracer_read_hit_ids(void *t, rt_hit_id *ids) { return ((RayTracer *)t)->readHitIds(ids) ? 0 : -1; }

@@ -40,11 +40,35 @@ template<class SceneT> inline void default_lights(SceneT &scene)
 
 // Height field y = 1.5 + 0.6 sin3x cos2.5z + 0.25 sin(9x+1) sin7z on [-4,4]^2, `cells` x `cells`
 // quads split in two, `pside` x `pside` usemtl parts, analytic normals, written as OBJ + MTL.
-inline void write_heightfield(const std::string &obj, const std::string &mtl, int cells, int pside)
+// 24-bit BMP (bottom-up, BGR, width a multiple of 4 so rows carry no padding): what Model::loadtex reads (Model.cpp:283-315)
+inline void write_bmp(const std::string &path, int w, int h)
+{
+	FILE *f = fopen(path.c_str(), "wb");
+	if (!f) { fprintf(stderr, "cannot write %s\n", path.c_str()); exit(2); }
+	const unsigned size = (unsigned)(w * h * 3);
+	unsigned char head[54] = { 'B', 'M' };
+	auto le32 = [&](int off, unsigned v) { head[off] = v & 255, head[off + 1] = (v >> 8) & 255, head[off + 2] = (v >> 16) & 255, head[off + 3] = (v >> 24) & 255; };
+	le32(2, 54 + size), le32(10, 54), le32(14, 40), le32(18, (unsigned)w), le32(22, (unsigned)h);
+	head[26] = 1, head[28] = 24;
+	le32(34, size);
+	fwrite(head, 1, 54, f);
+	for (int y = 0; y < h; ++y)
+		for (int x = 0; x < w; ++x)
+		{
+			// coloured checker with a gradient: every texel differs from its neighbours
+			const int c = ((x / 2 + y / 2) & 1) ? 200 : 40;
+			const unsigned char px[3] = { (unsigned char)((c + 7 * x) & 255), (unsigned char)((255 - c + 5 * y) & 255), (unsigned char)((90 + 11 * x + 13 * y) & 255) };
+			fwrite(px, 1, 3, f);
+		}
+	fclose(f);
+}
+
+inline void write_heightfield(const std::string &obj, const std::string &mtl, int cells, int pside, const std::string &texture = std::string())
 {
 	FILE *fm = fopen(mtl.c_str(), "w");
 	if (!fm) { fprintf(stderr, "cannot write %s\n", mtl.c_str()); exit(2); }
 	fprintf(fm, "newmtl hfa\nKa 0.100000 0.100000 0.100000\nKd 0.100000 0.500000 0.800000\nKs 1.000000 1.000000 1.000000\nNs 100.000000\n");
+	if (!texture.empty()) fprintf(fm, "map_Kd %s\n", texture.c_str());   // -> Model::loadtex of <texture without extension>.bmp (Model.cpp:260-278)
 	fprintf(fm, "newmtl hfb\nKa 0.200000 0.100000 0.100000\nKd 0.800000 0.400000 0.100000\nKs 0.500000 0.500000 0.500000\nNs 20.000000\n");
 	fclose(fm);
 	FILE *fo = fopen(obj.c_str(), "w");
@@ -116,12 +140,13 @@ inline void write_quadblob(const std::string &obj, int rings, int sectors)
 	fclose(fo);
 }
 
-template<class SceneT> inline int add_heightfield(SceneT &scene, const SceneArgs &a, int cells, int pside)
+template<class SceneT> inline int add_heightfield(SceneT &scene, const SceneArgs &a, int cells, int pside, bool textured = false)
 {
 	char tag[64];
-	snprintf(tag, sizeof tag, "/rt_hf_%d_%d", cells, pside);
-	const std::string obj = a.tmpdir + tag + ".obj", mtl = a.tmpdir + tag + ".mtl";
-	write_heightfield(obj, mtl, cells, pside);
+	snprintf(tag, sizeof tag, "/rt_hf_%d_%d%s", cells, pside, textured ? "_tex" : "");
+	const std::string obj = a.tmpdir + tag + ".obj", mtl = a.tmpdir + tag + ".mtl", tex = a.tmpdir + "/rt_tex_16x12.bmp";
+	if (textured) write_bmp(tex, 16, 12);
+	write_heightfield(obj, mtl, cells, pside, textured ? tex : std::string());
 	return scene.AddModel(widen(obj), widen(mtl));
 }
 
@@ -267,6 +292,29 @@ template<class SceneT> inline void build_t_twomesh(SceneT &scene, const SceneArg
 	scene.MovePos(MY_MODEL_OBJECT, q, Vertex(-6.0f, 4.5f, -4.0f));
 }
 
+// f-2: a mesh whose MTL names a texture (map_Kd -> 24-bit BMP through Model::loadtex, per-part texture on the device) next
+// to a model turned by Model::zRotate (Model.cpp:351-393: y/z swap of vertices, normals, part boxes -- and a min/max z that
+// is NOT re-ordered), a mirror sphere to see both again in a reflection
+template<class SceneT> inline void build_t_textured(SceneT &scene, const SceneArgs &a)
+{
+	SceneArgs b = a;
+	if (b.n <= 0) b.n = 32;
+	if (b.parts <= 0) b.parts = 2;
+	default_lights(scene);
+	scene.Lights[1].position = Vertex(2, 9, 13, 1.0f);
+	scene.AddPlane();
+	const int m = add_heightfield(scene, b, b.n, b.parts, true);
+	scene.MovePos(MY_MODEL_OBJECT, m, Vertex(-1.5f, 0, 4));
+	const std::string blob = b.tmpdir + "/rt_blob.obj";
+	write_quadblob(blob, 10, 16);
+	const int q = scene.AddModel(widen(blob), widen(b.tmpdir + "/rt_blob_missing.mtl"));
+	dynamic_cast<Model &>(*scene.Objects[q]).zRotate();
+	scene.MovePos(MY_MODEL_OBJECT, q, Vertex(4.5f, 3.0f, 6.0f));
+	const int s = scene.AddSphere(1.0f);
+	scene.ChgMtl(s, scene.MtlLiby[2]);
+	scene.MovePos(MY_MODEL_OBJECT, s, Vertex(1.5f, 2.4f, 8.5f));
+}
+
 // ---- edge cases ------------------------------------------------------------------------------------
 // nothing to hit: every ray misses (black frame, 1e20 distances)
 template<class SceneT> inline void build_t_empty(SceneT &scene, const SceneArgs &)
@@ -347,6 +395,36 @@ template<class CameraT> inline CameraT orbit_camera(const CameraT &base, int k, 
 	return c;
 }
 
+// ---- jittered supersampling (BASELINE configs[4]) ----------------------------------------------------------
+// side x side stratified sub-pixel offsets in [0,1)^2, fixed by `seed` (a 64-bit LCG: the table is the same in every
+// arm, language and run).  out: side*side (dx, dy) pairs.
+inline void stratified_table(int side, int seed, std::vector<float> &out)
+{
+	unsigned long long s = 0x9E3779B97F4A7C15ULL ^ (unsigned long long)seed;
+	out.clear();
+	for (int j = 0; j < side; ++j)
+		for (int i = 0; i < side; ++i)
+		{
+			s = s * 6364136223846793005ULL + 1442695040888963407ULL;
+			const double a = (double)((s >> 40) & 0xFFFFFFULL) / (double)(1 << 24);
+			s = s * 6364136223846793005ULL + 1442695040888963407ULL;
+			const double b = (double)((s >> 40) & 0xFFFFFFULL) / (double)(1 << 24);
+			out.push_back((float)((i + a) / side)), out.push_back((float)((j + b) / side));
+		}
+}
+
+// sample camera: the forward vector offset by a sub-pixel step, n' = n + u*(dx*dp) + v*(dy*dp) (deliberately NOT
+// re-normalised: primary rays are cam.n + cam.u*(xcur*dp) + cam.v*(ycur*dp), RayTracer.cpp:20-27, so this is the ray
+// through (x + dx, y + dy))
+template<class CameraT> inline CameraT jittered_camera(const CameraT &base, float dx, float dy)
+{
+	CameraT c = base;
+	const double dp = tan(c.fovy * 3.1415926535897932384626433832795 / 360) / (c.height / 2);
+	const Vertex n = c.n + c.u * (float)(dx * dp) + c.v * (float)(dy * dp);
+	c.n.x = n.x, c.n.y = n.y, c.n.z = n.z, c.n.w = n.w;
+	return c;
+}
+
 template<class SceneT> inline bool build(SceneT &scene, const SceneArgs &a)
 {
 	if (a.name == "c1") build_c1(scene, a);
@@ -357,6 +435,7 @@ template<class SceneT> inline bool build(SceneT &scene, const SceneArgs &a)
 	else if (a.name == "t_ballplane") build_t_ballplane(scene, a);
 	else if (a.name == "t_mesh") build_t_mesh(scene, a);
 	else if (a.name == "t_twomesh") build_t_twomesh(scene, a);
+	else if (a.name == "t_textured") build_t_textured(scene, a);
 	else if (a.name == "t_empty") build_t_empty(scene, a);
 	else if (a.name == "t_nolight") build_t_nolight(scene, a);
 	else if (a.name == "t_lights") build_t_lights(scene, a);

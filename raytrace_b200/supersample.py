@@ -8,6 +8,17 @@ n' = n + u*(dx*dp) + v*(dy*dp), dp = tan(fovy*pi/360)/(H/2)  (host/capi.cpp rth_
 import numpy as np
 
 
+def device_table(side=4, seed=0):
+    """the same table as the C++ side computes it (scenes.h stratified_table, float offsets) -- what RayTracer.samples
+    and bench.py's c5 use"""
+    import ctypes as C
+
+    from ._capi import rth
+    buf = (C.c_float * (2 * side * side))()
+    n = rth.rth_stratified_table(side, seed, buf)
+    return [(buf[2 * i], buf[2 * i + 1]) for i in range(n)]
+
+
 def stratified_table(side=4, seed=0):
     """side x side stratified sub-pixel offsets in [0,1)^2, fixed by `seed` (PCG-free LCG, no numpy RNG
     so the table is identical everywhere)."""

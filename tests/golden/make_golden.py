@@ -35,6 +35,8 @@ CASES = [
     ("c2", 960, 576, 5, 16, 0, 0x80),
     ("t_mesh", 640, 384, 3, 0, 0, 0x80),
     ("t_twomesh", 640, 384, 3, 0, 0, 0x80),
+    ("t_textured", 640, 384, 3, 0, 0, 0x80),   # map_Kd + 24-bit BMP on a mesh part, a zRotate()d model, both again in a mirror
+    ("t_textured", 320, 192, 1, 0, 0, 0x04),   # RTtex: the texture lookup alone
     ("c3", 640, 384, 5, 96, 6, 0x80),
     ("c4", 640, 384, 6, 96, 6, 0x80),
     ("t_empty", 256, 128, 2, 0, 0, 0x80),

@@ -25,14 +25,14 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"librt_b200.so does not export {s}"
     assert set(syms) == set(_capi.RT_SYMBOLS), "ctypes table and header disagree"
-    assert _capi.rt.rt_abi_version() == 1
+    assert _capi.rt.rt_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header():
     # sizes the C compiler gives the ABI structs (checked against ctypes mirrors)
     assert C.sizeof(_capi.Vec4) == 16 and C.sizeof(_capi.Material) == 80 and C.sizeof(_capi.Light) == 96
     assert C.sizeof(_capi.Camera) == 96 and C.sizeof(_capi.Prim) == 96 and C.sizeof(_capi.Model) == 64
-    assert C.sizeof(_capi.Part) == 48 and C.sizeof(_capi.HitId) == 20 and C.sizeof(_capi.RenderParams) == 24
+    assert C.sizeof(_capi.Part) == 48 and C.sizeof(_capi.HitId) == 20 and C.sizeof(_capi.RenderParams) == 32
 
 
 @pytest.mark.skipif(os.path.exists("/dev/nvidiactl"), reason="box has a GPU")

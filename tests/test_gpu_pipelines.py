@@ -242,3 +242,66 @@ def test_stop_of_a_coalescing_tracer_leaves_the_others_alone(gpu_present):
                 assert np.array_equal(t.output(), oimg), (rep, k)
     for t in tracers:                                        # every tracer, the stopped ones too, renders correctly afterwards
         assert np.array_equal(t.render(R.MY_MODEL_RAYTRACE), oimg)
+
+
+def test_moving_a_model_refits_its_bvh_instead_of_rebuilding(gpu_present):
+    # f-3: Scene::MovePos of a Model only re-translates bounds in the reference (Model.cpp:404,418-419); here the 4-wide
+    # tree keeps its topology and is refitted level by level from the new triangle boxes -- same frames as a rebuild
+    sc = R.Scene("t_twomesh", 448, 320)
+    t = R.RayTracer(sc)
+    t.maxLevel = 3
+    img = t.render(R.MY_MODEL_RAYTRACE)
+    c0 = t.counters()
+    assert c0.bvh_refit == 0 and np.array_equal(img, oracle_render(sc, 3, want_ids=False)[0])
+    for k, (obj, mv) in enumerate(((1, (0.7, 0.3, -1.1)), (3, (2.5, -1.0, 3.0)), (1, (-6.0, 0.2, 4.0)), (3, (0.001, 0.0, 0.0)))):
+        sc.move(R.MY_MODEL_OBJECT, obj, *mv)               # objects 1 and 3 are the two meshes
+        img = t.render(R.MY_MODEL_RAYTRACE, flags=R.RT_FLAG_HIT_IDS)
+        ids, c = t.hit_ids(), t.counters()
+        oimg, oids, oc = oracle_render(sc, 3)
+        assert np.array_equal(img, oimg), k
+        from parity_util import compare_ids
+        assert compare_ids(ids, oids) == (0, 0)
+        assert (c.primary, c.shadow, c.reflect, c.refract) == (oc.primary, oc.shadow, oc.reflect, oc.refract)
+        assert c.bvh_refit == 1 and c.bvh_nodes == c0.bvh_nodes, k
+    # the refitted tree against brute force (every primitive, no BVH): nothing was lost
+    b = t.render(R.MY_MODEL_RAYTRACE, flags=R.RT_FLAG_BRUTE)
+    assert np.array_equal(b, img)
+    # an edit that is not a pure move rebuilds: hiding the box changes the object list
+    sc.switch(R.MY_MODEL_OBJECT, 2, False)
+    img = t.render(R.MY_MODEL_RAYTRACE)
+    assert t.counters().bvh_refit == 0 and np.array_equal(img, oracle_render(sc, 3, want_ids=False)[0])
+
+
+def test_progressive_output_fills_in_band_by_band(gpu_present):
+    # f-3: main.cpp:207-208,246-254 blits RayTracer::output while !isFinish.  progressiveBands = k renders the frame as k
+    # bands of its row tiles; a band's rows are in `output` -- final -- as soon as bandsDone counts it
+    w, h, level = 1920, 1088, 5
+    sc = R.Scene("c3", w, h, 240, 15)
+    t = R.RayTracer(sc)
+    t.maxLevel = level
+    final = t.render(R.MY_MODEL_RAYTRACE)                      # one launch
+    t.progressiveBands = 17                                   # 17 tiles of 64 rows: one per band
+    seen = []
+    t.start(R.MY_MODEL_RAYTRACE)
+    while not t.isFinish:
+        b = t.bandsDone
+        snap = t.peek_output()
+        seen.append((b, snap))
+        if len(seen) > 4000:
+            break
+    t.wait()
+    assert not t.failed and t.bandsDone == 17
+    assert np.array_equal(t.output(), final)                  # same pixels as the single launch
+    partial = [(b, s) for b, s in seen if 0 < b < 17]
+    assert partial, "the frame finished before a single partial state could be observed"
+    for b, snap in partial:
+        assert np.array_equal(snap[:b * 64], final[:b * 64])  # completed bands are final ...
+    b, snap = seen[0]
+    assert (snap[(b + 1) * 64:] == 127).all()                 # ... the bands not started yet are still grey
+    # a sharded progressive frame (serpentine 8-row tiles): still equal to the oracle's shard
+    t.progressiveBands = 5
+    part = t.render(R.MY_MODEL_RAYTRACE, flags=R.RT_FLAG_SERPENTINE, rank=1, world=3, tile_rows=8)
+    opart = oracle_render(sc, level, want_ids=False, rank=1, world=3, tile_rows=8, flags=R.RT_FLAG_SERPENTINE)[0]
+    assert np.array_equal(part, opart)
+    t.progressiveBands = 0
+    assert np.array_equal(t.render(R.MY_MODEL_RAYTRACE), final)

@@ -21,7 +21,7 @@ GOLDEN = {(c["scene"], c["w"], c["h"], c["level"], c["n"], c["parts"], c["type"]
 
 # (scene, w, h, level, n, parts): the mesh goldens + the deep glass case
 MESH_CASES = [("t_mesh", 640, 384, 3, 0, 0), ("t_twomesh", 640, 384, 3, 0, 0), ("c3", 640, 384, 5, 96, 6),
-              ("c4", 640, 384, 6, 96, 6), ("t_mixed", 320, 192, 8, 0, 0)]
+              ("c4", 640, 384, 6, 96, 6), ("t_mixed", 320, 192, 8, 0, 0), ("t_textured", 640, 384, 3, 0, 0)]
 
 
 def ck(rc):
@@ -122,3 +122,90 @@ def test_full_size_c4_band_against_oracle(gpu_present):
     assert len(rows) == 32 and np.array_equal(full[rows], part[rows])
     again = t.render(R.MY_MODEL_RAYTRACE)
     assert np.array_equal(again, full)                                       # deterministic at 74 M rays
+
+
+# ---- BASELINE configs[4]: jittered supersampling accumulated on the device ------------------------------
+
+def oracle_supersampled(sc, level, table, **kw):
+    """integer mean of len(table) oracle renders through the jittered sample cameras == the definition of an spp frame"""
+    n0 = sc.camera_n()
+    acc = None
+    try:
+        for dx, dy in table:
+            sc.set_camera_n(n0)
+            sc.camera_jitter(dx, dy)
+            f = oracle_render(sc, level, want_ids=False, **kw)[0].astype(np.uint32)
+            acc = f if acc is None else acc + f
+    finally:
+        sc.set_camera_n(n0)
+    return (acc // len(table)).astype(np.uint8)
+
+
+@pytest.mark.parametrize("scene,w,h,level,side", [("t_mesh", 320, 192, 3, 2), ("c4", 256, 192, 4, 4)])
+def test_device_side_supersampling_equals_n_oracle_renders(gpu_present, monkeypatch, scene, w, h, level, side):
+    from raytrace_b200.supersample import device_table
+    table = device_table(side, seed=0)
+    assert len(table) == side * side and all(0.0 <= dx < 1.0 and 0.0 <= dy < 1.0 for dx, dy in table)
+    sc = R.Scene(scene, w, h, 48 if scene == "c4" else 0, 3 if scene == "c4" else 0)
+    want = oracle_supersampled(sc, level, table)
+    single = oracle_render(sc, level, want_ids=False)[0]
+    assert not np.array_equal(want, single)                       # the jitter really moves the samples
+    t = R.RayTracer(sc)
+    t.maxLevel = level
+    t.set_samples(table)
+    got = t.render(R.MY_MODEL_RAYTRACE)
+    assert np.array_equal(got, want)
+    c = t.counters()
+    assert c.primary == side * side * (w // 64 * 64) * (h // 64 * 64)
+    # band by band (what an 8K frame does): the budget forces several launches per frame, same pixels, same ray totals
+    monkeypatch.setenv("RT_B200_SS_PIXELS", str(side * side * (w // 64 * 64) * 64))
+    sc2 = R.Scene(scene, w, h, 48 if scene == "c4" else 0, 3 if scene == "c4" else 0)
+    t2 = R.RayTracer(sc2)
+    t2.maxLevel = level
+    t2.set_samples(table)
+    assert np.array_equal(t2.render(R.MY_MODEL_RAYTRACE), want)
+    c2 = t2.counters()
+    assert (c2.primary, c2.shadow, c2.reflect, c2.refract) == (c.primary, c.shadow, c.reflect, c.refract)
+    assert c2.launches > c.launches
+    # a shard of the supersampled frame (what each GPU of a multi-GPU run renders): serpentine 8-row tiles, rank 1 of 3
+    part = t2.render(R.MY_MODEL_RAYTRACE, flags=R.RT_FLAG_SERPENTINE, rank=1, world=3, tile_rows=8)
+    from raytrace_b200.distributed import bands_of
+    tiles = bands_of(1, 3, h, 8, serpentine=True)
+    rows = [y for y in range(h // 64 * 64) if y // 8 in tiles]
+    other = [y for y in range(h) if y // 8 not in tiles or y >= h // 64 * 64]
+    assert np.array_equal(part[rows], want[rows]) and (part[other] == 127).all()
+    # back to one sample per pixel on the same tracer
+    t2.set_samples([])
+    assert np.array_equal(t2.render(R.MY_MODEL_RAYTRACE), single)
+
+
+def test_tile_window_renders_a_band_of_the_shard(gpu_present):
+    # rt_render_params::tile_first / tile_count: the band mechanism under the supersampling loop, against the oracle
+    w, h, level = 448, 320, 3
+    sc = R.Scene("t_mesh", w, h)
+    full = oracle_render(sc, level, want_ids=False)[0]
+    ctx = R.Context()
+    ctx.upload(sc.flatten())
+    from raytrace_b200.distributed import bands_of
+    for rank, world, tr, serp, first, count in ((0, 1, 64, False, 1, 2), (1, 3, 8, True, 2, 5), (2, 4, 16, False, 0, 1), (0, 2, 8, True, 17, 0)):
+        flags = R.RT_FLAG_SERPENTINE if serp else 0
+        ctx.render_async(R.MY_MODEL_RAYTRACE, level, rank, world, flags | R.RT_FLAG_HIT_IDS, tr, first, count)
+        ctx.wait()
+        img = ctx.read_output(w, h)
+        ids = ctx.hit_ids(w, h)
+        p = R.RenderParams(R.MY_MODEL_RAYTRACE, level, rank, world, flags, tr, first, count)
+        import ctypes as C
+        from parity_util import oracle_lib
+        oimg = np.empty((h, w, 3), np.uint8)
+        oids = np.zeros(w * h, R.HIT_DTYPE)
+        oc = R.Counters()
+        assert oracle_lib().rto_render(sc.flatten(), C.byref(p), oimg.ctypes.data, oids.ctypes.data, C.byref(oc), 8) == 0
+        mine = bands_of(rank, world, h, tr, serpentine=serp)
+        win = mine[first:first + count] if count else mine[first:]
+        rows = [y for y in range(h) if y // tr in win]
+        assert len(rows) == len(win) * tr
+        assert np.array_equal(img[rows], full[rows]) and np.array_equal(img[rows], oimg[rows])
+        assert compare_ids(ids[rows], oids.reshape(h, w)[rows]) == (0, 0)
+        c = ctx.counters()
+        assert (c.primary, c.shadow, c.reflect, c.refract) == (oc.primary, oc.shadow, oc.reflect, oc.refract)
+        assert c.primary == len(rows) * (w // 64 * 64)

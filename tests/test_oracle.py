@@ -89,3 +89,34 @@ def test_oracle_serpentine_shards_tile_the_frame():
     assert sorted(seen) == list(range(16))
     assert bands_of(0, 3, 256, 16, serpentine=True) == [0, 5, 6, 11, 12] and bands_of(2, 3, 256, 16, serpentine=True) == [2, 3, 8, 9, 14, 15]
     assert np.array_equal(acc, full)
+
+
+def test_tile_window_of_the_oracle_partitions_a_shard():
+    # rt_render_params::tile_first / tile_count (the band loop of supersampled frames): the windows of a shard tile it
+    import ctypes as C
+
+    import numpy as np
+
+    import raytrace_b200 as R
+    from parity_util import oracle_lib
+    w, h, level = 192, 192, 2
+    sc = R.Scene("t_mixed", w, h)
+    lib = oracle_lib()
+
+    def render(rank, world, flags, tr, first, count):
+        out = np.empty((h, w, 3), np.uint8)
+        cnt = R.Counters()
+        p = R.RenderParams(R.MY_MODEL_RAYTRACE, level, rank, world, flags, tr, first, count)
+        assert lib.rto_render(sc.flatten(), C.byref(p), out.ctypes.data, None, C.byref(cnt), 4) == 0
+        return out, cnt.primary + cnt.shadow + cnt.reflect + cnt.refract
+    for rank, world, flags, tr in ((0, 1, 0, 64), (1, 2, R.RT_FLAG_SERPENTINE, 8), (2, 3, 0, 16)):
+        whole, rays = render(rank, world, flags, tr, 0, 0)
+        acc, total, first = np.full_like(whole, 127), 0, 0
+        for count in (1, 2, 0):
+            part, r = render(rank, world, flags, tr, first, count)
+            sel = (part != 127).any(axis=(1, 2))
+            assert (acc[sel] == 127).all()          # windows do not overlap
+            acc[sel] = part[sel]
+            total += r
+            first += count
+        assert np.array_equal(acc, whole) and total == rays

@@ -94,24 +94,34 @@ int main(int argc, char **argv)
 		// frame pays it once, a sample must not be charged all of it -- see render_taps.h)
 		long px = 0;
 		std::vector<double> prepares;
+		std::vector<unsigned long long> raysPer;
+		unsigned long long rays = 0;
 		for (int r = 0; r < warmup + repeat; ++r)
 		{
 			double prep = 0, trace = 0;
-			if (orbit > 0) scene.cam = rtscenes::orbit_camera(baseCam, orbitK + r, orbit);
-			px = rt_taps::render_tiles(scene, rayt, width, height, tiles, seed, threads, type, nullptr, &prep, &trace);
-			if (r >= warmup) walls.push_back(trace), prepares.push_back(prep);
+			// timed pass s of `repeat` looks through camera floor(s * orbit / repeat): the passes are spread evenly over the
+			// whole orbit, whatever their number (the cameras of an orbit differ in cost by up to 2x)
+			if (orbit > 0) scene.cam = rtscenes::orbit_camera(baseCam, orbitK + (r >= warmup ? (int)(((long long)(r - warmup) * orbit) / repeat) : r), orbit);
+			// with --counts every pass is counted (a relaxed atomic add per ray and object walk: noise next to a ray's
+			// tens of microseconds), so rays and seconds belong to the same cameras
+			rt_taps::Counts pc;
+			px = rt_taps::render_tiles(scene, rayt, width, height, tiles, seed, threads, type, counts ? &pc : nullptr, &prep, &trace);
+			if (r >= warmup)
+			{
+				walls.push_back(trace), prepares.push_back(prep);
+				raysPer.push_back(pc.primary + pc.shadow + pc.reflect + pc.refract);
+				rays += raysPer.back();
+				cnt = pc;
+			}
 		}
-		unsigned long long rays = 0;
-		if (counts)
-		{
-			rt_taps::render_tiles(scene, rayt, width, height, tiles, seed, threads, type, &cnt);
-			rays = cnt.primary + cnt.shadow + cnt.reflect + cnt.refract;
-		}
+		if (!raysPer.empty()) rays /= raysPer.size();   // rays_per_step = mean over the timed passes
 		printf("{\"scene\":\"%s\",\"arm\":\"%s\",\"w\":%d,\"h\":%d,\"level\":%d,\"threads\":%d,\"tiles\":%d,\"pixels\":%ld,\"rays_per_step\":%llu,\"hash\":\"%016llx\",\"step_s\":[",
 			sa.name.c_str(), rt_taps::arm(), width, height, level, threads, tiles, px, rays, (unsigned long long)fnv1a64(rayt.output, need));
 		for (size_t i = 0; i < walls.size(); ++i) printf("%s%.6f", i ? "," : "", walls[i]);
 		printf("],\"prepare_s\":[");
 		for (size_t i = 0; i < prepares.size(); ++i) printf("%s%.6f", i ? "," : "", prepares[i]);
+		printf("],\"rays_s\":[");
+		for (size_t i = 0; i < raysPer.size(); ++i) printf("%s%llu", i ? "," : "", raysPer[i]);
 		printf("],\"frame_tiles\":%d,\"stratified\":%s}\n", (width / 64) * (height / 64), seed < 0 ? "true" : "false");
 		return 0;
 	}
