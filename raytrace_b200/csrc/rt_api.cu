@@ -1513,7 +1513,7 @@ extern "C" int rt_read_hit_ids(rt_ctx *c, rt_hit_id *ids)
 	{
 		const uint32_t tile = i >> 6, in = i & 63u, tx = tile % tilesX, ty = tile / tilesX;
 		const uint32_t tileRows = c->lastParams.tile_rows ? c->lastParams.tile_rows : 64u;
-		const uint32_t x = tx * 8u + (in & 7u), row = ty * 8u + (in >> 3), band = row / tileRows;
+		const uint32_t x = tx * 8u + (in & 7u), row = ty * 8u + (in >> 3), band = row / tileRows + c->lastTileFirst;
 		const uint32_t y = shard_tile(band, rank, world, (c->lastParams.flags & RT_FLAG_SERPENTINE) && world > 1) * tileRows + row % tileRows;
 		rt_hit_id id = { -1, -1, -1, -1, hp[i].w };
 		const uint32_t h = hid[i].y;
