@@ -142,7 +142,7 @@ struct rt_ctx
 	bool lastCamsGiven = false, lastOutsGiven = false;
 	int schedMode = 0;              // 0 auto, 1 k_frame (one persistent launch per frame), 2 per-level waves (RT_B200_SCHED=auto|frame|waves)
 	bool frameSched = false;        // what the last frame used
-	int travAsync = 0;              // RT_B200_TRAV=async: the wave kernels walk lane-asynchronously (rt_async.cuh; bit-exact, measured slower -- DESIGN.md); default: the batch-synchronous voted walk
+	int travWalk = 0;               // RT_B200_TRAV: how the wave kernels walk the scene -- voted (default: one batch of 32 rays at a time), split (two-stage: rays that enter the last Model's BVH are collected per warp; bit-exact, -5 % instructions, measured 2 % slower), async (rt_async.cuh; bit-exact, measured slower)
 	int waveGen = 1;                // k_wave(0) makes the primary rays itself (RT_B200_WAVE_GENPRIMARY=0: k_raygen writes them first)
 	uint32_t frameEpoch = 0;
 	// several frames in flight on one GPU: a pipeline created by rt_create_shared renders its parent's
@@ -204,7 +204,7 @@ extern "C" int rt_create(int device, rt_ctx **out)
 	if (const char *v = getenv("RT_B200_LEAF_SIZE")) c->leafSize = (uint32_t)atoi(v);
 	if (const char *v = getenv("RT_B200_LEVEL_FACTOR")) c->levelFactor = (float)atof(v);
 	if (const char *v = getenv("RT_B200_SCHED")) c->schedMode = !strcmp(v, "frame") ? 1 : (!strcmp(v, "waves") ? 2 : 0);
-	if (const char *v = getenv("RT_B200_TRAV")) c->travAsync = strcmp(v, "async") == 0;
+	if (const char *v = getenv("RT_B200_TRAV")) c->travWalk = !strcmp(v, "async") ? 1 : (!strcmp(v, "split") ? 2 : 0);
 	c->waveGen = RT_WAVE_GENPRIMARY_DEFAULT;
 	if (const char *v = getenv("RT_B200_WAVE_GENPRIMARY")) c->waveGen = atoi(v);
 	{ static std::atomic<uint32_t> created{0}; c->keepSalt = created.fetch_add(1u); }
@@ -876,8 +876,9 @@ static int render_frames(rt_ctx *c, const rt_render_params *p, uint32_t nFrames,
 			uint32_t items = traceOn ? c->levels[l].capacity : 0;
 			if (shadowOn) items = std::max(items, (uint32_t)std::min<uint64_t>((uint64_t)c->levels[l - 1].capacity * enabledLights, 0x7FFFFFFFu));
 			// the lane-asynchronous walk has no brute-force mode and keeps shadow destinations (light x capacity + slot) in 32 bits
-			const bool async = c->travAsync && !c->S.brute && (!shadowOn || (uint64_t)c->levels[l - 1].capacity * F.n_lights < 0xFFFFFFFFull);
-			rtk_wave(st, c->S, c->dFrame, LS.l[l], LS.l[traceOn ? l + 1 : l], LS.l[l ? l - 1 : 0], c->dWave, l, traceOn, shadowOn, zNear, items, c->sms, stats, c->ctasPerSm, async);
+			int walk = c->travWalk;
+			if (walk == 1 && (c->S.brute || (shadowOn && (uint64_t)c->levels[l - 1].capacity * F.n_lights >= 0xFFFFFFFFull))) walk = 0;
+			rtk_wave(st, c->S, c->dFrame, LS.l[l], LS.l[traceOn ? l + 1 : l], LS.l[l ? l - 1 : 0], c->dWave, l, traceOn, shadowOn, zNear, items, c->sms, stats, c->ctasPerSm, walk);
 			++launches;
 		}
 		if (c->stageTiming) CU(cudaEventRecord(c->evStage[1], st));

@@ -816,6 +816,194 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_wave_async(SceneDev S, const
 	flush_stats<STATS>(ws, st);
 }
 
+// ---- two-stage wave kernel ------------------------------------------------------------------------------
+// k_wave with the scene walk split into head and tail (rt_traverse.cuh "two stages"): per warp, rays that have to walk the
+// last Model's BVH wait in a small shared-memory list until 32 of them are there; finished rays wait in a second list for
+// an epilogue that also runs 32 at a time.  Everything is warp-converged, so the list lengths live in registers.
+struct SplitLists
+{
+	uint4 todo[64];   // closest: slot, best.t, best.id, best.newobj   |   shadow: work index w in .x
+	uint4 fin[64];    // closest: slot, best.t, best.id, best.newobj
+};
+
+// the ray in slot i of level L (or, for primary rays made in place, through its pixel)
+__device__ __forceinline__ RayD wave_ray(const FrameParams &F, const LevelBuf &L, uint32_t i, bool made, float &bwc)
+{
+	RayD ray;
+	if (made)
+	{
+		ray.d = primary_dir(F, i, ray.o);
+		ray.mtlrfr = 1.0f, ray.skip = RT_ID_NONE, ray.type = MY_RAY_BASERAY_, ray.isInside = 0;
+		bwc = 1.0f;
+	}
+	else
+	{
+		ray = load_ray(L, i);
+		bwc = L.ray_d[i].w;
+	}
+	return ray;
+}
+
+template<bool STATS, int CTAS>
+__global__ void __launch_bounds__(RT_BLOCK, CTAS) k_wave_split(SceneDev S, const FrameParams *__restrict__ Fp, LevelBuf L, LevelBuf N, LevelBuf Lprev,
+	WaveState *ws, uint32_t level, uint32_t traceOn, uint32_t shadowOn, float zNear)
+{
+	__shared__ SplitLists lists[RT_BLOCK / 32];
+	SplitLists &Q = lists[threadIdx.x >> 5];
+	const FrameParams &F = *Fp;
+	const uint32_t lane = threadIdx.x & 31u, lt = lanemask_lt();
+	const bool hasTail = scene_has_tail(S);
+	TravStats st = { 0, 0, 0 };
+
+	// ---- phase A: closest hit + surface attributes + children ------------------------------------
+	if (traceOn)
+	{
+		const uint32_t n = ws->count[level] < L.capacity ? ws->count[level] : L.capacity;
+		const uint32_t batch = fetch_batch(n);
+		const bool made = level == 0u && (F.sched_flags & 4u);
+		uint32_t nTodo = 0, nFin = 0;
+		bool dry = n == 0u;
+		while (true)
+		{
+			if (nFin >= 32u || (dry && nTodo == 0u && nFin > 0u))
+			{
+				// ---- epilogue of 32 finished rays ----
+				const uint32_t cnt = nFin < 32u ? nFin : 32u;
+				const bool valid = lane < cnt;
+				const uint4 e = Q.fin[nFin - cnt + (valid ? lane : 0u)];
+				nFin -= cnt;
+				RayD ray;
+				float bwc = 1.0f;
+				if (valid) ray = wave_ray(F, L, e.x, made, bwc);
+				const Best best = { __uint_as_float(e.y), e.z, e.w };
+				trace_epilogue(S, F, L, N, ws, level, zNear, valid, e.x, ray, bwc, made, best);
+				__syncwarp();
+			}
+			else if (nTodo >= 32u || (dry && nTodo > 0u))
+			{
+				// ---- tail: 32 rays that passed the last Model's box test walk its BVH, full lanes ----
+				const uint32_t cnt = nTodo < 32u ? nTodo : 32u;
+				const bool valid = lane < cnt;
+				const uint4 e = Q.todo[nTodo - cnt + (valid ? lane : 0u)];
+				nTodo -= cnt;
+				Best best = { __uint_as_float(e.y), e.z, e.w };
+				if (valid)
+				{
+					float bwc;
+					const RayD ray = wave_ray(F, L, e.x, made, bwc);
+					bool done = false;
+					trace_scene_tail<false, STATS>(S, ray, best, done, st);
+				}
+				__syncwarp();
+				if (valid) Q.fin[nFin + lane] = make_uint4(e.x, __float_as_uint(best.t), best.id, best.newobj);
+				nFin += cnt;
+				__syncwarp();
+			}
+			else if (!dry)
+			{
+				// ---- head: 32 new rays, everything before the last Model's BVH ----
+				const uint32_t base = warp_fetch(&ws->head_trace[level], batch);
+				if (base >= n || frame_cancelled(ws, F))
+				{
+					dry = true;
+					continue;
+				}
+				const uint32_t i = lane < batch ? base + lane : 0xFFFFFFFFu;
+				const bool valid = i < n;
+				bool enter = false;
+				Best best = { 1e20f, RT_ID_NONE, RT_ID_NONE };
+				if (valid)
+				{
+					float bwc;
+					const RayD ray = wave_ray(F, L, i, made, bwc);
+					best.newobj = ray.skip;
+					bool done = false;
+					enter = trace_scene_head<false, STATS>(S, ray, best, done, st, hasTail);
+				}
+				const uint32_t mT = __ballot_sync(0xffffffffu, valid && enter), mF = __ballot_sync(0xffffffffu, valid && !enter);
+				const uint4 rec = make_uint4(i, __float_as_uint(best.t), best.id, best.newobj);
+				if (valid && enter) Q.todo[nTodo + __popc(mT & lt)] = rec;
+				if (valid && !enter) Q.fin[nFin + __popc(mF & lt)] = rec;
+				nTodo += __popc(mT), nFin += __popc(mF);
+				if (base + batch >= n) dry = true;
+				__syncwarp();
+			}
+			else
+				break;
+		}
+	}
+
+	// ---- phase B: shadow any-hit of the previous level's surfaces -----------------------------------
+	if (shadowOn)
+	{
+		__syncwarp();
+		const uint32_t lp = level - 1u;
+		const uint32_t nHit = ws->n_hit[lp];
+		const uint32_t n = nHit * F.n_enabled;
+		const uint32_t batch = fetch_batch(n);
+		const uint8_t rayType = (F.type == RT_TYPE_REFLECT || F.type == RT_TYPE_SHADOW) ? 0 : MY_RAY_SHADOWRAY_;
+		uint32_t nTodo = 0;
+		bool dry = n == 0u;
+		while (true)
+		{
+			const bool tail = nTodo >= 32u || (dry && nTodo > 0u);
+			if (!tail && dry)
+				break;
+			uint32_t w = 0xFFFFFFFFu;
+			if (tail)
+			{
+				const uint32_t cnt = nTodo < 32u ? nTodo : 32u;
+				if (lane < cnt) w = Q.todo[nTodo - cnt + lane].x;
+				nTodo -= cnt;
+			}
+			else
+			{
+				const uint32_t base = warp_fetch(&ws->head_shadow[lp], batch);
+				if (base >= n || frame_cancelled(ws, F))
+				{
+					dry = true;
+					continue;
+				}
+				if (lane < batch && base + lane < n) w = base + lane;
+				if (base + batch >= n) dry = true;
+			}
+			bool enter = false;
+			if (w != 0xFFFFFFFFu)
+			{
+				// the shadow ray of work item w = (enabled light w / n_hit, surface w % n_hit); made again for the tail (a few
+				// L2 hits and one normalisation against 16 bytes of shared memory per waiting ray)
+				const uint32_t k = F.enabled_index[w / nHit], i = Lprev.hit_list[w % nHit] - 1u;
+				const float4 hp = Lprev.hit_p[i];
+				RayD ray;
+				float dis, lum;
+				light_dir(F.lights[k], f3(hp), ray.d, dis, lum);
+				ray.o = f3(hp);
+				ray.mtlrfr = 1.0f;
+				ray.skip = Lprev.hit_id[i].y;
+				ray.type = rayType;
+				ray.isInside = 0;
+				Best best = { dis, RT_ID_NONE, RT_ID_NONE };
+				bool done = false;
+				if (tail)
+					trace_scene_tail<true, STATS>(S, ray, best, done, st);
+				else
+					enter = trace_scene_head<true, STATS>(S, ray, best, done, st, hasTail);
+				if (!enter)
+					Lprev.shadow[(size_t)k * Lprev.capacity + i] = done ? 1 : 0;
+			}
+			__syncwarp();
+			if (!tail)
+			{
+				const uint32_t mT = __ballot_sync(0xffffffffu, enter);
+				if (enter) Q.todo[nTodo + __popc(mT & lt)].x = w;
+				nTodo += __popc(mT);
+				__syncwarp();
+			}
+		}
+	}
+	flush_stats<STATS>(ws, st);
+}
+
 // ---- whole-frame persistent scheduler ---------------------------------------------------------------
 //
 // One launch traces every ray of the frame.  Resident warps repeatedly take a batch of rays from
@@ -1657,11 +1845,19 @@ static int traversal_ctas_per_sm()
 }
 
 void rtk_wave(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const LevelBuf &N, const LevelBuf &Lprev, WaveState *ws,
-	uint32_t level, bool traceOn, bool shadowOn, float zNear, uint32_t maxItems, unsigned sms, bool stats, unsigned ctasPerSm, bool async)
+	uint32_t level, bool traceOn, bool shadowOn, float zNear, uint32_t maxItems, unsigned sms, bool stats, unsigned ctasPerSm, int walk)
 {
 	const int occ = traversal_ctas_per_sm();
 	const unsigned g = grid_for(maxItems, RT_BLOCK, sms * (ctasPerSm && (int)ctasPerSm < occ ? ctasPerSm : occ));   // persistent: all CTAs resident
-	if (async)
+	if (walk == 2)
+	{
+		// two-stage walk: rays that enter the last Model's BVH are collected per warp, so its walk starts with full lanes
+		if (stats) k_wave_split<true, RT_CTAS_PER_SM><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+		else if (occ == 6) k_wave_split<false, 6><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+		else k_wave_split<false, RT_CTAS_PER_SM><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+		return;
+	}
+	if (walk == 1)
 	{
 		// lane-asynchronous walk (rt_async.cuh); shadow destinations are 32-bit indices there
 		if (stats) k_wave_async<true, RT_CTAS_PER_SM><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);

@@ -490,3 +490,115 @@ __device__ __forceinline__ void trace_scene(const SceneDev &S, const RayD &ray, 
 			return;
 	}
 }
+
+// ---- the scene walk in two stages ------------------------------------------------------------------------------------
+// Measured on C3 (RT_FLAG_STATS histogram): 60 % of the closest-hit rays and 45 % of the shadow rays never enter the mesh's
+// BVH -- they miss the Model's box (sky, rays leaving the height field) -- while the others visit 4..15 nodes.  In a batch of
+// 32 rays the lanes of the former idle through the whole walk of the latter.  The wave kernels therefore run the walk in
+// two stages: `head` = everything up to and including the box test of the LAST scene item when that item is a Model
+// (RayTracer.cpp:458-465 visits the objects in order; Model.cpp:752 is the box test), `tail` = the walk of that Model's
+// BVH.  Rays that pass the box test are collected per warp until 32 of them are there, so the tail always starts with full
+// lanes.  The per-ray arithmetic and the order of the objects are those of trace_scene.
+__device__ __forceinline__ bool scene_has_tail(const SceneDev &S)
+{
+	return S.n_items > 0u && !S.brute && S.items[S.n_items - 1u].kind == RT_ITEM_MODEL && S.items[S.n_items - 1u].count > 0u;
+}
+
+// -> true: the ray passed the last Model's box test and its BVH has to be walked (trace_scene_tail); false: the ray is
+// through (any-hit: `done` says occluded)
+template<bool ANY, bool STATS>
+__device__ __forceinline__ bool trace_scene_head(const SceneDev &S, const RayD &ray, Best &best, bool &done, TravStats &st, bool hasTail)
+{
+	const F3 idir = f3(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
+	const uint32_t nHead = hasTail ? S.n_items - 1u : S.n_items;
+	for (uint32_t i = 0; i < nHead; ++i)
+	{
+		const SceneItem it = S.items[i];
+		if (it.kind == RT_ITEM_PRIM)
+		{
+			if (STATS) ++st.prims;
+			test_prim<ANY>(S, ray, it.first, false, best, done);
+		}
+		else if (S.brute && it.kind == RT_ITEM_PRIMBVH)
+		{
+			for (uint32_t p = it.first; p < it.first + it.count; ++p)
+			{
+				if (STATS) ++st.prims;
+				test_prim<ANY>(S, ray, p, false, best, done);
+				if (ANY && done)
+					return false;
+			}
+		}
+		else if (it.kind == RT_ITEM_PRIMBVH)
+		{
+			const uint32_t end = it.first + it.count;
+			if (!ANY && ray.isInside && !(ray.skip & RT_ID_TRI) && ray.skip >= it.first && ray.skip < end)
+			{
+				traverse<ANY, false, false, STATS>(S, ray, idir, it.root, best.t, it.first, end, best, done, st, it.first, ray.skip);
+				if (STATS) ++st.prims;
+				test_prim<ANY>(S, ray, ray.skip, false, best, done);
+				traverse<ANY, false, false, STATS>(S, ray, idir, it.root, best.t, it.first, end, best, done, st, ray.skip + 1u, end);
+			}
+			else
+				traverse<ANY, false, false, STATS>(S, ray, idir, it.root, best.t, it.first, end, best, done, st);
+		}
+		else
+		{
+			const DevModel &M = S.models[it.first];
+			const float4 mn = __ldg(&M.border_min), mx = __ldg(&M.border_max);
+			if (!(border_test(ray.o, ray.d, idir, f3(mn), f3(mx)) < best.t))
+				continue;
+			const uint32_t tb = __ldg(&M.tri_begin);
+			if (S.brute)
+			{
+				const uint32_t te = tb + __ldg(&M.tri_count);
+				PartCache pc;
+				pc.part = 0xFFFFFFFFu, pc.mask = 0;
+				bool slow = false;
+				leaf_tris<ANY, false, STATS>(S, ray, idir, tb, te - tb, best.t, tb, te, pc, best, done, slow, st);
+			}
+			else if (ANY)
+				traverse<true, true, false, STATS>(S, ray, idir, it.root, best.t, tb, tb + __ldg(&M.tri_count), best, done, st);
+			else
+			{
+				const Best before = best;
+				traverse<false, true, true, STATS>(S, ray, idir, it.root, before.t, tb, tb + __ldg(&M.tri_count), best, done, st);
+				if (best.t < 0.0f)
+				{
+					best = before;
+					traverse<false, true, false, STATS>(S, ray, idir, it.root, before.t, tb, tb + __ldg(&M.tri_count), best, done, st);
+				}
+			}
+		}
+		if (ANY && done)
+			return false;
+	}
+	if (!hasTail)
+		return false;
+	// Model.cpp:752: `if (BorderTest(ray, BorderMin, BorderMax) < hr.distance)`
+	const DevModel &M = S.models[S.items[S.n_items - 1u].first];
+	const float4 mn = __ldg(&M.border_min), mx = __ldg(&M.border_max);
+	return border_test(ray.o, ray.d, idir, f3(mn), f3(mx)) < best.t;
+}
+
+template<bool ANY, bool STATS>
+__device__ __forceinline__ void trace_scene_tail(const SceneDev &S, const RayD &ray, Best &best, bool &done, TravStats &st)
+{
+	const F3 idir = f3(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
+	const SceneItem it = S.items[S.n_items - 1u];
+	const DevModel &M = S.models[it.first];
+	const uint32_t tb = __ldg(&M.tri_begin), te = tb + __ldg(&M.tri_count);
+	if (ANY)
+		traverse<true, true, false, STATS>(S, ray, idir, it.root, best.t, tb, te, best, done, st);
+	else
+	{
+		const Best before = best;
+		traverse<false, true, true, STATS>(S, ray, idir, it.root, before.t, tb, te, best, done, st);
+		if (best.t < 0.0f)
+		{
+			best = before;
+			traverse<false, true, false, STATS>(S, ray, idir, it.root, before.t, tb, te, best, done, st);
+		}
+	}
+}
+
