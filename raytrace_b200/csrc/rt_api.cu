@@ -71,9 +71,9 @@ struct LevelStore
 	DevBuf<uint2> ray_meta, hit_id;
 	DevBuf<int4> aux;
 	DevBuf<uint8_t> shadow;
-	DevBuf<uint32_t> hit_list;
+	DevBuf<uint32_t> hit_list, order, sort_key;
 	uint32_t capacity = 0, lights = 0;
-	void release() { ray_o.release(), ray_d.release(), hit_p.release(), color.release(), ray_meta.release(), hit_id.release(), aux.release(), shadow.release(), hit_list.release(), hit_n.release(), hit_uv.release(); capacity = 0; }
+	void release() { ray_o.release(), ray_d.release(), hit_p.release(), color.release(), ray_meta.release(), hit_id.release(), aux.release(), shadow.release(), hit_list.release(), hit_n.release(), hit_uv.release(), order.release(), sort_key.release(); capacity = 0; }
 };
 
 struct rt_ctx
@@ -116,6 +116,16 @@ struct rt_ctx
 	DevBuf<DevPart> dParts;
 	DevBuf<BvhNode> nodes;      // binary LBVH (build-time only)
 	DevBuf<BvhNode4> nodes4;    // 4-wide collapse used by the traversal
+	DevBuf<BvhNode8> nodes8;    // 8-wide quantised collapse of the Model BVHs (RT_BVH8)
+	uint32_t bvhStackNeed = 0;  // deepest traversal stack any path of the 8-wide trees can need
+	// Coherence binning of the secondary rays (wave scheduler, rtk_bin_rays).  RT_B200_BIN = cell bits per axis, 0 = off;
+	// unset = auto: 3 bits when the scene refracts -- binary ray trees interleave the reflect and refract children of every
+	// parent warp in the queues (c4: +32 %) -- and off otherwise, where the queues inherit the screen-space order of the
+	// primary rays and binning only costs its three launches per level (c3: -8 %, c2: -7 %; profiles/r2_binning.md)
+	int binMode = -1;
+	uint32_t binBits = 0;
+	BinGrid binGrid = { { 0, 0, 0 }, { 1, 1, 1 }, 1, 7 };
+	DevBuf<uint32_t> binHist;
 	DevBuf<SceneItem> items;
 	SceneDev S;
 	BuildScratch *scratch = nullptr;
@@ -142,7 +152,7 @@ struct rt_ctx
 	bool lastCamsGiven = false, lastOutsGiven = false;
 	int schedMode = 0;              // 0 auto, 1 k_frame (one persistent launch per frame), 2 per-level waves (RT_B200_SCHED=auto|frame|waves)
 	bool frameSched = false;        // what the last frame used
-	int travWalk = 0;               // RT_B200_TRAV: how the wave kernels walk the scene -- voted (default: one batch of 32 rays at a time), split (two-stage: rays that enter the last Model's BVH are collected per warp; bit-exact, -5 % instructions, measured 2 % slower), async (rt_async.cuh; bit-exact, measured slower)
+	int travWalk = 0;               // RT_B200_TRAV: how the wave kernels walk the scene -- voted (default: one batch of 32 rays at a time), split (two-stage: rays that enter the last Model's BVH are collected per warp; bit-exact, -5 % instructions, measured 2 % slower)
 	int waveGen = 1;                // k_wave(0) makes the primary rays itself (RT_B200_WAVE_GENPRIMARY=0: k_raygen writes them first)
 	uint32_t frameEpoch = 0;
 	// several frames in flight on one GPU: a pipeline created by rt_create_shared renders its parent's
@@ -204,7 +214,8 @@ extern "C" int rt_create(int device, rt_ctx **out)
 	if (const char *v = getenv("RT_B200_LEAF_SIZE")) c->leafSize = (uint32_t)atoi(v);
 	if (const char *v = getenv("RT_B200_LEVEL_FACTOR")) c->levelFactor = (float)atof(v);
 	if (const char *v = getenv("RT_B200_SCHED")) c->schedMode = !strcmp(v, "frame") ? 1 : (!strcmp(v, "waves") ? 2 : 0);
-	if (const char *v = getenv("RT_B200_TRAV")) c->travWalk = !strcmp(v, "async") ? 1 : (!strcmp(v, "split") ? 2 : 0);
+	if (const char *v = getenv("RT_B200_TRAV")) c->travWalk = !strcmp(v, "split") ? 2 : (!strcmp(v, "defer") ? 3 : 0);
+	if (const char *v = getenv("RT_B200_BIN")) { int b = atoi(v); c->binMode = b < 0 ? 0 : (b > 6 ? 6 : b); }
 	c->waveGen = RT_WAVE_GENPRIMARY_DEFAULT;
 	if (const char *v = getenv("RT_B200_WAVE_GENPRIMARY")) c->waveGen = atoi(v);
 	{ static std::atomic<uint32_t> created{0}; c->keepSalt = created.fetch_add(1u); }
@@ -242,6 +253,7 @@ static void adopt_scene(rt_ctx *c)
 		c->prims = p->prims, c->models = p->models, c->parts = p->parts, c->adoptedTables = p->tablesVersion;
 	c->lights = p->lights;
 	c->camera = p->camera, c->envLight = p->envLight, c->anyRefract = p->anyRefract, c->nTris = p->nTris;
+	c->binGrid = p->binGrid, c->binBits = p->binBits;
 	c->S = p->S, c->bvhNodes = p->bvhNodes, c->bvhDepth = p->bvhDepth, c->leafSize = p->leafSize;
 	c->uploadMs = p->uploadMs, c->buildMs = p->buildMs, c->uploadBytes = p->uploadBytes;
 	c->adoptedVersion = p->sceneVersion;
@@ -257,7 +269,7 @@ extern "C" void rt_destroy(rt_ctx *c)
 	c->primGeom.release(), c->materials.release(), c->triPoints.release(), c->triNorms.release(), c->triGeomOrig.release(), c->triGeom.release();
 	c->boxLo.release(), c->boxHi.release(), c->partMid.release(), c->partPos.release(), c->primMeta.release(), c->textures.release(), c->texels.release();
 	c->triTcoords.release(), c->bvhPrims.release(), c->triSlot.release(), c->triPart.release(), c->leafOrder.release(), c->leafOrderAll.release();
-	c->dModels.release(), c->dParts.release(), c->nodes.release(), c->nodes4.release(), c->items.release(), c->out.release();
+	c->dModels.release(), c->dParts.release(), c->nodes.release(), c->nodes4.release(), c->nodes8.release(), c->items.release(), c->out.release();
 	for (auto &b : c->batchOut) b.release();
 	rtb_free_scratch(c->scratch);
 	cudaFreeHost(c->hFrame), cudaFree(c->dFrame), cudaFreeHost(c->hWave), cudaFreeHost(c->hWaveInit), cudaFree(c->dWave);
@@ -469,7 +481,11 @@ static int upload_scene_tables(rt_ctx *c, const rt_scene_desc *s, bool hadScene)
 			rtb_prepare_tris(st, a);
 			rtb_scatter_tris(st, c->triGeomOrig.p, c->leafOrderAll.p + M.tri_begin, M.tri_begin, M.tri_begin, M.tri_count, c->triGeom.p, c->triSlot.p);
 			const std::vector<uint32_t> &lv = c->modelLevels[m];
+#if RT_BVH8
+			rtb_refit8(st, c->nodes8.p, c->modelNodeBase[m], lv.data(), (uint32_t)lv.size(), c->boxLo.p, c->boxHi.p, c->leafOrderAll.p);
+#else
 			rtb_refit4(st, c->nodes4.p, c->modelNodeBase[m], lv.data(), (uint32_t)lv.size(), c->boxLo.p, c->boxHi.p, c->leafOrderAll.p);
+#endif
 		}
 		CU(cudaGetLastError());
 		CU(cudaEventRecord(c->evStop, st));
@@ -563,6 +579,9 @@ static int upload_scene_tables(rt_ctx *c, const rt_scene_desc *s, bool hadScene)
 		}
 		CU(c->nodes.reserve(nodeBudget + 1));
 		CU(c->nodes4.reserve(nodeBudget + 1));
+#if RT_BVH8
+		CU(c->nodes8.reserve(nodeBudget + 1));
+#endif
 		CU(c->bvhPrims.reserve(primLeafSlots + 1));
 		CU(c->triGeomOrig.reserve(3 * (size_t)s->n_tris + 1));
 		CU(c->triGeom.reserve(RT_TRI_F4 * (size_t)s->n_tris + 1));
@@ -579,7 +598,7 @@ static int upload_scene_tables(rt_ctx *c, const rt_scene_desc *s, bool hadScene)
 		cudaEvent_t b0 = c->evB;
 		CU(cudaEventRecord(b0, st));
 		uint32_t nodeCursor = 0, primLeafCursor = 0;
-		c->bvhDepth = 0;
+		c->bvhDepth = 0, c->bvhStackNeed = 0;
 		for (SceneItem &it : items)
 		{
 			BvhBuildResult res;
@@ -604,7 +623,8 @@ static int upload_scene_tables(rt_ctx *c, const rt_scene_desc *s, bool hadScene)
 				a.tri_geom_orig = c->triGeomOrig.p + 3 * (size_t)M.tri_begin, a.box_lo = c->boxLo.p, a.box_hi = c->boxHi.p, a.n = M.tri_count;
 				a.id_base = M.tri_begin;
 				rtb_prepare_tris(st, a);
-				int rc = rtb_build(st, &c->scratch, c->boxLo.p, c->boxHi.p, M.tri_count, c->leafSize, c->nodes.p, c->nodes4.p, nodeCursor, M.tri_begin, c->leafOrder.p, &res);
+				int rc = rtb_build(st, &c->scratch, c->boxLo.p, c->boxHi.p, M.tri_count, c->leafSize, c->nodes.p, c->nodes4.p, nodeCursor, M.tri_begin, c->leafOrder.p, &res, RT_BVH8 ? c->nodes8.p : nullptr);
+				c->bvhStackNeed = std::max(c->bvhStackNeed, res.maxStack);
 				if (rc) return fail(RT_E_CUDA, "LBVH build (model %u) failed: %s", it.first, cudaGetErrorString((cudaError_t)rc));
 				rtb_scatter_tris(st, c->triGeomOrig.p, c->leafOrder.p, M.tri_begin, M.tri_begin, M.tri_count, c->triGeom.p, c->triSlot.p);
 				// kept for refits after position-only edits: the leaf order (global slot -> model-local triangle) and the level table
@@ -620,6 +640,9 @@ static int upload_scene_tables(rt_ctx *c, const rt_scene_desc *s, bool hadScene)
 		// a 4-wide step pushes up to three siblings and descends two binary levels
 		if (3 * ((c->bvhDepth + 1) / 2) + 1 > RT_STACK)
 			return fail(RT_E_LIMIT, "LBVH depth %u exceeds the traversal stack (%d)", c->bvhDepth, RT_STACK);
+		// an 8-wide step pushes up to seven siblings: the collapse reports the deepest need over all root-to-leaf paths
+		if (c->bvhStackNeed + 1 > RT_STACK)
+			return fail(RT_E_LIMIT, "8-wide BVH needs %u traversal stack slots (%d)", c->bvhStackNeed + 1, RT_STACK);
 		CU(c->items.upload(items.data(), items.size(), st, ub));
 		CU(cudaEventRecord(c->evStop, st));
 		CU(cudaStreamSynchronize(st));
@@ -631,8 +654,29 @@ static int upload_scene_tables(rt_ctx *c, const rt_scene_desc *s, bool hadScene)
 		S.prim_geom = c->primGeom.p, S.prim_meta = c->primMeta.p, S.bvh_prims = c->bvhPrims.p;
 		S.models = c->dModels.p, S.parts = c->dParts.p;
 		S.tri_geom = c->triGeom.p, S.tri_norms = c->triNorms.p, S.tri_tcoords = c->triTcoords.p;
-		S.tri_slot = c->triSlot.p, S.tri_part = c->triPart.p, S.nodes4 = c->nodes4.p, S.items = c->items.p;
+		S.tri_slot = c->triSlot.p, S.tri_part = c->triPart.p, S.nodes4 = c->nodes4.p, S.nodes8 = c->nodes8.p, S.items = c->items.p;
 		S.n_items = (uint32_t)items.size(), S.n_prims = s->n_prims, S.n_tris = s->n_tris, S.n_parts = s->n_parts;
+	}
+	{
+		// grid of the coherence binning: the bounded objects of the scene (planes are infinite; origins beyond the grid clamp)
+		float lo[3] = { 3e38f, 3e38f, 3e38f }, hi[3] = { -3e38f, -3e38f, -3e38f };
+		auto grow = [&](float x, float y, float z) { const float v[3] = { x, y, z }; for (int a = 0; a < 3; ++a) lo[a] = std::min(lo[a], v[a]), hi[a] = std::max(hi[a], v[a]); };
+		for (const rt_model &M : c->models) { grow(M.ver_min.x + M.position.x, M.ver_min.y + M.position.y, M.ver_min.z + M.position.z); grow(M.ver_max.x + M.position.x, M.ver_max.y + M.position.y, M.ver_max.z + M.position.z); }
+		for (const rt_prim &P : c->prims)
+		{
+			if (P.kind == RT_OBJ_SPHERE) { grow(P.position.x - P.radius, P.position.y - P.radius, P.position.z - P.radius); grow(P.position.x + P.radius, P.position.y + P.radius, P.position.z + P.radius); }
+			else if (P.kind == RT_OBJ_CUBE) { grow(P.a.x + P.position.x, P.a.y + P.position.y, P.a.z + P.position.z); grow(P.b.x + P.position.x, P.b.y + P.position.y, P.b.z + P.position.z); }
+		}
+		c->binBits = c->binMode >= 0 ? (uint32_t)c->binMode : (c->anyRefract ? 3u : 0u);
+		const uint32_t bits = c->binBits ? c->binBits : 1u;
+		c->binGrid.bits = bits;
+		{ const char *e = getenv("RT_B200_BIN_KEY"); c->binGrid.parts = e ? (uint32_t)atoi(e) : 7u; }
+		for (int a = 0; a < 3; ++a)
+		{
+			const float ext = hi[a] > lo[a] ? hi[a] - lo[a] : 1.0f;
+			c->binGrid.lo[a] = hi[a] >= lo[a] ? lo[a] : 0.0f;
+			c->binGrid.scale[a] = (float)(1u << bits) / ext;
+		}
 	}
 	c->S.materials = c->materials.p, c->S.textures = c->textures.p, c->S.texels = c->texels.p;
 	if (c->uploadBytes)
@@ -649,10 +693,12 @@ static int upload_scene_tables(rt_ctx *c, const rt_scene_desc *s, bool hadScene)
 static int ensure_level(rt_ctx *c, uint32_t l, uint32_t cap, uint32_t lights)
 {
 	LevelStore &L = c->levels[l];
+	if (c->binBits && l >= 1 && L.order.cap < std::max<size_t>(cap, L.capacity)) { CU(L.order.reserve(std::max<size_t>(cap, L.capacity))); CU(L.sort_key.reserve(std::max<size_t>(cap, L.capacity))); }
 	if (cap <= L.capacity && lights <= L.lights) return RT_OK;
 	L.capacity = 0;
 	CU(L.ray_o.reserve(cap)); CU(L.ray_d.reserve(cap)); CU(L.ray_meta.reserve(cap)); CU(L.hit_p.reserve(cap));
 	CU(L.hit_id.reserve(cap)); CU(L.color.reserve(cap)); CU(L.aux.reserve(cap)); CU(L.shadow.reserve((size_t)cap * (lights ? lights : 1))); CU(L.hit_list.reserve(cap)); CU(L.hit_n.reserve(cap)); CU(L.hit_uv.reserve(cap));
+	if (c->binBits && l >= 1) { CU(L.order.reserve(cap)); CU(L.sort_key.reserve(cap)); }   // (reserve keeps a large enough buffer)
 	// k_frame recognises a written slot by the epoch in ray_meta: fresh memory must not look written
 	CU(cudaMemsetAsync(L.ray_meta.p, 0, sizeof(uint2) * L.ray_meta.cap, c->stream));
 	CU(cudaMemsetAsync(L.hit_list.p, 0, sizeof(uint32_t) * L.hit_list.cap, c->stream));
@@ -665,6 +711,7 @@ static LevelBuf level_buf(const LevelStore &L)
 	LevelBuf b;
 	b.ray_o = L.ray_o.p, b.ray_d = L.ray_d.p, b.ray_meta = L.ray_meta.p, b.hit_p = L.hit_p.p, b.hit_id = L.hit_id.p;
 	b.color = L.color.p, b.aux = L.aux.p, b.shadow = L.shadow.p, b.hit_list = L.hit_list.p, b.hit_n = L.hit_n.p, b.hit_uv = L.hit_uv.p, b.capacity = L.capacity;
+	b.order = nullptr, b.sort_key = L.sort_key.p;   // order is switched on per frame by the wave scheduler
 	return b;
 }
 
@@ -855,6 +902,10 @@ static int render_frames(rt_ctx *c, const rt_render_params *p, uint32_t nFrames,
 
 	const bool stats = (p->flags & RT_FLAG_STATS) != 0;
 	c->S.brute = (p->flags & RT_FLAG_BRUTE) ? 1u : 0u;
+	{
+		static const uint32_t trig = []{ const char *e = getenv("RT_B200_DQ"); int v = e ? atoi(e) : 4; return (uint32_t)(v < 1 ? 1 : (v > 64 ? 64 : v)); }();
+		c->S.dq_trigger = trig;
+	}
 	uint32_t launches = 0;
 	if (nPix)
 	{
@@ -875,9 +926,15 @@ static int render_frames(rt_ctx *c, const rt_render_params *p, uint32_t nFrames,
 			const float zNear = l == 0 ? F.zNear : 0.0f;
 			uint32_t items = traceOn ? c->levels[l].capacity : 0;
 			if (shadowOn) items = std::max(items, (uint32_t)std::min<uint64_t>((uint64_t)c->levels[l - 1].capacity * enabledLights, 0x7FFFFFFFu));
-			// the lane-asynchronous walk has no brute-force mode and keeps shadow destinations (light x capacity + slot) in 32 bits
-			int walk = c->travWalk;
-			if (walk == 1 && (c->S.brute || (shadowOn && (uint64_t)c->levels[l - 1].capacity * F.n_lights >= 0xFFFFFFFFull))) walk = 0;
+			const int walk = c->travWalk;
+			if (c->binBits && traceOn && l >= 1 && walk != 2 && !debugStage && c->levels[l].order.p)
+			{
+				// coherence binning of this level's rays; k_wave(l) then fetches them through `order`
+				if (!c->binHist.p) CU(c->binHist.reserve((size_t)1u << (3u * 6u + 4u)));
+				LS.l[l].order = c->levels[l].order.p;
+				rtk_bin_rays(st, LS.l[l], c->dWave, l, c->binGrid, c->binHist.p, c->sms);
+				launches += 3;
+			}
 			rtk_wave(st, c->S, c->dFrame, LS.l[l], LS.l[traceOn ? l + 1 : l], LS.l[l ? l - 1 : 0], c->dWave, l, traceOn, shadowOn, zNear, items, c->sms, stats, c->ctasPerSm, walk);
 			++launches;
 		}

@@ -59,8 +59,8 @@ static int ensure_scratch(BuildScratch **ps, uint32_t n)
 	CK(cudaMalloc(&s->bounds, sizeof(int) * 8));
 	CK(cudaMalloc(&s->parentOfInternal, sizeof(int) * cap));
 	CK(cudaMalloc(&s->parentOfLeaf, sizeof(int) * cap));
-	CK(cudaMalloc(&s->children, sizeof(int2) * cap));
-	CK(cudaMalloc(&s->range, sizeof(int2) * cap));
+	CK(cudaMalloc(&s->children, sizeof(int4) * cap));   // int2 per internal node; twice the room: the 8-wide collapse keeps int4 frontier records here
+	CK(cudaMalloc(&s->range, sizeof(int4) * cap));
 	CK(cudaMalloc(&s->flags, sizeof(uint32_t) * cap));
 	CK(cudaMalloc(&s->ilo, sizeof(float4) * cap));
 	CK(cudaMalloc(&s->ihi, sizeof(float4) * cap));
@@ -564,10 +564,198 @@ __global__ void k_collapse4_sah(Collapse4Args a)
 	}
 }
 
-int rtb_build(cudaStream_t st, BuildScratch **scratch, const float4 *box_lo, const float4 *box_hi, uint32_t n,
-	uint32_t leafSize, BvhNode *nodes, BvhNode4 *nodes4, uint32_t nodeBase, uint32_t leafBase, uint32_t *leafOrder, BvhBuildResult *res)
+
+// ---- collapse to 8-wide nodes with quantised child boxes (BvhNode8) ---------------------------------------
+// Same top-down scheme as k_collapse4_sah -- a node keeps opening its inner child with the largest surface area -- up to
+// eight children, then the child boxes are quantised to 8 bits per plane relative to the node's own box.
+
+// s = 2^e with 250 * s >= extent (five quanta of head-room for the outward rounding and the padding); returns the biased
+// exponent byte
+__device__ __forceinline__ uint32_t quant_exponent(float extent)
 {
-	res->nLevels = 0;
+	const float want = fmaxf(extent, 1e-30f) * (1.0f / 250.0f);
+	int e = (int)((__float_as_uint(want) >> 23) & 0xFFu) + 1;   // 2^(floor(log2 want) + 1) >= want
+	e = e < 1 ? 1 : (e > 254 ? 254 : e);
+	return (uint32_t)e;
+}
+
+// the node record for m <= 8 child boxes (exact floats) and links; boxes are rounded outward and padded by one quantum
+__device__ __forceinline__ BvhNode8 quantise_node8(const float (*lo)[3], const float (*hi)[3], const int *link, int m)
+{
+	const float inf = __int_as_float(0x7f800000);
+	float nlo[3] = { inf, inf, inf }, nhi[3] = { -inf, -inf, -inf };
+	for (int k = 0; k < m; ++k)
+		for (int a = 0; a < 3; ++a)
+			nlo[a] = fminf(nlo[a], lo[k][a]), nhi[a] = fmaxf(nhi[a], hi[k][a]);
+	BvhNode8 o;
+	o.px = nlo[0], o.py = nlo[1], o.pz = nlo[2];
+	uint32_t eb[3];
+	float inv[3];
+	for (int a = 0; a < 3; ++a)
+	{
+		eb[a] = quant_exponent(nhi[a] - nlo[a]);
+		inv[a] = __uint_as_float((254u - eb[a]) << 23);   // 1 / 2^(e - 127), exact
+	}
+	uint32_t q[6][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 }, { 0, 0 }, { 0, 0 }, { 0, 0 } };
+	uint32_t valid = 0;
+	for (int k = 0; k < 8; ++k)
+	{
+		uint32_t ql[3] = { 255u, 255u, 255u }, qh[3] = { 0u, 0u, 0u };   // unused child: an inverted box no ray hits
+		if (k < m)
+		{
+			valid |= 1u << k;
+			for (int a = 0; a < 3; ++a)
+			{
+				// outward rounding with a margin (the quotient itself carries a rounding error), then one quantum of padding:
+				// the traversal reconstructs plane distances with an absolute error far below a quantum (rt_traverse.cuh)
+				const float xl = (lo[k][a] - nlo[a]) * inv[a], xh = (hi[k][a] - nlo[a]) * inv[a];
+				const int il = (int)floorf(xl - 1e-3f) - 1, ih = (int)ceilf(xh + 1e-3f) + 1;
+				ql[a] = (uint32_t)(il < 0 ? 0 : (il > 255 ? 255 : il));
+				qh[a] = (uint32_t)(ih < 0 ? 0 : (ih > 255 ? 255 : ih));
+			}
+		}
+		const int w = k >> 2, sh = (k & 3) * 8;
+		q[0][w] |= ql[0] << sh, q[1][w] |= ql[1] << sh, q[2][w] |= ql[2] << sh;
+		q[3][w] |= qh[0] << sh, q[4][w] |= qh[1] << sh, q[5][w] |= qh[2] << sh;
+		o.link[k] = k < m ? link[k] : 0x7FFFFFFF;
+	}
+	o.exyz = eb[0] | (eb[1] << 8) | (eb[2] << 16) | (valid << 24);
+	o.qlox[0] = q[0][0], o.qlox[1] = q[0][1], o.qloy[0] = q[1][0], o.qloy[1] = q[1][1], o.qloz[0] = q[2][0], o.qloz[1] = q[2][1];
+	o.qhix[0] = q[3][0], o.qhix[1] = q[3][1], o.qhiy[0] = q[4][0], o.qhiy[1] = q[4][1], o.qhiz[0] = q[5][0], o.qhiz[1] = q[5][1];
+	return o;
+}
+
+// the (padded) box the traversal sees for child k of a node: [p + qlo * s, p + qhi * s]
+__device__ __forceinline__ void dequant_child8(const BvhNode8 &n, int k, float *lo, float *hi)
+{
+	const float s[3] = { __uint_as_float((n.exyz & 0xFFu) << 23), __uint_as_float(((n.exyz >> 8) & 0xFFu) << 23), __uint_as_float(((n.exyz >> 16) & 0xFFu) << 23) };
+	const float p[3] = { n.px, n.py, n.pz };
+	const uint32_t *ql[3] = { n.qlox, n.qloy, n.qloz }, *qh[3] = { n.qhix, n.qhiy, n.qhiz };
+	for (int a = 0; a < 3; ++a)
+	{
+		const float l = (float)((ql[a][k >> 2] >> ((k & 3) * 8)) & 0xFFu), h = (float)((qh[a][k >> 2] >> ((k & 3) * 8)) & 0xFFu);
+		lo[a] = p[a] + l * s[a], hi[a] = p[a] + h * s[a];
+		// the sums round to nearest: step outward so that the float box contains the real-valued one
+		lo[a] = nextafterf(lo[a], -3.0e38f), hi[a] = nextafterf(hi[a], 3.0e38f);
+	}
+}
+
+struct Collapse8Args
+{
+	const BvhNode *nodes;      // binary nodes, links are global indices (leaves < 0)
+	BvhNode8 *nodes8;
+	const int4 *frontier;      // (binary node, 8-wide slot, stack need of the path so far, -)
+	int4 *next;
+	uint32_t *counters;        // [level] = frontier length of level + 1, [126] = deepest stack need, [127] = slots handed out
+	uint32_t level, nodeBase;
+};
+
+__global__ void k_collapse8(Collapse8Args a)
+{
+	const uint32_t nFrontier = a.level == 0 ? 1u : a.counters[a.level - 1];
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nFrontier; i += gridDim.x * blockDim.x)
+	{
+		const int4 item = a.level == 0 ? make_int4((int)a.nodeBase, (int)a.nodeBase, 0, 0) : a.frontier[i];
+		float lo[8][3], hi[8][3];
+		int link[8];
+		const BvhNode root = a.nodes[item.x];
+		node_child(root, 0, lo[0], hi[0], link[0]);
+		node_child(root, 1, lo[1], hi[1], link[1]);
+		int m = 2;
+		while (m < 8)
+		{
+			int best = -1;
+			float bestArea = -1.0f;
+			for (int k = 0; k < m; ++k)
+				if (link[k] >= 0)
+				{
+					const float ar = box_area(lo[k], hi[k]);
+					if (ar > bestArea) bestArea = ar, best = k;
+				}
+			if (best < 0) break;
+			const BvhNode c = a.nodes[link[best]];
+			node_child(c, 0, lo[best], hi[best], link[best]);
+			node_child(c, 1, lo[m], hi[m], link[m]);
+			++m;
+		}
+		int inner = 0;
+		for (int k = 0; k < m; ++k) inner += link[k] >= 0;
+		const int need = item.z + m - 1;   // a step pushes up to m - 1 siblings
+		atomicMax(&a.counters[126], (uint32_t)need);
+		if (inner)
+		{
+			const uint32_t slot0 = atomicAdd(&a.counters[127], (uint32_t)inner);
+			const uint32_t q0 = atomicAdd(&a.counters[a.level], (uint32_t)inner);
+			int j = 0;
+			for (int k = 0; k < m; ++k)
+				if (link[k] >= 0)
+				{
+					const int slot = (int)(a.nodeBase + 1u + slot0 + (uint32_t)j);
+					a.next[q0 + j] = make_int4(link[k], slot, need, 0);
+					link[k] = slot;
+					++j;
+				}
+		}
+		a.nodes8[item.y] = quantise_node8(lo, hi, link, m);
+	}
+}
+
+// refit of one level of the 8-wide tree: child boxes again from the triangle boxes (leaf children) or from the child
+// node's own -- already refitted, dequantised -- child boxes; then the node is quantised anew
+__global__ void k_refit8_level(BvhNode8 *nodes8, uint32_t begin, uint32_t count, const float4 *box_lo, const float4 *box_hi, const uint32_t *leafOrder)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count) return;
+	const BvhNode8 n = nodes8[begin + i];
+	const float inf = __int_as_float(0x7f800000);
+	float lo[8][3], hi[8][3];
+	int link[8], m = 0;
+	for (int k = 0; k < 8; ++k)
+	{
+		if (n.link[k] == 0x7FFFFFFF) continue;   // (valid children are a prefix: m counts them)
+		float l[3] = { inf, inf, inf }, h[3] = { -inf, -inf, -inf };
+		if (n.link[k] < 0)
+		{
+			const uint32_t first = ((uint32_t)n.link[k] & 0x7FFFFFFFu) >> 3, cnt = ((uint32_t)n.link[k] & 7u) + 1u;
+			for (uint32_t s = first; s < first + cnt; ++s)
+			{
+				const uint32_t t = leafOrder[s];
+				const float4 a = box_lo[t], b = box_hi[t];
+				l[0] = fminf(l[0], a.x), l[1] = fminf(l[1], a.y), l[2] = fminf(l[2], a.z), h[0] = fmaxf(h[0], b.x), h[1] = fmaxf(h[1], b.y), h[2] = fmaxf(h[2], b.z);
+			}
+		}
+		else
+		{
+			const BvhNode8 c = nodes8[n.link[k]];
+			for (int j = 0; j < 8; ++j)
+				if (c.link[j] != 0x7FFFFFFF)
+				{
+					float cl[3], ch[3];
+					dequant_child8(c, j, cl, ch);
+					for (int a = 0; a < 3; ++a) l[a] = fminf(l[a], cl[a]), h[a] = fmaxf(h[a], ch[a]);
+				}
+		}
+		for (int a = 0; a < 3; ++a) lo[m][a] = l[a], hi[m][a] = h[a];
+		link[m++] = n.link[k];
+	}
+	nodes8[begin + i] = quantise_node8(lo, hi, link, m);
+}
+
+void rtb_refit8(cudaStream_t st, BvhNode8 *nodes8, uint32_t nodeBase, const uint32_t *levelNodes, uint32_t nLevels,
+	const float4 *box_lo, const float4 *box_hi, const uint32_t *leafOrder)
+{
+	uint32_t begin[129];
+	begin[0] = nodeBase;
+	for (uint32_t k = 0; k < nLevels; ++k) begin[k + 1] = begin[k] + levelNodes[k];
+	for (int k = (int)nLevels - 1; k >= 0; --k)
+		if (levelNodes[k])
+			k_refit8_level<<<(levelNodes[k] + 63) / 64, 64, 0, st>>>(nodes8, begin[k], levelNodes[k], box_lo, box_hi, leafOrder);
+}
+
+int rtb_build(cudaStream_t st, BuildScratch **scratch, const float4 *box_lo, const float4 *box_hi, uint32_t n,
+	uint32_t leafSize, BvhNode *nodes, BvhNode4 *nodes4, uint32_t nodeBase, uint32_t leafBase, uint32_t *leafOrder, BvhBuildResult *res, BvhNode8 *nodes8)
+{
+	res->nLevels = 0, res->maxStack = 0;
 	if (n == 0) { res->root = 0, res->nodesUsed = 0, res->depth = 0; return 0; }
 	if (leafSize < 1) leafSize = 1;
 	if (leafSize > 8) leafSize = 8;
@@ -599,7 +787,29 @@ int rtb_build(cudaStream_t st, BuildScratch **scratch, const float4 *box_lo, con
 	CK(cudaMemcpyAsync(&depth, s->height, sizeof depth, cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));
 	static const int collapseSah = []{ const char *e = getenv("RT_B200_COLLAPSE"); return (e && !strcmp(e, "even")) ? 0 : 1; }();
-	if (!collapseSah)
+	if (nodes8)
+	{
+		// 8-wide quantised nodes (Model BVHs): frontier ping-pong in children / range (int2 pairs reused as int4: n - 1 >= 2 * frontier)
+		CK(cudaMemsetAsync(s->flags, 0, sizeof(uint32_t) * 128, st));
+		Collapse8Args ca;
+		ca.nodes = nodes, ca.nodes8 = nodes8, ca.counters = s->flags, ca.nodeBase = nodeBase;
+		const unsigned cblocks = blocks < 2048 ? blocks : 2048;
+		for (uint32_t level = 0; level < depth && level < 120; ++level)
+		{
+			ca.level = level;
+			ca.frontier = (const int4 *)((level & 1) ? s->range : s->children);
+			ca.next = (int4 *)((level & 1) ? s->children : s->range);
+			k_collapse8<<<level < 3 ? 1 : cblocks, 128, 0, st>>>(ca);
+		}
+		uint32_t counters[128];
+		CK(cudaMemcpyAsync(counters, s->flags, sizeof counters, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		res->nLevels = 1, res->levelNodes[0] = 1;
+		for (uint32_t level = 0; level < depth && level < 120 && counters[level]; ++level)
+			res->levelNodes[res->nLevels++] = counters[level];
+		res->maxStack = counters[126];
+	}
+	else if (!collapseSah)
 		k_collapse4<<<blocks, 256, 0, st>>>(nodes, nodes4, s->parentOfInternal, nodeBase, (int)n - 1);
 	else
 	{

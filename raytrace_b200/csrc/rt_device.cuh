@@ -174,6 +174,27 @@ struct BvhNode4
 	int4 pad;
 };
 
+// 8-wide node with quantised child boxes, used for the Model BVHs (RT_BVH8): 96 bytes for 8 children (12 bytes per
+// child against 32 in BvhNode4), six 128-bit loads.  Child k's box is [p + qlo_k * s, p + qhi_k * s] per axis with
+// s = 2^e (the byte e is the biased float exponent), rounded OUTWARD and padded by one quantum at build time, so it
+// contains the exact box: the BVH boxes are only a conservative cull, every accepted distance still comes from the exact
+// triangle operator.  Fewer, fatter steps per ray (measured: DESIGN.md) and a third of the node bytes.
+// Measured (profiles/r2k_bvh8_ab.md): 5.9 instead of 8.1 node visits per ray and 42 % instead of 67 % L1 wavefront load, but an
+// 8-wide step costs 265 instructions against 145 and the wave kernels sit at their ~70 % issue ceiling with either tree:
+// +17 % warp instructions, 11 % slower.  Off by default.
+#ifndef RT_BVH8
+#define RT_BVH8 0
+#endif
+struct BvhNode8
+{
+	float px, py, pz;          // origin = low corner of the union of the child boxes
+	uint32_t exyz;             // ex | ey << 8 | ez << 16 | valid-child mask << 24
+	uint32_t qlox[2], qloy[2]; // child k: byte k & 3 of word k >> 2
+	uint32_t qloz[2], qhix[2];
+	uint32_t qhiy[2], qhiz[2];
+	int link[8];               // >= 0 node index, < 0 leaf code 0x80000000 | first << 3 | (count - 1), 0x7FFFFFFF unused
+};
+
 struct SceneDev
 {
 	// analytic primitives: 4 float4 + 1 int4 each
@@ -194,10 +215,12 @@ struct SceneDev
 	const float2 *tri_tcoords;   // 3 per triangle
 	const uint32_t *tri_slot;    // original index -> leaf-order slot (to re-run the hit test when shading)
 	const uint32_t *tri_part;    // original index -> global part index
-	const BvhNode4 *nodes4;
+	const BvhNode4 *nodes4;      // prim-run BVHs (and Model BVHs when RT_BVH8 == 0)
+	const BvhNode8 *nodes8;      // Model BVHs (RT_BVH8)
 	const SceneItem *items;
 	uint32_t n_items, n_prims, n_tris, n_parts;
 	uint32_t brute;              // RT_FLAG_BRUTE: ignore the BVHs, test every primitive (diagnostic cross-check)
+	uint32_t dq_trigger;         // deferred triangle tests (rt_defer.cuh): a test round starts when fewer than 1/dq_trigger of the walking lanes are not waiting for results
 };
 
 __device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }

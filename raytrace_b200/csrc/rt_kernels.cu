@@ -20,7 +20,7 @@
 // c = c*(1-kr) + c_refl*kr ; c = c*(1-kt) + (c_refr (*) beer)*kt sequence, so the colour
 // arithmetic is bit-identical to the recursive evaluation order.
 #include "rt_traverse.cuh"
-#include "rt_async.cuh"
+#include "rt_defer.cuh"
 #include "rt_kernels.h"
 #include <cstdlib>
 #include <algorithm>
@@ -285,12 +285,16 @@ __device__ __forceinline__ bool frame_cancelled(const WaveState *ws, const Frame
 
 // ---- fused wave kernel: closest hit of level `level` + shadow rays of level `level - 1` -------------
 
-template<bool STATS, int CTAS>
+// DEFER: Model BVHs are walked with deferred triangle tests (rt_defer.cuh); the counting launches (STATS) keep the voted walk,
+// whose node / triangle counts are the algorithmic ones (no speculative visits).
+template<bool STATS, int CTAS, bool DEFER>
 __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_wave(SceneDev S, const FrameParams *__restrict__ Fp, LevelBuf L, LevelBuf N, LevelBuf Lprev,
 	WaveState *ws, uint32_t level, uint32_t traceOn, uint32_t shadowOn, float zNear)
 {
 	const FrameParams &F = *Fp;
 	TravStats st = { 0, 0, 0 };
+	__shared__ WarpDefer wdefer[DEFER ? RT_BLOCK / 32 : 1];
+	WarpDefer *W = &wdefer[DEFER ? (threadIdx.x >> 5) : 0];
 
 	// ---- phase A: closest hit + surface attributes + children ------------------------------------
 	if (traceOn)
@@ -305,29 +309,34 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_wave(SceneDev S, const Frame
 			if (base >= n || frame_cancelled(ws, F))   // queue dry, or rt_stop
 				break;
 			const uint32_t lane = threadIdx.x & 31u;
-			const uint32_t i = lane < batch ? base + lane : 0xFFFFFFFFu;
+			uint32_t i = lane < batch ? base + lane : 0xFFFFFFFFu;
+			if (L.order && i < n) i = L.order[i];   // coherence binning: the k-th ray to trace is slot order[k]
 			bool surface = false, wantFlec = false, wantFrac = false;
 			float4 co = make_float4(0, 0, 0, 0), cdFlec = co, cdFrac = co;
 			uint2 metaFlec = make_uint2(0, 0), metaFrac = metaFlec;
 			float fracRfr = 1.0f;
 			int4 aux = make_int4(-1, -1, -1, 0);
+			// primary rays are made here (sched_flags bit 2: k_raygen did not run): no 40-byte record written
+			// by one kernel and read back by the next
+			const bool made = level == 0u && (F.sched_flags & 4u);
+			RayD ray;
+			ray.o = f3(0.0f, 0.0f, 0.0f), ray.d = f3(0.0f, 0.0f, 1.0f);
+			ray.mtlrfr = 1.0f, ray.skip = RT_ID_NONE, ray.type = MY_RAY_BASERAY_, ray.isInside = 0;
 			if (i < n)
 			{
-				// primary rays are made here (sched_flags bit 2: k_raygen did not run): no 40-byte record written
-				// by one kernel and read back by the next
-				const bool made = level == 0u && (F.sched_flags & 4u);
-				RayD ray;
 				if (made)
-				{
 					ray.d = primary_dir(F, i, ray.o);
-					ray.mtlrfr = 1.0f, ray.skip = RT_ID_NONE, ray.type = MY_RAY_BASERAY_, ray.isInside = 0;
-				}
 				else
 					ray = load_ray(L, i);
-				Best best = { 1e20f, RT_ID_NONE, ray.skip };
-				bool done = false;
+			}
+			Best best = { 1e20f, RT_ID_NONE, ray.skip };
+			bool done = false;
+			if (DEFER)
+				trace_scene_defer<false>(S, ray, i < n, best, done, *W);   // the whole warp: idle lanes help with the triangle test rounds
+			if (i < n)
+			{
 				const uint32_t nodes0 = st.nodes;
-				trace_scene<false, STATS>(S, ray, best, done, st);
+				if (!DEFER) trace_scene<false, STATS>(S, ray, best, done, st);
 				if (STATS) atomicAdd(&ws->node_hist[min(11, 31 - __clz((int)(st.nodes - nodes0 + 1u)))], 1u);
 				const F3 P = ray.o + ray.d * best.t;
 				L.hit_p[i] = make_float4(P.x, P.y, P.z, best.t);
@@ -434,22 +443,29 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_wave(SceneDev S, const Frame
 				break;
 			const uint32_t lane = threadIdx.x & 31u;
 			const uint32_t w = lane < batch ? base + lane : 0xFFFFFFFFu;
+			uint32_t k = 0, i = 0;
+			RayD ray;
+			ray.o = f3(0.0f, 0.0f, 0.0f), ray.d = f3(0.0f, 0.0f, 1.0f);
+			ray.mtlrfr = 1.0f, ray.skip = RT_ID_NONE, ray.type = 0, ray.isInside = 0;
+			float dis = 0.0f;
 			if (w < n)
 			{
-				const uint32_t k = F.enabled_index[w / nHit], i = Lprev.hit_list[w % nHit] - 1u;
+				k = F.enabled_index[w / nHit], i = Lprev.hit_list[w % nHit] - 1u;
 				const float4 hp = Lprev.hit_p[i];
-				RayD ray;
-				float dis, lum;
+				float lum;
 				light_dir(F.lights[k], f3(hp), ray.d, dis, lum);
 				ray.o = f3(hp);
-				ray.mtlrfr = 1.0f;
 				ray.skip = Lprev.hit_id[i].y;
 				ray.type = (F.type == RT_TYPE_REFLECT || F.type == RT_TYPE_SHADOW) ? 0 : MY_RAY_SHADOWRAY_;
-				ray.isInside = 0;
-				Best best = { dis, RT_ID_NONE, RT_ID_NONE };
-				bool done = false;
+			}
+			Best best = { dis, RT_ID_NONE, RT_ID_NONE };
+			bool done = false;
+			if (DEFER)
+				trace_scene_defer<true>(S, ray, w < n, best, done, *W);
+			if (w < n)
+			{
 				const uint32_t nodes0 = st.nodes;
-				trace_scene<true, STATS>(S, ray, best, done, st);
+				if (!DEFER) trace_scene<true, STATS>(S, ray, best, done, st);
 				if (STATS) atomicAdd(&ws->node_hist[12 + min(11, 31 - __clz((int)(st.nodes - nodes0 + 1u)))], 1u);
 				Lprev.shadow[(size_t)k * Lprev.capacity + i] = done ? 1 : 0;
 			}
@@ -458,10 +474,8 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_wave(SceneDev S, const Frame
 	flush_stats<STATS>(ws, st);
 }
 
-// ---- lane-asynchronous wave kernel ---------------------------------------------------------------------
-// Same work as k_wave -- closest hit of level `level` (+ surface attributes, child rays) and the shadow rays of
-// level `level - 1` -- with the walk of rt_async.cuh: lanes take rays out of a per-warp pool one by one, finished
-// rays wait in the pool for an epilogue that runs 32 at a time.
+// (A lane-asynchronous variant -- per-warp ray pool, lanes swap rays in one by one -- was measured 35 % slower and removed:
+// profiles/r2_fma_slab_ab.txt.)
 
 // One finished closest-hit ray: hit record, early cut, surface attributes, child rays, queue appends (the epilogue
 // of k_wave's phase A).  Called by ALL 32 lanes (lanes without a ray pass valid = false): appends are warp-aggregated.
@@ -562,258 +576,6 @@ __device__ __forceinline__ void trace_epilogue(const SceneDev &S, const FramePar
 		if (mf) atomicAdd(&ws->n_reflect, (unsigned long long)__popc(mf));
 		if (mr) atomicAdd(&ws->n_refract, (unsigned long long)__popc(mr));
 	}
-}
-
-__device__ __forceinline__ uint32_t pool_count(const uint32_t *p) { return *(const volatile uint32_t *)p; }
-
-// lanes of `grp` whose ray is through hand in their pool entry, lanes without a ray take one; -> nothing left to take
-template<bool ANY>
-__device__ __forceinline__ bool pool_exchange(WarpPool &P, Lane &Ln, uint32_t grp, bool fin, float firstT)
-{
-	const uint32_t lane = threadIdx.x & 31u, lt = lanemask_lt(), leader = __ffs((int)grp) - 1;
-	if (!ANY)
-	{
-		const uint32_t mFin = __ballot_sync(grp, fin);
-		if (mFin)
-		{
-			const uint32_t nD = pool_count(&P.nDone);
-			if (fin)
-			{
-				PoolEntry &E = P.e[Ln.entry];
-				E.t = Ln.bt, E.id = Ln.bid, E.newobj = Ln.bnew;
-				P.doneQ[nD + __popc(mFin & lt)] = (uint8_t)Ln.entry;
-				Ln.flags = 0;
-			}
-			__syncwarp(grp);
-			if (lane == leader) P.nDone = nD + __popc(mFin);
-		}
-	}
-	const bool need = !(Ln.flags & LF_HAS);
-	const uint32_t mNeed = __ballot_sync(grp, need);
-	if (!mNeed)
-		return false;
-	const uint32_t nR = pool_count(&P.nReady);
-	if (!nR)
-		return false;
-	const uint32_t r = __popc(mNeed & lt);
-	if (need && r < nR)
-	{
-		const uint32_t e = ANY ? nR - 1u - r : (uint32_t)P.readyQ[nR - 1u - r];
-		lane_take(Ln, P.e[e], e);
-		if (ANY)
-		{
-			Ln.entry = P.e[e].slot;            // shadow rays: where the occlusion flag goes
-			Ln.bt = P.e[e].o.w;                // light distance
-			Ln.bid = Ln.bnew = RT_ID_NONE;
-		}
-		else
-			Ln.bt = firstT, Ln.bid = RT_ID_NONE, Ln.bnew = Ln.skip;
-	}
-	__syncwarp(grp);
-	const uint32_t taken = __popc(mNeed) < nR ? __popc(mNeed) : nR;
-	if (lane == leader) P.nReady = nR - taken;
-	__syncwarp(grp);
-	return true;
-}
-
-template<bool STATS, int CTAS>
-__global__ void __launch_bounds__(RT_BLOCK, CTAS) k_wave_async(SceneDev S, const FrameParams *__restrict__ Fp, LevelBuf L, LevelBuf N, LevelBuf Lprev,
-	WaveState *ws, uint32_t level, uint32_t traceOn, uint32_t shadowOn, float zNear)
-{
-	__shared__ WarpPool pools[RT_BLOCK / 32];
-	WarpPool &P = pools[threadIdx.x >> 5];
-	const FrameParams &F = *Fp;
-	const uint32_t lane = threadIdx.x & 31u;
-	TravStats st = { 0, 0, 0 };
-
-	// ---- phase A: closest hit + surface attributes + children ------------------------------------
-	if (traceOn)
-	{
-		const uint32_t n = ws->count[level] < L.capacity ? ws->count[level] : L.capacity;
-		const uint32_t batch = fetch_batch(n);
-		const bool made = level == 0u && (F.sched_flags & 4u);   // primary rays are made at refill (k_raygen did not run)
-		pool_init(P);
-		uint2 stack[RT_STACK];
-		Lane Ln;
-		Ln.flags = 0, Ln.cur = RT_TRAV_DONE, Ln.sp = 0, Ln.item = 0, Ln.entry = 0;
-		bool dry = n == 0u;
-		while (true)
-		{
-			const bool has = (Ln.flags & LF_HAS) != 0u;
-			const bool atNode = has && Ln.cur >= 0, atLeaf = has && Ln.cur < 0 && Ln.cur != RT_TRAV_DONE;
-			const uint32_t nReady = pool_count(&P.nReady), nDone = pool_count(&P.nDone);
-			const bool wantAdv = (has && Ln.cur == RT_TRAV_DONE) || (!has && nReady > 0u);
-			const uint32_t mN = __ballot_sync(0xffffffffu, atNode), mL = __ballot_sync(0xffffffffu, atLeaf), mA = __ballot_sync(0xffffffffu, wantAdv);
-			const uint32_t busy = __ballot_sync(0xffffffffu, has);
-			const bool starving = nReady == 0u && !dry && (32 - __popc(busy) >= RT_REFILL_IDLE || busy == 0u);
-			const bool lastFlush = busy == 0u && nReady == 0u && dry && nDone > 0u;
-			if (nDone >= 32u || starving || lastFlush)
-			{
-				// ---- service: the epilogue of the finished rays, 32 at a time, then 32 new rays into the pool ----
-				uint32_t nD = nDone, nR = nReady, nF = pool_count(&P.nFree);
-				while (nD >= 32u || (nD > 0u && (starving || lastFlush)))
-				{
-					const uint32_t cnt = nD < 32u ? nD : 32u;
-					const bool valid = lane < cnt;
-					const uint32_t e = valid ? (uint32_t)P.doneQ[nD - cnt + lane] : 0u;
-					const PoolEntry &E = P.e[e];
-					const float4 o4 = E.o, d4 = E.d;
-					RayD ray;
-					ray.o = f3(o4), ray.d = f3(d4), ray.mtlrfr = o4.w, ray.skip = E.skip;
-					ray.type = (uint8_t)(E.meta & 0xFFu), ray.isInside = (uint8_t)((E.meta >> 8) & 0xFFu);
-					const Best best = { E.t, E.id, E.newobj };
-					trace_epilogue(S, F, L, N, ws, level, zNear, valid, E.slot, ray, d4.w, made, best);
-					if (valid) P.freeQ[nF + lane] = (uint8_t)e;
-					nF += cnt, nD -= cnt;
-				}
-				if (!dry && nR < 16u && nF > 0u)
-				{
-					const uint32_t want = batch < nF ? batch : nF;
-					const uint32_t base = warp_fetch(&ws->head_trace[level], want);
-					if (base >= n || frame_cancelled(ws, F))
-						dry = true, nR = frame_cancelled(ws, F) ? 0u : nR;
-					else
-					{
-						const uint32_t cnt = want < n - base ? want : n - base;
-						if (lane < cnt)
-						{
-							const uint32_t i = base + lane, e = (uint32_t)P.freeQ[nF - 1u - lane];
-							PoolEntry &E = P.e[e];
-							if (made)
-							{
-								F3 o;
-								const F3 d = primary_dir(F, i, o);
-								E.o = make_float4(o.x, o.y, o.z, 1.0f), E.d = make_float4(d.x, d.y, d.z, 1.0f);
-								E.skip = RT_ID_NONE, E.meta = (uint32_t)MY_RAY_BASERAY_;
-							}
-							else
-							{
-								const uint2 m = L.ray_meta[i];
-								E.o = L.ray_o[i], E.d = L.ray_d[i];
-								E.skip = m.x, E.meta = m.y & 0xFFFFu;
-							}
-							E.slot = i;
-							P.readyQ[nR + lane] = (uint8_t)e;
-						}
-						nF -= cnt, nR += cnt;
-						if (base + want >= n) dry = true;
-					}
-				}
-				__syncwarp();
-				if (lane == 0) P.nDone = nD, P.nReady = nR, P.nFree = nF;
-				__syncwarp();
-				continue;
-			}
-			if ((mN | mL | mA) == 0u)
-				break;
-			const int cN = __popc(mN), cL = __popc(mL), cA = __popc(mA);
-			if (cN >= cL && cN >= cA)
-			{
-				if (atNode) node_step<false, STATS>(S, Ln, stack, st);
-			}
-			else if (cL >= cA)
-			{
-				if (atLeaf) leaf_step<false, STATS>(S, Ln, stack, st);
-			}
-			else if (wantAdv)
-			{
-				__syncwarp(mA);
-				for (int round = 0; round < 2; ++round)
-				{
-					bool fin = false;
-					if ((Ln.flags & LF_HAS) && Ln.cur == RT_TRAV_DONE)
-						fin = advance_items<false, STATS>(S, Ln, st);
-					if (!pool_exchange<false>(P, Ln, mA, fin, 1e20f))
-						break;
-				}
-			}
-			__syncwarp();
-		}
-	}
-
-	// ---- phase B: shadow any-hit of the previous level's surfaces -----------------------------------
-	if (shadowOn)
-	{
-		__syncwarp();
-		const uint32_t lp = level - 1u;
-		const uint32_t nHit = ws->n_hit[lp];
-		const uint32_t n = nHit * F.n_enabled;
-		const uint32_t batch = fetch_batch(n);
-		const uint32_t rayType = (F.type == RT_TYPE_REFLECT || F.type == RT_TYPE_SHADOW) ? 0u : (uint32_t)MY_RAY_SHADOWRAY_;
-		if (lane == 0) P.nReady = 0, P.nDone = 0, P.nFree = 0;
-		__syncwarp();
-		int stack[RT_STACK];
-		Lane Ln;
-		Ln.flags = 0, Ln.cur = RT_TRAV_DONE, Ln.sp = 0, Ln.item = 0, Ln.entry = 0;
-		bool dry = n == 0u;
-		while (true)
-		{
-			const bool has = (Ln.flags & LF_HAS) != 0u;
-			const bool atNode = has && Ln.cur >= 0, atLeaf = has && Ln.cur < 0 && Ln.cur != RT_TRAV_DONE;
-			const uint32_t nReady = pool_count(&P.nReady);
-			const bool wantAdv = (has && Ln.cur == RT_TRAV_DONE) || (!has && nReady > 0u);
-			const uint32_t mN = __ballot_sync(0xffffffffu, atNode), mL = __ballot_sync(0xffffffffu, atLeaf), mA = __ballot_sync(0xffffffffu, wantAdv);
-			const uint32_t busy = __ballot_sync(0xffffffffu, has);
-			if (nReady == 0u && !dry && (32 - __popc(busy) >= RT_REFILL_IDLE || busy == 0u))
-			{
-				// ---- refill: 32 shadow rays set up by the whole warp (light direction, occlusion range) ----
-				const uint32_t base = warp_fetch(&ws->head_shadow[lp], batch);
-				uint32_t nR = 0;
-				if (base >= n || frame_cancelled(ws, F))
-					dry = true;
-				else
-				{
-					const uint32_t cnt = batch < n - base ? batch : n - base;
-					if (lane < cnt)
-					{
-						const uint32_t w = base + lane;
-						const uint32_t k = F.enabled_index[w / nHit], i = Lprev.hit_list[w % nHit] - 1u;
-						const float4 hp = Lprev.hit_p[i];
-						F3 dir;
-						float dis, lum;
-						light_dir(F.lights[k], f3(hp), dir, dis, lum);
-						PoolEntry &E = P.e[lane];
-						E.o = make_float4(hp.x, hp.y, hp.z, dis), E.d = make_float4(dir.x, dir.y, dir.z, 0.0f);
-						E.skip = Lprev.hit_id[i].y, E.meta = rayType;
-						E.slot = k * Lprev.capacity + i;
-					}
-					nR = cnt;
-					if (base + batch >= n) dry = true;
-				}
-				__syncwarp();
-				if (lane == 0) P.nReady = nR;
-				__syncwarp();
-				continue;
-			}
-			if ((mN | mL | mA) == 0u)
-				break;
-			const int cN = __popc(mN), cL = __popc(mL), cA = __popc(mA);
-			if (cN >= cL && cN >= cA)
-			{
-				if (atNode) node_step<true, STATS>(S, Ln, stack, st);
-			}
-			else if (cL >= cA)
-			{
-				if (atLeaf) leaf_step<true, STATS>(S, Ln, stack, st);
-			}
-			else if (wantAdv)
-			{
-				__syncwarp(mA);
-				for (int round = 0; round < 2; ++round)
-				{
-					if ((Ln.flags & LF_HAS) && Ln.cur == RT_TRAV_DONE && advance_items<true, STATS>(S, Ln, st))
-					{
-						Lprev.shadow[Ln.entry] = (Ln.flags & LF_OCCL) ? 1 : 0;
-						Ln.flags = 0;
-					}
-					if (!pool_exchange<true>(P, Ln, mA, false, 0.0f))
-						break;
-				}
-			}
-			__syncwarp();
-		}
-	}
-	flush_stats<STATS>(ws, st);
 }
 
 // ---- two-stage wave kernel ------------------------------------------------------------------------------
@@ -1844,6 +1606,102 @@ static int traversal_ctas_per_sm()
 	return v;
 }
 
+// ---- coherence binning (see rt_kernels.h BinGrid) ----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t spread3(uint32_t v)
+{
+	// 0b...cba -> 0b..c00b00a (up to 10 bits)
+	v = (v | (v << 16)) & 0x030000FFu;
+	v = (v | (v << 8)) & 0x0300F00Fu;
+	v = (v | (v << 4)) & 0x030C30C3u;
+	v = (v | (v << 2)) & 0x09249249u;
+	return v;
+}
+
+// one atomic per distinct key of the warp: neighbouring rays mostly share their bin
+__device__ __forceinline__ uint32_t warp_bin_add(uint32_t *hist, uint32_t key, bool valid)
+{
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t peers = __match_any_sync(0xffffffffu, valid ? key : 0xFFFFFFFFu);
+	const uint32_t leader = __ffs((int)peers) - 1;
+	uint32_t base = 0;
+	if (valid && lane == leader) base = atomicAdd(&hist[key], (uint32_t)__popc(peers));
+	base = __shfl_sync(0xffffffffu, base, leader);
+	return base + __popc(peers & ((1u << lane) - 1u));
+}
+
+__global__ void __launch_bounds__(256) k_bin_keys(LevelBuf L, const WaveState *__restrict__ ws, uint32_t level, BinGrid G, uint32_t *hist)
+{
+	const uint32_t n = ws->count[level] < L.capacity ? ws->count[level] : L.capacity;
+	const uint32_t top = (1u << G.bits) - 1u;
+	for (uint32_t j0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; j0 < n; j0 += gridDim.x * blockDim.x)
+	{
+		const uint32_t j = j0 + (threadIdx.x & 31u);
+		uint32_t key = 0;
+		if (j < n)
+		{
+			const float4 o = L.ray_o[j], d = L.ray_d[j];
+			const uint2 meta = L.ray_meta[j];
+			const uint32_t qx = (uint32_t)fminf(fmaxf((o.x - G.lo[0]) * G.scale[0], 0.0f), (float)top);
+			const uint32_t qy = (uint32_t)fminf(fmaxf((o.y - G.lo[1]) * G.scale[1], 0.0f), (float)top);
+			const uint32_t qz = (uint32_t)fminf(fmaxf((o.z - G.lo[2]) * G.scale[2], 0.0f), (float)top);
+			const uint32_t oct = (__float_as_uint(d.x) >> 31) | ((__float_as_uint(d.y) >> 31) << 1) | ((__float_as_uint(d.z) >> 31) << 2);
+			uint32_t inside = (meta.y >> 8) & 1u;
+			if (G.parts & 8u) inside = ((meta.y & 0xFFu) == (uint32_t)MY_RAY_REFRACTRAY_) ? 1u : 0u;
+			const uint32_t cell = (spread3(qx) << 2) | (spread3(qy) << 1) | spread3(qz);
+			key = ((((G.parts & 9u) ? inside << 3 : 0u) | ((G.parts & 2u) ? oct : 0u)) << (3u * G.bits)) | ((G.parts & 4u) ? cell : 0u);
+			L.sort_key[j] = key;
+		}
+		warp_bin_add(hist, key, j < n);
+	}
+}
+
+// exclusive prefix sum over the bins, one block (the histogram is L2-resident)
+__global__ void __launch_bounds__(1024) k_bin_scan(uint32_t *hist, uint32_t total)
+{
+	__shared__ uint32_t part[1024];
+	const uint32_t per = (total + 1023u) / 1024u;
+	const uint32_t lo = threadIdx.x * per, hi = min(lo + per, total);
+	uint32_t sum = 0;
+	for (uint32_t i = lo; i < hi; ++i) sum += hist[i];
+	part[threadIdx.x] = sum;
+	__syncthreads();
+	for (uint32_t off = 1; off < 1024; off <<= 1)
+	{
+		const uint32_t v = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+		__syncthreads();
+		part[threadIdx.x] += v;
+		__syncthreads();
+	}
+	uint32_t run = part[threadIdx.x] - sum;
+	for (uint32_t i = lo; i < hi; ++i)
+	{
+		const uint32_t c = hist[i];
+		hist[i] = run;
+		run += c;
+	}
+}
+
+__global__ void __launch_bounds__(256) k_bin_scatter(LevelBuf L, const WaveState *__restrict__ ws, uint32_t level, uint32_t *hist)
+{
+	const uint32_t n = ws->count[level] < L.capacity ? ws->count[level] : L.capacity;
+	for (uint32_t j0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; j0 < n; j0 += gridDim.x * blockDim.x)
+	{
+		const uint32_t j = j0 + (threadIdx.x & 31u);
+		const uint32_t key = j < n ? L.sort_key[j] : 0u;
+		const uint32_t pos = warp_bin_add(hist, key, j < n);
+		if (j < n) L.order[pos] = j;
+	}
+}
+
+void rtk_bin_rays(cudaStream_t st, const LevelBuf &L, const WaveState *ws, uint32_t level, const BinGrid &G, uint32_t *hist, unsigned sms)
+{
+	const uint32_t bins = 1u << (3u * G.bits + 4u);
+	cudaMemsetAsync(hist, 0, sizeof(uint32_t) * bins, st);
+	k_bin_keys<<<sms * 8, 256, 0, st>>>(L, ws, level, G, hist);
+	k_bin_scan<<<1, 1024, 0, st>>>(hist, bins);
+	k_bin_scatter<<<sms * 8, 256, 0, st>>>(L, ws, level, hist);
+}
+
 void rtk_wave(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const LevelBuf &N, const LevelBuf &Lprev, WaveState *ws,
 	uint32_t level, bool traceOn, bool shadowOn, float zNear, uint32_t maxItems, unsigned sms, bool stats, unsigned ctasPerSm, int walk)
 {
@@ -1857,20 +1715,14 @@ void rtk_wave(cudaStream_t st, const SceneDev &S, const FrameParams *F, const Le
 		else k_wave_split<false, RT_CTAS_PER_SM><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
 		return;
 	}
-	if (walk == 1)
-	{
-		// lane-asynchronous walk (rt_async.cuh); shadow destinations are 32-bit indices there
-		if (stats) k_wave_async<true, RT_CTAS_PER_SM><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
-		else if (occ == 6) k_wave_async<false, 6><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
-		else k_wave_async<false, RT_CTAS_PER_SM><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
-		return;
-	}
-	if (stats) k_wave<true, RT_CTAS_PER_SM><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
-	else if (occ == 4) k_wave<false, 4><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
-	else if (occ == 6) k_wave<false, 6><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
-	else if (occ == 10) k_wave<false, 10><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
-	else if (occ == 12) k_wave<false, 12><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
-	else k_wave<false, RT_CTAS_PER_SM><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+	if (stats) k_wave<true, RT_CTAS_PER_SM, false><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+	else if (walk == 3 && occ == 6) k_wave<false, 6, true><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+	else if (walk == 3) k_wave<false, RT_CTAS_PER_SM, true><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+	else if (occ == 4) k_wave<false, 4, false><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+	else if (occ == 6) k_wave<false, 6, false><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+	else if (occ == 10) k_wave<false, 10, false><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+	else if (occ == 12) k_wave<false, 12, false><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+	else k_wave<false, RT_CTAS_PER_SM, false><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
 }
 
 void rtk_frame(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelSet &LS, WaveState *ws, uint32_t nPix, unsigned sms, bool stats, unsigned ctasPerSm)

@@ -22,8 +22,23 @@ struct LevelBuf
 	float4 *hit_n;       // HitRes::normal.xyz, bits of the material index
 	float4 *hit_uv;      // HitRes::tcoord.u, .v, bits of the texture index (-1 none), unused
 	uint32_t *hit_list;  // compacted (slot + 1) of the rays that found a surface inside [zNear, zFar]; 0 = not written yet
+	uint32_t *order;     // coherence binning (rtk_bin_rays): k-th ray to trace -> slot; NULL = slot order
+	uint32_t *sort_key;  // scratch of the binning pass: bin of every slot
 	uint32_t capacity;
 };
+
+// Coherence binning of one level's rays before they are traced (wave scheduler, levels >= 1): a counting sort of the ray
+// slots by (starts inside a sphere, direction octant, Morton cell of the origin in a grid over the bounded scene objects).
+// Only the ORDER in which k_wave fetches the rays changes -- slot = ray-tree node stays as it is, so nothing downstream
+// (children links, hit lists, combine) notices.
+struct BinGrid
+{
+	float lo[3], scale[3];   // cell = clamp((origin - lo) * scale, 0, 2^bits - 1) per axis
+	uint32_t bits;           // per axis: 3 * bits + 4 key bits, 2^(3 * bits + 4) bins
+	uint32_t parts;          // which components make the key (experiments): 1 starts inside a sphere, 2 direction octant, 4 origin cell, 8 ray type
+};
+struct WaveState;
+void rtk_bin_rays(cudaStream_t st, const LevelBuf &L, const WaveState *ws, uint32_t level, const BinGrid &G, uint32_t *hist, unsigned sms);
 
 struct LevelSet { LevelBuf l[RT_MAX_LEVELS + 2]; };
 
@@ -46,7 +61,7 @@ struct WaveState
 
 void rtk_raygen(cudaStream_t st, const FrameParams *F, const LevelBuf &L, uint32_t n, unsigned sms);
 void rtk_wave(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelBuf &L, const LevelBuf &N, const LevelBuf &Lprev, WaveState *ws,
-	uint32_t level, bool traceOn, bool shadowOn, float zNear, uint32_t maxItems, unsigned sms, bool stats, unsigned ctasPerSm = 0, int walk = 0 /* 0: batch-synchronous voted walk, 1: lane-asynchronous (rt_async.cuh), 2: two-stage (k_wave_split) */);
+	uint32_t level, bool traceOn, bool shadowOn, float zNear, uint32_t maxItems, unsigned sms, bool stats, unsigned ctasPerSm = 0, int walk = 0 /* 0: batch-synchronous voted walk, 2: two-stage (k_wave_split) */);
 // whole-frame persistent scheduler (all ray levels in one launch)
 void rtk_frame(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelSet &LS, WaveState *ws, uint32_t nPix, unsigned sms, bool stats, unsigned ctasPerSm = 0);
 void rtk_shade(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelSet &LS, const WaveState *ws, uint32_t levels, uint32_t maxRays, unsigned sms, bool resetHits = false);
@@ -101,10 +116,13 @@ struct BvhBuildResult
 	// 4-wide nodes per level of the collapsed tree (breadth-first slots: level 0 = the root at nodeBase, level k >= 1 the
 	// next levelNodes[k] slots); nLevels = 0 when the tree was not collapsed level by level.  What rtb_refit4 walks.
 	uint32_t nLevels; uint32_t levelNodes[128];
+	uint32_t maxStack;   // 8-wide collapse: the deepest traversal stack any root-to-leaf path can need (sum of children - 1)
 };
 int rtb_build(cudaStream_t st, BuildScratch **scratch, const float4 *box_lo, const float4 *box_hi, uint32_t n,
 	uint32_t leafSize, BvhNode *nodes, BvhNode4 *nodes4, uint32_t nodeBase, uint32_t leafBase, uint32_t *leafOrder /* out: leaf slot -> input index */,
-	BvhBuildResult *res);
+	BvhBuildResult *res, BvhNode8 *nodes8 = nullptr /* non-NULL: collapse to 8-wide quantised nodes instead of nodes4 */);
+void rtb_refit8(cudaStream_t st, BvhNode8 *nodes8, uint32_t nodeBase, const uint32_t *levelNodes, uint32_t nLevels,
+	const float4 *box_lo, const float4 *box_hi, const uint32_t *leafOrder);
 void rtb_free_scratch(BuildScratch *s);
 // Refit instead of rebuild (Model::RTPrepare after a MovePos only re-translates bounds, Model.cpp:404,418-419): the
 // 4-wide tree of a model keeps its topology and leaf order, every node's child boxes are recomputed bottom-up, level by

@@ -230,6 +230,37 @@ __device__ __forceinline__ void test_prim(const SceneDev &S, const RayD &ray, ui
 // interleaves with box tests); which phase runs next is voted per step, see below.  The stack lives
 // in local memory (L1-resident, one 128-byte line per depth and warp) so no shared memory is
 // reserved and occupancy is bound by registers only.
+#if RT_BVH8
+// ---- 8-wide quantised node step (Model BVHs) ---------------------------------------------------------------------------
+// Plane distance of quantised coordinate q along one axis: t = (p + q*s - o) * id.  The byte is planted into the mantissa of
+// 1.0f with one PRMT (f = 1 + q * 2^-15), so t = f * A + B with A = 2^15 * s * id (exact scaling of id) and
+// B = (p - o) * id - A, both per node and axis: one PRMT and one FFMA per plane, no integer-to-float conversion.  B carries a
+// rounding error of about 2^-17 of the node's parametric length, far below the one-quantum padding of the boxes
+// (rt_build.cu quantise_node8), so the test stays conservative without an epsilon of its own.
+// `one` holds 0x3F800000 in a register the compiler cannot fold (otherwise ptxas makes the constant the immediate and
+// re-materialises the byte selector into a register for every plane).
+template<int K>
+__device__ __forceinline__ float qplane(uint32_t word, uint32_t one, float A, float B)
+{
+	uint32_t f;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(f) : "r"(word), "r"(one), "n"(0x7604 + (K << 4)));
+	return __fmaf_rn(__uint_as_float(f), A, B);
+}
+#endif
+
+// RT_NODE_FETCH == 2: the near / far plane vectors of an axis are fetched by PREDICATED loads at immediate offsets -- the sign
+// of the ray direction picks which of two loads runs -- instead of loads at per-ray byte offsets, whose six 64-bit address
+// sums (and the offsets themselves, re-made every step for want of registers) were 24 of the ~150 instructions of a node step.
+template<int LO, int HI>
+__device__ __forceinline__ void ldg_near_far(const char *n, uint32_t s, float4 &nr, float4 &fr)
+{
+	asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %8, 0;\n\t"
+		"@p ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%9+%11];\n\t@!p ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%9+%10];\n\t"
+		"@p ld.global.nc.v4.f32 {%4,%5,%6,%7}, [%9+%10];\n\t@!p ld.global.nc.v4.f32 {%4,%5,%6,%7}, [%9+%11];\n\t}"
+		: "=f"(nr.x), "=f"(nr.y), "=f"(nr.z), "=f"(nr.w), "=f"(fr.x), "=f"(fr.y), "=f"(fr.z), "=f"(fr.w)
+		: "r"(s), "l"(n), "n"(LO), "n"(HI));
+}
+
 template<bool ANY> struct StackSlot { typedef uint2 T; };
 template<> struct StackSlot<true> { typedef int T; };
 __device__ __forceinline__ void slot_put(int &s, int link, float) { s = link; }
@@ -275,6 +306,14 @@ __device__ __forceinline__ void traverse(const SceneDev &S, const RayD &ray, con
 	// RT_EARLY_HOLD steps, and the caller publishes their results while the rest keeps walking.
 	uint32_t wmask = __activemask();
 	uint32_t waited = 0;
+#if RT_BVH8
+	// The quantised step works with a reciprocal direction clamped to +-1e12 (+-inf for a zero component included): t = f * A + B
+	// must not meet inf - inf.  The clamp keeps the test conservative -- along such an axis the ray moves less than 1e-9 over
+	// the whole scene, so "origin inside the padded slab" decides, and (plane - o) * 1e12 still lies far beyond every distance
+	// the other axes allow unless the origin sits exactly on the padded plane, one quantum outside the real box.
+	const uint32_t one = 0x3F800000u + (S.n_items >> 31);   // = 0x3F800000: see qplane
+	const F3 qid = f3(copysignf(fminf(fabsf(idir.x), 1e12f), idir.x), copysignf(fminf(fabsf(idir.y), 1e12f), idir.y), copysignf(fminf(fabsf(idir.z), 1e12f), idir.z));
+#endif
 #if RT_SLAB_FMA
 	const F3 oi = f3(-(ray.o.x * idir.x), -(ray.o.y * idir.y), -(ray.o.z * idir.z));
 	float eps = fmaxf(fmaxf(fabsf(oi.x), fabsf(oi.y)), fabsf(oi.z)) * 2.4e-7f;
@@ -306,6 +345,58 @@ __device__ __forceinline__ void traverse(const SceneDev &S, const RayD &ray, con
 		}
 		if (__popc(mN) >= __popc(mL))
 		{
+#if RT_BVH8
+			if (atNode && TRIS)
+			{
+				const uint4 *nd = (const uint4 *)&S.nodes8[cur];
+				const uint4 hd = __ldg(nd), q0 = __ldg(nd + 1), q1 = __ldg(nd + 2), q2 = __ldg(nd + 3);
+				const uint4 la = __ldg(nd + 4), lb = __ldg(nd + 5);
+				if (STATS) ++st.nodes;
+				// A = 2^15 * s * id, B = (p - o) * id - A per axis
+				const float Ax = __uint_as_float(((hd.w & 0xFFu) + 15u) << 23) * qid.x;
+				const float Ay = __uint_as_float((((hd.w >> 8) & 0xFFu) + 15u) << 23) * qid.y;
+				const float Az = __uint_as_float((((hd.w >> 16) & 0xFFu) + 15u) << 23) * qid.z;
+				const float Bx = (__uint_as_float(hd.x) - ray.o.x) * qid.x - Ax;
+				const float By = (__uint_as_float(hd.y) - ray.o.y) * qid.y - Ay;
+				const float Bz = (__uint_as_float(hd.z) - ray.o.z) * qid.z - Az;
+				// near / far plane words by the ray's direction signs (qlo* = q0.xy, q0.zw, q1.xy; qhi* = q1.zw, q2.xy, q2.zw)
+				const uint32_t nx0 = sx ? q1.z : q0.x, nx1 = sx ? q1.w : q0.y, fx0 = sx ? q0.x : q1.z, fx1 = sx ? q0.y : q1.w;
+				const uint32_t ny0 = sy ? q2.x : q0.z, ny1 = sy ? q2.y : q0.w, fy0 = sy ? q0.z : q2.x, fy1 = sy ? q0.w : q2.y;
+				const uint32_t nz0 = sz ? q2.z : q1.x, nz1 = sz ? q2.w : q1.y, fz0 = sz ? q1.x : q2.z, fz1 = sz ? q1.y : q2.w;
+				// nearest hit child is walked next, the other hit children go on the stack as they are found (no arrays: the
+				// running nearest lives in two registers and is swapped out to the stack by a nearer sibling)
+				int bl = RT_TRAV_DONE;
+				float bt = __int_as_float(0x7f800000);
+#define RT_CHILD8(k, NX, NY, NZ, FX, FY, FZ, LINK) \
+				{ \
+					const float t0 = fmaxf(fmaxf(qplane<(k) & 3>(NX, one, Ax, Bx), qplane<(k) & 3>(NY, one, Ay, By)), fmaxf(qplane<(k) & 3>(NZ, one, Az, Bz), 0.0f)); \
+					const float t1 = fminf(fminf(qplane<(k) & 3>(FX, one, Ax, Bx), qplane<(k) & 3>(FY, one, Ay, By)), fminf(qplane<(k) & 3>(FZ, one, Az, Bz), best.t)); \
+					const bool hit = t0 <= t1;   /* an unused child is an inverted box: near plane behind far plane on every axis */ \
+					const bool nearer = hit && t0 < bt; \
+					const int pl = nearer ? bl : (int)(LINK); \
+					const float pt = nearer ? bt : t0; \
+					bl = nearer ? (int)(LINK) : bl, bt = nearer ? t0 : bt; \
+					if (hit && pl != RT_TRAV_DONE) { slot_put(stack[sp], pl, pt); ++sp; } \
+				}
+				RT_CHILD8(0, nx0, ny0, nz0, fx0, fy0, fz0, la.x)
+				RT_CHILD8(1, nx0, ny0, nz0, fx0, fy0, fz0, la.y)
+				RT_CHILD8(2, nx0, ny0, nz0, fx0, fy0, fz0, la.z)
+				RT_CHILD8(3, nx0, ny0, nz0, fx0, fy0, fz0, la.w)
+				RT_CHILD8(4, nx1, ny1, nz1, fx1, fy1, fz1, lb.x)
+				RT_CHILD8(5, nx1, ny1, nz1, fx1, fy1, fz1, lb.y)
+				RT_CHILD8(6, nx1, ny1, nz1, fx1, fy1, fz1, lb.z)
+				RT_CHILD8(7, nx1, ny1, nz1, fx1, fy1, fz1, lb.w)
+#undef RT_CHILD8
+				cur = bl;
+				if (bl == RT_TRAV_DONE)
+					while (sp)
+					{
+						const typename StackSlot<ANY>::T e = stack[--sp];
+						if (ANY || slot_t(e) <= best.t) { cur = slot_link(e); break; }
+					}
+			}
+			else
+#endif
 			if (atNode)
 			{
 				const char *n = (const char *)&S.nodes4[cur];
@@ -314,6 +405,9 @@ __device__ __forceinline__ void traverse(const SceneDev &S, const RayD &ray, con
 				ldg8(n, lx, hx), ldg8(n + 32, ly, hy), ldg8(n + 64, lz, hz);
 				const float4 nx = sx ? hx : lx, ny = sy ? hy : ly, nz = sz ? hz : lz;
 				const float4 fx = sx ? lx : hx, fy = sy ? ly : hy, fz = sz ? lz : hz;
+#elif RT_NODE_FETCH == 2
+				float4 nx, ny, nz, fx, fy, fz;
+				ldg_near_far<0, 48>(n, sx, nx, fx), ldg_near_far<16, 64>(n, sy, ny, fy), ldg_near_far<32, 80>(n, sz, nz, fz);
 #else
 				const float4 nx = ldg4((const float4 *)(n + onx)), ny = ldg4((const float4 *)(n + ony)), nz = ldg4((const float4 *)(n + onz));
 				const float4 fx = ldg4((const float4 *)(n + ofx)), fy = ldg4((const float4 *)(n + ofy)), fz = ldg4((const float4 *)(n + ofz));

@@ -32,13 +32,22 @@ def counts(c):
     return (c.primary, c.shadow, c.reflect, c.refract)
 
 
-@pytest.mark.parametrize("sched", ["waves", "frame"])
+@pytest.mark.parametrize("sched", ["waves", "waves-defer", "waves-voted", "waves-bin", "frame"])
 @pytest.mark.parametrize("genprimary", ["0", "1"])
 @pytest.mark.parametrize("case", MESH_CASES, ids=lambda c: f"{c[0]}-{c[1]}x{c[2]}-l{c[3]}")
 def test_forced_scheduler_matches_reference_golden(gpu_present, monkeypatch, case, genprimary, sched):
     if sched == "frame" and genprimary == "0":
         pytest.skip("k_frame always makes its own primary rays")
     scene, w, h, level, n, parts = case
+    if sched.startswith("waves-"):
+        # the Model walk of the wave kernels: deferred triangle tests (rt_defer.cuh) or the voted walk, whichever is not the default
+        if genprimary == "0":
+            pytest.skip("one primary-ray mode is enough for the non-default walk")
+        if sched == "waves-bin":
+            monkeypatch.setenv("RT_B200_BIN", "4")      # coherence binning of the secondary rays (rtk_bin_rays)
+        else:
+            monkeypatch.setenv("RT_B200_TRAV", sched[6:])
+        sched = "waves"
     monkeypatch.setenv("RT_B200_SCHED", sched)
     monkeypatch.setenv("RT_B200_WAVE_GENPRIMARY", genprimary)
     sc = R.Scene(scene, w, h, n, parts)
@@ -55,12 +64,18 @@ def test_forced_scheduler_matches_reference_golden(gpu_present, monkeypatch, cas
     assert R.fnv1a64(img) == g["hash"] and R.fnv1a64(ids) == g["ids_hash"]      # == the unmodified reference
 
 
-@pytest.mark.parametrize("genprimary", ["0", "1"])
+@pytest.mark.parametrize("genprimary", ["0", "1", "1-defer", "1-voted", "1-bin"])
 @pytest.mark.parametrize("case", [("t_mesh", 448, 320, 4, 0, 0), ("c3", 448, 320, 5, 96, 6), ("c4", 448, 320, 6, 96, 6)],
                          ids=lambda c: f"{c[0]}-l{c[3]}")
 def test_wave_scheduler_batches_with_distinct_cameras(gpu_present, monkeypatch, case, genprimary):
     # what bench.py times: rt_render_batch_async under the wave kernels over a Model BVH, one camera per frame
     scene, w, h, level, n, parts = case
+    if "-" in genprimary:
+        genprimary, walk = genprimary.split("-")
+        if walk == "bin":
+            monkeypatch.setenv("RT_B200_BIN", "5")
+        else:
+            monkeypatch.setenv("RT_B200_TRAV", walk)
     monkeypatch.setenv("RT_B200_SCHED", "waves")
     monkeypatch.setenv("RT_B200_WAVE_GENPRIMARY", genprimary)
     sc = R.Scene(scene, w, h, n, parts)
