@@ -86,7 +86,17 @@ def ncu_traffic(name, world, B):
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         e = t.get(f"{name}:n{world}:b{B}")
-        return (e["bytes_per_launch"], e["source"]) if e else (None, None)
+        if not e:
+            return (None, None)
+        # a capture of other kernel sources is not quoted
+        import hashlib
+        h = hashlib.sha256()
+        d = os.path.join(ROOT, "raytrace_b200", "csrc")
+        for f in ("rt_device.cuh", "rt_intersect.cuh", "rt_traverse.cuh", "rt_defer.cuh", "rt_kernels.cu", "rt_kernels.h"):   # tools/ncu_traffic.py DEVICE_SOURCES
+            h.update(open(os.path.join(d, f), "rb").read())
+        if h.hexdigest()[:16] != e.get("kernel_source_hash"):
+            return (None, "profiles/ncu_traffic.json holds a capture of older kernel sources: not quoted")
+        return (e["bytes_per_launch"], e["source"])
     except Exception:
         return (None, None)
 
@@ -527,7 +537,7 @@ def main():
             frame, landing = None, None
             if p2p:
                 # rank 0 renders straight into the landing buffer the other ranks push their rows to
-                landing = FrameLanding(hnd, w, h, rank, world)
+                landing = FrameLanding(hnd, w, h, rank, world, backpressure=True)
                 if rank == 0:
                     outs[f] = landing.device_ptr()[0]
             if not (p2p and rank == 0):
@@ -550,7 +560,7 @@ def main():
         ck(R.rt.rt_render_batch_async(p["ctx"], C.byref(params), nb, cam_ptr(first), p["outs"]), "rt_render_batch_async")
         for f in range(nb):
             if p["landings"][f] is not None:
-                p["landings"][f].push(p["ctx"], p["consumer"], frame=f)   # NVLink P2P: this rank's row tiles -> their place in rank 0's frame (copy engines) + signal
+                p["landings"][f].push(p["ctx"], p["consumer"], frame=f, release=True)   # (back-pressure: a push waits until rank 0's consumer has released the frame pushed into this buffer before) NVLink P2P: this rank's row tiles -> their place in rank 0's frame (copy engines) + signal
             elif p["gather"] is not None:
                 with torch.cuda.stream(p["stream"]):
                     p["assembled"][f] = p["gather"].gather(p["frames"][f])   # NCCL: this rank's row tiles -> rank 0, de-interleaved there

@@ -298,7 +298,13 @@ int rt_set_output(rt_ctx *ctx, void *device_ptr, size_t bytes);
  * rt_landing_wait makes a stream of the destination (the consumer's, or the pipeline's own) wait until
  * ranks 0..world-1 delivered `seq`.
  * The landing buffer of the destination rank may also be its own rt_set_output target (then its own
- * rows need no copy).  A buffer may be pushed to again only when its consumer is done with it. */
+ * rows need no copy).
+ * Back-pressure: the consumer hands a buffer back with rt_landing_release(seq) -- a stream write of `seq` into the
+ * buffer's ack word, behind whatever it read on that stream -- and a rank's NEXT push into the same buffer first makes
+ * its stream wait (cuStreamWaitValue64 on the peer-mapped ack word, no SM work, no host round trip) until the frame it
+ * pushed before has been released.  The owner arms the protocol with rt_landing_release(seq = 0) before it ships the
+ * handle; a buffer that was never armed is not waited for (its ack word reads "all released"): the caller's own pacing
+ * then decides, as before. */
 typedef struct rt_landing rt_landing;
 int rt_landing_create(rt_ctx *ctx, int width, int height, rt_landing **out, void *ipc_handle64);
 int rt_landing_open(rt_ctx *ctx, int width, int height, const void *ipc_handle64, rt_landing **out);
@@ -307,6 +313,7 @@ int rt_landing_ptr(rt_landing *landing, void **device_ptr, size_t *bytes);
 int rt_push_rows(rt_ctx *ctx, rt_landing *landing, uint64_t seq);
 int rt_push_batch_rows(rt_ctx *ctx, uint32_t frame, rt_landing *landing, uint64_t seq);   /* the same for frame `frame` of the last batch */
 int rt_landing_wait(rt_ctx *ctx, rt_landing *landing, uint64_t seq, uint32_t world, void *consumer_stream /* NULL: ctx's stream */);
+int rt_landing_release(rt_ctx *ctx, rt_landing *landing, uint64_t seq, void *consumer_stream /* NULL: ctx's stream */);
 
 /* page-locked host memory for RayTracer::output: rt_read_output into it runs at full PCIe speed */
 int rt_host_alloc(void **ptr, size_t bytes);

@@ -127,6 +127,7 @@ RT_SYMBOLS = {
     "rt_landing_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "rt_push_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "rt_landing_wait": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]),
+    "rt_landing_release": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "rt_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "rt_host_free": (C.c_int, [C.c_void_p]),
     "rt_intersect_object": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(Ray), C.POINTER(Hit), C.c_float, C.POINTER(Hit), C.c_uint32]),

@@ -1305,8 +1305,11 @@ struct rt_landing
 	int width = 0, height = 0, device = 0;
 	bool owner = false;
 	uint64_t *hSeq = nullptr;     // pinned ring: source of the flag copies when stream mem-ops are unavailable
+	uint64_t pushedSeq = 0;       // the frame this handle pushed last: the next push waits until it has been released
+	bool acks = false;            // owner: rt_landing_release has been called at least once (the ack word is live)
 };
 #define RT_LANDING_FLAGS 64
+#define RT_LANDING_ACK (RT_LANDING_FLAGS - 1)   // last flag word: highest frame the consumer has released (~0 until the first release)
 #define RT_LANDING_RING 4096
 
 typedef int (*StreamValue64Fn)(cudaStream_t, unsigned long long, unsigned long long, unsigned int);
@@ -1333,6 +1336,7 @@ extern "C" int rt_landing_create(rt_ctx *c, int width, int height, rt_landing **
 	if (cudaMalloc(&L->base, total) != cudaSuccess) { delete L; return fail(RT_E_CUDA, "rt_landing_create: cudaMalloc of %zu bytes failed", total); }
 	CU(cudaMemset(L->base, 127, L->frameBytes));
 	CU(cudaMemset(L->base + ((L->frameBytes + 255) & ~(size_t)255), 0, RT_LANDING_FLAGS * sizeof(uint64_t)));
+	CU(cudaMemset(L->base + ((L->frameBytes + 255) & ~(size_t)255) + RT_LANDING_ACK * sizeof(uint64_t), 0xFF, sizeof(uint64_t)));   // "everything released"
 	CU(cudaHostAlloc(&L->hSeq, RT_LANDING_RING * sizeof(uint64_t), cudaHostAllocDefault));
 	CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)ipc_handle64, L->base));
 	{ std::lock_guard<std::mutex> lock(g_landingMutex); g_landingBases.push_back(L->base); }
@@ -1403,11 +1407,24 @@ static int push_rows(rt_ctx *c, rt_landing *L, uint64_t seq, uint32_t frame)
 	CU(cudaSetDevice(c->device));
 	const rt_render_params &p = c->lastParams;
 	const uint32_t world = p.world > 1 ? p.world : 1, rank = p.world > 1 ? p.rank : 0;
-	if (rank >= RT_LANDING_FLAGS) return fail(RT_E_LIMIT, "rt_push_rows: rank %u (landing buffers hold %d flags)", rank, RT_LANDING_FLAGS);
+	if (rank >= RT_LANDING_ACK) return fail(RT_E_LIMIT, "rt_push_rows: rank %u (landing buffers hold %d flags)", rank, RT_LANDING_ACK);
 	cudaStream_t st = c->stream;
 	const uint8_t *src = c->lastBatch > 1 || frame ? c->lastOuts[frame] : c->fb;
 	if (src != L->base)
 	{
+		// back-pressure: the frame this rank pushed into the buffer before must have been released by its consumer
+		// (unsigned compare against the ack word; ~0 = the consumer does not release, nothing to wait for)
+		if (L->pushedSeq)
+		{
+			static const StreamValue64Fn waitAck = driver_fn("cuStreamWaitValue64");
+			uint64_t *ack = landing_flags(L) + RT_LANDING_ACK;
+			if (!waitAck || waitAck(st, (unsigned long long)(uintptr_t)ack, L->pushedSeq, 0u /* GEQ */) != 0)
+			{
+				CU(cudaStreamSynchronize(st));
+				uint64_t v = 0;
+				do CU(cudaMemcpy(&v, ack, sizeof v, cudaMemcpyDeviceToHost)); while (v < L->pushedSeq);
+			}
+		}
 		int rc = copy_shard_rows(c, src, L->base, (size_t)c->outW * 3, cudaMemcpyDeviceToDevice, st, nullptr);
 		if (rc != RT_OK) return rc;
 	}
@@ -1421,6 +1438,33 @@ static int push_rows(rt_ctx *c, rt_landing *L, uint64_t seq, uint32_t frame)
 		*src = seq;
 		CU(cudaMemcpyAsync(flag, src, sizeof(uint64_t), cudaMemcpyDefault, st));
 	}
+	L->pushedSeq = seq;
+	return RT_OK;
+}
+
+extern "C" int rt_landing_release(rt_ctx *c, rt_landing *L, uint64_t seq, void *consumer_stream)
+{
+	if (!c || !L) return fail(RT_E_INVALID, "rt_landing_release: NULL argument");
+	if (!L->owner) return fail(RT_E_INVALID, "rt_landing_release: only the rank that created the landing buffer releases it");
+	CU(cudaSetDevice(c->device));
+	cudaStream_t st = consumer_stream ? (cudaStream_t)consumer_stream : c->stream;
+	static const StreamValue64Fn writeValue = driver_fn("cuStreamWriteValue64");
+	uint64_t *ack = landing_flags(L) + RT_LANDING_ACK;
+	if (seq == 0)
+	{
+		// arming (before the handle is shipped): from now on a push of frame k waits for the release of frame k - 1
+		const uint64_t zero = 0;
+		CU(cudaMemcpy(ack, &zero, sizeof zero, cudaMemcpyHostToDevice));
+		L->acks = true;
+		return RT_OK;
+	}
+	if (!writeValue || writeValue(st, (unsigned long long)(uintptr_t)ack, seq, 0u) != 0)
+	{
+		uint64_t *src = &L->hSeq[(seq + RT_LANDING_RING / 2) % RT_LANDING_RING];
+		*src = seq;
+		CU(cudaMemcpyAsync(ack, src, sizeof(uint64_t), cudaMemcpyDefault, st));
+	}
+	L->acks = true;
 	return RT_OK;
 }
 

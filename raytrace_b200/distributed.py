@@ -71,7 +71,7 @@ class FrameLanding:
     copies its row tiles straight to their final place in it (one strided peer copy on the copy
     engines) and signals with a sequence number.  torch.distributed only ships the 64-byte handle."""
 
-    def __init__(self, ctx, width: int, height: int, rank: int, world: int, dst: int = 0):
+    def __init__(self, ctx, width: int, height: int, rank: int, world: int, dst: int = 0, backpressure: bool = False):
         from ._capi import rt
 
         def _check(rc, what):
@@ -83,6 +83,8 @@ class FrameLanding:
         handle = (C.c_ubyte * 64)()
         if rank == dst:
             _check(rt.rt_landing_create(ctx, width, height, C.byref(self._h), handle), "rt_landing_create")
+            if backpressure:   # armed before anyone can push: push k then waits for the release of frame k - 1
+                _check(rt.rt_landing_release(ctx, self._h, 0, None), "rt_landing_release")
         box = [bytes(handle) if rank == dst else None]
         if world > 1:
             dist.broadcast_object_list(box, src=dst)
@@ -95,10 +97,12 @@ class FrameLanding:
         self._check(self._rt.rt_landing_ptr(self._h, C.byref(p), C.byref(n)), "rt_landing_ptr")
         return p.value, n.value
 
-    def push(self, ctx, consumer_stream=None, frame=None):
+    def push(self, ctx, consumer_stream=None, frame=None, release=False):
         """Enqueue, behind the frame just rendered on `ctx`, the copy of this rank's rows + the signal;
         on the destination rank also the wait for every rank's signal -- on `consumer_stream` (a
-        torch.cuda.Stream: whoever reads the assembled frame) or, if None, on the pipeline's own stream."""
+        torch.cuda.Stream: whoever reads the assembled frame) or, if None, on the pipeline's own stream.
+        release=True: the destination hands the buffer back right behind that wait (a consumer that reads the frame
+        calls release() itself after its read); the other ranks' next push into this buffer waits for it."""
         self.seq += 1
         if frame is None:
             self._check(self._rt.rt_push_rows(ctx, self._h, self.seq), "rt_push_rows")
@@ -107,6 +111,14 @@ class FrameLanding:
         if self.rank == self.dst and not os.environ.get("RT_DIAG_NO_LANDING_WAIT"):
             cs = C.c_void_p(consumer_stream.cuda_stream) if consumer_stream is not None else None
             self._check(self._rt.rt_landing_wait(ctx, self._h, self.seq, self.world, cs), "rt_landing_wait")
+            if release:
+                self._check(self._rt.rt_landing_release(ctx, self._h, self.seq, cs), "rt_landing_release")
+
+    def release(self, ctx, consumer_stream=None):
+        """Destination rank: the consumer is done with the frame of the last push (stream-ordered on `consumer_stream`)."""
+        if self.rank == self.dst:
+            cs = C.c_void_p(consumer_stream.cuda_stream) if consumer_stream is not None else None
+            self._check(self._rt.rt_landing_release(ctx, self._h, self.seq, cs), "rt_landing_release")
 
     def close(self):
         if self._h:

@@ -21,3 +21,6 @@ def test_p2p_landing_and_nccl_gather_assemble_the_full_frame(gpu_present):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "first p2p landing == full frame: True" in r.stdout and "first p2p landing == full frame: False" not in r.stdout
     assert "p2p landing == full frame: True" in r.stdout and "nccl gather == full frame: True" in r.stdout
+    # back-pressure: four frames pushed back to back into ONE landing buffer whose consumer is slow -- no snapshot shows a later frame
+    assert r.stdout.count("back-pressure: snapshot of frame") == 4 and "back-pressure: snapshot of frame" in r.stdout
+    assert "full frame of camera 0: True" in r.stdout and "full frame of camera 3: True" in r.stdout and "of camera 1: False" not in r.stdout and "of camera 2: False" not in r.stdout

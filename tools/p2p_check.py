@@ -105,7 +105,68 @@ if rank == 0:
         print(f"batched p2p landing {f} == full frame:", same, flush=True)
         ok = ok and same
 dist.barrier()
+# (a3) back-pressure: ONE landing buffer, four frames with four cameras pushed back to back, a consumer on rank 0 that is
+# slow (it sleeps on its stream before it snapshots the assembled frame, then releases the buffer).  A peer's push of
+# frame k + 1 must wait for the release of frame k, or the snapshot of frame k shows rows of frame k + 1.
+class _DevView:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+bp, bst = pipes[0][0], pipes[0][1]
+bl = FrameLanding(bp, w, h, rank, world, backpressure=True)
+bframe = None
+if rank == 0:
+    bptr, bn = bl.device_ptr()
+    bview = torch.as_tensor(_DevView(bptr, bn), device=dev)
+else:
+    bframe = torch.full((h, w, 3), 127, dtype=torch.uint8, device=dev)
+cons = torch.cuda.Stream(dev)
+moves = ((0.3, -0.2, 0.5), (-0.6, 0.3, 0.2), (0.4, 0.4, -0.3), (-0.2, -0.5, 0.6))
+cams = (R.Camera * 4)()
+for k, mv in enumerate(moves):
+    sc.camera_move(*mv)
+    cams[k] = sc.flatten().contents.camera
+fulls, snaps, ev = [], [], None
+if rank == 0:
+    fp = R.RenderParams(R.MY_MODEL_RAYTRACE, level, 0, 1, 0, 64)
+    for k in range(4):
+        ck(R.rt.rt_render_batch_async(owner, C.byref(fp), 1, C.cast(C.byref(cams, k * C.sizeof(R.Camera)), C.POINTER(R.Camera)), None), "render full k")
+        ck(R.rt.rt_wait(owner, None), "rt_wait")
+        g = np.empty((h, w, 3), dtype=np.uint8)
+        ck(R.rt.rt_read_batch_output(owner, 0, g.ctypes.data_as(C.c_void_p), w * 3, 0), "rt_read_batch_output")
+        fulls.append(g)
+dist.barrier()
+one = (C.c_void_p * 1)()
+one[0] = bl.device_ptr()[0] if rank == 0 else bframe.data_ptr()
+for k in range(4):
+    if rank == 0 and ev is not None:
+        bst.wait_event(ev)            # rank 0's own rows of frame k + 1 also wait for the snapshot of frame k
+    ck(R.rt.rt_render_batch_async(bp, C.byref(params), 1, C.cast(C.byref(cams, k * C.sizeof(R.Camera)), C.POINTER(R.Camera)), one), "rt_render_batch_async")
+    bl.push(bp, cons, frame=0)
+    if rank == 0:
+        with torch.cuda.stream(cons):
+            torch.cuda._sleep(60_000_000)          # ~30 ms: long enough for the peers to have enqueued every later frame
+            snaps.append(bview.clone())
+        bl.release(bp, cons)
+        ev = torch.cuda.Event()
+        ev.record(cons)
+ck(R.rt.rt_wait(bp, None), "rt_wait")
+bst.synchronize(), cons.synchronize()
+torch.cuda.synchronize(dev)
+dist.barrier()
+if rank == 0:
+    for k in range(4):
+        same = bool(np.array_equal(snaps[k].cpu().numpy().reshape(h, w, 3), fulls[k]))
+        print(f"back-pressure: snapshot of frame {k} == full frame of camera {k}:", same, flush=True)
+        ok = ok and same
+dist.barrier()
+bl.close()
 # (b) NCCL gather of the same shards
+for _ in range(4):
+    pass
+sc = R.Scene("c3", w, h, 96, 6, tmpdir=f"/tmp/rt_p2p_{rank}")       # back to the configuration's own camera
+ck(R.rt.rt_upload_scene(owner, sc.flatten()), "rt_upload_scene")
 p, st, landing, frame = pipes[0]
 if rank == 0:
     frame = torch.full((h, w, 3), 127, dtype=torch.uint8, device=dev)
