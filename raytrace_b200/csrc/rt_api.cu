@@ -1309,7 +1309,8 @@ struct rt_landing
 	bool acks = false;            // owner: rt_landing_release has been called at least once (the ack word is live)
 };
 #define RT_LANDING_FLAGS 64
-#define RT_LANDING_ACK (RT_LANDING_FLAGS - 1)   // last flag word: highest frame the consumer has released (~0 until the first release)
+#define RT_LANDING_ACK (RT_LANDING_FLAGS - 1)   // last flag word: highest frame the consumer has released (RT_LANDING_UNARMED until armed)
+#define RT_LANDING_UNARMED 0x3FFFFFFFFFFFFFFFull
 #define RT_LANDING_RING 4096
 
 typedef int (*StreamValue64Fn)(cudaStream_t, unsigned long long, unsigned long long, unsigned int);
@@ -1336,7 +1337,12 @@ extern "C" int rt_landing_create(rt_ctx *c, int width, int height, rt_landing **
 	if (cudaMalloc(&L->base, total) != cudaSuccess) { delete L; return fail(RT_E_CUDA, "rt_landing_create: cudaMalloc of %zu bytes failed", total); }
 	CU(cudaMemset(L->base, 127, L->frameBytes));
 	CU(cudaMemset(L->base + ((L->frameBytes + 255) & ~(size_t)255), 0, RT_LANDING_FLAGS * sizeof(uint64_t)));
-	CU(cudaMemset(L->base + ((L->frameBytes + 255) & ~(size_t)255) + RT_LANDING_ACK * sizeof(uint64_t), 0xFF, sizeof(uint64_t)));   // "everything released"
+	{
+		// "everything released" for a buffer that is never armed.  cuStreamWaitValue64(GEQ) compares CYCLICALLY,
+		// (int64_t)(*addr - value) >= 0, so the marker is the largest value that is >= every sequence number in that sense
+		const uint64_t unarmed = RT_LANDING_UNARMED;
+		CU(cudaMemcpy(L->base + ((L->frameBytes + 255) & ~(size_t)255) + RT_LANDING_ACK * sizeof(uint64_t), &unarmed, sizeof unarmed, cudaMemcpyHostToDevice));
+	}
 	CU(cudaHostAlloc(&L->hSeq, RT_LANDING_RING * sizeof(uint64_t), cudaHostAllocDefault));
 	CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)ipc_handle64, L->base));
 	{ std::lock_guard<std::mutex> lock(g_landingMutex); g_landingBases.push_back(L->base); }
@@ -1413,7 +1419,7 @@ static int push_rows(rt_ctx *c, rt_landing *L, uint64_t seq, uint32_t frame)
 	if (src != L->base)
 	{
 		// back-pressure: the frame this rank pushed into the buffer before must have been released by its consumer
-		// (unsigned compare against the ack word; ~0 = the consumer does not release, nothing to wait for)
+		// (cyclic >= against the ack word; RT_LANDING_UNARMED = the consumer does not release, nothing to wait for)
 		if (L->pushedSeq)
 		{
 			static const StreamValue64Fn waitAck = driver_fn("cuStreamWaitValue64");
@@ -1422,7 +1428,7 @@ static int push_rows(rt_ctx *c, rt_landing *L, uint64_t seq, uint32_t frame)
 			{
 				CU(cudaStreamSynchronize(st));
 				uint64_t v = 0;
-				do CU(cudaMemcpy(&v, ack, sizeof v, cudaMemcpyDeviceToHost)); while (v < L->pushedSeq);
+				do CU(cudaMemcpy(&v, ack, sizeof v, cudaMemcpyDeviceToHost)); while ((int64_t)(v - L->pushedSeq) < 0);
 			}
 		}
 		int rc = copy_shard_rows(c, src, L->base, (size_t)c->outW * 3, cudaMemcpyDeviceToDevice, st, nullptr);

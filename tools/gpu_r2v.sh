@@ -1,11 +1,11 @@
 # N ranks (gpurun --gpus N): landing-buffer check incl. back-pressure, then the driver's bench command
 N=${1:-2}
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 tools/p2p_check.py > gpurun_out/r2v_p2p_n$N.txt 2>&1
+timeout 180 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 tools/p2p_check.py > gpurun_out/r2v_p2p_n$N.txt 2>&1
 grep -E "==|Error|error|Traceback|line " gpurun_out/r2v_p2p_n$N.txt | head -30
 for cfg in c3 c5; do
   steps=20; [ $cfg = c5 ] && steps=2
-  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --config $cfg --steps $steps --warmup 5 --no-cpu-baseline > gpurun_out/r2v_bench_${cfg}_n$N.json 2> gpurun_out/r2v_bench_${cfg}_n$N.err
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --config $cfg --steps $steps --warmup 5 --no-cpu-baseline > gpurun_out/r2v_bench_${cfg}_n$N.json 2> gpurun_out/r2v_bench_${cfg}_n$N.err
   python - <<PY
 import json
 try:
