@@ -72,6 +72,9 @@ def workload_config(name):
             "l2_policy": "per-step working set (ray/hit queues of ~8 M pixels per launch + BVH + triangles, > 2 GB touched per launch) exceeds the 126 MB L2; no flush needed"}
 
 
+BACKPRESSURE = os.environ.get("RT_BENCH_BACKPRESSURE", "1") != "0"   # landing buffers armed + released (diagnostic switch)
+
+
 def golden_fullsize(name):
     try:
         return json.load(open(os.path.join(ROOT, "tests", "golden", "fullsize.json"))).get(name)
@@ -537,7 +540,7 @@ def main():
             frame, landing = None, None
             if p2p:
                 # rank 0 renders straight into the landing buffer the other ranks push their rows to
-                landing = FrameLanding(hnd, w, h, rank, world, backpressure=True)
+                landing = FrameLanding(hnd, w, h, rank, world, backpressure=BACKPRESSURE)
                 if rank == 0:
                     outs[f] = landing.device_ptr()[0]
             if not (p2p and rank == 0):
@@ -546,7 +549,7 @@ def main():
             frames.append(frame), landings.append(landing)
         pipes.append({"ctx": hnd, "stream": st, "frames": frames, "landings": landings, "outs": outs, "assembled": [None] * B,
                       "consumer": torch.cuda.Stream(dev) if p2p and rank == 0 else None,   # where the assembled frames become visible
-                      "gather": FrameGather(w, h, rank, world, dev, tile_rows, serp) if world > 1 and not p2p else None})
+                      "gather": [FrameGather(w, h, rank, world, dev, tile_rows, serp) for _ in range(B)] if world > 1 and not p2p else None})   # one per frame of a launch: a FrameGather assembles into its own pre-allocated frame
 
     def cam_ptr(first):
         return C.cast(C.byref(cams, first * C.sizeof(R.Camera)), C.POINTER(R.Camera))
@@ -560,10 +563,10 @@ def main():
         ck(R.rt.rt_render_batch_async(p["ctx"], C.byref(params), nb, cam_ptr(first), p["outs"]), "rt_render_batch_async")
         for f in range(nb):
             if p["landings"][f] is not None:
-                p["landings"][f].push(p["ctx"], p["consumer"], frame=f, release=True)   # (back-pressure: a push waits until rank 0's consumer has released the frame pushed into this buffer before) NVLink P2P: this rank's row tiles -> their place in rank 0's frame (copy engines) + signal
+                p["landings"][f].push(p["ctx"], p["consumer"], frame=f, release=BACKPRESSURE)   # (back-pressure: a push waits until rank 0's consumer has released the frame pushed into this buffer before) NVLink P2P: this rank's row tiles -> their place in rank 0's frame (copy engines) + signal
             elif p["gather"] is not None:
                 with torch.cuda.stream(p["stream"]):
-                    p["assembled"][f] = p["gather"].gather(p["frames"][f])   # NCCL: this rank's row tiles -> rank 0, de-interleaved there
+                    p["assembled"][f] = p["gather"][f].gather(p["frames"][f])   # NCCL: this rank's row tiles -> rank 0, de-interleaved there
         return p, nb
 
     state = {"gj": 0}

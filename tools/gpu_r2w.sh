@@ -1,7 +1,7 @@
 # N ranks: the driver's bench command for c3 (and c5), no p2p_check
 N=${1:-8}
 mkdir -p gpurun_out
-for cfg in c3 c5; do
+for cfg in ${CFGS:-c3 c5}; do
   steps=20; [ $cfg = c5 ] && steps=2
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --config $cfg --steps $steps --warmup 5 --no-cpu-baseline > gpurun_out/r2w_bench_${cfg}_n$N.json 2> gpurun_out/r2w_bench_${cfg}_n$N.err
   python - <<PY
