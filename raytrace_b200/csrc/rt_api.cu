@@ -214,7 +214,7 @@ extern "C" int rt_create(int device, rt_ctx **out)
 	if (const char *v = getenv("RT_B200_LEAF_SIZE")) c->leafSize = (uint32_t)atoi(v);
 	if (const char *v = getenv("RT_B200_LEVEL_FACTOR")) c->levelFactor = (float)atof(v);
 	if (const char *v = getenv("RT_B200_SCHED")) c->schedMode = !strcmp(v, "frame") ? 1 : (!strcmp(v, "waves") ? 2 : 0);
-	if (const char *v = getenv("RT_B200_TRAV")) c->travWalk = !strcmp(v, "split") ? 2 : (!strcmp(v, "defer") ? 3 : 0);
+	if (const char *v = getenv("RT_B200_TRAV")) c->travWalk = !strcmp(v, "split") ? 2 : (!strcmp(v, "defer") ? 3 : (!strcmp(v, "steal") ? 4 : 0));
 	if (const char *v = getenv("RT_B200_BIN")) { int b = atoi(v); c->binMode = b < 0 ? 0 : (b > 6 ? 6 : b); }
 	c->waveGen = RT_WAVE_GENPRIMARY_DEFAULT;
 	if (const char *v = getenv("RT_B200_WAVE_GENPRIMARY")) c->waveGen = atoi(v);

@@ -219,9 +219,23 @@ __device__ __forceinline__ void traverse_deferred(const SceneDev &S, const RayD 
 	__syncwarp();
 }
 
-// trace_scene for a whole converged warp: lanes without a ray pass valid = false and only help with the test rounds.
+#include "rt_steal.cuh"
+
+// the Model walk of a whole converged warp, by the kind of per-warp workspace it is given
 template<bool ANY>
-__device__ __forceinline__ void trace_scene_defer(const SceneDev &S, const RayD &ray, bool valid, Best &best, bool &done, WarpDefer &W)
+__device__ __forceinline__ void traverse_warp(const SceneDev &S, const RayD &ray, const F3 &idir, bool enter, int root, float hr_distance, Best &best, bool &done, WarpDefer &W)
+{
+	traverse_deferred<ANY>(S, ray, idir, enter, root, hr_distance, best, done, W);
+}
+template<bool ANY>
+__device__ __forceinline__ void traverse_warp(const SceneDev &S, const RayD &ray, const F3 &idir, bool enter, int root, float hr_distance, Best &best, bool &done, WarpSteal &W)
+{
+	traverse_steal<ANY>(S, ray, idir, enter, root, hr_distance, best, done, W);
+}
+
+// trace_scene for a whole converged warp: lanes without a ray pass valid = false and only help (test rounds / stolen subtrees).
+template<bool ANY, class WS>
+__device__ __forceinline__ void trace_scene_warp(const SceneDev &S, const RayD &ray, bool valid, Best &best, bool &done, WS &W)
 {
 	const F3 idir = f3(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
 	TravStats st = { 0, 0, 0 };
@@ -242,7 +256,7 @@ __device__ __forceinline__ void trace_scene_defer(const SceneDev &S, const RayD 
 			if (__ballot_sync(0xffffffffu, enter) == 0u)
 				continue;
 			const Best before = best;
-			traverse_deferred<ANY>(S, ray, idir, enter, it.root, before.t, best, done, W);
+			traverse_warp<ANY>(S, ray, idir, enter, it.root, before.t, best, done, W);
 			if (!ANY && enter && best.t < 0.0f)
 			{
 				const uint32_t tb = __ldg(&M.tri_begin);

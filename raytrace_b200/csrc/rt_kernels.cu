@@ -287,14 +287,17 @@ __device__ __forceinline__ bool frame_cancelled(const WaveState *ws, const Frame
 
 // DEFER: Model BVHs are walked with deferred triangle tests (rt_defer.cuh); the counting launches (STATS) keep the voted walk,
 // whose node / triangle counts are the algorithmic ones (no speculative visits).
-template<bool STATS, int CTAS, bool DEFER>
+template<int WALK> struct WarpWork { typedef WarpDefer T; };
+template<> struct WarpWork<2> { typedef WarpSteal T; };
+
+template<bool STATS, int CTAS, int DEFER /* 0: voted walk, 1: deferred triangle tests, 2: work stealing inside the warp */>
 __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_wave(SceneDev S, const FrameParams *__restrict__ Fp, LevelBuf L, LevelBuf N, LevelBuf Lprev,
 	WaveState *ws, uint32_t level, uint32_t traceOn, uint32_t shadowOn, float zNear)
 {
 	const FrameParams &F = *Fp;
 	TravStats st = { 0, 0, 0 };
-	__shared__ WarpDefer wdefer[DEFER ? RT_BLOCK / 32 : 1];
-	WarpDefer *W = &wdefer[DEFER ? (threadIdx.x >> 5) : 0];
+	__shared__ typename WarpWork<DEFER>::T wdefer[DEFER ? RT_BLOCK / 32 : 1];
+	typename WarpWork<DEFER>::T *W = &wdefer[DEFER ? (threadIdx.x >> 5) : 0];
 
 	// ---- phase A: closest hit + surface attributes + children ------------------------------------
 	if (traceOn)
@@ -332,7 +335,7 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_wave(SceneDev S, const Frame
 			Best best = { 1e20f, RT_ID_NONE, ray.skip };
 			bool done = false;
 			if (DEFER)
-				trace_scene_defer<false>(S, ray, i < n, best, done, *W);   // the whole warp: idle lanes help with the triangle test rounds
+				trace_scene_warp<false>(S, ray, i < n, best, done, *W);   // the whole warp: idle lanes help with the triangle test rounds
 			if (i < n)
 			{
 				const uint32_t nodes0 = st.nodes;
@@ -461,7 +464,7 @@ __global__ void __launch_bounds__(RT_BLOCK, CTAS) k_wave(SceneDev S, const Frame
 			Best best = { dis, RT_ID_NONE, RT_ID_NONE };
 			bool done = false;
 			if (DEFER)
-				trace_scene_defer<true>(S, ray, w < n, best, done, *W);
+				trace_scene_warp<true>(S, ray, w < n, best, done, *W);
 			if (w < n)
 			{
 				const uint32_t nodes0 = st.nodes;
@@ -1715,14 +1718,16 @@ void rtk_wave(cudaStream_t st, const SceneDev &S, const FrameParams *F, const Le
 		else k_wave_split<false, RT_CTAS_PER_SM><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
 		return;
 	}
-	if (stats) k_wave<true, RT_CTAS_PER_SM, false><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
-	else if (walk == 3 && occ == 6) k_wave<false, 6, true><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
-	else if (walk == 3) k_wave<false, RT_CTAS_PER_SM, true><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
-	else if (occ == 4) k_wave<false, 4, false><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
-	else if (occ == 6) k_wave<false, 6, false><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
-	else if (occ == 10) k_wave<false, 10, false><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
-	else if (occ == 12) k_wave<false, 12, false><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
-	else k_wave<false, RT_CTAS_PER_SM, false><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+	if (stats) k_wave<true, RT_CTAS_PER_SM, 0><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+	else if (walk == 3 && occ == 6) k_wave<false, 6, 1><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+	else if (walk == 3) k_wave<false, RT_CTAS_PER_SM, 1><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+	else if (walk == 4 && occ == 6) k_wave<false, 6, 2><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+	else if (walk == 4) k_wave<false, RT_CTAS_PER_SM, 2><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+	else if (occ == 4) k_wave<false, 4, 0><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+	else if (occ == 6) k_wave<false, 6, 0><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+	else if (occ == 10) k_wave<false, 10, 0><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+	else if (occ == 12) k_wave<false, 12, 0><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
+	else k_wave<false, RT_CTAS_PER_SM, 0><<<g, RT_BLOCK, 0, st>>>(S, F, L, N, Lprev, ws, level, traceOn, shadowOn, zNear);
 }
 
 void rtk_frame(cudaStream_t st, const SceneDev &S, const FrameParams *F, const LevelSet &LS, WaveState *ws, uint32_t nPix, unsigned sms, bool stats, unsigned ctasPerSm)

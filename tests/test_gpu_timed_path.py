@@ -32,7 +32,7 @@ def counts(c):
     return (c.primary, c.shadow, c.reflect, c.refract)
 
 
-@pytest.mark.parametrize("sched", ["waves", "waves-defer", "waves-voted", "waves-bin", "frame"])
+@pytest.mark.parametrize("sched", ["waves", "waves-defer", "waves-steal", "waves-voted", "waves-bin", "frame"])
 @pytest.mark.parametrize("genprimary", ["0", "1"])
 @pytest.mark.parametrize("case", MESH_CASES, ids=lambda c: f"{c[0]}-{c[1]}x{c[2]}-l{c[3]}")
 def test_forced_scheduler_matches_reference_golden(gpu_present, monkeypatch, case, genprimary, sched):
@@ -64,7 +64,7 @@ def test_forced_scheduler_matches_reference_golden(gpu_present, monkeypatch, cas
     assert R.fnv1a64(img) == g["hash"] and R.fnv1a64(ids) == g["ids_hash"]      # == the unmodified reference
 
 
-@pytest.mark.parametrize("genprimary", ["0", "1", "1-defer", "1-voted", "1-bin"])
+@pytest.mark.parametrize("genprimary", ["0", "1", "1-defer", "1-steal", "1-voted", "1-bin"])
 @pytest.mark.parametrize("case", [("t_mesh", 448, 320, 4, 0, 0), ("c3", 448, 320, 5, 96, 6), ("c4", 448, 320, 6, 96, 6)],
                          ids=lambda c: f"{c[0]}-l{c[3]}")
 def test_wave_scheduler_batches_with_distinct_cameras(gpu_present, monkeypatch, case, genprimary):
