@@ -95,7 +95,7 @@ def ncu_traffic(name, world, B):
         import hashlib
         h = hashlib.sha256()
         d = os.path.join(ROOT, "raytrace_b200", "csrc")
-        for f in ("rt_device.cuh", "rt_intersect.cuh", "rt_traverse.cuh", "rt_defer.cuh", "rt_kernels.cu", "rt_kernels.h"):   # tools/ncu_traffic.py DEVICE_SOURCES
+        for f in ("rt_device.cuh", "rt_intersect.cuh", "rt_traverse.cuh", "rt_defer.cuh", "rt_steal.cuh", "rt_kernels.cu", "rt_kernels.h"):   # tools/ncu_traffic.py DEVICE_SOURCES
             h.update(open(os.path.join(d, f), "rb").read())
         if h.hexdigest()[:16] != e.get("kernel_source_hash"):
             return (None, "profiles/ncu_traffic.json holds a capture of older kernel sources: not quoted")

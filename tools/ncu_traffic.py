@@ -14,7 +14,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-DEVICE_SOURCES = ["rt_device.cuh", "rt_intersect.cuh", "rt_traverse.cuh", "rt_defer.cuh", "rt_kernels.cu", "rt_kernels.h"]   # what the traced kernels are compiled from
+DEVICE_SOURCES = ["rt_device.cuh", "rt_intersect.cuh", "rt_traverse.cuh", "rt_defer.cuh", "rt_steal.cuh", "rt_kernels.cu", "rt_kernels.h"]   # what the traced kernels are compiled from
 
 
 def kernel_source_hash():
