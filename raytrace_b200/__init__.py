@@ -47,7 +47,7 @@ class Scene:
             raise RtError(rth.rth_last_error().decode())
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and rth is not None:   # (module globals are already gone at interpreter exit)
             rth.rth_scene_free(self._h)
             self._h = None
 
@@ -129,7 +129,7 @@ class RayTracer:
         self.coalesce = False   # throughput mode: frames of this Scene's tracers that wait together are rendered in one launch (host/RayTracer.h)
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and rth is not None:
             rth.rth_tracer_free(self._h)
             self._h = None
 
@@ -219,7 +219,7 @@ class Context:
         self._h = h
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and rt is not None:
             rt.rt_destroy(self._h)
             self._h = None
 
