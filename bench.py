@@ -505,7 +505,7 @@ def main():
             raise RuntimeError(f"{what}: {R.rt.rt_last_error().decode()}")
 
     # ---- frame pipelines: one resident scene, M launches in flight, B frames per launch -----------------
-    # about 8 M pixels per launch and GPU (sweeps in profiles/r1i_batch_sweep_c3.txt: launches of that size run the
+    # about 16 M pixels per launch and GPU (sweeps in profiles/r1i_batch_sweep_c3.txt and r2ac_batch_sweep_c3.txt: launches of that size run the
     # per-level wave kernels with queues long enough that their tails do not matter, and two launches in flight
     # cover each other's level boundaries).  Scenes of analytic primitives only (c1, c2) trace 12-17 Grays/s: their
     # launches are bound by the ray-queue traffic, which stays closer to the L2 with one frame per launch; they keep
@@ -513,7 +513,8 @@ def main():
     big = w * h // world > 3_000_000
     pix_rank = (w // 64 * 64) * (h // 64 * 64) // world
     mesh = args.config in ("c3", "c4")
-    B = args.batch if args.batch > 0 else (1 if big or not mesh else max(1, min(64, S, round(8_000_000 / max(pix_rank, 1)))))
+    B = args.batch if args.batch > 0 else (1 if big or not mesh else max(1, min(64, S, round(16_000_000 / max(pix_rank, 1)))))
+    B_e2e = B if args.batch > 0 else (1 if big or not mesh else max(1, min(64, S, round(8_000_000 / max(pix_rank, 1)))))   # tracers of the RayTracer::start() leg: 4 x this
     M = args.pipelines if args.pipelines > 0 else (1 if big else 2 if B > 1 else 3)
     share = args.sm_share if args.sm_share >= 0 else (0 if M == 1 or B > 1 else 4)
     L = (S + B - 1) // B                         # launches per step
@@ -726,8 +727,8 @@ def main():
     e2e = None
     if not args.no_e2e:
         env_c = os.environ.get("RT_BENCH_COALESCE")
-        coalesce = B > 1 and (env_c != "0")
-        M_e2e = 1 if big else (min(64, int(env_c or "4") * B) if coalesce else 3 if world == 1 else 4 if world < 8 else 8)
+        coalesce = B_e2e > 1 and (env_c != "0")
+        M_e2e = 1 if big else (min(64, int(env_c or "4") * B_e2e) if coalesce else 3 if world == 1 else 4 if world < 8 else 8)
         share_e2e = 0 if M_e2e == 1 or coalesce else 4 if world == 1 else 2 if world < 8 else 1
         tracers = []
         for _ in range(M_e2e):
