@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <deque>
@@ -89,6 +90,7 @@ struct SceneResidency
 	}
 	bool workersUp = false, quit = false;
 	int coalescers = 0;       // tracers of this Scene in throughput mode (sizes the coalescing window)
+	std::atomic<int> launchesInFlight{0};   // batch launches between rt_render_batch_async and the end of rt_wait
 
 	static bool sameLaunch(const FrameRequest &a, const FrameRequest &b)
 	{
@@ -120,12 +122,19 @@ struct SceneResidency
 				const int div = wantDiv > 0 ? wantDiv : nWorkers + 1;
 				const size_t want = std::max<size_t>(1, std::min(kMaxBatch, (size_t)(coalescers + div - 1) / div));
 				wantLast = want, tFirst = nowS();
+				// While another worker's launch keeps the GPU busy there is no hurry: a worker that took what was there
+				// after one quiet window launched batches of one or two frames, every such launch pays the fixed tail of
+				// a launch, its tracers come back early, are restarted alone, ... -- a convoy of small batches that the
+				// bench fell into on every other run at two GPUs (2 063 against 8 120 Mrays/s).  The quiet-window rule only
+				// applies when the GPU would otherwise idle; the wait for a full batch is bounded (a caller may be blocked
+				// in wait() on a tracer whose request sits here).
+				const double tCollect = nowS();
 				while (!quit && pending.size() < want)
 				{
 					const size_t before = pending.size();
 					qCv.wait_for(lock, std::chrono::microseconds(250));
-					if (pending.size() == before)
-						break;   // nothing new within the window
+					if (pending.size() == before && (launchesInFlight.load() == 0 || nowS() - tCollect > 4e-3))
+						break;   // nothing new within the window and nothing rendering (or waited long enough)
 				}
 				if (pending.empty())
 					continue;   // the other worker took them
@@ -142,12 +151,15 @@ struct SceneResidency
 			double seconds = 0.0;
 			int rc;
 			tLaunch = nowS();
+			++launchesInFlight;
 			{
 				// the launch adopts the parent's scene tables: not while a start() is uploading into them
 				std::lock_guard<std::mutex> lock(mutex);
 				rc = rt_render_batch_async(c, &batch[0].rp, (uint32_t)batch.size(), cams.data(), nullptr);
 			}
 			if (rc == RT_OK) rc = rt_wait(c, &seconds);
+			--launchesInFlight;
+			qCv.notify_all();   // a worker that is collecting re-evaluates "is anything rendering"
 			tRendered = nowS();
 			// all copies enqueued back to back, one wait (the last call completes them all)
 			for (size_t f = 0; f < batch.size() && rc == RT_OK; ++f)
