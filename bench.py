@@ -728,7 +728,7 @@ def main():
     if not args.no_e2e:
         env_c = os.environ.get("RT_BENCH_COALESCE")
         coalesce = B_e2e > 1 and (env_c != "0")
-        M_e2e = 1 if big else (min(64, int(env_c or "4") * B_e2e) if coalesce else 3 if world == 1 else 4 if world < 8 else 8)
+        M_e2e = 1 if big else (min(64, int(env_c or "8") * B_e2e) if coalesce else 3 if world == 1 else 4 if world < 8 else 8)
         share_e2e = 0 if M_e2e == 1 or coalesce else 4 if world == 1 else 2 if world < 8 else 1
         tracers = []
         for _ in range(M_e2e):

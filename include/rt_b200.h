@@ -240,6 +240,10 @@ int rt_create_shared(rt_ctx *parent, rt_ctx **out);
 /* resident traversal CTAs per SM this pipeline may occupy (1..8, 0 = all): pipelines that run
  * concurrently split the 8 slots between them */
 int rt_set_sm_share(rt_ctx *ctx, int ctas_per_sm);
+/* (new) announce the largest rt_render_batch_async launch this pipeline will see: ray queues and library-owned framebuffers are
+ * then sized for n_frames frames by the next launch, so batches that grow (the coalesced RayTracer::start() calls: one frame,
+ * then three, then eight) do not free and re-allocate gigabytes at every new size.  0 = size by the launch (default). */
+int rt_reserve_batch(rt_ctx *ctx, uint32_t n_frames);
 
 /* replaces the per-start scene walk + Model::RTPrepare (RayTracer.cpp:621-625, Model.cpp:402-480):
  * copies the description to SoA device buffers and (re)builds the LBVHs when geometry changed */

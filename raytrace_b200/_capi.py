@@ -108,6 +108,7 @@ RT_SYMBOLS = {
     "rt_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rt_create_shared": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "rt_set_sm_share": (C.c_int, [C.c_void_p, C.c_int]),
+    "rt_reserve_batch": (C.c_int, [C.c_void_p, C.c_uint32]),
     "rt_upload_scene": (C.c_int, [C.c_void_p, C.POINTER(SceneDesc)]),
     "rt_render_async": (C.c_int, [C.c_void_p, C.POINTER(RenderParams)]),
     "rt_render_supersampled": (C.c_int, [C.c_void_p, C.POINTER(RenderParams), C.c_uint32, C.POINTER(Camera)]),

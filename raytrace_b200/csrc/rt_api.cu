@@ -146,6 +146,7 @@ struct rt_ctx
 	double uploadMs = 0, buildMs = 0, renderMs = 0;
 	uint64_t uploadBytes = 0, frameH2D = 0, frameD2H = 0;
 	float levelFactor = 2.0f;
+	uint32_t reserveFrames = 0;   // rt_reserve_batch: size the ray queues for launches of up to this many frames at once
 	uint32_t minCap[RT_MAX_LEVELS + 2] = {};   // per-level queue capacities learnt from overflowing frames (finish_frame regrows and re-renders)
 	uint32_t regrowTries = 0;
 	std::vector<rt_camera> lastCams;           // the last launch's arguments, kept for that re-render
@@ -724,6 +725,14 @@ extern "C" int rt_render_async(rt_ctx *c, const rt_render_params *p)
 	return render_frames(c, p, 1, nullptr, nullptr);
 }
 
+extern "C" int rt_reserve_batch(rt_ctx *c, uint32_t n_frames)
+{
+	if (!c) return fail(RT_E_INVALID, "rt_reserve_batch: ctx is NULL");
+	if (n_frames > RT_MAX_BATCH) return fail(RT_E_LIMIT, "rt_reserve_batch: %u frames (0..%d)", n_frames, RT_MAX_BATCH);
+	c->reserveFrames = n_frames;
+	return RT_OK;
+}
+
 extern "C" int rt_render_batch_async(rt_ctx *c, const rt_render_params *p, uint32_t n_frames, const rt_camera *cameras, void *const *device_outputs)
 {
 	if (n_frames < 1 || n_frames > RT_MAX_BATCH) return fail(RT_E_LIMIT, "rt_render_batch_async: %u frames (1..%d)", n_frames, RT_MAX_BATCH);
@@ -815,6 +824,12 @@ static int render_frames(rt_ctx *c, const rt_render_params *p, uint32_t nFrames,
 		// a batch: one framebuffer per frame, the caller's or the library's (rt_read_batch_output)
 		if (c->batchOut.size() < nFrames) c->batchOut.resize(nFrames);
 		if (c->batchFill.size() < nFrames) c->batchFill.resize(nFrames, nullptr);
+		if (!outs && c->reserveFrames > c->batchOut.size())
+		{
+			// the library-owned framebuffers of an announced batch size, all at once
+			c->batchOut.resize(std::min<uint32_t>(c->reserveFrames, RT_MAX_BATCH)), c->batchFill.resize(c->batchOut.size(), nullptr);
+			for (auto &b : c->batchOut) CU(b.reserve((size_t)W * H * 3));
+		}
 		const bool shardChanged = W != c->fillW || H != c->fillH || rank != c->fillRank || world != c->fillWorld || tileRows != c->fillTile || F.serpentine != c->fillSerp;
 		for (uint32_t f = 0; f < nFrames; ++f)
 		{
@@ -863,9 +878,12 @@ static int render_frames(rt_ctx *c, const rt_render_params *p, uint32_t nFrames,
 	}
 
 	const bool refr = c->anyRefract && p->type != RT_TYPE_REFLECT;
+	// (rt_reserve_batch: queues sized for the largest launch the caller announced, so that launches that grow from one frame
+	// to a full batch do not re-allocate -- cudaFree + cudaMalloc of GBs, tens of ms -- at every new size)
+	const uint32_t capPix = (uint32_t)std::min<uint64_t>((uint64_t)nPixFrame * std::max(nFrames, std::min<uint32_t>(c->reserveFrames, RT_MAX_BATCH)), 0x7FFFFFFFull);
 	for (uint32_t l = 0; l <= maxLevel; ++l)
 	{
-		uint32_t cap = l == 0 || !refr ? nPix : (uint32_t)std::min<double>((double)nPix * c->levelFactor, 4.0e9);
+		uint32_t cap = l == 0 || !refr ? capPix : (uint32_t)std::min<double>((double)capPix * c->levelFactor, 4.0e9);
 		if (l > 0 && c->minCap[l] > cap) cap = c->minCap[l];
 		int rc = ensure_level(c, l, cap ? cap : 1, F.n_lights);
 		if (rc != RT_OK) return rc;

@@ -90,6 +90,7 @@ struct SceneResidency
 	}
 	bool workersUp = false, quit = false;
 	int coalescers = 0;       // tracers of this Scene in throughput mode (sizes the coalescing window)
+	size_t reserved[8] = {};  // per worker: the batch size its pipeline's buffers were announced for (rt_reserve_batch)
 	std::atomic<int> launchesInFlight{0};   // batch launches between rt_render_batch_async and the end of rt_wait
 
 	static bool sameLaunch(const FrameRequest &a, const FrameRequest &b)
@@ -151,6 +152,12 @@ struct SceneResidency
 			double seconds = 0.0;
 			int rc;
 			tLaunch = nowS();
+			if (wantLast > reserved[w])
+			{
+				// the queues of this worker's pipeline are sized for its full share once, not re-allocated as the batches grow
+				rt_reserve_batch(c, (uint32_t)std::min(wantLast, kMaxBatch));
+				reserved[w] = wantLast;
+			}
 			++launchesInFlight;
 			{
 				// the launch adopts the parent's scene tables: not while a start() is uploading into them
